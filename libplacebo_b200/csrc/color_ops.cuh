@@ -1,0 +1,557 @@
+// Per-pixel colour op interpreter: executes the typed op list a pl_shader recorded, in order.
+// Each op is the fp32 restatement of one GLSL snippet of the reference:
+//   MATRIX           src/shaders/colorspace.c:308, :569
+//   LINEARIZE        pl_shader_linearize    colorspace.c:589-720
+//   DELINEARIZE      pl_shader_delinearize  colorspace.c:722-847
+//   DE/ENCODE_SPECIAL ICtCp & BT.2020-CL    colorspace.c:311-390, :474-524
+//   SIGMOID          colorspace.c:851-894
+//   COLOR_MAP        pl_shader_color_map_ex colorspace.c:1791-1995
+//   DITHER           pl_shader_dither       dithering.c:181-271
+// The switch is warp-uniform (the program is a kernel parameter), so there is no divergence.
+#pragma once
+
+#include "kernels_common.cuh"
+
+// One copy of the PQ/HLG literal table per translation unit (no relocatable device code);
+// every .cu that includes this header instantiates PLB_DEFINE_PQ_UPLOAD(name) and
+// plb_upload_pq_consts() (shaders.cpp) calls them all at pl_cuda_create time.
+static __constant__ plb_pq_consts c_pq;
+#define PLB_DEFINE_PQ_UPLOAD(name) \
+    extern "C" bool name(const plb_pq_consts *q) \
+    { return cudaMemcpyToSymbol(c_pq, q, sizeof(*q)) == cudaSuccess; }
+
+enum {
+    TRC_UNKNOWN = 0, TRC_BT_1886, TRC_SRGB, TRC_LINEAR, TRC_GAMMA18, TRC_GAMMA20,
+    TRC_GAMMA22, TRC_GAMMA24, TRC_GAMMA26, TRC_GAMMA28, TRC_PRO_PHOTO, TRC_ST428,
+    TRC_PQ, TRC_HLG, TRC_V_LOG, TRC_S_LOG1, TRC_S_LOG2, TRC_SCRGB,
+};
+
+PLB_DEV float plb_dot3_fma(float a0, float a1, float a2, float x, float y, float z)
+{
+    float r = a0 * x;
+    r = __fmaf_rn(a1, y, r);
+    r = __fmaf_rn(a2, z, r);
+    return r;
+}
+
+// M (row-major) * v
+PLB_DEV void plb_matv(const float *m, float &r, float &g, float &b)
+{
+    float x = r, y = g, z = b;
+    r = plb_dot3_fma(m[0], m[1], m[2], x, y, z);
+    g = plb_dot3_fma(m[3], m[4], m[5], x, y, z);
+    b = plb_dot3_fma(m[6], m[7], m[8], x, y, z);
+}
+
+// GLSL mat3(9 literals) * v, column-major literal order
+PLB_DEV void plb_mat3_lit(const float *m, float &r, float &g, float &b)
+{
+    float x = r, y = g, z = b;
+    r = plb_dot3_fma(m[0], m[3], m[6], x, y, z);
+    g = plb_dot3_fma(m[1], m[4], m[7], x, y, z);
+    b = plb_dot3_fma(m[2], m[5], m[8], x, y, z);
+}
+
+PLB_DEV float plb_pq_eotf(float x, bool clamp0)
+{
+    x = powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.inv_m2);
+    x = fmaxf(x - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x);
+    return powf(x, c_pq.inv_m1);
+}
+
+PLB_DEV float plb_pq_oetf(float x, bool clamp0)
+{
+    x = powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.m1);
+    x = (c_pq.c1 + c_pq.c2 * x) / (1.0f + c_pq.c3 * x);
+    return powf(x, c_pq.m2);
+}
+
+PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
+{
+    if (t.trc == TRC_LINEAR)
+        return;
+    if (t.trc != TRC_SCRGB) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = fmaxf(c[k], 0.0f);
+    }
+    bool post_scale = false;
+    switch (t.trc) {
+    case TRC_SRGB:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.04045f < c[k] ? powf((c[k] + 0.055f) / 1.055f, 2.4f)
+                                   : c[k] * (float) (1.0 / 12.92);
+        post_scale = true;
+        break;
+    case TRC_BT_1886:
+        for (int k = 0; k < 3; k++)
+            c[k] = t.a * powf(c[k] + t.b, 2.4f);
+        break;
+    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 1.8f); post_scale = true; break;
+    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.0f); post_scale = true; break;
+    case TRC_UNKNOWN:
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.2f); post_scale = true; break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.4f); post_scale = true; break;
+    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.6f); post_scale = true; break;
+    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.8f); post_scale = true; break;
+    case TRC_PRO_PHOTO:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.03125f < c[k] ? powf(c[k], 1.8f) : c[k] * (float) (1.0 / 16.0);
+        post_scale = true;
+        break;
+    case TRC_ST428:
+        for (int k = 0; k < 3; k++)
+            c[k] = (float) (52.37 / 48.0) * powf(c[k], 2.6f);
+        post_scale = true;
+        break;
+    case TRC_PQ:
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_eotf(c[k], false) * c_pq.from_pq;
+        break;
+    case TRC_HLG: {
+        // t.a = y, t.b = b
+        for (int k = 0; k < 3; k++) {
+            float x = (1 - t.b) * c[k] + t.b;
+            x = 0.5f < x ? expf((x - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b : 4.0f * x * x;
+            c[k] = x * (float) (1.0 / 12.0);
+        }
+        float y = plb_dot3_fma(t.luma[0], t.luma[1], t.luma[2], c[0], c[1], c[2]);
+        float g = t.csp_max * powf(fmaxf(y, 0.0f), t.a - 1);
+        for (int k = 0; k < 3; k++)
+            c[k] *= g;
+        break;
+    }
+    case TRC_SCRGB:
+        for (int k = 0; k < 3; k++)
+            c[k] *= t.a; // 80/203 literal
+        break;
+    default:
+        break; // camera log curves: recorded as unsupported by the host (shader fails)
+    }
+    if (post_scale && (t.csp_max != 1 || t.csp_min != 0)) {
+        for (int k = 0; k < 3; k++)
+            c[k] = (t.csp_max - t.csp_min) * c[k] + t.csp_min;
+    }
+}
+
+PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
+{
+    if (t.trc == TRC_LINEAR)
+        return;
+    if (t.black_scaled) {
+        const float ps_a = 1 / (t.csp_max - t.csp_min), ps_b = -t.csp_min / (t.csp_max - t.csp_min);
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = ps_a * c[k] + ps_b;
+    }
+    if (t.trc != TRC_SCRGB) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = fmaxf(c[k], 0.0f);
+    }
+    switch (t.trc) {
+    case TRC_SRGB:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.0031308f <= c[k] ? 1.055f * powf(c[k], (float) (1.0 / 2.4)) - 0.055f
+                                      : c[k] * 12.92f;
+        break;
+    case TRC_BT_1886: // t.a = 1/a, t.b = b
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = powf(t.a * c[k], (float) (1.0 / 2.4)) - t.b;
+        break;
+    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 1.8)); break;
+    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.0)); break;
+    case TRC_UNKNOWN:
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.2)); break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.4)); break;
+    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.6)); break;
+    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.8)); break;
+    case TRC_ST428:
+        for (int k = 0; k < 3; k++)
+            c[k] = powf(c[k] * (float) (48.0 / 52.37), (float) (1.0 / 2.6));
+        break;
+    case TRC_PRO_PHOTO:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.001953f <= c[k] ? powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
+        break;
+    case TRC_PQ:
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_oetf(c[k] * c_pq.inv_from_pq, false);
+        break;
+    case TRC_HLG: {
+        for (int k = 0; k < 3; k++)
+            c[k] *= 1.0f / t.csp_max;
+        float y = plb_dot3_fma(t.luma[0], t.luma[1], t.luma[2], c[0], c[1], c[2]);
+        float g = 12.0f * powf(fmaxf(1e-6f, y), (1 - t.a) / t.a);
+        for (int k = 0; k < 3; k++) {
+            float x = c[k] * g;
+            x = 1.0f < x ? c_pq.hlg_a * logf(x - c_pq.hlg_b) + c_pq.hlg_c : 0.5f * sqrtf(x);
+            c[k] = (1 / (1 - t.b)) * x + (-t.b / (1 - t.b));
+        }
+        break;
+    }
+    case TRC_SCRGB:
+        for (int k = 0; k < 3; k++)
+            c[k] *= t.a; // 203/80 literal
+        break;
+    default:
+        break;
+    }
+}
+
+PLB_DEV void plb_decode_special(int sys, float c[3])
+{
+    const float lms2rgb[9] = { 3.43661f, -0.79133f, -0.0259499f,
+                               -2.50645f, 1.98360f, -0.0989137f,
+                               0.06984f, -0.192271f, 1.12486f };
+    switch (sys) {
+    case PL_COLOR_SYSTEM_BT_2020_C: {
+        float g = c[1];
+        c[2] = c[2] * (c[2] <= 0.0f ? 1.9404f : 1.5816f) + g;
+        c[0] = c[0] * (c[0] <= 0.0f ? 1.7184f : 0.9936f) + g;
+        float lin[3];
+        for (int k = 0; k < 3; k++)
+            lin[k] = 0.08145f <= c[k]
+                   ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                   : c[k] * (float) (1.0 / 4.5);
+        float gg = (lin[1] - 0.2627f * lin[0] - 0.0593f * lin[2]) * (float) (1.0 / 0.6780);
+        c[1] = 0.0181f <= gg ? 1.0993f * powf(gg, 0.45f) - 0.0993f : gg * 4.5f;
+        break;
+    }
+    case PL_COLOR_SYSTEM_BT_2100_PQ:
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_eotf(c[k], true);
+        plb_mat3_lit(lms2rgb, c[0], c[1], c[2]);
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_oetf(c[k], true);
+        break;
+    case PL_COLOR_SYSTEM_BT_2100_HLG:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.5f < c[k] ? expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
+                               : 4.0f * c[k] * c[k];
+        plb_mat3_lit(lms2rgb, c[0], c[1], c[2]);
+        for (int k = 0; k < 3; k++)
+            c[k] = 1.0f < c[k] ? c_pq.hlg_a * logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
+                               : 0.5f * sqrtf(c[k]);
+        break;
+    }
+}
+
+PLB_DEV void plb_encode_special(int sys, float c[3])
+{
+    const float rgb2lms[9] = { 0.412109f, 0.166748f, 0.024170f,
+                               0.523925f, 0.720459f, 0.075440f,
+                               0.063965f, 0.112793f, 0.900394f };
+    switch (sys) {
+    case PL_COLOR_SYSTEM_BT_2020_C: {
+        float lin[3];
+        for (int k = 0; k < 3; k++)
+            lin[k] = 0.08145f <= c[k]
+                   ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                   : c[k] * (float) (1.0 / 4.5);
+        float g = plb_dot3_fma(0.2627f, 0.6780f, 0.0593f, lin[0], lin[1], lin[2]);
+        g = 0.0181f <= g ? 1.0993f * powf(g, 0.45f) - 0.0993f : g * 4.5f;
+        c[1] = g;
+        c[2] = c[2] - g;
+        c[0] = c[0] - g;
+        c[2] *= c[2] <= 0.0f ? (float) (1.0 / 1.9404) : (float) (1.0 / 1.5816);
+        c[0] *= c[0] <= 0.0f ? (float) (1.0 / 1.7184) : (float) (1.0 / 0.9936);
+        break;
+    }
+    case PL_COLOR_SYSTEM_BT_2100_PQ:
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_eotf(c[k], true);
+        plb_mat3_lit(rgb2lms, c[0], c[1], c[2]);
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_oetf(c[k], false);
+        break;
+    case PL_COLOR_SYSTEM_BT_2100_HLG:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.5f < c[k] ? expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
+                               : 4.0f * c[k] * c[k];
+        plb_mat3_lit(rgb2lms, c[0], c[1], c[2]);
+        for (int k = 0; k < 3; k++)
+            c[k] = 1.0f < c[k] ? c_pq.hlg_a * logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
+                               : 0.5f * sqrtf(c[k]);
+        break;
+    }
+}
+
+// trilinear fetch from the rgba16 gamut 3DLUT; addressing = lut.c:285-295 per axis
+PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], float out[3])
+{
+    const int n[3] = { p.lut_I, p.lut_C, p.lut_h };
+    int b[3];
+    float f[3];
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float base = 0.5f / n[a], end = 1.0f - 0.5f / n[a];
+        const float scale = end - base;
+        float u = scale * idx[a] + base;
+        float t = u * (float) n[a] - 0.5f;
+        float fl = floorf(t);
+        // guard the int conversion against NaN/huge values
+        b[a] = (int) fminf(fmaxf(fl, -2.0f), (float) n[a]);
+        f[a] = t - fl;
+    }
+    float c[2][2][2][3];
+    #pragma unroll
+    for (int dz = 0; dz < 2; dz++) {
+        #pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            #pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                int i = plb_clampi(b[0] + dx, 0, n[0] - 1);
+                int cc = plb_clampi(b[1] + dy, 0, n[1] - 1);
+                int h = plb_clampi(b[2] + dz, 0, n[2] - 1);
+                const ushort4 t = __ldg((const ushort4 *) p.gamut_lut + ((size_t) h * n[1] + cc) * n[0] + i);
+                c[dz][dy][dx][0] = t.x / 65535.0f;
+                c[dz][dy][dx][1] = t.y / 65535.0f;
+                c[dz][dy][dx][2] = t.z / 65535.0f;
+            }
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float x00 = plb_mix(c[0][0][0][k], c[0][0][1][k], f[0]);
+        float x01 = plb_mix(c[0][1][0][k], c[0][1][1][k], f[0]);
+        float x10 = plb_mix(c[1][0][0][k], c[1][0][1][k], f[0]);
+        float x11 = plb_mix(c[1][1][0][k], c[1][1][1][k], f[0]);
+        float y0 = plb_mix(x00, x01, f[1]), y1 = plb_mix(x10, x11, f[1]);
+        out[k] = plb_mix(y0, y1, f[2]);
+    }
+}
+
+PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
+{
+    const float lms2ipt[9] = { 0.4000f, 0.4000f, 0.2000f, 4.4550f, -4.8510f, 0.3960f,
+                               0.8056f, 0.3572f, -1.1628f };
+    const float ipt2lms[9] = { 1.0f, 0.0975689f, 0.205226f, 1.0f, -0.1138760f, 0.133217f,
+                               1.0f, 0.0326151f, -0.676887f };
+    float lms[3] = { px[0], px[1], px[2] };
+    plb_matv(p.rgb2lms, lms[0], lms[1], lms[2]);
+    float ipt[3];
+    #pragma unroll
+    for (int k = 0; k < 3; k++)
+        ipt[k] = plb_pq_oetf(c_pq.to_pq * lms[k], true);
+    plb_matv(lms2ipt, ipt[0], ipt[1], ipt[2]);
+    const float i_orig = ipt[0];
+
+    if (p.need_tone) {
+        float x = ipt[0];
+        if (p.tone_kind == 1) {
+            x = plb_clamp(x, p.in_min, p.in_max);
+        } else if (p.tone_kind == 2) {
+            x = p.lin_a * x + p.lin_b;
+            x = plb_clamp(x, 0.0f, 1.0f);
+            x = (p.out_max - p.out_min) * x + p.out_min;
+        } else {
+            x = plb_lut1d(p.tone_lut, p.tone_lut_size, p.tone_a * x + p.tone_b);
+        }
+        ipt[0] = x;
+        float h0 = ((i_orig - 6.0f) * i_orig + 9.0f) * i_orig;
+        float h1 = ((ipt[0] - 6.0f) * ipt[0] + 9.0f) * ipt[0];
+        float s = fminf(i_orig / ipt[0], h1 / h0);
+        ipt[1] *= s;
+        ipt[2] *= s;
+    }
+
+    if (p.need_gamut) {
+        float idx[3];
+        idx[0] = p.g_a * ipt[0] + p.g_b;
+        idx[1] = 2.0f * sqrtf(__fmaf_rn(ipt[1], ipt[1], ipt[2] * ipt[2]));
+        idx[2] = c_pq.inv_2pi * atan2f(ipt[2], ipt[1]) + 0.5f;
+        plb_gamut_sample(p, idx, ipt);
+        ipt[1] -= (float) (32768.0 / 65535.0);
+        ipt[2] -= (float) (32768.0 / 65535.0);
+    }
+
+    plb_matv(ipt2lms, ipt[0], ipt[1], ipt[2]);
+    #pragma unroll
+    for (int k = 0; k < 3; k++)
+        lms[k] = plb_pq_eotf(ipt[k], true) * c_pq.from_pq;
+    plb_matv(p.lms2rgb, lms[0], lms[1], lms[2]);
+    px[0] = lms[0]; px[1] = lms[1]; px[2] = lms[2];
+}
+
+PLB_DEV void plb_dither(const plb_op_dither &p, int x, int y, float c[4])
+{
+    int size = 0;
+    if (p.method == PL_DITHER_BLUE_NOISE || p.method == PL_DITHER_ORDERED_LUT)
+        size = p.lut_size;
+    else if (p.method == PL_DITHER_ORDERED_FIXED)
+        size = 16;
+    const float scale = (float) ((1ull << p.new_depth) - 1);
+    float bias = 0.0f, px = 0.0f, py = 0.0f;
+    if (size) {
+        const float inv_size = 1.0f / (float) size;
+        px = ((float) x + 0.5f) * inv_size;
+        py = ((float) y + 0.5f) * inv_size;
+        px -= floorf(px);
+        py -= floorf(py);
+        if (p.temporal) {
+            float nx = __fmaf_rn(p.rot[2], py, p.rot[0] * px) + 1.0f;
+            float ny = __fmaf_rn(p.rot[3], py, p.rot[1] * px) + 1.0f;
+            px = nx - floorf(nx);
+            py = ny - floorf(ny);
+        }
+    }
+    switch (p.method) {
+    case PL_DITHER_WHITE_NOISE: {
+        uint3 st = make_uint3((uint32_t) x, (uint32_t) y, p.temporal ? p.frame_index : 0);
+        bias = plb_prng(st).x;
+        break;
+    }
+    case PL_DITHER_ORDERED_FIXED: {
+        uint32_t xx = (uint32_t) (px * 16.0f) % 16u, yy = (uint32_t) (py * 16.0f) % 16u;
+        xx = xx ^ yy;
+        xx = (xx | xx << 2) & 0x33333333u; yy = (yy | yy << 2) & 0x33333333u;
+        xx = (xx | xx << 1) & 0x55555555u; yy = (yy | yy << 1) & 0x55555555u;
+        uint32_t b = xx + (yy << 1);
+        b = (b * 0x0802u & 0x22110u) | (b * 0x8020u & 0x88440u);
+        b = 0x10101u * b;
+        b = (b >> 16) & 0xFFu;
+        bias = (float) b * (1.0f / 256.0f);
+        break;
+    }
+    default: {
+        int ix = (int) (px * (float) size), iy = (int) (py * (float) size);
+        bias = __ldg(p.lut + iy * size + ix);
+        break;
+    }
+    }
+
+    if (p.gamma != 1.0f && p.new_depth <= 4) {
+        for (int k = 0; k < 4; k++) {
+            float col = c[k];
+            float col_lin = powf(col, p.gamma);
+            float low, high, offset;
+            if (p.new_depth == 1) {
+                low = 0.0f; high = 1.0f; offset = col_lin;
+            } else {
+                low = floorf(col * scale) / scale;
+                high = ceilf(col * scale) / scale;
+                float low_lin = powf(low, p.gamma), high_lin = powf(high, p.gamma);
+                float range = high_lin - low_lin;
+                offset = (col_lin - low_lin) / fmaxf(range, 1e-6f);
+            }
+            c[k] = offset > bias ? high : low;
+        }
+    } else {
+        const float inv_scale = 1.0f / scale;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float v = scale * c[k] + bias;
+            c[k] = floorf(v) * inv_scale;
+        }
+    }
+}
+
+PLB_DEV float plb_round_fbo(float v, int kind, int bits)
+{
+    if (kind == 0)
+        return __half2float(__float2half_rn(v));
+    if (kind == 1) {
+        const float maxv = (float) ((1u << bits) - 1);
+        return rintf(plb_clamp(v, 0.0f, 1.0f) * maxv) / maxv;
+    }
+    return v;
+}
+
+// PLB_OP_PEAK is handled by the kernel that owns the block-wide reduction; here we only
+// compute the per-pixel 14-bit PQ luma (colorspace.c:1279-1288, exact float constants)
+PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
+{
+    float c[3] = { c_in[0], c_in[1], c_in[2] };
+    plb_linearize(p.lin, c);
+    float luma = plb_dot3_fma(p.lin.luma[0], p.lin.luma[1], p.lin.luma[2], c[0], c[1], c[2]);
+    const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
+                PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
+    luma *= 203.0f / 10000.0f;
+    luma = powf(plb_clamp(luma, 0.0f, 1.0f), PQ_M1);
+    luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
+    luma = powf(luma, PQ_M2);
+    if (p.cutoff != 0.0f) {
+        float t = plb_clamp((luma - 0.0f) / (p.cutoff - 0.0f), 0.0f, 1.0f);
+        luma *= t * t * (3.0f - 2.0f * t);
+    }
+    return (uint32_t) (16383.0f * luma);
+}
+
+// Runs all ops except PEAK (returned through peak_op for the caller to reduce).
+// Deliberately NOT inlined: one copy per translation unit keeps every sampling kernel small
+// (the call costs nothing next to the transcendental chains inside).
+static __device__ __noinline__ void plb_run_color_ops(const plb_color_prog &prog, int x, int y, float c[4],
+                               const plb_op_peak **peak_op, uint32_t *y_pq)
+{
+    for (int i = 0; i < prog.n; i++) {
+        const plb_color_op &op = prog.ops[i];
+        switch (op.kind) {
+        case PLB_OP_SCALE:
+            c[0] *= op.u.scale.s; c[1] *= op.u.scale.s; c[2] *= op.u.scale.s;
+            if (op.u.scale.with_alpha)
+                c[3] *= op.u.scale.s;
+            break;
+        case PLB_OP_MATRIX: {
+            plb_matv(op.u.matrix.m, c[0], c[1], c[2]);
+            if (op.u.matrix.has_c) {
+                c[0] += op.u.matrix.c[0]; c[1] += op.u.matrix.c[1]; c[2] += op.u.matrix.c[2];
+            }
+            break;
+        }
+        case PLB_OP_LINEARIZE:   plb_linearize(op.u.trc, c); break;
+        case PLB_OP_DELINEARIZE: plb_delinearize(op.u.trc, c); break;
+        case PLB_OP_DECODE_SPECIAL: plb_decode_special(op.u.special.sys, c); break;
+        case PLB_OP_ENCODE_SPECIAL: plb_encode_special(op.u.special.sys, c); break;
+        case PLB_OP_SIGMOID:
+            for (int k = 0; k < 3; k++) {
+                float v = plb_clamp(c[k], 0.0f, 1.0f);
+                c[k] = op.u.sigmoid.center - (1.0f / op.u.sigmoid.slope) *
+                       logf(1.0f / (v * op.u.sigmoid.scale + op.u.sigmoid.offset) - 1.0f);
+            }
+            break;
+        case PLB_OP_UNSIGMOID:
+            for (int k = 0; k < 3; k++) {
+                float v = plb_clamp(c[k], 0.0f, 1.0f);
+                c[k] = (1.0f / op.u.sigmoid.scale) /
+                       (1.0f + expf(op.u.sigmoid.slope * (op.u.sigmoid.center - v))) -
+                       op.u.sigmoid.offset / op.u.sigmoid.scale;
+            }
+            break;
+        case PLB_OP_COLOR_MAP: plb_color_map(op.u.cmap, c); break;
+        case PLB_OP_DITHER:    plb_dither(op.u.dither, x, y, c); break;
+        case PLB_OP_ROUND_FBO:
+            #pragma unroll
+            for (int k = 0; k < 4; k++)
+                c[k] = plb_round_fbo(c[k], op.u.round_fbo.kind, op.u.round_fbo.bits);
+            break;
+        case PLB_OP_ALPHA:
+            // pl_shader_set_alpha, colorspace.c (independent <-> premultiplied)
+            if (op.u.alpha.to == PL_ALPHA_NONE && op.u.alpha.from == PL_ALPHA_UNKNOWN) {
+                c[3] = 1.0f;
+            } else if (op.u.alpha.from == PL_ALPHA_INDEPENDENT && op.u.alpha.to == PL_ALPHA_PREMULTIPLIED) {
+                c[0] *= c[3]; c[1] *= c[3]; c[2] *= c[3];
+            } else if (op.u.alpha.from == PL_ALPHA_PREMULTIPLIED && op.u.alpha.to != PL_ALPHA_PREMULTIPLIED) {
+                if (c[3] > 1e-6f) { // colorspace.c:34-38
+                    c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3];
+                }
+                if (op.u.alpha.to == PL_ALPHA_NONE)
+                    c[3] = 1.0f;
+            }
+            break;
+        case PLB_OP_GAMMA:
+            for (int k = 0; k < 3; k++)
+                c[k] = powf(fmaxf(c[k], 0.0f), op.u.gamma.g);
+            break;
+        case PLB_OP_PEAK:
+            *peak_op = &op.u.peak;
+            *y_pq = plb_peak_ypq(op.u.peak, c);
+            break;
+        default:
+            break;
+        }
+    }
+}

@@ -1,0 +1,185 @@
+// pl_dispatch on the CUDA backend: lowers a recorded pl_shader to kernel launches.
+// Replaces src/dispatch.c (pl_dispatch_finish :1199-1368, translate_compute_shader :1079-1144,
+// pl_dispatch_reset_frame :1613-1622): no GLSL generation, no pass cache — the "pass" is one
+// of the hand-written kernels in k_*.cu parameterised by the shader's op list.
+#include "shader_priv.h"
+
+pl_dispatch pl_dispatch_create(pl_log log, pl_gpu gpu)
+{
+    if (!gpu) {
+        plb_msg(log, PL_LOG_ERR, "pl_dispatch_create: no gpu");
+        return NULL;
+    }
+    struct pl_dispatch_t *dp = calloc(1, sizeof(*dp));
+    dp->log = log;
+    dp->gpu = gpu;
+    return dp;
+}
+
+void pl_dispatch_destroy(pl_dispatch *pdp)
+{
+    if (!pdp || !*pdp)
+        return;
+    free(*pdp);
+    *pdp = NULL;
+}
+
+void pl_dispatch_reset_frame(pl_dispatch dp) { dp->current_index++; }
+void pl_dispatch_set_frame_index(pl_dispatch dp, uint8_t index) { dp->current_index = index; }
+
+pl_shader pl_dispatch_begin(pl_dispatch dp)
+{
+    pl_shader sh = pl_shader_alloc(dp->log, pl_shader_params(
+        .gpu = dp->gpu,
+        .index = dp->current_index,
+    ));
+    sh->dp = dp;
+    return sh;
+}
+
+void pl_dispatch_abort(pl_dispatch dp, pl_shader *psh)
+{
+    (void) dp;
+    pl_shader_free(psh);
+}
+
+static bool prog_has_peak(const struct plb_color_prog *prog)
+{
+    for (int i = 0; i < prog->n; i++) {
+        if (prog->ops[i].kind == PLB_OP_PEAK)
+            return true;
+    }
+    return false;
+}
+
+// Run the shader over `rc` of `target` (target == NULL: statistics-only dispatch of w x h)
+bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc, int w, int h,
+                      pl_timer timer)
+{
+    pl_gpu gpu = dp->gpu;
+    if (sh->failed) {
+        PLB_ERR(dp->log, "Trying to dispatch a failed shader.");
+        return false;
+    }
+    if (sh->src == PLB_SRC_NONE) {
+        PLB_ERR(dp->log, "Trying to dispatch a shader without a source stage.");
+        return false;
+    }
+    struct plb_pixel_launch *px = &sh->px;
+    if (target) {
+        if (!target->params.renderable && !target->params.storable) {
+            PLB_ERR(dp->log, "pl_dispatch_finish: target texture is neither renderable nor "
+                    "storable");
+            return false;
+        }
+        if (!rc.x0 && !rc.x1) rc.x1 = target->params.w;
+        if (!rc.y0 && !rc.y1) rc.y1 = target->params.h;
+        if (rc.x1 < rc.x0 || rc.y1 < rc.y0) {
+            PLB_ERR(dp->log, "pl_dispatch_finish: flipped target rects are not supported on "
+                    "the CUDA backend");
+            return false;
+        }
+        if (rc.x0 < 0 || rc.y0 < 0 || rc.x1 > target->params.w || rc.y1 > target->params.h) {
+            PLB_ERR(dp->log, "pl_dispatch_finish: rect out of target bounds");
+            return false;
+        }
+        w = rc.x1 - rc.x0;
+        h = rc.y1 - rc.y0;
+        px->dst = plb_tex_priv(target)->d;
+    } else {
+        memset(&px->dst, 0, sizeof(px->dst));
+        rc = (pl_rect2d) { 0, 0, w, h };
+    }
+    if ((sh->out_w && sh->out_w != w) || (sh->out_h && sh->out_h != h)) {
+        PLB_ERR(dp->log, "Trying to dispatch a shader with incompatible size %dx%d to a "
+                "region of size %dx%d!", sh->out_w, sh->out_h, w, h);
+        return false;
+    }
+    px->dst_rect = rc;
+    px->out_w = w;
+    px->out_h = h;
+    px->frame_index = sh->params.index;
+    // work-group geometry as the reference's merged compute shader would have it:
+    // rigid 32x32 from the polar sampler, else the flexible 16x16 of pl_shader_detect_peak
+    px->wg_w = sh->is_compute ? sh->wg_w : 16;
+    px->wg_h = sh->is_compute ? sh->wg_h : 16;
+    if (prog_has_peak(&px->prog) && (32 % px->wg_w || 32 % px->wg_h)) {
+        // our tiles hold whole work groups of 8/16/32; anything else falls back to 16x16,
+        // which only changes the statistics within the reference's own tolerance
+        px->wg_w = px->wg_h = 16;
+    }
+
+    plb_timer_begin(gpu, timer);
+    bool ok = false;
+    switch (sh->src) {
+    case PLB_SRC_PLANES:
+        ok = plb_launch_pixel(gpu, px);
+        break;
+    case PLB_SRC_POLAR:
+        sh->polar.tail = *px;
+        ok = plb_launch_polar(gpu, &sh->polar);
+        break;
+    case PLB_SRC_ORTHO:
+        sh->ortho.tail = *px;
+        ok = plb_launch_ortho(gpu, &sh->ortho);
+        break;
+    case PLB_SRC_ERRDIFF:
+        ok = plb_launch_errdiff(gpu, &sh->errdiff);
+        break;
+    default:
+        break;
+    }
+    plb_timer_end(gpu, timer);
+    return ok;
+}
+
+bool pl_dispatch_finish(pl_dispatch dp, const struct pl_dispatch_params *params)
+{
+    pl_shader sh = params && params->shader ? *params->shader : NULL;
+    bool ok = false;
+    if (!sh) {
+        PLB_ERR(dp->log, "pl_dispatch_finish: no shader");
+        return false;
+    }
+    if (!params->target) {
+        PLB_ERR(dp->log, "pl_dispatch_finish: no target texture");
+        goto done;
+    }
+    if (params->blend_params) {
+        PLB_ERR(dp->log, "pl_dispatch_finish: blending is outside the CUDA hot path");
+        goto done;
+    }
+    if (sh->src == PLB_SRC_ERRDIFF) {
+        PLB_ERR(dp->log, "Trying to dispatch a compute-only shader with pl_dispatch_finish; "
+                "use pl_dispatch_compute");
+        goto done;
+    }
+    ok = plb_dispatch_run(dp, sh, params->target, params->rect, 0, 0, params->timer);
+done:
+    // the dispatch consumes the shader either way (dispatch.h:84-90)
+    pl_shader_free(params->shader);
+    return ok;
+}
+
+bool pl_dispatch_compute(pl_dispatch dp, const struct pl_dispatch_compute_params *params)
+{
+    pl_shader sh = params && params->shader ? *params->shader : NULL;
+    bool ok = false;
+    if (!sh) {
+        PLB_ERR(dp->log, "pl_dispatch_compute: no shader");
+        return false;
+    }
+    if (sh->src == PLB_SRC_ERRDIFF) {
+        // the error diffusion shader carries its own textures (dithering.c:326-406)
+        ok = plb_dispatch_run(dp, sh, NULL, (pl_rect2d) {0}, sh->errdiff.w, sh->errdiff.h,
+                              params->timer);
+    } else if (params->width > 0 && params->height > 0) {
+        // output-less compute pass (e.g. a stand-alone peak detection run)
+        ok = plb_dispatch_run(dp, sh, NULL, (pl_rect2d) {0}, params->width, params->height,
+                              params->timer);
+    } else {
+        PLB_ERR(dp->log, "pl_dispatch_compute: width/height required on the CUDA backend");
+    }
+    pl_shader_free(params->shader);
+    return ok;
+}

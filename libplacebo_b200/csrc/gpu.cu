@@ -1,0 +1,785 @@
+// pl_cuda: the CUDA sibling of the reference's pl_gpu backends (src/vulkan/gpu.c, src/dummy.c).
+// Textures are pitched linear allocations in HBM (kernels address them directly and do their
+// own format conversion/filtering in fp32, so no CUarray / texture objects), buffers are
+// device allocations with an optional pinned host mirror, timers are cudaEvent pairs, and
+// every operation is ordered on one stream so that callers may reuse frames as soon as a call
+// returns (reference contract: renderer.h:725-727).
+//
+// Validation mirrors the wrappers of src/gpu.c (pl_tex_create :383-470, pl_tex_upload/
+// download :704-860): bad parameters -> log + false/NULL, never abort.
+#include "internal.h"
+
+#include <cuda_runtime.h>
+#include <new>
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------
+// log.h
+// ---------------------------------------------------------------------------------------
+
+struct plb_log {
+    struct pl_log_t pub;
+};
+
+pl_log pl_log_create_365(int api_ver, const struct pl_log_params *params)
+{
+    (void) api_ver;
+    struct plb_log *log = (struct plb_log *) calloc(1, sizeof(*log));
+    if (params)
+        log->pub.params = *params;
+    return &log->pub;
+}
+
+void pl_log_destroy(pl_log *plog)
+{
+    if (!plog || !*plog)
+        return;
+    free((void *) *plog);
+    *plog = NULL;
+}
+
+void pl_log_simple(void *stream, enum pl_log_level level, const char *msg)
+{
+    static const char *prefix[] = { "", "fatal", "error", "warn", "info", "debug", "trace" };
+    FILE *h = stream ? (FILE *) stream : (level <= PL_LOG_WARN ? stderr : stdout);
+    fprintf(h, "%5s: %s\n", prefix[level], msg);
+}
+
+void plb_msg(pl_log log, enum pl_log_level lev, const char *fmt, ...)
+{
+    if (!log || !log->params.log_cb || lev > log->params.log_level)
+        return;
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    log->params.log_cb(log->params.log_priv, lev, buf);
+}
+
+// ---------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------
+
+bool plb_cuda_check(pl_gpu gpu, int err, const char *what)
+{
+    if (err == cudaSuccess)
+        return true;
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    PLB_ERR(gpu->log, "CUDA error in %s: %s", what, cudaGetErrorString((cudaError_t) err));
+    // sticky errors mean the context is gone (pl_gpu_is_failed, gpu.h:1398)
+    if (err != cudaErrorInvalidValue && err != cudaErrorMemoryAllocation &&
+        err != cudaErrorInvalidConfiguration)
+        p->failed = true;
+    cudaGetLastError();
+    return false;
+}
+
+#define CK(gpu, call) plb_cuda_check(gpu, (int) (call), #call)
+#define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
+
+void *plb_gpu_staging(pl_gpu gpu, size_t size)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (p->staging_size >= size)
+        return p->staging;
+    if (p->staging) {
+        cudaStreamSynchronize(STREAM(gpu));
+        cudaFreeHost(p->staging);
+        p->staging = NULL;
+        p->staging_size = 0;
+    }
+    if (!CK(gpu, cudaMallocHost(&p->staging, size)))
+        return NULL;
+    p->staging_size = size;
+    return p->staging;
+}
+
+void *plb_dev_alloc(pl_gpu gpu, size_t size)
+{
+    void *ptr = NULL;
+    if (!CK(gpu, cudaMalloc(&ptr, size)))
+        return NULL;
+    return ptr;
+}
+
+void plb_dev_free(pl_gpu gpu, void *ptr)
+{
+    if (!ptr)
+        return;
+    // work that still reads the allocation is ordered before the free on the same stream
+    CK(gpu, cudaFreeAsync(ptr, STREAM(gpu)));
+}
+
+bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
+{
+    // LUT-sized payloads: go through the pinned staging area so that the source may be
+    // freed/modified by the caller right after we return
+    void *st = plb_gpu_staging(gpu, size);
+    if (!st)
+        return false;
+    // the staging area may still be in flight from a previous upload
+    if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
+        return false;
+    memcpy(st, src, size);
+    return CK(gpu, cudaMemcpyAsync(dst, st, size, cudaMemcpyHostToDevice, STREAM(gpu)));
+}
+
+bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size)
+{
+    void *st = plb_gpu_staging(gpu, size);
+    if (!st)
+        return false;
+    if (!CK(gpu, cudaMemcpyAsync(st, src, size, cudaMemcpyDeviceToHost, STREAM(gpu))))
+        return false;
+    if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
+        return false;
+    memcpy(dst, st, size);
+    return true;
+}
+
+bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size)
+{
+    return CK(gpu, cudaMemsetAsync(dst, val, size, STREAM(gpu)));
+}
+
+// ---------------------------------------------------------------------------------------
+// formats — names as in src/vulkan/formats.c:96-120 / src/dummy.c
+// ---------------------------------------------------------------------------------------
+
+struct fmt_def {
+    const char *name;
+    enum pl_fmt_type type;
+    int comps, depth, bytes;
+    int kind;
+};
+
+static const struct fmt_def fmt_defs[] = {
+    {"r8",       PL_FMT_UNORM, 1,  8, 1, PLB_FK_UNORM8},
+    {"rg8",      PL_FMT_UNORM, 2,  8, 1, PLB_FK_UNORM8},
+    {"rgba8",    PL_FMT_UNORM, 4,  8, 1, PLB_FK_UNORM8},
+    {"r16",      PL_FMT_UNORM, 1, 16, 2, PLB_FK_UNORM16},
+    {"rg16",     PL_FMT_UNORM, 2, 16, 2, PLB_FK_UNORM16},
+    {"rgba16",   PL_FMT_UNORM, 4, 16, 2, PLB_FK_UNORM16},
+    {"r16hf",    PL_FMT_FLOAT, 1, 16, 2, PLB_FK_HALF},
+    {"rg16hf",   PL_FMT_FLOAT, 2, 16, 2, PLB_FK_HALF},
+    {"rgba16hf", PL_FMT_FLOAT, 4, 16, 2, PLB_FK_HALF},
+    {"r32f",     PL_FMT_FLOAT, 1, 32, 4, PLB_FK_FLOAT},
+    {"rg32f",    PL_FMT_FLOAT, 2, 32, 4, PLB_FK_FLOAT},
+    {"rgba32f",  PL_FMT_FLOAT, 4, 32, 4, PLB_FK_FLOAT},
+    {"r32u",     PL_FMT_UINT,  1, 32, 4, PLB_FK_UINT32},
+};
+
+static void setup_formats(struct plb_gpu *p)
+{
+    const int n = PLB_ARRAY_SIZE(fmt_defs);
+    p->fmts = (struct plb_fmt *) calloc(n, sizeof(struct plb_fmt));
+    p->fmt_list = (pl_fmt *) calloc(n, sizeof(pl_fmt));
+    for (int i = 0; i < n; i++) {
+        const struct fmt_def *d = &fmt_defs[i];
+        struct pl_fmt_t *f = &p->fmts[i].pub;
+        f->name = d->name;
+        f->signature = 0xB200F000ull + i;
+        f->type = d->type;
+        int caps = PL_FMT_CAP_SAMPLEABLE | PL_FMT_CAP_STORABLE | PL_FMT_CAP_RENDERABLE |
+                   PL_FMT_CAP_BLITTABLE | PL_FMT_CAP_HOST_READABLE | PL_FMT_CAP_READWRITE;
+        if (d->type != PL_FMT_UINT)
+            caps |= PL_FMT_CAP_LINEAR | PL_FMT_CAP_BLENDABLE;
+        f->caps = (enum pl_fmt_caps) caps;
+        f->num_components = d->comps;
+        for (int c = 0; c < d->comps; c++) {
+            f->component_depth[c] = d->depth;
+            f->host_bits[c] = d->bytes * 8;
+            f->sample_order[c] = c;
+        }
+        f->texel_size = f->internal_size = (size_t) d->comps * d->bytes;
+        f->texel_align = d->bytes;
+        f->gatherable = true;
+        p->fmts[i].kind = d->kind;
+        p->fmt_list[i] = f;
+    }
+    p->pub.formats = p->fmt_list;
+    p->pub.num_formats = n;
+}
+
+pl_fmt pl_find_named_fmt(pl_gpu gpu, const char *name)
+{
+    if (!name)
+        return NULL;
+    for (int i = 0; i < gpu->num_formats; i++) {
+        if (strcmp(gpu->formats[i]->name, name) == 0)
+            return gpu->formats[i];
+    }
+    return NULL;
+}
+
+// src/gpu.c pl_find_fmt: first format (in list order) matching type, component count,
+// minimum depth, host bits and caps
+pl_fmt pl_find_fmt(pl_gpu gpu, enum pl_fmt_type type, int num_components, int min_depth,
+                   int host_bits, enum pl_fmt_caps caps)
+{
+    for (int i = 0; i < gpu->num_formats; i++) {
+        pl_fmt fmt = gpu->formats[i];
+        if (fmt->type != type || fmt->num_components != num_components)
+            continue;
+        if ((fmt->caps & caps) != caps)
+            continue;
+        if (fmt->component_depth[0] < min_depth)
+            continue;
+        if (host_bits && fmt->host_bits[0] != host_bits)
+            continue;
+        return fmt;
+    }
+    return NULL;
+}
+
+// ---------------------------------------------------------------------------------------
+// pl_cuda_create / destroy
+// ---------------------------------------------------------------------------------------
+
+pl_gpu pl_cuda_create(pl_log log, const struct pl_cuda_params *params)
+{
+    static const struct pl_cuda_params defaults = {0};
+    params = params ? params : &defaults;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || params->device >= count) {
+        // no CPU fallback on this backend: fail loudly
+        plb_msg(log, PL_LOG_FATAL, "pl_cuda_create: no usable CUDA device %d (%s)",
+                params->device, err != cudaSuccess ? cudaGetErrorString(err) : "out of range");
+        return NULL;
+    }
+
+    struct plb_gpu *p = (struct plb_gpu *) calloc(1, sizeof(*p));
+    p->pub.log = log;
+    p->device = params->device;
+    p->no_timers = params->no_timers;
+    p->coord_mode = params->literal_coords ? PLB_COORD_LITERAL : PLB_COORD_EXACT;
+    pl_gpu gpu = &p->pub;
+    if (!CK(gpu, cudaSetDevice(p->device)))
+        goto error;
+    if (params->stream) {
+        p->stream = params->stream;
+    } else {
+        cudaStream_t s;
+        if (!CK(gpu, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)))
+            goto error;
+        p->stream = s;
+        p->own_stream = true;
+    }
+
+    {
+        cudaDeviceProp prop;
+        if (!CK(gpu, cudaGetDeviceProperties(&prop, p->device)))
+            goto error;
+        p->sm_count = prop.multiProcessorCount;
+        p->pub.glsl.version = 450;
+        p->pub.glsl.compute = true;
+        p->pub.glsl.max_shmem_size = prop.sharedMemPerBlockOptin;
+        p->pub.glsl.max_group_threads = 1024;
+        p->pub.glsl.max_group_size[0] = p->pub.glsl.max_group_size[1] = 1024;
+        p->pub.glsl.max_group_size[2] = 64;
+        p->pub.glsl.subgroup_size = 32;
+        p->pub.glsl.min_gather_offset = -32;
+        p->pub.glsl.max_gather_offset = 31;
+        p->pub.limits.thread_safe = false;
+        p->pub.limits.callbacks = true;
+        p->pub.limits.max_buf_size = prop.totalGlobalMem;
+        p->pub.limits.max_ssbo_size = prop.totalGlobalMem;
+        p->pub.limits.max_tex_1d_dim = 1u << 27;
+        p->pub.limits.max_tex_2d_dim = 65536;
+        p->pub.limits.max_tex_3d_dim = 4096;
+        p->pub.limits.buf_transfer = true;
+        p->pub.limits.align_tex_xfer_pitch = 256;
+        p->pub.limits.align_tex_xfer_offset = 256;
+        p->pub.limits.max_dispatch[0] = 2147483647u;
+        p->pub.limits.max_dispatch[1] = p->pub.limits.max_dispatch[2] = 65535;
+        PLB_INFO(log, "pl_cuda: device %d '%s' sm_%d%d, %d SMs, %.1f GiB", p->device,
+                 prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+                 prop.totalGlobalMem / 1073741824.0);
+    }
+
+    setup_formats(p);
+    if (!plb_upload_pq_consts(gpu))
+        goto error;
+    return gpu;
+
+error:
+    pl_cuda_destroy(&gpu);
+    return NULL;
+}
+
+void pl_cuda_destroy(pl_gpu *pgpu)
+{
+    if (!pgpu || !*pgpu)
+        return;
+    struct plb_gpu *p = plb_gpu_priv(*pgpu);
+    cudaSetDevice(p->device);
+    if (p->stream)
+        cudaStreamSynchronize((cudaStream_t) p->stream);
+    if (p->staging)
+        cudaFreeHost(p->staging);
+    if (p->own_stream && p->stream)
+        cudaStreamDestroy((cudaStream_t) p->stream);
+    free(p->fmts);
+    free(p->fmt_list);
+    free(p);
+    *pgpu = NULL;
+}
+
+void *pl_cuda_stream(pl_gpu gpu) { return plb_gpu_priv(gpu)->stream; }
+int plb_gpu_coord_mode(pl_gpu gpu) { return plb_gpu_priv(gpu)->coord_mode; }
+
+bool plb_pq_upload_polar(const plb_pq_consts *q);
+bool plb_pq_upload_pixel(const plb_pq_consts *q);
+
+bool plb_upload_pq_consts(pl_gpu gpu)
+{
+    struct plb_pq_consts q;
+    plb_pq_literal(&q);
+    bool ok = plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q);
+    if (!ok)
+        PLB_ERR(gpu->log, "failed uploading constant tables");
+    return ok;
+}
+uint64_t pl_cuda_launch_count(pl_gpu gpu) { return plb_gpu_priv(gpu)->launches; }
+
+void pl_gpu_flush(pl_gpu gpu) { (void) gpu; }
+
+void pl_gpu_finish(pl_gpu gpu)
+{
+    CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+}
+
+bool pl_gpu_is_failed(pl_gpu gpu) { return plb_gpu_priv(gpu)->failed; }
+
+// ---------------------------------------------------------------------------------------
+// textures
+// ---------------------------------------------------------------------------------------
+
+static int fmt_kind(pl_fmt fmt) { return ((const struct plb_fmt *) fmt)->kind; }
+
+static bool tex_params_valid(pl_gpu gpu, const struct pl_tex_params *params)
+{
+    if (!params || !params->format) {
+        PLB_ERR(gpu->log, "pl_tex_create: missing params/format");
+        return false;
+    }
+    if (params->w <= 0 || params->h < 0 || params->d < 0) {
+        PLB_ERR(gpu->log, "pl_tex_create: invalid dimensions %dx%dx%d", params->w, params->h,
+                params->d);
+        return false;
+    }
+    if ((uint32_t) params->w > gpu->limits.max_tex_2d_dim ||
+        (uint32_t) params->h > gpu->limits.max_tex_2d_dim) {
+        PLB_ERR(gpu->log, "pl_tex_create: dimensions exceed limits");
+        return false;
+    }
+    return true;
+}
+
+pl_tex pl_tex_create(pl_gpu gpu, const struct pl_tex_params *params)
+{
+    if (!tex_params_valid(gpu, params))
+        return NULL;
+    struct plb_tex *t = (struct plb_tex *) calloc(1, sizeof(*t));
+    t->pub.params = *params;
+    t->pub.params.initial_data = NULL;
+    t->gpu = gpu;
+    const int h = PLB_MAX(params->h, 1), d = PLB_MAX(params->d, 1);
+    const size_t row = params->w * params->format->texel_size;
+    t->d.pitch = (row + 255) & ~(size_t) 255;
+    t->d.w = params->w;
+    t->d.h = h * d; // 3D textures are stored as d slices of h rows
+    t->d.comps = params->format->num_components;
+    t->d.kind = fmt_kind(params->format);
+    t->alloc_size = t->d.pitch * h * d;
+    t->owned = true;
+    if (!CK(gpu, cudaMalloc(&t->d.ptr, t->alloc_size))) {
+        free(t);
+        return NULL;
+    }
+    if (params->initial_data) {
+        struct pl_tex_transfer_params tp = {0};
+        tp.tex = &t->pub;
+        tp.ptr = (void *) params->initial_data;
+        if (!pl_tex_upload(gpu, &tp)) {
+            pl_tex tex = &t->pub;
+            pl_tex_destroy(gpu, &tex);
+            return NULL;
+        }
+    }
+    return &t->pub;
+}
+
+pl_tex pl_cuda_wrap(pl_gpu gpu, const struct pl_cuda_wrap_params *params)
+{
+    if (!params || !params->ptr || !params->format || params->w <= 0 || params->h <= 0) {
+        PLB_ERR(gpu->log, "pl_cuda_wrap: invalid parameters");
+        return NULL;
+    }
+    const size_t row = params->w * params->format->texel_size;
+    if (params->pitch < row || params->pitch % params->format->texel_align) {
+        PLB_ERR(gpu->log, "pl_cuda_wrap: pitch %zu too small/misaligned for %d texels of %s",
+                params->pitch, params->w, params->format->name);
+        return NULL;
+    }
+    struct plb_tex *t = (struct plb_tex *) calloc(1, sizeof(*t));
+    t->pub.params.w = params->w;
+    t->pub.params.h = params->h;
+    t->pub.params.format = params->format;
+    t->pub.params.sampleable = t->pub.params.renderable = t->pub.params.storable = true;
+    t->pub.params.host_writable = t->pub.params.host_readable = true;
+    t->pub.params.blit_src = t->pub.params.blit_dst = true;
+    t->gpu = gpu;
+    t->d.ptr = params->ptr;
+    t->d.pitch = params->pitch;
+    t->d.w = params->w;
+    t->d.h = params->h;
+    t->d.comps = params->format->num_components;
+    t->d.kind = fmt_kind(params->format);
+    t->owned = false;
+    return &t->pub;
+}
+
+void *pl_cuda_tex_ptr(pl_tex tex, size_t *out_pitch)
+{
+    const struct plb_tex *t = plb_tex_priv(tex);
+    if (out_pitch)
+        *out_pitch = t->d.pitch;
+    return t->d.ptr;
+}
+
+void pl_tex_destroy(pl_gpu gpu, pl_tex *ptex)
+{
+    if (!ptex || !*ptex)
+        return;
+    struct plb_tex *t = (struct plb_tex *) *ptex;
+    if (t->owned && t->d.ptr)
+        CK(gpu, cudaFreeAsync(t->d.ptr, STREAM(gpu)));
+    free(t);
+    *ptex = NULL;
+}
+
+// src/gpu.c:472-520: keep the texture if the parameters are compatible
+bool pl_tex_recreate(pl_gpu gpu, pl_tex *tex, const struct pl_tex_params *params)
+{
+    if (params->initial_data) {
+        PLB_ERR(gpu->log, "pl_tex_recreate may not be used with `initial_data`!");
+        return false;
+    }
+    if (*tex) {
+        const struct pl_tex_params *cur = &(*tex)->params;
+        if (cur->w == params->w && cur->h == params->h && cur->d == params->d &&
+            cur->format == params->format)
+            return true;
+        pl_tex_destroy(gpu, tex);
+    }
+    *tex = pl_tex_create(gpu, params);
+    return !!*tex;
+}
+
+void pl_tex_invalidate(pl_gpu gpu, pl_tex tex) { (void) gpu; (void) tex; }
+
+extern bool plb_launch_clear(pl_gpu gpu, const struct plb_tex_desc *dst, const float color[4]);
+
+void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4])
+{
+    plb_launch_clear(gpu, &plb_tex_priv(dst)->d, color);
+}
+
+static void CUDART_CB host_cb_trampoline(void *data)
+{
+    void **pair = (void **) data;
+    void (*cb)(void *) = (void (*)(void *)) pair[0];
+    cb(pair[1]);
+    free(pair);
+}
+
+static bool fix_transfer(pl_gpu gpu, const struct pl_tex_transfer_params *params,
+                         pl_rect3d *rc, size_t *row_pitch, const char *what)
+{
+    pl_tex tex = params->tex;
+    if (!tex) {
+        PLB_ERR(gpu->log, "%s: no texture", what);
+        return false;
+    }
+    *rc = params->rc;
+    // src/gpu.c strip_coords / infer_rc: empty rect = whole texture
+    if (!rc->x0 && !rc->x1) rc->x1 = tex->params.w;
+    if (!rc->y0 && !rc->y1) rc->y1 = PLB_MAX(tex->params.h, 1);
+    if (rc->x0 < 0 || rc->y0 < 0 || rc->x1 > tex->params.w ||
+        rc->y1 > PLB_MAX(tex->params.h, 1) * PLB_MAX(tex->params.d, 1) ||
+        rc->x1 <= rc->x0 || rc->y1 <= rc->y0) {
+        PLB_ERR(gpu->log, "%s: rect out of bounds", what);
+        return false;
+    }
+    size_t min_pitch = (size_t) (rc->x1 - rc->x0) * tex->params.format->texel_size;
+    *row_pitch = params->row_pitch ? params->row_pitch : min_pitch;
+    if (*row_pitch < min_pitch) {
+        PLB_ERR(gpu->log, "%s: row_pitch %zu smaller than a row (%zu)", what, *row_pitch, min_pitch);
+        return false;
+    }
+    if (!params->ptr && !params->buf) {
+        PLB_ERR(gpu->log, "%s: neither ptr nor buf given", what);
+        return false;
+    }
+    return true;
+}
+
+bool pl_tex_upload(pl_gpu gpu, const struct pl_tex_transfer_params *params)
+{
+    pl_rect3d rc;
+    size_t row_pitch;
+    if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_upload"))
+        return false;
+    const struct plb_tex *t = plb_tex_priv(params->tex);
+    const size_t ts = params->tex->params.format->texel_size;
+    char *dst = (char *) t->d.ptr + (size_t) rc.y0 * t->d.pitch + rc.x0 * ts;
+    const size_t wbytes = (size_t) (rc.x1 - rc.x0) * ts;
+    bool ok;
+    if (params->buf) {
+        const struct plb_buf *b = (const struct plb_buf *) params->buf;
+        const char *src = (const char *) (b->dptr ? b->dptr : b->hptr) + params->buf_offset;
+        ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, src, row_pitch, wbytes, rc.y1 - rc.y0,
+                                       b->dptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                       STREAM(gpu)));
+    } else {
+        ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, params->ptr, row_pitch, wbytes,
+                                       rc.y1 - rc.y0, cudaMemcpyHostToDevice, STREAM(gpu)));
+    }
+    if (ok && params->callback) {
+        void **pair = (void **) malloc(2 * sizeof(void *));
+        pair[0] = (void *) params->callback;
+        pair[1] = params->priv;
+        ok = CK(gpu, cudaLaunchHostFunc(STREAM(gpu), host_cb_trampoline, pair));
+    }
+    return ok;
+}
+
+bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
+{
+    pl_rect3d rc;
+    size_t row_pitch;
+    if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_download"))
+        return false;
+    const struct plb_tex *t = plb_tex_priv(params->tex);
+    const size_t ts = params->tex->params.format->texel_size;
+    const char *src = (const char *) t->d.ptr + (size_t) rc.y0 * t->d.pitch + rc.x0 * ts;
+    const size_t wbytes = (size_t) (rc.x1 - rc.x0) * ts;
+    bool ok;
+    if (params->buf) {
+        const struct plb_buf *b = (const struct plb_buf *) params->buf;
+        char *dst = (char *) (b->dptr ? b->dptr : b->hptr) + params->buf_offset;
+        ok = CK(gpu, cudaMemcpy2DAsync(dst, row_pitch, src, t->d.pitch, wbytes, rc.y1 - rc.y0,
+                                       b->dptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                       STREAM(gpu)));
+    } else {
+        ok = CK(gpu, cudaMemcpy2DAsync(params->ptr, row_pitch, src, t->d.pitch, wbytes,
+                                       rc.y1 - rc.y0, cudaMemcpyDeviceToHost, STREAM(gpu)));
+    }
+    if (!ok)
+        return false;
+    if (params->callback) {
+        void **pair = (void **) malloc(2 * sizeof(void *));
+        pair[0] = (void *) params->callback;
+        pair[1] = params->priv;
+        return CK(gpu, cudaLaunchHostFunc(STREAM(gpu), host_cb_trampoline, pair));
+    }
+    // blocking semantics when no callback/buffer polling is requested (gpu.h:905-910)
+    if (!params->buf)
+        return CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+    return true;
+}
+
+bool pl_tex_poll(pl_gpu gpu, pl_tex tex, uint64_t timeout)
+{
+    (void) tex;
+    if (timeout) {
+        CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+        return false;
+    }
+    return cudaStreamQuery(STREAM(gpu)) == cudaErrorNotReady;
+}
+
+// ---------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------
+
+pl_buf pl_buf_create(pl_gpu gpu, const struct pl_buf_params *params)
+{
+    if (!params || !params->size) {
+        PLB_ERR(gpu->log, "pl_buf_create: zero-sized buffer");
+        return NULL;
+    }
+    struct plb_buf *b = (struct plb_buf *) calloc(1, sizeof(*b));
+    b->pub.params = *params;
+    b->pub.params.initial_data = NULL;
+    bool host_only = params->memory_type == PL_BUF_MEM_HOST ||
+                     (params->host_mapped && !params->storable && !params->uniform);
+    if (!host_only && !CK(gpu, cudaMalloc(&b->dptr, params->size)))
+        goto error;
+    if (host_only || params->host_mapped || params->host_readable || params->host_writable) {
+        if (!CK(gpu, cudaMallocHost(&b->hptr, params->size)))
+            goto error;
+        memset(b->hptr, 0, params->size);
+    }
+    if (params->host_mapped)
+        b->pub.data = (uint8_t *) b->hptr;
+    if (params->initial_data) {
+        if (b->hptr)
+            memcpy(b->hptr, params->initial_data, params->size);
+        if (b->dptr) {
+            if (b->hptr) {
+                if (!CK(gpu, cudaMemcpyAsync(b->dptr, b->hptr, params->size,
+                                             cudaMemcpyHostToDevice, STREAM(gpu))))
+                    goto error;
+            } else if (!plb_dev_upload(gpu, b->dptr, params->initial_data, params->size)) {
+                goto error;
+            }
+        }
+    } else if (b->dptr) {
+        CK(gpu, cudaMemsetAsync(b->dptr, 0, params->size, STREAM(gpu)));
+    }
+    return &b->pub;
+
+error:
+    if (b->dptr) cudaFree(b->dptr);
+    if (b->hptr) cudaFreeHost(b->hptr);
+    free(b);
+    return NULL;
+}
+
+void pl_buf_destroy(pl_gpu gpu, pl_buf *pbuf)
+{
+    if (!pbuf || !*pbuf)
+        return;
+    struct plb_buf *b = (struct plb_buf *) *pbuf;
+    if (b->hptr) {
+        CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+        cudaFreeHost(b->hptr);
+    }
+    if (b->dptr)
+        CK(gpu, cudaFreeAsync(b->dptr, STREAM(gpu)));
+    free(b);
+    *pbuf = NULL;
+}
+
+bool pl_buf_recreate(pl_gpu gpu, pl_buf *buf, const struct pl_buf_params *params)
+{
+    if (*buf && (*buf)->params.size >= params->size)
+        return true;
+    pl_buf_destroy(gpu, buf);
+    *buf = pl_buf_create(gpu, params);
+    return !!*buf;
+}
+
+void pl_buf_write(pl_gpu gpu, pl_buf buf, size_t buf_offset, const void *data, size_t size)
+{
+    struct plb_buf *b = (struct plb_buf *) buf;
+    if (buf_offset + size > buf->params.size) {
+        PLB_ERR(gpu->log, "pl_buf_write: out of bounds");
+        return;
+    }
+    if (b->hptr) {
+        // host mirror may be read by in-flight copies
+        CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+        memcpy((char *) b->hptr + buf_offset, data, size);
+        if (b->dptr)
+            CK(gpu, cudaMemcpyAsync((char *) b->dptr + buf_offset, (char *) b->hptr + buf_offset,
+                                    size, cudaMemcpyHostToDevice, STREAM(gpu)));
+    } else {
+        plb_dev_upload(gpu, (char *) b->dptr + buf_offset, data, size);
+    }
+}
+
+bool pl_buf_read(pl_gpu gpu, pl_buf buf, size_t buf_offset, void *dest, size_t size)
+{
+    struct plb_buf *b = (struct plb_buf *) buf;
+    if (buf_offset + size > buf->params.size) {
+        PLB_ERR(gpu->log, "pl_buf_read: out of bounds");
+        return false;
+    }
+    if (b->dptr)
+        return plb_dev_download(gpu, dest, (char *) b->dptr + buf_offset, size);
+    if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
+        return false;
+    memcpy(dest, (char *) b->hptr + buf_offset, size);
+    return true;
+}
+
+void pl_buf_copy(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset,
+                 size_t size)
+{
+    struct plb_buf *d = (struct plb_buf *) dst, *s = (struct plb_buf *) src;
+    void *dp = (char *) (d->dptr ? d->dptr : d->hptr) + dst_offset;
+    const void *sp = (const char *) (s->dptr ? s->dptr : s->hptr) + src_offset;
+    CK(gpu, cudaMemcpyAsync(dp, sp, size, cudaMemcpyDefault, STREAM(gpu)));
+}
+
+bool pl_buf_poll(pl_gpu gpu, pl_buf buf, uint64_t timeout)
+{
+    return pl_tex_poll(gpu, NULL, timeout) && buf;
+}
+
+// ---------------------------------------------------------------------------------------
+// timers: cudaEvent pairs recorded around dispatches (reference: gpu.h:415-437)
+// ---------------------------------------------------------------------------------------
+
+struct pl_timer_t {
+    cudaEvent_t start, stop;
+    bool recorded;
+};
+
+pl_timer pl_timer_create(pl_gpu gpu)
+{
+    struct pl_timer_t *t = (struct pl_timer_t *) calloc(1, sizeof(*t));
+    if (!CK(gpu, cudaEventCreate(&t->start)) || !CK(gpu, cudaEventCreate(&t->stop))) {
+        free(t);
+        return NULL;
+    }
+    return t;
+}
+
+void pl_timer_destroy(pl_gpu gpu, pl_timer *pt)
+{
+    (void) gpu;
+    if (!pt || !*pt)
+        return;
+    cudaEventDestroy((*pt)->start);
+    cudaEventDestroy((*pt)->stop);
+    free(*pt);
+    *pt = NULL;
+}
+
+void plb_timer_begin(pl_gpu gpu, pl_timer t)
+{
+    if (t)
+        CK(gpu, cudaEventRecord(t->start, STREAM(gpu)));
+}
+
+void plb_timer_end(pl_gpu gpu, pl_timer t)
+{
+    if (t) {
+        CK(gpu, cudaEventRecord(t->stop, STREAM(gpu)));
+        t->recorded = true;
+    }
+}
+
+// nanoseconds of the last recorded interval, 0 if not available yet
+uint64_t pl_timer_query(pl_gpu gpu, pl_timer t)
+{
+    (void) gpu;
+    if (!t || !t->recorded)
+        return 0;
+    if (cudaEventQuery(t->stop) != cudaSuccess)
+        return 0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t->start, t->stop) != cudaSuccess)
+        return 0;
+    t->recorded = false;
+    return (uint64_t) (ms * 1e6);
+}
+
+} // extern "C"

@@ -1,0 +1,289 @@
+// Internal definitions shared by the host side and the CUDA kernels of libplacebo_b200.
+// Nothing here is part of the C ABI (include/libplacebo_b200.h is).
+#ifndef PLB_INTERNAL_H_
+#define PLB_INTERNAL_H_
+
+#include "../../include/libplacebo_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---------------------------------------------------------------------------------------
+// logging (reference: src/log.h PL_ERR/PL_WARN/... macros)
+// ---------------------------------------------------------------------------------------
+void plb_msg(pl_log log, enum pl_log_level lev, const char *fmt, ...)
+    __attribute__((format(printf, 3, 4)));
+#define PLB_ERR(log, ...)   plb_msg(log, PL_LOG_ERR, __VA_ARGS__)
+#define PLB_WARN(log, ...)  plb_msg(log, PL_LOG_WARN, __VA_ARGS__)
+#define PLB_INFO(log, ...)  plb_msg(log, PL_LOG_INFO, __VA_ARGS__)
+#define PLB_DEBUG(log, ...) plb_msg(log, PL_LOG_DEBUG, __VA_ARGS__)
+
+#define PLB_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define PLB_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define PLB_DEF(x, d) ((x) ? (x) : (d))
+#define PLB_ARRAY_SIZE(a) (sizeof(a) / sizeof((a)[0]))
+
+// ---------------------------------------------------------------------------------------
+// Texel formats as the kernels see them
+// ---------------------------------------------------------------------------------------
+enum plb_fmt_kind {
+    PLB_FK_UNORM8 = 0,
+    PLB_FK_UNORM16,
+    PLB_FK_HALF,
+    PLB_FK_FLOAT,
+    PLB_FK_UINT32,
+};
+
+// Device-side view of a 2D (or 3D, for LUTs) texture: pitched linear memory in HBM
+struct plb_tex_desc {
+    void *ptr;
+    size_t pitch;      // bytes per row
+    int w, h;
+    int comps;         // 1..4
+    int kind;          // enum plb_fmt_kind
+};
+
+// The private object behind a pl_tex (public part first, like PL_PRIV in src/pl_alloc.h)
+struct plb_tex {
+    struct pl_tex_t pub;
+    pl_gpu gpu;
+    struct plb_tex_desc d;
+    bool owned;        // false for pl_cuda_wrap
+    size_t alloc_size;
+};
+static inline const struct plb_tex *plb_tex_priv(pl_tex tex) { return (const struct plb_tex *) tex; }
+
+struct plb_buf {
+    struct pl_buf_t pub;
+    void *dptr;        // device memory (NULL for pure host buffers)
+    void *hptr;        // pinned host mirror for host_readable / host_mapped buffers
+};
+
+struct plb_fmt {
+    struct pl_fmt_t pub;
+    int kind;
+};
+
+struct plb_gpu {
+    struct pl_gpu_t pub;
+    int device;
+    void *stream;          // cudaStream_t
+    bool own_stream;
+    bool failed;
+    bool no_timers;
+    int coord_mode;        // enum plb_coord_mode used by samplers
+    uint64_t launches;     // kernels launched (pl_cuda_launch_count)
+    int sm_count;
+    struct plb_fmt *fmts;
+    pl_fmt *fmt_list;
+    void *staging;         // pinned staging buffer for pl_tex_upload/download
+    size_t staging_size;
+};
+static inline struct plb_gpu *plb_gpu_priv(pl_gpu gpu) { return (struct plb_gpu *) gpu; }
+bool plb_cuda_check(pl_gpu gpu, int err, const char *what);
+void *plb_gpu_staging(pl_gpu gpu, size_t size);
+
+// small device allocations for LUTs / parameter blocks, owned by shader objects
+void *plb_dev_alloc(pl_gpu gpu, size_t size);
+void plb_dev_free(pl_gpu gpu, void *ptr);
+bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size);
+bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size);
+bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size);
+
+// ---------------------------------------------------------------------------------------
+// Colour op program: the typed replacement of the GLSL text a pl_shader accumulates.
+// Executed per pixel by plb_run_color_ops() (csrc/color_ops.cuh) inside the pixel, polar
+// and ortho kernels, in recording order.
+// ---------------------------------------------------------------------------------------
+enum plb_op_kind {
+    PLB_OP_NONE = 0,
+    PLB_OP_SCALE,          // color *= f (optionally incl. alpha)
+    PLB_OP_MATRIX,         // color.rgb = M*color.rgb + c
+    PLB_OP_LINEARIZE,      // pl_shader_linearize
+    PLB_OP_DELINEARIZE,    // pl_shader_delinearize
+    PLB_OP_DECODE_SPECIAL, // ICtCp / BT.2020-CL tail of pl_shader_decode_color
+    PLB_OP_ENCODE_SPECIAL,
+    PLB_OP_SIGMOID,
+    PLB_OP_UNSIGMOID,
+    PLB_OP_COLOR_MAP,      // IPT tone/gamut mapping core of pl_shader_color_map_ex
+    PLB_OP_DITHER,         // pl_shader_dither
+    PLB_OP_ROUND_FBO,      // emulate a store+load through an intermediate FBO format
+    PLB_OP_ALPHA,          // pl_shader_set_alpha conversions
+    PLB_OP_DOVI_RESHAPE,   // pl_shader_dovi_reshape
+    PLB_OP_GAMMA,          // color adjustment gamma
+    PLB_OP_PEAK,           // pl_shader_detect_peak tap (needs block-wide reduction)
+};
+
+struct plb_trc_consts {
+    int trc;
+    float csp_min, csp_max;
+    float luma[3];
+    float a, b;            // BT.1886 a, b (or 1/a, b for delinearize); HLG: y, b
+    int black_scaled;      // delinearize pre-scale enabled
+};
+
+struct plb_op_color_map {
+    float rgb2lms[9], lms2rgb[9];
+    int need_tone, need_gamut;
+    int tone_kind;                     // 0 LUT, 1 clip, 2 linear
+    const float *tone_lut; int tone_lut_size;
+    float tone_a, tone_b;              // 1/range, -min/range
+    float in_min, in_max, out_min, out_max;
+    float lin_a, lin_b;                // linear fast path
+    const uint16_t *gamut_lut;         // rgba16 texels, I fastest
+    int lut_I, lut_C, lut_h;
+    float g_a, g_b;
+};
+
+struct plb_op_dither {
+    int method;
+    const float *lut; int lut_size;
+    int new_depth;
+    int temporal;
+    uint32_t frame_index;
+    float gamma;
+    float rot[4];
+};
+
+struct plb_op_peak {
+    struct plb_trc_consts lin;
+    float cutoff;
+    int use_histogram;
+    uint32_t *buf;                     // device struct peak_buf_data (3264 B)
+};
+
+struct plb_dovi_dev;                   // uploaded reshape tables
+
+struct plb_color_op {
+    int kind;
+    union {
+        struct { float s; int with_alpha; } scale;
+        struct { float m[9]; float c[3]; int has_c; } matrix;
+        struct plb_trc_consts trc;
+        struct { int sys; } special;
+        struct { float center, slope, offset, scale; } sigmoid;
+        struct plb_op_color_map cmap;
+        struct plb_op_dither dither;
+        struct { int kind; int bits; } round_fbo;
+        struct { int from, to; } alpha;
+        struct { const struct plb_dovi_dev *tab; } dovi;
+        struct { float g; } gamma;
+        struct plb_op_peak peak;
+    } u;
+};
+
+#define PLB_MAX_OPS 12
+struct plb_color_prog {
+    int n;
+    struct plb_color_op ops[PLB_MAX_OPS];
+};
+
+// PQ constants as the reference's GLSL text carries them ("%f" = 6 decimals), computed on
+// the host once (csrc/shaders.cpp: plb_pq_literal) and handed to kernels in constant memory
+struct plb_pq_consts {
+    float m1, m2, c1, c2, c3, inv_m1, inv_m2, to_pq, from_pq, inv_from_pq;
+    float hlg_a, hlg_b, hlg_c, hlg_inv_a;
+    float inv_2pi;
+};
+
+// ---------------------------------------------------------------------------------------
+// Sampling stage descriptions
+// ---------------------------------------------------------------------------------------
+enum plb_coord_mode { PLB_COORD_LITERAL = 0, PLB_COORD_EXACT = 1 };
+
+// A sampler launch = primary sampler + the common per-pixel tail (struct plb_pixel_launch:
+// extra planes to merge, colour program, target). Declared below.
+struct plb_pixel_launch;
+enum plb_plane_kind {
+    PLB_PLANE_NONE = 0,
+    PLB_PLANE_DIRECT,      // pl_shader_sample_direct / nearest / bilinear
+    PLB_PLANE_DEBAND,      // pl_shader_deband
+    PLB_PLANE_GRAIN_AV1,   // pl_shader_film_grain (AV1)
+    PLB_PLANE_GRAIN_H274,
+};
+
+struct plb_av1_dev;        // uploaded grain LUTs, see k_grain.cu
+struct plb_h274_dev;
+
+struct plb_plane_src {
+    int kind;
+    struct plb_tex_desc tex;
+    pl_rect2df rect;       // source rect in texels, mapped over the output
+    int linear;            // bilinear instead of nearest (DIRECT)
+    float scale;
+    int8_t map[4];         // colour index written by texture component k (-1 = none)
+    // deband
+    int iterations;
+    float threshold, radius, grain_str;
+    float neutral[3];
+    uint8_t comp_mask;
+    // grain
+    const struct plb_av1_dev *av1;
+    const struct plb_h274_dev *h274;
+    struct plb_tex_desc luma;  // AV1 chroma needs the luma plane
+};
+
+struct plb_pixel_launch {
+    int nplanes;
+    struct plb_plane_src planes[4];
+    float init[4];         // colour before planes are merged (renderer.c:1792)
+    struct plb_tex_desc dst;   // dst.ptr == NULL: no store (peak measurement only)
+    pl_rect2d dst_rect;
+    int out_w, out_h;
+    int coord_mode;
+    uint32_t frame_index;
+    int wg_w, wg_h;        // work-group geometry (matters to PLB_OP_PEAK only)
+    struct plb_color_prog prog;
+};
+bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p);
+
+struct plb_polar_launch {
+    struct plb_tex_desc src;
+    pl_rect2df rect;           // source rect (texels)
+    const float *lut;          // device copy of pl_filter->weights (256 floats)
+    const float *host_lut;     // host copy (phase tables of the 2x fast path)
+    int lut_entries;
+    float radius, radius_zero, antiring, scale;
+    uint8_t comp_mask;
+    int allow_fast;            // phase-table fast path permitted (needs PLB_COORD_EXACT)
+    int8_t src_map[4];         // colour index receiving sampled component k
+    struct plb_pixel_launch tail;
+};
+bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p);
+
+struct plb_ortho_launch {
+    struct plb_tex_desc src;
+    pl_rect2df rect;
+    const float *lut;          // device: 256 rows * row_stride (after fill_ortho_lut)
+    int lut_entries, row_size, row_stride;
+    int use_linear;
+    float antiring, ratio, scale;
+    uint8_t comp_mask;
+    int pass;                  // 0 vertical, 1 horizontal
+    int8_t src_map[4];
+    struct plb_pixel_launch tail;
+};
+bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p);
+
+struct plb_errdiff_launch {
+    struct plb_tex_desc src, dst;
+    int w, h;
+    int new_depth;
+    int shift, divisor;
+    int pattern[3][5];
+};
+bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p);
+
+void plb_pq_literal(struct plb_pq_consts *q);
+bool plb_upload_pq_consts(pl_gpu gpu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

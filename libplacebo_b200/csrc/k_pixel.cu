@@ -1,0 +1,118 @@
+// Plain pixel pass: what the reference does with a fragment/compute shader that samples up to
+// four planes 1:1 (or through a free bilinear/nearest resize), merges them, runs colour ops and
+// writes the target — pass_read_image's merge shader (src/renderer.c:1788-1897), the FBO ->
+// colour-map -> dither -> target pass (renderer.c:2157-2279, 2586-2964) and the standalone
+// pl_dispatch_finish of sample_direct/deband shaders.
+//
+// CTA = 32x8 threads covering a 32x32 output tile (4 rows per thread, x fastest so that
+// loads/stores of a warp are one contiguous row segment). The tile is a whole number of
+// peak-detection work groups (8/16/32 wide), see pixel_core.cuh.
+#include "pixel_core.cuh"
+
+PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_pixel)
+
+#define PIX_TILE 32
+
+__global__ void __launch_bounds__(256)
+k_pixel(const __grid_constant__ plb_tail_args a)
+{
+    __shared__ plb_peak_smem ps;
+    const int X0 = blockIdx.x * PIX_TILE, Y0 = blockIdx.y * PIX_TILE;
+    const int gx = X0 + threadIdx.x;
+
+    // Does the program contain a peak tap? (uniform)
+    bool has_peak = false;
+    for (int i = 0; i < a.prog.n; i++)
+        has_peak |= a.prog.ops[i].kind == PLB_OP_PEAK;
+    const int wgs_x = has_peak ? PIX_TILE / a.wg_w : 1, wgs_y = has_peak ? PIX_TILE / a.wg_h : 1;
+    const int nwgx = has_peak ? (a.out_w + a.wg_w - 1) / a.wg_w : 1;
+    const int nwgy = has_peak ? (a.out_h + a.wg_h - 1) / a.wg_h : 1;
+    if (has_peak)
+        plb_peak_begin(ps);
+
+    const plb_op_peak *pk_any = nullptr;
+    #pragma unroll 1
+    for (int r = 0; r < PIX_TILE / 8; r++) {
+        const int gy = Y0 + threadIdx.y + 8 * r;
+        const bool inside = gx < a.out_w && gy < a.out_h;
+        if (!has_peak && !inside)
+            continue;
+        float color[4];
+        uint32_t ypq = 0;
+        const plb_op_peak *pk = nullptr;
+        plb_tail_color(a, gx, gy, nullptr, color, &ypq, &pk);
+        if (has_peak) {
+            const int lx = (gx - X0) / a.wg_w, ly = (gy - Y0) / a.wg_h;
+            const int wg_local = ly * wgs_x + lx;
+            const bool valid = (X0 / a.wg_w + lx) < nwgx && (Y0 / a.wg_h + ly) < nwgy;
+            pk_any = pk;
+            plb_peak_add(ps, *pk, valid, wg_local, ypq);
+        }
+        if (inside && a.dst.ptr)
+            plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy,
+                      make_float4(color[0], color[1], color[2], color[3]));
+    }
+
+    if (has_peak)
+        plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / a.wg_w, Y0 / a.wg_h, nwgx, nwgy,
+                        (uint32_t) (a.wg_w * a.wg_h));
+}
+
+#define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
+
+void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p)
+{
+    memset(t, 0, sizeof(*t));
+    t->nplanes = p->nplanes;
+    for (int i = 0; i < p->nplanes; i++) {
+        t->planes[i] = p->planes[i];
+        // deband/grain shaders are always evaluated on exact texel centres of their own
+        // plane (1:1 sub-pass); plain sampling follows the requested coordinate mode
+        t->plane_cc[i] = plb_coord_init(p->coord_mode, p->planes[i].tex, p->planes[i].rect,
+                                        p->out_w, p->out_h);
+    }
+    memcpy(t->init, p->init, sizeof(t->init));
+    for (int k = 0; k < 4; k++)
+        t->src_map[k] = -1;
+    t->dst = p->dst;
+    t->dst_x0 = p->dst_rect.x0;
+    t->dst_y0 = p->dst_rect.y0;
+    t->out_w = p->out_w;
+    t->out_h = p->out_h;
+    t->frame_index = p->frame_index;
+    t->wg_w = PLB_DEF(p->wg_w, 16);
+    t->wg_h = PLB_DEF(p->wg_h, 16);
+    t->prog = p->prog;
+}
+
+static bool prog_has_peak(const plb_color_prog *prog)
+{
+    for (int i = 0; i < prog->n; i++) {
+        if (prog->ops[i].kind == PLB_OP_PEAK)
+            return true;
+    }
+    return false;
+}
+
+extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
+{
+    static plb_tail_args t;
+    plb_fill_tail(&t, p);
+    if (prog_has_peak(&p->prog)) {
+        if (PIX_TILE % t.wg_w || PIX_TILE % t.wg_h ||
+            (PIX_TILE / t.wg_w) * (PIX_TILE / t.wg_h) > PLB_MAX_WG_PER_CTA) {
+            PLB_ERR(gpu->log, "peak detection: unsupported work group size %dx%d", t.wg_w, t.wg_h);
+            return false;
+        }
+    }
+    dim3 block(32, 8);
+    dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
+    if (prog_has_peak(&p->prog)) {
+        // cover every work group of the reference dispatch, including overhanging ones
+        grid.x = ((p->out_w + t.wg_w - 1) / t.wg_w * t.wg_w + PIX_TILE - 1) / PIX_TILE;
+        grid.y = ((p->out_h + t.wg_h - 1) / t.wg_h * t.wg_h + PIX_TILE - 1) / PIX_TILE;
+    }
+    k_pixel<<<grid, block, 0, STREAM(gpu)>>>(t);
+    plb_gpu_priv(gpu)->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel");
+}

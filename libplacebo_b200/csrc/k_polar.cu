@@ -1,0 +1,474 @@
+// Polar (EWA) resampling — the CUDA replacement of the GLSL emitted by
+// pl_shader_sample_polar (src/shaders/sampling.c:587-912, per-tap body polar_sample :503-558).
+//
+// Two kernels:
+//
+//  k_polar_generic   any ratio / rect / filter / anti-ringing. One thread per output pixel,
+//                    per-pixel sub-texel fraction and per-tap weight (sqrt + LUT lerp), source
+//                    texels straight from L1/L2. Follows the oracle operation by operation in
+//                    both coordinate modes, so it is bit-exact with it up to store rounding.
+//
+//  k_polar_up2<NC,R2> exact 2x upscale of a whole texture (chroma 4:2:0 -> luma size, 1080p ->
+//                    4K): with exact coordinates the sub-texel fraction takes only the values
+//                    {0.75, 0.25} per axis, so the 4 x 64 tap weights are tabulated once on the
+//                    host (same fp32 ops as the per-pixel path -> identical values) and handed
+//                    to the kernel as __grid_constant__ parameters (constant bank operands of
+//                    the FFMAs). Each thread produces a 4x2 output block from a 10x9 source
+//                    window held in registers, read as float2 from a planar fp32 tile staged in
+//                    shared memory; taps are visited in the reference's (y, x) order and
+//                    accumulated with FFMA, so results equal the exact-coordinate oracle bit
+//                    for bit. Taps that can never contribute for radius^2 < R2/16 are removed
+//                    at compile time (30 of 64 for EWA-Lanczos).
+//
+// Roofline notes: 2x EWA-Lanczos needs 30 taps x NC FFMA per output
+// pixel; at 128 FFMA/clk/SM that is the binding limit (not HBM): 0.70 clk/px/SM for NC=3.
+#include "pixel_core.cuh"
+
+void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p);
+
+PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_polar)
+
+#define MAX_TAPS 144
+
+struct polar_generic_args {
+    plb_tex_desc src;
+    plb_coord cc;
+    const float *lut;
+    int lut_entries;
+    float radius, inv_radius, radius_zero, antiring, scale;
+    uint8_t comp_mask;
+    int ntaps;
+    int8_t tap_x[MAX_TAPS], tap_y[MAX_TAPS];
+    uint8_t tap_flags[MAX_TAPS]; // bit0 guard, bit1 anti-ringing candidate
+    plb_tail_args tail;
+};
+
+// the EWA sum for one output pixel; out = vec4 as pl_shader_sample_polar leaves `color`
+PLB_DEV void polar_pixel(const polar_generic_args &a, int gx, int gy, float out[4])
+{
+    int jx, jy;
+    float fx, fy;
+    plb_coord_texel(a.cc, gx, gy, jx, jy, fx, fy);
+    float color[4] = {0, 0, 0, 0};
+    float wsum = 0.0f;
+    float ar[4][2] = {{0}}, wwsum[4][2] = {{0}};
+    const bool use_ar = a.antiring > 0.0f;
+
+    for (int t = 0; t < a.ntaps; t++) {
+        const float ox = (float) a.tap_x[t], oy = (float) a.tap_y[t];
+        const float dx = ox - fx, dy = oy - fy;
+        const float d = sqrtf(__fmaf_rn(dx, dx, dy * dy));
+        if ((a.tap_flags[t] & 1) && !(d < a.radius))
+            continue;
+        const float w = plb_lut1d(a.lut, a.lut_entries, d * a.inv_radius);
+        wsum += w;
+        const float4 c4 = plb_load_clamped(a.src, jx + a.tap_x[t], jy + a.tap_y[t]);
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(a.comp_mask & (1 << k)) || k >= a.src.comps)
+                continue;
+            color[k] = __fmaf_rn(w, c[k], color[k]);
+            if ((a.tap_flags[t] & 2) && d <= a.radius_zero) {
+                float cc0 = 1.0f - a.scale * c[k], cc1 = a.scale * c[k];
+                float ww0 = cc0 + 0.10f, ww1 = cc1 + 0.10f;
+                #pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    ww0 = ww0 * ww0;
+                    ww1 = ww1 * ww1;
+                }
+                ww0 = w * ww0;
+                ww1 = w * ww1;
+                ar[k][0] = __fmaf_rn(ww0, cc0, ar[k][0]);
+                ar[k][1] = __fmaf_rn(ww1, cc1, ar[k][1]);
+                wwsum[k][0] += ww0;
+                wwsum[k][1] += ww1;
+            }
+        }
+    }
+
+    const float norm = a.scale / wsum;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool have = (a.comp_mask & (1 << k)) && k < a.src.comps;
+        float v = norm * color[k];
+        if (have && use_ar) {
+            float wx = ar[k][0] / wwsum[k][0], wy = ar[k][1] / wwsum[k][1];
+            wx = 1.0f - wx;
+            float w = plb_clamp(v, wx, wy);
+            if (wx > wy)
+                w = wx * 0.5f + wy * 0.5f;
+            v = plb_mix(v, w, a.antiring);
+        }
+        out[k] = have ? v : 0.0f;
+    }
+    if (!(a.comp_mask & 8))
+        out[3] = 1.0f;
+}
+
+// CTA = 32x8 threads over a 32x32 output tile, like k_pixel
+__global__ void __launch_bounds__(256)
+k_polar_generic(const __grid_constant__ polar_generic_args a)
+{
+    __shared__ plb_peak_smem ps;
+    const plb_tail_args &t = a.tail;
+    const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+    const int gx = X0 + threadIdx.x;
+    bool has_peak = false;
+    for (int i = 0; i < t.prog.n; i++)
+        has_peak |= t.prog.ops[i].kind == PLB_OP_PEAK;
+    const int wgs_x = has_peak ? 32 / t.wg_w : 1, wgs_y = has_peak ? 32 / t.wg_h : 1;
+    const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
+    const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
+    if (has_peak)
+        plb_peak_begin(ps);
+    const plb_op_peak *pk_any = nullptr;
+    #pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int gy = Y0 + threadIdx.y + 8 * r;
+        const bool inside = gx < t.out_w && gy < t.out_h;
+        if (!has_peak && !inside)
+            continue;
+        float prim[4], color[4];
+        polar_pixel(a, gx, gy, prim);
+        uint32_t ypq = 0;
+        const plb_op_peak *pk = nullptr;
+        plb_tail_color(t, gx, gy, prim, color, &ypq, &pk);
+        if (has_peak) {
+            const int lx = (gx - X0) / t.wg_w, ly = (gy - Y0) / t.wg_h;
+            const bool valid = (X0 / t.wg_w + lx) < nwgx && (Y0 / t.wg_h + ly) < nwgy;
+            pk_any = pk;
+            plb_peak_add(ps, *pk, valid, ly * wgs_x + lx, ypq);
+        }
+        if (inside && t.dst.ptr)
+            plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy,
+                      make_float4(color[0], color[1], color[2], color[3]));
+    }
+    if (has_peak)
+        plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
+                        (uint32_t) (t.wg_w * t.wg_h));
+}
+
+// ---------------------------------------------------------------------------------------
+// 2x fast path
+// ---------------------------------------------------------------------------------------
+
+#define UP2_TX 16           // threads per CTA in x
+#define UP2_TY 16
+#define UP2_OX 4            // outputs per thread in x
+#define UP2_OY 2
+#define UP2_TILE_W (UP2_TX * UP2_OX / 2 + 9)   // 41 source columns
+#define UP2_TILE_WP 42                          // padded to an even width (float2 reads)
+#define UP2_TILE_H (UP2_TY * UP2_OY / 2 + 8)   // 24 source rows
+
+struct polar_up2_args {
+    plb_tex_desc src;
+    float w[2][2][8][8];    // [phase_y][phase_x][oy+3][ox+3]; phase 0 = fraction 0.75
+    float norm[2][2];       // scale / wsum per phase
+    plb_tail_args tail;
+};
+
+// Is tap (ox, oy) of phase (py, px) inside radius^2 < R2_16/16 ? (phase 0 -> f = 3/4)
+template <int R2_16>
+__host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
+{
+    return ox >= -3 && ox <= 4 && oy >= -3 && oy <= 4 &&
+           ((4 * ox - (px ? 1 : 3)) * (4 * ox - (px ? 1 : 3)) +
+            (4 * oy - (py ? 1 : 3)) * (4 * oy - (py ? 1 : 3))) < R2_16;
+}
+
+template <int NC, int R2_16>
+__global__ void __launch_bounds__(UP2_TX * UP2_TY)
+k_polar_up2(const __grid_constant__ polar_up2_args a)
+{
+    __shared__ __align__(16) float tile[NC][UP2_TILE_H][UP2_TILE_WP];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int X0 = blockIdx.x * (UP2_TX * UP2_OX), Y0 = blockIdx.y * (UP2_TY * UP2_OY);
+    const int col0 = X0 / 2 - 4, row0 = Y0 / 2 - 4;
+
+    // Stage the source tile (clamp-to-edge) as planar fp32
+    for (int i = ty * UP2_TX + tx; i < UP2_TILE_H * UP2_TILE_WP; i += UP2_TX * UP2_TY) {
+        const int r = i / UP2_TILE_WP, c = i - r * UP2_TILE_WP;
+        const float4 v = plb_load_clamped(a.src, col0 + c, row0 + r);
+        tile[0][r][c] = v.x;
+        if (NC > 1) tile[1 % NC][r][c] = v.y;
+        if (NC > 2) tile[2 % NC][r][c] = v.z;
+        if (NC > 3) tile[3 % NC][r][c] = v.w;
+    }
+    __syncthreads();
+
+    float acc[UP2_OY][UP2_OX][NC];
+    #pragma unroll
+    for (int i = 0; i < UP2_OY; i++)
+        #pragma unroll
+        for (int j = 0; j < UP2_OX; j++)
+            #pragma unroll
+            for (int k = 0; k < NC; k++)
+                acc[i][j][k] = 0.0f;
+
+    // thread's source cells: columns i0 = X0/2 + 2*tx (+1), row jj = Y0/2 + ty
+    // window column wx <-> source column i0 - 4 + wx  (tile column 2*tx + wx)
+    // window row    wy <-> source row    jj - 4 + wy  (tile row    ty + wy)
+    #pragma unroll
+    for (int wy = 0; wy < 9; wy++) {
+        float v[NC][10];
+        #pragma unroll
+        for (int k = 0; k < NC; k++) {
+            const float2 *rowp = (const float2 *) &tile[k][ty + wy][2 * tx];
+            #pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const float2 f = rowp[q];
+                v[k][2 * q] = f.x;
+                v[k][2 * q + 1] = f.y;
+            }
+        }
+        #pragma unroll
+        for (int oyo = 0; oyo < UP2_OY; oyo++) {
+            // output row 2*jj + oyo: phase oyo, base row jj - 1 (phase 0) or jj (phase 1)
+            const int oy = wy - 4 + (oyo == 0 ? 1 : 0);
+            #pragma unroll
+            for (int oxo = 0; oxo < UP2_OX; oxo++) {
+                const int ci = oxo >> 1, px = oxo & 1;
+                #pragma unroll
+                for (int wx = 0; wx < 10; wx++) {
+                    const int ox = wx - 4 - ci + (px == 0 ? 1 : 0);
+                    if (up2_tap_on<R2_16>(oyo, px, oy, ox)) {
+                        const float w = a.w[oyo][px][oy + 3][ox + 3];
+                        #pragma unroll
+                        for (int k = 0; k < NC; k++)
+                            acc[oyo][oxo][k] = __fmaf_rn(w, v[k][wx], acc[oyo][oxo][k]);
+                    }
+                }
+            }
+        }
+    }
+
+    const plb_tail_args &t = a.tail;
+    bool has_peak = false;
+    for (int i = 0; i < t.prog.n; i++)
+        has_peak |= t.prog.ops[i].kind == PLB_OP_PEAK;
+    const int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
+    const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
+    const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
+    const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
+    __shared__ plb_peak_smem ps;
+    if (has_peak)
+        plb_peak_begin(ps);
+    const plb_op_peak *pk_any = nullptr;
+
+    #pragma unroll
+    for (int oyo = 0; oyo < UP2_OY; oyo++) {
+        const int gy = Y0 + ty * UP2_OY + oyo;
+        #pragma unroll
+        for (int oxo = 0; oxo < UP2_OX; oxo++) {
+            const int gx = X0 + tx * UP2_OX + oxo;
+            const bool inside = gx < t.out_w && gy < t.out_h;
+            if (!has_peak && !inside)
+                continue;
+            const float norm = a.norm[oyo][oxo & 1];
+            float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+            #pragma unroll
+            for (int k = 0; k < NC; k++)
+                prim[k] = norm * acc[oyo][oxo][k];
+            float color[4];
+            uint32_t ypq = 0;
+            const plb_op_peak *pk = nullptr;
+            plb_tail_color(t, gx, gy, prim, color, &ypq, &pk);
+            if (has_peak) {
+                const int lx = (gx - X0) / t.wg_w, ly = (gy - Y0) / t.wg_h;
+                const bool valid = (X0 / t.wg_w + lx) < nwgx && (Y0 / t.wg_h + ly) < nwgy;
+                pk_any = pk;
+                plb_peak_add(ps, *pk, valid, ly * wgs_x + lx, ypq);
+            }
+            if (inside && t.dst.ptr)
+                plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy,
+                          make_float4(color[0], color[1], color[2], color[3]));
+        }
+    }
+    if (has_peak)
+        plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
+                        (uint32_t) (t.wg_w * t.wg_h));
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+
+// Tap list with the reference's build-time culling (sampling.c:508-522, :776-783)
+static int build_taps(float radius, float radius_zero, bool use_ar, int8_t *tx, int8_t *ty,
+                      uint8_t *flags)
+{
+    const int bound = (int) ceilf(radius);
+    int n = 0;
+    for (int y = 1 - bound; y <= bound; y++) {
+        for (int x = 1 - bound; x <= bound; x++) {
+            int yy = y > 0 ? y - 1 : y;
+            int xx = x > 0 ? x - 1 : x;
+            float dmin = sqrt((double) (xx * xx + yy * yy));
+            if (dmin >= radius)
+                continue;
+            if (n >= MAX_TAPS)
+                return -1;
+            tx[n] = x;
+            ty[n] = y;
+            flags[n] = (dmin >= radius - M_SQRT2 ? 1 : 0) |
+                       (use_ar && dmin < radius_zero ? 2 : 0);
+            n++;
+        }
+    }
+    return n;
+}
+
+static float host_lut1d(const float *lut, int n, float x)
+{
+    float fpos = fminf(fmaxf(x, 0.0f), 1.0f) * (float) (n - 1);
+    float fbase = floorf(fpos), fceil = ceilf(fpos);
+    float t = fpos - fbase;
+    return lut[(int) fbase] * (1.0f - t) + lut[(int) fceil] * t;
+}
+
+#define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
+
+template <int NC>
+static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
+{
+    dim3 block(UP2_TX, UP2_TY);
+    // the tile is a whole number of peak work groups, so this also covers overhanging ones
+    dim3 grid((args.tail.out_w + UP2_TX * UP2_OX - 1) / (UP2_TX * UP2_OX),
+              (args.tail.out_h + UP2_TY * UP2_OY - 1) / (UP2_TY * UP2_OY));
+    switch (r2_class) {
+    case 160: k_polar_up2<NC, 160><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    case 168: k_polar_up2<NC, 168><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    default:  k_polar_up2<NC, 1000><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    }
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_polar_up2");
+}
+
+extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
+{
+    struct plb_gpu *g = plb_gpu_priv(gpu);
+    const struct plb_pixel_launch *tl = &p->tail;
+    const int bound = (int) ceilf(p->radius);
+    if (bound > 6) {
+        PLB_ERR(gpu->log, "polar radius %f exceeds implementation capacity", p->radius);
+        return false;
+    }
+    bool has_peak = false;
+    for (int i = 0; i < tl->prog.n; i++)
+        has_peak |= tl->prog.ops[i].kind == PLB_OP_PEAK;
+    const int wg_w = PLB_DEF(tl->wg_w, 32), wg_h = PLB_DEF(tl->wg_h, 32);
+
+    // --- 2x fast path eligibility ---
+    const bool full = p->rect.x0 == 0 && p->rect.y0 == 0 && p->rect.x1 == p->src.w &&
+                      p->rect.y1 == p->src.h;
+    const uint8_t mask = p->comp_mask;
+    const int nc = mask == 0x1 ? 1 : mask == 0x3 ? 2 : mask == 0x7 ? 3 : mask == 0xF ? 4 : 0;
+    bool fast = p->allow_fast && tl->coord_mode == PLB_COORD_EXACT && full && p->host_lut &&
+                tl->out_w == 2 * p->src.w && tl->out_h == 2 * p->src.h && bound <= 4 &&
+                !(p->antiring > 0) && nc && nc <= p->src.comps;
+    const int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
+    if (has_peak && (TW % wg_w || TH % wg_h || (TW / wg_w) * (TH / wg_h) > PLB_MAX_WG_PER_CTA))
+        fast = false;
+    if (has_peak && !fast && (32 % wg_w || 32 % wg_h)) {
+        PLB_ERR(gpu->log, "peak detection: unsupported work group size %dx%d", wg_w, wg_h);
+        return false;
+    }
+
+    if (fast) {
+        static polar_up2_args args; // large; keep off the stack
+        memset(&args, 0, sizeof(args));
+        args.src = p->src;
+        plb_fill_tail(&args.tail, tl);
+        args.tail.wg_w = wg_w;
+        args.tail.wg_h = wg_h;
+        memcpy(args.tail.src_map, p->src_map, sizeof(p->src_map));
+        int8_t tx[MAX_TAPS], ty[MAX_TAPS];
+        uint8_t fl[MAX_TAPS];
+        const int ntaps = build_taps(p->radius, p->radius_zero, false, tx, ty, fl);
+        const float inv_radius = 1.0f / p->radius;
+        int max_d16 = 0;
+        for (int py = 0; py < 2; py++) {
+            for (int px = 0; px < 2; px++) {
+                const float fx = px ? 0.25f : 0.75f, fy = py ? 0.25f : 0.75f;
+                float wsum = 0.0f;
+                for (int t = 0; t < ntaps; t++) {
+                    const float dx = (float) tx[t] - fx, dy = (float) ty[t] - fy;
+                    const float d = sqrtf(fmaf(dx, dx, dy * dy));
+                    if ((fl[t] & 1) && !(d < p->radius))
+                        continue;
+                    const float w = host_lut1d(p->host_lut, p->lut_entries, d * inv_radius);
+                    wsum += w;
+                    args.w[py][px][ty[t] + 3][tx[t] + 3] = w;
+                    if (w != 0.0f) {
+                        int ax = 4 * tx[t] - (px ? 1 : 3), ay = 4 * ty[t] - (py ? 1 : 3);
+                        int d16 = ax * ax + ay * ay;
+                        max_d16 = PLB_MAX(max_d16, d16);
+                    }
+                }
+                args.norm[py][px] = p->scale / wsum;
+            }
+        }
+        const int r2_class = max_d16 < 160 ? 160 : max_d16 < 168 ? 168 : 1000;
+        bool ok;
+        switch (nc) {
+        case 1: ok = launch_up2<1>(gpu, args, r2_class); break;
+        case 2: ok = launch_up2<2>(gpu, args, r2_class); break;
+        case 3: ok = launch_up2<3>(gpu, args, r2_class); break;
+        default: ok = launch_up2<4>(gpu, args, r2_class); break;
+        }
+        g->launches++;
+        return ok;
+    }
+
+    static polar_generic_args a;
+    memset(&a, 0, sizeof(a));
+    a.src = p->src;
+    a.cc = plb_coord_init(tl->coord_mode, p->src, p->rect, tl->out_w, tl->out_h);
+    a.lut = p->lut;
+    a.lut_entries = p->lut_entries;
+    a.radius = p->radius;
+    a.inv_radius = 1.0f / p->radius;
+    a.radius_zero = p->radius_zero;
+    a.antiring = p->antiring;
+    a.scale = p->scale;
+    a.comp_mask = p->comp_mask;
+    a.ntaps = build_taps(p->radius, p->radius_zero, p->antiring > 0, a.tap_x, a.tap_y, a.tap_flags);
+    if (a.ntaps < 0) {
+        PLB_ERR(gpu->log, "polar filter needs too many taps");
+        return false;
+    }
+    plb_fill_tail(&a.tail, tl);
+    a.tail.wg_w = wg_w;
+    a.tail.wg_h = wg_h;
+    memcpy(a.tail.src_map, p->src_map, sizeof(p->src_map));
+    dim3 block(32, 8);
+    dim3 grid((tl->out_w + 31) / 32, (tl->out_h + 31) / 32);
+    if (has_peak) {
+        grid.x = ((tl->out_w + wg_w - 1) / wg_w * wg_w + 31) / 32;
+        grid.y = ((tl->out_h + wg_h - 1) / wg_h * wg_h + 31) / 32;
+    }
+    k_polar_generic<<<grid, block, 0, STREAM(gpu)>>>(a);
+    g->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_polar_generic");
+}
+
+// ---------------------------------------------------------------------------------------
+// pl_tex_clear
+// ---------------------------------------------------------------------------------------
+
+__global__ void k_clear(plb_tex_desc dst, float4 color)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < dst.w && y < dst.h)
+        plb_store(dst, x, y, color);
+}
+
+extern "C" bool plb_launch_clear(pl_gpu gpu, const struct plb_tex_desc *dst, const float color[4])
+{
+    dim3 block(32, 8), grid((dst->w + 31) / 32, (dst->h + 7) / 8);
+    k_clear<<<grid, block, 0, STREAM(gpu)>>>(*dst, make_float4(color[0], color[1], color[2], color[3]));
+    plb_gpu_priv(gpu)->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_clear");
+}

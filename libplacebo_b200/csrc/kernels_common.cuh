@@ -1,0 +1,280 @@
+// Device helpers shared by all kernels: texel load/store with format conversion, sampling,
+// pixel coordinates. All kernels are compiled with -fmad=false; every fused multiply-add is
+// written explicitly (__fmaf_rn) so that the fp32 operation sequence is exactly the one the
+// CPU oracle performs (oracle/pl_oracle.h "arithmetic conventions").
+#pragma once
+
+#include "internal.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PLB_DEV __device__ __forceinline__
+
+PLB_DEV float plb_mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+PLB_DEV float plb_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+PLB_DEV int plb_clampi(int x, int lo, int hi) { return min(max(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------
+// Texel access. Conversions: unorm -> v / (2^n - 1) with an IEEE division (what texture units
+// and the oracle do), half -> exact widening.
+// ---------------------------------------------------------------------------------------
+
+template <int KIND, int COMPS>
+PLB_DEV float4 plb_load_t(const plb_tex_desc &t, int x, int y)
+{
+    const char *row = (const char *) t.ptr + (size_t) y * t.pitch;
+    float v[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+    if (KIND == PLB_FK_UNORM8) {
+        const uint8_t *p = (const uint8_t *) row + x * COMPS;
+        if (COMPS == 4) {
+            uchar4 u = *(const uchar4 *) p;
+            v[0] = u.x / 255.0f; v[1] = u.y / 255.0f; v[2] = u.z / 255.0f; v[3] = u.w / 255.0f;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < COMPS; c++)
+                v[c] = p[c] / 255.0f;
+        }
+    } else if (KIND == PLB_FK_UNORM16) {
+        const uint16_t *p = (const uint16_t *) row + x * COMPS;
+        if (COMPS == 4) {
+            ushort4 u = *(const ushort4 *) p;
+            v[0] = u.x / 65535.0f; v[1] = u.y / 65535.0f; v[2] = u.z / 65535.0f; v[3] = u.w / 65535.0f;
+        } else if (COMPS == 2) {
+            ushort2 u = *(const ushort2 *) p;
+            v[0] = u.x / 65535.0f; v[1] = u.y / 65535.0f;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < COMPS; c++)
+                v[c] = p[c] / 65535.0f;
+        }
+    } else if (KIND == PLB_FK_HALF) {
+        const __half *p = (const __half *) row + x * COMPS;
+        if (COMPS == 4) {
+            uint2 raw = *(const uint2 *) p;
+            __half2 a = *(__half2 *) &raw.x, b = *(__half2 *) &raw.y;
+            float2 fa = __half22float2(a), fb = __half22float2(b);
+            v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+        } else if (COMPS == 2) {
+            float2 f = __half22float2(*(const __half2 *) p);
+            v[0] = f.x; v[1] = f.y;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < COMPS; c++)
+                v[c] = __half2float(p[c]);
+        }
+    } else { // float
+        const float *p = (const float *) row + x * COMPS;
+        if (COMPS == 4) {
+            float4 f = *(const float4 *) p;
+            return f;
+        } else if (COMPS == 2) {
+            float2 f = *(const float2 *) p;
+            v[0] = f.x; v[1] = f.y;
+        } else {
+            #pragma unroll
+            for (int c = 0; c < COMPS; c++)
+                v[c] = p[c];
+        }
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// Runtime-dispatched variant for the generic kernels (uniform branches)
+PLB_DEV float4 plb_load(const plb_tex_desc &t, int x, int y)
+{
+#define L(K) \
+    switch (t.comps) { \
+    case 1: return plb_load_t<K, 1>(t, x, y); \
+    case 2: return plb_load_t<K, 2>(t, x, y); \
+    case 3: return plb_load_t<K, 3>(t, x, y); \
+    default: return plb_load_t<K, 4>(t, x, y); \
+    }
+    switch (t.kind) {
+    case PLB_FK_UNORM8:  L(PLB_FK_UNORM8)
+    case PLB_FK_UNORM16: L(PLB_FK_UNORM16)
+    case PLB_FK_HALF:    L(PLB_FK_HALF)
+    default:             L(PLB_FK_FLOAT)
+    }
+#undef L
+}
+
+PLB_DEV float4 plb_load_clamped(const plb_tex_desc &t, int x, int y)
+{
+    return plb_load(t, plb_clampi(x, 0, t.w - 1), plb_clampi(y, 0, t.h - 1));
+}
+
+// textureLod(NEAREST) at normalised coords
+PLB_DEV float4 plb_tex_nearest(const plb_tex_desc &t, float u, float v)
+{
+    int x = (int) floorf(u * (float) t.w), y = (int) floorf(v * (float) t.h);
+    return plb_load_clamped(t, x, y);
+}
+
+PLB_DEV float4 plb_tex_linear(const plb_tex_desc &t, float u, float v)
+{
+    float tx = u * (float) t.w - 0.5f, ty = v * (float) t.h - 0.5f;
+    float bx = floorf(tx), by = floorf(ty);
+    float fx = tx - bx, fy = ty - by;
+    int x = (int) bx, y = (int) by;
+    float4 a = plb_load_clamped(t, x, y), b = plb_load_clamped(t, x + 1, y);
+    float4 c = plb_load_clamped(t, x, y + 1), d = plb_load_clamped(t, x + 1, y + 1);
+    float4 r;
+    r.x = plb_mix(plb_mix(a.x, b.x, fx), plb_mix(c.x, d.x, fx), fy);
+    r.y = plb_mix(plb_mix(a.y, b.y, fx), plb_mix(c.y, d.y, fx), fy);
+    r.z = plb_mix(plb_mix(a.z, b.z, fx), plb_mix(c.z, d.z, fx), fy);
+    r.w = plb_mix(plb_mix(a.w, b.w, fx), plb_mix(c.w, d.w, fx), fy);
+    return r;
+}
+
+// Store one texel. unorm: round-to-nearest-even of clamp(v)*max (GL/Vulkan conversion rule);
+// half: RNE narrowing.
+PLB_DEV uint32_t plb_unorm(float v, float maxv)
+{
+    return (uint32_t) rintf(plb_clamp(v, 0.0f, 1.0f) * maxv);
+}
+
+PLB_DEV void plb_store(const plb_tex_desc &t, int x, int y, float4 c)
+{
+    char *row = (char *) t.ptr + (size_t) y * t.pitch;
+    const float v[4] = {c.x, c.y, c.z, c.w};
+    switch (t.kind) {
+    case PLB_FK_UNORM8: {
+        uint8_t *p = (uint8_t *) row + x * t.comps;
+        if (t.comps == 4) {
+            *(uchar4 *) p = make_uchar4(plb_unorm(v[0], 255.0f), plb_unorm(v[1], 255.0f),
+                                        plb_unorm(v[2], 255.0f), plb_unorm(v[3], 255.0f));
+        } else {
+            for (int k = 0; k < t.comps; k++)
+                p[k] = plb_unorm(v[k], 255.0f);
+        }
+        break;
+    }
+    case PLB_FK_UNORM16: {
+        uint16_t *p = (uint16_t *) row + x * t.comps;
+        if (t.comps == 4) {
+            *(ushort4 *) p = make_ushort4(plb_unorm(v[0], 65535.0f), plb_unorm(v[1], 65535.0f),
+                                          plb_unorm(v[2], 65535.0f), plb_unorm(v[3], 65535.0f));
+        } else {
+            for (int k = 0; k < t.comps; k++)
+                p[k] = plb_unorm(v[k], 65535.0f);
+        }
+        break;
+    }
+    case PLB_FK_HALF: {
+        __half *p = (__half *) row + x * t.comps;
+        if (t.comps == 4) {
+            __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+            uint2 raw;
+            raw.x = *(uint32_t *) &a;
+            raw.y = *(uint32_t *) &b;
+            *(uint2 *) p = raw;
+        } else if (t.comps == 2) {
+            *(__half2 *) p = __floats2half2_rn(v[0], v[1]);
+        } else {
+            for (int k = 0; k < t.comps; k++)
+                p[k] = __float2half_rn(v[k]);
+        }
+        break;
+    }
+    default: {
+        float *p = (float *) row + x * t.comps;
+        if (t.comps == 4) {
+            *(float4 *) p = c;
+        } else {
+            for (int k = 0; k < t.comps; k++)
+                p[k] = v[k];
+        }
+        break;
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pixel coordinates — same two modes as the oracle (oracle/pl_oracle.c coord_pos/coord_texel);
+// LITERAL restates src/dispatch.c:1038-1062 in fp32.
+// ---------------------------------------------------------------------------------------
+
+struct plb_coord {
+    int mode;
+    float px0, px1, py0, py1;
+    float osx, osy;
+    float sizex, sizey;
+    float ptx, pty;
+    double dx0, dxs, dy0, dys;
+};
+
+static inline plb_coord plb_coord_init(int mode, const plb_tex_desc &src, pl_rect2df rc, int dw, int dh)
+{
+    plb_coord c;
+    c.mode = mode;
+    float sx = (float) (1.0 / src.w), sy = (float) (1.0 / src.h);
+    c.ptx = sx; c.pty = sy;
+    c.px0 = sx * rc.x0; c.px1 = sx * rc.x1;
+    c.py0 = sy * rc.y0; c.py1 = sy * rc.y1;
+    c.osx = (float) (1.0 / dw);
+    c.osy = (float) (1.0 / dh);
+    c.sizex = (float) src.w;
+    c.sizey = (float) src.h;
+    c.dx0 = rc.x0; c.dxs = ((double) rc.x1 - rc.x0) / dw;
+    c.dy0 = rc.y0; c.dys = ((double) rc.y1 - rc.y0) / dh;
+    return c;
+}
+
+PLB_DEV void plb_coord_pos(const plb_coord &c, int gx, int gy, float &posx, float &posy)
+{
+    if (c.mode == PLB_COORD_LITERAL) {
+        float fx = c.osx * ((float) gx + 0.5f);
+        float fy = c.osy * ((float) gy + 0.5f);
+        float mx = plb_mix(c.px0, c.px1, fx);
+        posx = plb_mix(mx, mx, fy);
+        posy = plb_mix(plb_mix(c.py0, c.py0, fx), plb_mix(c.py1, c.py1, fx), fy);
+    } else {
+        posx = (float) ((c.dx0 + c.dxs * (gx + 0.5)) / c.sizex);
+        posy = (float) ((c.dy0 + c.dys * (gy + 0.5)) / c.sizey);
+    }
+}
+
+PLB_DEV void plb_coord_texel(const plb_coord &c, int gx, int gy, int &jx, int &jy, float &fx, float &fy)
+{
+    if (c.mode == PLB_COORD_LITERAL) {
+        float px, py;
+        plb_coord_pos(c, gx, gy, px, py);
+        float tx = px * c.sizex - 0.5f, ty = py * c.sizey - 0.5f;
+        float bx = floorf(tx), by = floorf(ty);
+        jx = (int) bx; jy = (int) by;
+        fx = tx - bx; fy = ty - by;
+    } else {
+        double tx = c.dx0 + c.dxs * (gx + 0.5) - 0.5;
+        double ty = c.dy0 + c.dys * (gy + 0.5) - 0.5;
+        double bx = floor(tx), by = floor(ty);
+        jx = (int) bx; jy = (int) by;
+        fx = (float) (tx - bx); fy = (float) (ty - by);
+    }
+}
+
+// 1-D linear LUT, array form of src/shaders/lut.c:700-715
+PLB_DEV float plb_lut1d(const float *lut, int n, float x)
+{
+    float fpos = plb_clamp(x, 0.0f, 1.0f) * (float) (n - 1);
+    float fbase = floorf(fpos), fceil = ceilf(fpos);
+    return plb_mix(lut[(int) fbase], lut[(int) fceil], fpos - fbase);
+}
+
+// sh_prng (src/shaders.c:965-998), pcg3d
+PLB_DEV float3 plb_prng(uint3 &s)
+{
+    s.x = 1664525u * s.x + 1013904223u;
+    s.y = 1664525u * s.y + 1013904223u;
+    s.z = 1664525u * s.z + 1013904223u;
+    s.x += s.y * s.z;
+    s.y += s.z * s.x;
+    s.z += s.x * s.y;
+    s.x ^= s.x >> 16; s.y ^= s.y >> 16; s.z ^= s.z >> 16;
+    s.x += s.y * s.z;
+    s.y += s.z * s.x;
+    s.z += s.x * s.y;
+    const float k = 1.0f / 4294967296.0f;
+    return make_float3(__uint2float_rn(s.x) * k, __uint2float_rn(s.y) * k, __uint2float_rn(s.z) * k);
+}

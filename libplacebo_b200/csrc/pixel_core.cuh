@@ -1,0 +1,253 @@
+// The per-pixel tail shared by every sampling kernel (polar, ortho, plain pixel pass):
+//   1. merge extra planes into the colour (renderer.c:1788-1897: "color[map] = tmp[k]"),
+//      each plane being sampled directly, debanded (sampling.c:183-275) or grain-synthesised
+//   2. run the recorded colour ops (color_ops.cuh)
+//   3. fold the pixel into the peak-detection statistics of its work group
+//      (colorspace.c:1290-1348), using warp match/reduce + shared-memory atomics
+//   4. convert and store to the target texture
+#pragma once
+
+#include "color_ops.cuh"
+
+struct plb_tail_args {
+    int nplanes;
+    plb_plane_src planes[4];
+    plb_coord plane_cc[4];
+    float init[4];
+    int8_t src_map[4];     // colour index for component k of the primary sampler (-1 none)
+    plb_tex_desc dst;      // ptr == NULL: statistics only
+    int dst_x0, dst_y0;
+    int out_w, out_h;
+    uint32_t frame_index;
+    int wg_w, wg_h;        // work-group geometry for PLB_OP_PEAK
+    plb_color_prog prog;
+};
+
+#define PLB_MAX_WG_PER_CTA 16
+#define PLB_HIST_BINS 64
+#define PLB_PEAK_SLICES 12
+
+struct plb_peak_smem {
+    uint32_t sum[PLB_MAX_WG_PER_CTA], mx[PLB_MAX_WG_PER_CTA], black[PLB_MAX_WG_PER_CTA];
+    uint32_t hist[PLB_MAX_WG_PER_CTA][PLB_HIST_BINS];
+};
+
+// pl_shader_deband for one plane at output pixel (gx, gy); c = texel at pos (already loaded)
+PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx, float posy,
+                        int gx, int gy, uint32_t frame_index, float color[4])
+{
+    const uint8_t mask = pl.comp_mask & ~0x8u;
+    if (!mask)
+        return;
+    uint3 state = make_uint3((uint32_t) gx, (uint32_t) gy, frame_index);
+    float res[3] = { color[0], color[1], color[2] };
+    for (int i = 1; i <= pl.iterations; i++) {
+        const float3 rnd = plb_prng(state);
+        const float dist = rnd.x * ((float) i * pl.radius);
+        const float dir = rnd.y * 6.283185f;
+        const float dx = dist * cosf(dir), dy = dist * sinf(dir);
+        float avg[3] = {0.0f, 0.0f, 0.0f};
+        #pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float sx = (t == 0 || t == 3) ? 1.0f : -1.0f, sy = t < 2 ? 1.0f : -1.0f;
+            const float4 c = plb_tex_nearest(pl.tex, posx + cc.ptx * (sx * dx),
+                                             posy + cc.pty * (sy * dy));
+            avg[0] += c.x; avg[1] += c.y; avg[2] += c.z;
+        }
+        const float bound = pl.threshold / (float) i;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (!(mask & (1 << k)))
+                continue;
+            const float a = avg[k] * 0.25f;
+            const float diff = fabsf(res[k] - a);
+            res[k] = diff > bound ? res[k] : a;
+        }
+    }
+    if (pl.grain_str > 0.0f) {
+        const float3 rnd3 = plb_prng(state);
+        const float rnd[3] = { rnd3.x, rnd3.y, rnd3.z };
+        int idx = 0;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (!(mask & (1 << k)))
+                continue;
+            const float bound = pl.neutral[idx] / pl.scale;
+            const float strength = fminf(fabsf(res[k] - bound), pl.grain_str);
+            res[k] = __fmaf_rn(strength, rnd[idx] - 0.5f, res[k]);
+            idx++;
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (mask & (1 << k))
+            color[k] = res[k];
+    }
+}
+
+#ifdef PLB_HAVE_GRAIN
+PLB_DEV void plb_grain_av1(const plb_plane_src &pl, int gx, int gy, float color[4]);
+#endif
+
+// Sample plane `pl` at output pixel (gx, gy) -> vec4 (already multiplied by its scale)
+PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
+                              uint32_t frame_index, float out[4])
+{
+    float posx, posy;
+    plb_coord_pos(cc, gx, gy, posx, posy);
+    float4 c4;
+    if (pl.kind == PLB_PLANE_DIRECT && pl.linear)
+        c4 = plb_tex_linear(pl.tex, posx, posy);
+    else
+        c4 = plb_tex_nearest(pl.tex, posx, posy);
+    out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
+    if (pl.kind == PLB_PLANE_DEBAND)
+        plb_deband(pl, cc, posx, posy, gx, gy, frame_index, out);
+#ifdef PLB_HAVE_GRAIN
+    if (pl.kind == PLB_PLANE_GRAIN_AV1) {
+        plb_grain_av1(pl, gx, gy, out);
+        return; // grain applies its own scale
+    }
+#endif
+    #pragma unroll
+    for (int k = 0; k < 4; k++)
+        out[k] *= pl.scale;
+}
+
+// Steps 1-2 + the pixel's PQ luma for step 3. `prim` = output of the primary sampler (or NULL)
+// Not inlined on purpose (one copy per translation unit; see plb_run_color_ops).
+static __device__ __noinline__ bool plb_tail_color_slow(const plb_tail_args &a, int gx, int gy,
+                                                 const float *prim, float color[4],
+                                                 uint32_t *ypq, const plb_op_peak **pk);
+
+PLB_DEV bool plb_tail_color(const plb_tail_args &a, int gx, int gy, const float *prim,
+                            float color[4], uint32_t *ypq, const plb_op_peak **pk)
+{
+    if (a.nplanes == 0 && a.prog.n == 0 && prim) {
+        // pure resampling pass: nothing to merge, nothing to run
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            color[k] = a.init[k];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (a.src_map[k] >= 0)
+                color[a.src_map[k]] = prim[k];
+        }
+        *pk = nullptr;
+        return false;
+    }
+    return plb_tail_color_slow(a, gx, gy, prim, color, ypq, pk);
+}
+
+static __device__ __noinline__ bool plb_tail_color_slow(const plb_tail_args &a, int gx, int gy, const float *prim,
+                            float color[4], uint32_t *ypq, const plb_op_peak **pk)
+{
+    #pragma unroll
+    for (int k = 0; k < 4; k++)
+        color[k] = a.init[k];
+    if (prim) {
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (a.src_map[k] >= 0)
+                color[a.src_map[k]] = prim[k];
+        }
+    }
+    for (int i = 0; i < a.nplanes; i++) {
+        float tmp[4];
+        plb_sample_plane(a.planes[i], a.plane_cc[i], gx, gy, a.frame_index, tmp);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (a.planes[i].map[k] >= 0)
+                color[a.planes[i].map[k]] = tmp[k];
+        }
+    }
+    *pk = nullptr;
+    if (a.prog.n)
+        plb_run_color_ops(a.prog, gx, gy, color, pk, ypq);
+    return *pk != nullptr;
+}
+
+// Step 3, block-cooperative. All threads of the CTA must call plb_peak_begin/finish; pixels
+// are added with plb_peak_add (by any subset of lanes, so it uses a full-warp vote first).
+PLB_DEV void plb_peak_begin(plb_peak_smem &s)
+{
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < PLB_MAX_WG_PER_CTA; i += nt)
+        s.sum[i] = s.mx[i] = s.black[i] = 0;
+    for (int i = tid; i < PLB_MAX_WG_PER_CTA * PLB_HIST_BINS; i += nt)
+        (&s.hist[0][0])[i] = 0;
+    __syncthreads();
+}
+
+// `valid`: this lane contributes a pixel (its work group exists in the reference's grid).
+// Must be called convergently by all 32 lanes of the warp.
+PLB_DEV void plb_peak_add(plb_peak_smem &s, const plb_op_peak &p, bool valid, int wg_local,
+                          uint32_t ypq)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    const int key = valid ? wg_local : -1;
+    const unsigned m = __match_any_sync(full, key);
+    if (valid) {
+        const uint32_t gsum = __reduce_add_sync(m, ypq);
+        const uint32_t gmax = __reduce_max_sync(m, ypq);
+        const unsigned blackm = __ballot_sync(m, ypq == 0u) & m;
+        if (lane == __ffs(m) - 1) {
+            atomicAdd(&s.sum[wg_local], gsum);
+            atomicMax(&s.mx[wg_local], gmax);
+            if (p.cutoff != 0.0f)
+                atomicAdd(&s.black[wg_local], (uint32_t) __popc(blackm));
+        }
+    }
+    if (p.use_histogram) {
+        int bin = (int) ypq >> (14 - 7);
+        bin -= 64;
+        bin = plb_clampi(bin, 0, PLB_HIST_BINS - 1);
+        const int hkey = valid ? wg_local * PLB_HIST_BINS + bin : -1;
+        const unsigned hm = __match_any_sync(full, hkey);
+        if (valid && lane == __ffs(hm) - 1)
+            atomicAdd(&s.hist[wg_local][bin], (uint32_t) __popc(hm));
+    }
+}
+
+// One thread per work group publishes to the 12-slice global buffer exactly like
+// colorspace.c:1329-1348. (wgs_x, wgs_y) = work groups per CTA tile; (wg0x, wg0y) = global
+// index of the CTA's first work group; (nwgx, nwgy) = work groups in the whole dispatch.
+PLB_DEV void plb_peak_finish(plb_peak_smem &s, const plb_op_peak &p, int wgs_x, int wgs_y,
+                             int wg0x, int wg0y, int nwgx, int nwgy, uint32_t wg_size)
+{
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    uint32_t *buf = p.buf;
+    uint32_t *wg_count = buf, *wg_active = buf + PLB_PEAK_SLICES,
+             *sum_pq = buf + 2 * PLB_PEAK_SLICES, *max_pq = buf + 3 * PLB_PEAK_SLICES,
+             *hist = buf + 4 * PLB_PEAK_SLICES;
+    const int nwg = wgs_x * wgs_y;
+    if (p.use_histogram) {
+        for (int i = tid; i < nwg * PLB_HIST_BINS; i += nt) {
+            const int wl = i / PLB_HIST_BINS, bin = i - wl * PLB_HIST_BINS;
+            const int wx = wg0x + wl % wgs_x, wy = wg0y + wl / wgs_x;
+            if (wx >= nwgx || wy >= nwgy)
+                continue;
+            const uint32_t slice = (uint32_t) (wy * nwgx + wx) % PLB_PEAK_SLICES;
+            uint32_t v = s.hist[wl][bin];
+            if (bin == 0 && p.cutoff != 0.0f)
+                v -= s.black[wl];
+            if (v)
+                atomicAdd(&hist[slice * PLB_HIST_BINS + bin], v);
+        }
+    }
+    for (int wl = tid; wl < nwg; wl += nt) {
+        const int wx = wg0x + wl % wgs_x, wy = wg0y + wl / wgs_x;
+        if (wx >= nwgx || wy >= nwgy)
+            continue;
+        const uint32_t slice = (uint32_t) (wy * nwgx + wx) % PLB_PEAK_SLICES;
+        const uint32_t num = wg_size - s.black[wl];
+        atomicAdd(&wg_count[slice], 1u);
+        atomicAdd(&wg_active[slice], min(num, 1u));
+        if (num > 0u) {
+            atomicAdd(&sum_pq[slice], s.sum[wl] / num);
+            atomicMax(&max_pq[slice], s.mx[wl]);
+        }
+    }
+}

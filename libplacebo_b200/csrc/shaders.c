@@ -1,0 +1,951 @@
+// pl_shader on the CUDA backend: every pl_shader_* entry point of the hot path RECORDS a typed
+// op (with all parameters derived on the host exactly like the reference derives its GLSL
+// constants) instead of emitting GLSL text. Same call protocol as the reference: one
+// sampling/source call first, colour ops after it, failures latch in pl_shader_is_failed.
+//
+//   pl_shader_sample_polar   src/shaders/sampling.c:587-912  (host part :596-631, :661, :720)
+//   pl_shader_sample_ortho2  sampling.c:950-1104
+//   pl_shader_sample_direct/nearest/bilinear  sampling.c:277-340
+//   pl_shader_deband         sampling.c:183-275
+//   pl_shader_decode_color   src/shaders/colorspace.c:275-460, encode :462-573
+//   pl_shader_linearize/delinearize :589-847, sigmoid :851-894
+//   pl_shader_dither         src/shaders/dithering.c:109-274
+#define _GNU_SOURCE
+#include "shader_priv.h"
+
+#include <math.h>
+
+// ---------------------------------------------------------------------------------------
+// shader object plumbing (src/shaders.c:60-130, :909-963)
+// ---------------------------------------------------------------------------------------
+
+pl_shader pl_shader_alloc(pl_log log, const struct pl_shader_params *params)
+{
+    struct pl_shader_t *sh = calloc(1, sizeof(*sh));
+    sh->log = log;
+    pl_shader_reset(sh, params);
+    return sh;
+}
+
+static void shader_unref_objs(pl_shader sh)
+{
+    for (int i = 0; i < sh->num_objs; i++) {
+        pl_shader_obj obj = sh->objs[i];
+        pl_shader_obj_destroy(&obj);
+    }
+    sh->num_objs = 0;
+}
+
+void pl_shader_free(pl_shader *psh)
+{
+    if (!psh || !*psh)
+        return;
+    shader_unref_objs(*psh);
+    free(*psh);
+    *psh = NULL;
+}
+
+void pl_shader_reset(pl_shader sh, const struct pl_shader_params *params)
+{
+    pl_log log = sh->log;
+    pl_dispatch dp = sh->dp;
+    shader_unref_objs(sh);
+    memset(sh, 0, sizeof(*sh));
+    sh->log = log;
+    sh->dp = dp;
+    if (params)
+        sh->params = *params;
+    sh->px.init[3] = 1.0f;
+    for (int k = 0; k < 4; k++) {
+        sh->polar.src_map[k] = k;
+        sh->ortho.src_map[k] = k;
+    }
+}
+
+bool pl_shader_is_failed(const pl_shader sh) { return sh->failed; }
+bool pl_shader_is_compute(const pl_shader sh) { return sh->is_compute; }
+
+bool pl_shader_output_size(const pl_shader sh, int *w, int *h)
+{
+    if (!sh->out_w || !sh->out_h)
+        return false;
+    *w = sh->out_w;
+    *h = sh->out_h;
+    return true;
+}
+
+void plb_shader_fail(pl_shader sh, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    PLB_ERR(sh->log, "%s", buf);
+    sh->failed = true;
+}
+
+void pl_shader_obj_destroy(pl_shader_obj *ptr)
+{
+    pl_shader_obj obj = ptr ? *ptr : NULL;
+    if (!obj)
+        return;
+    *ptr = NULL;
+    if (--obj->refcount > 0)
+        return;
+    pl_gpu gpu = obj->gpu;
+    switch (obj->type) {
+    case PLB_OBJ_SAMPLER:
+        for (struct plb_sampler_obj *s = &obj->u.sampler; s;) {
+            pl_filter_free(&s->filter);
+            plb_dev_free(gpu, s->dev_lut);
+            free(s->host_lut);
+            struct plb_sampler_obj *next = s->pass2;
+            if (s != &obj->u.sampler)
+                free(s);
+            s = next;
+        }
+        break;
+    case PLB_OBJ_COLOR_MAP:
+        plb_dev_free(gpu, obj->u.cmap.dev_tone_lut);
+        plb_dev_free(gpu, obj->u.cmap.dev_gamut_lut);
+        plb_dev_free(gpu, obj->u.cmap.peak.dev_buf);
+        break;
+    case PLB_OBJ_DITHER:
+        plb_dev_free(gpu, obj->u.dither.dev_lut);
+        break;
+    case PLB_OBJ_GRAIN: {
+        extern void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g);
+        plb_grain_obj_free(gpu, obj->u.grain);
+        break;
+    }
+    default:
+        break;
+    }
+    free(obj);
+}
+
+// SH_OBJ: lazily create a state object of the given type and keep it alive with the shader
+void *plb_shader_obj(pl_shader sh, pl_shader_obj *ptr, enum plb_obj_type type)
+{
+    if (!ptr) {
+        plb_shader_fail(sh, "shader state object required but none given");
+        return NULL;
+    }
+    pl_shader_obj obj = *ptr;
+    if (obj && obj->gpu != sh->params.gpu) {
+        plb_shader_fail(sh, "Passed pl_shader_obj belongs to different GPU!");
+        return NULL;
+    }
+    if (obj && obj->type != type) {
+        plb_shader_fail(sh, "Passed pl_shader_obj of wrong type! Shader objects must always "
+                        "be used with the same type of shader.");
+        return NULL;
+    }
+    if (!obj) {
+        obj = calloc(1, sizeof(*obj));
+        obj->type = type;
+        obj->gpu = sh->params.gpu;
+        obj->refcount = 1;
+        *ptr = obj;
+    }
+    if (sh->num_objs < (int) PLB_ARRAY_SIZE(sh->objs)) {
+        obj->refcount++;
+        sh->objs[sh->num_objs++] = obj;
+    }
+    return &obj->u;
+}
+
+struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind)
+{
+    if (sh->px.prog.n >= PLB_MAX_OPS) {
+        plb_shader_fail(sh, "too many colour operations in one shader (max %d)", PLB_MAX_OPS);
+        return NULL;
+    }
+    struct plb_color_op *op = &sh->px.prog.ops[sh->px.prog.n++];
+    memset(op, 0, sizeof(*op));
+    op->kind = kind;
+    return op;
+}
+
+// sh_require(sh, PL_SHADER_SIG_COLOR, 0, 0)
+bool plb_shader_require_color(pl_shader sh, const char *who)
+{
+    if (sh->failed)
+        return false;
+    if (sh->src == PLB_SRC_NONE) {
+        plb_shader_fail(sh, "%s: shader has no input colour yet (call a sampling shader "
+                        "first)", who);
+        return false;
+    }
+    return true;
+}
+
+static bool require_input_none(pl_shader sh, int w, int h, const char *who)
+{
+    if (sh->failed)
+        return false;
+    if (sh->src != PLB_SRC_NONE) {
+        plb_shader_fail(sh, "%s: illegal sequence of shader operations (shader already has "
+                        "a source stage)", who);
+        return false;
+    }
+    if ((sh->out_w && w && sh->out_w != w) || (sh->out_h && h && sh->out_h != h)) {
+        plb_shader_fail(sh, "%s: incompatible output size requirements %dx%d and %dx%d", who,
+                        sh->out_w, sh->out_h, w, h);
+        return false;
+    }
+    sh->out_w = PLB_DEF(sh->out_w, w);
+    sh->out_h = PLB_DEF(sh->out_h, h);
+    return true;
+}
+
+// sh_try_compute (src/shaders.c:214-285), minus the shared-memory accounting
+bool plb_shader_try_compute(pl_shader sh, int bw, int bh, bool flex)
+{
+    if (bw * bh > 1024) {
+        if (!flex)
+            return false;
+        bw = PLB_MIN(bw, 1024);
+        bh = 1024 / bw;
+    }
+    // not a compute shader yet, or a flexible geometry meets a rigid one: take the new one
+    if (!sh->is_compute || (sh->wg_flexible && !flex)) {
+        sh->wg_w = bw;
+        sh->wg_h = bh;
+        sh->is_compute = true;
+        sh->wg_flexible = flex;
+        return true;
+    }
+    if (sh->wg_flexible && flex) {
+        sh->wg_w = PLB_MAX(sh->wg_w, bw);
+        sh->wg_h = PLB_MAX(sh->wg_h, bh);
+        return true;
+    }
+    // existing rigid geometry: a second rigid request must match, a flexible one adapts
+    if (!flex && (bw != sh->wg_w || bh != sh->wg_h))
+        return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// setup_src (sampling.c:45-181)
+// ---------------------------------------------------------------------------------------
+
+struct src_info {
+    float src_w, src_h;
+    int out_w, out_h;
+    float rx, ry, scale;
+    uint8_t mask;
+    pl_rect2df rect;
+    struct plb_tex_desc tex;
+};
+
+static bool setup_src(pl_shader sh, const struct pl_sample_src *src, struct src_info *o,
+                      bool resizable, bool need_linear, const char *who)
+{
+    if (!src || !src->tex) {
+        plb_shader_fail(sh, "%s: pl_sample_src.tex is required on the CUDA backend (the "
+                        "sampler2D signature cannot be honoured without GLSL)", who);
+        return false;
+    }
+    pl_tex tex = src->tex;
+    pl_fmt fmt = tex->params.format;
+    if (pl_tex_params_dimension(tex->params) != 2) {
+        plb_shader_fail(sh, "%s: not a 2D texture!", who);
+        return false;
+    }
+    if (need_linear && !(fmt->caps & PL_FMT_CAP_LINEAR)) {
+        plb_shader_fail(sh, "Trying to use a shader that requires linear sampling with a "
+                        "texture whose format (%s) does not support PL_FMT_CAP_LINEAR",
+                        fmt->name);
+        return false;
+    }
+    o->src_w = pl_rect_w(src->rect);
+    o->src_h = pl_rect_h(src->rect);
+    o->src_w = PLB_DEF(o->src_w, tex->params.w);
+    o->src_h = PLB_DEF(o->src_h, tex->params.h);
+    o->out_w = PLB_DEF(src->new_w, (int) roundf(fabs(o->src_w)));
+    o->out_h = PLB_DEF(src->new_h, (int) roundf(fabs(o->src_h)));
+    o->rx = o->out_w / fabs(o->src_w);
+    o->ry = o->out_h / fabs(o->src_h);
+    o->scale = PLB_DEF(src->scale, 1.0);
+    if (fmt->type == PL_FMT_UINT)
+        o->scale *= 1.0 / ((1ull << fmt->component_depth[0]) - 1);
+    uint8_t tex_mask = (1 << fmt->num_components) - 1;
+    uint8_t src_mask = src->component_mask;
+    if (!src_mask)
+        src_mask = (1 << PLB_DEF(src->components, 4)) - 1;
+    o->mask = tex_mask & src_mask;
+    o->rect = (pl_rect2df) {
+        src->rect.x0, src->rect.y0, src->rect.x0 + o->src_w, src->rect.y0 + o->src_h,
+    };
+    o->tex = plb_tex_priv(tex)->d;
+    if (!require_input_none(sh, resizable ? 0 : o->out_w, resizable ? 0 : o->out_h, who))
+        return false;
+    if (!tex->params.sampleable) {
+        plb_shader_fail(sh, "%s: texture not sampleable!", who);
+        return false;
+    }
+    return true;
+}
+
+static int coord_mode(pl_shader sh)
+{
+    extern int plb_gpu_coord_mode(pl_gpu gpu);
+    return plb_gpu_coord_mode(sh->params.gpu);
+}
+
+// ---------------------------------------------------------------------------------------
+// direct samplers
+// ---------------------------------------------------------------------------------------
+
+static bool sample_simple(pl_shader sh, const struct pl_sample_src *src, int linear,
+                          const char *who)
+{
+    struct src_info si;
+    if (!setup_src(sh, src, &si, true, linear == 1, who))
+        return false;
+    sh->src = PLB_SRC_PLANES;
+    struct plb_plane_src *pl = &sh->px.planes[0];
+    memset(pl, 0, sizeof(*pl));
+    pl->kind = PLB_PLANE_DIRECT;
+    pl->tex = si.tex;
+    pl->rect = si.rect;
+    // BEST (sample_direct): linear if the format can
+    pl->linear = linear < 0 ? !!(src->tex->params.format->caps & PL_FMT_CAP_LINEAR) : linear;
+    pl->scale = si.scale;
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k;
+    sh->px.nplanes = 1;
+    sh->px.coord_mode = coord_mode(sh);
+    return true;
+}
+
+bool pl_shader_sample_direct(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_simple(sh, src, -1, "pl_shader_sample_direct");
+}
+
+bool pl_shader_sample_nearest(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_simple(sh, src, 0, "pl_shader_sample_nearest");
+}
+
+bool pl_shader_sample_bilinear(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_simple(sh, src, 1, "pl_shader_sample_bilinear");
+}
+
+// ---------------------------------------------------------------------------------------
+// debanding
+// ---------------------------------------------------------------------------------------
+
+const struct pl_deband_params pl_deband_default_params = { PL_DEBAND_DEFAULTS };
+
+void pl_shader_deband(pl_shader sh, const struct pl_sample_src *src,
+                      const struct pl_deband_params *params)
+{
+    struct src_info si;
+    if (!setup_src(sh, src, &si, false, false, "pl_shader_deband"))
+        return;
+    params = params ? params : &pl_deband_default_params;
+    sh->src = PLB_SRC_PLANES;
+    struct plb_plane_src *pl = &sh->px.planes[0];
+    memset(pl, 0, sizeof(*pl));
+    pl->kind = PLB_PLANE_DEBAND;
+    pl->tex = si.tex;
+    pl->rect = si.rect;
+    pl->scale = si.scale;
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k;
+    pl->comp_mask = si.mask & ~0x8u;
+    pl->iterations = params->iterations;
+    pl->radius = params->radius;
+    // constants exactly as sampling.c:224-226, :261, :266 compute them
+    pl->threshold = params->threshold / (1000 * si.scale);
+    pl->grain_str = params->grain > 0 ? (float) (params->grain / (1000.0 * si.scale)) : 0.0f;
+    memcpy(pl->neutral, params->grain_neutral, sizeof(pl->neutral));
+    sh->px.nplanes = 1;
+    // the deband shader runs 1:1 on texel centres (NEAREST), coordinates are exact
+    sh->px.coord_mode = PLB_COORD_EXACT;
+}
+
+// ---------------------------------------------------------------------------------------
+// scaler LUT handling shared by polar / ortho
+// ---------------------------------------------------------------------------------------
+
+#define SCALER_LUT_SIZE   256
+#define SCALER_LUT_CUTOFF 1e-3f
+
+static bool sampler_update(pl_shader sh, struct plb_sampler_obj *obj,
+                           const struct pl_filter_config *cfg, bool polar)
+{
+    pl_gpu gpu = sh->params.gpu;
+    if (obj->filter && pl_filter_config_eq(&obj->filter->params.config, cfg))
+        return true;
+    pl_filter_free(&obj->filter);
+    struct pl_filter_params fp = {
+        .config = *cfg,
+        .lut_entries = SCALER_LUT_SIZE,
+        .cutoff = polar ? SCALER_LUT_CUTOFF : 0.0f,
+        .max_row_size = polar ? 0 : (int) (gpu->limits.max_tex_2d_dim / 4),
+        .row_stride_align = polar ? 0 : 4,
+    };
+    obj->filter = pl_filter_generate(sh->log, &fp);
+    if (!obj->filter) {
+        plb_shader_fail(sh, "Failed initializing %s filter!", polar ? "polar" : "separated");
+        return false;
+    }
+    pl_filter f = obj->filter;
+    size_t n = polar ? SCALER_LUT_SIZE : (size_t) SCALER_LUT_SIZE * f->row_stride;
+    free(obj->host_lut);
+    obj->host_lut = malloc(n * sizeof(float));
+    if (polar || f->radius != f->radius_zero) {
+        memcpy(obj->host_lut, f->weights, n * sizeof(float));
+    } else {
+        // fill_ortho_lut, sampling.c:919-936: positive-lobe filters use the linear sampling
+        // trick, the LUT stores (w0+w1, w1/(w0+w1)) pairs
+        for (int i = 0; i < SCALER_LUT_SIZE; i++) {
+            const float *w = f->weights + (size_t) i * f->row_stride;
+            float *row = obj->host_lut + (size_t) i * f->row_stride;
+            int k = 0;
+            for (; k < f->row_size; k += 2) {
+                const float w0 = w[k], w1 = w[k + 1];
+                row[k] = w0 + w1;
+                row[k + 1] = w1 / (w0 + w1);
+            }
+            for (; k < f->row_stride; k++)
+                row[k] = k >= 4 ? row[k - 4] : 0;
+        }
+    }
+    if (obj->lut_floats != n) {
+        plb_dev_free(gpu, obj->dev_lut);
+        obj->dev_lut = plb_dev_alloc(gpu, n * sizeof(float));
+        obj->lut_floats = n;
+    }
+    if (!obj->dev_lut || !plb_dev_upload(gpu, obj->dev_lut, obj->host_lut, n * sizeof(float))) {
+        plb_shader_fail(sh, "Failed initializing scaler LUT!");
+        return false;
+    }
+    return true;
+}
+
+bool pl_shader_sample_polar(pl_shader sh, const struct pl_sample_src *src,
+                            const struct pl_sample_filter_params *params)
+{
+    if (!params || !params->filter.polar) {
+        plb_shader_fail(sh, "Trying to use polar sampling with a non-polar filter?");
+        return false;
+    }
+    struct src_info si;
+    if (!setup_src(sh, src, &si, false, false, "pl_shader_sample_polar"))
+        return false;
+    struct plb_sampler_obj *obj = plb_shader_obj(sh, params->lut, PLB_OBJ_SAMPLER);
+    if (!obj)
+        return false;
+
+    // anti-alias widening when downscaling, sampling.c:608-616
+    float inv_scale = 1.0 / PLB_MIN(si.rx, si.ry);
+    inv_scale = PLB_MAX(inv_scale, 1.0);
+    if (params->no_widening)
+        inv_scale = 1.0;
+    struct pl_filter_config cfg = params->filter;
+    cfg.antiring = PLB_DEF(cfg.antiring, params->antiring);
+    cfg.blur = PLB_DEF(cfg.blur, 1.0f) * inv_scale;
+    if (!sampler_update(sh, obj, &cfg, true))
+        return false;
+
+    sh->src = PLB_SRC_POLAR;
+    struct plb_polar_launch *p = &sh->polar;
+    p->src = si.tex;
+    p->rect = si.rect;
+    p->lut = obj->dev_lut;
+    p->host_lut = obj->host_lut;
+    p->lut_entries = SCALER_LUT_SIZE;
+    p->radius = obj->filter->radius;
+    p->radius_zero = obj->filter->radius_zero;
+    p->antiring = cfg.antiring;
+    p->scale = si.scale;
+    p->comp_mask = si.mask;
+    p->allow_fast = true;
+    sh->px.coord_mode = coord_mode(sh);
+    // the reference turns this into a 32x(max_threads/32) compute shader when radius < 6
+    // (sampling.c:668-699); we mirror the geometry because peak detection statistics are
+    // defined per work group
+    if (!params->no_compute && obj->filter->radius < 6.0)
+        plb_shader_try_compute(sh, 32, 32, false);
+    return true;
+}
+
+bool pl_shader_sample_ortho2(pl_shader sh, const struct pl_sample_src *src,
+                             const struct pl_sample_filter_params *params)
+{
+    if (!params || params->filter.polar) {
+        plb_shader_fail(sh, "Trying to use separated sampling with a polar filter?");
+        return false;
+    }
+    struct src_info si;
+    if (!setup_src(sh, src, &si, false, true, "pl_shader_sample_ortho2"))
+        return false;
+    int pass;
+    if (fabs(si.rx - 1.0f) < 1e-6f) {
+        pass = 0; // SEP_VERT
+    } else if (fabs(si.ry - 1.0f) < 1e-6f) {
+        pass = 1; // SEP_HORIZ
+    } else {
+        plb_shader_fail(sh, "Trying to use pl_shader_sample_ortho with a pl_sample_src that "
+                        "requires scaling in multiple directions (rx=%f, ry=%f), this is not "
+                        "possible!", si.rx, si.ry);
+        return false;
+    }
+    struct plb_sampler_obj *obj = plb_shader_obj(sh, params->lut, PLB_OBJ_SAMPLER);
+    if (!obj)
+        return false;
+    if (pass != 0) {
+        if (!obj->pass2)
+            obj->pass2 = calloc(1, sizeof(*obj->pass2));
+        obj = obj->pass2;
+    }
+    const float ratio = pass ? si.rx : si.ry;
+    float inv_scale = 1.0 / ratio;
+    inv_scale = PLB_MAX(inv_scale, 1.0);
+    if (params->no_widening)
+        inv_scale = 1.0;
+    struct pl_filter_config cfg = params->filter;
+    cfg.antiring = PLB_DEF(cfg.antiring, params->antiring);
+    cfg.blur = PLB_DEF(cfg.blur, 1.0f) * inv_scale;
+    if (!sampler_update(sh, obj, &cfg, false))
+        return false;
+
+    sh->src = PLB_SRC_ORTHO;
+    struct plb_ortho_launch *p = &sh->ortho;
+    p->src = si.tex;
+    p->rect = si.rect;
+    p->lut = obj->dev_lut;
+    p->lut_entries = SCALER_LUT_SIZE;
+    p->row_size = obj->filter->row_size;
+    p->row_stride = obj->filter->row_stride;
+    p->use_linear = obj->filter->radius == obj->filter->radius_zero;
+    p->antiring = cfg.antiring;
+    p->ratio = ratio;
+    p->scale = si.scale;
+    p->comp_mask = si.mask;
+    p->pass = pass;
+    sh->px.coord_mode = coord_mode(sh);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// colour ops
+// ---------------------------------------------------------------------------------------
+
+// decimal text of printf("%f"), which is what the reference's GLSL carries for these
+static double glsl6(double x)
+{
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%f", x);
+    return strtod(buf, NULL);
+}
+
+static const float PQ_M1 = 2610./4096 * 1./4, PQ_M2 = 2523./4096 * 128, PQ_C1 = 3424./4096,
+                   PQ_C2 = 2413./4096 * 32, PQ_C3 = 2392./4096 * 32;
+static const float HLG_A = 0.17883277, HLG_B = 0.28466892, HLG_C = 0.55991073;
+static const float HLG_REF = 1000.0 / PL_COLOR_SDR_WHITE;
+
+void plb_pq_literal(struct plb_pq_consts *q)
+{
+    q->m1 = (float) glsl6(PQ_M1);
+    q->m2 = (float) glsl6(PQ_M2);
+    q->c1 = (float) glsl6(PQ_C1);
+    q->c2 = (float) glsl6(PQ_C2);
+    q->c3 = (float) glsl6(PQ_C3);
+    q->inv_m1 = (float) (1.0 / glsl6(PQ_M1));
+    q->inv_m2 = (float) (1.0 / glsl6(PQ_M2));
+    q->to_pq = (float) glsl6(PL_COLOR_SDR_WHITE / 10000);
+    q->from_pq = (float) glsl6(10000 / PL_COLOR_SDR_WHITE);
+    q->inv_from_pq = (float) (1.0 / glsl6(10000 / PL_COLOR_SDR_WHITE));
+    q->hlg_a = (float) glsl6(HLG_A);
+    q->hlg_b = (float) glsl6(HLG_B);
+    q->hlg_c = (float) glsl6(HLG_C);
+    q->hlg_inv_a = (float) (1.0 / glsl6(HLG_A));
+    q->inv_2pi = (float) glsl6(0.5f / M_PI);
+}
+
+void pl_shader_set_alpha(pl_shader sh, struct pl_color_repr *repr, enum pl_alpha_mode mode)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_set_alpha"))
+        return;
+    const bool src_has_alpha = repr->alpha == PL_ALPHA_INDEPENDENT ||
+                               repr->alpha == PL_ALPHA_PREMULTIPLIED;
+    const bool dst_not_premul = mode == PL_ALPHA_INDEPENDENT || mode == PL_ALPHA_NONE;
+    if (repr->alpha == PL_ALPHA_PREMULTIPLIED && dst_not_premul) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_ALPHA);
+        if (!op)
+            return;
+        op->u.alpha.from = PL_ALPHA_PREMULTIPLIED;
+        op->u.alpha.to = PL_ALPHA_INDEPENDENT;
+        repr->alpha = PL_ALPHA_INDEPENDENT;
+    }
+    if (repr->alpha == PL_ALPHA_INDEPENDENT && mode == PL_ALPHA_PREMULTIPLIED) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_ALPHA);
+        if (!op)
+            return;
+        op->u.alpha.from = PL_ALPHA_INDEPENDENT;
+        op->u.alpha.to = PL_ALPHA_PREMULTIPLIED;
+        repr->alpha = PL_ALPHA_PREMULTIPLIED;
+    }
+    if (src_has_alpha && mode == PL_ALPHA_NONE) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_ALPHA);
+        if (!op)
+            return;
+        op->u.alpha.from = PL_ALPHA_UNKNOWN; // "color.a = 1.0"
+        op->u.alpha.to = PL_ALPHA_NONE;
+        repr->alpha = PL_ALPHA_NONE;
+    }
+}
+
+static void push_matrix(pl_shader sh, const pl_transform3x3 *tr)
+{
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_MATRIX);
+    if (!op)
+        return;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            op->u.matrix.m[3*i + j] = tr->mat.m[i][j];
+        op->u.matrix.c[i] = tr->c[i];
+    }
+    op->u.matrix.has_c = 1;
+}
+
+extern void plb_record_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data);
+
+void pl_shader_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_dovi_reshape") || !data)
+        return;
+    plb_record_dovi_reshape(sh, data);
+}
+
+void pl_shader_decode_color(pl_shader sh, struct pl_color_repr *repr,
+                            const struct pl_color_adjustment *params)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_decode_color"))
+        return;
+    if (repr->sys == PL_COLOR_SYSTEM_DOLBYVISION) {
+        if (!repr->dovi) {
+            plb_shader_fail(sh, "pl_shader_decode_color: Dolby Vision without metadata");
+            return;
+        }
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
+        if (!op)
+            return;
+        op->u.scale.s = pl_color_repr_normalize(repr); // colorspace.c:287 (updates repr)
+        pl_shader_dovi_reshape(sh, repr->dovi);
+    }
+
+    const enum pl_color_system orig_sys = repr->sys;
+    const struct pl_dovi_metadata *dovi = repr->dovi;
+    pl_transform3x3 tr = pl_color_repr_decode(repr, params);
+    if (memcmp(&tr, &pl_transform3x3_identity, sizeof(tr)))
+        push_matrix(sh, &tr);
+
+    switch (orig_sys) {
+    case PL_COLOR_SYSTEM_BT_2020_C:
+    case PL_COLOR_SYSTEM_BT_2100_PQ:
+    case PL_COLOR_SYSTEM_BT_2100_HLG: {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_DECODE_SPECIAL);
+        if (op)
+            op->u.special.sys = orig_sys;
+        break;
+    }
+    case PL_COLOR_SYSTEM_DOLBYVISION: {
+        // PQ EOTF -> (hard-coded HPE LMS->RGB * dovi->linear) -> PQ OETF, colorspace.c:392-422
+        extern void plb_record_dovi_lms(pl_shader sh, const struct pl_dovi_metadata *data);
+        plb_record_dovi_lms(sh, dovi);
+        break;
+    }
+    default:
+        break;
+    }
+
+    if (params && params->gamma == 0) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
+        if (op)
+            op->u.scale.s = 0.0f;
+    } else if (params && params->gamma != 1) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_GAMMA);
+        if (op)
+            op->u.gamma.g = 1 / params->gamma;
+    }
+    pl_shader_set_alpha(sh, repr, PL_ALPHA_INDEPENDENT);
+}
+
+void pl_shader_encode_color(pl_shader sh, const struct pl_color_repr *repr)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_encode_color"))
+        return;
+    if (repr->alpha == PL_ALPHA_PREMULTIPLIED) {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_ALPHA);
+        if (!op)
+            return;
+        op->u.alpha.from = PL_ALPHA_INDEPENDENT;
+        op->u.alpha.to = PL_ALPHA_PREMULTIPLIED;
+    }
+    switch (repr->sys) {
+    case PL_COLOR_SYSTEM_BT_2020_C:
+    case PL_COLOR_SYSTEM_BT_2100_PQ:
+    case PL_COLOR_SYSTEM_BT_2100_HLG: {
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_ENCODE_SPECIAL);
+        if (op)
+            op->u.special.sys = repr->sys;
+        break;
+    }
+    case PL_COLOR_SYSTEM_DOLBYVISION:
+        plb_shader_fail(sh, "Cannot un-apply dolbyvision yet (no inverse reshaping)!");
+        return;
+    default:
+        break;
+    }
+    // skip when the representation is plain full-range RGB at native depth (:546-552)
+    bool skip = true;
+    skip &= PLB_DEF(repr->sys, PL_COLOR_SYSTEM_RGB) == PL_COLOR_SYSTEM_RGB;
+    skip &= PLB_DEF(repr->levels, PL_COLOR_LEVELS_FULL) == PL_COLOR_LEVELS_FULL;
+    skip &= !repr->bits.sample_depth || !repr->bits.color_depth ||
+            repr->bits.sample_depth == repr->bits.color_depth;
+    skip &= !repr->bits.bit_shift;
+    if (!skip) {
+        struct pl_color_repr copy = *repr;
+        pl_transform3x3 tr = pl_color_repr_decode(&copy, NULL);
+        pl_transform3x3_invert(&tr);
+        push_matrix(sh, &tr);
+    }
+}
+
+static void fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp, bool delin)
+{
+    memset(t, 0, sizeof(*t));
+    t->trc = csp->transfer;
+    pl_color_space_nominal_luma_ex(pl_nominal_luma_params(
+        .color = csp,
+        .metadata = PL_HDR_METADATA_HDR10,
+        .scaling = PL_HDR_NORM,
+        .out_min = &t->csp_min,
+        .out_max = &t->csp_max,
+    ));
+    const pl_matrix3x3 rgb2xyz = pl_get_rgb2xyz_matrix(pl_raw_primaries_get(csp->primaries));
+    for (int i = 0; i < 3; i++)
+        t->luma[i] = rgb2xyz.m[1][i];
+    switch (csp->transfer) {
+    case PL_COLOR_TRC_BT_1886: {
+        const float lb = powf(t->csp_min, 1/2.4f);
+        const float lw = powf(t->csp_max, 1/2.4f);
+        const float a = powf(lw - lb, 2.4f);
+        const float b = lb / (lw - lb);
+        t->a = delin ? (float) (1.0 / a) : a;
+        t->b = b;
+        break;
+    }
+    case PL_COLOR_TRC_HLG: {
+        const float y = 1.2f * powf(1.111f, log2f(t->csp_max / HLG_REF));
+        const float b = sqrtf(3 * powf(t->csp_min / t->csp_max, 1 / y));
+        t->a = y;
+        t->b = b;
+        break;
+    }
+    case PL_COLOR_TRC_SCRGB:
+        t->a = delin ? (float) glsl6(PL_COLOR_SDR_WHITE / PL_COLOR_SCRGB_WHITE)
+                     : (float) glsl6(PL_COLOR_SCRGB_WHITE / PL_COLOR_SDR_WHITE);
+        break;
+    default:
+        break;
+    }
+    if (delin) {
+        t->black_scaled = pl_color_space_is_black_scaled(csp) &&
+                          csp->transfer != PL_COLOR_TRC_HLG &&
+                          (t->csp_max != 1 || t->csp_min != 0);
+    }
+}
+
+static bool trc_supported(pl_shader sh, enum pl_color_transfer trc)
+{
+    switch (trc) {
+    case PL_COLOR_TRC_V_LOG:
+    case PL_COLOR_TRC_S_LOG1:
+    case PL_COLOR_TRC_S_LOG2:
+        plb_shader_fail(sh, "camera log transfer %d is not implemented on the CUDA backend",
+                        (int) trc);
+        return false;
+    default:
+        return true;
+    }
+}
+
+void plb_record_linearize(pl_shader sh, const struct pl_color_space *csp)
+{
+    if (csp->transfer == PL_COLOR_TRC_LINEAR || !trc_supported(sh, csp->transfer))
+        return;
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_LINEARIZE);
+    if (op)
+        fill_trc(&op->u.trc, csp, false);
+}
+
+void plb_record_delinearize(pl_shader sh, const struct pl_color_space *csp)
+{
+    if (csp->transfer == PL_COLOR_TRC_LINEAR || !trc_supported(sh, csp->transfer))
+        return;
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_DELINEARIZE);
+    if (op)
+        fill_trc(&op->u.trc, csp, true);
+}
+
+void plb_fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp, bool delin)
+{
+    fill_trc(t, csp, delin);
+}
+
+void pl_shader_linearize(pl_shader sh, const struct pl_color_space *csp)
+{
+    if (plb_shader_require_color(sh, "pl_shader_linearize"))
+        plb_record_linearize(sh, csp);
+}
+
+void pl_shader_delinearize(pl_shader sh, const struct pl_color_space *csp)
+{
+    if (plb_shader_require_color(sh, "pl_shader_delinearize"))
+        plb_record_delinearize(sh, csp);
+}
+
+const struct pl_sigmoid_params pl_sigmoid_default_params = { PL_SIGMOID_DEFAULTS };
+
+static void push_sigmoid(pl_shader sh, const struct pl_sigmoid_params *params, int kind)
+{
+    params = params ? params : &pl_sigmoid_default_params;
+    const float center = PLB_DEF(params->center, pl_sigmoid_default_params.center);
+    const float slope = PLB_DEF(params->slope, pl_sigmoid_default_params.slope);
+    struct plb_color_op *op = plb_shader_push_op(sh, kind);
+    if (!op)
+        return;
+    op->u.sigmoid.center = center;
+    op->u.sigmoid.slope = slope;
+    op->u.sigmoid.offset = 1.0 / (1 + expf(slope * center));
+    op->u.sigmoid.scale = 1.0 / (1 + expf(slope * (center - 1))) - op->u.sigmoid.offset;
+}
+
+void pl_shader_sigmoidize(pl_shader sh, const struct pl_sigmoid_params *params)
+{
+    if (plb_shader_require_color(sh, "pl_shader_sigmoidize"))
+        push_sigmoid(sh, params, PLB_OP_SIGMOID);
+}
+
+void pl_shader_unsigmoidize(pl_shader sh, const struct pl_sigmoid_params *params)
+{
+    if (plb_shader_require_color(sh, "pl_shader_unsigmoidize"))
+        push_sigmoid(sh, params, PLB_OP_UNSIGMOID);
+}
+
+// ---------------------------------------------------------------------------------------
+// dithering (dithering.c:109-274)
+// ---------------------------------------------------------------------------------------
+
+const struct pl_dither_params pl_dither_default_params = { PL_DITHER_DEFAULTS };
+
+static float approx_gamma(enum pl_color_transfer trc)
+{
+    switch (trc) {
+    case PL_COLOR_TRC_UNKNOWN:
+    case PL_COLOR_TRC_LINEAR:
+    case PL_COLOR_TRC_SCRGB:     return 1.0f;
+    case PL_COLOR_TRC_PRO_PHOTO:
+    case PL_COLOR_TRC_GAMMA18:   return 1.8f;
+    case PL_COLOR_TRC_GAMMA20:   return 2.0f;
+    case PL_COLOR_TRC_GAMMA24:   return 2.4f;
+    case PL_COLOR_TRC_GAMMA26:
+    case PL_COLOR_TRC_ST428:     return 2.6f;
+    case PL_COLOR_TRC_GAMMA28:   return 2.8f;
+    case PL_COLOR_TRC_SRGB:
+    case PL_COLOR_TRC_BT_1886:
+    case PL_COLOR_TRC_GAMMA22:   return 2.2f;
+    default:                     return 2.0f; // PQ, HLG, camera logs
+    }
+}
+
+void pl_shader_dither(pl_shader sh, int new_depth, pl_shader_obj *dither_state,
+                      const struct pl_dither_params *params)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_dither"))
+        return;
+    if (new_depth <= 0 || new_depth > 256) {
+        PLB_WARN(sh->log, "Invalid dither depth: %d.. ignoring", new_depth);
+        return;
+    }
+    params = params ? params : &pl_dither_default_params;
+    if (params->lut_size < 0 || params->lut_size > 8) {
+        plb_shader_fail(sh, "Invalid `lut_size` specified: %d", params->lut_size);
+        return;
+    }
+    if (new_depth >= 64) {
+        // (1 << depth) - 1 is not representable; the reference's GLSL would overflow too
+        PLB_WARN(sh->log, "dither depth %d too large.. ignoring", new_depth);
+        return;
+    }
+
+    enum pl_dither_method method = params->method;
+    const bool is_lut = method == PL_DITHER_BLUE_NOISE || method == PL_DITHER_ORDERED_LUT;
+    struct plb_dither_obj *obj = NULL;
+    int lut_size = 0;
+    if (is_lut) {
+        if (!dither_state) {
+            PLB_WARN(sh->log, "LUT-based dither method specified but no dither state object "
+                     "given, falling back to non-LUT based methods.");
+            method = PL_DITHER_ORDERED_FIXED;
+        } else {
+            obj = plb_shader_obj(sh, dither_state, PLB_OBJ_DITHER);
+            if (!obj)
+                return;
+            lut_size = 1 << PLB_DEF(params->lut_size, pl_dither_default_params.lut_size);
+            if (!obj->dev_lut || obj->lut_size != lut_size || obj->method != (int) method) {
+                pl_gpu gpu = sh->params.gpu;
+                float *tmp = malloc(sizeof(float) * lut_size * lut_size);
+                if (method == PL_DITHER_ORDERED_LUT)
+                    pl_generate_bayer_matrix(tmp, lut_size);
+                else
+                    pl_generate_blue_noise(tmp, lut_size);
+                plb_dev_free(gpu, obj->dev_lut);
+                obj->dev_lut = plb_dev_alloc(gpu, sizeof(float) * lut_size * lut_size);
+                bool ok = obj->dev_lut &&
+                          plb_dev_upload(gpu, obj->dev_lut, tmp, sizeof(float) * lut_size * lut_size);
+                free(tmp);
+                if (!ok) {
+                    plb_shader_fail(sh, "failed uploading dither matrix");
+                    return;
+                }
+                obj->lut_size = lut_size;
+                obj->method = method;
+            }
+        }
+    }
+
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_DITHER);
+    if (!op)
+        return;
+    struct plb_op_dither *d = &op->u.dither;
+    d->method = method;
+    d->lut = obj ? obj->dev_lut : NULL;
+    d->lut_size = lut_size;
+    d->new_depth = new_depth;
+    d->temporal = params->temporal;
+    d->frame_index = sh->params.index;
+    d->gamma = approx_gamma(params->transfer);
+    d->rot[0] = 1; d->rot[1] = 0; d->rot[2] = 0; d->rot[3] = 1;
+    if (params->temporal) {
+        // dithering.c:185-199; mat2 built from row-major floats, uploaded column-major
+        const int phase = sh->params.index % 8;
+        const float r = phase * (M_PI / 2);
+        const float m = phase < 4 ? 1 : -1;
+        d->rot[0] = cos(r);
+        d->rot[1] = -sin(r);
+        d->rot[2] = sin(r) * m;
+        d->rot[3] = cos(r) * m;
+    }
+}

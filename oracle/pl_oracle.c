@@ -1,0 +1,544 @@
+/*
+ * TEST INFRASTRUCTURE — see pl_oracle.h for scope, conventions and pinning status.
+ * Part 1: coordinates, samplers (polar / ortho / direct), PRNG, debanding, storage rounding.
+ *
+ * Compile: gcc -std=c11 -O2 -fopenmp -ffp-contract=off -fno-math-errno -fPIC -shared
+ */
+#define _GNU_SOURCE
+#include "pl_oracle.h"
+
+#include <math.h>
+#include <stdbool.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// GLSL helpers with the rounding conventions documented in pl_oracle.h
+// ------------------------------------------------------------------------------------------
+
+static inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+static inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+static inline float fractf(float x) { return x - floorf(x); }
+static inline float lengthf2(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
+static inline int clampi(int x, int lo, int hi) { return x < lo ? lo : x > hi ? hi : x; }
+static inline float smoothstepf(float e0, float e1, float x)
+{
+    float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return t * t * (3.0f - 2.0f * t);
+}
+
+// 1-D linear LUT, array form of src/shaders/lut.c:700-715
+static inline float lut1d_linear(const float *lut, int n, float x)
+{
+    float fpos = clampf(x, 0.0f, 1.0f) * (float) (n - 1);
+    float fbase = floorf(fpos), fceil = ceilf(fpos);
+    float fc = fpos - fbase;
+    return mixf(lut[(int) fbase], lut[(int) fceil], fc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pixel coordinates. sh_bind (src/shaders.c:513-571) turns the source rect into a vec2
+// vertex attribute whose corner values are rect/tex_size; the compute path of
+// src/dispatch.c:1038-1062 evaluates it per invocation as
+//   frag_map = out_scale * (gid + 0.5);  pos = mix(mix(p0,p1,fx), mix(p2,p3,fx), fy)
+// Returns t = pos * size - 0.5 (texel-space position of the sample, minus half), which is
+// what every sampler derives its base texel and sub-texel fraction from.
+// ------------------------------------------------------------------------------------------
+
+struct coord_ctx {
+    int mode;
+    float px0, px1, py0, py1; // corner values (literal mode)
+    float osx, osy;           // out_scale
+    float sizex, sizey;
+    float ptx, pty;
+    double dx0, dxs, dy0, dys; // exact mode: t = d0 + ds*(gid+0.5) - 0.5
+};
+
+static struct coord_ctx coord_init(int mode, const struct orc_tex *src, struct orc_rect rc,
+                                   int dw, int dh)
+{
+    struct coord_ctx c = { .mode = mode };
+    float sx = (float) (1.0 / src->w), sy = (float) (1.0 / src->h);
+    c.ptx = sx;
+    c.pty = sy;
+    c.px0 = sx * rc.x0; c.px1 = sx * rc.x1;
+    c.py0 = sy * rc.y0; c.py1 = sy * rc.y1;
+    c.osx = (float) (1.0 / dw);
+    c.osy = (float) (1.0 / dh);
+    c.sizex = (float) src->w;
+    c.sizey = (float) src->h;
+    c.dx0 = rc.x0; c.dxs = ((double) rc.x1 - rc.x0) / dw;
+    c.dy0 = rc.y0; c.dys = ((double) rc.y1 - rc.y0) / dh;
+    return c;
+}
+
+// normalised position (pos) of invocation (gx, gy)
+static inline void coord_pos(const struct coord_ctx *c, int gx, int gy, float *posx, float *posy)
+{
+    if (c->mode == ORC_COORD_LITERAL) {
+        float fx = c->osx * ((float) gx + 0.5f);
+        float fy = c->osy * ((float) gy + 0.5f);
+        float mx = mixf(c->px0, c->px1, fx);
+        float my0 = c->py0, my1 = c->py1;
+        *posx = mixf(mx, mx, fy);
+        *posy = mixf(mixf(my0, my0, fx), mixf(my1, my1, fx), fy);
+    } else {
+        *posx = (float) ((c->dx0 + c->dxs * (gx + 0.5)) / c->sizex);
+        *posy = (float) ((c->dy0 + c->dys * (gy + 0.5)) / c->sizey);
+    }
+}
+
+// t = pos*size - 0.5 split into integer base texel and fraction
+static inline void coord_texel(const struct coord_ctx *c, int gx, int gy,
+                               int *jx, int *jy, float *fx, float *fy)
+{
+    if (c->mode == ORC_COORD_LITERAL) {
+        float px, py;
+        coord_pos(c, gx, gy, &px, &py);
+        float tx = px * c->sizex - 0.5f, ty = py * c->sizey - 0.5f;
+        float bx = floorf(tx), by = floorf(ty);
+        *jx = (int) bx; *jy = (int) by;
+        *fx = tx - bx;  *fy = ty - by;
+    } else {
+        double tx = c->dx0 + c->dxs * (gx + 0.5) - 0.5;
+        double ty = c->dy0 + c->dys * (gy + 0.5) - 0.5;
+        double bx = floor(tx), by = floor(ty);
+        *jx = (int) bx; *jy = (int) by;
+        *fx = (float) (tx - bx); *fy = (float) (ty - by);
+    }
+}
+
+static inline const float *texel(const struct orc_tex *t, int x, int y)
+{
+    x = clampi(x, 0, t->w - 1);
+    y = clampi(y, 0, t->h - 1);
+    return t->data + ((size_t) y * t->w + x) * t->comps;
+}
+
+// textureLod with NEAREST at normalised coordinate (u, v): floor(u*size), clamp-to-edge
+static inline const float *tex_nearest(const struct orc_tex *t, float u, float v)
+{
+    int x = (int) floorf(u * (float) t->w), y = (int) floorf(v * (float) t->h);
+    return texel(t, x, y);
+}
+
+// textureLod with LINEAR
+static inline void tex_linear(const struct orc_tex *t, float u, float v, float out[4])
+{
+    float tx = u * (float) t->w - 0.5f, ty = v * (float) t->h - 0.5f;
+    float bx = floorf(tx), by = floorf(ty);
+    float fx = tx - bx, fy = ty - by;
+    int x = (int) bx, y = (int) by;
+    const float *a = texel(t, x, y), *b = texel(t, x + 1, y);
+    const float *c = texel(t, x, y + 1), *d = texel(t, x + 1, y + 1);
+    for (int k = 0; k < t->comps; k++)
+        out[k] = mixf(mixf(a[k], b[k], fx), mixf(c[k], d[k], fx), fy);
+}
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_sample_polar — src/shaders/sampling.c:587-912; per-tap body polar_sample :503-558
+// ------------------------------------------------------------------------------------------
+
+void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
+                      const struct orc_polar_params *p, float *dst)
+{
+    const struct coord_ctx cc = coord_init(p->coord_mode, src, rect, dw, dh);
+    const int bound = (int) ceilf(p->radius);        // sampling.c:661
+    const float radius = p->radius;
+    const float inv_radius = 1.0f / radius;          // `d * 1.0 / radius`, constant-folded
+    const bool use_ar_global = p->antiring > 0.0f;
+    const float ar_radius = p->radius_zero;
+
+    // Compile-time tap list (sampling.c:776-783 with the culling of :508-522)
+    int ntaps = 0;
+    int tap_x[256], tap_y[256];
+    unsigned char tap_guard[256], tap_ar[256];
+    for (int y = 1 - bound; y <= bound; y++) {
+        for (int x = 1 - bound; x <= bound; x++) {
+            int yy = y > 0 ? y - 1 : y;
+            int xx = x > 0 ? x - 1 : x;
+            float dmin = sqrt(xx * xx + yy * yy);
+            if (dmin >= radius)
+                continue;
+            tap_x[ntaps] = x;
+            tap_y[ntaps] = y;
+            tap_guard[ntaps] = dmin >= radius - M_SQRT2;
+            tap_ar[ntaps] = use_ar_global && dmin < ar_radius;
+            ntaps++;
+        }
+    }
+
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < dh; gy++) {
+        for (int gx = 0; gx < dw; gx++) {
+            int jx, jy;
+            float fx, fy;
+            coord_texel(&cc, gx, gy, &jx, &jy, &fx, &fy);
+            float color[4] = {0, 0, 0, 0};
+            float wsum = 0.0f;
+            float ar[4][2] = {{0}}, wwsum[4][2] = {{0}};
+            for (int t = 0; t < ntaps; t++) {
+                float ox = (float) tap_x[t], oy = (float) tap_y[t];
+                float d = lengthf2(ox - fx, oy - fy);
+                if (tap_guard[t] && !(d < radius))
+                    continue;
+                float w = lut1d_linear(p->lut, p->lut_entries, d * inv_radius);
+                wsum += w;
+                const float *c = texel(src, jx + tap_x[t], jy + tap_y[t]);
+                for (int k = 0; k < 4; k++) {
+                    if (!(p->comp_mask & (1 << k)) || k >= src->comps)
+                        continue;
+                    color[k] = fmaf(w, c[k], color[k]);
+                    if (tap_ar[t] && d <= ar_radius) {
+                        // anti-ringing accumulators, sampling.c:539-555
+                        float cc0 = 1.0f - p->scale * c[k], cc1 = p->scale * c[k];
+                        float ww0 = cc0 + 0.10f, ww1 = cc1 + 0.10f;
+                        for (int i = 0; i < 5; i++) {
+                            ww0 = ww0 * ww0;
+                            ww1 = ww1 * ww1;
+                        }
+                        ww0 = w * ww0;
+                        ww1 = w * ww1;
+                        ar[k][0] = fmaf(ww0, cc0, ar[k][0]);
+                        ar[k][1] = fmaf(ww1, cc1, ar[k][1]);
+                        wwsum[k][0] += ww0;
+                        wwsum[k][1] += ww1;
+                    }
+                }
+            }
+
+            // sampling.c:896-908
+            float norm = p->scale / wsum;
+            float *o = dst + ((size_t) gy * dw + gx) * 4;
+            for (int k = 0; k < 4; k++) {
+                bool have = (p->comp_mask & (1 << k)) && k < src->comps;
+                float v = norm * color[k];
+                if (have && use_ar_global) {
+                    float wx = ar[k][0] / wwsum[k][0], wy = ar[k][1] / wwsum[k][1];
+                    wx = 1.0f - wx;
+                    float w = clampf(v, wx, wy);
+                    if (wx > wy)
+                        w = wx * 0.5f + wy * 0.5f; // dot(ww, vec2(0.5))
+                    v = mixf(v, w, p->antiring);
+                }
+                o[k] = have ? v : 0.0f;
+            }
+            if (!(p->comp_mask & 8))
+                o[3] = 1.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_sample_ortho2 — sampling.c:950-1104
+// The weights texture is rgba32f, width = row_stride/4, height = 256, sampled LINEARly at
+// (float(n/4)/denom, fcoord): x hits texel centres exactly, y interpolates between phases.
+// ------------------------------------------------------------------------------------------
+
+static inline void ortho_weights(const struct orc_ortho_params *p, int quad, float fcoord,
+                                 float ws[4])
+{
+    // LUT position macro of lut.c:285-295 along y: texel-space = fcoord * (n-1)
+    int width = p->row_stride / 4;
+    (void) width;
+    float fpos = clampf(fcoord, 0.0f, 1.0f) * (float) (p->lut_entries - 1);
+    float fbase = floorf(fpos), fceil = ceilf(fpos);
+    float fc = fpos - fbase;
+    const float *r0 = p->lut + (size_t) fbase * p->row_stride + 4 * quad;
+    const float *r1 = p->lut + (size_t) fceil * p->row_stride + 4 * quad;
+    for (int k = 0; k < 4; k++)
+        ws[k] = mixf(r0[k], r1[k], fc);
+}
+
+void orc_sample_ortho(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
+                      const struct orc_ortho_params *p, float *dst)
+{
+    const struct coord_ctx cc = coord_init(p->coord_mode, src, rect, dw, dh);
+    const int N = p->row_size;
+    const int dirx = p->pass == 1, diry = p->pass == 0;
+    const bool use_ar = p->antiring > 0 && p->ratio > 1.0f && !p->use_linear;
+
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < dh; gy++) {
+        for (int gx = 0; gx < dw; gx++) {
+            float posx, posy;
+            coord_pos(&cc, gx, gy, &posx, &posy);
+            // fcoord2 = fract(pos*size - 0.5); fcoord = dot(fcoord2, dir)
+            float f2x = fractf(posx * cc.sizex - 0.5f), f2y = fractf(posy * cc.sizey - 0.5f);
+            float fcoord = f2x * (float) dirx + f2y * (float) diry;
+            float ptx = cc.ptx * (float) dirx, pty = cc.pty * (float) diry;
+            float off0 = (float) (N / 2 - 1);
+            float basex = posx - fcoord * ptx - ptx * off0;
+            float basey = posy - fcoord * pty - pty * off0;
+            float ca[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, lo[4] = {1e9f, 1e9f, 1e9f, 1e9f};
+            float ws[4] = {0};
+            for (int n = 0; n < N; n += p->use_linear ? 2 : 1) {
+                if (n % 4 == 0)
+                    ortho_weights(p, n / 4, fcoord, ws);
+                float off = (float) n;
+                float c[4] = {0, 0, 0, 0};
+                float u, v;
+                if (p->use_linear) {
+                    off += ws[n % 4 + 1];
+                    u = basex + ptx * off;
+                    v = basey + pty * off;
+                    tex_linear(src, u, v, c);
+                } else {
+                    u = basex + ptx * off;
+                    v = basey + pty * off;
+                    // setup_src(LINEAR): the texture is bound with linear filtering, but the
+                    // coordinate sits on a texel centre along `dir` and on pos along the
+                    // other axis, which for the 1:1 axis is also a texel centre
+                    tex_linear(src, u, v, c);
+                }
+                if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
+                    for (int k = 0; k < src->comps; k++) {
+                        lo[k] = fminf(lo[k], c[k]);
+                        hi[k] = fmaxf(hi[k], c[k]);
+                    }
+                }
+                for (int k = 0; k < src->comps; k++)
+                    ca[k] = fmaf(ws[n % 4], c[k], ca[k]);
+            }
+            float *o = dst + ((size_t) gy * dw + gx) * 4;
+            o[0] = o[1] = o[2] = 0.0f;
+            o[3] = 1.0f;
+            for (int k = 0; k < 4; k++) {
+                if (!(p->comp_mask & (1 << k)) || k >= src->comps)
+                    continue;
+                float v = ca[k];
+                if (use_ar)
+                    v = mixf(v, clampf(v, lo[k], hi[k]), p->antiring);
+                o[k] = p->scale * v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_sample_direct / nearest / bilinear — sampling.c:277-340:
+//   color = scale * textureLod(src_tex, pos, 0.0)
+// ------------------------------------------------------------------------------------------
+
+void orc_sample_direct(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
+                       int linear, float scale, int coord_mode, float *dst)
+{
+    const struct coord_ctx cc = coord_init(coord_mode, src, rect, dw, dh);
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < dh; gy++) {
+        for (int gx = 0; gx < dw; gx++) {
+            float posx, posy;
+            coord_pos(&cc, gx, gy, &posx, &posy);
+            // GLSL texture() returns (0,0,0,1) for missing components
+            float c[4] = {0, 0, 0, 1};
+            if (linear) {
+                tex_linear(src, posx, posy, c);
+            } else {
+                const float *t = tex_nearest(src, posx, posy);
+                for (int k = 0; k < src->comps; k++)
+                    c[k] = t[k];
+            }
+            float *o = dst + ((size_t) gy * dw + gx) * 4;
+            for (int k = 0; k < 4; k++)
+                o[k] = scale * c[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sh_prng — src/shaders.c:965-998 (pcg3d). float(0xFFFFFFFFu) rounds to 2^32.
+// ------------------------------------------------------------------------------------------
+
+void orc_prng(uint32_t s[3], float out[3])
+{
+    for (int i = 0; i < 3; i++)
+        s[i] = 1664525u * s[i] + 1013904223u;
+    s[0] += s[1] * s[2];
+    s[1] += s[2] * s[0];
+    s[2] += s[0] * s[1];
+    for (int i = 0; i < 3; i++)
+        s[i] ^= s[i] >> 16;
+    s[0] += s[1] * s[2];
+    s[1] += s[2] * s[0];
+    s[2] += s[0] * s[1];
+    const float k = 1.0f / 4294967296.0f;
+    for (int i = 0; i < 3; i++)
+        out[i] = (float) s[i] * k;
+}
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_deband — sampling.c:183-275. The source is bound NEAREST (setup_src(..., NEAREST)),
+// pos is the texel centre of the output pixel (1:1 pass), taps are at pos + pt*(±d.x, ±d.y).
+// ------------------------------------------------------------------------------------------
+
+void orc_deband(const struct orc_tex *src, const struct orc_deband_params *p, float *dst)
+{
+    const int w = src->w, h = src->h;
+    const struct orc_rect full = { 0, 0, (float) w, (float) h };
+    const struct coord_ctx cc = coord_init(ORC_COORD_EXACT, src, full, w, h);
+    uint8_t mask = p->comp_mask & ~0x8u;
+    const float radius = p->radius;
+    const float threshold = p->threshold / (1000 * p->scale); // sampling.c:225-226
+    const float two_pi = (float) (M_PI * 2);                  // printed with %f: 6.283185
+    // "%f" prints 6 decimals; the GLSL literal is 6.283185
+    const float two_pi_lit = 6.283185f;
+    (void) two_pi;
+    const float grain_str = (float) (p->grain / (1000.0 * p->scale));
+
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < h; gy++) {
+        for (int gx = 0; gx < w; gx++) {
+            float posx, posy;
+            coord_pos(&cc, gx, gy, &posx, &posy);
+            float color[4] = {0, 0, 0, 1};
+            const float *c0 = tex_nearest(src, posx, posy);
+            for (int k = 0; k < src->comps; k++)
+                color[k] = c0[k];
+            float *o = dst + ((size_t) gy * w + gx) * 4;
+            if (!mask) {
+                for (int k = 0; k < 4; k++)
+                    o[k] = color[k] * p->scale;
+                continue;
+            }
+
+            // uvec3(gl_FragCoord.xy, index): gl_FragCoord = gid + 0.5, truncated
+            uint32_t state[3] = { (uint32_t) gx, (uint32_t) gy, p->frame_index };
+            float res[4], avg[4];
+            for (int k = 0; k < 4; k++)
+                res[k] = color[k];
+
+            for (int i = 1; i <= p->iterations; i++) {
+                float rnd[3];
+                orc_prng(state, rnd);
+                // d = RAND.xy * vec2(i * radius, 2pi); d = d.x * vec2(cos(d.y), sin(d.y))
+                float dist = rnd[0] * ((float) i * radius);
+                float dir = rnd[1] * two_pi_lit;
+                float dx = dist * cosf(dir), dy = dist * sinf(dir);
+                const float sgx[4] = {+1, -1, -1, +1}, sgy[4] = {+1, +1, -1, -1};
+                for (int k = 0; k < 4; k++)
+                    avg[k] = 0.0f;
+                for (int t = 0; t < 4; t++) {
+                    const float *c = tex_nearest(src, posx + cc.ptx * (sgx[t] * dx),
+                                                      posy + cc.pty * (sgy[t] * dy));
+                    for (int k = 0; k < src->comps; k++)
+                        avg[k] += c[k];
+                }
+                float bound = threshold / (float) i;
+                for (int k = 0; k < 3; k++) {
+                    if (!(mask & (1 << k)))
+                        continue;
+                    float a = avg[k] * 0.25f;
+                    float diff = fabsf(res[k] - a);
+                    res[k] = diff > bound ? res[k] : a; // mix(avg, res, greaterThan(diff, bound))
+                }
+            }
+
+            if (p->grain > 0) {
+                float rnd[3];
+                orc_prng(state, rnd);
+                int idx = 0;
+                for (int k = 0; k < 3; k++) {
+                    if (!(mask & (1 << k)))
+                        continue;
+                    float bound = p->grain_neutral[idx] / p->scale;
+                    float strength = fminf(fabsf(res[k] - bound), grain_str);
+                    res[k] = fmaf(strength, rnd[idx] - 0.5f, res[k]);
+                    idx++;
+                }
+            }
+
+            for (int k = 0; k < 3; k++) {
+                if (mask & (1 << k))
+                    color[k] = res[k];
+            }
+            for (int k = 0; k < 4; k++)
+                o[k] = color[k] * p->scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Storage rounding
+// ------------------------------------------------------------------------------------------
+
+static inline float round_half(float v) { return (float) (_Float16) v; }
+
+void orc_store_round(float *data, size_t n, int kind, int bits)
+{
+    if (kind == 2)
+        return;
+    const float maxv = (float) ((1u << bits) - 1);
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        if (kind == 0) {
+            data[i] = round_half(data[i]);
+        } else {
+            float c = clampf(data[i], 0.0f, 1.0f);
+            data[i] = rintf(c * maxv) / maxv;
+        }
+    }
+}
+
+void orc_store_unorm(const float *data, size_t n, int bits, uint16_t *out)
+{
+    const float maxv = (float) ((1u << bits) - 1);
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        float c = clampf(data[i], 0.0f, 1.0f); // NaN -> 0 via fmaxf/fminf ordering
+        out[i] = (uint16_t) rintf(c * maxv);
+    }
+}
+
+void orc_store_half(const float *data, size_t n, uint16_t *out)
+{
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        _Float16 hval = (_Float16) data[i];
+        memcpy(&out[i], &hval, 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Double-precision ideal EWA resampler for config C1: weights straight from
+// pl_filter_sample (src/filters.c:82-124), no LUT, no cutoff other than `radius`.
+// ------------------------------------------------------------------------------------------
+
+void orc_polar_ideal(const struct orc_tex *src, int dw, int dh, double radius,
+                     orc_weight_fn fn, void *priv, double *dst)
+{
+    const int bound = (int) ceil(radius);
+    for (int gy = 0; gy < dh; gy++) {
+        for (int gx = 0; gx < dw; gx++) {
+            double tx = (gx + 0.5) * src->w / dw - 0.5, ty = (gy + 0.5) * src->h / dh - 0.5;
+            double bx = floor(tx), by = floor(ty);
+            double fx = tx - bx, fy = ty - by;
+            double acc[4] = {0}, wsum = 0;
+            for (int y = 1 - bound; y <= bound; y++) {
+                for (int x = 1 - bound; x <= bound; x++) {
+                    double d = sqrt((x - fx) * (x - fx) + (y - fy) * (y - fy));
+                    if (d >= radius)
+                        continue;
+                    double w = fn(priv, d);
+                    const float *c = texel(src, (int) bx + x, (int) by + y);
+                    wsum += w;
+                    for (int k = 0; k < src->comps; k++)
+                        acc[k] += w * c[k];
+                }
+            }
+            for (int k = 0; k < src->comps; k++)
+                dst[((size_t) gy * dw + gx) * src->comps + k] = acc[k] / wsum;
+        }
+    }
+}

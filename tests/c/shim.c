@@ -1,0 +1,303 @@
+/*
+ * Test driver for libplacebo_b200: plain C written against the PUBLIC header only, the way
+ * the reference's own tests (src/tests/gpu_tests.c, tests/dummy.c) drive libplacebo. pytest
+ * loads it through ctypes and only passes flat arguments, so no struct layout is ever
+ * duplicated in Python.
+ *
+ *   plt_*   flat wrappers over the host-side T0 API (same source as the reference-side
+ *           hvt_* wrappers in oracle/harvest.c: oracle/t0_flat.inc)
+ *   shim_*  GPU drivers: create gpu/textures, build a pl_shader with the public pl_shader_*
+ *           calls, pl_dispatch_finish it, download
+ */
+#include <libplacebo_b200.h>
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+#define PL_DEF(x, d) ((x) ? (x) : (d))
+
+static pl_log shim_log;
+
+static void log_cb(void *priv, enum pl_log_level level, const char *msg)
+{
+    (void) priv;
+    fprintf(stderr, "[plb:%d] %s\n", (int) level, msg);
+}
+
+static void shim_init(void)
+{
+    if (!shim_log)
+        shim_log = pl_log_create(PL_API_VER, pl_log_params(
+            .log_cb = log_cb,
+            .log_level = getenv("PLB_DEBUG") ? PL_LOG_DEBUG : PL_LOG_WARN,
+        ));
+}
+
+#define T0_FN(n) plt_##n
+#define T0_API API
+#define T0_INIT() shim_init()
+#define T0_LOG shim_log
+#include "../../oracle/t0_flat.inc"
+
+/* ---- gpu / textures ---------------------------------------------------------------------- */
+
+struct shim_ctx {
+    pl_gpu gpu;
+    pl_dispatch dp;
+};
+
+API void *shim_create(int literal_coords)
+{
+    shim_init();
+    pl_gpu gpu = pl_cuda_create(shim_log, pl_cuda_params( .literal_coords = literal_coords ));
+    if (!gpu)
+        return NULL;
+    struct shim_ctx *c = calloc(1, sizeof(*c));
+    c->gpu = gpu;
+    c->dp = pl_dispatch_create(shim_log, gpu);
+    return c;
+}
+
+API void shim_destroy(struct shim_ctx *c)
+{
+    if (!c)
+        return;
+    pl_dispatch_destroy(&c->dp);
+    pl_cuda_destroy(&c->gpu);
+    free(c);
+}
+
+API void shim_set_frame_index(struct shim_ctx *c, int index)
+{
+    pl_dispatch_set_frame_index(c->dp, (uint8_t) index);
+}
+
+API unsigned long long shim_launch_count(struct shim_ctx *c)
+{
+    return pl_cuda_launch_count(c->gpu);
+}
+
+/* data = tightly packed texels or NULL */
+API void *shim_tex_create(struct shim_ctx *c, const char *fmt, int w, int h, const void *data)
+{
+    pl_fmt f = pl_find_named_fmt(c->gpu, fmt);
+    if (!f)
+        return NULL;
+    return (void *) pl_tex_create(c->gpu, pl_tex_params(
+        .w = w,
+        .h = h,
+        .format = f,
+        .sampleable = true,
+        .renderable = true,
+        .storable = true,
+        .host_writable = true,
+        .host_readable = true,
+        .initial_data = data,
+    ));
+}
+
+API void shim_tex_destroy(struct shim_ctx *c, void *tex)
+{
+    pl_tex t = tex;
+    pl_tex_destroy(c->gpu, &t);
+}
+
+API int shim_tex_upload(struct shim_ctx *c, void *tex, const void *data)
+{
+    return pl_tex_upload(c->gpu, pl_tex_transfer_params( .tex = tex, .ptr = (void *) data )) ? 0 : -1;
+}
+
+API int shim_tex_download(struct shim_ctx *c, void *tex, void *out)
+{
+    return pl_tex_download(c->gpu, pl_tex_transfer_params( .tex = tex, .ptr = out )) ? 0 : -1;
+}
+
+API void shim_finish(struct shim_ctx *c) { pl_gpu_finish(c->gpu); }
+
+/* ---- shader drivers ------------------------------------------------------------------------ */
+
+/*
+ * One generic driver: a source stage followed by colour ops, dispatched into `dst`.
+ * src_kind: 0 direct, 1 nearest, 2 bilinear, 3 deband, 4 polar, 5 ortho (one pass)
+ * sargs:    source arguments (see below)
+ * ops:      list of op codes terminated by 0; each op consumes floats from `oargs`
+ *   1 decode_color   sys, levels, sample_depth, color_depth, bit_shift
+ *   2 encode_color   sys, levels, sample_depth, color_depth, bit_shift
+ *   3 linearize      csp[20]
+ *   4 delinearize    csp[20]
+ *   5 color_map      src csp[20], dst csp[20], preset(0 default/1 hq), tone_fn idx (-1 keep),
+ *                    gamut_fn idx (-1 keep), use_state
+ *   6 dither         depth, method, lut_size, temporal, transfer
+ *   7 sigmoidize / 8 unsigmoidize   center, slope
+ *   9 detect_peak    csp[20], hq   (statistics land in out_peak if given)
+ */
+struct shim_objs {
+    pl_shader_obj sampler, cmap, dither;
+};
+
+static struct shim_objs objs; /* persistent across calls so LUT caching paths are exercised */
+
+API void shim_reset_objs(void)
+{
+    pl_shader_obj_destroy(&objs.sampler);
+    pl_shader_obj_destroy(&objs.cmap);
+    pl_shader_obj_destroy(&objs.dither);
+}
+
+API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
+                 const float *sargs, const char *filter_name, const int *ops, const float *oargs,
+                 float *out_peak /* avg_pq, max_pq or NULL */)
+{
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    pl_tex src = src_tex, dst = dst_tex;
+    int ret = -1;
+
+    /* sargs: [0..3] rect (all zero = full), [4] new_w, [5] new_h, [6] components, [7] scale,
+     *        deband: [8] iterations [9] threshold [10] radius [11] grain [12..14] neutral
+     *        scalers: [8] antiring (<0 = filter default) */
+    struct pl_sample_src ssrc = {
+        .tex = src,
+        .rect = { sargs[0], sargs[1], sargs[2], sargs[3] },
+        .new_w = (int) sargs[4],
+        .new_h = (int) sargs[5],
+        .components = (int) sargs[6],
+        .scale = sargs[7],
+    };
+    bool ok = true;
+    switch (src_kind) {
+    case 0: ok = pl_shader_sample_direct(sh, &ssrc); break;
+    case 1: ok = pl_shader_sample_nearest(sh, &ssrc); break;
+    case 2: ok = pl_shader_sample_bilinear(sh, &ssrc); break;
+    case 3: {
+        struct pl_deband_params dp = {
+            .iterations = (int) sargs[8],
+            .threshold = sargs[9],
+            .radius = sargs[10],
+            .grain = sargs[11],
+            .grain_neutral = { sargs[12], sargs[13], sargs[14] },
+        };
+        pl_shader_deband(sh, &ssrc, &dp);
+        break;
+    }
+    case 4:
+    case 5: {
+        const struct pl_filter_config *cfg = pl_find_filter_config(filter_name, 0);
+        if (!cfg)
+            goto done;
+        struct pl_sample_filter_params fp = {
+            .filter = *cfg,
+            .lut = &objs.sampler,
+        };
+        if (sargs[8] >= 0)
+            fp.antiring = sargs[8];
+        ok = src_kind == 4 ? pl_shader_sample_polar(sh, &ssrc, &fp)
+                           : pl_shader_sample_ortho2(sh, &ssrc, &fp);
+        break;
+    }
+    default:
+        goto done;
+    }
+    if (!ok || pl_shader_is_failed(sh))
+        goto done;
+
+    const float *a = oargs;
+    for (; ops && *ops; ops++) {
+        switch (*ops) {
+        case 1:
+        case 2: {
+            struct pl_color_repr repr = {
+                .sys = (int) a[0],
+                .levels = (int) a[1],
+                .bits = { (int) a[2], (int) a[3], (int) a[4] },
+            };
+            a += 5;
+            if (*ops == 1)
+                pl_shader_decode_color(sh, &repr, NULL);
+            else
+                pl_shader_encode_color(sh, &repr);
+            break;
+        }
+        case 3:
+        case 4: {
+            struct pl_color_space csp = csp_from_flat(a);
+            a += CSP_FLOATS;
+            if (*ops == 3)
+                pl_shader_linearize(sh, &csp);
+            else
+                pl_shader_delinearize(sh, &csp);
+            break;
+        }
+        case 5: {
+            struct pl_color_space s = csp_from_flat(a), d = csp_from_flat(a + CSP_FLOATS);
+            a += 2 * CSP_FLOATS;
+            struct pl_color_map_params par = a[0] ? pl_color_map_high_quality_params
+                                                  : pl_color_map_default_params;
+            par.contrast_recovery = 0;
+            if (a[1] >= 0)
+                par.tone_mapping_function = pl_tone_map_functions[(int) a[1]];
+            if (a[2] >= 0)
+                par.gamut_mapping = pl_gamut_map_functions[(int) a[2]];
+            bool use_state = a[3];
+            a += 4;
+            pl_shader_color_map_ex(sh, &par, pl_color_map_args(
+                .src = s,
+                .dst = d,
+                .state = use_state ? &objs.cmap : NULL,
+            ));
+            break;
+        }
+        case 6: {
+            struct pl_dither_params dp = {
+                .method = (int) a[1],
+                .lut_size = (int) a[2],
+                .temporal = a[3],
+                .transfer = (int) a[4],
+            };
+            pl_shader_dither(sh, (int) a[0], &objs.dither, &dp);
+            a += 5;
+            break;
+        }
+        case 7:
+        case 8: {
+            struct pl_sigmoid_params sp = { a[0], a[1] };
+            a += 2;
+            if (*ops == 7)
+                pl_shader_sigmoidize(sh, &sp);
+            else
+                pl_shader_unsigmoidize(sh, &sp);
+            break;
+        }
+        case 9: {
+            struct pl_color_space csp = csp_from_flat(a);
+            bool hq = a[CSP_FLOATS];
+            a += CSP_FLOATS + 1;
+            if (!pl_shader_detect_peak(sh, csp, &objs.cmap,
+                                       hq ? &pl_peak_detect_high_quality_params
+                                          : &pl_peak_detect_default_params))
+                goto done;
+            break;
+        }
+        default:
+            goto done;
+        }
+    }
+    if (pl_shader_is_failed(sh))
+        goto done;
+
+    ok = pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst ));
+    if (ok && out_peak) {
+        struct pl_hdr_metadata md = {0};
+        if (pl_get_detected_hdr_metadata(objs.cmap, &md)) {
+            out_peak[0] = md.avg_pq_y;
+            out_peak[1] = md.max_pq_y;
+        }
+    }
+    ret = ok ? 0 : -2;
+
+done:
+    pl_dispatch_abort(c->dp, &sh);
+    return ret;
+}
