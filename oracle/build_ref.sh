@@ -60,11 +60,11 @@ for f in colorspace custom custom_mpv deinterlacing dithering film_grain film_gr
 done
 [ obj/convert.o -nt "$R/src/convert.cc" ] || g++ -std=c++20 $CF -c "$R/src/convert.cc" -o obj/convert.o &
 wait
-g++ -shared -o libplacebo_ref.so $OBJS obj/convert.o -lm -lpthread
+g++ -shared -Wl,-Bsymbolic -o libplacebo_ref.so $OBJS obj/convert.o -lm -lpthread
 # record where the headers were so harvest.c can be compiled against them
 echo "$CF" > cflags.txt
 echo "build_ref: OK -> $W/libplacebo_ref.so"
 # the harvester shim (our code, compiled against the reference headers in place)
-gcc -std=c11 $CF -shared -o "$W/libplref_harvest.so" "$HERE/harvest.c" -L"$W" -lplacebo_ref \
+gcc -std=c11 $CF -shared -Wl,-Bsymbolic -o "$W/libplref_harvest.so" "$HERE/harvest.c" -L"$W" -lplacebo_ref \
     -Wl,-rpath,'$ORIGIN' -lm -lpthread
 echo "build_ref: OK -> $W/libplref_harvest.so"

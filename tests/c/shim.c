@@ -44,9 +44,15 @@ static void shim_init(void)
 
 /* ---- gpu / textures ---------------------------------------------------------------------- */
 
+/* shader state objects persist across calls so that LUT caching paths are exercised */
+struct shim_objs {
+    pl_shader_obj sampler, cmap, dither;
+};
+
 struct shim_ctx {
     pl_gpu gpu;
     pl_dispatch dp;
+    struct shim_objs objs;
 };
 
 API void *shim_create(int literal_coords)
@@ -61,10 +67,13 @@ API void *shim_create(int literal_coords)
     return c;
 }
 
+API void shim_reset_objs(struct shim_ctx *c);
+
 API void shim_destroy(struct shim_ctx *c)
 {
     if (!c)
         return;
+    shim_reset_objs(c);
     pl_dispatch_destroy(&c->dp);
     pl_cuda_destroy(&c->gpu);
     free(c);
@@ -134,17 +143,11 @@ API void shim_finish(struct shim_ctx *c) { pl_gpu_finish(c->gpu); }
  *   7 sigmoidize / 8 unsigmoidize   center, slope
  *   9 detect_peak    csp[20], hq   (statistics land in out_peak if given)
  */
-struct shim_objs {
-    pl_shader_obj sampler, cmap, dither;
-};
-
-static struct shim_objs objs; /* persistent across calls so LUT caching paths are exercised */
-
-API void shim_reset_objs(void)
+API void shim_reset_objs(struct shim_ctx *c)
 {
-    pl_shader_obj_destroy(&objs.sampler);
-    pl_shader_obj_destroy(&objs.cmap);
-    pl_shader_obj_destroy(&objs.dither);
+    pl_shader_obj_destroy(&c->objs.sampler);
+    pl_shader_obj_destroy(&c->objs.cmap);
+    pl_shader_obj_destroy(&c->objs.dither);
 }
 
 API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
@@ -189,7 +192,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
             goto done;
         struct pl_sample_filter_params fp = {
             .filter = *cfg,
-            .lut = &objs.sampler,
+            .lut = &c->objs.sampler,
         };
         if (sargs[8] >= 0)
             fp.antiring = sargs[8];
@@ -245,7 +248,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
             pl_shader_color_map_ex(sh, &par, pl_color_map_args(
                 .src = s,
                 .dst = d,
-                .state = use_state ? &objs.cmap : NULL,
+                .state = use_state ? &c->objs.cmap : NULL,
             ));
             break;
         }
@@ -256,7 +259,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
                 .temporal = a[3],
                 .transfer = (int) a[4],
             };
-            pl_shader_dither(sh, (int) a[0], &objs.dither, &dp);
+            pl_shader_dither(sh, (int) a[0], &c->objs.dither, &dp);
             a += 5;
             break;
         }
@@ -274,7 +277,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
             struct pl_color_space csp = csp_from_flat(a);
             bool hq = a[CSP_FLOATS];
             a += CSP_FLOATS + 1;
-            if (!pl_shader_detect_peak(sh, csp, &objs.cmap,
+            if (!pl_shader_detect_peak(sh, csp, &c->objs.cmap,
                                        hq ? &pl_peak_detect_high_quality_params
                                           : &pl_peak_detect_default_params))
                 goto done;
@@ -290,7 +293,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
     ok = pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst ));
     if (ok && out_peak) {
         struct pl_hdr_metadata md = {0};
-        if (pl_get_detected_hdr_metadata(objs.cmap, &md)) {
+        if (pl_get_detected_hdr_metadata(c->objs.cmap, &md)) {
             out_peak[0] = md.avg_pq_y;
             out_peak[1] = md.max_pq_y;
         }
