@@ -546,6 +546,19 @@ static __device__ __noinline__ void plb_run_color_ops(const plb_color_prog &prog
             for (int k = 0; k < 3; k++)
                 c[k] = powf(fmaxf(c[k], 0.0f), op.u.gamma.g);
             break;
+        case PLB_OP_SWIZZLE: {
+            const float o[4] = { c[0], c[1], c[2], c[3] };
+            c[0] = c[1] = c[2] = 0.0f;
+            c[3] = 1.0f;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < op.u.swizzle.comps && op.u.swizzle.map[k] >= 0)
+                    c[k] = o[op.u.swizzle.map[k]];
+            }
+            if (op.u.swizzle.force_alpha)
+                c[3] = o[3];
+            break;
+        }
         case PLB_OP_PEAK:
             *peak_op = &op.u.peak;
             *y_pq = plb_peak_ypq(op.u.peak, c);

@@ -118,6 +118,7 @@ enum plb_op_kind {
     PLB_OP_DOVI_RESHAPE,   // pl_shader_dovi_reshape
     PLB_OP_GAMMA,          // color adjustment gamma
     PLB_OP_PEAK,           // pl_shader_detect_peak tap (needs block-wide reduction)
+    PLB_OP_SWIZZLE,        // swizzle_color (src/renderer.c:791-808)
 };
 
 struct plb_trc_consts {
@@ -175,6 +176,7 @@ struct plb_color_op {
         struct { const struct plb_dovi_dev *tab; } dovi;
         struct { float g; } gamma;
         struct plb_op_peak peak;
+        struct { int8_t map[4]; int comps; int force_alpha; } swizzle;
     } u;
 };
 

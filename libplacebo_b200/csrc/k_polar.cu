@@ -168,16 +168,29 @@ struct polar_up2_args {
     plb_tail_args tail;
 };
 
-// Is tap (ox, oy) of phase (py, px) inside radius^2 < R2_16/16 ? (phase 0 -> f = 3/4)
-template <int R2_16>
+// Sub-texel phases of an exact 2x upscale, per axis. MODE 0 ("centred": rect origin 0, e.g.
+// RGB frames or centre-sited chroma): fractions 3/4, 1/4 and the first output of a cell starts
+// one texel to the left. MODE 1 ("left"/"top" sited chroma, rect origin 0.25): fractions 0, 1/2,
+// both outputs share the cell's texel as base.
+__host__ __device__ constexpr int up2_frac4(int mode, int phase)
+{
+    return mode == 0 ? (phase ? 1 : 3) : (phase ? 2 : 0);
+}
+__host__ __device__ constexpr int up2_shift(int mode, int phase)
+{
+    return mode == 0 && phase == 0 ? 1 : 0;
+}
+
+// Is tap (ox, oy) of phase (py, px) inside radius^2 < R2_16/16 ?
+template <int R2_16, int XM, int YM>
 __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
 {
     return ox >= -3 && ox <= 4 && oy >= -3 && oy <= 4 &&
-           ((4 * ox - (px ? 1 : 3)) * (4 * ox - (px ? 1 : 3)) +
-            (4 * oy - (py ? 1 : 3)) * (4 * oy - (py ? 1 : 3))) < R2_16;
+           ((4 * ox - up2_frac4(XM, px)) * (4 * ox - up2_frac4(XM, px)) +
+            (4 * oy - up2_frac4(YM, py)) * (4 * oy - up2_frac4(YM, py))) < R2_16;
 }
 
-template <int NC, int R2_16>
+template <int NC, int R2_16, int XM, int YM>
 __global__ void __launch_bounds__(UP2_TX * UP2_TY)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
 {
@@ -226,14 +239,14 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
         #pragma unroll
         for (int oyo = 0; oyo < UP2_OY; oyo++) {
             // output row 2*jj + oyo: phase oyo, base row jj - 1 (phase 0) or jj (phase 1)
-            const int oy = wy - 4 + (oyo == 0 ? 1 : 0);
+            const int oy = wy - 4 + up2_shift(YM, oyo);
             #pragma unroll
             for (int oxo = 0; oxo < UP2_OX; oxo++) {
                 const int ci = oxo >> 1, px = oxo & 1;
                 #pragma unroll
                 for (int wx = 0; wx < 10; wx++) {
-                    const int ox = wx - 4 - ci + (px == 0 ? 1 : 0);
-                    if (up2_tap_on<R2_16>(oyo, px, oy, ox)) {
+                    const int ox = wx - 4 - ci + up2_shift(XM, px);
+                    if (up2_tap_on<R2_16, XM, YM>(oyo, px, oy, ox)) {
                         const float w = a.w[oyo][px][oy + 3][ox + 3];
                         #pragma unroll
                         for (int k = 0; k < NC; k++)
@@ -330,7 +343,7 @@ static float host_lut1d(const float *lut, int n, float x)
 
 #define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
 
-template <int NC>
+template <int NC, int XM, int YM>
 static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
 {
     dim3 block(UP2_TX, UP2_TY);
@@ -338,9 +351,8 @@ static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
     dim3 grid((args.tail.out_w + UP2_TX * UP2_OX - 1) / (UP2_TX * UP2_OX),
               (args.tail.out_h + UP2_TY * UP2_OY - 1) / (UP2_TY * UP2_OY));
     switch (r2_class) {
-    case 160: k_polar_up2<NC, 160><<<grid, block, 0, STREAM(gpu)>>>(args); break;
-    case 168: k_polar_up2<NC, 168><<<grid, block, 0, STREAM(gpu)>>>(args); break;
-    default:  k_polar_up2<NC, 1000><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    case 160: k_polar_up2<NC, 160, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    default:  k_polar_up2<NC, 1000, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
     }
     return plb_cuda_check(gpu, cudaGetLastError(), "k_polar_up2");
 }
@@ -360,13 +372,17 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
     const int wg_w = PLB_DEF(tl->wg_w, 32), wg_h = PLB_DEF(tl->wg_h, 32);
 
     // --- 2x fast path eligibility ---
-    const bool full = p->rect.x0 == 0 && p->rect.y0 == 0 && p->rect.x1 == p->src.w &&
-                      p->rect.y1 == p->src.h;
+    // whole texture, origin 0 (centred phases) or 0.25 (left/top sited chroma) per axis
+    const int xm = p->rect.x0 == 0.0f ? 0 : p->rect.x0 == 0.25f ? 1 : -1;
+    const int ym = p->rect.y0 == 0.0f ? 0 : p->rect.y0 == 0.25f ? 1 : -1;
+    const bool full = xm >= 0 && ym >= 0 && p->rect.x1 - p->rect.x0 == (float) p->src.w &&
+                      p->rect.y1 - p->rect.y0 == (float) p->src.h;
     const uint8_t mask = p->comp_mask;
     const int nc = mask == 0x1 ? 1 : mask == 0x3 ? 2 : mask == 0x7 ? 3 : mask == 0xF ? 4 : 0;
     bool fast = p->allow_fast && tl->coord_mode == PLB_COORD_EXACT && full && p->host_lut &&
                 tl->out_w == 2 * p->src.w && tl->out_h == 2 * p->src.h && bound <= 4 &&
-                !(p->antiring > 0) && nc && nc <= p->src.comps;
+                !(p->antiring > 0) && nc && nc <= p->src.comps &&
+                (nc <= 2 || (xm == 0 && ym == 0));
     const int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
     if (has_peak && (TW % wg_w || TH % wg_h || (TW / wg_w) * (TH / wg_h) > PLB_MAX_WG_PER_CTA))
         fast = false;
@@ -390,7 +406,7 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
         int max_d16 = 0;
         for (int py = 0; py < 2; py++) {
             for (int px = 0; px < 2; px++) {
-                const float fx = px ? 0.25f : 0.75f, fy = py ? 0.25f : 0.75f;
+                const float fx = up2_frac4(xm, px) * 0.25f, fy = up2_frac4(ym, py) * 0.25f;
                 float wsum = 0.0f;
                 for (int t = 0; t < ntaps; t++) {
                     const float dx = (float) tx[t] - fx, dy = (float) ty[t] - fy;
@@ -401,7 +417,7 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
                     wsum += w;
                     args.w[py][px][ty[t] + 3][tx[t] + 3] = w;
                     if (w != 0.0f) {
-                        int ax = 4 * tx[t] - (px ? 1 : 3), ay = 4 * ty[t] - (py ? 1 : 3);
+                        int ax = 4 * tx[t] - up2_frac4(xm, px), ay = 4 * ty[t] - up2_frac4(ym, py);
                         int d16 = ax * ax + ay * ay;
                         max_d16 = PLB_MAX(max_d16, d16);
                     }
@@ -409,13 +425,25 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
                 args.norm[py][px] = p->scale / wsum;
             }
         }
-        const int r2_class = max_d16 < 160 ? 160 : max_d16 < 168 ? 168 : 1000;
+        const int r2_class = max_d16 < 160 ? 160 : 1000;
         bool ok;
-        switch (nc) {
-        case 1: ok = launch_up2<1>(gpu, args, r2_class); break;
-        case 2: ok = launch_up2<2>(gpu, args, r2_class); break;
-        case 3: ok = launch_up2<3>(gpu, args, r2_class); break;
-        default: ok = launch_up2<4>(gpu, args, r2_class); break;
+        // centred phases for every component count; sited-chroma phases for 1-2 components
+        const int mode = xm * 2 + ym;
+        if (mode == 0) {
+            switch (nc) {
+            case 1: ok = launch_up2<1, 0, 0>(gpu, args, r2_class); break;
+            case 2: ok = launch_up2<2, 0, 0>(gpu, args, r2_class); break;
+            case 3: ok = launch_up2<3, 0, 0>(gpu, args, r2_class); break;
+            default: ok = launch_up2<4, 0, 0>(gpu, args, r2_class); break;
+            }
+        } else if (nc == 1) {
+            ok = mode == 1 ? launch_up2<1, 0, 1>(gpu, args, r2_class)
+               : mode == 2 ? launch_up2<1, 1, 0>(gpu, args, r2_class)
+                           : launch_up2<1, 1, 1>(gpu, args, r2_class);
+        } else {
+            ok = mode == 1 ? launch_up2<2, 0, 1>(gpu, args, r2_class)
+               : mode == 2 ? launch_up2<2, 1, 0>(gpu, args, r2_class)
+                           : launch_up2<2, 1, 1>(gpu, args, r2_class);
         }
         g->launches++;
         return ok;

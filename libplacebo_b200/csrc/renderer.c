@@ -1,0 +1,1364 @@
+// pl_renderer on the CUDA backend: the per-frame planner.
+//
+// Restates the planning logic of the reference's src/renderer.c for the hot path
+// (pl_render_image :3433 -> pass_read_image :1553, pass_scale_main :1964, hdr_update_peak
+// :1183, pass_convert_colors :2157, pass_output_target :2586), building pl_shader op lists
+// instead of GLSL and materialising intermediates in the SAME places and formats (FBO format
+// selection find_fbo_format :383-434, img_tex :505-547), because every intermediate store is
+// a rounding step that is part of the reference's result:
+//     A. same-sized chroma planes are merged into one 2-component texture   (:1617-1699)
+//     B. deband -> [film grain] per plane; planes that need resampling are stored to an
+//        fp16 FBO first, then scaled by the plane scaler                    (:1763-1871)
+//     C. all planes are merged 1:1 into the main pass, decoded to RGB       (:1874-1957)
+//     D. main scaler (with optional linearisation / sigmoidisation), HDR peak detection,
+//        colour mapping, encoding, dithering, store                         (:1964-2964)
+// Features of pl_render_params outside the hot path (hooks, custom LUTs, ICC, overlays,
+// distortion, blending, deinterlacing, rotation, frame mixing) are rejected loudly instead of
+// being silently ignored.
+#define _GNU_SOURCE
+#include "shader_priv.h"
+
+#include <math.h>
+
+bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc, int w, int h,
+                      pl_timer timer);
+
+#define MAX_FBOS 16
+
+struct sampler_state {
+    pl_shader_obj up, down;
+};
+
+struct pl_renderer_t {
+    pl_log log;
+    pl_gpu gpu;
+    pl_dispatch dp;
+    enum pl_render_error errors;
+    pl_fmt fbofmt[5];
+    pl_tex fbos[MAX_FBOS];
+    bool fbo_used[MAX_FBOS];
+    struct sampler_state sampler_main, samplers_src[4];
+    pl_shader_obj tone_map_state, dither_state, grain_state[4];
+    int prev_dither;
+    bool have_frame_index;
+    uint8_t frame_index;
+    bool have_peak_override;
+    struct pl_peak_state peak_override;
+};
+
+const struct pl_render_params pl_render_fast_params = { PL_RENDER_DEFAULTS };
+const struct pl_render_params pl_render_default_params = {
+    PL_RENDER_DEFAULTS
+    .upscaler           = &pl_filter_lanczos,
+    .downscaler         = &pl_filter_hermite,
+    .sigmoid_params     = &pl_sigmoid_default_params,
+    .dither_params      = &pl_dither_default_params,
+    .peak_detect_params = &pl_peak_detect_default_params,
+};
+const struct pl_render_params pl_render_high_quality_params = {
+    PL_RENDER_DEFAULTS
+    .upscaler           = &pl_filter_ewa_lanczossharp,
+    .downscaler         = &pl_filter_hermite,
+    .sigmoid_params     = &pl_sigmoid_default_params,
+    .peak_detect_params = &pl_peak_detect_high_quality_params,
+    .color_map_params   = &pl_color_map_high_quality_params,
+    .dither_params      = &pl_dither_default_params,
+    .deband_params      = &pl_deband_default_params,
+};
+
+pl_renderer pl_renderer_create(pl_log log, pl_gpu gpu)
+{
+    if (!gpu) {
+        plb_msg(log, PL_LOG_ERR, "pl_renderer_create: no gpu");
+        return NULL;
+    }
+    struct pl_renderer_t *rr = calloc(1, sizeof(*rr));
+    rr->log = log;
+    rr->gpu = gpu;
+    rr->dp = pl_dispatch_create(log, gpu);
+    return rr;
+}
+
+void pl_renderer_destroy(pl_renderer *prr)
+{
+    pl_renderer rr = prr ? *prr : NULL;
+    if (!rr)
+        return;
+    for (int i = 0; i < MAX_FBOS; i++)
+        pl_tex_destroy(rr->gpu, &rr->fbos[i]);
+    pl_shader_obj_destroy(&rr->sampler_main.up);
+    pl_shader_obj_destroy(&rr->sampler_main.down);
+    for (int i = 0; i < 4; i++) {
+        pl_shader_obj_destroy(&rr->samplers_src[i].up);
+        pl_shader_obj_destroy(&rr->samplers_src[i].down);
+        pl_shader_obj_destroy(&rr->grain_state[i]);
+    }
+    pl_shader_obj_destroy(&rr->tone_map_state);
+    pl_shader_obj_destroy(&rr->dither_state);
+    pl_dispatch_destroy(&rr->dp);
+    free(rr);
+    *prr = NULL;
+}
+
+struct pl_render_errors pl_renderer_get_errors(pl_renderer rr)
+{
+    return (struct pl_render_errors) { .errors = rr->errors };
+}
+
+void pl_renderer_reset_errors(pl_renderer rr, const struct pl_render_errors *errors)
+{
+    if (!errors) {
+        rr->errors = PL_RENDER_ERR_NONE;
+        return;
+    }
+    rr->errors &= ~errors->errors;
+}
+
+void pl_renderer_flush_cache(pl_renderer rr)
+{
+    pl_reset_detected_peak(rr->tone_map_state);
+}
+
+bool pl_renderer_get_hdr_metadata(pl_renderer rr, struct pl_hdr_metadata *metadata)
+{
+    return pl_get_detected_hdr_metadata(rr->tone_map_state, metadata);
+}
+
+void pl_renderer_set_frame_index(pl_renderer rr, uint8_t index)
+{
+    rr->have_frame_index = true;
+    rr->frame_index = index;
+}
+
+void pl_renderer_set_peak_state(pl_renderer rr, const struct pl_peak_state *state)
+{
+    rr->have_peak_override = state != NULL;
+    if (state)
+        rr->peak_override = *state;
+}
+
+// ---------------------------------------------------------------------------------------
+// frame fix-ups (renderer.c:3043-3233)
+// ---------------------------------------------------------------------------------------
+
+enum plane_type { PLANE_INVALID = 0, PLANE_ALPHA, PLANE_CHROMA, PLANE_LUMA, PLANE_RGB, PLANE_XYZ };
+
+static enum plane_type detect_plane_type(const struct pl_plane *plane,
+                                         const struct pl_color_repr *repr)
+{
+    if (pl_color_system_is_ycbcr_like(repr->sys)) {
+        int t = PLANE_INVALID;
+        for (int c = 0; c < plane->components; c++) {
+            switch (plane->component_mapping[c]) {
+            case PL_CHANNEL_Y: t = PLB_MAX(t, PLANE_LUMA); break;
+            case PL_CHANNEL_A: t = PLB_MAX(t, PLANE_ALPHA); break;
+            case PL_CHANNEL_CB:
+            case PL_CHANNEL_CR: t = PLB_MAX(t, PLANE_CHROMA); break;
+            default: break;
+            }
+        }
+        return t;
+    }
+    if (plane->components == 1 && plane->component_mapping[0] == PL_CHANNEL_A)
+        return PLANE_ALPHA;
+    return repr->sys == PL_COLOR_SYSTEM_XYZ ? PLANE_XYZ : PLANE_RGB;
+}
+
+static int frame_ref(const struct pl_frame *frame)
+{
+    for (int i = 0; i < frame->num_planes; i++) {
+        switch (detect_plane_type(&frame->planes[i], &frame->repr)) {
+        case PLANE_RGB:
+        case PLANE_LUMA:
+        case PLANE_XYZ:
+            return i;
+        default:
+            continue;
+        }
+    }
+    return 0;
+}
+
+static enum pl_color_primaries primaries_guess(int width, int height)
+{
+    if (width >= 1280 || height > 576)
+        return PL_COLOR_PRIM_BT_709;
+    switch (height) {
+    case 576: return PL_COLOR_PRIM_BT_601_625;
+    case 480:
+    case 486: return PL_COLOR_PRIM_BT_601_525;
+    default:  return PL_COLOR_PRIM_BT_709;
+    }
+}
+
+static void fix_frame(struct pl_frame *frame)
+{
+    pl_tex tex = frame->planes[frame_ref(frame)].texture;
+    if (frame->repr.sys == PL_COLOR_SYSTEM_XYZ) {
+        frame->color.primaries = PL_COLOR_PRIM_DCI_P3;
+        frame->color.transfer = PL_COLOR_TRC_ST428;
+    }
+    if (tex && !frame->color.primaries)
+        frame->color.primaries = primaries_guess(tex->params.w, tex->params.h);
+    bool has_alpha = false;
+    for (int p = 0; p < frame->num_planes; p++)
+        for (int c = 0; c < frame->planes[p].components; c++)
+            has_alpha |= frame->planes[p].component_mapping[c] == PL_CHANNEL_A;
+    if (!has_alpha)
+        frame->repr.alpha = PL_ALPHA_NONE;
+    struct pl_bit_encoding *bits = &frame->repr.bits;
+    if (!bits->sample_depth && tex && tex->params.format->type == PL_FMT_UNORM) {
+        bits->sample_depth = tex->params.format->component_depth[0];
+        bits->color_depth = PLB_DEF(bits->color_depth, bits->sample_depth);
+        bits->color_depth = PLB_MIN(bits->color_depth, bits->sample_depth);
+        bits->bit_shift += bits->sample_depth - bits->color_depth;
+    }
+}
+
+struct pass_state {
+    pl_renderer rr;
+    const struct pl_render_params *params;
+    struct pl_frame image, target;
+    int src_ref, dst_ref;
+    pl_rect2df ref_rect;
+    pl_rect2d dst_rect;
+    bool need_peak_fbo;
+    // current image
+    pl_shader sh;       // pending shader (NULL if materialised in `tex`)
+    pl_tex tex;
+    int w, h, comps;
+    pl_rect2df rect;
+    struct pl_color_repr repr;
+    struct pl_color_space color;
+};
+
+static bool fix_refs_and_rects(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    struct pl_frame *image = &pass->image, *target = &pass->target;
+    pl_rect2df *dst = &target->crop, *src = &image->crop;
+    pass->dst_ref = frame_ref(target);
+    pl_tex dst_ref = target->planes[pass->dst_ref].texture;
+    const int dst_w = dst_ref->params.w, dst_h = dst_ref->params.h;
+    if ((!dst->x0 && !dst->x1) || (!dst->y0 && !dst->y1)) {
+        dst->x0 = dst->y0 = 0;
+        dst->x1 = dst_w;
+        dst->y1 = dst_h;
+    }
+    pass->src_ref = frame_ref(image);
+    pl_tex src_ref = image->planes[pass->src_ref].texture;
+    if ((!src->x0 && !src->x1) || (!src->y0 && !src->y1)) {
+        src->x0 = src->y0 = 0;
+        src->x1 = src_ref->params.w;
+        src->y1 = src_ref->params.h;
+    }
+    if (image->rotation != target->rotation) {
+        PLB_ERR(rr->log, "pl_render_image: rotation is outside the CUDA hot path");
+        return false;
+    }
+    if (src->x0 > src->x1 || src->y0 > src->y1 || dst->x0 > dst->x1 || dst->y0 > dst->y1) {
+        PLB_ERR(rr->log, "pl_render_image: flipped crops are outside the CUDA hot path");
+        return false;
+    }
+    // snap the destination to whole pixels and adjust the source accordingly (:3089-3120)
+    const float rx0 = roundf(fminf(fmaxf(dst->x0, 0.0), dst_w)),
+                ry0 = roundf(fminf(fmaxf(dst->y0, 0.0), dst_h)),
+                rx1 = roundf(fminf(fmaxf(dst->x1, 0.0), dst_w)),
+                ry1 = roundf(fminf(fmaxf(dst->y1, 0.0), dst_h));
+    const float scale_x = pl_rect_w(*src) / pl_rect_w(*dst),
+                scale_y = pl_rect_h(*src) / pl_rect_h(*dst),
+                base_x = src->x0, base_y = src->y0;
+    src->x0 = base_x + (rx0 - dst->x0) * scale_x;
+    src->x1 = base_x + (rx1 - dst->x0) * scale_x;
+    src->y0 = base_y + (ry0 - dst->y0) * scale_y;
+    src->y1 = base_y + (ry1 - dst->y0) * scale_y;
+    *dst = (pl_rect2df) { rx0, ry0, rx1, ry1 };
+    pass->ref_rect = *src;
+    pass->dst_rect = (pl_rect2d) { dst->x0, dst->y0, dst->x1, dst->y1 };
+    return true;
+}
+
+static bool pass_fix_frames(struct pass_state *pass)
+{
+    struct pl_frame *image = &pass->image, *target = &pass->target;
+    if (!fix_refs_and_rects(pass))
+        return false;
+    fix_frame(image);
+    pl_color_space_infer_map(&image->color, &target->color);
+    fix_frame(target);
+    if (image->repr.alpha == PL_ALPHA_UNKNOWN)
+        image->repr.alpha = PL_ALPHA_INDEPENDENT;
+    if (target->repr.alpha == PL_ALPHA_UNKNOWN)
+        target->repr.alpha = PL_ALPHA_PREMULTIPLIED;
+    return true;
+}
+
+void pl_frames_infer(pl_renderer rr, struct pl_frame *image, struct pl_frame *target)
+{
+    struct pass_state pass = { .rr = rr, .image = *image, .target = *target };
+    if (pass_fix_frames(&pass)) {
+        *image = pass.image;
+        *target = pass.target;
+    }
+}
+
+void pl_frame_set_chroma_location(struct pl_frame *frame, enum pl_chroma_location loc)
+{
+    pl_tex ref = frame->planes[frame_ref(frame)].texture;
+    for (int i = 0; i < frame->num_planes; i++) {
+        struct pl_plane *plane = &frame->planes[i];
+        bool apply;
+        if (ref) {
+            apply = plane->texture->params.w < ref->params.w ||
+                    plane->texture->params.h < ref->params.h;
+        } else {
+            apply = detect_plane_type(plane, &frame->repr) == PLANE_CHROMA;
+        }
+        if (apply)
+            pl_chroma_location_offset(loc, &plane->shift_x, &plane->shift_y);
+    }
+}
+
+bool pl_frame_is_cropped(const struct pl_frame *frame)
+{
+    int x0 = roundf(PLB_MIN(frame->crop.x0, frame->crop.x1)),
+        y0 = roundf(PLB_MIN(frame->crop.y0, frame->crop.y1)),
+        x1 = roundf(PLB_MAX(frame->crop.x0, frame->crop.x1)),
+        y1 = roundf(PLB_MAX(frame->crop.y0, frame->crop.y1));
+    pl_tex ref = frame->planes[frame_ref(frame)].texture;
+    if (!x0 && !x1) x1 = ref->params.w;
+    if (!y0 && !y1) y1 = ref->params.h;
+    return x0 > 0 || y0 > 0 || x1 < ref->params.w || y1 < ref->params.h;
+}
+
+// ---------------------------------------------------------------------------------------
+// FBOs (renderer.c:383-547)
+// ---------------------------------------------------------------------------------------
+
+static bool find_fbo_format(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    if (params->disable_fbos || (rr->errors & PL_RENDER_ERR_FBO)) {
+        PLB_ERR(rr->log, "pl_render_image: rendering without FBOs is not supported on the "
+                "CUDA backend");
+        return false;
+    }
+    static const struct { enum pl_fmt_type type; int depth; } prefs[] = {
+        { PL_FMT_FLOAT, 16 }, { PL_FMT_UNORM, 16 }, { PL_FMT_UNORM, 8 },
+    };
+    for (size_t i = 0; i < PLB_ARRAY_SIZE(prefs); i++) {
+        if (params->force_low_bit_depth_fbos && prefs[i].depth > 8)
+            continue;
+        pl_fmt fmt = pl_find_fmt(rr->gpu, prefs[i].type, 4, prefs[i].depth, 0,
+                                 PL_FMT_CAP_RENDERABLE | PL_FMT_CAP_LINEAR);
+        if (!fmt)
+            continue;
+        rr->fbofmt[4] = fmt;
+        for (int c = 3; c >= 1; c--) {
+            rr->fbofmt[c] = pl_find_fmt(rr->gpu, prefs[i].type, c, prefs[i].depth, 0, fmt->caps);
+            rr->fbofmt[c] = PLB_DEF(rr->fbofmt[c], rr->fbofmt[c + 1]);
+        }
+        return true;
+    }
+    return false;
+}
+
+static pl_tex get_fbo(struct pass_state *pass, int w, int h, pl_fmt fmt, int comps)
+{
+    pl_renderer rr = pass->rr;
+    fmt = PLB_DEF(fmt, rr->fbofmt[PLB_DEF(comps, 4)]);
+    int free_slot = -1;
+    for (int i = 0; i < MAX_FBOS; i++) {
+        if (rr->fbo_used[i])
+            continue;
+        pl_tex t = rr->fbos[i];
+        if (t && t->params.w == w && t->params.h == h && t->params.format == fmt) {
+            rr->fbo_used[i] = true;
+            return t;
+        }
+        if (free_slot < 0 || (!t && rr->fbos[free_slot]))
+            free_slot = i;
+    }
+    if (free_slot < 0) {
+        PLB_ERR(rr->log, "out of FBO slots");
+        return NULL;
+    }
+    if (!pl_tex_recreate(rr->gpu, &rr->fbos[free_slot], pl_tex_params(
+            .w = w, .h = h, .format = fmt,
+            .sampleable = true, .renderable = true, .storable = true)))
+        return NULL;
+    rr->fbo_used[free_slot] = true;
+    return rr->fbos[free_slot];
+}
+
+// img_tex: materialise a pending shader
+static pl_tex shader_to_tex(struct pass_state *pass, pl_shader *sh, int w, int h, pl_fmt fmt,
+                            int comps)
+{
+    pl_renderer rr = pass->rr;
+    pl_tex tex = get_fbo(pass, w, h, fmt, comps);
+    if (!tex) {
+        pl_dispatch_abort(rr->dp, sh);
+        rr->errors |= PL_RENDER_ERR_FBO;
+        return NULL;
+    }
+    if (!pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = sh, .target = tex ))) {
+        PLB_ERR(rr->log, "Failed dispatching intermediate pass!");
+        return NULL;
+    }
+    return tex;
+}
+
+static pl_shader begin(struct pass_state *pass)
+{
+    return pl_dispatch_begin(pass->rr->dp);
+}
+
+static pl_tex img_tex(struct pass_state *pass)
+{
+    if (pass->tex)
+        return pass->tex;
+    pass->tex = shader_to_tex(pass, &pass->sh, pass->w, pass->h, NULL, pass->comps);
+    pass->sh = NULL;
+    return pass->tex;
+}
+
+static pl_shader img_sh(struct pass_state *pass)
+{
+    if (pass->sh)
+        return pass->sh;
+    pass->sh = begin(pass);
+    pl_shader_sample_direct(pass->sh, pl_sample_src( .tex = pass->tex ));
+    pass->tex = NULL;
+    return pass->sh;
+}
+
+// ---------------------------------------------------------------------------------------
+// samplers (renderer.c:597-789)
+// ---------------------------------------------------------------------------------------
+
+enum sampler_type { SAMPLER_DIRECT, SAMPLER_NEAREST, SAMPLER_COMPLEX };
+enum sampler_dir { SAMPLER_NOOP, SAMPLER_UP, SAMPLER_DOWN };
+enum sampler_usage { SAMPLER_MAIN, SAMPLER_PLANE };
+
+struct sampler_info {
+    const struct pl_filter_config *config;
+    enum sampler_type type;
+    enum sampler_dir dir, dir_sep[2];
+};
+
+static struct sampler_info sample_src_info(struct pass_state *pass,
+                                           const struct pl_sample_src *src,
+                                           enum sampler_usage usage)
+{
+    const struct pl_render_params *params = pass->params;
+    struct sampler_info info = {0};
+    const float rx = src->new_w / fabsf(pl_rect_w(src->rect));
+    const float ry = src->new_h / fabsf(pl_rect_h(src->rect));
+    if (rx < 1.0 - 1e-6)
+        info.dir_sep[0] = SAMPLER_DOWN;
+    else if (rx > 1.0 + 1e-6)
+        info.dir_sep[0] = SAMPLER_UP;
+    if (ry < 1.0 - 1e-6)
+        info.dir_sep[1] = SAMPLER_DOWN;
+    else if (ry > 1.0 + 1e-6)
+        info.dir_sep[1] = SAMPLER_UP;
+    if (params->correct_subpixel_offsets) {
+        if (!info.dir_sep[0] && fabsf(src->rect.x0) > 1e-6f)
+            info.dir_sep[0] = SAMPLER_UP;
+        if (!info.dir_sep[1] && fabsf(src->rect.y0) > 1e-6f)
+            info.dir_sep[1] = SAMPLER_UP;
+    }
+    info.dir = PLB_MAX(info.dir_sep[0], info.dir_sep[1]);
+    switch (info.dir) {
+    case SAMPLER_DOWN:
+        info.config = usage == SAMPLER_PLANE && params->plane_downscaler
+                    ? params->plane_downscaler : params->downscaler;
+        break;
+    case SAMPLER_UP:
+        info.config = usage == SAMPLER_PLANE && params->plane_upscaler
+                    ? params->plane_upscaler : params->upscaler;
+        break;
+    case SAMPLER_NOOP:
+        info.type = SAMPLER_NEAREST;
+        return info;
+    }
+    if ((pass->rr->errors & PL_RENDER_ERR_SAMPLING) || !info.config) {
+        info.type = SAMPLER_DIRECT;
+    } else {
+        info.type = SAMPLER_COMPLEX;
+        const bool can_fast = info.dir == SAMPLER_UP || params->skip_anti_aliasing;
+        if (can_fast && !params->disable_builtin_scalers) {
+            // the reference's built-in fast paths: bilinear / nearest map onto the texture
+            // unit; bicubic/hermite/gaussian fast paths are not implemented here and take
+            // the generic separable path instead (same maths up to the linear-sampling trick)
+            if (pl_filter_config_eq(info.config, &pl_filter_bilinear))
+                info.type = SAMPLER_DIRECT;
+            if (pl_filter_config_eq(info.config, &pl_filter_nearest))
+                info.type = SAMPLER_NEAREST;
+        }
+    }
+    return info;
+}
+
+// Records the right sampler into `sh`. For two-pass separable scaling the first pass is
+// dispatched into an FBO here.
+static bool dispatch_sampler(struct pass_state *pass, pl_shader sh, struct sampler_state *st,
+                             enum sampler_usage usage, const struct pl_sample_src *src)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    const struct sampler_info info = sample_src_info(pass, src, usage);
+    if (info.dir == SAMPLER_NOOP || info.type == SAMPLER_DIRECT)
+        return pl_shader_sample_direct(sh, src);
+    if (info.type == SAMPLER_NEAREST)
+        return pl_shader_sample_nearest(sh, src);
+
+    struct pl_sample_filter_params fp = {
+        .filter = *info.config,
+        .antiring = params->antiringing_strength,
+        .no_widening = params->skip_anti_aliasing,
+        .lut = info.dir == SAMPLER_UP ? &st->up : &st->down,
+    };
+    bool ok;
+    if (info.config->polar) {
+        ok = pl_shader_sample_polar(sh, src, &fp);
+    } else if (info.dir_sep[0] && info.dir_sep[1]) {
+        // vertical pass into an FBO, horizontal pass into `sh` (renderer.c:742-768)
+        struct pl_sample_src src1 = *src, src2 = *src;
+        src1.new_w = src->tex->params.w;
+        src1.rect.x0 = 0;
+        src1.rect.x1 = src1.new_w;
+        src2.rect.y0 = 0;
+        src2.rect.y1 = src1.new_h;
+        pl_shader tsh = begin(pass);
+        ok = pl_shader_sample_ortho2(tsh, &src1, &fp);
+        if (!ok) {
+            pl_dispatch_abort(rr->dp, &tsh);
+        } else {
+            src2.tex = shader_to_tex(pass, &tsh, src1.new_w, src1.new_h, NULL, src->components);
+            src2.scale = 1.0;
+            ok = src2.tex && pl_shader_sample_ortho2(sh, &src2, &fp);
+        }
+    } else {
+        ok = pl_shader_sample_ortho2(sh, src, &fp);
+    }
+    if (!ok) {
+        PLB_ERR(rr->log, "Failed dispatching scaler..");
+        rr->errors |= PL_RENDER_ERR_SAMPLING;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass_read_image (renderer.c:1553-1962)
+// ---------------------------------------------------------------------------------------
+
+struct plane_state {
+    enum plane_type type;
+    struct pl_plane plane;
+    pl_tex tex;             // current texture (original, merged or FBO)
+    pl_shader sh;           // pending single-plane shader (deband / grain)
+    int w, h, comps;
+    pl_fmt fmt;             // format whose sample_order applies
+    struct pl_color_repr repr;
+    pl_rect2df rect;
+    int plane_w, plane_h;
+};
+
+// Move the (single) plane of sub-shader `sub` into the plane list of `sh`, mapping its
+// components into colour channels (sh_subpass + "color[map[c]] = tmp[c]", :1874-1891)
+static bool merge_plane_shader(pl_shader sh, pl_shader sub, const int map[4], int comps,
+                               float scale)
+{
+    if (sub->failed || sub->src != PLB_SRC_PLANES || sub->px.nplanes != 1 || sub->px.prog.n) {
+        plb_shader_fail(sh, "internal: cannot merge this sub-shader");
+        return false;
+    }
+    if (sh->px.nplanes >= 4) {
+        plb_shader_fail(sh, "too many planes in one pass");
+        return false;
+    }
+    struct plb_plane_src *pl = &sh->px.planes[sh->px.nplanes++];
+    *pl = sub->px.planes[0];
+    pl->scale *= scale;
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k < comps ? map[k] : -1;
+    // keep the LUT objects of the sub-shader alive
+    for (int i = 0; i < sub->num_objs && sh->num_objs < (int) PLB_ARRAY_SIZE(sh->objs); i++) {
+        sub->objs[i]->refcount++;
+        sh->objs[sh->num_objs++] = sub->objs[i];
+    }
+    return true;
+}
+
+static bool needs_grain(const struct pass_state *pass)
+{
+    return pass->image.film_grain.type != PL_FILM_GRAIN_NONE;
+}
+
+static bool want_merge(struct pass_state *pass, const struct plane_state *st,
+                       const struct plane_state *ref)
+{
+    const struct pl_render_params *params = pass->params;
+    if (!(pass->rr->errors & PL_RENDER_ERR_DEBANDING) && params->deband_params)
+        return true;
+    struct pl_sample_src src = {
+        .new_w = ref->w,
+        .new_h = ref->h,
+        .rect = { .x1 = st->w, .y1 = st->h },
+    };
+    if (sample_src_info(pass, &src, SAMPLER_PLANE).type == SAMPLER_COMPLEX)
+        return true;
+    return needs_grain(pass);
+}
+
+extern bool plb_plane_film_grain(pl_renderer rr, pl_shader sh, pl_shader_obj *state,
+                                 const struct pl_frame *image, const struct pl_plane *plane,
+                                 pl_tex tex, pl_tex luma_tex, int luma_comp,
+                                 struct pl_color_repr *repr);
+
+static bool pass_read_image(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    struct pl_frame *image = &pass->image;
+    struct plane_state planes[4] = {0};
+    struct plane_state *ref = &planes[pass->src_ref];
+
+    for (int i = 0; i < image->num_planes; i++) {
+        struct plane_state *st = &planes[i];
+        st->type = detect_plane_type(&image->planes[i], &image->repr);
+        st->plane = image->planes[i];
+        st->tex = image->planes[i].texture;
+        st->w = st->tex->params.w;
+        st->h = st->tex->params.h;
+        st->comps = image->planes[i].components;
+        st->fmt = st->tex->params.format;
+        st->repr = image->repr;
+        if (st->plane.flipped) {
+            PLB_ERR(rr->log, "pl_render_image: flipped planes are outside the CUDA hot path");
+            return false;
+        }
+        if (image->repr.alpha == PL_ALPHA_NONE) {
+            if (st->type == PLANE_ALPHA) {
+                st->type = PLANE_INVALID;
+                continue;
+            }
+            for (int j = 0; j < st->plane.components; j++) {
+                if (st->plane.component_mapping[j] == PL_CHANNEL_A)
+                    st->plane.component_mapping[j] = PL_CHANNEL_NONE;
+            }
+        }
+    }
+    pl_tex ref_tex = ref->plane.texture;
+
+    // --- A. merge compatible planes (chroma pairs) ---
+    for (int i = 0; i < image->num_planes; i++) {
+        struct plane_state *sti = &planes[i];
+        if (!sti->type || !want_merge(pass, sti, ref))
+            continue;
+        for (int j = i + 1; j < image->num_planes; j++) {
+            struct plane_state *stj = &planes[j];
+            const bool merge = sti->type == stj->type && sti->w == stj->w && sti->h == stj->h &&
+                               sti->plane.shift_x == stj->plane.shift_x &&
+                               sti->plane.shift_y == stj->plane.shift_y;
+            if (!merge || sti->fmt->type != stj->fmt->type)
+                continue;
+            const int num_comps = PLB_MIN(4, sti->comps + stj->comps);
+            const int depth = PLB_MAX(sti->repr.bits.sample_depth, stj->repr.bits.sample_depth);
+            pl_fmt fmt = sti->fmt->type == PL_FMT_UINT ? rr->fbofmt[num_comps]
+                       : pl_find_fmt(rr->gpu, sti->fmt->type, num_comps, depth, 0,
+                                     PL_FMT_CAP_SAMPLEABLE);
+            if (!fmt)
+                continue;
+            // one pass that copies both planes into adjacent components
+            pl_shader sh = begin(pass), sa = begin(pass), sb = begin(pass);
+            pl_shader_sample_direct(sa, pl_sample_src( .tex = sti->tex ));
+            pl_shader_sample_direct(sb, pl_sample_src( .tex = stj->tex ));
+            int comp_map[4] = {-1, -1, -1, -1}, mapa[4] = {-1, -1, -1, -1}, mapb[4] = {-1, -1, -1, -1};
+            int n = 0;
+            for (int c = 0; c < sti->comps; c++) {
+                if (sti->plane.component_mapping[c] == PL_CHANNEL_NONE)
+                    continue;
+                mapa[c] = n;
+                comp_map[n++] = sti->plane.component_mapping[c];
+            }
+            for (int c = 0; c < stj->comps && n < 4; c++) {
+                if (stj->plane.component_mapping[c] == PL_CHANNEL_NONE)
+                    continue;
+                mapb[c] = n;
+                comp_map[n++] = stj->plane.component_mapping[c];
+            }
+            sh->src = PLB_SRC_PLANES;
+            sh->px.coord_mode = PLB_COORD_EXACT;
+            bool ok = merge_plane_shader(sh, sa, mapa, sti->comps, 1.0f) &&
+                      merge_plane_shader(sh, sb, mapb, stj->comps, 1.0f);
+            pl_dispatch_abort(rr->dp, &sa);
+            pl_dispatch_abort(rr->dp, &sb);
+            pl_tex merged = ok ? shader_to_tex(pass, &sh, sti->w, sti->h, fmt, n) : NULL;
+            if (!merged) {
+                pl_dispatch_abort(rr->dp, &sh);
+                PLB_ERR(rr->log, "Failed dispatching plane merging shader");
+                return false;
+            }
+            sti->tex = merged;
+            sti->fmt = fmt;
+            sti->comps = sti->plane.components = n;
+            memcpy(sti->plane.component_mapping, comp_map, sizeof(comp_map));
+            *stj = (struct plane_state) {0};
+        }
+    }
+
+    // neutral values (:1715-1721)
+    const int bits = image->repr.bits.sample_depth;
+    const float out_scale = bits ? (1llu << bits) / ((1llu << bits) - 1.0f) : 1.0f;
+    float neutral_luma = 0.0, neutral_chroma = 0.5f * out_scale;
+    if (pl_color_levels_guess(&image->repr) == PL_COLOR_LEVELS_LIMITED)
+        neutral_luma = 16 / 256.0f * out_scale;
+    if (!pl_color_system_is_ycbcr_like(image->repr.sys))
+        neutral_chroma = neutral_luma;
+
+    // --- B. per-plane rects, debanding, grain ---
+    for (int i = 0; i < image->num_planes; i++) {
+        struct plane_state *st = &planes[i];
+        if (!st->type)
+            continue;
+        const float rx = (float) st->plane.texture->params.w / ref_tex->params.w,
+                    ry = (float) st->plane.texture->params.h / ref_tex->params.h;
+        const float rrx = rx >= 1 ? roundf(rx) : 1.0 / roundf(1.0 / rx),
+                    rry = ry >= 1 ? roundf(ry) : 1.0 / roundf(1.0 / ry);
+        const float sx = st->plane.shift_x, sy = st->plane.shift_y;
+        st->rect = (pl_rect2df) {
+            (image->crop.x0 - sx) * rrx, (image->crop.y0 - sy) * rry,
+            (image->crop.x1 - sx) * rrx, (image->crop.y1 - sy) * rry,
+        };
+        st->plane_w = ref_tex->params.w * rrx;
+        st->plane_h = ref_tex->params.h * rry;
+
+        float neutral[3] = {0.0};
+        for (int c = 0, idx = 0; c < st->plane.components; c++) {
+            switch (st->plane.component_mapping[c]) {
+            case PL_CHANNEL_Y: neutral[idx++] = neutral_luma; break;
+            case PL_CHANNEL_U:
+            case PL_CHANNEL_V: neutral[idx++] = neutral_chroma; break;
+            }
+        }
+
+        if (params->deband_params && !(rr->errors & PL_RENDER_ERR_DEBANDING)) {
+            struct pl_color_repr repr = st->repr;
+            struct pl_sample_src src = {
+                .tex = st->tex,
+                .components = st->comps,
+                .scale = pl_color_repr_normalize(&repr),
+            };
+            // keep the grain amplitude independent of the source's nominal peak (:1336-1342)
+            struct pl_deband_params dparams = *params->deband_params;
+            dparams.grain /= image->color.hdr.max_luma / PL_COLOR_SDR_WHITE;
+            memcpy(dparams.grain_neutral, neutral, sizeof(dparams.grain_neutral));
+            st->sh = begin(pass);
+            pl_shader_deband(st->sh, &src, &dparams);
+            if (pl_shader_is_failed(st->sh)) {
+                pl_dispatch_abort(rr->dp, &st->sh);
+                rr->errors |= PL_RENDER_ERR_DEBANDING;
+            } else {
+                st->repr = repr;
+            }
+        }
+
+        if (needs_grain(pass)) {
+            // grain needs the (possibly debanded) plane as a texture
+            if (st->sh) {
+                st->tex = shader_to_tex(pass, &st->sh, st->w, st->h, NULL, st->comps);
+                st->sh = NULL;
+                st->fmt = st->tex ? st->tex->params.format : st->fmt;
+                if (!st->tex)
+                    return false;
+            }
+            int luma_comp = 0;
+            for (int c = 0; c < ref->plane.components; c++) {
+                if (ref->plane.component_mapping[c] == PL_CHANNEL_Y)
+                    luma_comp = c;
+            }
+            pl_shader gsh = begin(pass);
+            struct pl_color_repr grepr = st->repr;
+            if (plb_plane_film_grain(rr, gsh, &rr->grain_state[i], image, &st->plane, st->tex,
+                                     ref_tex, luma_comp, &grepr)) {
+                st->sh = gsh;
+                st->repr = grepr;
+            } else {
+                const bool failed = pl_shader_is_failed(gsh);
+                pl_dispatch_abort(rr->dp, &gsh);
+                if (failed) {
+                    rr->errors |= PL_RENDER_ERR_FILM_GRAIN;
+                    PLB_ERR(rr->log, "Failed applying film grain..");
+                    return false;
+                }
+            }
+        }
+    }
+
+    // --- C. align all planes onto the reference grid and merge them ---
+    pl_shader sh = begin(pass);
+    sh->px.init[0] = neutral_luma;
+    sh->px.init[1] = sh->px.init[2] = neutral_chroma;
+    sh->px.init[3] = 1.0f;
+    sh->px.coord_mode = plb_gpu_priv(rr->gpu)->coord_mode;
+
+    const pl_rect2df ref_rc = ref->rect;
+    pl_rect2d ref_rounded;
+    ref_rounded.x0 = truncf(ref_rc.x0);
+    ref_rounded.y0 = truncf(ref_rc.y0);
+    ref_rounded.x1 = ref_rounded.x0 + roundf(pl_rect_w(ref_rc));
+    ref_rounded.y1 = ref_rounded.y0 + roundf(pl_rect_h(ref_rc));
+    const float off_x = ref_rc.x0 - ref_rounded.x0, off_y = ref_rc.y0 - ref_rounded.y0,
+                stretch_x = pl_rect_w(ref_rounded) / pl_rect_w(ref_rc),
+                stretch_y = pl_rect_h(ref_rounded) / pl_rect_h(ref_rc);
+    const int out_w = pl_rect_w(ref_rounded), out_h = pl_rect_h(ref_rounded);
+
+    for (int i = 0; i < image->num_planes; i++) {
+        struct plane_state *st = &planes[i];
+        if (!st->type)
+            continue;
+        const float scale_x = pl_rect_w(st->rect) / pl_rect_w(ref_rc),
+                    scale_y = pl_rect_h(st->rect) / pl_rect_h(ref_rc),
+                    base_x = st->rect.x0 - scale_x * off_x,
+                    base_y = st->rect.y0 - scale_y * off_y;
+        struct pl_sample_src src = {
+            .components = st->plane.components,
+            .address_mode = st->plane.address_mode,
+            .scale = pl_color_repr_normalize(&st->repr),
+            .new_w = out_w,
+            .new_h = out_h,
+            .rect = {
+                base_x, base_y,
+                base_x + stretch_x * pl_rect_w(st->rect),
+                base_y + stretch_y * pl_rect_h(st->rect),
+            },
+        };
+        int map[4] = {-1, -1, -1, -1};
+        for (int c = 0; c < src.components; c++)
+            map[st->fmt->sample_order[c]] = st->plane.component_mapping[c];
+
+        const pl_rect2d unscaled = { .x1 = out_w, .y1 = out_h };
+        const bool aligned = st->w == out_w && st->h == out_h && pl_rect2d_eq(src.rect, unscaled);
+        bool ok;
+        if (st->sh && aligned) {
+            // pending 1:1 plane shader (deband / grain): merge as is
+            ok = merge_plane_shader(sh, st->sh, map, src.components, src.scale);
+            sh->src = PLB_SRC_PLANES;
+            pl_dispatch_abort(rr->dp, &st->sh);
+        } else {
+            if (st->sh) {
+                st->tex = shader_to_tex(pass, &st->sh, st->w, st->h, NULL, st->comps);
+                st->sh = NULL;
+                if (!st->tex)
+                    goto error;
+            }
+            src.tex = st->tex;
+            const struct sampler_info info = sample_src_info(pass, &src, SAMPLER_PLANE);
+            if (info.type == SAMPLER_COMPLEX && sh->src != PLB_SRC_POLAR && sh->src != PLB_SRC_ORTHO) {
+                // this plane's scaler becomes the primary sampler of the merged pass
+                const enum plb_src_kind had = sh->src;
+                sh->src = PLB_SRC_NONE;
+                ok = dispatch_sampler(pass, sh, &rr->samplers_src[i], SAMPLER_PLANE, &src);
+                if (ok && (sh->src == PLB_SRC_POLAR || sh->src == PLB_SRC_ORTHO)) {
+                    int8_t *smap = sh->src == PLB_SRC_POLAR ? sh->polar.src_map : sh->ortho.src_map;
+                    for (int k = 0; k < 4; k++)
+                        smap[k] = k < src.components ? map[k] : -1;
+                } else if (ok) {
+                    // fell back to direct sampling: turn it into a plane entry
+                    struct plb_plane_src tmp = sh->px.planes[0];
+                    sh->px.nplanes--;
+                    sh->px.planes[sh->px.nplanes] = tmp;
+                    for (int k = 0; k < 4; k++)
+                        sh->px.planes[sh->px.nplanes].map[k] = k < src.components ? map[k] : -1;
+                    sh->px.nplanes++;
+                    sh->src = had ? had : PLB_SRC_PLANES;
+                }
+                sh->out_w = sh->out_h = 0; // the merged pass is sized by the reference plane
+            } else {
+                pl_shader psh = begin(pass);
+                if (info.type == SAMPLER_COMPLEX) {
+                    // a second scaled plane: materialise at full precision, then merge 1:1
+                    ok = dispatch_sampler(pass, psh, &rr->samplers_src[i], SAMPLER_PLANE, &src);
+                    pl_fmt f32 = pl_find_fmt(rr->gpu, PL_FMT_FLOAT, st->comps == 3 ? 4 : st->comps,
+                                             32, 0, PL_FMT_CAP_SAMPLEABLE);
+                    pl_tex t = ok ? shader_to_tex(pass, &psh, out_w, out_h, f32, st->comps) : NULL;
+                    psh = begin(pass);
+                    ok = t && pl_shader_sample_direct(psh, pl_sample_src( .tex = t ));
+                    src.scale = 1.0;
+                } else if (info.type == SAMPLER_NEAREST) {
+                    ok = pl_shader_sample_nearest(psh, &(struct pl_sample_src) {
+                        .tex = src.tex, .rect = src.rect, .new_w = out_w, .new_h = out_h });
+                } else {
+                    ok = pl_shader_sample_direct(psh, &(struct pl_sample_src) {
+                        .tex = src.tex, .rect = src.rect, .new_w = out_w, .new_h = out_h });
+                }
+                ok = ok && merge_plane_shader(sh, psh, map, src.components, src.scale);
+                if (sh->src == PLB_SRC_NONE)
+                    sh->src = PLB_SRC_PLANES;
+                pl_dispatch_abort(rr->dp, &psh);
+            }
+        }
+        if (!ok)
+            goto error;
+    }
+
+    pass->sh = sh;
+    pass->tex = NULL;
+    pass->w = out_w;
+    pass->h = out_h;
+    pass->repr = ref->repr;
+    pass->color = image->color;
+    pass->comps = ref->repr.alpha == PL_ALPHA_NONE ? 3 : 4;
+    pass->rect = (pl_rect2df) { off_x, off_y, off_x + pl_rect_w(ref_rc), off_y + pl_rect_h(ref_rc) };
+    pass->ref_rect = pass->rect;
+
+    if (pass->repr.sys == PL_COLOR_SYSTEM_XYZ) {
+        pl_shader_linearize(sh, &pass->color);
+        pass->color.transfer = PL_COLOR_TRC_LINEAR;
+    }
+    pl_shader_decode_color(sh, &pass->repr, params->color_adjustment);
+    pl_shader_set_alpha(sh, &pass->repr, PL_ALPHA_PREMULTIPLIED);
+    return !pl_shader_is_failed(sh);
+
+error:
+    pl_dispatch_abort(rr->dp, &sh);
+    for (int i = 0; i < 4; i++)
+        pl_dispatch_abort(rr->dp, &planes[i].sh);
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// hdr_update_peak (renderer.c:1183-1250)
+// ---------------------------------------------------------------------------------------
+
+static void hdr_update_peak(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    if (!params->peak_detect_params || !pl_color_space_is_hdr(&pass->image.color))
+        goto cleanup;
+    if (rr->errors & PL_RENDER_ERR_PEAK_DETECT)
+        goto cleanup;
+    float max_peak = pl_color_transfer_nominal_peak(pass->image.color.transfer) * PL_COLOR_SDR_WHITE;
+    if (pass->image.color.transfer == PL_COLOR_TRC_HLG)
+        max_peak = pass->color.hdr.max_luma;
+    if (max_peak <= pass->target.color.hdr.max_luma + 1e-6)
+        goto cleanup; // nothing to adapt
+    if (pass->color.hdr.avg_pq_y)
+        goto cleanup; // dynamic metadata already present
+    const struct pl_color_map_params *cpars = params->color_map_params;
+    const enum pl_hdr_metadata_type metadata = cpars ? cpars->metadata : PL_HDR_METADATA_ANY;
+    if (metadata && metadata != PL_HDR_METADATA_CIE_Y)
+        goto cleanup;
+    const bool uses_ootf = cpars && cpars->tone_mapping_function == &pl_tone_map_st2094_40;
+    if (uses_ootf && pass->color.hdr.ootf.num_anchors)
+        goto cleanup;
+    if (rr->have_peak_override) {
+        // frame-parallel mode: the caller supplies the smoothed state (renderer.h extension)
+        goto cleanup_keep;
+    }
+    if (!pl_shader_detect_peak(img_sh(pass), pass->color, &rr->tone_map_state,
+                               params->peak_detect_params)) {
+        PLB_WARN(rr->log, "Failed creating HDR peak detection shader.. disabling");
+        rr->errors |= PL_RENDER_ERR_PEAK_DETECT;
+        goto cleanup;
+    }
+    pass->need_peak_fbo = !params->peak_detect_params->allow_delayed;
+    return;
+
+cleanup:
+    pl_reset_detected_peak(rr->tone_map_state);
+cleanup_keep:
+    return;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass_scale_main (renderer.c:1964-2087)
+// ---------------------------------------------------------------------------------------
+
+static bool pass_scale_main(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    const pl_rect2df new_rect = {
+        .x1 = abs(pl_rect_w(pass->dst_rect)),
+        .y1 = abs(pl_rect_h(pass->dst_rect)),
+    };
+    struct pl_sample_src src = {
+        .components = pass->comps,
+        .new_w = pl_rect_w(new_rect),
+        .new_h = pl_rect_h(new_rect),
+        .rect = pass->rect,
+    };
+    const struct sampler_info info = sample_src_info(pass, &src, SAMPLER_MAIN);
+    bool use_sigmoid = info.dir == SAMPLER_UP && params->sigmoid_params;
+    bool use_linear = info.dir == SAMPLER_DOWN;
+    if (info.dir == SAMPLER_UP)
+        hdr_update_peak(pass);
+
+    if (info.dir == SAMPLER_NOOP) {
+        // 1:1: nothing to do (src and dst sizes agree by construction)
+        goto done;
+    }
+    if (info.type == SAMPLER_DIRECT) {
+        // "free" bilinear resize: needs the image as a texture anyway on this backend
+        use_sigmoid = use_linear = false;
+    }
+
+    pl_fmt fbofmt = rr->fbofmt[pass->comps];
+    if (params->disable_linear_scaling || fbofmt->component_depth[0] < 16)
+        use_sigmoid = use_linear = false;
+    if (pl_color_space_is_hdr(&pass->color)) {
+        use_sigmoid = false;
+        if (fbofmt->type != PL_FMT_FLOAT)
+            use_linear = false;
+    }
+    if (use_linear || use_sigmoid) {
+        pl_shader_linearize(img_sh(pass), &pass->color);
+        pass->color.transfer = PL_COLOR_TRC_LINEAR;
+    }
+    if (use_sigmoid)
+        pl_shader_sigmoidize(img_sh(pass), params->sigmoid_params);
+
+    src.tex = img_tex(pass);
+    if (!src.tex)
+        return false;
+    pass->need_peak_fbo = false;
+
+    pl_shader sh = begin(pass);
+    if (!dispatch_sampler(pass, sh, &rr->sampler_main, SAMPLER_MAIN, &src)) {
+        pl_dispatch_abort(rr->dp, &sh);
+        return false;
+    }
+    pass->tex = NULL;
+    pass->sh = sh;
+    pass->w = src.new_w;
+    pass->h = src.new_h;
+    pass->rect = new_rect;
+    if (use_sigmoid)
+        pl_shader_unsigmoidize(sh, params->sigmoid_params);
+
+done:
+    if (info.dir != SAMPLER_UP)
+        hdr_update_peak(pass);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// pass_convert_colors (renderer.c:2157-2279)
+// ---------------------------------------------------------------------------------------
+
+static bool pass_convert_colors(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    const struct pl_frame *image = &pass->image, *target = &pass->target;
+    pl_shader sh = img_sh(pass);
+    bool prelinearized = false;
+    if (pass->color.transfer == PL_COLOR_TRC_LINEAR) {
+        if (pass->repr.alpha == PL_ALPHA_PREMULTIPLIED) {
+            pass->color.transfer = image->color.transfer;
+            pl_shader_delinearize(sh, &pass->color);
+        } else {
+            prelinearized = true;
+        }
+    } else if (pass->color.transfer != image->color.transfer) {
+        if (image->color.transfer == PL_COLOR_TRC_LINEAR) {
+            pl_shader_linearize(sh, &pass->color);
+            pass->color.transfer = PL_COLOR_TRC_LINEAR;
+        }
+    }
+    pl_shader_set_alpha(sh, &pass->repr, PL_ALPHA_INDEPENDENT);
+
+    if (pass->need_peak_fbo && !img_tex(pass))
+        return false;
+    sh = img_sh(pass);
+
+    struct pl_color_space src_csp = image->color;
+    pl_shader_obj override_state = NULL, *state = &rr->tone_map_state;
+    (void) override_state;
+    if (rr->have_peak_override) {
+        // the reference would read these from its own smoothed state (colorspace.c:1620-1621)
+        src_csp.hdr.max_pq_y = rr->peak_override.max_pq;
+        src_csp.hdr.avg_pq_y = rr->peak_override.avg_pq;
+    }
+    pl_shader_color_map_ex(sh, params->color_map_params, pl_color_map_args(
+        .src = src_csp,
+        .dst = target->color,
+        .prelinearized = prelinearized,
+        .state = state,
+    ));
+    pass->color = target->color;
+    return !pl_shader_is_failed(sh);
+}
+
+// ---------------------------------------------------------------------------------------
+// pass_output_target (renderer.c:2586-2964)
+// ---------------------------------------------------------------------------------------
+
+extern bool plb_record_swizzle(pl_shader sh, int comps, const int comp_map[4], bool force_alpha);
+extern bool plb_pass_error_diffusion(pl_renderer rr, pl_dispatch dp, pl_shader *sh, int new_depth,
+                                     int comps, int out_w, int out_h, pl_fmt fbofmt,
+                                     const struct pl_error_diffusion_kernel *kernel,
+                                     pl_tex (*get_fbo)(void *, int, int, pl_fmt, int), void *priv);
+
+static pl_tex get_fbo_cb(void *priv, int w, int h, pl_fmt fmt, int comps)
+{
+    return get_fbo(priv, w, h, fmt, comps);
+}
+
+static bool pass_output_target(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    const struct pl_render_params *params = pass->params;
+    const struct pl_frame *target = &pass->target;
+    if (target->num_planes != 1) {
+        PLB_ERR(rr->log, "pl_render_image: planar targets are not implemented on the CUDA "
+                "backend yet (single packed RGB(A) plane only)");
+        return false;
+    }
+    if (pl_frame_is_cropped(target) && params->border != PL_CLEAR_SKIP) {
+        // clear the target to the background colour first (clear_target :2516-2584); only
+        // black / the configured solid colour is supported
+        float bg[4] = { params->background_color[0], params->background_color[1],
+                        params->background_color[2], 1.0 - params->background_transparency };
+        pl_tex_clear(rr->gpu, target->planes[0].texture, bg);
+    }
+
+    pl_shader sh = img_sh(pass);
+    const struct pl_plane *plane = &target->planes[0];
+
+    // alpha handling for opaque sources / targets (:2713-2761): the hot path has no alpha
+    if (pass->comps == 4) {
+        PLB_ERR(rr->log, "pl_render_image: alpha blending is outside the CUDA hot path");
+        return false;
+    }
+
+    struct pl_color_repr repr = target->repr;
+    const float scale = pl_color_repr_normalize(&repr);
+    repr.alpha = PL_ALPHA_NONE; // img->comps < 4
+    pl_shader_encode_color(sh, &repr);
+    if (repr.sys == PL_COLOR_SYSTEM_XYZ) {
+        pass->color.transfer = PL_COLOR_TRC_ST428;
+        pl_shader_delinearize(sh, &pass->color);
+    }
+
+    const int rx0 = pass->dst_rect.x0, ry0 = pass->dst_rect.y0,
+              rx1 = pass->dst_rect.x1, ry1 = pass->dst_rect.y1;
+
+    const int depth = target->repr.bits.color_depth;
+    int applied_dither = 0;
+    if (depth && (depth < 16 || params->force_dither)) {
+        if (params->error_diffusion && !(rr->errors & PL_RENDER_ERR_ERROR_DIFFUSION)) {
+            pass->sh = NULL;
+            if (plb_pass_error_diffusion(rr, rr->dp, &sh, depth, plane->components, rx1 - rx0,
+                                         ry1 - ry0, rr->fbofmt[4], params->error_diffusion,
+                                         get_fbo_cb, pass)) {
+                applied_dither = depth;
+            } else {
+                rr->errors |= PL_RENDER_ERR_ERROR_DIFFUSION;
+                if (!sh)
+                    return false;
+            }
+            pass->sh = sh;
+        }
+        if (!applied_dither && params->dither_params) {
+            struct pl_dither_params dparams = *params->dither_params;
+            if (!params->disable_dither_gamma_correction)
+                dparams.transfer = target->color.transfer;
+            pl_shader_dither(sh, depth, &rr->dither_state, &dparams);
+            applied_dither = depth;
+        }
+    }
+    if (applied_dither != rr->prev_dither) {
+        if (applied_dither)
+            PLB_INFO(rr->log, "Dithering to %d bit depth", applied_dither);
+        else
+            PLB_INFO(rr->log, "Dithering disabled");
+        rr->prev_dither = applied_dither;
+    }
+
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
+    if (!op)
+        return false;
+    op->u.scale.s = (float) (1.0 / scale);
+    op->u.scale.with_alpha = 1;
+    if (!plb_record_swizzle(sh, plane->components, plane->component_mapping, false))
+        return false;
+
+    pass->sh = NULL;
+    return pl_dispatch_finish(rr->dp, pl_dispatch_params(
+        .shader = &sh,
+        .target = plane->texture,
+        .rect = { rx0, ry0, rx1, ry1 },
+    ));
+}
+
+// ---------------------------------------------------------------------------------------
+// entry points
+// ---------------------------------------------------------------------------------------
+
+static bool check_params(pl_renderer rr, const struct pl_render_params *p,
+                         const struct pl_frame *image, const struct pl_frame *target)
+{
+#define REJECT(cond, what) \
+    if (cond) { \
+        PLB_ERR(rr->log, "pl_render_image: %s is outside the CUDA hot path (SURVEY.md §2)", what); \
+        return false; \
+    }
+    REJECT(p->num_hooks, "user hooks");
+    REJECT(p->lut, "custom LUTs");
+    REJECT(image->lut || target->lut, "per-frame LUTs");
+    REJECT(image->icc || target->icc, "ICC profiles");
+    REJECT(image->num_overlays || target->num_overlays, "overlays");
+    REJECT(p->cone_params, "cone distortion");
+    REJECT(p->blend_params, "blending");
+    REJECT(p->deinterlace_params && image->field != PL_FIELD_NONE, "deinterlacing");
+    REJECT(p->distort_params, "distortion");
+    REJECT(p->corner_rounding > 0, "corner rounding");
+    REJECT(p->border == PL_CLEAR_BLUR, "blurred borders");
+#undef REJECT
+    if (!image->num_planes || image->num_planes > PL_MAX_PLANES ||
+        !target->num_planes || target->num_planes > PL_MAX_PLANES) {
+        PLB_ERR(rr->log, "pl_render_image: invalid number of planes");
+        return false;
+    }
+    for (int i = 0; i < image->num_planes; i++) {
+        const struct pl_plane *pl = &image->planes[i];
+        if (!pl->texture || !pl->texture->params.sampleable || pl->components <= 0 ||
+            pl->components > 4) {
+            PLB_ERR(rr->log, "pl_render_image: invalid source plane %d", i);
+            return false;
+        }
+    }
+    for (int i = 0; i < target->num_planes; i++) {
+        const struct pl_plane *pl = &target->planes[i];
+        if (!pl->texture || !pl->texture->params.renderable || pl->components <= 0 ||
+            pl->components > 4) {
+            PLB_ERR(rr->log, "pl_render_image: invalid target plane %d", i);
+            return false;
+        }
+    }
+    if (!pl_rect_w(image->crop) != !pl_rect_h(image->crop) ||
+        !pl_rect_w(target->crop) != !pl_rect_h(target->crop)) {
+        PLB_ERR(rr->log, "pl_render_image: inconsistent crop");
+        return false;
+    }
+    return true;
+}
+
+static bool pass_begin(struct pass_state *pass)
+{
+    pl_renderer rr = pass->rr;
+    if (!check_params(rr, pass->params, &pass->image, &pass->target))
+        return false;
+    if (!find_fbo_format(pass))
+        return false;
+    if (!pass_fix_frames(pass))
+        return false;
+    if (rr->have_frame_index)
+        pl_dispatch_set_frame_index(rr->dp, rr->frame_index);
+    else
+        pl_dispatch_reset_frame(rr->dp);
+    memset(rr->fbo_used, 0, sizeof(rr->fbo_used));
+    return true;
+}
+
+bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
+                     const struct pl_frame *ptarget, const struct pl_render_params *params)
+{
+    params = params ? params : &pl_render_default_params;
+    if (!pimage || !ptarget) {
+        PLB_ERR(rr->log, "pl_render_image: image and target are required");
+        return false;
+    }
+    struct pass_state pass = {
+        .rr = rr,
+        .params = params,
+        .image = *pimage,
+        .target = *ptarget,
+    };
+    if (!pass_begin(&pass))
+        return false;
+    if (!pl_rect_w(pass.dst_rect) || !pl_rect_h(pass.dst_rect))
+        return true; // empty crop
+    bool ok = pass_read_image(&pass) && pass_scale_main(&pass) && pass_convert_colors(&pass) &&
+              pass_output_target(&pass);
+    if (!ok) {
+        PLB_ERR(rr->log, "Failed rendering image!");
+        pl_dispatch_abort(rr->dp, &pass.sh);
+    }
+    return ok;
+}
+
+// Phase 1 of the frame-parallel scheme: run the path up to (and including) the peak detection
+// tap, keep only the raw statistics
+bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
+                              const struct pl_render_params *params, void *out_peak_buf)
+{
+    params = params ? params : &pl_render_default_params;
+    if (!params->peak_detect_params) {
+        PLB_ERR(rr->log, "pl_renderer_measure_peak: peak_detect_params required");
+        return false;
+    }
+    // a dummy target of the same size/space as the image: only its colour space matters
+    struct pl_frame target = {
+        .num_planes = 1,
+        .planes = {{ .texture = pimage->planes[0].texture, .components = 3,
+                     .component_mapping = {0, 1, 2} }},
+        .repr = { .sys = PL_COLOR_SYSTEM_RGB, .levels = PL_COLOR_LEVELS_FULL },
+        .color = pl_color_space_bt709,
+    };
+    struct pass_state pass = { .rr = rr, .params = params, .image = *pimage, .target = target };
+    const bool had_override = rr->have_peak_override;
+    rr->have_peak_override = false;
+    bool ok = false;
+    struct pl_render_params hacked = *params;
+    hacked.upscaler = hacked.downscaler = NULL;
+    pass.params = &hacked;
+    if (!find_fbo_format(&pass))
+        goto done;
+    // skip the rect fixing against the dummy target: measure on the source grid
+    pass.src_ref = frame_ref(&pass.image);
+    {
+        pl_tex ref = pass.image.planes[pass.src_ref].texture;
+        pl_rect2df *crop = &pass.image.crop;
+        if ((!crop->x0 && !crop->x1) || (!crop->y0 && !crop->y1))
+            *crop = (pl_rect2df) { 0, 0, ref->params.w, ref->params.h };
+        pass.dst_rect = (pl_rect2d) { 0, 0, roundf(pl_rect_w(*crop)), roundf(pl_rect_h(*crop)) };
+    }
+    fix_frame(&pass.image);
+    pl_color_space_infer_map(&pass.image.color, &pass.target.color);
+    if (pass.image.repr.alpha == PL_ALPHA_UNKNOWN)
+        pass.image.repr.alpha = PL_ALPHA_INDEPENDENT;
+    if (rr->have_frame_index)
+        pl_dispatch_set_frame_index(rr->dp, rr->frame_index);
+    else
+        pl_dispatch_reset_frame(rr->dp);
+    memset(rr->fbo_used, 0, sizeof(rr->fbo_used));
+    if (!pass_read_image(&pass))
+        goto done;
+    pl_reset_detected_peak(rr->tone_map_state);
+    if (!pl_shader_detect_peak(img_sh(&pass), pass.color, &rr->tone_map_state,
+                               params->peak_detect_params))
+        goto done;
+    {
+        pl_shader sh = pass.sh;
+        pass.sh = NULL;
+        ok = plb_dispatch_run(rr->dp, sh, NULL, (pl_rect2d) {0}, pass.w, pass.h, NULL);
+        pl_dispatch_abort(rr->dp, &sh);
+    }
+    if (ok) {
+        struct plb_peak_state *pk = &rr->tone_map_state->u.cmap.peak;
+        ok = plb_dev_download(rr->gpu, out_peak_buf, pk->dev_buf, PL_PEAK_BUF_SIZE);
+        pk->pending = false;
+    }
+done:
+    pl_dispatch_abort(rr->dp, &pass.sh);
+    rr->have_peak_override = had_override;
+    return ok;
+}

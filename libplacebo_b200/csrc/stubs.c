@@ -51,3 +51,37 @@ bool pl_shader_error_diffusion(pl_shader sh, const struct pl_error_diffusion_par
     plb_shader_fail(sh, "error diffusion: not implemented yet");
     return false;
 }
+
+bool plb_record_swizzle(pl_shader sh, int comps, const int comp_map[4], bool force_alpha)
+{
+    static const int def_map[4] = {0, 1, 2, 3};
+    comp_map = comp_map ? comp_map : def_map;
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SWIZZLE);
+    if (!op)
+        return false;
+    for (int k = 0; k < 4; k++)
+        op->u.swizzle.map[k] = comp_map[k];
+    op->u.swizzle.comps = comps;
+    op->u.swizzle.force_alpha = force_alpha;
+    return true;
+}
+
+bool plb_plane_film_grain(pl_renderer rr, pl_shader sh, pl_shader_obj *state,
+                          const struct pl_frame *image, const struct pl_plane *plane,
+                          pl_tex tex, pl_tex luma_tex, int luma_comp, struct pl_color_repr *repr)
+{
+    (void) rr; (void) state; (void) image; (void) plane; (void) tex; (void) luma_tex;
+    (void) luma_comp; (void) repr;
+    plb_shader_fail(sh, "film grain: not implemented yet");
+    return false;
+}
+
+bool plb_pass_error_diffusion(pl_renderer rr, pl_dispatch dp, pl_shader *sh, int new_depth,
+                              int comps, int out_w, int out_h, pl_fmt fbofmt,
+                              const struct pl_error_diffusion_kernel *kernel,
+                              pl_tex (*get_fbo)(void *, int, int, pl_fmt, int), void *priv)
+{
+    (void) rr; (void) dp; (void) sh; (void) new_depth; (void) comps; (void) out_w; (void) out_h;
+    (void) fbofmt; (void) kernel; (void) get_fbo; (void) priv;
+    return false;
+}

@@ -499,6 +499,12 @@ void orc_detect_peak(const float *rgba, int w, int h, const struct orc_peak_para
     const float cutoff = fmaxf(p->black_cutoff, 0.0f) * 1e-2f;
     const float to_pq = SDR_WHITE / 10000.0f;
 
+    // linearization is pointwise: do the whole image in one (parallel) call, then walk the
+    // work groups serially
+    float *lin = malloc((size_t) w * h * 4 * sizeof(float));
+    memcpy(lin, rgba, (size_t) w * h * 4 * sizeof(float));
+    orc_linearize(lin, (size_t) w * h, p->trc, p->csp_min, p->csp_max, p->luma_coeffs);
+
     for (int wy = 0; wy < gh; wy++) {
         for (int wx = 0; wx < gw; wx++) {
             unsigned wg_idx = wy * gw + wx, slice = wg_idx % ORC_PEAK_SLICES;
@@ -509,9 +515,7 @@ void orc_detect_peak(const float *rgba, int w, int h, const struct orc_peak_para
                     int x = wx * p->wg_w + lx, y = wy * p->wg_h + ly;
                     x = x < w ? x : w - 1; // clamped texture fetch beyond the edge
                     y = y < h ? y : h - 1;
-                    float px[4];
-                    memcpy(px, rgba + ((size_t) y * w + x) * 4, sizeof(px));
-                    orc_linearize(px, 1, p->trc, p->csp_min, p->csp_max, p->luma_coeffs);
+                    const float *px = lin + ((size_t) y * w + x) * 4;
                     float luma = p->luma_coeffs[0] * px[0];
                     luma = fmaf(p->luma_coeffs[1], px[1], luma);
                     luma = fmaf(p->luma_coeffs[2], px[2], luma);
@@ -550,6 +554,7 @@ void orc_detect_peak(const float *rgba, int w, int h, const struct orc_peak_para
             }
         }
     }
+    free(lin);
 }
 
 // measure_peak, colorspace.c:1020-1069

@@ -52,6 +52,7 @@ struct shim_objs {
 struct shim_ctx {
     pl_gpu gpu;
     pl_dispatch dp;
+    pl_renderer rr;
     struct shim_objs objs;
 };
 
@@ -74,6 +75,7 @@ API void shim_destroy(struct shim_ctx *c)
     if (!c)
         return;
     shim_reset_objs(c);
+    pl_renderer_destroy(&c->rr);
     pl_dispatch_destroy(&c->dp);
     pl_cuda_destroy(&c->gpu);
     free(c);
@@ -303,4 +305,134 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
 done:
     pl_dispatch_abort(c->dp, &sh);
     return ret;
+}
+
+/* ---- pl_render_image driver ------------------------------------------------------------------
+ * planes: up to 3 source textures (Y, U, V) or a single packed one (nplanes = 1, RGB)
+ * img / tgt: repr (sys, levels, sample_depth, color_depth, bit_shift) followed by csp[20]
+ * opts: [0] deband  [1] peak detect (0 off, 1 default, 2 hq)  [2] allow_delayed
+ *       [3] dither (0 off, 1 blue noise default, 2 ordered LUT, 3 ordered fixed, 4 white)
+ *       [4] colour map preset (0 default, 1 hq without contrast recovery)  [5] chroma location
+ *       [6] sigmoid  [7] frame index (-1: renderer counts)  [8] error diffusion kernel idx+1
+ *       [9] tone fn idx+1  [10] gamut fn idx+1 [11] temporal dither [12] film grain (1 = AV1 fixture)
+ *       [13] grain seed
+ */
+static struct pl_av1_grain_data shim_av1_fixture(void);
+
+API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, const float *img,
+                    const float *tgt, const int *opts, const char *upscaler,
+                    const char *plane_upscaler, const char *downscaler, float *out_peak)
+{
+    if (!c->rr)
+        c->rr = pl_renderer_create(shim_log, c->gpu);
+    struct pl_frame image = {
+        .num_planes = nplanes,
+        .repr = { .sys = (int) img[0], .levels = (int) img[1],
+                  .bits = { (int) img[2], (int) img[3], (int) img[4] } },
+        .color = csp_from_flat(img + 5),
+    };
+    if (nplanes == 3) {
+        for (int i = 0; i < 3; i++) {
+            image.planes[i] = (struct pl_plane) {
+                .texture = planes[i],
+                .components = 1,
+                .component_mapping = { i },
+            };
+        }
+        pl_frame_set_chroma_location(&image, opts[5] ? opts[5] : PL_CHROMA_LEFT);
+    } else {
+        image.planes[0] = (struct pl_plane) {
+            .texture = planes[0],
+            .components = 3,
+            .component_mapping = { 0, 1, 2 },
+        };
+    }
+    if (opts[12]) {
+        image.film_grain.type = PL_FILM_GRAIN_AV1;
+        image.film_grain.seed = (uint64_t) opts[13];
+        image.film_grain.params.av1 = shim_av1_fixture();
+        image.film_grain.params.av1.overlap = opts[12] > 1;
+    }
+    pl_tex dtex = dst;
+    struct pl_frame target = {
+        .num_planes = 1,
+        .planes = {{
+            .texture = dtex,
+            .components = dtex->params.format->num_components,
+            .component_mapping = { 0, 1, 2, 3 },
+        }},
+        .repr = { .sys = (int) tgt[0], .levels = (int) tgt[1],
+                  .bits = { (int) tgt[2], (int) tgt[3], (int) tgt[4] } },
+        .color = csp_from_flat(tgt + 5),
+    };
+
+    struct pl_deband_params deband = pl_deband_default_params;
+    struct pl_peak_detect_params peak = opts[1] == 2 ? pl_peak_detect_high_quality_params
+                                                     : pl_peak_detect_default_params;
+    peak.allow_delayed = opts[2];
+    struct pl_dither_params dither = pl_dither_default_params;
+    if (opts[3] > 1)
+        dither.method = opts[3] - 1;
+    dither.temporal = opts[11];
+    struct pl_color_map_params cmap = opts[4] ? pl_color_map_high_quality_params
+                                              : pl_color_map_default_params;
+    cmap.contrast_recovery = 0;
+    if (opts[9])
+        cmap.tone_mapping_function = pl_tone_map_functions[opts[9] - 1];
+    if (opts[10])
+        cmap.gamut_mapping = pl_gamut_map_functions[opts[10] - 1];
+    struct pl_render_params par = {
+        PL_RENDER_DEFAULTS
+        .upscaler = upscaler && *upscaler ? pl_find_filter_config(upscaler, 0) : NULL,
+        .downscaler = downscaler && *downscaler ? pl_find_filter_config(downscaler, 0) : NULL,
+        .plane_upscaler = plane_upscaler && *plane_upscaler ? pl_find_filter_config(plane_upscaler, 0) : NULL,
+        .deband_params = opts[0] ? &deband : NULL,
+        .peak_detect_params = opts[1] ? &peak : NULL,
+        .dither_params = opts[3] ? &dither : NULL,
+        .sigmoid_params = opts[6] ? &pl_sigmoid_default_params : NULL,
+        .error_diffusion = opts[8] ? pl_error_diffusion_kernels[opts[8] - 1] : NULL,
+    };
+    par.color_map_params = &cmap;
+    if (opts[7] >= 0)
+        pl_renderer_set_frame_index(c->rr, (uint8_t) opts[7]);
+    if (!pl_render_image(c->rr, &image, &target, &par))
+        return -1;
+    if (out_peak) {
+        struct pl_hdr_metadata md = {0};
+        if (pl_renderer_get_hdr_metadata(c->rr, &md)) {
+            out_peak[0] = md.avg_pq_y;
+            out_peak[1] = md.max_pq_y;
+        }
+    }
+    return pl_renderer_get_errors(c->rr).errors;
+}
+
+API void shim_renderer_reset(struct shim_ctx *c)
+{
+    pl_renderer_destroy(&c->rr);
+}
+
+/* the AV1 grain parameters of the reference's own test fixture (src/tests/utils.h:240-262) */
+static struct pl_av1_grain_data shim_av1_fixture(void)
+{
+    return (struct pl_av1_grain_data) {
+        .num_points_y = 6,
+        .points_y = {{0, 4}, {27, 33}, {54, 55}, {67, 61}, {108, 71}, {255, 72}},
+        .chroma_scaling_from_luma = false,
+        .num_points_uv = {2, 2},
+        .points_uv = {{{0, 64}, {255, 64}}, {{0, 64}, {255, 64}}},
+        .scaling_shift = 11,
+        .ar_coeff_lag = 3,
+        .ar_coeffs_y = {4, 1, 3, 0, 1, -3, 8, -3, 7, -23, 1, -25,
+                        0, -10, 6, -17, -4, 53, 36, 5, -5, -17, 8, 66},
+        .ar_coeffs_uv = {
+            {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 127},
+            {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 127},
+        },
+        .ar_coeff_shift = 7,
+        .grain_scale_shift = 0,
+        .uv_mult = {0, 0},
+        .uv_mult_luma = {64, 64},
+        .uv_offset = {0, 0},
+    };
 }

@@ -1,0 +1,335 @@
+"""CPU restatement of the reference's per-frame pass graph (src/renderer.c pl_render_image)
+for planar YCbCr 4:2:0 sources and one packed RGB target, composed from the oracle's per-stage
+functions (oracle/pl_oracle*.c). It is written independently of libplacebo_b200/csrc/renderer.c
+(numpy, different structure) so that the two planners check each other, and it is also the
+"port" CPU baseline that bench.py times.
+
+Pass graph (file:line in /root/reference/src/renderer.c):
+  merge U+V into one rg16 texture (exact copy)                               :1617-1699
+  per plane: deband (:1318) -> chroma stored to an rg16hf FBO (:1861) -> plane scaler (:1864)
+  merged pass: planes -> colour, decode_color (:1942)                        :1788-1957
+  main scaler: [peak detect] [linearize] [sigmoid] -> rgba16hf FBO -> polar  :1964-2087
+  colour map: [rgba16hf FBO when same-frame peak] -> color_map_ex            :2157-2279
+  output: encode_color, dither, 1/scale, store                               :2586-2964
+"""
+import ctypes as C
+
+import numpy as np
+
+import plbtest as T
+
+f32 = np.float32
+
+
+def _filter_for(t0, name, rx, ry, no_widening=False):
+    """pl_shader_sample_polar's filter config: blur widened when downscaling (sampling.c:608-616)"""
+    inv = f32(1.0) / f32(min(rx, ry))
+    inv = max(inv, f32(1.0))
+    if no_widening:
+        inv = f32(1.0)
+    base = t0.filter_generate(name)
+    blur = f32(base["blur"] if base["blur"] else 1.0) * f32(inv)
+    return t0.filter_generate(name, blur=float(blur)) if blur != 1.0 else base
+
+
+def luma_coeffs(t0, prim):
+    return t0.matrix(0, t0.raw_primaries(prim))[3:6].copy()
+
+
+class Frame:
+    def __init__(self, planes, sys, levels=T.LEVELS["LIMITED"], sample_depth=16, color_depth=10,
+                 bit_shift=0, csp=None, chroma_loc="left"):
+        self.planes = planes
+        self.sys, self.levels = sys, levels
+        self.bits = (sample_depth, color_depth, bit_shift)
+        self.csp = csp if csp is not None else T.csp()
+        self.chroma_loc = chroma_loc
+
+
+class Target:
+    def __init__(self, w, h, fmt="rgba16hf", sys=T.SYS["RGB"], levels=T.LEVELS["FULL"],
+                 sample_depth=0, color_depth=0, csp=None):
+        self.w, self.h, self.fmt = w, h, fmt
+        self.sys, self.levels = sys, levels
+        self.bits = (sample_depth, color_depth, 0)
+        self.csp = csp if csp is not None else T.csp()
+
+
+CHROMA_SHIFT = {"left": (-0.5, 0.0), "center": (0.0, 0.0), "top_left": (-0.5, -0.5)}
+CHROMA_ENUM = {"left": 1, "center": 2, "top_left": 3}
+
+
+def fix_bits(fmt_depth, bits):
+    """fix_frame (renderer.c:3131-3160) for UNORM textures"""
+    sd, cd, sh = bits
+    if not sd and fmt_depth:
+        sd = fmt_depth
+        cd = cd or sd
+        cd = min(cd, sd)
+        sh += sd - cd
+    return sd, cd, sh
+
+
+def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0,
+           allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
+           coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None):
+    """Returns (output array in target storage type, new peak state). `peak_state` carries the
+    smoothed (avg, max) between frames like sh_color_map_obj.peak does."""
+    t0, orc = T.t0(), T.oracle()
+    Y, U, V = img.planes
+    H, W = Y.shape
+    ch, cw = U.shape
+    plane_up = plane_upscaler or upscaler
+
+    # ---- colour spaces / representation fix-ups (pass_fix_frames :3195-3233)
+    src_csp = img.csp.copy()
+    if not src_csp[0]:
+        src_csp[0] = T.PRIM["BT_709"] if (W >= 1280 or H > 576) else (
+            T.PRIM["BT_601_625"] if H == 576 else T.PRIM["BT_601_525"] if H in (480, 486) else T.PRIM["BT_709"])
+    src_csp, dst_csp = t0.csp_infer_map(src_csp, tgt.csp)
+    sbits = fix_bits(16, img.bits)
+    tdepth = {"rgba8": 8, "rgba16": 16}.get(tgt.fmt, 0)
+    tbits = fix_bits(tdepth, tgt.bits)
+
+    norm = t0.repr_decode(img.sys, img.levels, *sbits)["scale"]  # pl_color_repr_normalize
+    ycbcr = img.sys not in (T.SYS["UNKNOWN"], T.SYS["RGB"], T.SYS["XYZ"])
+    limited = (img.levels or (T.LEVELS["LIMITED"] if ycbcr else T.LEVELS["FULL"])) == T.LEVELS["LIMITED"]
+    out_scale = f32(2.0 ** sbits[0]) / (f32(2.0 ** sbits[0]) - f32(1.0))
+    neutral_luma = f32(16 / 256.0) * out_scale if limited else f32(0.0)
+    neutral_chroma = f32(0.5) * out_scale if ycbcr else neutral_luma
+
+    Yf = T.unorm16_to_float(Y)[:, :, None]
+    UVf = np.stack([T.unorm16_to_float(U), T.unorm16_to_float(V)], -1)  # merged rg16: exact
+
+    # ---- B. per plane
+    grain = f32(4.0) / (f32(src_csp[11]) / f32(203.0))  # dparams.grain /= max_luma / SDR_WHITE
+    sx, sy = CHROMA_SHIFT[img.chroma_loc]
+    rrx, rry = cw / W, ch / H
+    crect = ((0 - sx) * rrx, (0 - sy) * rry, (W - sx) * rrx, (H - sy) * rry)
+    if deband:
+        luma = orc.deband(Yf, 1, 3.0, 16.0, float(grain), (neutral_luma, 0, 0), float(norm), 1, frame_index)
+        luma_v = luma[..., 0]
+        cdb = orc.deband(UVf, 1, 3.0, 16.0, float(grain), (neutral_chroma, neutral_chroma, 0),
+                         float(norm), 3, frame_index)
+        ctex = orc.store_round(cdb[..., :2], 0)  # rg16hf FBO
+        cscale = 1.0
+    else:
+        luma_v = (Yf[..., 0] * f32(norm)).astype(f32)
+        ctex, cscale = UVf, float(norm)
+
+    # plane scaler (SAMPLER_PLANE)
+    crect_f = tuple(f32(v) for v in crect)
+    if plane_up and (cw != W or ch != H):
+        rx, ry = W / (crect[2] - crect[0]), H / (crect[3] - crect[1])
+        filt = _filter_for(t0, plane_up, rx, ry)
+        chroma = orc.sample_polar(ctex, W, H, filt, comp_mask=3, rect=crect_f, scale=cscale,
+                                  coord_mode=coord_mode)
+    else:
+        chroma = orc.sample_direct(ctex, W, H, linear=(cw != W or ch != H), rect=crect_f,
+                                   scale=cscale, coord_mode=coord_mode)
+
+    # ---- C. merge + decode
+    color = np.empty((H, W, 4), f32)
+    color[..., 0] = luma_v
+    color[..., 1] = chroma[..., 0]
+    color[..., 2] = chroma[..., 1]
+    color[..., 3] = 1.0
+    dec = t0.repr_decode(img.sys, img.levels, sbits[0], sbits[0], 0)  # repr already normalised
+    color = orc.apply_matrix(color, dec["m"], dec["c"])
+    if img.sys in (T.SYS["BT_2020_C"], T.SYS["BT_2100_PQ"], T.SYS["BT_2100_HLG"]):
+        color = orc.decode_special(color, img.sys)
+
+    src_trc = int(src_csp[1])
+    src_hdr = src_csp[11] > 203.0 or src_trc in (T.TRC["PQ"], T.TRC["HLG"], T.TRC["V_LOG"],
+                                                 T.TRC["S_LOG1"], T.TRC["S_LOG2"], T.TRC["SCRGB"])
+    src_luma = luma_coeffs(t0, int(src_csp[0]))
+    smin, smax, _ = t0.nominal_luma(src_csp, T.META["HDR10"], T.HDR["NORM"])
+
+    # ---- peak detection decision (hdr_update_peak :1183-1250)
+    def want_peak():
+        if not peak or not src_hdr:
+            return False
+        max_peak = {T.TRC["PQ"]: 10000.0, T.TRC["SCRGB"]: 10000.0}.get(src_trc, 203.0)
+        if src_trc == T.TRC["HLG"]:
+            max_peak = src_csp[11]
+        return not (max_peak <= dst_csp[11] + 1e-6) and not src_csp[19]
+
+    new_state = peak_state
+    def run_peak(image, wg):
+        nonlocal new_state
+        hq = peak == 2
+        buf = orc.detect_peak(image, src_trc, smin, smax, src_luma, 1.0, hq, wg)
+        st, used = orc.peak_update(peak_state or (0.0, 0.0), buf, 20.0, 1.0, 3.0,
+                                   99.995 if hq else 100.0)
+        new_state = st
+        if stats is not None:
+            stats["peak_buf"] = buf
+
+    # work-group geometry of the merged pass: rigid 32x32 if it contains a polar compute
+    # sampler (radius < 6), else the flexible 16x16 of detect_peak
+    merged_has_polar = bool(plane_up) and (cw != W or ch != H) and plane_up.startswith("ewa")
+    wg = (32, 32) if merged_has_polar else (16, 16)
+
+    # ---- D. main scaler
+    out_w, out_h = tgt.w, tgt.h
+    up = out_w > W or out_h > H
+    down = out_w < W or out_h < H
+    scaling = up or down
+    measured = False
+    if scaling and up and want_peak():
+        run_peak(color, wg)
+        measured = True
+    if scaling:
+        main = upscaler if up else None
+        img_fbo = orc.store_round(color, 0)  # rgba16hf FBO at source size
+        if main and main.startswith("ewa"):
+            filt = _filter_for(t0, main, out_w / W, out_h / H)
+            color = orc.sample_polar(img_fbo, out_w, out_h, filt, comp_mask=7, coord_mode=coord_mode)
+            wg = (32, 32)
+        else:
+            color = orc.sample_direct(img_fbo, out_w, out_h, linear=True, coord_mode=coord_mode)
+            wg = (16, 16)
+    if not measured and want_peak():
+        run_peak(color, wg)
+        measured = True
+        if not allow_delayed:
+            color = orc.store_round(color, 0)  # need_peak_fbo: rgba16hf at output size
+
+    # ---- colour mapping (pl_shader_color_map_ex host logic, colorspace.c:1618-1790)
+    src2 = src_csp.copy()
+    use = new_state if (measured and not allow_delayed) else peak_state
+    if peak and use and use[0]:
+        src2[19], src2[18] = use[0], use[1]
+    cm = color_map_params(t0, src2, dst_csp, hq=cmap_hq, tone_fn=tone_fn, gamut_fn=gamut_fn)
+    if cm is not None:
+        color = orc.color_map(color, cm["params"])
+
+    # ---- output: encode, dither, scale, store
+    enc_skip = (tgt.sys in (T.SYS["UNKNOWN"], T.SYS["RGB"]) and tgt.levels in (0, T.LEVELS["FULL"])
+                and (not tbits[0] or not tbits[1] or tbits[0] == tbits[1]) and not tbits[2])
+    tnorm = t0.repr_decode(tgt.sys, tgt.levels, *tbits)["scale"]
+    if not enc_skip:
+        enc = t0.repr_encode(tgt.sys, tgt.levels, tbits[0], tbits[0], 0)
+        color = orc.apply_matrix(color, enc["m"], enc["c"])
+    depth = tbits[1]
+    if depth and depth < 16 and dither:
+        lut = t0.dither_matrix(0 if dither == 1 else 1, 64) if dither in (1, 2) else None
+        method = {1: 0, 2: 1, 3: 2, 4: 3}[dither]
+        gamma = approx_gamma(int(dst_csp[1]))
+        color = orc.dither(color, depth, method, lut, False, frame_index, gamma)
+    color = orc.scale(color, float(f32(1.0 / tnorm)), True)
+    color[..., 3] = 1.0  # swizzle_color leaves alpha = 1 for opaque images
+    return store(orc, color, tgt.fmt), new_state
+
+
+def approx_gamma(trc):
+    g = {0: 1.0, 3: 1.0, 17: 1.0, 10: 1.8, 4: 1.8, 5: 2.0, 7: 2.4, 8: 2.6, 11: 2.6, 9: 2.8,
+         2: 2.2, 1: 2.2, 6: 2.2}
+    return g.get(trc, 2.0)
+
+
+def store(orc, color, fmt):
+    if fmt == "rgba16hf":
+        return orc.store_half(color)
+    if fmt == "rgba16":
+        return orc.store_unorm(color, 16)
+    if fmt == "rgba8":
+        return orc.store_unorm(color, 8).astype(np.uint8)
+    return color
+
+
+_keepalive = []
+
+
+def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None):
+    """Host logic of pl_shader_color_map_ex -> OrcColorMap (or None when src == dst)."""
+    src, dst = t0.csp_infer_map(src, dst)
+    if np.array_equal(src, dst):
+        return None
+    tone_fn = tone_fn or "spline"
+    gamut_fn = gamut_fn or "perceptual"
+    imin, imax, iavg = t0.nominal_luma(src, T.META["ANY"], T.HDR["PQ"])
+    omin, omax, _ = t0.nominal_luma(dst, T.META["HDR10"], T.HDR["PQ"])
+    tone = t0.tone_map_generate(tone_fn, imin, imax, iavg, omin, omax, hdr_csp=src)
+    tpar = tone["params"]
+    imin, imax, iavg, omin, omax = (f32(v) for v in tpar[3:8])
+    if abs(float(imax) - float(omax)) < 1e-6:
+        omax = imax
+    if abs(float(imin) - float(omin)) < 1e-6:
+        omin = imin
+    omax = min(omax, imax)  # no inverse tone mapping
+    # regenerate with the adjusted range (infer is idempotent)
+    tone = t0.tone_map_generate(tone_fn, imin, imax, iavg, omin, omax, hdr_csp=src)
+    need_tone = not tone["noop"]
+
+    gmin, gmax, _ = t0.nominal_luma(dst, T.META["HDR10"], T.HDR["PQ"])
+    in_prim, out_prim = src[2:10].copy(), dst[2:10].copy()
+    bidir = gamut_fn in ("perceptual", "saturation")
+    if bidir and t0.primaries_compatible(in_prim, out_prim):
+        out_prim, _ = t0.primaries_clip(out_prim, in_prim)
+    g = t0.gamut_map_generate(gamut_fn, in_prim, out_prim, gmin, gmax, generate=False)
+    need_gamut = not g["noop"]
+
+    rgb2lms = t0.matrix(2, t0.raw_primaries(int(src[0])))
+    lms2rgb = t0.matrix(3, t0.raw_primaries(int(dst[0])))
+    smin, smax, _ = t0.nominal_luma(src, T.META["HDR10"], T.HDR["NORM"])
+    dmin, dmax, _ = t0.nominal_luma(dst, T.META["HDR10"], T.HDR["NORM"])
+    p = T.OrcColorMap()
+    p.src_trc, p.dst_trc = int(src[1]), int(dst[1])
+    p.src_min, p.src_max, p.dst_min, p.dst_max = smin, smax, dmin, dmax
+    p.src_luma = (C.c_float * 3)(*luma_coeffs(t0, int(src[0])))
+    p.dst_luma = (C.c_float * 3)(*luma_coeffs(t0, int(dst[0])))
+    black_scaled = int(dst[1]) not in (T.TRC["BT_1886"], T.TRC["PQ"], T.TRC["SCRGB"],
+                                       T.TRC["V_LOG"], T.TRC["S_LOG1"], T.TRC["S_LOG2"])
+    p.dst_black_scaled = int(black_scaled)
+    p.prelinearized = 0
+    p.need_tone_map, p.need_gamut_map = int(need_tone), int(need_gamut)
+    if not need_tone and not need_gamut:
+        # fast path: plain primaries conversion
+        m = mat_mul(lms2rgb, rgb2lms) if int(src[0]) != int(dst[0]) else np.eye(3, dtype=f32).ravel()
+        p.lms2rgb = (C.c_float * 9)(*m)
+        p.rgb2lms = (C.c_float * 9)(*rgb2lms)
+        return dict(params=p)
+    p.rgb2lms = (C.c_float * 9)(*rgb2lms)
+    p.lms2rgb = (C.c_float * 9)(*lms2rgb)
+    keep = []
+    if need_tone:
+        lut = np.ascontiguousarray(tone["lut"], f32)
+        keep.append(lut)
+        p.tone_kind = 1 if tone_fn == "clip" else 0
+        p.tone_lut, p.tone_lut_size = T.fp(lut), lut.size
+        p.tone_input_min, p.tone_input_max = imin, imax
+        p.tone_output_min, p.tone_output_max = omin, omax
+        p.tone_exposure = 1.0
+    if need_gamut:
+        full = t0.gamut_map_generate(gamut_fn, in_prim, out_prim, gmin, gmax)["lut"].reshape(-1, 3)
+        q = np.zeros((full.shape[0], 4), np.uint16)
+        # fill_gamut_lut (src/shaders/colorspace.c:1589-1610)
+        q[:, 0] = c_roundf(full[:, 0] * f32(65535))
+        q[:, 1] = c_roundf(full[:, 1] * f32(65535) + f32(32767))
+        q[:, 2] = c_roundf(full[:, 2] * f32(65535) + f32(32767))
+        glut = T.unorm16_to_float(q)
+        keep.append(glut)
+        p.gamut_lut = T.fp(glut)
+        p.lut_I, p.lut_C, p.lut_h = 48, 32, 256
+        p.gamut_min_luma, p.gamut_max_luma = gmin, gmax
+    _keepalive.append(keep)
+    if len(_keepalive) > 8:
+        _keepalive.pop(0)
+    return dict(params=p, tone=tone, keep=keep)
+
+
+def c_roundf(a):
+    """C roundf (half away from zero) on float32 arrays, result as uint16"""
+    a = np.asarray(a, f32)
+    return (np.sign(a) * np.floor(np.abs(a) + f32(0.5))).astype(np.int64).astype(np.uint16)
+
+
+def mat_mul(a, b):
+    """pl_matrix3x3_mul in float32, same summation order (src/common.c:171-182)"""
+    a, b = a.reshape(3, 3).astype(f32), b.reshape(3, 3).astype(f32)
+    o = np.zeros((3, 3), f32)
+    for r in range(3):
+        for c in range(3):
+            o[r, c] = f32(f32(f32(a[r, 0] * b[0, c]) + f32(a[r, 1] * b[1, c])) + f32(a[r, 2] * b[2, c]))
+    return o.ravel()

@@ -220,6 +220,10 @@ class T0:
         compat = self.f("primaries_clip")(fp(src8), fp(dst8), fp(o))
         return o, bool(compat)
 
+    def primaries_compatible(self, a8, b8):
+        return bool(self.f("primaries_compatible")(fp(np.ascontiguousarray(a8, f32)),
+                                                   fp(np.ascontiguousarray(b8, f32))))
+
     def dither_matrix(self, method, size):
         o = np.zeros(size * size, f32)
         self.f("dither_matrix")(method, size, fp(o))

@@ -129,3 +129,18 @@ def test_deband_zero_iterations_is_identity(gpu, oracle):
     src = rand_tex(32, 48, 4, seed=2, dtype=np.float32)
     got = gpu.simple("deband", src, "rgba32f", 48, 32, comps=3, sargs_extra=[0, 0.0, 0.0, 0.0, 0, 0, 0])
     assert np.abs(got[..., :3] - src[..., :3]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("ox,oy", [(0.25, 0.0), (0.0, 0.25), (0.25, 0.25)])
+@pytest.mark.parametrize("comps", [1, 2])
+def test_polar_2x_sited_chroma_phases(gpu, oracle, ox, oy, comps):
+    """4:2:0 chroma with left / top-left siting: source rect offset by a quarter texel, the
+    phase set becomes {0, 1/2}; the tabulated-phase kernel must still equal the oracle."""
+    src = rand_tex(54, 96, comps, seed=21)
+    fmt = {1: "r16hf", 2: "rg16hf"}[comps]
+    f = T.t0().filter_generate("ewa_lanczos")
+    rect = (ox, oy, 96 + ox, 54 + oy)
+    got = gpu.polar(src, fmt, 192, 108, "ewa_lanczos", comps=comps, out_fmt="rgba32f", rect=rect)
+    want = oracle.sample_polar(src.astype(np.float32), 192, 108, f, comp_mask=(1 << comps) - 1,
+                               rect=rect, coord_mode=T.COORD_EXACT)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
