@@ -126,8 +126,23 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
         for (int k = 0; k < 3; k++)
             c[k] *= t.a; // 80/203 literal
         break;
+    case TRC_V_LOG:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.181f <= c[k] ? powf(10.0f, (c[k] - c_pq.vlog_d) * c_pq.vlog_inv_c) - c_pq.vlog_b
+                                  : (c[k] - 0.125f) * (float) (1.0 / 5.6);
+        break;
+    case TRC_S_LOG1:
+        for (int k = 0; k < 3; k++)
+            c[k] = powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b;
+        break;
+    case TRC_S_LOG2:
+        for (int k = 0; k < 3; k++)
+            c[k] = c_pq.slog_q <= c[k]
+                 ? (powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b) * c_pq.slog_inv_k2
+                 : (c[k] - c_pq.slog_q) * c_pq.slog_inv_p;
+        break;
     default:
-        break; // camera log curves: recorded as unsupported by the host (shader fails)
+        break;
     }
     if (post_scale && (t.csp_max != 1 || t.csp_min != 0)) {
         for (int k = 0; k < 3; k++)
@@ -196,6 +211,20 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
     case TRC_SCRGB:
         for (int k = 0; k < 3; k++)
             c[k] *= t.a; // 203/80 literal
+        break;
+    case TRC_V_LOG:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.01f <= c[k] ? c_pq.vlog_c10 * logf(c[k] + c_pq.vlog_b) + c_pq.vlog_d
+                                 : 5.6f * c[k] + 0.125f;
+        break;
+    case TRC_S_LOG1:
+        for (int k = 0; k < 3; k++)
+            c[k] = c_pq.slog_a10 * logf(c[k] + c_pq.slog_b) + c_pq.slog_c;
+        break;
+    case TRC_S_LOG2:
+        for (int k = 0; k < 3; k++)
+            c[k] = 0.0f <= c[k] ? c_pq.slog_a10 * logf(c_pq.slog_k2 * c[k] + c_pq.slog_b) + c_pq.slog_c
+                                : c_pq.slog_p * c[k] + c_pq.slog_q;
         break;
     default:
         break;

@@ -192,6 +192,9 @@ struct plb_pq_consts {
     float m1, m2, c1, c2, c3, inv_m1, inv_m2, to_pq, from_pq, inv_from_pq;
     float hlg_a, hlg_b, hlg_c, hlg_inv_a;
     float inv_2pi;
+    // camera log curves (colorspace.c:629-655, 789-812), constants as printed by "%f"
+    float vlog_b, vlog_d, vlog_inv_c, vlog_c10;
+    float slog_b, slog_c, slog_inv_a, slog_a10, slog_p, slog_inv_p, slog_q, slog_k2, slog_inv_k2;
 };
 
 // ---------------------------------------------------------------------------------------

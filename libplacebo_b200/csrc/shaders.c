@@ -551,6 +551,10 @@ static double glsl6(double x)
 static const float PQ_M1 = 2610./4096 * 1./4, PQ_M2 = 2523./4096 * 128, PQ_C1 = 3424./4096,
                    PQ_C2 = 2413./4096 * 32, PQ_C3 = 2392./4096 * 32;
 static const float HLG_A = 0.17883277, HLG_B = 0.28466892, HLG_C = 0.55991073;
+// Panasonic V-Log / Sony S-Log published curve constants (float-typed, like the reference's)
+static const float VLOG_B = 0.00873, VLOG_C = 0.241514, VLOG_D = 0.598206;
+static const float SLOG_A = 0.432699, SLOG_B = 0.037584, SLOG_C = 0.616596 + 0.03,
+                   SLOG_P = 3.538813, SLOG_Q = 0.030001, SLOG_K2 = 155.0 / 219.0;
 static const float HLG_REF = 1000.0 / PL_COLOR_SDR_WHITE;
 
 void plb_pq_literal(struct plb_pq_consts *q)
@@ -570,6 +574,19 @@ void plb_pq_literal(struct plb_pq_consts *q)
     q->hlg_c = (float) glsl6(HLG_C);
     q->hlg_inv_a = (float) (1.0 / glsl6(HLG_A));
     q->inv_2pi = (float) glsl6(0.5f / M_PI);
+    q->vlog_b = (float) glsl6(VLOG_B);
+    q->vlog_d = (float) glsl6(VLOG_D);
+    q->vlog_inv_c = (float) (1.0 / glsl6(VLOG_C));
+    q->vlog_c10 = (float) glsl6(VLOG_C / M_LN10);
+    q->slog_b = (float) glsl6(SLOG_B);
+    q->slog_c = (float) glsl6(SLOG_C);
+    q->slog_inv_a = (float) (1.0 / glsl6(SLOG_A));
+    q->slog_a10 = (float) glsl6(SLOG_A / M_LN10);
+    q->slog_p = (float) glsl6(SLOG_P);
+    q->slog_inv_p = (float) (1.0 / glsl6(SLOG_P));
+    q->slog_q = (float) glsl6(SLOG_Q);
+    q->slog_k2 = (float) glsl6(SLOG_K2);
+    q->slog_inv_k2 = (float) (1.0 / glsl6(SLOG_K2));
 }
 
 void pl_shader_set_alpha(pl_shader sh, struct pl_color_repr *repr, enum pl_alpha_mode mode)
@@ -769,16 +786,11 @@ static void fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp,
 
 static bool trc_supported(pl_shader sh, enum pl_color_transfer trc)
 {
-    switch (trc) {
-    case PL_COLOR_TRC_V_LOG:
-    case PL_COLOR_TRC_S_LOG1:
-    case PL_COLOR_TRC_S_LOG2:
-        plb_shader_fail(sh, "camera log transfer %d is not implemented on the CUDA backend",
-                        (int) trc);
+    if (trc < 0 || trc >= PL_COLOR_TRC_COUNT) {
+        plb_shader_fail(sh, "invalid transfer function %d", (int) trc);
         return false;
-    default:
-        return true;
     }
+    return true;
 }
 
 void plb_record_linearize(pl_shader sh, const struct pl_color_space *csp)

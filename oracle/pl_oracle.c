@@ -6,6 +6,7 @@
  */
 #define _GNU_SOURCE
 #include "pl_oracle.h"
+#include "pl_oracle_math.h"
 
 #include <math.h>
 #include <stdbool.h>
@@ -425,7 +426,9 @@ void orc_deband(const struct orc_tex *src, const struct orc_deband_params *p, fl
                 // d = RAND.xy * vec2(i * radius, 2pi); d = d.x * vec2(cos(d.y), sin(d.y))
                 float dist = rnd[0] * ((float) i * radius);
                 float dir = rnd[1] * two_pi_lit;
-                float dx = dist * cosf(dir), dy = dist * sinf(dir);
+                float sn, cs;
+                pm_sincosf(dir, &sn, &cs);
+                float dx = dist * cs, dy = dist * sn;
                 const float sgx[4] = {+1, -1, -1, +1}, sgy[4] = {+1, +1, -1, -1};
                 for (int k = 0; k < 4; k++)
                     avg[k] = 0.0f;
@@ -539,6 +542,29 @@ void orc_polar_ideal(const struct orc_tex *src, int dw, int dh, double radius,
             }
             for (int k = 0; k < src->comps; k++)
                 dst[((size_t) gy * dw + gx) * src->comps + k] = acc[k] / wsum;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Array front-end to the portable math definitions (pl_oracle_math.h), for the tests that pin
+// them against libm and against the CUDA restatement.
+//   fn: 0 pow(a,b)  1 exp(a)  2 log(a)  3 sin(a)  4 cos(a)  5 atan2(a,b)  6 log2(a)
+// ------------------------------------------------------------------------------------------
+void orc_math(int fn, const float *a, const float *b, float *out, size_t n)
+{
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        float s, c;
+        switch (fn) {
+        case 0: out[i] = pm_powf(a[i], b[i]); break;
+        case 1: out[i] = pm_expf(a[i]); break;
+        case 2: out[i] = pm_logf(a[i]); break;
+        case 3: pm_sincosf(a[i], &s, &c); out[i] = s; break;
+        case 4: pm_sincosf(a[i], &s, &c); out[i] = c; break;
+        case 5: out[i] = pm_atan2f(a[i], b[i]); break;
+        case 6: out[i] = pm_log2f(a[i]); break;
+        default: out[i] = NAN;
         }
     }
 }

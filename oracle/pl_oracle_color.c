@@ -15,6 +15,7 @@
 #include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include "pl_oracle_math.h"
 #include <string.h>
 
 static inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
@@ -140,66 +141,66 @@ void orc_linearize(float *rgba, size_t npix, int trc, float csp_min, float csp_m
         switch (trc) {
         case TRC_SRGB:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.04045f < c[k] ? powf((c[k] + 0.055f) / 1.055f, 2.4f)
+                c[k] = 0.04045f < c[k] ? pm_powf((c[k] + 0.055f) / 1.055f, 2.4f)
                                        : c[k] * (float) (1.0 / 12.92);
             post_scale = true;
             break;
         case TRC_BT_1886:
             for (int k = 0; k < 3; k++)
-                c[k] = bt_a * powf(c[k] + bt_b, 2.4f);
+                c[k] = bt_a * pm_powf(c[k] + bt_b, 2.4f);
             break;
-        case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 1.8f); post_scale = true; break;
-        case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.0f); post_scale = true; break;
+        case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 1.8f); post_scale = true; break;
+        case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.0f); post_scale = true; break;
         case TRC_UNKNOWN:
-        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.2f); post_scale = true; break;
-        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.4f); post_scale = true; break;
-        case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.6f); post_scale = true; break;
-        case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.8f); post_scale = true; break;
+        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.2f); post_scale = true; break;
+        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.4f); post_scale = true; break;
+        case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.6f); post_scale = true; break;
+        case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.8f); post_scale = true; break;
         case TRC_PRO_PHOTO:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.03125f < c[k] ? powf(c[k], 1.8f) : c[k] * (float) (1.0 / 16.0);
+                c[k] = 0.03125f < c[k] ? pm_powf(c[k], 1.8f) : c[k] * (float) (1.0 / 16.0);
             post_scale = true;
             break;
         case TRC_ST428:
             for (int k = 0; k < 3; k++)
-                c[k] = (float) (52.37 / 48.0) * powf(c[k], 2.6f);
+                c[k] = (float) (52.37 / 48.0) * pm_powf(c[k], 2.6f);
             post_scale = true;
             break;
         case TRC_PQ:
             for (int k = 0; k < 3; k++) {
-                float x = powf(c[k], q.inv_m2);
+                float x = pm_powf(c[k], q.inv_m2);
                 x = fmaxf(x - q.c1, 0.0f) / (q.c2 - q.c3 * x);
-                x = powf(x, q.inv_m1);
+                x = pm_powf(x, q.inv_m1);
                 c[k] = x * q.from_pq;
             }
             break;
         case TRC_HLG: {
             for (int k = 0; k < 3; k++) {
                 float x = (1 - hlg_b) * c[k] + hlg_b;
-                x = 0.5f < x ? expf((x - hlgC) * hlg_inv_a) + hlgB : 4.0f * x * x;
+                x = 0.5f < x ? pm_expf((x - hlgC) * hlg_inv_a) + hlgB : 4.0f * x * x;
                 c[k] = x * (float) (1.0 / 12.0);
             }
             float y = luma[0] * c[0];
             y = fmaf(luma[1], c[1], y);
             y = fmaf(luma[2], c[2], y);
-            float g = csp_max * powf(fmaxf(y, 0.0f), hlg_y - 1);
+            float g = csp_max * pm_powf(fmaxf(y, 0.0f), hlg_y - 1);
             for (int k = 0; k < 3; k++)
                 c[k] *= g;
             break;
         }
         case TRC_V_LOG:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.181f <= c[k] ? powf(10.0f, (c[k] - vlogD) * vlog_inv_c) - vlogB
+                c[k] = 0.181f <= c[k] ? pm_powf(10.0f, (c[k] - vlogD) * vlog_inv_c) - vlogB
                                       : (c[k] - 0.125f) * (float) (1.0 / 5.6);
             break;
         case TRC_S_LOG1:
             for (int k = 0; k < 3; k++)
-                c[k] = powf(10.0f, (c[k] - slogC) * slog_inv_a) - slogB;
+                c[k] = pm_powf(10.0f, (c[k] - slogC) * slog_inv_a) - slogB;
             break;
         case TRC_S_LOG2:
             for (int k = 0; k < 3; k++)
                 c[k] = slogQ <= c[k]
-                     ? (powf(10.0f, (c[k] - slogC) * slog_inv_a) - slogB) * slog_inv_k2
+                     ? (pm_powf(10.0f, (c[k] - slogC) * slog_inv_a) - slogB) * slog_inv_k2
                      : (c[k] - slogQ) * slog_inv_p;
             break;
         case TRC_SCRGB:
@@ -256,34 +257,34 @@ void orc_delinearize(float *rgba, size_t npix, int trc, float csp_min, float csp
         switch (trc) {
         case TRC_SRGB:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.0031308f <= c[k] ? 1.055f * powf(c[k], (float) (1.0 / 2.4)) - 0.055f
+                c[k] = 0.0031308f <= c[k] ? 1.055f * pm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
                                           : c[k] * 12.92f;
             break;
         case TRC_BT_1886:
             for (int k = 0; k < 3; k++)
-                c[k] = powf(bt_inv_a * c[k], (float) (1.0 / 2.4)) - bt_b;
+                c[k] = pm_powf(bt_inv_a * c[k], (float) (1.0 / 2.4)) - bt_b;
             break;
-        case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 1.8)); break;
-        case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.0)); break;
+        case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 1.8)); break;
+        case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.0)); break;
         case TRC_UNKNOWN:
-        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.2)); break;
-        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.4)); break;
-        case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.6)); break;
-        case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.8)); break;
+        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.2)); break;
+        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.4)); break;
+        case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.6)); break;
+        case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.8)); break;
         case TRC_ST428:
             for (int k = 0; k < 3; k++)
-                c[k] = powf(c[k] * (float) (48.0 / 52.37), (float) (1.0 / 2.6));
+                c[k] = pm_powf(c[k] * (float) (48.0 / 52.37), (float) (1.0 / 2.6));
             break;
         case TRC_PRO_PHOTO:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.001953f <= c[k] ? powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
+                c[k] = 0.001953f <= c[k] ? pm_powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
             break;
         case TRC_PQ:
             for (int k = 0; k < 3; k++) {
                 float x = c[k] * pq_pre;
-                x = powf(x, q.m1);
+                x = pm_powf(x, q.m1);
                 x = (q.c1 + q.c2 * x) / (1.0f + q.c3 * x);
-                c[k] = powf(x, q.m2);
+                c[k] = pm_powf(x, q.m2);
             }
             break;
         case TRC_HLG: {
@@ -292,26 +293,26 @@ void orc_delinearize(float *rgba, size_t npix, int trc, float csp_min, float csp
             float y = luma[0] * c[0];
             y = fmaf(luma[1], c[1], y);
             y = fmaf(luma[2], c[2], y);
-            float g = 12.0f * powf(fmaxf(1e-6f, y), (1 - hlg_y) / hlg_y);
+            float g = 12.0f * pm_powf(fmaxf(1e-6f, y), (1 - hlg_y) / hlg_y);
             for (int k = 0; k < 3; k++) {
                 float x = c[k] * g;
-                x = 1.0f < x ? hlgA * logf(x - hlgB) + hlgC : 0.5f * sqrtf(x);
+                x = 1.0f < x ? hlgA * pm_logf(x - hlgB) + hlgC : 0.5f * sqrtf(x);
                 c[k] = (1 / (1 - hlg_b)) * x + (-hlg_b / (1 - hlg_b));
             }
             break;
         }
         case TRC_V_LOG:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.01f <= c[k] ? vlog_c10 * logf(c[k] + vlogB) + vlogD
+                c[k] = 0.01f <= c[k] ? vlog_c10 * pm_logf(c[k] + vlogB) + vlogD
                                      : 5.6f * c[k] + 0.125f;
             break;
         case TRC_S_LOG1:
             for (int k = 0; k < 3; k++)
-                c[k] = slog_a10 * logf(c[k] + slogB) + slogC;
+                c[k] = slog_a10 * pm_logf(c[k] + slogB) + slogC;
             break;
         case TRC_S_LOG2:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.0f <= c[k] ? slog_a10 * logf(slogK2 * c[k] + slogB) + slogC
+                c[k] = 0.0f <= c[k] ? slog_a10 * pm_logf(slogK2 * c[k] + slogB) + slogC
                                     : slogP * c[k] + slogQ;
             break;
         case TRC_SCRGB:
@@ -342,16 +343,16 @@ static void mat3_mul(const float m[9], float v[3])
 
 static inline float pq_eotf_lit(const struct pq_lit *q, float x)
 {
-    x = powf(fmaxf(x, 0.0f), q->inv_m2);
+    x = pm_powf(fmaxf(x, 0.0f), q->inv_m2);
     x = fmaxf(x - q->c1, 0.0f) / (q->c2 - q->c3 * x);
-    return powf(x, q->inv_m1);
+    return pm_powf(x, q->inv_m1);
 }
 
 static inline float pq_oetf_lit(const struct pq_lit *q, float x, int clamp0)
 {
-    x = powf(clamp0 ? fmaxf(x, 0.0f) : x, q->m1);
+    x = pm_powf(clamp0 ? fmaxf(x, 0.0f) : x, q->m1);
     x = (q->c1 + q->c2 * x) / (1.0f + q->c3 * x);
-    return powf(x, q->m2);
+    return pm_powf(x, q->m2);
 }
 
 void orc_decode_special(float *rgba, size_t npix, int sys)
@@ -374,10 +375,10 @@ void orc_decode_special(float *rgba, size_t npix, int sys)
             float lin[3];
             for (int k = 0; k < 3; k++)
                 lin[k] = 0.08145f <= c[k]
-                       ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                       ? pm_powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
                        : c[k] * (float) (1.0 / 4.5);
             float gg = (lin[1] - 0.2627f * lin[0] - 0.0593f * lin[2]) * (float) (1.0 / 0.6780);
-            c[1] = 0.0181f <= gg ? 1.0993f * powf(gg, 0.45f) - 0.0993f : gg * 4.5f;
+            c[1] = 0.0181f <= gg ? 1.0993f * pm_powf(gg, 0.45f) - 0.0993f : gg * 4.5f;
             break;
         }
         case 6: // ICtCp PQ, :356-371
@@ -389,10 +390,10 @@ void orc_decode_special(float *rgba, size_t npix, int sys)
             break;
         case 7: // ICtCp HLG, :375-389
             for (int k = 0; k < 3; k++)
-                c[k] = 0.5f < c[k] ? expf((c[k] - hlgC) * hlg_inv_a) + hlgB : 4.0f * c[k] * c[k];
+                c[k] = 0.5f < c[k] ? pm_expf((c[k] - hlgC) * hlg_inv_a) + hlgB : 4.0f * c[k] * c[k];
             mat3_mul(lms2rgb, c);
             for (int k = 0; k < 3; k++)
-                c[k] = 1.0f < c[k] ? hlgA * logf(c[k] - hlgB) + hlgC : 0.5f * sqrtf(c[k]);
+                c[k] = 1.0f < c[k] ? hlgA * pm_logf(c[k] - hlgB) + hlgC : 0.5f * sqrtf(c[k]);
             break;
         }
         p[0] = c[0]; p[1] = c[1]; p[2] = c[2];
@@ -416,12 +417,12 @@ void orc_encode_special(float *rgba, size_t npix, int sys)
             float lin[3];
             for (int k = 0; k < 3; k++)
                 lin[k] = 0.08145f <= c[k]
-                       ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                       ? pm_powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
                        : c[k] * (float) (1.0 / 4.5);
             float g = 0.2627f * lin[0];
             g = fmaf(0.6780f, lin[1], g);
             g = fmaf(0.0593f, lin[2], g);
-            g = 0.0181f <= g ? 1.0993f * powf(g, 0.45f) - 0.0993f : g * 4.5f;
+            g = 0.0181f <= g ? 1.0993f * pm_powf(g, 0.45f) - 0.0993f : g * 4.5f;
             c[1] = g;
             c[2] = c[2] - g;
             c[0] = c[0] - g;
@@ -438,10 +439,10 @@ void orc_encode_special(float *rgba, size_t npix, int sys)
             break;
         case 7: // :512-523
             for (int k = 0; k < 3; k++)
-                c[k] = 0.5f < c[k] ? expf((c[k] - hlgC) * hlg_inv_a) + hlgB : 4.0f * c[k] * c[k];
+                c[k] = 0.5f < c[k] ? pm_expf((c[k] - hlgC) * hlg_inv_a) + hlgB : 4.0f * c[k] * c[k];
             mat3_mul(rgb2lms, c);
             for (int k = 0; k < 3; k++)
-                c[k] = 1.0f < c[k] ? hlgA * logf(c[k] - hlgB) + hlgC : 0.5f * sqrtf(c[k]);
+                c[k] = 1.0f < c[k] ? hlgA * pm_logf(c[k] - hlgB) + hlgC : 0.5f * sqrtf(c[k]);
             break;
         }
         p[0] = c[0]; p[1] = c[1]; p[2] = c[2];
@@ -461,7 +462,7 @@ void orc_sigmoidize(float *rgba, size_t npix, float center, float slope)
     for (size_t i = 0; i < npix; i++) {
         for (int k = 0; k < 3; k++) {
             float c = clampf(rgba[4*i + k], 0.0f, 1.0f);
-            rgba[4*i + k] = center - inv_slope * logf(1.0f / (c * scale + offset) - 1.0f);
+            rgba[4*i + k] = center - inv_slope * pm_logf(1.0f / (c * scale + offset) - 1.0f);
         }
     }
 }
@@ -475,7 +476,7 @@ void orc_unsigmoidize(float *rgba, size_t npix, float center, float slope)
     for (size_t i = 0; i < npix; i++) {
         for (int k = 0; k < 3; k++) {
             float c = clampf(rgba[4*i + k], 0.0f, 1.0f);
-            rgba[4*i + k] = inv_scale / (1.0f + expf(slope * (center - c))) - os;
+            rgba[4*i + k] = inv_scale / (1.0f + pm_expf(slope * (center - c))) - os;
         }
     }
 }
@@ -520,9 +521,9 @@ void orc_detect_peak(const float *rgba, int w, int h, const struct orc_peak_para
                     luma = fmaf(p->luma_coeffs[1], px[1], luma);
                     luma = fmaf(p->luma_coeffs[2], px[2], luma);
                     luma *= to_pq;
-                    luma = powf(clampf(luma, 0.0f, 1.0f), PQ_M1);
+                    luma = pm_powf(clampf(luma, 0.0f, 1.0f), PQ_M1);
                     luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
-                    luma = powf(luma, PQ_M2);
+                    luma = pm_powf(luma, PQ_M2);
                     if (cutoff)
                         luma *= smoothstepf(0.0f, cutoff, luma);
                     unsigned y_pq = (unsigned) ((float) PQ_MAXV * luma);
@@ -760,9 +761,9 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
         matv(p->rgb2lms, px, lms);
         for (int k = 0; k < 3; k++) {
             float x = q.to_pq * lms[k];
-            x = powf(fmaxf(x, 0.0f), q.m1);
+            x = pm_powf(fmaxf(x, 0.0f), q.m1);
             x = (q.c1 + q.c2 * x) / (1.0f + q.c3 * x);
-            lmspq[k] = powf(x, q.m2);
+            lmspq[k] = pm_powf(x, q.m2);
         }
         matv(LMS2IPT, lmspq, ipt);
         float i_orig = ipt[0];
@@ -791,7 +792,7 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
             float idx[3];
             idx[0] = g_a * ipt[0] + g_b;
             idx[1] = 2.0f * sqrtf(fmaf(ipt[1], ipt[1], ipt[2] * ipt[2]));
-            idx[2] = inv_2pi * atan2f(ipt[2], ipt[1]) + 0.5f;
+            idx[2] = inv_2pi * pm_atan2f(ipt[2], ipt[1]) + 0.5f;
             gamut_sample(p, idx, ipt);
             ipt[1] -= chroma_bias;
             ipt[2] -= chroma_bias;
@@ -799,9 +800,9 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
 
         matv(IPT2LMS, ipt, lmspq);
         for (int k = 0; k < 3; k++) {
-            float x = powf(fmaxf(lmspq[k], 0.0f), q.inv_m2);
+            float x = pm_powf(fmaxf(lmspq[k], 0.0f), q.inv_m2);
             x = fmaxf(x - q.c1, 0.0f) / (q.c2 - q.c3 * x);
-            x = powf(x, q.inv_m1);
+            x = pm_powf(x, q.inv_m1);
             lms[k] = x * q.from_pq;
         }
         matv(p->lms2rgb, lms, px);
@@ -887,14 +888,14 @@ void orc_dither(float *rgba, int w, int h, const struct orc_dither_params *p)
             if (p->gamma != 1.0f && p->new_depth <= 4) {
                 for (int k = 0; k < 4; k++) {
                     float col = c[k];
-                    float col_lin = powf(col, p->gamma);
+                    float col_lin = pm_powf(col, p->gamma);
                     float low, high, offset;
                     if (p->new_depth == 1) {
                         low = 0.0f; high = 1.0f; offset = col_lin;
                     } else {
                         low = floorf(col * scale) / scale;
                         high = ceilf(col * scale) / scale;
-                        float low_lin = powf(low, p->gamma), high_lin = powf(high, p->gamma);
+                        float low_lin = pm_powf(low, p->gamma), high_lin = pm_powf(high, p->gamma);
                         float range = high_lin - low_lin;
                         offset = (col_lin - low_lin) / fmaxf(range, 1e-6f);
                     }

@@ -333,3 +333,25 @@ def mat_mul(a, b):
         for c in range(3):
             o[r, c] = f32(f32(f32(a[r, 0] * b[0, c]) + f32(a[r, 1] * b[1, c])) + f32(a[r, 2] * b[2, c]))
     return o.ravel()
+
+
+SPECIAL_SYS = ("BT_2020_C", "BT_2100_PQ", "BT_2100_HLG", "XYZ")
+
+
+def decode_color(orc, t0, rgba, sys, levels, bits):
+    """pl_shader_decode_color (colorspace.c:275-470) without colour adjustment: the transform
+    of pl_color_repr_decode (scale folded in), then the system's non-linear part."""
+    dec = t0.repr_decode(sys, levels, *bits)
+    out = orc.apply_matrix(rgba, dec["m"], dec["c"])
+    if sys in [T.SYS[k] for k in SPECIAL_SYS if k in T.SYS]:
+        out = orc.decode_special(out, sys)
+    return out
+
+
+def encode_color(orc, t0, rgba, sys, levels, bits):
+    """pl_shader_encode_color (colorspace.c:472-600)."""
+    out = rgba
+    if sys in [T.SYS[k] for k in SPECIAL_SYS if k in T.SYS]:
+        out = orc.encode_special(out, sys)
+    enc = t0.repr_encode(sys, levels, *bits)
+    return orc.apply_matrix(out, enc["m"], enc["c"])

@@ -224,10 +224,20 @@ class T0:
         return bool(self.f("primaries_compatible")(fp(np.ascontiguousarray(a8, f32)),
                                                    fp(np.ascontiguousarray(b8, f32))))
 
-    def dither_matrix(self, method, size):
-        o = np.zeros(size * size, f32)
-        self.f("dither_matrix")(method, size, fp(o))
-        return o.reshape(size, size)
+    _dither_cache = {}
+
+    def dither_matrix(self, method, size, fresh=False):
+        """The reference's blue-noise generator breaks ties with libc rand() and never seeds
+        it, so only the FIRST call in a process is reproducible (fresh-process behaviour, which
+        is what the product reproduces). Cache that first result per library."""
+        key = (self.prefix, method, size)
+        if fresh or key not in T0._dither_cache:
+            o = np.zeros(size * size, f32)
+            self.f("dither_matrix")(method, size, fp(o))
+            if fresh:
+                return o.reshape(size, size)
+            T0._dither_cache[key] = o.reshape(size, size)
+        return T0._dither_cache[key].copy()
 
     def error_diffusion_kernel(self, name):
         o = np.zeros(17, np.int32)

@@ -1,0 +1,167 @@
+"""Colour shaders (decode, linearize/delinearize, sigmoid, colour map, dither, peak detection)
+through the C ABI against the CPU oracle. Input and output are rgba32f so any difference is
+arithmetic, not storage rounding. Tolerances (written per test) cover the different powf /
+expf / log implementations (CUDA libdevice vs glibc), both within 2 ULP of the true value."""
+import numpy as np
+import pytest
+
+import pipeline_oracle as P
+import plbtest as T
+
+pytestmark = pytest.mark.gpu
+
+W, H = 96, 64
+
+
+def rgb(seed, lo=0.0, hi=1.0, gray_frac=0.2):
+    r = np.random.default_rng(seed)
+    a = r.uniform(lo, hi, (H, W, 4)).astype(np.float32)
+    g = r.random((H, W)) < gray_frac
+    a[g, 1] = a[g, 0]
+    a[g, 2] = a[g, 0]
+    a[..., 3] = 1.0
+    a[0, :8, :3] = 0.0
+    a[0, 8:16, :3] = hi
+    return a
+
+
+def run_ops(gpu, src, ops, oargs, want_peak=False):
+    return gpu.simple("direct", src, "rgba32f", W, H, ops=ops, oargs=oargs, want_peak=want_peak)
+
+
+def relerr(got, want, floor=1e-4):
+    got, want = got[..., :3].astype(np.float64), want[..., :3].astype(np.float64)
+    return np.abs(got - want) / np.maximum(np.abs(want), floor)
+
+
+@pytest.mark.parametrize("trc", [k for k in T.TRC if k != "UNKNOWN"])
+def test_linearize_delinearize(gpu, oracle, trc):
+    t = T.TRC[trc]
+    csp = T.csp(T.PRIM["BT_709"], t)
+    c2 = T.t0().csp_infer(csp)
+    smin, smax, _ = T.t0().nominal_luma(c2, T.META["HDR10"], T.HDR["NORM"])
+    luma = P.luma_coeffs(T.t0(), int(c2[0]))
+    src = rgb(1)
+    got = run_ops(gpu, src, [3], [csp])
+    want = oracle.linearize(src, t, smin, smax, luma)
+    e = relerr(got, want, 1e-5)
+    assert e.max() < 2e-5, (trc, e.max())
+    lin = want.copy()
+    got2 = run_ops(gpu, lin, [4], [csp])
+    black_scaled = t not in (T.TRC["BT_1886"], T.TRC["PQ"], T.TRC["SCRGB"], T.TRC["LINEAR"])
+    want2 = oracle.delinearize(lin, t, smin, smax, luma, black_scaled=black_scaled)
+    e2 = relerr(got2, want2, 1e-4)
+    assert e2.max() < 5e-5, (trc, e2.max())
+
+
+@pytest.mark.parametrize("sys,levels,depth", [("BT_709", "LIMITED", 10), ("BT_2020_NC", "LIMITED", 10),
+                                              ("BT_601", "FULL", 8), ("YCGCO", "FULL", 8),
+                                              ("RGB", "LIMITED", 8), ("BT_2100_PQ", "LIMITED", 10),
+                                              ("BT_2100_HLG", "LIMITED", 10), ("BT_2020_C", "LIMITED", 10),
+                                              ("XYZ", "FULL", 12)])
+def test_decode_encode_color(gpu, oracle, sys, levels, depth):
+    s, l = T.SYS[sys], T.LEVELS[levels]
+    src = rgb(2, gray_frac=0.0)
+    got = run_ops(gpu, src, [1], [[s, l, 16, depth, 0]])
+    want = P.decode_color(oracle, T.t0(), src, s, l, (16, depth, 0))
+    ok = np.isfinite(want[..., :3])
+    assert np.array_equal(ok, np.isfinite(got[..., :3]))
+    assert relerr(got, want, 1.0)[ok].max() < 1e-5, sys
+    if sys == "XYZ":
+        return
+    lin = np.clip(np.nan_to_num(want), 0, 1)
+    got2 = run_ops(gpu, lin, [2], [[s, l, 16, depth, 0]])
+    want2 = P.encode_color(oracle, T.t0(), lin, s, l, (16, depth, 0))
+    assert relerr(got2, want2, 1.0).max() < 1e-5, sys
+
+
+def test_sigmoid(gpu, oracle):
+    src = rgb(3)
+    got = run_ops(gpu, src, [7], [[0.75, 6.5]])
+    want = oracle.sigmoidize(src)
+    assert relerr(got, want).max() < 1e-5
+    got = run_ops(gpu, want, [8], [[0.75, 6.5]])
+    want2 = oracle.sigmoidize(want, inverse=True)
+    assert relerr(got, want2).max() < 1e-5
+
+
+HDR10 = T.csp(T.PRIM["BT_2020"], T.TRC["PQ"], max_luma=1000)
+SDR = T.csp(T.PRIM["BT_709"], T.TRC["BT_1886"])
+P3PQ = T.csp(T.PRIM["DISPLAY_P3"], T.TRC["PQ"], max_luma=600) if "DISPLAY_P3" in T.PRIM else None
+
+
+def _cmap(gpu, oracle, src_csp, dst_csp, hq, tone, gamut, src):
+    t0 = T.t0()
+    oa = [src_csp, dst_csp, [1.0 if hq else 0.0,
+                              T.TONE_FNS.index(tone) if tone else -1,
+                              T.GAMUT_FNS.index(gamut) if gamut else -1, 0.0]]
+    got = run_ops(gpu, src, [5], oa)
+    cm = P.color_map_params(t0, src_csp.copy(), dst_csp.copy(), hq=hq, tone_fn=tone, gamut_fn=gamut)
+    want = oracle.color_map(src, cm["params"]) if cm is not None else src
+    return got, want
+
+
+@pytest.mark.parametrize("hq", [False, True])
+def test_color_map_hdr10_to_sdr_default(gpu, oracle, hq):
+    # linear light relative to SDR white; HDR10 1000 nits -> up to ~4.9
+    src = rgb(4, 0.0, 4.9)
+    got, want = _cmap(gpu, oracle, HDR10, SDR, hq, None, None, src)
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() < 2e-4, (d.max(), np.mean(d > 1e-5))
+
+
+@pytest.mark.parametrize("tone", T.TONE_FNS)
+def test_color_map_tone_functions(gpu, oracle, tone):
+    src = rgb(5, 0.0, 4.9)
+    got, want = _cmap(gpu, oracle, HDR10, SDR, False, tone, "clip", src)
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() < 2e-4, (tone, d.max())
+
+
+@pytest.mark.parametrize("gamut", T.GAMUT_FNS)
+def test_color_map_gamut_functions(gpu, oracle, gamut):
+    src = rgb(6, 0.0, 1.0)
+    s = T.csp(T.PRIM["BT_2020"], T.TRC["BT_1886"])
+    got, want = _cmap(gpu, oracle, s, SDR, False, "clip", gamut, src)
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() < 2e-4, (gamut, d.max())
+
+
+def test_color_map_inverse_and_noop(gpu, oracle):
+    src = rgb(7)
+    got, want = _cmap(gpu, oracle, SDR, SDR, False, None, None, src)
+    assert np.array_equal(got, want)
+    got, want = _cmap(gpu, oracle, SDR, HDR10, False, None, None, src)
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() < 2e-4, d.max()
+
+
+@pytest.mark.parametrize("method,depth", [(0, 8), (1, 8), (2, 8), (3, 8), (0, 10), (0, 6)])
+def test_dither(gpu, oracle, method, depth):
+    """Methods: 0 blue noise, 1 ordered LUT, 2 ordered fixed, 3 white noise."""
+    gpu.set_frame_index(0)
+    src = rgb(8)
+    got = run_ops(gpu, src, [6], [[depth, method, 6, 0, 0]])
+    lut = None
+    if method in (0, 1):
+        lut = T.t0().dither_matrix(method, 64)
+    want = oracle.dither(src, depth, method=method, lut=lut)
+    scale = float((1 << depth) - 1)
+    gq, wq = np.round(got[..., :3] * scale), np.round(want[..., :3] * scale)
+    assert np.mean(gq != wq) < 1e-4, (method, depth, np.mean(gq != wq))
+    assert np.abs(gq - wq).max() <= 1
+
+
+@pytest.mark.parametrize("hq", [False, True])
+def test_detect_peak(gpu, oracle, hq):
+    import ctypes as C
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    t0 = T.t0()
+    csp = t0.csp_infer(HDR10)
+    smin, smax, _ = t0.nominal_luma(csp, T.META["HDR10"], T.HDR["NORM"])
+    luma = P.luma_coeffs(t0, int(csp[0]))
+    src = rgb(9)  # PQ-encoded
+    _, peak = run_ops(gpu, src, [9], [HDR10, [1.0 if hq else 0.0]], want_peak=True)
+    buf = oracle.detect_peak(src, T.TRC["PQ"], smin, smax, luma, 1.0, hq, (16, 16))
+    st, used = oracle.peak_update((0.0, 0.0), buf, percentile=99.995 if hq else 100.0)
+    assert abs(peak[0] - st[0]) < 2e-5 and abs(peak[1] - st[1]) < 2e-5, (peak, st)
