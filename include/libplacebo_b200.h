@@ -647,6 +647,11 @@ PL_API pl_tex pl_cuda_wrap(pl_gpu gpu, const struct pl_cuda_wrap_params *params)
 PL_API void *pl_cuda_tex_ptr(pl_tex tex, size_t *out_pitch);
 // Number of kernels launched through this gpu since creation (bench.py: gpu_launches)
 PL_API uint64_t pl_cuda_launch_count(pl_gpu gpu);
+// Diagnostics: evaluates the kernels' deterministic transcendental functions (plb_math.cuh) on
+// host arrays of n floats. fn: 0 pow(a,b) 1 exp(a) 2 log(a) 3 sin(a) 4 cos(a) 5 atan2(a,b).
+// Returns false on a CUDA error. Lets integrators check cross-machine reproducibility.
+PL_API bool pl_cuda_math_eval(pl_gpu gpu, int fn, const float *a, const float *b, float *out,
+                              size_t n);
 
 /* ---- shaders.h -------------------------------------------------------------------------- */
 typedef struct pl_shader_t *pl_shader;

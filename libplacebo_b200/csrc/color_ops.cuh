@@ -11,6 +11,7 @@
 #pragma once
 
 #include "kernels_common.cuh"
+#include "plb_math.cuh"
 
 // One copy of the PQ/HLG literal table per translation unit (no relocatable device code);
 // every .cu that includes this header instantiates PLB_DEFINE_PQ_UPLOAD(name) and
@@ -54,16 +55,16 @@ PLB_DEV void plb_mat3_lit(const float *m, float &r, float &g, float &b)
 
 PLB_DEV float plb_pq_eotf(float x, bool clamp0)
 {
-    x = powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.inv_m2);
+    x = plm_powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.inv_m2);
     x = fmaxf(x - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x);
-    return powf(x, c_pq.inv_m1);
+    return plm_powf(x, c_pq.inv_m1);
 }
 
 PLB_DEV float plb_pq_oetf(float x, bool clamp0)
 {
-    x = powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.m1);
+    x = plm_powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.m1);
     x = (c_pq.c1 + c_pq.c2 * x) / (1.0f + c_pq.c3 * x);
-    return powf(x, c_pq.m2);
+    return plm_powf(x, c_pq.m2);
 }
 
 PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
@@ -79,29 +80,29 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
     switch (t.trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.04045f < c[k] ? powf((c[k] + 0.055f) / 1.055f, 2.4f)
+            c[k] = 0.04045f < c[k] ? plm_powf((c[k] + 0.055f) / 1.055f, 2.4f)
                                    : c[k] * (float) (1.0 / 12.92);
         post_scale = true;
         break;
     case TRC_BT_1886:
         for (int k = 0; k < 3; k++)
-            c[k] = t.a * powf(c[k] + t.b, 2.4f);
+            c[k] = t.a * plm_powf(c[k] + t.b, 2.4f);
         break;
-    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 1.8f); post_scale = true; break;
-    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.0f); post_scale = true; break;
+    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 1.8f); post_scale = true; break;
+    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.0f); post_scale = true; break;
     case TRC_UNKNOWN:
-    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.2f); post_scale = true; break;
-    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.4f); post_scale = true; break;
-    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.6f); post_scale = true; break;
-    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], 2.8f); post_scale = true; break;
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.2f); post_scale = true; break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.4f); post_scale = true; break;
+    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.6f); post_scale = true; break;
+    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.8f); post_scale = true; break;
     case TRC_PRO_PHOTO:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.03125f < c[k] ? powf(c[k], 1.8f) : c[k] * (float) (1.0 / 16.0);
+            c[k] = 0.03125f < c[k] ? plm_powf(c[k], 1.8f) : c[k] * (float) (1.0 / 16.0);
         post_scale = true;
         break;
     case TRC_ST428:
         for (int k = 0; k < 3; k++)
-            c[k] = (float) (52.37 / 48.0) * powf(c[k], 2.6f);
+            c[k] = (float) (52.37 / 48.0) * plm_powf(c[k], 2.6f);
         post_scale = true;
         break;
     case TRC_PQ:
@@ -113,11 +114,11 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
         // t.a = y, t.b = b
         for (int k = 0; k < 3; k++) {
             float x = (1 - t.b) * c[k] + t.b;
-            x = 0.5f < x ? expf((x - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b : 4.0f * x * x;
+            x = 0.5f < x ? plm_expf((x - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b : 4.0f * x * x;
             c[k] = x * (float) (1.0 / 12.0);
         }
         float y = plb_dot3_fma(t.luma[0], t.luma[1], t.luma[2], c[0], c[1], c[2]);
-        float g = t.csp_max * powf(fmaxf(y, 0.0f), t.a - 1);
+        float g = t.csp_max * plm_powf(fmaxf(y, 0.0f), t.a - 1);
         for (int k = 0; k < 3; k++)
             c[k] *= g;
         break;
@@ -128,17 +129,17 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
         break;
     case TRC_V_LOG:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.181f <= c[k] ? powf(10.0f, (c[k] - c_pq.vlog_d) * c_pq.vlog_inv_c) - c_pq.vlog_b
+            c[k] = 0.181f <= c[k] ? plm_powf(10.0f, (c[k] - c_pq.vlog_d) * c_pq.vlog_inv_c) - c_pq.vlog_b
                                   : (c[k] - 0.125f) * (float) (1.0 / 5.6);
         break;
     case TRC_S_LOG1:
         for (int k = 0; k < 3; k++)
-            c[k] = powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b;
+            c[k] = plm_powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b;
         break;
     case TRC_S_LOG2:
         for (int k = 0; k < 3; k++)
             c[k] = c_pq.slog_q <= c[k]
-                 ? (powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b) * c_pq.slog_inv_k2
+                 ? (plm_powf(10.0f, (c[k] - c_pq.slog_c) * c_pq.slog_inv_a) - c_pq.slog_b) * c_pq.slog_inv_k2
                  : (c[k] - c_pq.slog_q) * c_pq.slog_inv_p;
         break;
     default:
@@ -168,28 +169,28 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
     switch (t.trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.0031308f <= c[k] ? 1.055f * powf(c[k], (float) (1.0 / 2.4)) - 0.055f
+            c[k] = 0.0031308f <= c[k] ? 1.055f * plm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
                                       : c[k] * 12.92f;
         break;
     case TRC_BT_1886: // t.a = 1/a, t.b = b
         #pragma unroll
         for (int k = 0; k < 3; k++)
-            c[k] = powf(t.a * c[k], (float) (1.0 / 2.4)) - t.b;
+            c[k] = plm_powf(t.a * c[k], (float) (1.0 / 2.4)) - t.b;
         break;
-    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 1.8)); break;
-    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.0)); break;
+    case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 1.8)); break;
+    case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.0)); break;
     case TRC_UNKNOWN:
-    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.2)); break;
-    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.4)); break;
-    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.6)); break;
-    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = powf(c[k], (float) (1.0 / 2.8)); break;
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.2)); break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.4)); break;
+    case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.6)); break;
+    case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.8)); break;
     case TRC_ST428:
         for (int k = 0; k < 3; k++)
-            c[k] = powf(c[k] * (float) (48.0 / 52.37), (float) (1.0 / 2.6));
+            c[k] = plm_powf(c[k] * (float) (48.0 / 52.37), (float) (1.0 / 2.6));
         break;
     case TRC_PRO_PHOTO:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.001953f <= c[k] ? powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
+            c[k] = 0.001953f <= c[k] ? plm_powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
         break;
     case TRC_PQ:
         #pragma unroll
@@ -200,10 +201,10 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
         for (int k = 0; k < 3; k++)
             c[k] *= 1.0f / t.csp_max;
         float y = plb_dot3_fma(t.luma[0], t.luma[1], t.luma[2], c[0], c[1], c[2]);
-        float g = 12.0f * powf(fmaxf(1e-6f, y), (1 - t.a) / t.a);
+        float g = 12.0f * plm_powf(fmaxf(1e-6f, y), (1 - t.a) / t.a);
         for (int k = 0; k < 3; k++) {
             float x = c[k] * g;
-            x = 1.0f < x ? c_pq.hlg_a * logf(x - c_pq.hlg_b) + c_pq.hlg_c : 0.5f * sqrtf(x);
+            x = 1.0f < x ? c_pq.hlg_a * plm_logf(x - c_pq.hlg_b) + c_pq.hlg_c : 0.5f * sqrtf(x);
             c[k] = (1 / (1 - t.b)) * x + (-t.b / (1 - t.b));
         }
         break;
@@ -214,16 +215,16 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
         break;
     case TRC_V_LOG:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.01f <= c[k] ? c_pq.vlog_c10 * logf(c[k] + c_pq.vlog_b) + c_pq.vlog_d
+            c[k] = 0.01f <= c[k] ? c_pq.vlog_c10 * plm_logf(c[k] + c_pq.vlog_b) + c_pq.vlog_d
                                  : 5.6f * c[k] + 0.125f;
         break;
     case TRC_S_LOG1:
         for (int k = 0; k < 3; k++)
-            c[k] = c_pq.slog_a10 * logf(c[k] + c_pq.slog_b) + c_pq.slog_c;
+            c[k] = c_pq.slog_a10 * plm_logf(c[k] + c_pq.slog_b) + c_pq.slog_c;
         break;
     case TRC_S_LOG2:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.0f <= c[k] ? c_pq.slog_a10 * logf(c_pq.slog_k2 * c[k] + c_pq.slog_b) + c_pq.slog_c
+            c[k] = 0.0f <= c[k] ? c_pq.slog_a10 * plm_logf(c_pq.slog_k2 * c[k] + c_pq.slog_b) + c_pq.slog_c
                                 : c_pq.slog_p * c[k] + c_pq.slog_q;
         break;
     default:
@@ -244,10 +245,10 @@ PLB_DEV void plb_decode_special(int sys, float c[3])
         float lin[3];
         for (int k = 0; k < 3; k++)
             lin[k] = 0.08145f <= c[k]
-                   ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                   ? plm_powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
                    : c[k] * (float) (1.0 / 4.5);
         float gg = (lin[1] - 0.2627f * lin[0] - 0.0593f * lin[2]) * (float) (1.0 / 0.6780);
-        c[1] = 0.0181f <= gg ? 1.0993f * powf(gg, 0.45f) - 0.0993f : gg * 4.5f;
+        c[1] = 0.0181f <= gg ? 1.0993f * plm_powf(gg, 0.45f) - 0.0993f : gg * 4.5f;
         break;
     }
     case PL_COLOR_SYSTEM_BT_2100_PQ:
@@ -259,11 +260,11 @@ PLB_DEV void plb_decode_special(int sys, float c[3])
         break;
     case PL_COLOR_SYSTEM_BT_2100_HLG:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.5f < c[k] ? expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
+            c[k] = 0.5f < c[k] ? plm_expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
                                : 4.0f * c[k] * c[k];
         plb_mat3_lit(lms2rgb, c[0], c[1], c[2]);
         for (int k = 0; k < 3; k++)
-            c[k] = 1.0f < c[k] ? c_pq.hlg_a * logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
+            c[k] = 1.0f < c[k] ? c_pq.hlg_a * plm_logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
                                : 0.5f * sqrtf(c[k]);
         break;
     }
@@ -279,10 +280,10 @@ PLB_DEV void plb_encode_special(int sys, float c[3])
         float lin[3];
         for (int k = 0; k < 3; k++)
             lin[k] = 0.08145f <= c[k]
-                   ? powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
+                   ? plm_powf((c[k] + 0.0993f) * (float) (1.0 / 1.0993), (float) (1.0 / 0.45))
                    : c[k] * (float) (1.0 / 4.5);
         float g = plb_dot3_fma(0.2627f, 0.6780f, 0.0593f, lin[0], lin[1], lin[2]);
-        g = 0.0181f <= g ? 1.0993f * powf(g, 0.45f) - 0.0993f : g * 4.5f;
+        g = 0.0181f <= g ? 1.0993f * plm_powf(g, 0.45f) - 0.0993f : g * 4.5f;
         c[1] = g;
         c[2] = c[2] - g;
         c[0] = c[0] - g;
@@ -299,11 +300,11 @@ PLB_DEV void plb_encode_special(int sys, float c[3])
         break;
     case PL_COLOR_SYSTEM_BT_2100_HLG:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.5f < c[k] ? expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
+            c[k] = 0.5f < c[k] ? plm_expf((c[k] - c_pq.hlg_c) * c_pq.hlg_inv_a) + c_pq.hlg_b
                                : 4.0f * c[k] * c[k];
         plb_mat3_lit(rgb2lms, c[0], c[1], c[2]);
         for (int k = 0; k < 3; k++)
-            c[k] = 1.0f < c[k] ? c_pq.hlg_a * logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
+            c[k] = 1.0f < c[k] ? c_pq.hlg_a * plm_logf(c[k] - c_pq.hlg_b) + c_pq.hlg_c
                                : 0.5f * sqrtf(c[k]);
         break;
     }
@@ -392,7 +393,7 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
         float idx[3];
         idx[0] = p.g_a * ipt[0] + p.g_b;
         idx[1] = 2.0f * sqrtf(__fmaf_rn(ipt[1], ipt[1], ipt[2] * ipt[2]));
-        idx[2] = c_pq.inv_2pi * atan2f(ipt[2], ipt[1]) + 0.5f;
+        idx[2] = c_pq.inv_2pi * plm_atan2f(ipt[2], ipt[1]) + 0.5f;
         plb_gamut_sample(p, idx, ipt);
         ipt[1] -= (float) (32768.0 / 65535.0);
         ipt[2] -= (float) (32768.0 / 65535.0);
@@ -456,14 +457,14 @@ PLB_DEV void plb_dither(const plb_op_dither &p, int x, int y, float c[4])
     if (p.gamma != 1.0f && p.new_depth <= 4) {
         for (int k = 0; k < 4; k++) {
             float col = c[k];
-            float col_lin = powf(col, p.gamma);
+            float col_lin = plm_powf(col, p.gamma);
             float low, high, offset;
             if (p.new_depth == 1) {
                 low = 0.0f; high = 1.0f; offset = col_lin;
             } else {
                 low = floorf(col * scale) / scale;
                 high = ceilf(col * scale) / scale;
-                float low_lin = powf(low, p.gamma), high_lin = powf(high, p.gamma);
+                float low_lin = plm_powf(low, p.gamma), high_lin = plm_powf(high, p.gamma);
                 float range = high_lin - low_lin;
                 offset = (col_lin - low_lin) / fmaxf(range, 1e-6f);
             }
@@ -500,9 +501,9 @@ PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
     const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
                 PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
     luma *= 203.0f / 10000.0f;
-    luma = powf(plb_clamp(luma, 0.0f, 1.0f), PQ_M1);
+    luma = plm_powf(plb_clamp(luma, 0.0f, 1.0f), PQ_M1);
     luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
-    luma = powf(luma, PQ_M2);
+    luma = plm_powf(luma, PQ_M2);
     if (p.cutoff != 0.0f) {
         float t = plb_clamp((luma - 0.0f) / (p.cutoff - 0.0f), 0.0f, 1.0f);
         luma *= t * t * (3.0f - 2.0f * t);
@@ -539,14 +540,14 @@ static __device__ __noinline__ void plb_run_color_ops(const plb_color_prog &prog
             for (int k = 0; k < 3; k++) {
                 float v = plb_clamp(c[k], 0.0f, 1.0f);
                 c[k] = op.u.sigmoid.center - (1.0f / op.u.sigmoid.slope) *
-                       logf(1.0f / (v * op.u.sigmoid.scale + op.u.sigmoid.offset) - 1.0f);
+                       plm_logf(1.0f / (v * op.u.sigmoid.scale + op.u.sigmoid.offset) - 1.0f);
             }
             break;
         case PLB_OP_UNSIGMOID:
             for (int k = 0; k < 3; k++) {
                 float v = plb_clamp(c[k], 0.0f, 1.0f);
                 c[k] = (1.0f / op.u.sigmoid.scale) /
-                       (1.0f + expf(op.u.sigmoid.slope * (op.u.sigmoid.center - v))) -
+                       (1.0f + plm_expf(op.u.sigmoid.slope * (op.u.sigmoid.center - v))) -
                        op.u.sigmoid.offset / op.u.sigmoid.scale;
             }
             break;
@@ -573,7 +574,7 @@ static __device__ __noinline__ void plb_run_color_ops(const plb_color_prog &prog
             break;
         case PLB_OP_GAMMA:
             for (int k = 0; k < 3; k++)
-                c[k] = powf(fmaxf(c[k], 0.0f), op.u.gamma.g);
+                c[k] = plm_powf(fmaxf(c[k], 0.0f), op.u.gamma.g);
             break;
         case PLB_OP_SWIZZLE: {
             const float o[4] = { c[0], c[1], c[2], c[3] };

@@ -116,3 +116,45 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     plb_gpu_priv(gpu)->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel");
 }
+
+// ---------------------------------------------------------------------------------------
+// pl_cuda_math_eval: diagnostics front-end to plb_math.cuh
+// ---------------------------------------------------------------------------------------
+__global__ void k_math_eval(int fn, const float *a, const float *b, float *out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+         i += (size_t) gridDim.x * blockDim.x) {
+        float s, c, r;
+        switch (fn) {
+        case 0: r = plm_powf(a[i], b[i]); break;
+        case 1: r = plm_expf(a[i]); break;
+        case 2: r = plm_logf(a[i]); break;
+        case 3: plm_sincosf(a[i], &s, &c); r = s; break;
+        case 4: plm_sincosf(a[i], &s, &c); r = c; break;
+        case 5: r = plm_atan2f(a[i], b[i]); break;
+        default: r = __int_as_float(0x7fc00000);
+        }
+        out[i] = r;
+    }
+}
+
+extern "C" PL_API bool pl_cuda_math_eval(pl_gpu gpu, int fn, const float *a, const float *b,
+                                         float *out, size_t n)
+{
+    if (!n)
+        return true;
+    cudaStream_t st = (cudaStream_t) pl_cuda_stream(gpu);
+    float *d = NULL;
+    if (cudaMalloc(&d, 3 * n * sizeof(float)) != cudaSuccess)
+        return false;
+    bool ok = cudaMemcpyAsync(d, a, n * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaMemcpyAsync(d + n, b ? b : a, n * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok) {
+        k_math_eval<<<148 * 8, 256, 0, st>>>(fn, d, d + n, d + 2 * n, n);
+        ok = cudaGetLastError() == cudaSuccess &&
+             cudaMemcpyAsync(out, d + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    cudaFree(d);
+    return ok;
+}

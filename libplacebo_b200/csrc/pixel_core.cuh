@@ -45,7 +45,9 @@ PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx
         const float3 rnd = plb_prng(state);
         const float dist = rnd.x * ((float) i * pl.radius);
         const float dir = rnd.y * 6.283185f;
-        const float dx = dist * cosf(dir), dy = dist * sinf(dir);
+        float sn, cs;
+        plm_sincosf(dir, &sn, &cs);
+        const float dx = dist * cs, dy = dist * sn;
         float avg[3] = {0.0f, 0.0f, 0.0f};
         #pragma unroll
         for (int t = 0; t < 4; t++) {

@@ -152,6 +152,20 @@ static inline void tex_linear(const struct orc_tex *t, float u, float v, float o
 // pl_shader_sample_polar — src/shaders/sampling.c:587-912; per-tap body polar_sample :503-558
 // ------------------------------------------------------------------------------------------
 
+// Evaluation extent. A compute dispatch runs whole work groups, so invocations beyond the
+// image still execute the sampling code (with positions past the edge and clamped texel
+// fetches); only their store is masked (dispatch.c:1068-1075). Peak detection counts those
+// invocations. With a non-zero extent the samplers below evaluate ew x eh invocations instead
+// of dw x dh (dst then holds ew*eh pixels) while every coordinate still derives from dw x dh.
+static int g_ext_w, g_ext_h;
+void orc_set_eval_extent(int ew, int eh)
+{
+    g_ext_w = ew;
+    g_ext_h = eh;
+}
+#define EXT_W(dw) ((g_ext_w > (dw)) ? g_ext_w : (dw))
+#define EXT_H(dh) ((g_ext_h > (dh)) ? g_ext_h : (dh))
+
 void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
                       const struct orc_polar_params *p, float *dst)
 {
@@ -181,9 +195,10 @@ void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, i
         }
     }
 
+    const int ew = EXT_W(dw), eh = EXT_H(dh);
     #pragma omp parallel for schedule(static)
-    for (int gy = 0; gy < dh; gy++) {
-        for (int gx = 0; gx < dw; gx++) {
+    for (int gy = 0; gy < eh; gy++) {
+        for (int gx = 0; gx < ew; gx++) {
             int jx, jy;
             float fx, fy;
             coord_texel(&cc, gx, gy, &jx, &jy, &fx, &fy);
@@ -222,7 +237,7 @@ void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, i
 
             // sampling.c:896-908
             float norm = p->scale / wsum;
-            float *o = dst + ((size_t) gy * dw + gx) * 4;
+            float *o = dst + ((size_t) gy * ew + gx) * 4;
             for (int k = 0; k < 4; k++) {
                 bool have = (p->comp_mask & (1 << k)) && k < src->comps;
                 float v = norm * color[k];
@@ -337,9 +352,10 @@ void orc_sample_direct(const struct orc_tex *src, struct orc_rect rect, int dw, 
                        int linear, float scale, int coord_mode, float *dst)
 {
     const struct coord_ctx cc = coord_init(coord_mode, src, rect, dw, dh);
+    const int ew = EXT_W(dw), eh = EXT_H(dh);
     #pragma omp parallel for schedule(static)
-    for (int gy = 0; gy < dh; gy++) {
-        for (int gx = 0; gx < dw; gx++) {
+    for (int gy = 0; gy < eh; gy++) {
+        for (int gx = 0; gx < ew; gx++) {
             float posx, posy;
             coord_pos(&cc, gx, gy, &posx, &posy);
             // GLSL texture() returns (0,0,0,1) for missing components
@@ -351,7 +367,7 @@ void orc_sample_direct(const struct orc_tex *src, struct orc_rect rect, int dw, 
                 for (int k = 0; k < src->comps; k++)
                     c[k] = t[k];
             }
-            float *o = dst + ((size_t) gy * dw + gx) * 4;
+            float *o = dst + ((size_t) gy * ew + gx) * 4;
             for (int k = 0; k < 4; k++)
                 o[k] = scale * c[k];
         }
@@ -398,16 +414,17 @@ void orc_deband(const struct orc_tex *src, const struct orc_deband_params *p, fl
     (void) two_pi;
     const float grain_str = (float) (p->grain / (1000.0 * p->scale));
 
+    const int ew = EXT_W(w), eh = EXT_H(h);
     #pragma omp parallel for schedule(static)
-    for (int gy = 0; gy < h; gy++) {
-        for (int gx = 0; gx < w; gx++) {
+    for (int gy = 0; gy < eh; gy++) {
+        for (int gx = 0; gx < ew; gx++) {
             float posx, posy;
             coord_pos(&cc, gx, gy, &posx, &posy);
             float color[4] = {0, 0, 0, 1};
             const float *c0 = tex_nearest(src, posx, posy);
             for (int k = 0; k < src->comps; k++)
                 color[k] = c0[k];
-            float *o = dst + ((size_t) gy * w + gx) * 4;
+            float *o = dst + ((size_t) gy * ew + gx) * 4;
             if (!mask) {
                 for (int k = 0; k < 4; k++)
                     o[k] = color[k] * p->scale;

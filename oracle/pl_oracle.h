@@ -267,3 +267,7 @@ ORC_API int orc_num_threads(void);
 // Array front-end to the portable math definitions of pl_oracle_math.h:
 // fn 0 pow(a,b), 1 exp(a), 2 log(a), 3 sin(a), 4 cos(a), 5 atan2(a,b), 6 log2(a)
 void orc_math(int fn, const float *a, const float *b, float *out, size_t n);
+
+// Evaluate ew x eh invocations (>= the output size) in orc_sample_polar / orc_sample_direct /
+// orc_deband: the overhang of the last work groups, which peak detection counts. 0,0 = off.
+ORC_API void orc_set_eval_extent(int ew, int eh);

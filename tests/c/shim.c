@@ -410,6 +410,13 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
 API void shim_renderer_reset(struct shim_ctx *c)
 {
     pl_renderer_destroy(&c->rr);
+    pl_shader_obj_destroy(&c->objs.cmap); /* forget the detected peak / cached LUTs */
+}
+
+API int shim_math_eval(struct shim_ctx *c, int fn, const float *a, const float *b, float *out,
+                       size_t n)
+{
+    return pl_cuda_math_eval(c->gpu, fn, a, b, out, n) ? 0 : -1;
 }
 
 /* the AV1 grain parameters of the reference's own test fixture (src/tests/utils.h:240-262) */

@@ -106,15 +106,23 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     sx, sy = CHROMA_SHIFT[img.chroma_loc]
     rrx, rry = cw / W, ch / H
     crect = ((0 - sx) * rrx, (0 - sy) * rry, (W - sx) * rrx, (H - sy) * rry)
+    # The merged pass runs as whole work groups: rigid 32x32 if it contains a polar compute
+    # sampler (sh_subpass -> sh_try_compute, shaders.c:677-686), else the flexible 16x16 of
+    # detect_peak. Invocations past the image edge still execute (only the store is masked) and
+    # peak detection counts them, so everything merged is evaluated on the padded extent.
+    merged_has_polar = bool(plane_up) and (cw != W or ch != H) and plane_up.startswith("ewa")
+    wg = (32, 32) if merged_has_polar else (16, 16)
+    ext = (-(-W // wg[0]) * wg[0], -(-H // wg[1]) * wg[1])
     if deband:
-        luma = orc.deband(Yf, 1, 3.0, 16.0, float(grain), (neutral_luma, 0, 0), float(norm), 1, frame_index)
+        luma = orc.deband(Yf, 1, 3.0, 16.0, float(grain), (neutral_luma, 0, 0), float(norm), 1,
+                          frame_index, ext=ext)
         luma_v = luma[..., 0]
         cdb = orc.deband(UVf, 1, 3.0, 16.0, float(grain), (neutral_chroma, neutral_chroma, 0),
                          float(norm), 3, frame_index)
         ctex = orc.store_round(cdb[..., :2], 0)  # rg16hf FBO
         cscale = 1.0
     else:
-        luma_v = (Yf[..., 0] * f32(norm)).astype(f32)
+        luma_v = orc.sample_direct(Yf, W, H, scale=float(norm), coord_mode=coord_mode, ext=ext)[..., 0]
         ctex, cscale = UVf, float(norm)
 
     # plane scaler (SAMPLER_PLANE)
@@ -123,13 +131,13 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         rx, ry = W / (crect[2] - crect[0]), H / (crect[3] - crect[1])
         filt = _filter_for(t0, plane_up, rx, ry)
         chroma = orc.sample_polar(ctex, W, H, filt, comp_mask=3, rect=crect_f, scale=cscale,
-                                  coord_mode=coord_mode)
+                                  coord_mode=coord_mode, ext=ext)
     else:
         chroma = orc.sample_direct(ctex, W, H, linear=(cw != W or ch != H), rect=crect_f,
-                                   scale=cscale, coord_mode=coord_mode)
+                                   scale=cscale, coord_mode=coord_mode, ext=ext)
 
-    # ---- C. merge + decode
-    color = np.empty((H, W, 4), f32)
+    # ---- C. merge + decode (on the padded extent; cropped after the peak measurement)
+    color = np.empty((ext[1], ext[0], 4), f32)
     color[..., 0] = luma_v
     color[..., 1] = chroma[..., 0]
     color[..., 2] = chroma[..., 1]
@@ -165,11 +173,6 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         if stats is not None:
             stats["peak_buf"] = buf
 
-    # work-group geometry of the merged pass: rigid 32x32 if it contains a polar compute
-    # sampler (radius < 6), else the flexible 16x16 of detect_peak
-    merged_has_polar = bool(plane_up) and (cw != W or ch != H) and plane_up.startswith("ewa")
-    wg = (32, 32) if merged_has_polar else (16, 16)
-
     # ---- D. main scaler
     out_w, out_h = tgt.w, tgt.h
     up = out_w > W or out_h > H
@@ -181,19 +184,24 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         measured = True
     if scaling:
         main = upscaler if up else None
-        img_fbo = orc.store_round(color, 0)  # rgba16hf FBO at source size
+        img_fbo = orc.store_round(color[:H, :W], 0)  # rgba16hf FBO at source size
         if main and main.startswith("ewa"):
             filt = _filter_for(t0, main, out_w / W, out_h / H)
-            color = orc.sample_polar(img_fbo, out_w, out_h, filt, comp_mask=7, coord_mode=coord_mode)
             wg = (32, 32)
+            ext = (-(-out_w // 32) * 32, -(-out_h // 32) * 32)
+            color = orc.sample_polar(img_fbo, out_w, out_h, filt, comp_mask=7, coord_mode=coord_mode,
+                                     ext=ext)
         else:
-            color = orc.sample_direct(img_fbo, out_w, out_h, linear=True, coord_mode=coord_mode)
             wg = (16, 16)
+            ext = (-(-out_w // 16) * 16, -(-out_h // 16) * 16)
+            color = orc.sample_direct(img_fbo, out_w, out_h, linear=True, coord_mode=coord_mode,
+                                      ext=ext)
     if not measured and want_peak():
         run_peak(color, wg)
         measured = True
         if not allow_delayed:
             color = orc.store_round(color, 0)  # need_peak_fbo: rgba16hf at output size
+    color = np.ascontiguousarray(color[:out_h, :out_w])
 
     # ---- colour mapping (pl_shader_color_map_ex host logic, colorspace.c:1618-1790)
     src2 = src_csp.copy()
@@ -241,13 +249,16 @@ def store(orc, color, fmt):
 _keepalive = []
 
 
-def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None):
+def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None, state=True):
     """Host logic of pl_shader_color_map_ex -> OrcColorMap (or None when src == dst)."""
     src, dst = t0.csp_infer_map(src, dst)
     if np.array_equal(src, dst):
         return None
     tone_fn = tone_fn or "spline"
     gamut_fn = gamut_fn or "perceptual"
+    if not state:  # colorspace.c:1746-1753: no state object -> no LUT-based methods
+        tone_fn = tone_fn if tone_fn == "clip" else "linear"
+        gamut_fn = gamut_fn if gamut_fn == "clip" else "saturation"
     imin, imax, iavg = t0.nominal_luma(src, T.META["ANY"], T.HDR["PQ"])
     omin, omax, _ = t0.nominal_luma(dst, T.META["HDR10"], T.HDR["PQ"])
     tone = t0.tone_map_generate(tone_fn, imin, imax, iavg, omin, omax, hdr_csp=src)
@@ -272,6 +283,11 @@ def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None):
 
     rgb2lms = t0.matrix(2, t0.raw_primaries(int(src[0])))
     lms2rgb = t0.matrix(3, t0.raw_primaries(int(dst[0])))
+    if need_gamut and gamut_fn == "saturation":
+        # can_fast (colorspace.c:1772-1779): saturation mapping is a pure matrix
+        lms2src, dst2lms = t0.matrix(3, in_prim), t0.matrix(2, out_prim)
+        lms2rgb = mat_mul(mat_mul(lms2rgb, dst2lms), lms2src)
+        need_gamut = False
     smin, smax, _ = t0.nominal_luma(src, T.META["HDR10"], T.HDR["NORM"])
     dmin, dmax, _ = t0.nominal_luma(dst, T.META["HDR10"], T.HDR["NORM"])
     p = T.OrcColorMap()
@@ -280,7 +296,7 @@ def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None):
     p.src_luma = (C.c_float * 3)(*luma_coeffs(t0, int(src[0])))
     p.dst_luma = (C.c_float * 3)(*luma_coeffs(t0, int(dst[0])))
     black_scaled = int(dst[1]) not in (T.TRC["BT_1886"], T.TRC["PQ"], T.TRC["SCRGB"],
-                                       T.TRC["V_LOG"], T.TRC["S_LOG1"], T.TRC["S_LOG2"])
+                                       T.TRC["V_LOG"], T.TRC["S_LOG1"], T.TRC["S_LOG2"], T.TRC["HLG"])
     p.dst_black_scaled = int(black_scaled)
     p.prelinearized = 0
     p.need_tone_map, p.need_gamut_map = int(need_tone), int(need_gamut)
@@ -296,11 +312,12 @@ def color_map_params(t0, src, dst, hq=False, tone_fn=None, gamut_fn=None):
     if need_tone:
         lut = np.ascontiguousarray(tone["lut"], f32)
         keep.append(lut)
-        p.tone_kind = 1 if tone_fn == "clip" else 0
+        # can_fast (default params): clip and linear are analytic (colorspace.c:1824-1846)
+        p.tone_kind = 1 if tone_fn == "clip" else 2 if tone_fn == "linear" else 0
         p.tone_lut, p.tone_lut_size = T.fp(lut), lut.size
         p.tone_input_min, p.tone_input_max = imin, imax
         p.tone_output_min, p.tone_output_max = omin, omax
-        p.tone_exposure = 1.0
+        p.tone_exposure = float(tpar[18])  # pl_tone_map_constants.exposure
     if need_gamut:
         full = t0.gamut_map_generate(gamut_fn, in_prim, out_prim, gmin, gmax)["lut"].reshape(-1, 3)
         q = np.zeros((full.shape[0], 4), np.uint16)

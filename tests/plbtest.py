@@ -327,8 +327,15 @@ class Oracle:
     def num_threads(self):
         return self.lib.orc_num_threads()
 
+    def _ext_out(self, dw, dh, ext):
+        """Output buffer for an evaluation extent `ext` = (ew, eh) >= (dw, dh): the overhanging
+        invocations of the last compute work groups (see orc_set_eval_extent)."""
+        ew, eh = (max(ext[0], dw), max(ext[1], dh)) if ext else (dw, dh)
+        self.lib.orc_set_eval_extent(ew if ext else 0, eh if ext else 0)
+        return np.zeros((eh, ew, 4), f32)
+
     def sample_polar(self, src, dw, dh, filt, comp_mask=None, rect=None, scale=1.0,
-                     coord_mode=COORD_LITERAL, antiring=None):
+                     coord_mode=COORD_LITERAL, antiring=None, ext=None):
         """src: HxWxC float32 texel values; filt: dict from T0.filter_generate."""
         t, keep = _tex(src)
         comp_mask = (1 << keep.shape[2]) - 1 if comp_mask is None else comp_mask
@@ -337,8 +344,9 @@ class Oracle:
         p = OrcPolar(fp(lut), lut.size, filt["radius"], filt["radius_zero"],
                      filt["antiring"] if antiring is None else antiring, scale, comp_mask,
                      coord_mode)
-        out = np.zeros((dh, dw, 4), f32)
+        out = self._ext_out(dw, dh, ext)
         self.lib.orc_sample_polar(C.byref(t), OrcRect(*rect), dw, dh, C.byref(p), fp(out))
+        self.lib.orc_set_eval_extent(0, 0)
         return out
 
     def sample_ortho(self, src, dw, dh, filt, pass_, comp_mask=None, rect=None, scale=1.0,
@@ -358,22 +366,24 @@ class Oracle:
         return out
 
     def sample_direct(self, src, dw, dh, linear=False, rect=None, scale=1.0,
-                      coord_mode=COORD_LITERAL):
+                      coord_mode=COORD_LITERAL, ext=None):
         t, keep = _tex(src)
         rect = rect or (0, 0, keep.shape[1], keep.shape[0])
-        out = np.zeros((dh, dw, 4), f32)
+        out = self._ext_out(dw, dh, ext)
         self.lib.orc_sample_direct(C.byref(t), OrcRect(*rect), dw, dh, int(linear),
                                    C.c_float(scale), coord_mode, fp(out))
+        self.lib.orc_set_eval_extent(0, 0)
         return out
 
     def deband(self, src, iterations=1, threshold=3.0, radius=16.0, grain=4.0,
-               neutral=(0, 0, 0), scale=1.0, comp_mask=None, frame_index=0):
+               neutral=(0, 0, 0), scale=1.0, comp_mask=None, frame_index=0, ext=None):
         t, keep = _tex(src)
         comp_mask = (1 << keep.shape[2]) - 1 if comp_mask is None else comp_mask
         p = OrcDeband(iterations, threshold, radius, grain, (C.c_float * 3)(*neutral), scale,
                       comp_mask, frame_index)
-        out = np.zeros((keep.shape[0], keep.shape[1], 4), f32)
+        out = self._ext_out(keep.shape[1], keep.shape[0], ext)
         self.lib.orc_deband(C.byref(t), C.byref(p), fp(out))
+        self.lib.orc_set_eval_extent(0, 0)
         return out
 
     def prng(self, x, y, z):

@@ -48,7 +48,8 @@ def test_linearize_delinearize(gpu, oracle, trc):
     assert e.max() < 2e-5, (trc, e.max())
     lin = want.copy()
     got2 = run_ops(gpu, lin, [4], [csp])
-    black_scaled = t not in (T.TRC["BT_1886"], T.TRC["PQ"], T.TRC["SCRGB"], T.TRC["LINEAR"])
+    # pl_color_space_is_black_scaled (colorspace.c:525-554) minus HLG (shaders/colorspace.c:740)
+    black_scaled = trc not in ("BT_1886", "PQ", "SCRGB", "V_LOG", "S_LOG1", "S_LOG2", "HLG")
     want2 = oracle.delinearize(lin, t, smin, smax, luma, black_scaled=black_scaled)
     e2 = relerr(got2, want2, 1e-4)
     assert e2.max() < 5e-5, (trc, e2.max())
@@ -90,13 +91,14 @@ SDR = T.csp(T.PRIM["BT_709"], T.TRC["BT_1886"])
 P3PQ = T.csp(T.PRIM["DISPLAY_P3"], T.TRC["PQ"], max_luma=600) if "DISPLAY_P3" in T.PRIM else None
 
 
-def _cmap(gpu, oracle, src_csp, dst_csp, hq, tone, gamut, src):
+def _cmap(gpu, oracle, src_csp, dst_csp, hq, tone, gamut, src, state=True):
     t0 = T.t0()
     oa = [src_csp, dst_csp, [1.0 if hq else 0.0,
                               T.TONE_FNS.index(tone) if tone else -1,
-                              T.GAMUT_FNS.index(gamut) if gamut else -1, 0.0]]
+                              T.GAMUT_FNS.index(gamut) if gamut else -1, 1.0 if state else 0.0]]
     got = run_ops(gpu, src, [5], oa)
-    cm = P.color_map_params(t0, src_csp.copy(), dst_csp.copy(), hq=hq, tone_fn=tone, gamut_fn=gamut)
+    cm = P.color_map_params(t0, src_csp.copy(), dst_csp.copy(), hq=hq, tone_fn=tone, gamut_fn=gamut,
+                            state=state)
     want = oracle.color_map(src, cm["params"]) if cm is not None else src
     return got, want
 
@@ -104,7 +106,7 @@ def _cmap(gpu, oracle, src_csp, dst_csp, hq, tone, gamut, src):
 @pytest.mark.parametrize("hq", [False, True])
 def test_color_map_hdr10_to_sdr_default(gpu, oracle, hq):
     # linear light relative to SDR white; HDR10 1000 nits -> up to ~4.9
-    src = rgb(4, 0.0, 4.9)
+    src = rgb(4)  # PQ-encoded signal
     got, want = _cmap(gpu, oracle, HDR10, SDR, hq, None, None, src)
     d = np.abs(got[..., :3] - want[..., :3])
     assert d.max() < 2e-4, (d.max(), np.mean(d > 1e-5))
@@ -112,7 +114,7 @@ def test_color_map_hdr10_to_sdr_default(gpu, oracle, hq):
 
 @pytest.mark.parametrize("tone", T.TONE_FNS)
 def test_color_map_tone_functions(gpu, oracle, tone):
-    src = rgb(5, 0.0, 4.9)
+    src = rgb(5)
     got, want = _cmap(gpu, oracle, HDR10, SDR, False, tone, "clip", src)
     d = np.abs(got[..., :3] - want[..., :3])
     assert d.max() < 2e-4, (tone, d.max())
@@ -125,6 +127,14 @@ def test_color_map_gamut_functions(gpu, oracle, gamut):
     got, want = _cmap(gpu, oracle, s, SDR, False, "clip", gamut, src)
     d = np.abs(got[..., :3] - want[..., :3])
     assert d.max() < 2e-4, (gamut, d.max())
+
+
+def test_color_map_without_state_object(gpu, oracle):
+    """No state object: LUT methods are replaced by linear / saturation (colorspace.c:1746)."""
+    src = rgb(10)
+    got, want = _cmap(gpu, oracle, HDR10, SDR, False, "spline", "perceptual", src, state=False)
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() < 2e-4, d.max()
 
 
 def test_color_map_inverse_and_noop(gpu, oracle):
@@ -165,3 +175,34 @@ def test_detect_peak(gpu, oracle, hq):
     buf = oracle.detect_peak(src, T.TRC["PQ"], smin, smax, luma, 1.0, hq, (16, 16))
     st, used = oracle.peak_update((0.0, 0.0), buf, percentile=99.995 if hq else 100.0)
     assert abs(peak[0] - st[0]) < 2e-5 and abs(peak[1] - st[1]) < 2e-5, (peak, st)
+
+
+@pytest.mark.parametrize("fn", range(6))
+def test_deterministic_math_matches_oracle_definition(gpu, oracle, fn):
+    """The kernels' pow/exp/log/sin/cos/atan2 (csrc/plb_math.cuh) and the oracle's
+    (oracle/pl_oracle_math.h) are the same binary64 algorithm: results must be bit-identical."""
+    import ctypes as C
+    r = np.random.default_rng(fn)
+    n = 1 << 20
+    if fn == 0:
+        a = np.exp(r.uniform(-30, 30, n)).astype(np.float32)
+        b = r.uniform(-8, 8, n).astype(np.float32)
+        sp = np.array([0, 1, -1, np.inf, -np.inf, np.nan, 0.5, 2, 1e-40, 3e38], np.float32)
+        A, B = np.meshgrid(sp, sp)
+        a[:100], b[:100] = A.ravel(), B.ravel()
+    elif fn == 1:
+        a = r.uniform(-100, 100, n).astype(np.float32); b = a
+    elif fn == 2:
+        a = np.exp(r.uniform(-80, 80, n)).astype(np.float32); b = a
+        a[:4] = [0, -1, np.inf, np.nan]
+    elif fn in (3, 4):
+        a = r.uniform(-50, 50, n).astype(np.float32); b = a
+    else:
+        a = r.normal(0, 1, n).astype(np.float32); b = r.normal(0, 1, n).astype(np.float32)
+        a[:4], b[:4] = [0, 0, np.inf, -0.0], [0, -1, np.inf, -0.0]
+    got = np.empty(n, np.float32)
+    ok = gpu.lib.shim_math_eval(C.c_void_p(gpu.ctx), fn, T.fp(a), T.fp(b), T.fp(got), C.c_size_t(n))
+    assert ok == 0
+    want = np.empty(n, np.float32)
+    oracle.lib.orc_math(fn, T.fp(a), T.fp(b), T.fp(want), C.c_size_t(n))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -53,8 +53,9 @@ def test_c2_sdr_upscale_2x_ewa_lanczos(gpu, kind, loc):
     got, _ = gpu_render(gpu, img, tgt, upscaler="ewa_lanczos")
     want, _ = P.render(img, tgt, upscaler="ewa_lanczos")
     ulp = T.ulp_diff_half(got, want)
-    assert ulp.max() <= 1, (ulp.max(), np.mean(ulp > 0))
-    assert np.mean(ulp > 0) < 1e-3
+    # stated tolerance: +-1 ULP of the 16-bit output; achieved: bit-exact (same fp32 operation
+    # order, same deterministic coordinates)
+    assert ulp.max() == 0, (ulp.max(), np.mean(ulp > 0))
 
 
 def test_c2_with_deband(gpu):
@@ -65,9 +66,7 @@ def test_c2_with_deband(gpu):
     got, _ = gpu_render(gpu, img, tgt, upscaler="ewa_lanczos", deband=True, frame_index=5)
     want, _ = P.render(img, tgt, upscaler="ewa_lanczos", deband=True, frame_index=5)
     ulp = T.ulp_diff_half(got, want)
-    # deband decisions can flip for isolated pixels (sin/cos from different libms)
-    assert np.mean(ulp > 1) < 2e-3
-    assert np.median(ulp) == 0
+    assert ulp.max() == 0, (ulp.max(), np.mean(ulp > 0))
 
 
 @pytest.mark.parametrize("fmt,depth", [("rgba16", 16), ("rgba8", 8)])
@@ -82,20 +81,15 @@ def test_c3_hdr10_to_sdr(gpu, fmt, depth):
     got, peak = gpu_render(gpu, img, tgt, **kw)
     st = {}
     want, pstate = P.render(img, tgt, stats=st, **kw)
-    # peak statistics are integers: the smoothed state must agree to float rounding
-    assert abs(peak[0] - pstate[0]) < 1e-4 and abs(peak[1] - pstate[1]) < 1e-4, (peak, pstate)
+    # peak statistics are integer sums over work groups: the smoothed state must be identical
+    assert np.float32(peak[0]) == np.float32(pstate[0]) and np.float32(peak[1]) == np.float32(pstate[1]), (peak, pstate)
     d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
-    if depth == 16:
-        assert np.mean(d > 1) < 5e-3, (d.max(), np.mean(d > 1))
-    else:
-        # dithered 8-bit: a value within float rounding of a floor() boundary may land on
-        # either side
-        assert np.mean(d > 0) < 5e-3 and d.max() <= 2, (d.max(), np.mean(d > 0))
+    # stated tolerance +-1 LSB of the 16-bit output; achieved: identical integers
+    assert d.max() == 0, (d.max(), np.mean(d > 0))
 
 
-def test_c3_no_deband_is_tight(gpu):
-    """Without the (discontinuous) deband stage the whole chain must stay within 1 LSB of the
-    16-bit output everywhere."""
+def test_c3_no_deband_noise_content(gpu):
+    """Saturated random content (worst case for the PQ / gamut-mapping arithmetic)."""
     gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
     planes = T.yuv420p10(256, 144, seed=8, kind="noise")
     img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
@@ -104,14 +98,54 @@ def test_c3_no_deband_is_tight(gpu):
     got, peak = gpu_render(gpu, img, tgt, **kw)
     want, pstate = P.render(img, tgt, **kw)
     d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
-    assert d.max() <= 1, (d.max(), np.mean(d > 0))
+    assert d.max() == 0, (d.max(), np.mean(d > 0))
 
 
-def test_unsupported_features_fail_loudly(gpu):
-    """pl_render_params members outside the hot path are rejected, not silently ignored."""
-    import gpu_helpers
+def test_plain_render_matches(gpu):
     planes = T.yuv420p10(64, 36, seed=1)
     img = P.Frame(planes, T.SYS["BT_709"], csp=SDR)
     tgt = P.Target(64, 36, "rgba16hf", csp=SDR)
-    got, _ = gpu_render(gpu, img, tgt)  # baseline works
-    assert np.isfinite(got.astype(np.float32)).all()
+    got, _ = gpu_render(gpu, img, tgt)
+    want, _ = P.render(img, tgt)
+    assert T.ulp_diff_half(got, want).max() == 0
+
+
+@pytest.mark.parametrize("size", [(192, 108, 384, 216), (200, 120, 400, 240), (160, 90, 250, 141)])
+def test_hdr_upscale_with_peak(gpu, size):
+    """HDR10 source that is also upscaled: the peak is measured on the source-resolution merged
+    pass (renderer.c:1460-1470), the FBO round trip feeds the main EWA scaler, then the colour
+    mapping runs with the same-frame peak. Odd sizes exercise the generic polar kernel and
+    partially filled work groups."""
+    w, h, ow, oh = size
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(w, h, seed=11)
+    img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(ow, oh, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", peak=2, cmap_hq=True)
+    got, peak = gpu_render(gpu, img, tgt, **kw)
+    want, pstate = P.render(img, tgt, **kw)
+    assert np.float32(peak[0]) == np.float32(pstate[0]) and np.float32(peak[1]) == np.float32(pstate[1])
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    exact_coords = (ow, oh) == (2 * w, 2 * h)
+    if exact_coords:
+        assert d.max() == 0, (d.max(), np.mean(d > 0))
+    else:
+        # generic ratios: sample positions are fp32 expressions evaluated in a different (but
+        # equally valid) order than the oracle's exact evaluation -> 1 LSB flips are possible
+        assert d.max() <= 1 and np.mean(d > 0) < 1e-2, (d.max(), np.mean(d > 0))
+
+
+def test_peak_smoothing_over_frames(gpu):
+    """Three consecutive frames: the IIR-smoothed peak state (colorspace.c:1071-1180) carried by
+    the renderer must track the oracle's state machine exactly, and so must every frame."""
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    tgt = P.Target(128, 72, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    state = None
+    for i, (seed, kind) in enumerate([(20, "rings"), (21, "noise"), (22, "rings")]):
+        planes = T.yuv420p10(128, 72, seed=seed, kind=kind)
+        img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+        kw = dict(peak=2, cmap_hq=True, frame_index=i)
+        got, peak = gpu_render(gpu, img, tgt, **kw)
+        want, state = P.render(img, tgt, peak_state=state, **kw)
+        assert np.float32(peak[0]) == np.float32(state[0]) and np.float32(peak[1]) == np.float32(state[1]), (i, peak, state)
+        assert np.array_equal(got[..., :3], want[..., :3]), i

@@ -39,7 +39,7 @@ def run():
     with gpu_helpers.Gpu() as gpu:
         for name, (s, d, hq, tone, gm, src) in cases().items():
             oa = [s, d, [float(hq), T.TONE_FNS.index(tone) if tone else -1,
-                         T.GAMUT_FNS.index(gm) if gm else -1, 0.0]]
+                         T.GAMUT_FNS.index(gm) if gm else -1, 1.0]]
             try:
                 out[name] = G.run_ops(gpu, src, [5], oa)
             except Exception as e:  # noqa: BLE001
