@@ -875,6 +875,31 @@ PL_API pl_dispatch pl_dispatch_create(pl_log log, pl_gpu gpu);
 PL_API void pl_dispatch_destroy(pl_dispatch *dp);
 PL_API void pl_dispatch_reset_frame(pl_dispatch dp);
 PL_API pl_shader pl_dispatch_begin(pl_dispatch dp);
+/* shaders.h:121-138; refcounting is a no-op here: the info lives as long as the pl_dispatch */
+typedef const struct pl_shader_info_t {
+    struct pl_shader_params params;
+    const char **steps;
+    int num_steps;
+    const char *description;
+} *pl_shader_info;
+PL_API pl_shader_info pl_shader_info_ref(pl_shader_info info);
+PL_API void pl_shader_info_deref(pl_shader_info *info);
+
+struct pl_dispatch_info { /* dispatch.h:50-65 */
+    pl_shader_info shader;
+    uint64_t signature;
+    uint64_t samples[256];
+    int num_samples;
+    uint64_t last;
+    uint64_t peak;
+    uint64_t average;
+};
+/* dispatch.h:77-82: `cb` runs for every successfully dispatched shader; the execution times it
+ * reports are cudaEvent intervals on the gpu's stream and arrive a few dispatches late (when
+ * the events have completed), never by blocking the stream. */
+PL_API void pl_dispatch_callback(pl_dispatch dp, void *priv,
+                                 void (*cb)(void *priv, const struct pl_dispatch_info *));
+
 struct pl_dispatch_params { /* dispatch.h:84-115 */
     pl_shader *shader;
     pl_tex target;
@@ -919,6 +944,17 @@ PL_API struct pl_render_errors pl_renderer_get_errors(pl_renderer rr);
 PL_API void pl_renderer_reset_errors(pl_renderer rr, const struct pl_render_errors *errors);
 enum pl_lut_type { PL_LUT_UNKNOWN = 0, PL_LUT_NATIVE, PL_LUT_NORMALIZED, PL_LUT_CONVERSION };
 enum pl_clear_mode { PL_CLEAR_COLOR = 0, PL_CLEAR_TILES, PL_CLEAR_SKIP, PL_CLEAR_BLUR, PL_CLEAR_MODE_COUNT };
+enum pl_render_stage { /* renderer.h:106-113 */
+    PL_RENDER_STAGE_FRAME,
+    PL_RENDER_STAGE_BLEND,
+    PL_RENDER_STAGE_COUNT,
+};
+struct pl_render_info { /* renderer.h:115-126 */
+    const struct pl_dispatch_info *pass;
+    enum pl_render_stage stage;
+    int index;
+    int count;
+};
 struct pl_render_params { /* renderer.h:130-368; members outside the hot path are accepted
                              but must be NULL/0, otherwise pl_render_image fails loudly */
     const struct pl_filter_config *upscaler;
@@ -961,7 +997,7 @@ struct pl_render_params { /* renderer.h:130-368; members outside the hot path ar
     bool disable_fbos;
     bool force_low_bit_depth_fbos;
     bool dynamic_constants;
-    void (*info_callback)(void *priv, const void *info);
+    void (*info_callback)(void *priv, const struct pl_render_info *info);
     void *info_priv;
 };
 #define PL_RENDER_DEFAULTS \

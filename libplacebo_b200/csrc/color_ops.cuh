@@ -310,7 +310,7 @@ PLB_DEV void plb_encode_special(int sys, float c[3])
     }
 }
 
-// trilinear fetch from the rgba16 gamut 3DLUT; addressing = lut.c:285-295 per axis
+// trilinear fetch from the gamut 3DLUT (rgba16 values pre-converted to float); addressing = lut.c:285-295 per axis
 PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], float out[3])
 {
     const int n[3] = { p.lut_I, p.lut_C, p.lut_h };
@@ -337,10 +337,10 @@ PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], flo
                 int i = plb_clampi(b[0] + dx, 0, n[0] - 1);
                 int cc = plb_clampi(b[1] + dy, 0, n[1] - 1);
                 int h = plb_clampi(b[2] + dz, 0, n[2] - 1);
-                const ushort4 t = __ldg((const ushort4 *) p.gamut_lut + ((size_t) h * n[1] + cc) * n[0] + i);
-                c[dz][dy][dx][0] = t.x / 65535.0f;
-                c[dz][dy][dx][1] = t.y / 65535.0f;
-                c[dz][dy][dx][2] = t.z / 65535.0f;
+                const float4 t = __ldg((const float4 *) p.gamut_lut + ((size_t) h * n[1] + cc) * n[0] + i);
+                c[dz][dy][dx][0] = t.x;
+                c[dz][dy][dx][1] = t.y;
+                c[dz][dy][dx][2] = t.z;
             }
         }
     }
@@ -514,9 +514,16 @@ PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
 // Runs all ops except PEAK (returned through peak_op for the caller to reduce).
 // Deliberately NOT inlined: one copy per translation unit keeps every sampling kernel small
 // (the call costs nothing next to the transcendental chains inside).
-static __device__ __noinline__ void plb_run_color_ops(const plb_color_prog &prog, int x, int y, float c[4],
+//
+// The program is read from a per-CTA shared-memory copy (plb_s_prog, staged by
+// plb_tail_stage): operands then come from LDS with link-time addresses instead of generic
+// loads through a pointer to the kernel parameters.
+static __shared__ plb_color_prog plb_s_prog;
+
+static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                                const plb_op_peak **peak_op, uint32_t *y_pq)
 {
+    const plb_color_prog &prog = plb_s_prog;
     for (int i = 0; i < prog.n; i++) {
         const plb_color_op &op = prog.ops[i];
         switch (op.kind) {

@@ -466,23 +466,29 @@ void pl_shader_color_map_ex(pl_shader sh, const struct pl_color_map_params *para
         const size_t texels = (size_t) gamut.lut_size_I * gamut.lut_size_C * gamut.lut_size_h;
         const uint64_t sig = gamut_signature(&gamut);
         if (!obj->have_gamut || obj->gamut_sig != sig || obj->gamut_texels != texels) {
-            // fill_gamut_lut, colorspace.c:1589-1610: rgba16 with chroma biased by 32767
+            // fill_gamut_lut, colorspace.c:1589-1610: quantised to rgba16 with the chroma biased
+            // by 32767. The reference's texture unit converts each fetched texel with n/65535;
+            // here that (exact IEEE) conversion happens once at upload, so the kernel fetches
+            // the very same float values as float4 and spares 24 divisions per pixel.
             float *tmp = malloc(texels * 3 * sizeof(float));
-            uint16_t *q = malloc(texels * 4 * sizeof(uint16_t));
+            float *q = malloc(texels * 4 * sizeof(float));
             pl_gamut_map_generate(tmp, &gamut);
             for (size_t i = 0; i < texels; i++) {
-                q[4*i + 0] = roundf(tmp[3*i + 0] * UINT16_MAX);
-                q[4*i + 1] = roundf(tmp[3*i + 1] * UINT16_MAX + (UINT16_MAX >> 1));
-                q[4*i + 2] = roundf(tmp[3*i + 2] * UINT16_MAX + (UINT16_MAX >> 1));
-                q[4*i + 3] = 0;
+                const uint16_t q0 = roundf(tmp[3*i + 0] * UINT16_MAX);
+                const uint16_t q1 = roundf(tmp[3*i + 1] * UINT16_MAX + (UINT16_MAX >> 1));
+                const uint16_t q2 = roundf(tmp[3*i + 2] * UINT16_MAX + (UINT16_MAX >> 1));
+                q[4*i + 0] = (float) q0 / 65535.0f;
+                q[4*i + 1] = (float) q1 / 65535.0f;
+                q[4*i + 2] = (float) q2 / 65535.0f;
+                q[4*i + 3] = 0.0f;
             }
             if (obj->gamut_texels != texels) {
                 plb_dev_free(gpu, obj->dev_gamut_lut);
-                obj->dev_gamut_lut = plb_dev_alloc(gpu, texels * 4 * sizeof(uint16_t));
+                obj->dev_gamut_lut = plb_dev_alloc(gpu, texels * 4 * sizeof(float));
                 obj->gamut_texels = texels;
             }
             bool ok = obj->dev_gamut_lut &&
-                      plb_dev_upload(gpu, obj->dev_gamut_lut, q, texels * 4 * sizeof(uint16_t));
+                      plb_dev_upload(gpu, obj->dev_gamut_lut, q, texels * 4 * sizeof(float));
             free(tmp);
             free(q);
             if (!ok) {

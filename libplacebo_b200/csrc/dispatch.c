@@ -20,8 +20,116 @@ void pl_dispatch_destroy(pl_dispatch *pdp)
 {
     if (!pdp || !*pdp)
         return;
-    free(*pdp);
+    struct pl_dispatch_t *dp = *pdp;
+    for (int i = 0; i < dp->num_passes; i++) {
+        for (int t = 0; t < PLB_PASS_TIMERS; t++)
+            pl_timer_destroy(dp->gpu, &dp->passes[i]->timers[t]);
+        free(dp->passes[i]);
+    }
+    free(dp);
     *pdp = NULL;
+}
+
+pl_shader_info pl_shader_info_ref(pl_shader_info info) { return info; }
+void pl_shader_info_deref(pl_shader_info *info) { if (info) *info = NULL; }
+
+void pl_dispatch_callback(pl_dispatch dp, void *priv,
+                          void (*cb)(void *priv, const struct pl_dispatch_info *))
+{
+    dp->info_callback = cb;
+    dp->info_priv = priv;
+}
+
+// ---- pass statistics (dispatch.c:1085-1197 `pass_info` / timer handling) ------------------
+static uint64_t fnv1a(uint64_t h, const void *data, size_t n)
+{
+    const unsigned char *p = data;
+    for (size_t i = 0; i < n; i++)
+        h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+
+static struct plb_pass *find_pass(pl_dispatch dp, pl_shader sh, int w, int h)
+{
+    uint64_t sig = 0xcbf29ce484222325ull;
+    const int key[6] = { (int) sh->src, w, h, sh->px.prog.n, sh->px.nplanes, sh->is_compute };
+    sig = fnv1a(sig, key, sizeof(key));
+    for (int i = 0; i < sh->num_steps; i++)
+        sig = fnv1a(sig, sh->steps[i], strlen(sh->steps[i]));
+    for (int i = 0; i < dp->num_passes; i++) {
+        if (dp->passes[i]->signature == sig)
+            return dp->passes[i];
+    }
+    if (dp->num_passes == (int) (sizeof(dp->passes) / sizeof(dp->passes[0])))
+        return NULL;
+    struct plb_pass *p = calloc(1, sizeof(*p));
+    if (!p)
+        return NULL;
+    p->signature = sig;
+    // pretty description with tallies, like sh_describe's "a, b x2" (shaders.c:185-215)
+    size_t len = 0;
+    for (int i = 0; i < sh->num_steps; i++) {
+        bool seen = false;
+        for (int j = 0; j < i; j++)
+            seen |= !strcmp(sh->steps[i], sh->steps[j]);
+        if (seen)
+            continue;
+        int count = 0;
+        for (int j = i; j < sh->num_steps; j++)
+            count += !strcmp(sh->steps[i], sh->steps[j]);
+        int n = count > 1
+            ? snprintf(p->description + len, sizeof(p->description) - len, "%s%s x%d",
+                       len ? ", " : "", sh->steps[i], count)
+            : snprintf(p->description + len, sizeof(p->description) - len, "%s%s",
+                       len ? ", " : "", sh->steps[i]);
+        if (n < 0 || (size_t) n >= sizeof(p->description) - len)
+            break;
+        len += n;
+        p->steps[p->info.num_steps++] = sh->steps[i];
+    }
+    p->info.params = sh->params;
+    p->info.steps = p->steps;
+    p->info.description = p->description;
+    p->stats.shader = &p->info;
+    p->stats.signature = sig;
+    dp->passes[dp->num_passes++] = p;
+    return p;
+}
+
+static void pass_collect(pl_dispatch dp, struct plb_pass *p)
+{
+    while (p->timer_tail != p->timer_head) {
+        pl_timer t = p->timers[p->timer_tail % PLB_PASS_TIMERS];
+        uint64_t ns = pl_timer_query(dp->gpu, t);
+        if (!ns)
+            break; // not finished yet (or sub-nanosecond, which cannot happen)
+        p->timer_tail++;
+        struct pl_dispatch_info *st = &p->stats;
+        st->samples[p->sample_idx++ % 256] = ns;
+        if (st->num_samples < 256)
+            st->num_samples++;
+        st->last = ns;
+        uint64_t sum = 0, peak = 0;
+        for (int i = 0; i < st->num_samples; i++) {
+            sum += st->samples[i];
+            peak = st->samples[i] > peak ? st->samples[i] : peak;
+        }
+        st->peak = peak;
+        st->average = sum / st->num_samples;
+    }
+}
+
+static pl_timer pass_timer(pl_dispatch dp, struct plb_pass *p)
+{
+    pass_collect(dp, p);
+    if (p->timer_head - p->timer_tail >= PLB_PASS_TIMERS)
+        return NULL; // all timers in flight: skip this sample rather than block
+    pl_timer *slot = &p->timers[p->timer_head % PLB_PASS_TIMERS];
+    if (!*slot)
+        *slot = pl_timer_create(dp->gpu);
+    if (*slot)
+        p->timer_head++;
+    return *slot;
 }
 
 void pl_dispatch_reset_frame(pl_dispatch dp) { dp->current_index++; }
@@ -109,6 +217,16 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         px->wg_w = px->wg_h = 16;
     }
 
+    // internal timing only when the caller did not claim the interval (dispatch.h:111-117)
+    struct plb_pass *pass = NULL;
+    if (!timer && dp->info_callback && !plb_gpu_no_timers(gpu)) {
+        pass = find_pass(dp, sh, w, h);
+        if (pass)
+            timer = pass_timer(dp, pass);
+    } else if (dp->info_callback) {
+        pass = find_pass(dp, sh, w, h);
+    }
+
     plb_timer_begin(gpu, timer);
     bool ok = false;
     switch (sh->src) {
@@ -130,6 +248,10 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         break;
     }
     plb_timer_end(gpu, timer);
+    if (ok && pass && dp->info_callback) {
+        pass_collect(dp, pass);
+        dp->info_callback(dp->info_priv, &pass->stats);
+    }
     return ok;
 }
 

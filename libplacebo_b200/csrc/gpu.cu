@@ -330,6 +330,7 @@ void pl_cuda_destroy(pl_gpu *pgpu)
 
 void *pl_cuda_stream(pl_gpu gpu) { return plb_gpu_priv(gpu)->stream; }
 int plb_gpu_coord_mode(pl_gpu gpu) { return plb_gpu_priv(gpu)->coord_mode; }
+bool plb_gpu_no_timers(pl_gpu gpu) { return plb_gpu_priv(gpu)->no_timers; }
 
 bool plb_pq_upload_polar(const plb_pq_consts *q);
 bool plb_pq_upload_pixel(const plb_pq_consts *q);

@@ -137,7 +137,7 @@ struct plb_op_color_map {
     float tone_a, tone_b;              // 1/range, -min/range
     float in_min, in_max, out_min, out_max;
     float lin_a, lin_b;                // linear fast path
-    const uint16_t *gamut_lut;         // rgba16 texels, I fastest
+    const float *gamut_lut;            // rgba32f texels (quantised to n/65535), I fastest
     int lut_I, lut_C, lut_h;
     float g_a, g_b;
 };
@@ -287,6 +287,7 @@ bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p);
 
 void plb_pq_literal(struct plb_pq_consts *q);
 bool plb_upload_pq_consts(pl_gpu gpu);
+bool plb_gpu_no_timers(pl_gpu gpu);
 
 #ifdef __cplusplus
 }

@@ -14,16 +14,20 @@ PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_pixel)
 #define PIX_TILE 32
 
 __global__ void __launch_bounds__(256)
-k_pixel(const __grid_constant__ plb_tail_args a)
+k_pixel(const __grid_constant__ plb_tail_args ap)
 {
     __shared__ plb_peak_smem ps;
+    plm_tables_init();
+    plb_tail_stage(ap);
+    __syncthreads();
+    const plb_tail_args &a = plb_s_tail;
     const int X0 = blockIdx.x * PIX_TILE, Y0 = blockIdx.y * PIX_TILE;
     const int gx = X0 + threadIdx.x;
 
     // Does the program contain a peak tap? (uniform)
     bool has_peak = false;
-    for (int i = 0; i < a.prog.n; i++)
-        has_peak |= a.prog.ops[i].kind == PLB_OP_PEAK;
+    for (int i = 0; i < plb_s_prog.n; i++)
+        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
     const int wgs_x = has_peak ? PIX_TILE / a.wg_w : 1, wgs_y = has_peak ? PIX_TILE / a.wg_h : 1;
     const int nwgx = has_peak ? (a.out_w + a.wg_w - 1) / a.wg_w : 1;
     const int nwgy = has_peak ? (a.out_h + a.wg_h - 1) / a.wg_h : 1;
@@ -40,7 +44,7 @@ k_pixel(const __grid_constant__ plb_tail_args a)
         float color[4];
         uint32_t ypq = 0;
         const plb_op_peak *pk = nullptr;
-        plb_tail_color(a, gx, gy, nullptr, color, &ypq, &pk);
+        plb_tail_color(gx, gy, nullptr, color, &ypq, &pk);
         if (has_peak) {
             const int lx = (gx - X0) / a.wg_w, ly = (gy - Y0) / a.wg_h;
             const int wg_local = ly * wgs_x + lx;
@@ -122,6 +126,8 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
 // ---------------------------------------------------------------------------------------
 __global__ void k_math_eval(int fn, const float *a, const float *b, float *out, size_t n)
 {
+    plm_tables_init();
+    __syncthreads();
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
          i += (size_t) gridDim.x * blockDim.x) {
         float s, c, r;

@@ -111,12 +111,15 @@ __global__ void __launch_bounds__(256)
 k_polar_generic(const __grid_constant__ polar_generic_args a)
 {
     __shared__ plb_peak_smem ps;
-    const plb_tail_args &t = a.tail;
+    plm_tables_init();
+    plb_tail_stage(a.tail);
+    __syncthreads();
+    const plb_tail_args &t = plb_s_tail;
     const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
     const int gx = X0 + threadIdx.x;
     bool has_peak = false;
-    for (int i = 0; i < t.prog.n; i++)
-        has_peak |= t.prog.ops[i].kind == PLB_OP_PEAK;
+    for (int i = 0; i < plb_s_prog.n; i++)
+        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
     const int wgs_x = has_peak ? 32 / t.wg_w : 1, wgs_y = has_peak ? 32 / t.wg_h : 1;
     const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
     const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
@@ -133,7 +136,7 @@ k_polar_generic(const __grid_constant__ polar_generic_args a)
         polar_pixel(a, gx, gy, prim);
         uint32_t ypq = 0;
         const plb_op_peak *pk = nullptr;
-        plb_tail_color(t, gx, gy, prim, color, &ypq, &pk);
+        plb_tail_color(gx, gy, prim, color, &ypq, &pk);
         if (has_peak) {
             const int lx = (gx - X0) / t.wg_w, ly = (gy - Y0) / t.wg_h;
             const bool valid = (X0 / t.wg_w + lx) < nwgx && (Y0 / t.wg_h + ly) < nwgy;
@@ -200,6 +203,8 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     const int X0 = blockIdx.x * (UP2_TX * UP2_OX), Y0 = blockIdx.y * (UP2_TY * UP2_OY);
     const int col0 = X0 / 2 - 4, row0 = Y0 / 2 - 4;
 
+    plm_tables_init(); // published by the barrier after the tile staging
+    plb_tail_stage(a.tail);
     // Stage the source tile (clamp-to-edge) as planar fp32
     for (int i = ty * UP2_TX + tx; i < UP2_TILE_H * UP2_TILE_WP; i += UP2_TX * UP2_TY) {
         const int r = i / UP2_TILE_WP, c = i - r * UP2_TILE_WP;
@@ -257,10 +262,10 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
         }
     }
 
-    const plb_tail_args &t = a.tail;
+    const plb_tail_args &t = plb_s_tail;
     bool has_peak = false;
-    for (int i = 0; i < t.prog.n; i++)
-        has_peak |= t.prog.ops[i].kind == PLB_OP_PEAK;
+    for (int i = 0; i < plb_s_prog.n; i++)
+        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
     const int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
     const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
     const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
@@ -287,7 +292,7 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
             float color[4];
             uint32_t ypq = 0;
             const plb_op_peak *pk = nullptr;
-            plb_tail_color(t, gx, gy, prim, color, &ypq, &pk);
+            plb_tail_color(gx, gy, prim, color, &ypq, &pk);
             if (has_peak) {
                 const int lx = (gx - X0) / t.wg_w, ly = (gy - Y0) / t.wg_h;
                 const bool valid = (X0 / t.wg_w + lx) < nwgx && (Y0 / t.wg_h + ly) < nwgy;

@@ -7,6 +7,8 @@
 //   4. convert and store to the target texture
 #pragma once
 
+#include <cstddef>
+
 #include "color_ops.cuh"
 
 struct plb_tail_args {
@@ -22,6 +24,29 @@ struct plb_tail_args {
     int wg_w, wg_h;        // work-group geometry for PLB_OP_PEAK
     plb_color_prog prog;
 };
+
+// Per-CTA shared-memory copy of the launch description (everything but .prog, which lives in
+// plb_s_prog). Every kernel calls plb_tail_stage() with its parameter first, then a barrier.
+static __shared__ plb_tail_args plb_s_tail;
+
+PLB_DEV void plb_tail_stage(const plb_tail_args &a)
+{
+    const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+    const int nt = blockDim.x * blockDim.y * blockDim.z;
+    const uint32_t *src = (const uint32_t *) &a;
+    uint32_t *dst = (uint32_t *) &plb_s_tail;
+    constexpr int head = (int) (offsetof(plb_tail_args, prog) / 4);
+    for (int i = tid; i < head; i += nt)
+        dst[i] = src[i];
+    // only the used part of the program
+    const uint32_t *psrc = (const uint32_t *) &a.prog;
+    uint32_t *pdst = (uint32_t *) &plb_s_prog;
+    const int pwords = (int) ((offsetof(plb_color_prog, ops) + (size_t) a.prog.n * sizeof(plb_color_op)) / 4);
+    for (int i = tid; i < pwords; i += nt)
+        pdst[i] = psrc[i];
+    if (tid == 0)
+        plb_s_tail.prog.n = a.prog.n;
+}
 
 #define PLB_MAX_WG_PER_CTA 16
 #define PLB_HIST_BINS 64
@@ -118,13 +143,14 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
 
 // Steps 1-2 + the pixel's PQ luma for step 3. `prim` = output of the primary sampler (or NULL)
 // Not inlined on purpose (one copy per translation unit; see plb_run_color_ops).
-static __device__ __noinline__ bool plb_tail_color_slow(const plb_tail_args &a, int gx, int gy,
+static __device__ __noinline__ bool plb_tail_color_slow(int gx, int gy,
                                                  const float *prim, float color[4],
                                                  uint32_t *ypq, const plb_op_peak **pk);
 
-PLB_DEV bool plb_tail_color(const plb_tail_args &a, int gx, int gy, const float *prim,
+PLB_DEV bool plb_tail_color(int gx, int gy, const float *prim,
                             float color[4], uint32_t *ypq, const plb_op_peak **pk)
 {
+    const plb_tail_args &a = plb_s_tail;
     if (a.nplanes == 0 && a.prog.n == 0 && prim) {
         // pure resampling pass: nothing to merge, nothing to run
         #pragma unroll
@@ -138,12 +164,13 @@ PLB_DEV bool plb_tail_color(const plb_tail_args &a, int gx, int gy, const float 
         *pk = nullptr;
         return false;
     }
-    return plb_tail_color_slow(a, gx, gy, prim, color, ypq, pk);
+    return plb_tail_color_slow(gx, gy, prim, color, ypq, pk);
 }
 
-static __device__ __noinline__ bool plb_tail_color_slow(const plb_tail_args &a, int gx, int gy, const float *prim,
+static __device__ __noinline__ bool plb_tail_color_slow(int gx, int gy, const float *prim,
                             float color[4], uint32_t *ypq, const plb_op_peak **pk)
 {
+    const plb_tail_args &a = plb_s_tail;
     #pragma unroll
     for (int k = 0; k < 4; k++)
         color[k] = a.init[k];
@@ -165,7 +192,7 @@ static __device__ __noinline__ bool plb_tail_color_slow(const plb_tail_args &a, 
     }
     *pk = nullptr;
     if (a.prog.n)
-        plb_run_color_ops(a.prog, gx, gy, color, pk, ypq);
+        plb_run_color_ops(gx, gy, color, pk, ypq);
     return *pk != nullptr;
 }
 

@@ -44,7 +44,22 @@ struct pl_renderer_t {
     uint8_t frame_index;
     bool have_peak_override;
     struct pl_peak_state peak_override;
+    // info_callback plumbing (renderer.c:3320-3345 `info_callback`)
+    const struct pl_render_params *info_params;
+    int info_index;
 };
+
+static void renderer_info_cb(void *priv, const struct pl_dispatch_info *dinfo)
+{
+    pl_renderer rr = priv;
+    if (!rr->info_params || !rr->info_params->info_callback)
+        return;
+    rr->info_params->info_callback(rr->info_params->info_priv, &(struct pl_render_info) {
+        .pass = dinfo,
+        .stage = PL_RENDER_STAGE_FRAME,
+        .index = rr->info_index++,
+    });
+}
 
 const struct pl_render_params pl_render_fast_params = { PL_RENDER_DEFAULTS };
 const struct pl_render_params pl_render_default_params = {
@@ -590,6 +605,8 @@ static bool merge_plane_shader(pl_shader sh, pl_shader sub, const int map[4], in
         sub->objs[i]->refcount++;
         sh->objs[sh->num_objs++] = sub->objs[i];
     }
+    for (int i = 0; i < sub->num_steps; i++)
+        plb_shader_describe(sh, sub->steps[i]);
     return true;
 }
 
@@ -1286,8 +1303,12 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
         return false;
     if (!pl_rect_w(pass.dst_rect) || !pl_rect_h(pass.dst_rect))
         return true; // empty crop
+    rr->info_params = params;
+    rr->info_index = 0;
+    pl_dispatch_callback(rr->dp, rr, params->info_callback ? renderer_info_cb : NULL);
     bool ok = pass_read_image(&pass) && pass_scale_main(&pass) && pass_convert_colors(&pass) &&
               pass_output_target(&pass);
+    rr->info_params = NULL;
     if (!ok) {
         PLB_ERR(rr->log, "Failed rendering image!");
         pl_dispatch_abort(rr->dp, &pass.sh);

@@ -45,7 +45,7 @@ struct plb_color_map_obj {
     size_t tone_lut_size;
     uint64_t gamut_sig;
     bool have_gamut;
-    uint16_t *dev_gamut_lut;
+    float *dev_gamut_lut;      // rgba32f texels = unorm16 values / 65535
     size_t gamut_texels;
     struct plb_peak_state peak;
 };
@@ -97,17 +97,42 @@ struct pl_shader_t {
     pl_shader_obj objs[16];
     int num_objs;
     pl_dispatch dp;            // owner, if created through pl_dispatch_begin
+    // friendly names of the recorded operations (sh_describe, src/shaders.h:155-165)
+    const char *steps[24];
+    int num_steps;
 };
+
+// `desc` must have static storage duration
+void plb_shader_describe(pl_shader sh, const char *desc);
 
 void plb_shader_fail(pl_shader sh, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind);
 bool plb_shader_require_color(pl_shader sh, const char *who);
 bool plb_shader_try_compute(pl_shader sh, int bw, int bh, bool flexible);
 
+// Per-pass bookkeeping behind pl_dispatch_callback (dispatch.c:65-100 `struct pass`): passes
+// are identified by a signature of their kernel kind, steps and geometry; each keeps a ring of
+// in-flight cudaEvent timers and the last execution times.
+#define PLB_PASS_TIMERS 64
+struct plb_pass {
+    uint64_t signature;
+    struct pl_shader_info_t info;
+    const char *steps[24];
+    char description[256];
+    pl_timer timers[PLB_PASS_TIMERS];
+    int timer_head, timer_tail;      // ring of pending timers
+    struct pl_dispatch_info stats;
+    int sample_idx;
+};
+
 struct pl_dispatch_t {
     pl_log log;
     pl_gpu gpu;
     uint8_t current_index;     // frame counter (dispatch.c:1613-1622)
+    struct plb_pass *passes[64];
+    int num_passes;
+    void *info_priv;
+    void (*info_callback)(void *priv, const struct pl_dispatch_info *info);
 };
 
 // renderer-internal: merge a sub-shader's planes into `sh` (sh_subpass + "color[i] = tmp[j]")

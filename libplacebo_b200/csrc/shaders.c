@@ -165,7 +165,29 @@ struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind)
     struct plb_color_op *op = &sh->px.prog.ops[sh->px.prog.n++];
     memset(op, 0, sizeof(*op));
     op->kind = kind;
+    // friendly step names, worded like the reference's sh_describe() calls
+    static const char *const names[] = {
+        [PLB_OP_MATRIX] = "color matrix",
+        [PLB_OP_LINEARIZE] = "linearization",
+        [PLB_OP_DELINEARIZE] = "delinearization",
+        [PLB_OP_DECODE_SPECIAL] = "color decoding",
+        [PLB_OP_ENCODE_SPECIAL] = "color encoding",
+        [PLB_OP_SIGMOID] = "sigmoidization",
+        [PLB_OP_UNSIGMOID] = "unsigmoidization",
+        [PLB_OP_COLOR_MAP] = "tone / gamut mapping",
+        [PLB_OP_DITHER] = "dithering",
+        [PLB_OP_DOVI_RESHAPE] = "reshaping",
+        [PLB_OP_PEAK] = "peak detection",
+    };
+    if (kind >= 0 && kind < (int) PLB_ARRAY_SIZE(names) && names[kind])
+        plb_shader_describe(sh, names[kind]);
     return op;
+}
+
+void plb_shader_describe(pl_shader sh, const char *desc)
+{
+    if (sh->num_steps < (int) PLB_ARRAY_SIZE(sh->steps))
+        sh->steps[sh->num_steps++] = desc;
 }
 
 // sh_require(sh, PL_SHADER_SIG_COLOR, 0, 0)
@@ -351,6 +373,7 @@ void pl_shader_deband(pl_shader sh, const struct pl_sample_src *src,
         return;
     params = params ? params : &pl_deband_default_params;
     sh->src = PLB_SRC_PLANES;
+    plb_shader_describe(sh, "debanding");
     struct plb_plane_src *pl = &sh->px.planes[0];
     memset(pl, 0, sizeof(*pl));
     pl->kind = PLB_PLANE_DEBAND;
@@ -457,6 +480,7 @@ bool pl_shader_sample_polar(pl_shader sh, const struct pl_sample_src *src,
         return false;
 
     sh->src = PLB_SRC_POLAR;
+    plb_shader_describe(sh, "polar scaling");
     struct plb_polar_launch *p = &sh->polar;
     p->src = si.tex;
     p->rect = si.rect;
@@ -519,6 +543,7 @@ bool pl_shader_sample_ortho2(pl_shader sh, const struct pl_sample_src *src,
         return false;
 
     sh->src = PLB_SRC_ORTHO;
+    plb_shader_describe(sh, "separable scaling");
     struct plb_ortho_launch *p = &sh->ortho;
     p->src = si.tex;
     p->rect = si.rect;

@@ -1,0 +1,60 @@
+"""Frame-parallel rendering of ONE stream across GPUs (one process per GPU, torch.distributed).
+
+The path's only cross-frame state is the peak-detection IIR (shaders/colorspace.c:1071-1180 in
+the reference): frame f's tone curve depends on the smoothed peak after frames 0..f. Frames are
+dealt round-robin (frame f = step * world + rank). Per step every rank
+
+  1. measures its frame: the pass graph up to the peak-detection tap, statistics only
+     (`pl_renderer_measure_peak`, raw `peak_buf_data`, 3264 bytes);
+  2. all-gathers the statistics (NCCL over NVLink: 3264 B per rank — the one collective of the
+     path; there is no pixel exchange);
+  3. replays the recurrence over the gathered buffers in frame order
+     (`pl_peak_state_update`, host arithmetic, identical on every rank), stopping at its own
+     frame to obtain the state the sequential reference would have had;
+  4. renders its frame with that state (`pl_renderer_set_peak_state` + `pl_render_image`).
+
+The output is bit-identical to rendering the stream on one GPU (tests/test_parallel.py checks
+the replay logic with the gloo backend on CPU, tests/test_gpu_parallel.py on GPUs).
+"""
+import numpy as np
+
+from .stream import PEAK_BUF_SIZE
+
+
+def replay(states_fn, state, bufs, upto):
+    """Apply the recurrence to bufs[0..upto] starting from `state`; returns the state after
+    bufs[upto] and the state after all of them. `states_fn(state, buf)` -> (new_state, used)."""
+    mine = None
+    for i, b in enumerate(bufs):
+        state, _ = states_fn(state, b)
+        if i == upto:
+            mine = state
+    return mine, state
+
+
+class PeakExchange:
+    def __init__(self, stream, dist, rank, world, device=None):
+        import torch
+        self.st, self.dist, self.rank, self.world = stream, dist, rank, world
+        self.torch = torch
+        self.state = (0.0, 0.0)  # smoothed (avg_pq, max_pq) after the last completed step
+        backend = dist.get_backend()
+        self.dev = device if device is not None else ("cuda" if backend == "nccl" else "cpu")
+        self.send = torch.zeros(PEAK_BUF_SIZE // 4, dtype=torch.int32, device=self.dev)
+        self.recv = torch.zeros(world * PEAK_BUF_SIZE // 4, dtype=torch.int32, device=self.dev)
+
+    def exchange(self, buf):
+        """buf: uint32[816] statistics of this rank's frame -> list of all ranks' buffers."""
+        t = self.torch
+        self.send.copy_(t.from_numpy(buf.view(np.int32)))
+        self.dist.all_gather_into_tensor(self.recv, self.send)
+        allb = self.recv.cpu().numpy().view(np.uint32).reshape(self.world, -1)
+        return [allb[r] for r in range(self.world)]
+
+    def render(self, slot, out_slot, step):
+        buf = self.st.measure_peak(slot)
+        bufs = self.exchange(buf)
+        mine, last = replay(self.st.peak_update, self.state, bufs, self.rank)
+        self.state = last
+        self.st.set_peak(mine)
+        self.st.render(slot, out_slot, frame_index=(step * self.world + self.rank) % 256)

@@ -15,10 +15,13 @@
 // dense sweeps.
 //
 // Definitions (x, y float; all intermediate arithmetic binary64, Horner steps are fma):
-//   log2(x):  x = m * 2^e with m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);
-//             log2(x) = e + s * P9(s^2),   P9 = sum_{k<9} 2/((2k+1) ln 2) * s^(2k)
-//   exp2(t):  t clamped to [-1100, 1100];  n = nearest integer;  r = t - n in [-1/2, 1/2];
-//             exp2(t) = 2^n * Q12(r),      Q12 = sum_{k<=12} (ln 2)^k / k! * r^k
+//   log2(x):  x = m * 2^e with m in [1, 2);  i = top 7 mantissa bits;  c_i = RCP[i] ~ 1/m with
+//             9 fractional bits (so r = m c_i - 1 is exact, |r| < 2^-7.7);
+//             log2(x) = e + LOGC[i] + r * A6(r),   A6 = sum_{k<=6} (-1)^(k+1) / (k ln 2) r^(k-1)
+//   exp2(t):  |t| >= 160 saturates to +-160;  k = nearest integer to 64 t;  r = t - k/64;
+//             exp2(t) = 2^(k >> 6) * EXP2[k & 63] * B5(r),   B5 = sum_{j<=5} (ln 2)^j / j! r^j
+//             (tables RCP, LOGC = -log2(c_i), EXP2 = 2^(j/64): pl_oracle_math_tables.h, generated
+//             by tools/gen_math_tables.py as exact binary64 literals)
 //   pow(x,y) = float(exp2(y * log2(x)))    for finite x > 0
 //   exp(x)   = float(exp2(x * log2(e))),   log(x) = float(log2(x) * ln 2)
 //   sin/cos:  k = nearest integer to x * 2/pi;  r = (x - k*pio2_hi) - k*pio2_lo;
@@ -33,64 +36,58 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "pl_oracle_math_tables.h"
+
 static inline double pm_from_bits(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
 static inline uint64_t pm_bits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+static inline uint32_t pm_fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float pm_ffrom_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-// log2 of a finite, strictly positive double that came from a float (so never subnormal as a
-// double)
-static inline double pm_log2_core(double x)
+// log2 of a finite, strictly positive float
+static inline double pm_log2_core(float x)
 {
-    uint64_t u = pm_bits(x);
-    int e = (int) (u >> 52) - 1023;
-    uint64_t mant = u & 0x000FFFFFFFFFFFFFull;
-    // m in [1,2); move to [sqrt(1/2), sqrt(2)) — compare on the mantissa bits of sqrt(2)
-    if (mant > 0x6A09E667F3BCCull) {
-        e += 1;
-        u = mant | 0x3FE0000000000000ull; // m/2 in [sqrt(1/2), 1)
-    } else {
-        u = mant | 0x3FF0000000000000ull;
+    uint32_t ix = pm_fbits(x);
+    int e = -127;
+    if (ix < 0x00800000u) {          // subnormal: scale by 2^24 (exact)
+        ix = pm_fbits(x * 16777216.0f);
+        e -= 24;
     }
-    const double m = pm_from_bits(u);
-    const double s = (m - 1.0) / (m + 1.0);
-    const double z = s * s;
-    double p = 0.16972882833987804;
-    p = fma(p, z, 0.19235933878519512);
-    p = fma(p, z, 0.22195308321368667);
-    p = fma(p, z, 0.2623081892525388);
-    p = fma(p, z, 0.3205988979753252);
-    p = fma(p, z, 0.4121985831111324);
-    p = fma(p, z, 0.5770780163555853);
-    p = fma(p, z, 0.9617966939259756);
-    p = fma(p, z, 2.8853900817779268);
-    return fma(s, p, (double) e);
+    e += (int) (ix >> 23);
+    const int i = (ix >> 16) & 127;  // top 7 mantissa bits
+    const double m = (double) pm_ffrom_bits((ix & 0x007FFFFFu) | 0x3F800000u); // [1, 2)
+    const double r = fma(m, PM_RCP[i], -1.0);                                  // exact, |r| < 2^-7.7
+    // log2(1 + r) = r * (a1 + r (a2 + ... r a6)),  a_k = (-1)^(k+1) / (k ln 2)
+    double p = -0x1.ec709dc3a03fdp-3;   // -1/(6 ln 2)
+    p = fma(p, r, 0x1.2776c50ef9bfep-2);  //  1/(5 ln 2)
+    p = fma(p, r, -0x1.71547652b82fep-2); // -1/(4 ln 2)
+    p = fma(p, r, 0x1.ec709dc3a03fdp-2);  //  1/(3 ln 2)
+    p = fma(p, r, -0x1.71547652b82fep-1); // -1/(2 ln 2)
+    p = fma(p, r, 0x1.71547652b82fep+0);  //  1/ln 2
+    return fma(r, p, PM_LOGC[i] + (double) e);
 }
 
-// 2^t as a double (t finite)
+// 2^t as a double whose conversion to float is the wanted result. |t| >= 160 saturates to
+// +-160 (2^160 converts to inf, 2^-160 to 0, like every larger magnitude), decided on the high
+// word so that the test is a single integer comparison.
 static inline double pm_exp2_core(double t)
 {
-    t = t < -1100.0 ? -1100.0 : t > 1100.0 ? 1100.0 : t;
+    const uint64_t ut = pm_bits(t);
+    if (((ut >> 32) & 0x7fffffffu) >= 0x40640000u)
+        t = (ut >> 63) ? -160.0 : 160.0;
     const double shift = 6755399441055744.0; // 1.5 * 2^52: adding it rounds to nearest integer
-    const double n = (t + shift) - shift;
-    const double r = t - n;
-    double q = 2.5678435993488206e-11;
-    q = fma(q, r, 4.4455382718708116e-10);
-    q = fma(q, r, 7.054911620801123e-09);
-    q = fma(q, r, 1.01780860092397e-07);
-    q = fma(q, r, 1.321548679014431e-06);
-    q = fma(q, r, 1.5252733804059841e-05);
-    q = fma(q, r, 0.0001540353039338161);
-    q = fma(q, r, 0.0013333558146428443);
-    q = fma(q, r, 0.009618129107628477);
-    q = fma(q, r, 0.05550410866482158);
-    q = fma(q, r, 0.24022650695910072);
-    q = fma(q, r, 0.6931471805599453);
+    const double kd = (t * 64.0 + shift) - shift; // k = nearest integer to 64 t
+    const double r = fma(kd, -0.015625, t);       // t - k/64, exact; |r| <= 1/128
+    const int k = (int) kd;
+    // 2^r = 1 + r (b1 + r (b2 + ... r b5)),  b_j = (ln 2)^j / j!
+    double q = 0x1.5d87fe78a6731p-10;   // b5
+    q = fma(q, r, 0x1.3b2ab6fba4e77p-7);  // b4
+    q = fma(q, r, 0x1.c6b08d704a0cp-5);   // b3
+    q = fma(q, r, 0x1.ebfbdff82c58fp-3);  // b2
+    q = fma(q, r, 0x1.62e42fefa39efp-1);  // b1
     q = fma(q, r, 1.0);
-    // scale by 2^n in two exact steps so that |n| up to 1100 cannot overflow the exponent field
-    const int ni = (int) n;
-    const int n1 = ni / 2, n2 = ni - n1;
-    const double s1 = pm_from_bits((uint64_t) (1023 + n1) << 52);
-    const double s2 = pm_from_bits((uint64_t) (1023 + n2) << 52);
-    return (q * s1) * s2;
+    // 2^(k >> 6) * EXP2[k & 63]: add k >> 6 (floor division) to the table entry's exponent field
+    const uint64_t tb = pm_bits(PM_EXP2[k & 63]) + ((uint64_t) (int64_t) (k >> 6) << 52);
+    return q * pm_from_bits(tb);
 }
 
 static inline float pm_powf(float x, float y)
@@ -109,7 +106,7 @@ static inline float pm_powf(float x, float y)
         return y > 0.0f ? INFINITY : 0.0f;
     if (isinf(y))
         return ((x > 1.0f) == (y > 0.0f)) ? INFINITY : 0.0f;
-    return (float) pm_exp2_core((double) y * pm_log2_core((double) x));
+    return (float) pm_exp2_core((double) y * pm_log2_core(x));
 }
 
 static inline float pm_expf(float x)
@@ -127,7 +124,7 @@ static inline float pm_logf(float x)
         return -INFINITY;
     if (isinf(x))
         return INFINITY;
-    return (float) (pm_log2_core((double) x) * 0.6931471805599453);
+    return (float) (pm_log2_core(x) * 0.6931471805599453);
 }
 
 static inline float pm_log2f(float x)
@@ -138,7 +135,7 @@ static inline float pm_log2f(float x)
         return -INFINITY;
     if (isinf(x))
         return INFINITY;
-    return (float) pm_log2_core((double) x);
+    return (float) pm_log2_core(x);
 }
 
 // sine and cosine of a float of magnitude < 2^20
