@@ -443,3 +443,15 @@ static struct pl_av1_grain_data shim_av1_fixture(void)
         .uv_offset = {0, 0},
     };
 }
+
+/* host-only: the peak recurrence of the frame-parallel scheme (no GPU needed) */
+API int shim_peak_update(float state[2], const void *buf, int hq)
+{
+    struct pl_peak_state st = { .avg_pq = state[0], .max_pq = state[1] };
+    const struct pl_peak_detect_params *par = hq ? &pl_peak_detect_high_quality_params
+                                                 : &pl_peak_detect_default_params;
+    bool used = pl_peak_state_update(&st, buf, par);
+    state[0] = st.avg_pq;
+    state[1] = st.max_pq;
+    return used;
+}
