@@ -519,6 +519,60 @@ PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
 // plb_tail_stage): operands then come from LDS with link-time addresses instead of generic
 // loads through a pointer to the kernel parameters.
 static __shared__ plb_color_prog plb_s_prog;
+static __shared__ plb_dovi_tab plb_s_dovi; // staged only when the program reshapes
+
+// pl_shader_dovi_reshape, colorspace.c:106-273 (reshape_mmr :52-92, reshape_poly :94-97)
+PLB_DEV float plb_dot4_fma(const float a[4], float x, float y, float z, float w)
+{
+    return __fmaf_rn(a[3], w, __fmaf_rn(a[2], z, __fmaf_rn(a[1], y, a[0] * x)));
+}
+
+PLB_DEV void plb_dovi_reshape(float c[4])
+{
+    const plb_dovi_tab &d = plb_s_dovi;
+    const float sig[3] = { plb_clamp(c[0], 0.0f, 1.0f), plb_clamp(c[1], 0.0f, 1.0f),
+                           plb_clamp(c[2], 0.0f, 1.0f) };
+    #pragma unroll 1
+    for (int ch = 0; ch < 3; ch++) {
+        const int np = d.num_pivots[ch];
+        if (!np)
+            continue;
+        float s = sig[ch];
+        int k = 0;
+        if (np > 2) {
+            const float *pv = d.pivots[ch];
+            // the mix tree of :206-216 (mix(a, b, bvec) takes b where true)
+            if (s >= pv[3])
+                k = s >= pv[5] ? (s >= pv[6] ? 7 : 6) : (s >= pv[4] ? 5 : 4);
+            else
+                k = s >= pv[1] ? (s >= pv[2] ? 3 : 2) : (s >= pv[0] ? 1 : 0);
+        }
+        const float *co = d.coeffs[ch][k];
+        if (co[3] == 0.0f) {
+            s = (co[2] * s + co[1]) * s + co[0];
+        } else {
+            const int idx = (int) co[1];
+            const unsigned order = (unsigned) co[3];
+            const float (*m)[4] = &d.mmr[ch][idx];
+            const float x0 = sig[0] * sig[1], x1 = sig[0] * sig[2], x2 = sig[1] * sig[2];
+            const float x3 = x0 * sig[2];
+            s = co[0];
+            s += plb_dot3_fma(m[0][0], m[0][1], m[0][2], sig[0], sig[1], sig[2]);
+            s += plb_dot4_fma(m[1], x0, x1, x2, x3);
+            if (order >= 2) {
+                const float q0 = sig[0] * sig[0], q1 = sig[1] * sig[1], q2 = sig[2] * sig[2];
+                const float y0 = x0 * x0, y1 = x1 * x1, y2 = x2 * x2, y3 = x3 * x3;
+                s += plb_dot3_fma(m[2][0], m[2][1], m[2][2], q0, q1, q2);
+                s += plb_dot4_fma(m[3], y0, y1, y2, y3);
+                if (order >= 3) {
+                    s += plb_dot3_fma(m[4][0], m[4][1], m[4][2], q0 * sig[0], q1 * sig[1], q2 * sig[2]);
+                    s += plb_dot4_fma(m[5], y0 * x0, y1 * x1, y2 * x2, y3 * x3);
+                }
+            }
+        }
+        c[ch] = plb_clamp(s, d.lo[ch], d.hi[ch]);
+    }
+}
 
 static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                                const plb_op_peak **peak_op, uint32_t *y_pq)
@@ -560,6 +614,16 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
             break;
         case PLB_OP_COLOR_MAP: plb_color_map(op.u.cmap, c); break;
         case PLB_OP_DITHER:    plb_dither(op.u.dither, x, y, c); break;
+        case PLB_OP_DOVI_RESHAPE: plb_dovi_reshape(c); break;
+        case PLB_OP_DOVI_LMS:
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                c[k] = plb_pq_eotf(c[k], true);
+            plb_matv(op.u.matrix.m, c[0], c[1], c[2]);
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                c[k] = plb_pq_oetf(c[k], true);
+            break;
         case PLB_OP_ROUND_FBO:
             #pragma unroll
             for (int k = 0; k < 4; k++)

@@ -334,12 +334,13 @@ bool plb_gpu_no_timers(pl_gpu gpu) { return plb_gpu_priv(gpu)->no_timers; }
 
 bool plb_pq_upload_polar(const plb_pq_consts *q);
 bool plb_pq_upload_pixel(const plb_pq_consts *q);
+bool plb_pq_upload_ortho(const plb_pq_consts *q);
 
 bool plb_upload_pq_consts(pl_gpu gpu)
 {
     struct plb_pq_consts q;
     plb_pq_literal(&q);
-    bool ok = plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q);
+    bool ok = plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
     if (!ok)
         PLB_ERR(gpu->log, "failed uploading constant tables");
     return ok;

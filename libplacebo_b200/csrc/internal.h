@@ -116,6 +116,7 @@ enum plb_op_kind {
     PLB_OP_ROUND_FBO,      // emulate a store+load through an intermediate FBO format
     PLB_OP_ALPHA,          // pl_shader_set_alpha conversions
     PLB_OP_DOVI_RESHAPE,   // pl_shader_dovi_reshape
+    PLB_OP_DOVI_LMS,       // Dolby Vision tail of decode_color: PQ EOTF, LMS->RGB, PQ OETF
     PLB_OP_GAMMA,          // color adjustment gamma
     PLB_OP_PEAK,           // pl_shader_detect_peak tap (needs block-wide reduction)
     PLB_OP_SWIZZLE,        // swizzle_color (src/renderer.c:791-808)
@@ -173,7 +174,7 @@ struct plb_color_op {
         struct plb_op_dither dither;
         struct { int kind; int bits; } round_fbo;
         struct { int from, to; } alpha;
-        struct { const struct plb_dovi_dev *tab; } dovi;
+        struct { int unused; } dovi;      // tables: plb_pixel_launch.dovi
         struct { float g; } gamma;
         struct plb_op_peak peak;
         struct { int8_t map[4]; int comps; int force_alpha; } swizzle;
@@ -234,6 +235,17 @@ struct plb_plane_src {
     struct plb_tex_desc luma;  // AV1 chroma needs the luma plane
 };
 
+// Dolby Vision reshaping tables as the reference packs them for the GPU
+// (shaders/colorspace.c:128-169): per component up to 8 pieces with (c0, c1, c2, order) or
+// (constant, mmr_idx, -, order), the internal pivots padded with 1e9, packed MMR weights.
+struct plb_dovi_tab {
+    int num_pivots[3];
+    float lo[3], hi[3];
+    float pivots[3][7];
+    float coeffs[3][8][4];
+    float mmr[3][48][4];
+};
+
 struct plb_pixel_launch {
     int nplanes;
     struct plb_plane_src planes[4];
@@ -244,6 +256,8 @@ struct plb_pixel_launch {
     int coord_mode;
     uint32_t frame_index;
     int wg_w, wg_h;        // work-group geometry (matters to PLB_OP_PEAK only)
+    int has_dovi;
+    struct plb_dovi_tab dovi;  // operand of PLB_OP_DOVI_RESHAPE (at most one per pass)
     struct plb_color_prog prog;
 };
 bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p);

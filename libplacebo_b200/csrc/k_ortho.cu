@@ -1,0 +1,184 @@
+// pl_shader_sample_ortho2 (src/shaders/sampling.c:950-1104): one 1-D pass of a separable
+// scaler. Weights come from the 256-row LUT (row = phase, bilinear in phase — the reference
+// samples an rgba32f texture LINEARly, sh_lut lut.c:285-295), taps from the source texture
+// through linear fetches; radius == radius_zero filters use the linear-sampling trick
+// (sampling.c:919-936, 1062-1088: two taps per fetch). Same per-pixel tail as every sampler.
+//
+// CTA = 32x8 threads over a 32x32 output tile (4 rows per thread); the N <= 2*ceil(R) taps of a
+// warp walk one row segment (horizontal pass) or N rows (vertical pass), so every fetch of a
+// warp is a contiguous, L1-resident segment. Bound: HBM for small N (lanczos N = 6: 6 fetches
+// + ~20 FMA per output), i.e. the source is read once from DRAM and N times from L1.
+#include "pixel_core.cuh"
+
+struct ortho_args {
+    plb_tex_desc src;
+    plb_coord cc;
+    const float *lut;
+    int lut_entries, row_size, row_stride;
+    int use_linear;
+    float antiring, ratio, scale;
+    uint8_t comp_mask;
+    int pass;
+    plb_tail_args tail;
+};
+
+PLB_DEV float plb_fractf(float x) { return x - floorf(x); }
+
+PLB_DEV void ortho_weights(const ortho_args &a, int quad, float fcoord, float ws[4])
+{
+    const float fpos = plb_clamp(fcoord, 0.0f, 1.0f) * (float) (a.lut_entries - 1);
+    const float fbase = floorf(fpos), fceil = ceilf(fpos);
+    const float fc = fpos - fbase;
+    const float4 r0 = __ldg((const float4 *) (a.lut + (size_t) fbase * a.row_stride + 4 * quad));
+    const float4 r1 = __ldg((const float4 *) (a.lut + (size_t) fceil * a.row_stride + 4 * quad));
+    ws[0] = plb_mix(r0.x, r1.x, fc);
+    ws[1] = plb_mix(r0.y, r1.y, fc);
+    ws[2] = plb_mix(r0.z, r1.z, fc);
+    ws[3] = plb_mix(r0.w, r1.w, fc);
+}
+
+PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
+{
+    const int N = a.row_size;
+    const float dirx = a.pass == 1 ? 1.0f : 0.0f, diry = a.pass == 0 ? 1.0f : 0.0f;
+    const bool use_ar = a.antiring > 0.0f && a.ratio > 1.0f && !a.use_linear;
+    float posx, posy;
+    plb_coord_pos(a.cc, gx, gy, posx, posy);
+    const float f2x = plb_fractf(posx * a.cc.sizex - 0.5f), f2y = plb_fractf(posy * a.cc.sizey - 0.5f);
+    const float fcoord = f2x * dirx + f2y * diry;
+    const float ptx = a.cc.ptx * dirx, pty = a.cc.pty * diry;
+    const float off0 = (float) (N / 2 - 1);
+    const float basex = posx - fcoord * ptx - ptx * off0;
+    const float basey = posy - fcoord * pty - pty * off0;
+    float ca[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, lo[4] = {1e9f, 1e9f, 1e9f, 1e9f};
+    float ws[4] = {0, 0, 0, 0};
+    for (int n = 0; n < N; n += a.use_linear ? 2 : 1) {
+        if (n % 4 == 0)
+            ortho_weights(a, n / 4, fcoord, ws);
+        float off = (float) n;
+        if (a.use_linear)
+            off += ws[n % 4 + 1];
+        const float4 c4 = plb_tex_linear(a.src, basex + ptx * off, basey + pty * off);
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < a.src.comps) {
+                    lo[k] = fminf(lo[k], c[k]);
+                    hi[k] = fmaxf(hi[k], c[k]);
+                }
+            }
+        }
+        const float w = ws[n % 4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < a.src.comps)
+                ca[k] = __fmaf_rn(w, c[k], ca[k]);
+        }
+    }
+    out[0] = out[1] = out[2] = 0.0f;
+    out[3] = 1.0f;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!(a.comp_mask & (1 << k)) || k >= a.src.comps)
+            continue;
+        float v = ca[k];
+        if (use_ar)
+            v = plb_mix(v, plb_clamp(v, lo[k], hi[k]), a.antiring);
+        out[k] = a.scale * v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ortho(const __grid_constant__ ortho_args a)
+{
+    __shared__ plb_peak_smem ps;
+    plm_tables_init();
+    plb_tail_stage(a.tail);
+    __syncthreads();
+    const plb_tail_args &t = plb_s_tail;
+    const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 32;
+    const int gx = X0 + threadIdx.x;
+    bool has_peak = false;
+    for (int i = 0; i < plb_s_prog.n; i++)
+        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
+    const int wgs_x = has_peak ? 32 / t.wg_w : 1, wgs_y = has_peak ? 32 / t.wg_h : 1;
+    const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
+    const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
+    if (has_peak)
+        plb_peak_begin(ps);
+    const plb_op_peak *pk_any = nullptr;
+    #pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int gy = Y0 + threadIdx.y + 8 * r;
+        const bool inside = gx < t.out_w && gy < t.out_h;
+        if (!has_peak && !inside)
+            continue;
+        float prim[4], color[4];
+        ortho_pixel(a, gx, gy, prim);
+        uint32_t ypq = 0;
+        const plb_op_peak *pk = nullptr;
+        plb_tail_color(gx, gy, prim, color, &ypq, &pk);
+        if (has_peak) {
+            const int lx = (gx - X0) / t.wg_w, ly = (gy - Y0) / t.wg_h;
+            const bool valid = (X0 / t.wg_w + lx) < nwgx && (Y0 / t.wg_h + ly) < nwgy;
+            pk_any = pk;
+            plb_peak_add(ps, *pk, valid, ly * wgs_x + lx, ypq);
+        }
+        if (inside && t.dst.ptr)
+            plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy,
+                      make_float4(color[0], color[1], color[2], color[3]));
+    }
+    if (has_peak)
+        plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
+                        (uint32_t) (t.wg_w * t.wg_h));
+}
+
+#define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
+void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p);
+PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_ortho)
+
+extern "C" bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p)
+{
+    struct plb_gpu *g = plb_gpu_priv(gpu);
+    const struct plb_pixel_launch *tl = &p->tail;
+    if (p->row_size < 2 || p->row_size > 64 || p->row_stride % 4) {
+        PLB_ERR(gpu->log, "ortho sampling: unsupported filter size %d", p->row_size);
+        return false;
+    }
+    bool has_peak = false;
+    for (int i = 0; i < tl->prog.n; i++)
+        has_peak |= tl->prog.ops[i].kind == PLB_OP_PEAK;
+    const int wg_w = PLB_DEF(tl->wg_w, 16), wg_h = PLB_DEF(tl->wg_h, 16);
+    if (has_peak && (32 % wg_w || 32 % wg_h)) {
+        PLB_ERR(gpu->log, "peak detection: unsupported work group size %dx%d", wg_w, wg_h);
+        return false;
+    }
+    static ortho_args a;
+    memset(&a, 0, sizeof(a));
+    a.src = p->src;
+    a.cc = plb_coord_init(tl->coord_mode, p->src, p->rect, tl->out_w, tl->out_h);
+    a.lut = p->lut;
+    a.lut_entries = p->lut_entries;
+    a.row_size = p->row_size;
+    a.row_stride = p->row_stride;
+    a.use_linear = p->use_linear;
+    a.antiring = p->antiring;
+    a.ratio = p->ratio;
+    a.scale = p->scale;
+    a.comp_mask = p->comp_mask;
+    a.pass = p->pass;
+    plb_fill_tail(&a.tail, tl);
+    a.tail.wg_w = wg_w;
+    a.tail.wg_h = wg_h;
+    memcpy(a.tail.src_map, p->src_map, sizeof(p->src_map));
+    dim3 block(32, 8);
+    dim3 grid((tl->out_w + 31) / 32, (tl->out_h + 31) / 32);
+    if (has_peak) {
+        grid.x = ((tl->out_w + wg_w - 1) / wg_w * wg_w + 31) / 32;
+        grid.y = ((tl->out_h + wg_h - 1) / wg_h * wg_h + 31) / 32;
+    }
+    k_ortho<<<grid, block, 0, STREAM(gpu)>>>(a);
+    g->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_ortho");
+}

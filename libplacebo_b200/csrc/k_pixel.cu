@@ -87,6 +87,8 @@ void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p)
     t->wg_w = PLB_DEF(p->wg_w, 16);
     t->wg_h = PLB_DEF(p->wg_h, 16);
     t->prog = p->prog;
+    if (p->has_dovi)
+        t->dovi = p->dovi;
 }
 
 static bool prog_has_peak(const plb_color_prog *prog)

@@ -23,6 +23,8 @@ struct plb_tail_args {
     uint32_t frame_index;
     int wg_w, wg_h;        // work-group geometry for PLB_OP_PEAK
     plb_color_prog prog;
+    // after .prog: staged to shared memory only when a reshape op is present
+    plb_dovi_tab dovi;
 };
 
 // Per-CTA shared-memory copy of the launch description (everything but .prog, which lives in
@@ -46,6 +48,15 @@ PLB_DEV void plb_tail_stage(const plb_tail_args &a)
         pdst[i] = psrc[i];
     if (tid == 0)
         plb_s_tail.prog.n = a.prog.n;
+    bool dovi = false;
+    for (int i = 0; i < a.prog.n; i++)
+        dovi |= a.prog.ops[i].kind == PLB_OP_DOVI_RESHAPE;
+    if (dovi) {
+        const uint32_t *dsrc = (const uint32_t *) &a.dovi;
+        uint32_t *ddst = (uint32_t *) &plb_s_dovi;
+        for (int i = tid; i < (int) (sizeof(plb_dovi_tab) / 4); i += nt)
+            ddst[i] = dsrc[i];
+    }
 }
 
 #define PLB_MAX_WG_PER_CTA 16

@@ -177,6 +177,7 @@ struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind)
         [PLB_OP_COLOR_MAP] = "tone / gamut mapping",
         [PLB_OP_DITHER] = "dithering",
         [PLB_OP_DOVI_RESHAPE] = "reshaping",
+        [PLB_OP_DOVI_LMS] = "color decoding",
         [PLB_OP_PEAK] = "peak detection",
     };
     if (kind >= 0 && kind < (int) PLB_ARRAY_SIZE(names) && names[kind])
@@ -660,7 +661,83 @@ static void push_matrix(pl_shader sh, const pl_transform3x3 *tr)
     op->u.matrix.has_c = 1;
 }
 
-extern void plb_record_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data);
+// pl_shader_dovi_reshape host part, colorspace.c:118-169: pack the per-piece coefficients and
+// the MMR weights the way the GLSL indexes them
+static void plb_record_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data)
+{
+    if (sh->px.has_dovi) {
+        plb_shader_fail(sh, "only one Dolby Vision reshaping step per pass is supported");
+        return;
+    }
+    struct plb_dovi_tab *d = &sh->px.dovi;
+    memset(d, 0, sizeof(*d));
+    bool any = false;
+    for (int c = 0; c < 3; c++) {
+        const struct pl_reshape_data *comp = &data->comp[c];
+        d->num_pivots[c] = comp->num_pivots;
+        if (!comp->num_pivots)
+            continue;
+        if (comp->num_pivots < 2 || comp->num_pivots > 9) {
+            plb_shader_fail(sh, "invalid number of Dolby Vision pivots: %d", comp->num_pivots);
+            return;
+        }
+        any = true;
+        int mmr_idx = 0;
+        for (int i = 0; i < comp->num_pivots - 1; i++) {
+            float *co = d->coeffs[c][i];
+            if (comp->method[i] == 0) {
+                for (int k = 0; k < 3; k++)
+                    co[k] = comp->poly_coeffs[i][k];
+                co[3] = 0.0f; // order 0 signals polynomial
+            } else if (comp->method[i] == 1 && comp->mmr_order[i] >= 1 && comp->mmr_order[i] <= 3) {
+                co[3] = (float) comp->mmr_order[i];
+                co[0] = comp->mmr_constant[i];
+                co[1] = (float) mmr_idx;
+                for (int j = 0; j < comp->mmr_order[i]; j++) {
+                    float *m = &d->mmr[c][mmr_idx][0];
+                    m[0] = comp->mmr_coeffs[i][j][0];
+                    m[1] = comp->mmr_coeffs[i][j][1];
+                    m[2] = comp->mmr_coeffs[i][j][2];
+                    m[3] = 0.0f;
+                    m[4] = comp->mmr_coeffs[i][j][3];
+                    m[5] = comp->mmr_coeffs[i][j][4];
+                    m[6] = comp->mmr_coeffs[i][j][5];
+                    m[7] = comp->mmr_coeffs[i][j][6];
+                    mmr_idx += 2;
+                }
+            } else {
+                plb_shader_fail(sh, "invalid Dolby Vision mapping method");
+                return;
+            }
+        }
+        for (int i = 0; i < 7; i++)
+            d->pivots[c][i] = i < comp->num_pivots - 2 ? comp->pivots[i + 1] : 1e9f;
+        d->lo[c] = comp->pivots[0];
+        d->hi[c] = comp->pivots[comp->num_pivots - 1];
+    }
+    if (!any)
+        return;
+    if (plb_shader_push_op(sh, PLB_OP_DOVI_RESHAPE))
+        sh->px.has_dovi = 1;
+}
+
+// Dolby Vision always outputs BT.2020-referred HPE LMS (colorspace.c:392-422)
+static void plb_record_dovi_lms(pl_shader sh, const struct pl_dovi_metadata *data)
+{
+    pl_matrix3x3 lms2rgb = {{
+        { 3.06441879, -2.16597676,  0.10155818},
+        {-0.65612108,  1.78554118, -0.12943749},
+        { 0.01736321, -0.04725154,  1.03004253},
+    }};
+    pl_matrix3x3_mul(&lms2rgb, &data->linear);
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_DOVI_LMS);
+    if (!op)
+        return;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            op->u.matrix.m[3 * i + j] = lms2rgb.m[i][j];
+    }
+}
 
 void pl_shader_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data)
 {
@@ -703,7 +780,6 @@ void pl_shader_decode_color(pl_shader sh, struct pl_color_repr *repr,
     }
     case PL_COLOR_SYSTEM_DOLBYVISION: {
         // PQ EOTF -> (hard-coded HPE LMS->RGB * dovi->linear) -> PQ OETF, colorspace.c:392-422
-        extern void plb_record_dovi_lms(pl_shader sh, const struct pl_dovi_metadata *data);
         plb_record_dovi_lms(sh, dovi);
         break;
     }

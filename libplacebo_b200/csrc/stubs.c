@@ -1,13 +1,6 @@
 // Entry points that are declared in the public header but not implemented yet fail loudly.
 #include "shader_priv.h"
 
-bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p)
-{
-    (void) p;
-    PLB_ERR(gpu->log, "ortho sampling: kernel not implemented yet");
-    return false;
-}
-
 bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p)
 {
     (void) p;
@@ -16,18 +9,6 @@ bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p)
 }
 
 void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g) { (void) gpu; (void) g; }
-
-void plb_record_dovi_reshape(pl_shader sh, const struct pl_dovi_metadata *data)
-{
-    (void) data;
-    plb_shader_fail(sh, "Dolby Vision reshaping: not implemented yet");
-}
-
-void plb_record_dovi_lms(pl_shader sh, const struct pl_dovi_metadata *data)
-{
-    (void) data;
-    plb_shader_fail(sh, "Dolby Vision LMS: not implemented yet");
-}
 
 bool pl_needs_film_grain(const struct pl_film_grain_params *params) { (void) params; return false; }
 

@@ -157,8 +157,10 @@ struct orc_dovi_comp {
     float mmr_constant[8];
     float mmr_coeffs[8][3][7];
 };
-ORC_API void orc_dovi_reshape(float *rgba, size_t npix, const struct orc_dovi_comp comp[3],
-                              const float nonlinear_offset[3], const float nonlinear[9]);
+ORC_API void orc_dovi_reshape(float *rgba, size_t npix, const struct orc_dovi_comp comp[3]);
+// the Dolby Vision tail of pl_shader_decode_color, colorspace.c:392-422: PQ EOTF, LMS -> RGB
+// matrix (hard-coded HPE matrix x dovi->linear, row-major), PQ OETF
+ORC_API void orc_dovi_lms(float *rgba, size_t npix, const float lms2rgb[9]);
 
 // struct peak_buf_data, colorspace.c:936-942
 #define ORC_PEAK_SLICES 12

@@ -910,3 +910,117 @@ void orc_dither(float *rgba, int w, int h, const struct orc_dither_params *p)
         }
     }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_dovi_reshape — colorspace.c:106-273 (+ reshape_mmr :52-92, reshape_poly :94-97)
+// ------------------------------------------------------------------------------------------
+static inline float dot3f(const float a[3], const float b[3])
+{
+    return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0]));
+}
+
+static inline float dot4f(const float a[4], const float b[4])
+{
+    return fmaf(a[3], b[3], fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])));
+}
+
+void orc_dovi_reshape(float *rgba, size_t npix, const struct orc_dovi_comp comp[3])
+{
+    // host-side packing exactly like :128-169
+    float coeffs[3][8][4], mmr[3][48][4], pivots[3][7];
+    memset(coeffs, 0, sizeof(coeffs));
+    memset(mmr, 0, sizeof(mmr));
+    for (int c = 0; c < 3; c++) {
+        const struct orc_dovi_comp *cp = &comp[c];
+        int mmr_idx = 0;
+        for (int i = 0; i < cp->num_pivots - 1; i++) {
+            if (cp->method[i] == 0) {
+                for (int k = 0; k < 3; k++)
+                    coeffs[c][i][k] = cp->poly_coeffs[i][k];
+            } else {
+                coeffs[c][i][3] = (float) cp->mmr_order[i];
+                coeffs[c][i][0] = cp->mmr_constant[i];
+                coeffs[c][i][1] = (float) mmr_idx;
+                for (int j = 0; j < cp->mmr_order[i]; j++) {
+                    float *m = &mmr[c][mmr_idx][0];
+                    m[0] = cp->mmr_coeffs[i][j][0]; m[1] = cp->mmr_coeffs[i][j][1];
+                    m[2] = cp->mmr_coeffs[i][j][2]; m[3] = 0.0f;
+                    m[4] = cp->mmr_coeffs[i][j][3]; m[5] = cp->mmr_coeffs[i][j][4];
+                    m[6] = cp->mmr_coeffs[i][j][5]; m[7] = cp->mmr_coeffs[i][j][6];
+                    mmr_idx += 2;
+                }
+            }
+        }
+        for (int i = 0; i < 7; i++)
+            pivots[c][i] = i < cp->num_pivots - 2 ? cp->pivots[i + 1] : 1e9f;
+    }
+
+    #pragma omp parallel for schedule(static)
+    for (size_t n = 0; n < npix; n++) {
+        float *px = rgba + 4 * n;
+        const float sig[3] = { clampf(px[0], 0.0f, 1.0f), clampf(px[1], 0.0f, 1.0f),
+                               clampf(px[2], 0.0f, 1.0f) };
+        for (int c = 0; c < 3; c++) {
+            const struct orc_dovi_comp *cp = &comp[c];
+            if (!cp->num_pivots)
+                continue;
+            float s = sig[c];
+            const float *co;
+            if (cp->num_pivots > 2) {
+                // mix tree :206-216: mix(a, b, bvec) picks b where true
+                #define TESTP(i) (s >= pivots[c][i])
+                int k;
+                if (TESTP(3))
+                    k = TESTP(5) ? (TESTP(6) ? 7 : 6) : (TESTP(4) ? 5 : 4);
+                else
+                    k = TESTP(1) ? (TESTP(2) ? 3 : 2) : (TESTP(0) ? 1 : 0);
+                #undef TESTP
+                co = coeffs[c][k];
+            } else {
+                co = coeffs[c][0];
+            }
+            if (co[3] == 0.0f) {
+                s = (co[2] * s + co[1]) * s + co[0];
+            } else {
+                const int idx = (int) co[1];
+                const unsigned order = (unsigned) co[3];
+                float sigX[4] = { sig[0] * sig[1], sig[0] * sig[2], sig[1] * sig[2], 0.0f };
+                sigX[3] = sigX[0] * sig[2];
+                s = co[0];
+                s += dot3f(mmr[c][idx + 0], sig);
+                s += dot4f(mmr[c][idx + 1], sigX);
+                if (order >= 2) {
+                    const float sig2[3] = { sig[0] * sig[0], sig[1] * sig[1], sig[2] * sig[2] };
+                    const float sigX2[4] = { sigX[0] * sigX[0], sigX[1] * sigX[1],
+                                             sigX[2] * sigX[2], sigX[3] * sigX[3] };
+                    s += dot3f(mmr[c][idx + 2], sig2);
+                    s += dot4f(mmr[c][idx + 3], sigX2);
+                    if (order >= 3) {
+                        const float sig3[3] = { sig2[0] * sig[0], sig2[1] * sig[1], sig2[2] * sig[2] };
+                        const float sigX3[4] = { sigX2[0] * sigX[0], sigX2[1] * sigX[1],
+                                                 sigX2[2] * sigX[2], sigX2[3] * sigX[3] };
+                        s += dot3f(mmr[c][idx + 4], sig3);
+                        s += dot4f(mmr[c][idx + 5], sigX3);
+                    }
+                }
+            }
+            px[c] = clampf(s, cp->pivots[0], cp->pivots[cp->num_pivots - 1]);
+        }
+    }
+}
+
+void orc_dovi_lms(float *rgba, size_t npix, const float lms2rgb[9])
+{
+    const struct pq_lit q = pq_literal();
+    #pragma omp parallel for schedule(static)
+    for (size_t n = 0; n < npix; n++) {
+        float *px = rgba + 4 * n;
+        float c[3];
+        for (int k = 0; k < 3; k++)
+            c[k] = pq_eotf_lit(&q, px[k]);
+        mat3_mul(lms2rgb, c);
+        for (int k = 0; k < 3; k++)
+            px[k] = pq_oetf_lit(&q, c[k], true);
+    }
+}

@@ -152,6 +152,72 @@ API void shim_reset_objs(struct shim_ctx *c)
     pl_shader_obj_destroy(&c->objs.dither);
 }
 
+/* Dolby Vision metadata of the reference's own test fixture (src/tests/utils.h:279-323).
+ * variant 0: as in the fixture (identity matrices); variant 1: same curves with a non-trivial
+ * `linear` / `nonlinear` matrix and offsets, to exercise the matrix paths as well. */
+static const struct pl_dovi_metadata *shim_dovi_fixture(int variant)
+{
+    static struct pl_dovi_metadata m[2];
+    static bool init;
+    if (!init) {
+        const struct pl_dovi_metadata base = {
+            .nonlinear = {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}},
+            .linear    = {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}},
+            .comp = {
+                {
+                    .num_pivots = 9,
+                    .pivots = {0.0615835786, 0.129032254, 0.353861183,
+                               0.604105592, 0.854349971, 0.890518069,
+                               0.906158328, 0.913978517, 0.92082113},
+                    .method = {0, 0, 0, 0, 0, 0, 0, 0},
+                    .poly_coeffs = {
+                        {-0.0488376617, 1.99335372, -2.41716385},
+                        {-0.0141925812, 1.61829138, -1.53397191},
+                        { 0.157061458, 0.63640213, -0.11302495},
+                        {0.25272119, 0.246226311, 0.27281332},
+                        {0.951621532, -1.35507894, 1.18898678},
+                        {6.41251612, -13.6188488, 8.07336903},
+                        {13.467535, -29.1869125, 16.6612244},
+                        {28.2321472, -61.8516273, 34.7264938}
+                    },
+                }, {
+                    .num_pivots = 2,
+                    .pivots = {0.0, 1.0},
+                    .method = {1},
+                    .mmr_order = {3},
+                    .mmr_constant = {-0.500733018},
+                    .mmr_coeffs = {{
+                        {1.08411026, 3.80807829, 0.0881733894, -3.23097038, -0.409078479, -1.31310081, 2.71297002},
+                        {-0.241833091, -3.57880807, -0.108109117, 3.13198471, 0.869203091, 1.96561158, -9.30871677},
+                        {-0.177356839, 1.48970401, 0.0908923149, -0.510447979, -0.687603354, -0.934977889, 12.3544884},
+                    }},
+                }, {
+                    .num_pivots = 2,
+                    .pivots = {0.0, 1.0},
+                    .method = {1},
+                    .mmr_order = {3},
+                    .mmr_constant = {-1.23833287},
+                    .mmr_coeffs = {{
+                        {3.52909589, 0.383154511, 5.50820637, -1.02094889, -6.36386824, 0.194121242, 0.64683497},
+                        {-2.57899785, -0.626081586, -6.05729723, 2.29143763, 9.14653015, -0.0507702827, -4.17724133},
+                        {0.705404401, 0.341412306, 2.98387456, -1.71712542, -4.91501331, 0.1465137, 6.38665438},
+                    }},
+                },
+            },
+        };
+        m[0] = m[1] = base;
+        m[1].nonlinear_offset[0] = 0.0625f;
+        m[1].nonlinear_offset[1] = 0.5f;
+        m[1].nonlinear_offset[2] = 0.5f;
+        m[1].nonlinear = (pl_matrix3x3) {{{1.0f, 0.0f, 1.5f}, {1.0f, -0.17f, -0.58f}, {1.0f, 1.88f, 0.0f}}};
+        m[1].linear = (pl_matrix3x3) {{{0.95f, 0.04f, 0.01f}, {0.02f, 0.96f, 0.02f}, {0.0f, 0.03f, 0.97f}}};
+        init = true;
+    }
+    return &m[variant ? 1 : 0];
+}
+
+API const void *shim_dovi_fixture_ptr(int variant) { return shim_dovi_fixture(variant); }
+
 API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
                  const float *sargs, const char *filter_name, const int *ops, const float *oargs,
                  float *out_peak /* avg_pq, max_pq or NULL */)
@@ -283,6 +349,21 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
                                        hq ? &pl_peak_detect_high_quality_params
                                           : &pl_peak_detect_default_params))
                 goto done;
+            break;
+        }
+        case 10: /* pl_shader_dovi_reshape with the reference's test fixture */
+            pl_shader_dovi_reshape(sh, shim_dovi_fixture((int) a[0]));
+            a += 1;
+            break;
+        case 11: { /* pl_shader_decode_color of a Dolby Vision repr (fixture, variant a[0]) */
+            struct pl_color_repr repr = {
+                .sys = PL_COLOR_SYSTEM_DOLBYVISION,
+                .levels = PL_COLOR_LEVELS_FULL,
+                .bits = { (int) a[1], (int) a[2], 0 },
+                .dovi = shim_dovi_fixture((int) a[0]),
+            };
+            a += 3;
+            pl_shader_decode_color(sh, &repr, NULL);
             break;
         }
         default:

@@ -164,6 +164,13 @@ class T0:
         self.f("repr_encode")(sys, levels, sample_depth, color_depth, bit_shift, fp(o))
         return dict(m=o[:9].copy(), c=o[9:12].copy(), scale=o[12], raw=o)
 
+    def repr_decode_dovi(self, sample_depth, color_depth, offset3, nonlinear9, linear9):
+        o = np.zeros(22, f32)
+        d = np.concatenate([np.asarray(offset3, f32), np.asarray(nonlinear9, f32)]).astype(f32)
+        l = np.ascontiguousarray(linear9, f32)
+        self.f("repr_decode_dovi")(sample_depth, color_depth, fp(d), fp(l), fp(o))
+        return dict(scale=o[0], m=o[1:10].copy(), c=o[10:13].copy(), lms2rgb=o[13:22].copy())
+
     def raw_primaries(self, prim):
         o = np.zeros(8, f32)
         self.f("raw_primaries")(prim, fp(o))
@@ -273,6 +280,30 @@ class OrcDeband(C.Structure):
     _fields_ = [("iterations", C.c_int), ("threshold", C.c_float), ("radius", C.c_float),
                 ("grain", C.c_float), ("grain_neutral", C.c_float * 3), ("scale", C.c_float),
                 ("comp_mask", C.c_uint8), ("frame_index", C.c_uint32)]
+
+
+class OrcDoviComp(C.Structure):
+    _fields_ = [("num_pivots", C.c_int), ("pivots", C.c_float * 9), ("method", C.c_int * 8),
+                ("poly_coeffs", (C.c_float * 3) * 8), ("mmr_order", C.c_int * 8),
+                ("mmr_constant", C.c_float * 8), ("mmr_coeffs", ((C.c_float * 7) * 3) * 8)]
+
+
+class DoviComp(C.Structure):  # struct pl_reshape_data of the public header
+    _fields_ = [("num_pivots", C.c_uint8), ("pivots", C.c_float * 9), ("method", C.c_uint8 * 8),
+                ("poly_coeffs", (C.c_float * 3) * 8), ("mmr_order", C.c_uint8 * 8),
+                ("mmr_constant", C.c_float * 8), ("mmr_coeffs", ((C.c_float * 7) * 3) * 8)]
+
+
+class DoviMeta(C.Structure):  # struct pl_dovi_metadata
+    _fields_ = [("nonlinear_offset", C.c_float * 3), ("nonlinear", C.c_float * 9),
+                ("linear", C.c_float * 9), ("comp", DoviComp * 3)]
+
+
+def dovi_fixture(variant=0):
+    """The reference's Dolby Vision test fixture (src/tests/utils.h:279-323) as held by the C shim."""
+    sh = shim()
+    sh.shim_dovi_fixture_ptr.restype = C.c_void_p
+    return DoviMeta.from_address(sh.shim_dovi_fixture_ptr(variant))
 
 
 class OrcPeakBuf(C.Structure):
@@ -443,6 +474,29 @@ class Oracle:
     def encode_special(self, rgba, sys):
         rgba = np.ascontiguousarray(rgba, f32).copy()
         self.lib.orc_encode_special(fp(rgba), C.c_size_t(rgba.size // 4), sys)
+        return rgba
+
+    def dovi_reshape(self, rgba, meta):
+        rgba = np.ascontiguousarray(rgba, f32).copy()
+        comps = (OrcDoviComp * 3)()
+        for c in range(3):
+            s, d = meta.comp[c], comps[c]
+            d.num_pivots = s.num_pivots
+            for i in range(9):
+                d.pivots[i] = s.pivots[i]
+            for i in range(8):
+                d.method[i], d.mmr_order[i], d.mmr_constant[i] = s.method[i], s.mmr_order[i], s.mmr_constant[i]
+                for k in range(3):
+                    d.poly_coeffs[i][k] = s.poly_coeffs[i][k]
+                    for j in range(7):
+                        d.mmr_coeffs[i][k][j] = s.mmr_coeffs[i][k][j]
+        self.lib.orc_dovi_reshape(fp(rgba), C.c_size_t(rgba.size // 4), comps)
+        return rgba
+
+    def dovi_lms(self, rgba, lms2rgb):
+        rgba = np.ascontiguousarray(rgba, f32).copy()
+        m = np.ascontiguousarray(lms2rgb, f32)
+        self.lib.orc_dovi_lms(fp(rgba), C.c_size_t(rgba.size // 4), fp(m))
         return rgba
 
     def sigmoidize(self, rgba, center=0.75, slope=6.5, inverse=False):

@@ -206,3 +206,30 @@ def test_deterministic_math_matches_oracle_definition(gpu, oracle, fn):
     want = np.empty(n, np.float32)
     oracle.lib.orc_math(fn, T.fp(a), T.fp(b), T.fp(want), C.c_size_t(n))
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_dovi_reshape(gpu, oracle, variant):
+    """pl_shader_dovi_reshape with the reference's fixture: 8-piece polynomial luma, order-3 MMR
+    chroma (config C5's curve set). Same fp32 operation order -> identical bits."""
+    src = rgb(12, gray_frac=0.0)
+    src[1, :16, 0] = np.linspace(-0.1, 1.1, 16)  # outside [0,1] and across every pivot
+    got = run_ops(gpu, src, [10], [[float(variant)]])
+    want = oracle.dovi_reshape(src, T.dovi_fixture(variant))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_dovi_decode_color(gpu, oracle, variant):
+    """pl_shader_decode_color for PL_COLOR_SYSTEM_DOLBYVISION (colorspace.c:285-310, 392-422):
+    normalise, reshape, RPU matrix + offsets, PQ EOTF, LMS->RGB, PQ OETF."""
+    src = rgb(13, gray_frac=0.0)
+    src[..., :3] *= np.float32(1023.0 / 65535.0)  # 10-bit code values in 16-bit samples
+    meta = T.dovi_fixture(variant)
+    got = run_ops(gpu, src, [11], [[float(variant), 16.0, 10.0]])
+    d = T.t0().repr_decode_dovi(16, 10, list(meta.nonlinear_offset), list(meta.nonlinear), list(meta.linear))
+    x = oracle.scale(src, float(d["scale"]), with_alpha=False)
+    x = oracle.dovi_reshape(x, meta)
+    x = oracle.apply_matrix(x, d["m"], d["c"])
+    want = oracle.dovi_lms(x, d["lms2rgb"])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -144,3 +144,47 @@ def test_polar_2x_sited_chroma_phases(gpu, oracle, ox, oy, comps):
     want = oracle.sample_polar(src.astype(np.float32), 192, 108, f, comp_mask=(1 << comps) - 1,
                                rect=rect, coord_mode=T.COORD_EXACT)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- separable (ortho) scaling: pl_shader_sample_ortho2, one 1-D pass per call -----------------
+ORTHO_FILTERS = ["lanczos", "gaussian", "spline36", "mitchell", "bilinear", "hermite", "ginseng"]
+
+
+def _ortho_case(gpu, oracle, name, src, dw, dh, comps, antiring=-1.0, fmt=None):
+    h, w = src.shape[:2]
+    pass_ = 0 if dw == w else 1
+    ratio = dh / h if pass_ == 0 else dw / w
+    blur = max(1.0 / ratio, 1.0)
+    f = T.t0().filter_generate(name, blur=blur, polar=False)
+    fmt = fmt or {1: "r16hf", 2: "rg16hf", 4: "rgba16hf"}[comps]
+    got = gpu.simple("ortho", src, fmt, dw, dh, comps=comps, filt=name, sargs_extra=[antiring])
+    want = oracle.sample_ortho(src.astype(np.float32), dw, dh, f, pass_, comp_mask=(1 << comps) - 1,
+                               coord_mode=T.COORD_EXACT,
+                               antiring=None if antiring < 0 else antiring, ratio=ratio)
+    return got, want
+
+
+@pytest.mark.parametrize("name", ORTHO_FILTERS)
+@pytest.mark.parametrize("direction", ["vertical", "horizontal"])
+def test_ortho_upscale_2x(gpu, oracle, name, direction):
+    src = rand_tex(45, 80, 4, seed=31)
+    dw, dh = (80, 90) if direction == "vertical" else (160, 45)
+    got, want = _ortho_case(gpu, oracle, name, src, dw, dh, 4)
+    assert max_ulp32(got, want) <= 1, (name, np.mean(got != want))
+    assert np.mean(got != want) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["lanczos", "mitchell", "hermite"])
+@pytest.mark.parametrize("size", [(80, 119), (80, 31), (211, 45), (57, 45)])
+def test_ortho_arbitrary_ratio(gpu, oracle, name, size):
+    """Non-integer up- and down-scaling (downscaling widens the kernel: blur = 1/ratio)."""
+    src = rand_tex(45, 80, 2, seed=32)
+    got, want = _ortho_case(gpu, oracle, name, src, size[0], size[1], 2)
+    d = np.abs(got - want)
+    assert d.max() < 2e-6, (name, size, d.max())
+
+
+def test_ortho_antiringing(gpu, oracle):
+    src = rand_tex(45, 80, 4, seed=33)
+    got, want = _ortho_case(gpu, oracle, "lanczos", src, 160, 45, 4, antiring=0.8)
+    assert max_ulp32(got, want) <= 1

@@ -162,3 +162,14 @@ def test_error_diffusion_kernels(ref, pt0):
         assert a["shift"] == b["shift"] and a["divisor"] == b["divisor"]
         assert np.array_equal(a["pattern"], b["pattern"])
     assert pt0.error_diffusion_kernel("nope") is None
+
+
+def test_dovi_repr_decode(ref, pt0):
+    """pl_color_repr_normalize + pl_color_repr_decode for a Dolby Vision repr (RPU matrix and
+    offsets) and the LMS->RGB x linear product: product T0 == compiled reference."""
+    for variant in (0, 1):
+        m = T.dovi_fixture(variant)
+        args = (16, 10, list(m.nonlinear_offset), list(m.nonlinear), list(m.linear))
+        a, b = ref.repr_decode_dovi(*args), pt0.repr_decode_dovi(*args)
+        for k in a:
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (variant, k)
