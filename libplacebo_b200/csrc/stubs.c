@@ -1,13 +1,6 @@
 // Entry points that are declared in the public header but not implemented yet fail loudly.
 #include "shader_priv.h"
 
-bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p)
-{
-    (void) p;
-    PLB_ERR(gpu->log, "error diffusion: kernel not implemented yet");
-    return false;
-}
-
 void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g) { (void) gpu; (void) g; }
 
 bool pl_needs_film_grain(const struct pl_film_grain_params *params) { (void) params; return false; }
@@ -17,19 +10,6 @@ bool pl_shader_film_grain(pl_shader sh, pl_shader_obj *grain_state,
 {
     (void) grain_state; (void) params;
     plb_shader_fail(sh, "film grain: not implemented yet");
-    return false;
-}
-
-size_t pl_error_diffusion_shmem_req(const struct pl_error_diffusion_kernel *kernel, int height)
-{
-    (void) kernel; (void) height;
-    return 0;
-}
-
-bool pl_shader_error_diffusion(pl_shader sh, const struct pl_error_diffusion_params *params)
-{
-    (void) params;
-    plb_shader_fail(sh, "error diffusion: not implemented yet");
     return false;
 }
 
@@ -57,12 +37,3 @@ bool plb_plane_film_grain(pl_renderer rr, pl_shader sh, pl_shader_obj *state,
     return false;
 }
 
-bool plb_pass_error_diffusion(pl_renderer rr, pl_dispatch dp, pl_shader *sh, int new_depth,
-                              int comps, int out_w, int out_h, pl_fmt fbofmt,
-                              const struct pl_error_diffusion_kernel *kernel,
-                              pl_tex (*get_fbo)(void *, int, int, pl_fmt, int), void *priv)
-{
-    (void) rr; (void) dp; (void) sh; (void) new_depth; (void) comps; (void) out_w; (void) out_h;
-    (void) fbofmt; (void) kernel; (void) get_fbo; (void) priv;
-    return false;
-}

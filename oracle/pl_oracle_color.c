@@ -1019,8 +1019,80 @@ void orc_dovi_lms(float *rgba, size_t npix, const float lms2rgb[9])
         float c[3];
         for (int k = 0; k < 3; k++)
             c[k] = pq_eotf_lit(&q, px[k]);
-        mat3_mul(lms2rgb, c);
+        // `lms2rgb` is the row-major pl_matrix3x3 (uploaded transposed, i.e. M * v as written)
+        float o[3];
+        for (int k = 0; k < 3; k++) {
+            float v = lms2rgb[3*k] * c[0];
+            v = fmaf(lms2rgb[3*k + 1], c[1], v);
+            o[k] = fmaf(lms2rgb[3*k + 2], c[2], v);
+        }
         for (int k = 0; k < 3; k++)
-            px[k] = pq_oetf_lit(&q, c[k], true);
+            px[k] = pq_oetf_lit(&q, o[k], true);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// pl_shader_error_diffusion — dithering.c:326-527. Serial restatement in shifted-column order
+// with the same packed RGB8 ring words (the packing's wrap-around is part of the semantics).
+// ------------------------------------------------------------------------------------------
+void orc_error_diffusion(const float *rgba_in, float *rgba_out, int w, int h,
+                         int new_depth, int shift, int divisor, const int *pattern)
+{
+    const int ring_rows = h + 2;
+    int rightmost = 0;
+    for (int dy = 0; dy <= 2; dy++) {
+        for (int dx = -2; dx <= 2; dx++) {
+            if (pattern[dy * 5 + dx + 2] && dx + dy * shift > rightmost)
+                rightmost = dx + dy * shift;
+        }
+    }
+    const uint32_t ring_size = (uint32_t) ring_rows * (uint32_t) (rightmost + 1);
+    uint32_t *err = calloc(ring_size, sizeof(uint32_t));
+    const float quant = (float) ((1ll << new_depth) - 1);
+    const int shifted_width = w + (h - 1) * shift;
+    for (int xs = 0; xs < shifted_width; xs++) {
+        for (int y = 0; y < h; y++) {
+            const int x = xs - y * shift;
+            if (x < 0 || x >= w)
+                continue;
+            const uint32_t idx = (uint32_t) (xs * ring_rows + y) % ring_size;
+            const float *po = rgba_in + ((size_t) y * w + x) * 4;
+            float *out = rgba_out + ((size_t) y * w + x) * 4;
+            uint32_t e = err[idx] + ((128u << 24) | (128u << 12) | 128u);
+            err[idx] = 0;
+            const int ei[3] = { (int) ((e >> 24) & 0xFFu) - 128, (int) ((e >> 12) & 0xFFu) - 128,
+                                (int) (e & 0xFFu) - 128 };
+            float pix[3], dith[3], ed[3];
+            for (int k = 0; k < 3; k++) {
+                pix[k] = po[k] * quant + (float) ei[k] / 254.0f;
+                dith[k] = roundf(pix[k]);
+                out[k] = dith[k] / quant;
+                ed[k] = (pix[k] - dith[k]) * 254.0f / (float) divisor;
+            }
+            out[3] = po[3];
+            for (int dividend = 1; dividend <= divisor; dividend++) {
+                bool assigned = false;
+                uint32_t packed = 0;
+                for (int dy = 0; dy <= 2; dy++) {
+                    for (int dx = -2; dx <= 2; dx++) {
+                        if (pattern[dy * 5 + dx + 2] != dividend)
+                            continue;
+                        if (!assigned) {
+                            assigned = true;
+                            const int t0 = (int) roundf(ed[0] * (float) dividend);
+                            const int t1 = (int) roundf(ed[1] * (float) dividend);
+                            const int t2 = (int) roundf(ed[2] * (float) dividend);
+                            packed = ((uint32_t) (t0 & 0xFF) << 24) | ((uint32_t) (t1 & 0xFF) << 12) |
+                                     (uint32_t) (t2 & 0xFF);
+                        }
+                        if (dx < 0 && !(x >= -dx))
+                            continue;
+                        const uint32_t delta = (uint32_t) ((dx + dy * shift) * ring_rows + dy);
+                        err[(idx + delta) % ring_size] += packed;
+                    }
+                }
+            }
+        }
+    }
+    free(err);
 }

@@ -494,6 +494,27 @@ API void shim_renderer_reset(struct shim_ctx *c)
     pl_shader_obj_destroy(&c->objs.cmap); /* forget the detected peak / cached LUTs */
 }
 
+/* pl_shader_error_diffusion as a stand-alone compute dispatch (src/tests/gpu_tests.c:1003-1040) */
+API int shim_error_diffusion(struct shim_ctx *c, void *src_tex, void *dst_tex, int new_depth,
+                             const char *kernel)
+{
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    bool ok = pl_shader_error_diffusion(sh, pl_error_diffusion_params(
+        .input_tex = src_tex,
+        .output_tex = dst_tex,
+        .new_depth = new_depth,
+        .kernel = pl_find_error_diffusion_kernel(kernel),
+    ));
+    if (!ok) {
+        pl_dispatch_abort(c->dp, &sh);
+        return -1;
+    }
+    return pl_dispatch_compute(c->dp, pl_dispatch_compute_params(
+        .shader = &sh,
+        .dispatch_size = {1, 1, 1},
+    )) ? 0 : -2;
+}
+
 API int shim_math_eval(struct shim_ctx *c, int fn, const float *a, const float *b, float *out,
                        size_t n)
 {

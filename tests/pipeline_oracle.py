@@ -72,7 +72,8 @@ def fix_bits(fmt_depth, bits):
 
 def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0,
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
-           coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None):
+           coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
+           error_diffusion=None):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
     smoothed (avg, max) between frames like sh_color_map_obj.peak does."""
     t0, orc = T.t0(), T.oracle()
@@ -220,7 +221,13 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         enc = t0.repr_encode(tgt.sys, tgt.levels, tbits[0], tbits[0], 0)
         color = orc.apply_matrix(color, enc["m"], enc["c"])
     depth = tbits[1]
-    if depth and depth < 16 and dither:
+    if depth and depth < 16 and error_diffusion:
+        # pass_error_diffusion (renderer.c:2282-2343): image -> rgba16hf FBO -> single work
+        # group diffusion -> rgba16hf FBO -> sampled 1:1
+        k = t0.error_diffusion_kernel(error_diffusion)
+        fbo = orc.store_round(color, 0)  # float values after rounding to half
+        color = orc.store_round(orc.error_diffusion(fbo, depth, k), 0)
+    elif depth and depth < 16 and dither:
         lut = t0.dither_matrix(0 if dither == 1 else 1, 64) if dither in (1, 2) else None
         method = {1: 0, 2: 1, 3: 2, 4: 3}[dither]
         gamma = approx_gamma(int(dst_csp[1]))

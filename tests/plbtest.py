@@ -41,6 +41,8 @@ HDR = dict(NORM=0, SQRT=1, NITS=2, PQ=3)
 META = dict(ANY=0, NONE=1, HDR10=2, HDR10PLUS=3, CIE_Y=4)
 TONE_FNS = ["clip", "st2094-40", "st2094-10", "bt2390", "bt2446a", "spline", "reinhard",
             "mobius", "hable", "gamma", "linear", "linearlight"]
+ED_KERNELS = ["simple", "false-fs", "sierra-lite", "floyd-steinberg", "atkinson",
+              "jarvis-judice-ninke", "stucki", "burkes", "sierra-2", "sierra-3"]
 GAMUT_FNS = ["clip", "perceptual", "softclip", "relative", "saturation", "absolute",
              "desaturate", "darken", "highlight", "linear"]
 TONE_CONSTANTS = np.array([0.4, 0.1, 0.8, 0.4, 1.0, 1.5, 0.2, 0.5, 0.5, 0.3, 1.0], f32)
@@ -525,6 +527,16 @@ class Oracle:
         rgba = np.ascontiguousarray(rgba, f32).copy()
         self.lib.orc_color_map(fp(rgba), C.c_size_t(rgba.size // 4), C.byref(params))
         return rgba
+
+    def error_diffusion(self, rgba, new_depth, kernel):
+        """kernel: dict from T0.error_diffusion_kernel"""
+        src = np.ascontiguousarray(rgba, f32)
+        h, w = src.shape[:2]
+        out = np.zeros_like(src)
+        pat = np.ascontiguousarray(kernel["pattern"], np.int32)
+        self.lib.orc_error_diffusion(fp(src), fp(out), w, h, new_depth, kernel["shift"],
+                                     kernel["divisor"], ip(pat))
+        return out
 
     def dither(self, rgba, new_depth, method=0, lut=None, temporal=False, frame_index=0,
                gamma=1.0):

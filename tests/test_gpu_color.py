@@ -233,3 +233,48 @@ def test_dovi_decode_color(gpu, oracle, variant):
     x = oracle.apply_matrix(x, d["m"], d["c"])
     want = oracle.dovi_lms(x, d["lms2rgb"])
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+ED_KERNELS = ["simple", "false-fs", "sierra-lite", "floyd-steinberg", "atkinson",
+              "jarvis-judice-ninke", "stucki", "burkes", "sierra-2", "sierra-3"]
+
+
+@pytest.mark.parametrize("name", ED_KERNELS)
+def test_error_diffusion_kernels(gpu, oracle, name):
+    """pl_shader_error_diffusion (all built-in kernels) as a stand-alone compute dispatch:
+    integer error words + identical float steps -> identical output."""
+    import ctypes as C
+    k = T.t0().error_diffusion_kernel(name)
+    assert k is not None, name
+    h, w = 50, 70
+    r = np.random.default_rng(5)
+    src = r.random((h, w, 4), dtype=np.float32)
+    src[:8] = src[:8] * 0.02 + 0.5  # flat-ish area: long error chains
+    s = gpu.tex("rgba32f", w, h, src)
+    d = gpu.tex("rgba32f", w, h)
+    try:
+        rc = gpu.lib.shim_error_diffusion(C.c_void_p(gpu.ctx), C.c_void_p(s), C.c_void_p(d), 8, name.encode())
+        assert rc == 0
+        got = gpu.download(d, "rgba32f", w, h)
+    finally:
+        gpu.free(s, d)
+    want = oracle.error_diffusion(src, 8, k)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.mean(got != want)
+
+
+@pytest.mark.parametrize("depth,size", [(8, (33, 1100)), (6, (64, 64)), (1, (40, 40))])
+def test_error_diffusion_depths_and_tall_images(gpu, oracle, depth, size):
+    """More rows than threads (1100 > 1024): a column is split over several rows per thread."""
+    import ctypes as C
+    k = T.t0().error_diffusion_kernel("sierra-lite")
+    w, h = size
+    src = np.random.default_rng(6).random((h, w, 4), dtype=np.float32)
+    s = gpu.tex("rgba32f", w, h, src)
+    d = gpu.tex("rgba32f", w, h)
+    try:
+        assert gpu.lib.shim_error_diffusion(C.c_void_p(gpu.ctx), C.c_void_p(s), C.c_void_p(d), depth, b"sierra-lite") == 0
+        got = gpu.download(d, "rgba32f", w, h)
+    finally:
+        gpu.free(s, d)
+    want = oracle.error_diffusion(src, depth, k)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, peak=0,
                allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, tone_fn=None,
-               gamut_fn=None):
+               gamut_fn=None, error_diffusion=None):
     Y, U, V = img.planes
     texs = [gpu.tex("r16", p.shape[1], p.shape[0], p) for p in (Y, U, V)]
     dst = gpu.tex(tgt.fmt, tgt.w, tgt.h)
@@ -27,6 +27,7 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
         opts[0], opts[1], opts[2], opts[3], opts[4] = deband, peak, allow_delayed, dither, cmap_hq
         opts[5] = P.CHROMA_ENUM[img.chroma_loc]
         opts[7] = frame_index
+        opts[8] = T.ED_KERNELS.index(error_diffusion) + 1 if error_diffusion else 0
         opts[9] = T.TONE_FNS.index(tone_fn) + 1 if tone_fn else 0
         opts[10] = T.GAMUT_FNS.index(gamut_fn) + 1 if gamut_fn else 0
         peak_out = np.zeros(2, T.f32)
@@ -149,3 +150,15 @@ def test_peak_smoothing_over_frames(gpu):
         want, state = P.render(img, tgt, peak_state=state, **kw)
         assert np.float32(peak[0]) == np.float32(state[0]) and np.float32(peak[1]) == np.float32(state[1]), (i, peak, state)
         assert np.array_equal(got[..., :3], want[..., :3]), i
+
+
+@pytest.mark.parametrize("kernel", ["sierra-lite", "floyd-steinberg"])
+def test_render_with_error_diffusion(gpu, kernel):
+    """Config C5's output stage at reduced size: error diffusion to 8 bits replaces the dither
+    matrix (renderer.c:2886-2899); two extra rgba16hf FBOs, one single-work-group dispatch."""
+    planes = T.yuv420p10(160, 90, seed=14)
+    img = P.Frame(planes, T.SYS["BT_709"], csp=SDR)
+    tgt = P.Target(160, 90, "rgba8", sample_depth=8, color_depth=8, csp=SDR)
+    got, _ = gpu_render(gpu, img, tgt, dither=1, error_diffusion=kernel)
+    want, _ = P.render(img, tgt, dither=1, error_diffusion=kernel)
+    assert np.array_equal(got[..., :3], want[..., :3]), np.mean(got[..., :3] != want[..., :3])
