@@ -40,7 +40,7 @@ L2_BYTES = 126e6
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_4k_hdr10_to_sdr")
@@ -254,6 +254,8 @@ def run_ours(args, rank, world, local_rank):
         ev0.record(lib_stream)
         for i in range(n):
             frame(i, e2e)
+        if e2e:
+            st.join()  # the timed interval ends when the last download has landed
         ev1.record(lib_stream)
         st.finish()
         barrier()

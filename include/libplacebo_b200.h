@@ -624,6 +624,8 @@ struct pl_cuda_params {
     int device;        // CUDA device ordinal
     void *stream;      // cudaStream_t to order all work on (NULL = create a private one)
     bool no_timers;    // skip cudaEvent timers in pl_dispatch
+    bool no_async_transfers; // run pl_tex_upload/download on the main stream instead of the
+                             // copy-engine streams (default: overlap transfers with kernels)
     // Sampling positions: by default they are evaluated exactly (like a rasteriser's
     // interpolators). Set this to reproduce, in fp32, the attribute emulation the reference
     // uses for compute shaders (src/dispatch.c:1038-1062); it disables the tabulated-phase
@@ -647,6 +649,9 @@ PL_API pl_tex pl_cuda_wrap(pl_gpu gpu, const struct pl_cuda_wrap_params *params)
 PL_API void *pl_cuda_tex_ptr(pl_tex tex, size_t *out_pitch);
 // Number of kernels launched through this gpu since creation (bench.py: gpu_launches)
 PL_API uint64_t pl_cuda_launch_count(pl_gpu gpu);
+// Makes the main stream (pl_cuda_stream) wait for every transfer enqueued so far on the
+// copy-engine streams — e.g. before recording an event that should cover a whole frame.
+PL_API void pl_cuda_join(pl_gpu gpu);
 // Diagnostics: evaluates the kernels' deterministic transcendental functions (plb_math.cuh) on
 // host arrays of n floats. fn: 0 pow(a,b) 1 exp(a) 2 log(a) 3 sin(a) 4 cos(a) 5 atan2(a,b).
 // Returns false on a CUDA error. Lets integrators check cross-machine reproducibility.

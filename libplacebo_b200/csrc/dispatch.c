@@ -227,6 +227,15 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         pass = find_pass(dp, sh, w, h);
     }
 
+    // order this launch after pending host<->device transfers of its textures
+    pl_tex texs[13];
+    int ntexs = 0;
+    for (int i = 0; i < sh->num_texs; i++)
+        texs[ntexs++] = sh->texs[i];
+    if (target)
+        texs[ntexs++] = target;
+    plb_gpu_before_use(gpu, texs, ntexs);
+
     plb_timer_begin(gpu, timer);
     bool ok = false;
     switch (sh->src) {
@@ -248,6 +257,7 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         break;
     }
     plb_timer_end(gpu, timer);
+    plb_gpu_after_use(gpu, texs, ntexs);
     if (ok && pass && dp->info_callback) {
         pass_collect(dp, pass);
         dp->info_callback(dp->info_priv, &pass->stats);

@@ -66,6 +66,8 @@ bool pl_shader_error_diffusion(pl_shader sh, const struct pl_error_diffusion_par
     sh->out_w = width;
     sh->out_h = height;
     plb_shader_describe(sh, "error diffusion");
+    plb_shader_use_tex(sh, params->input_tex);
+    plb_shader_use_tex(sh, params->output_tex);
     struct plb_errdiff_launch *e = &sh->errdiff;
     memset(e, 0, sizeof(*e));
     e->src = plb_tex_priv(params->input_tex)->d;

@@ -255,6 +255,7 @@ pl_gpu pl_cuda_create(pl_log log, const struct pl_cuda_params *params)
     p->pub.log = log;
     p->device = params->device;
     p->no_timers = params->no_timers;
+    p->async_xfer = !params->no_async_transfers;
     p->coord_mode = params->literal_coords ? PLB_COORD_LITERAL : PLB_COORD_EXACT;
     pl_gpu gpu = &p->pub;
     if (!CK(gpu, cudaSetDevice(p->device)))
@@ -267,6 +268,20 @@ pl_gpu pl_cuda_create(pl_log log, const struct pl_cuda_params *params)
             goto error;
         p->stream = s;
         p->own_stream = true;
+    }
+    if (p->async_xfer) {
+        cudaStream_t a, b;
+        if (!CK(gpu, cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking)) ||
+            !CK(gpu, cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking)))
+            goto error;
+        p->h2d_stream = a;
+        p->d2h_stream = b;
+        for (int i = 0; i < 64; i++) {
+            cudaEvent_t e;
+            if (!CK(gpu, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)))
+                goto error;
+            p->use_ring[i] = e;
+        }
     }
 
     {
@@ -318,6 +333,18 @@ void pl_cuda_destroy(pl_gpu *pgpu)
     cudaSetDevice(p->device);
     if (p->stream)
         cudaStreamSynchronize((cudaStream_t) p->stream);
+    if (p->h2d_stream) {
+        cudaStreamSynchronize((cudaStream_t) p->h2d_stream);
+        cudaStreamDestroy((cudaStream_t) p->h2d_stream);
+    }
+    if (p->d2h_stream) {
+        cudaStreamSynchronize((cudaStream_t) p->d2h_stream);
+        cudaStreamDestroy((cudaStream_t) p->d2h_stream);
+    }
+    for (int i = 0; i < 64; i++) {
+        if (p->use_ring[i])
+            cudaEventDestroy((cudaEvent_t) p->use_ring[i]);
+    }
     if (p->staging)
         cudaFreeHost(p->staging);
     if (p->own_stream && p->stream)
@@ -351,7 +378,91 @@ void pl_gpu_flush(pl_gpu gpu) { (void) gpu; }
 
 void pl_gpu_finish(pl_gpu gpu)
 {
+    struct plb_gpu *p = plb_gpu_priv(gpu);
     CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+    if (p->async_xfer) {
+        CK(gpu, cudaStreamSynchronize((cudaStream_t) p->h2d_stream));
+        CK(gpu, cudaStreamSynchronize((cudaStream_t) p->d2h_stream));
+    }
+}
+
+// ---- cross-stream ordering of textures ---------------------------------------------------
+// Every main-stream operation that touches textures is numbered; an event is recorded after it
+// in a ring of 64. A transfer on a copy stream first waits for the event of the texture's last
+// use (or, if that slot was recycled, for the newest event: later, hence still correct).
+void plb_gpu_before_use(pl_gpu gpu, pl_tex const *texs, int n)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (!p->async_xfer)
+        return;
+    for (int i = 0; i < n; i++) {
+        struct plb_tex *t = (struct plb_tex *) texs[i];
+        if (t && t->xfer_pending) {
+            CK(gpu, cudaStreamWaitEvent(STREAM(gpu), (cudaEvent_t) t->ev_xfer, 0));
+            t->xfer_pending = false;
+        }
+    }
+}
+
+void plb_gpu_after_use(pl_gpu gpu, pl_tex const *texs, int n)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (!p->async_xfer)
+        return;
+    p->seq++;
+    CK(gpu, cudaEventRecord((cudaEvent_t) p->use_ring[p->seq % 64], STREAM(gpu)));
+    for (int i = 0; i < n; i++) {
+        struct plb_tex *t = (struct plb_tex *) texs[i];
+        if (t)
+            t->last_use = p->seq;
+    }
+}
+
+// stream for a host<->device transfer of `t`, ordered after everything that used it so far
+static cudaStream_t xfer_begin(pl_gpu gpu, struct plb_tex *t, bool upload)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (!p->async_xfer)
+        return STREAM(gpu);
+    cudaStream_t s = (cudaStream_t) (upload ? p->h2d_stream : p->d2h_stream);
+    if (t->last_use) {
+        const uint64_t slot = p->seq - t->last_use < 64 ? t->last_use : p->seq;
+        CK(gpu, cudaStreamWaitEvent(s, (cudaEvent_t) p->use_ring[slot % 64], 0));
+    }
+    if (t->xfer_pending) // an earlier transfer on the other copy stream
+        CK(gpu, cudaStreamWaitEvent(s, (cudaEvent_t) t->ev_xfer, 0));
+    return s;
+}
+
+static bool xfer_end(pl_gpu gpu, struct plb_tex *t, cudaStream_t s)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (!p->async_xfer)
+        return true;
+    if (!t->ev_xfer) {
+        cudaEvent_t e;
+        if (!CK(gpu, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)))
+            return false;
+        t->ev_xfer = e;
+    }
+    t->xfer_pending = true;
+    return CK(gpu, cudaEventRecord((cudaEvent_t) t->ev_xfer, s));
+}
+
+void pl_cuda_join(pl_gpu gpu)
+{
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (!p->async_xfer)
+        return;
+    cudaEvent_t tmp[2];
+    cudaStream_t s[2] = { (cudaStream_t) p->h2d_stream, (cudaStream_t) p->d2h_stream };
+    for (int i = 0; i < 2; i++) {
+        if (!CK(gpu, cudaEventCreateWithFlags(&tmp[i], cudaEventDisableTiming)))
+            return;
+        CK(gpu, cudaEventRecord(tmp[i], s[i]));
+        CK(gpu, cudaStreamWaitEvent(STREAM(gpu), tmp[i], 0));
+        CK(gpu, cudaEventDestroy(tmp[i])); // released once the event has completed
+    }
 }
 
 bool pl_gpu_is_failed(pl_gpu gpu) { return plb_gpu_priv(gpu)->failed; }
@@ -458,8 +569,12 @@ void pl_tex_destroy(pl_gpu gpu, pl_tex *ptex)
     if (!ptex || !*ptex)
         return;
     struct plb_tex *t = (struct plb_tex *) *ptex;
+    if (t->xfer_pending)
+        CK(gpu, cudaStreamWaitEvent(STREAM(gpu), (cudaEvent_t) t->ev_xfer, 0));
     if (t->owned && t->d.ptr)
         CK(gpu, cudaFreeAsync(t->d.ptr, STREAM(gpu)));
+    if (t->ev_xfer)
+        cudaEventDestroy((cudaEvent_t) t->ev_xfer);
     free(t);
     *ptex = NULL;
 }
@@ -488,7 +603,9 @@ extern bool plb_launch_clear(pl_gpu gpu, const struct plb_tex_desc *dst, const f
 
 void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4])
 {
+    plb_gpu_before_use(gpu, &dst, 1);
     plb_launch_clear(gpu, &plb_tex_priv(dst)->d, color);
+    plb_gpu_after_use(gpu, &dst, 1);
 }
 
 static void CUDART_CB host_cb_trampoline(void *data)
@@ -536,26 +653,32 @@ bool pl_tex_upload(pl_gpu gpu, const struct pl_tex_transfer_params *params)
     size_t row_pitch;
     if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_upload"))
         return false;
-    const struct plb_tex *t = plb_tex_priv(params->tex);
+    struct plb_tex *t = (struct plb_tex *) params->tex;
     const size_t ts = params->tex->params.format->texel_size;
     char *dst = (char *) t->d.ptr + (size_t) rc.y0 * t->d.pitch + rc.x0 * ts;
     const size_t wbytes = (size_t) (rc.x1 - rc.x0) * ts;
     bool ok;
+    cudaStream_t s = STREAM(gpu);
     if (params->buf) {
         const struct plb_buf *b = (const struct plb_buf *) params->buf;
         const char *src = (const char *) (b->dptr ? b->dptr : b->hptr) + params->buf_offset;
+        pl_tex one = params->tex;
+        plb_gpu_before_use(gpu, &one, 1);
         ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, src, row_pitch, wbytes, rc.y1 - rc.y0,
                                        b->dptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                       STREAM(gpu)));
+                                       s));
+        plb_gpu_after_use(gpu, &one, 1);
     } else {
+        s = xfer_begin(gpu, t, true);
         ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, params->ptr, row_pitch, wbytes,
-                                       rc.y1 - rc.y0, cudaMemcpyHostToDevice, STREAM(gpu)));
+                                       rc.y1 - rc.y0, cudaMemcpyHostToDevice, s));
+        ok = ok && xfer_end(gpu, t, s);
     }
     if (ok && params->callback) {
         void **pair = (void **) malloc(2 * sizeof(void *));
         pair[0] = (void *) params->callback;
         pair[1] = params->priv;
-        ok = CK(gpu, cudaLaunchHostFunc(STREAM(gpu), host_cb_trampoline, pair));
+        ok = CK(gpu, cudaLaunchHostFunc(s, host_cb_trampoline, pair));
     }
     return ok;
 }
@@ -566,20 +689,26 @@ bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
     size_t row_pitch;
     if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_download"))
         return false;
-    const struct plb_tex *t = plb_tex_priv(params->tex);
+    struct plb_tex *t = (struct plb_tex *) params->tex;
     const size_t ts = params->tex->params.format->texel_size;
     const char *src = (const char *) t->d.ptr + (size_t) rc.y0 * t->d.pitch + rc.x0 * ts;
     const size_t wbytes = (size_t) (rc.x1 - rc.x0) * ts;
     bool ok;
+    cudaStream_t s = STREAM(gpu);
     if (params->buf) {
         const struct plb_buf *b = (const struct plb_buf *) params->buf;
         char *dst = (char *) (b->dptr ? b->dptr : b->hptr) + params->buf_offset;
+        pl_tex one = params->tex;
+        plb_gpu_before_use(gpu, &one, 1);
         ok = CK(gpu, cudaMemcpy2DAsync(dst, row_pitch, src, t->d.pitch, wbytes, rc.y1 - rc.y0,
                                        b->dptr ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                                       STREAM(gpu)));
+                                       s));
+        plb_gpu_after_use(gpu, &one, 1);
     } else {
+        s = xfer_begin(gpu, t, false);
         ok = CK(gpu, cudaMemcpy2DAsync(params->ptr, row_pitch, src, t->d.pitch, wbytes,
-                                       rc.y1 - rc.y0, cudaMemcpyDeviceToHost, STREAM(gpu)));
+                                       rc.y1 - rc.y0, cudaMemcpyDeviceToHost, s));
+        ok = ok && xfer_end(gpu, t, s);
     }
     if (!ok)
         return false;
@@ -587,11 +716,11 @@ bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
         void **pair = (void **) malloc(2 * sizeof(void *));
         pair[0] = (void *) params->callback;
         pair[1] = params->priv;
-        return CK(gpu, cudaLaunchHostFunc(STREAM(gpu), host_cb_trampoline, pair));
+        return CK(gpu, cudaLaunchHostFunc(s, host_cb_trampoline, pair));
     }
     // blocking semantics when no callback/buffer polling is requested (gpu.h:905-910)
     if (!params->buf)
-        return CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
+        return CK(gpu, cudaStreamSynchronize(s));
     return true;
 }
 

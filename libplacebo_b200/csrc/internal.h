@@ -56,6 +56,11 @@ struct plb_tex {
     struct plb_tex_desc d;
     bool owned;        // false for pl_cuda_wrap
     size_t alloc_size;
+    // cross-stream ordering (async copy engines): sequence number of the last main-stream
+    // operation that touched the texture, and the completion event of the last transfer
+    uint64_t last_use;
+    void *ev_xfer;     // cudaEvent_t, created on first transfer
+    bool xfer_pending; // main stream has not yet waited for ev_xfer
 };
 static inline const struct plb_tex *plb_tex_priv(pl_tex tex) { return (const struct plb_tex *) tex; }
 
@@ -84,7 +89,17 @@ struct plb_gpu {
     pl_fmt *fmt_list;
     void *staging;         // pinned staging buffer for pl_tex_upload/download
     size_t staging_size;
+    // Asynchronous transfers: uploads and downloads run on their own streams (the two copy
+    // engines) and are ordered against the kernels by events, so that frame N+1 uploads and
+    // frame N-1 downloads while frame N renders.
+    bool async_xfer;
+    void *h2d_stream, *d2h_stream;
+    uint64_t seq;          // main-stream operations that touched textures
+    void *use_ring[64];    // cudaEvent_t recorded after operation seq (slot seq % 64)
 };
+// Main-stream bookkeeping around every operation that reads or writes textures
+void plb_gpu_before_use(pl_gpu gpu, pl_tex const *texs, int n);
+void plb_gpu_after_use(pl_gpu gpu, pl_tex const *texs, int n);
 static inline struct plb_gpu *plb_gpu_priv(pl_gpu gpu) { return (struct plb_gpu *) gpu; }
 bool plb_cuda_check(pl_gpu gpu, int err, const char *what);
 void *plb_gpu_staging(pl_gpu gpu, size_t size);

@@ -250,11 +250,18 @@ API int plg_render(struct plg_stream *s, int slot, int out_slot, int frame_index
     return (int) pl_renderer_get_errors(s->rr).errors;
 }
 
+static void noop_cb(void *priv) { (void) priv; }
+
+// Asynchronous download (a callback makes pl_tex_download non-blocking, gpu.h:879-910): `host`
+// must stay valid until plg_finish / plg_join + stream synchronisation.
 API int plg_download(struct plg_stream *s, int out_slot, void *host)
 {
     return pl_tex_download(s->gpu, pl_tex_transfer_params( .tex = s->target[out_slot],
-                                                           .ptr = host )) ? 0 : -1;
+                                                           .ptr = host,
+                                                           .callback = noop_cb )) ? 0 : -1;
 }
+
+API void plg_join(struct plg_stream *s) { pl_cuda_join(s->gpu); }
 
 // ---- frame-parallel peak statistics (include/libplacebo_b200.h, "frame-parallel extensions")
 API int plg_measure_peak(struct plg_stream *s, int slot, void *out_buf /* PL_PEAK_BUF_SIZE */)

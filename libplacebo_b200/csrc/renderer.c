@@ -607,6 +607,8 @@ static bool merge_plane_shader(pl_shader sh, pl_shader sub, const int map[4], in
     }
     for (int i = 0; i < sub->num_steps; i++)
         plb_shader_describe(sh, sub->steps[i]);
+    for (int i = 0; i < sub->num_texs; i++)
+        plb_shader_use_tex(sh, sub->texs[i]);
     return true;
 }
 

@@ -100,7 +100,11 @@ struct pl_shader_t {
     // friendly names of the recorded operations (sh_describe, src/shaders.h:155-165)
     const char *steps[24];
     int num_steps;
+    // textures read by the recorded pass (ordering against the copy-engine streams)
+    pl_tex texs[12];
+    int num_texs;
 };
+void plb_shader_use_tex(pl_shader sh, pl_tex tex);
 
 // `desc` must have static storage duration
 void plb_shader_describe(pl_shader sh, const char *desc);

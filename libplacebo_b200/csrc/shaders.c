@@ -185,6 +185,16 @@ struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind)
     return op;
 }
 
+void plb_shader_use_tex(pl_shader sh, pl_tex tex)
+{
+    for (int i = 0; i < sh->num_texs; i++) {
+        if (sh->texs[i] == tex)
+            return;
+    }
+    if (sh->num_texs < (int) PLB_ARRAY_SIZE(sh->texs))
+        sh->texs[sh->num_texs++] = tex;
+}
+
 void plb_shader_describe(pl_shader sh, const char *desc)
 {
     if (sh->num_steps < (int) PLB_ARRAY_SIZE(sh->steps))
@@ -304,6 +314,7 @@ static bool setup_src(pl_shader sh, const struct pl_sample_src *src, struct src_
         src->rect.x0, src->rect.y0, src->rect.x0 + o->src_w, src->rect.y0 + o->src_h,
     };
     o->tex = plb_tex_priv(tex)->d;
+    plb_shader_use_tex(sh, tex);
     if (!require_input_none(sh, resizable ? 0 : o->out_w, resizable ? 0 : o->out_h, who))
         return false;
     if (!tex->params.sampleable) {

@@ -16,7 +16,7 @@ PEAK_BUF_SIZE = 3264  # PL_PEAK_BUF_SIZE
 
 # enum values of include/libplacebo_b200.h (identical to libplacebo's colorspace.h)
 SYS = dict(UNKNOWN=0, BT_601=1, BT_709=2, SMPTE_240M=3, BT_2020_NC=4, BT_2020_C=5, BT_2100_PQ=6,
-           BT_2100_HLG=7, DOLBYVISION=8, YCGCO=9, RGB=10, XYZ=11)
+           BT_2100_HLG=7, DOLBYVISION=8, YCGCO=9, YCGCO_RE=10, YCGCO_RO=11, RGB=12, XYZ=13)
 LEVELS = dict(UNKNOWN=0, LIMITED=1, FULL=2)
 PRIM = dict(UNKNOWN=0, BT_601_525=1, BT_601_625=2, BT_709=3, BT_470M=4, EBU_3213=5, BT_2020=6)
 TRC = dict(UNKNOWN=0, BT_1886=1, SRGB=2, LINEAR=3, PQ=12, HLG=13)
@@ -86,7 +86,7 @@ class Stream:
         L.plg_create.restype = C.c_void_p
         L.plg_cuda_stream.restype = C.c_void_p
         L.plg_launch_count.restype = C.c_uint64
-        for f in ("plg_destroy", "plg_finish", "plg_reset"):
+        for f in ("plg_destroy", "plg_finish", "plg_reset", "plg_join"):
             getattr(L, f).restype = None
         self.h = L.plg_create(device, int(literal_coords))
         if not self.h:
@@ -144,6 +144,10 @@ class Stream:
 
     def finish(self):
         self.lib.plg_finish(self.h)
+
+    def join(self):
+        """Main stream waits for all transfers enqueued so far (see pl_cuda_join)."""
+        self.lib.plg_join(self.h)
 
     def reset(self):
         self.lib.plg_reset(self.h)

@@ -43,3 +43,34 @@ def test_no_gpu_fails_loudly():
     shim = T.shim()
     shim.shim_create.restype = ctypes.c_void_p
     assert not shim.shim_create(0)
+
+
+def _header_enum(name, prefix):
+    import re
+    src = open(os.path.join(T.ROOT, "include", "libplacebo_b200.h")).read()
+    body = re.search(r"enum %s\s*\{(.*?)\};" % name, src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out, val = {}, -1
+    for item in body.split(","):
+        item = item.strip()
+        if not item:
+            continue
+        if "=" in item:
+            k, v = (x.strip() for x in item.split("="))
+            val = int(v, 0)
+        else:
+            k, val = item, val + 1
+        out[k.replace(prefix, "")] = val
+    return out
+
+
+def test_python_enums_match_header():
+    """The Python front-ends carry copies of the C enums; they must not drift."""
+    from libplacebo_b200 import stream as S
+    sys_h = _header_enum("pl_color_system", "PL_COLOR_SYSTEM_")
+    prim_h = _header_enum("pl_color_primaries", "PL_COLOR_PRIM_")
+    trc_h = _header_enum("pl_color_transfer", "PL_COLOR_TRC_")
+    for table, hdr in ((S.SYS, sys_h), (S.PRIM, prim_h), (S.TRC, trc_h),
+                       (T.SYS, sys_h), (T.PRIM, prim_h), (T.TRC, trc_h)):
+        for k, v in table.items():
+            assert hdr[k] == v, (k, v, hdr[k])
