@@ -193,7 +193,9 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
             (4 * oy - up2_frac4(YM, py)) * (4 * oy - up2_frac4(YM, py))) < R2_16;
 }
 
-template <int NC, int R2_16, int XM, int YM>
+// PURE: a resampling pass with nothing to merge and no colour program (config C2's main
+// scaler): the tail collapses to a component swizzle and four-texel vector stores.
+template <int NC, int R2_16, int XM, int YM, bool PURE = false>
 __global__ void __launch_bounds__(UP2_TX * UP2_TY)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
 {
@@ -263,6 +265,44 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     }
 
     const plb_tail_args &t = plb_s_tail;
+    if (PURE) {
+        #pragma unroll
+        for (int oyo = 0; oyo < UP2_OY; oyo++) {
+            const int gy = Y0 + ty * UP2_OY + oyo;
+            const int gx = X0 + tx * UP2_OX;
+            if (gy >= t.out_h || gx >= t.out_w)
+                continue;
+            float4 px4[UP2_OX];
+            #pragma unroll
+            for (int oxo = 0; oxo < UP2_OX; oxo++) {
+                const float norm = a.norm[oyo][oxo & 1];
+                float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+                #pragma unroll
+                for (int k = 0; k < NC; k++)
+                    prim[k] = norm * acc[oyo][oxo][k];
+                float color[4] = { t.init[0], t.init[1], t.init[2], t.init[3] };
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    // src_map is launch-uniform; the selects below stay in registers
+                    const int m = t.src_map[k];
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        color[j] = m == j ? prim[k] : color[j];
+                }
+                px4[oxo] = make_float4(color[0], color[1], color[2], color[3]);
+            }
+            if (gx + UP2_OX <= t.out_w) {
+                plb_store4(t.dst, t.dst_x0 + gx, t.dst_y0 + gy, px4);
+            } else {
+                #pragma unroll
+                for (int oxo = 0; oxo < UP2_OX; oxo++) {
+                    if (gx + oxo < t.out_w)
+                        plb_store(t.dst, t.dst_x0 + gx + oxo, t.dst_y0 + gy, px4[oxo]);
+                }
+            }
+        }
+        return;
+    }
     bool has_peak = false;
     for (int i = 0; i < plb_s_prog.n; i++)
         has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
@@ -355,9 +395,19 @@ static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
     // the tile is a whole number of peak work groups, so this also covers overhanging ones
     dim3 grid((args.tail.out_w + UP2_TX * UP2_OX - 1) / (UP2_TX * UP2_OX),
               (args.tail.out_h + UP2_TY * UP2_OY - 1) / (UP2_TY * UP2_OY));
-    switch (r2_class) {
-    case 160: k_polar_up2<NC, 160, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
-    default:  k_polar_up2<NC, 1000, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+    // pure resampling pass (nothing merged, empty colour program): centred phases only
+    const bool pure = XM == 0 && YM == 0 && args.tail.nplanes == 0 && args.tail.prog.n == 0 &&
+                      args.tail.dst.ptr;
+    if (pure) {
+        switch (r2_class) {
+        case 160: k_polar_up2<NC, 160, 0, 0, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        default:  k_polar_up2<NC, 1000, 0, 0, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        }
+    } else {
+        switch (r2_class) {
+        case 160: k_polar_up2<NC, 160, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        default:  k_polar_up2<NC, 1000, XM, YM><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        }
     }
     return plb_cuda_check(gpu, cudaGetLastError(), "k_polar_up2");
 }

@@ -191,6 +191,52 @@ PLB_DEV void plb_store(const plb_tex_desc &t, int x, int y, float4 c)
     }
 }
 
+// Store four horizontally consecutive RGBA texels (x % 4 == 0 and a 256-byte aligned pitch make
+// the 16-byte vector stores legal); falls back to scalar stores otherwise. Same conversions as
+// plb_store.
+PLB_DEV void plb_store4(const plb_tex_desc &t, int x, int y, const float4 c[4])
+{
+    char *row = (char *) t.ptr + (size_t) y * t.pitch;
+    if (t.comps == 4 && !(x & 3) && t.kind == PLB_FK_HALF) {
+        uint4 lo, hi;
+        __half2 h;
+        h = __floats2half2_rn(c[0].x, c[0].y); lo.x = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[0].z, c[0].w); lo.y = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[1].x, c[1].y); lo.z = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[1].z, c[1].w); lo.w = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[2].x, c[2].y); hi.x = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[2].z, c[2].w); hi.y = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[3].x, c[3].y); hi.z = *(uint32_t *) &h;
+        h = __floats2half2_rn(c[3].z, c[3].w); hi.w = *(uint32_t *) &h;
+        uint4 *p = (uint4 *) (row + (size_t) x * 8);
+        p[0] = lo;
+        p[1] = hi;
+    } else if (t.comps == 4 && !(x & 3) && t.kind == PLB_FK_UNORM8) {
+        uint4 v;
+        uint32_t *o = &v.x;
+        #pragma unroll
+        for (int i = 0; i < 4; i++)
+            o[i] = plb_unorm(c[i].x, 255.0f) | (plb_unorm(c[i].y, 255.0f) << 8) |
+                   (plb_unorm(c[i].z, 255.0f) << 16) | (plb_unorm(c[i].w, 255.0f) << 24);
+        *(uint4 *) (row + (size_t) x * 4) = v;
+    } else if (t.comps == 4 && !(x & 3) && t.kind == PLB_FK_UNORM16) {
+        uint4 *p = (uint4 *) (row + (size_t) x * 8);
+        #pragma unroll
+        for (int i = 0; i < 2; i++) {
+            uint4 v;
+            v.x = plb_unorm(c[2*i].x, 65535.0f) | (plb_unorm(c[2*i].y, 65535.0f) << 16);
+            v.y = plb_unorm(c[2*i].z, 65535.0f) | (plb_unorm(c[2*i].w, 65535.0f) << 16);
+            v.z = plb_unorm(c[2*i+1].x, 65535.0f) | (plb_unorm(c[2*i+1].y, 65535.0f) << 16);
+            v.w = plb_unorm(c[2*i+1].z, 65535.0f) | (plb_unorm(c[2*i+1].w, 65535.0f) << 16);
+            p[i] = v;
+        }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 4; i++)
+            plb_store(t, x + i, y, c[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Pixel coordinates — same two modes as the oracle (oracle/pl_oracle.c coord_pos/coord_texel);
 // LITERAL restates src/dispatch.c:1038-1062 in fp32.
