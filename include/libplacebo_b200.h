@@ -871,6 +871,14 @@ struct pl_film_grain_params { /* film_grain.h:100-128 */
 };
 #define pl_film_grain_params(...) (&(struct pl_film_grain_params) { __VA_ARGS__ })
 PL_API bool pl_needs_film_grain(const struct pl_film_grain_params *params);
+// Diagnostics (host only, no GPU needed): the AV1 tables pl_shader_film_grain generates for
+// `data` / `repr` — grain_y[64*64], grain_cb and grain_cr [(64 >> sub_x) * (64 >> sub_y)],
+// offsets[(align(tex_w << sub_x, 128) / 32) * (align(tex_h << sub_y, 128) / 32)], scaling[3][256].
+// Any output pointer may be NULL.
+PL_API bool pl_cuda_av1_tables_host(const struct pl_film_grain_data *data,
+                                    const struct pl_color_repr *repr, int sub_x, int sub_y,
+                                    int tex_w, int tex_h, float *grain_y, float *grain_cb,
+                                    float *grain_cr, uint32_t *offsets, float *scaling);
 PL_API bool pl_shader_film_grain(pl_shader sh, pl_shader_obj *grain_state,
                                  const struct pl_film_grain_params *params);
 

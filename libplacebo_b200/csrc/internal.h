@@ -26,6 +26,7 @@ void plb_msg(pl_log log, enum pl_log_level lev, const char *fmt, ...)
 
 #define PLB_MIN(a, b) ((a) < (b) ? (a) : (b))
 #define PLB_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define PLB_CLAMP(x, lo, hi) ((x) < (lo) ? (lo) : (x) > (hi) ? (hi) : (x))
 #define PLB_DEF(x, d) ((x) ? (x) : (d))
 #define PLB_ARRAY_SIZE(a) (sizeof(a) / sizeof((a)[0]))
 
@@ -232,6 +233,26 @@ enum plb_plane_kind {
 struct plb_av1_dev;        // uploaded grain LUTs, see k_grain.cu
 struct plb_h274_dev;
 
+// AV1 film grain for one plane pass (film_grain_av1.c:605-1013): device LUTs + constants.
+// Component i of the plane's texture is colour channel `channel[i]` (PL_CHANNEL_Y/CB/CR or -1).
+struct plb_av1_plane {
+    int ncomp;
+    int channel[3];
+    const float *grain[3];     // planar 2-D grain LUT of component i (NULL: no grain)
+    int grain_w[3];            // its row length (64 or 32)
+    const float *scaling[3];   // 256-entry scaling LUT of component i (NULL: skip component)
+    const uint32_t *offsets;   // packed block offsets (TL, T, L, N), one word per 32x32 block
+    int off_w;
+    int sub_x, sub_y, overlap;
+    float tex_scale, grain_min, grain_max;
+    float min_value, max_luma, max_chroma;
+    int chroma_from_luma;
+    float mult[3][2];          // (uv_mult_luma, uv_mult) / 64 for component i
+    float offset[3];
+    int luma_from_comp;        // >= 0: averageLuma = colour component of this texture
+    int luma_comp;             // else component of the separate luma texture
+};
+
 struct plb_plane_src {
     int kind;
     struct plb_tex_desc tex;
@@ -245,8 +266,7 @@ struct plb_plane_src {
     float neutral[3];
     uint8_t comp_mask;
     // grain
-    const struct plb_av1_dev *av1;
-    const struct plb_h274_dev *h274;
+    struct plb_av1_plane av1;
     struct plb_tex_desc luma;  // AV1 chroma needs the luma plane
 };
 

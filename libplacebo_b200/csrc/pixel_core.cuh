@@ -123,9 +123,82 @@ PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx
     }
 }
 
-#ifdef PLB_HAVE_GRAIN
-PLB_DEV void plb_grain_av1(const plb_plane_src &pl, int gx, int gy, float color[4]);
-#endif
+// pl_shader_fg_av1 (film_grain_av1.c:827-1013): grain = LUT[block offset + local id], blended
+// over the 2-pixel block overlap, scaled by a luma-dependent LUT, added and clamped.
+PLB_DEV float plb_av1_fetch(const plb_av1_plane &g, int i, uint32_t data, int off, int lx, int ly,
+                            int bw, int bh)
+{
+    const int dx = (off & 8) ? 1 : 0, dy = (off & 16) ? 1 : 0; // OFFSET_L = 8, OFFSET_T = 16
+    const int ox = (g.sub_x ? 1 : 2) * (int) ((data >> (off + 4)) & 0xFu);
+    const int oy = (g.sub_y ? 1 : 2) * (int) ((data >> off) & 0xFu);
+    const int px = ox + lx + bw * dx, py = oy + ly + bh * dy;
+    return __ldg(g.grain[i] + py * g.grain_w[i] + px);
+}
+
+PLB_DEV void plb_grain_av1(const plb_plane_src &pl, int gx, int gy, float color[4])
+{
+    const plb_av1_plane &g = pl.av1;
+    const int bw = 32 >> g.sub_x, bh = 32 >> g.sub_y;
+    const int bx = gx / bw, by = gy / bh;
+    const int lx = gx - bw * bx, ly = gy - bh * by;
+    const uint32_t data = __ldg(g.offsets + by * g.off_w + bx);
+    const float4 t = plb_load_clamped(pl.tex, gx, gy);
+    color[0] = g.tex_scale * t.x;
+    color[1] = g.tex_scale * t.y;
+    color[2] = g.tex_scale * t.z;
+    color[3] = g.tex_scale * t.w;
+    float avg_luma = 0.0f;
+    if (g.luma_from_comp >= 0) {
+        avg_luma = color[g.luma_from_comp];
+    } else if (g.luma_from_comp == -1) {
+        const float4 l = plb_load_clamped(pl.luma, gx << g.sub_x, gy << g.sub_y);
+        const float lv[4] = { l.x, l.y, l.z, l.w };
+        avg_luma = lv[g.luma_comp] * g.tex_scale;
+    }
+    const float wx0 = g.sub_x ? 23.0f / 32.0f : 27.0f / 32.0f, wx1 = g.sub_x ? 22.0f / 32.0f : 17.0f / 32.0f;
+    const float wy0 = g.sub_y ? 23.0f / 32.0f : 27.0f / 32.0f, wy1 = g.sub_y ? 22.0f / 32.0f : 17.0f / 32.0f;
+    for (int i = 0; i < g.ncomp; i++) {
+        if (!g.scaling[i])
+            continue;
+        float grain = plb_av1_fetch(g, i, data, 0, lx, ly, bw, bh);
+        if (g.overlap) {
+            const bool ovx = bx > 0 && lx < (2 >> g.sub_x);
+            if (ovx) {
+                const float a = lx == 1 ? wx1 : wx0, b = lx == 1 ? wx0 : wx1;
+                const float val = plb_av1_fetch(g, i, data, 8, lx, ly, bw, bh);
+                grain = __fmaf_rn(grain, b, val * a); // dot(vec2(val, grain), w)
+            }
+            if (by > 0 && ly < (2 >> g.sub_y)) {
+                const float a = ly == 1 ? wy1 : wy0, b = ly == 1 ? wy0 : wy1;
+                float val;
+                if (ovx) {
+                    const float a2 = lx == 1 ? wx1 : wx0, b2 = lx == 1 ? wx0 : wx1;
+                    const float tmp = plb_av1_fetch(g, i, data, 24, lx, ly, bw, bh);
+                    val = plb_av1_fetch(g, i, data, 16, lx, ly, bw, bh);
+                    val = __fmaf_rn(val, b2, tmp * a2);
+                } else {
+                    val = plb_av1_fetch(g, i, data, 16, lx, ly, bw, bh);
+                }
+                grain = __fmaf_rn(grain, b, val * a);
+            }
+            grain = plb_clamp(grain, g.grain_min, g.grain_max);
+        }
+        if (g.channel[i] == 0) { // PL_CHANNEL_Y
+            const float s = plb_lut1d(g.scaling[i], 256, color[i]);
+            color[i] = __fmaf_rn(s, grain, color[i]);
+            color[i] = plb_clamp(color[i], g.min_value, g.max_luma);
+        } else {
+            float val = avg_luma;
+            if (!g.chroma_from_luma) {
+                val = __fmaf_rn(color[i], g.mult[i][1], val * g.mult[i][0]);
+                val += g.offset[i];
+            }
+            const float s = plb_lut1d(g.scaling[i], 256, val);
+            color[i] = __fmaf_rn(s, grain, color[i]);
+            color[i] = plb_clamp(color[i], g.min_value, g.max_chroma);
+        }
+    }
+}
 
 // Sample plane `pl` at output pixel (gx, gy) -> vec4 (already multiplied by its scale)
 PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
@@ -141,12 +214,13 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
     out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
     if (pl.kind == PLB_PLANE_DEBAND)
         plb_deband(pl, cc, posx, posy, gx, gy, frame_index, out);
-#ifdef PLB_HAVE_GRAIN
     if (pl.kind == PLB_PLANE_GRAIN_AV1) {
         plb_grain_av1(pl, gx, gy, out);
-        return; // grain applies its own scale
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            out[k] *= pl.scale; // the renderer's "tmp = vec4(scale) * sub()"
+        return;
     }
-#endif
     #pragma unroll
     for (int k = 0; k < 4; k++)
         out[k] *= pl.scale;

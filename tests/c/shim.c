@@ -46,7 +46,7 @@ static void shim_init(void)
 
 /* shader state objects persist across calls so that LUT caching paths are exercised */
 struct shim_objs {
-    pl_shader_obj sampler, cmap, dither;
+    pl_shader_obj sampler, cmap, dither, grain[2];
 };
 
 struct shim_ctx {
@@ -150,6 +150,8 @@ API void shim_reset_objs(struct shim_ctx *c)
     pl_shader_obj_destroy(&c->objs.sampler);
     pl_shader_obj_destroy(&c->objs.cmap);
     pl_shader_obj_destroy(&c->objs.dither);
+    pl_shader_obj_destroy(&c->objs.grain[0]);
+    pl_shader_obj_destroy(&c->objs.grain[1]);
 }
 
 /* Dolby Vision metadata of the reference's own test fixture (src/tests/utils.h:279-323).
@@ -513,6 +515,52 @@ API int shim_error_diffusion(struct shim_ctx *c, void *src_tex, void *dst_tex, i
         .shader = &sh,
         .dispatch_size = {1, 1, 1},
     )) ? 0 : -2;
+}
+
+/* host tables of the AV1 grain for the reference's fixture (no GPU) */
+static struct pl_av1_grain_data shim_av1_fixture(void);
+API int shim_av1_tables(unsigned seed, int color_depth, int levels, int sys, int sub_x, int sub_y,
+                        int tex_w, int tex_h, float *gy, float *gcb, float *gcr, uint32_t *offsets,
+                        float *scaling)
+{
+    struct pl_film_grain_data data = {
+        .type = PL_FILM_GRAIN_AV1,
+        .seed = seed,
+        .params.av1 = shim_av1_fixture(),
+    };
+    struct pl_color_repr repr = { .sys = sys, .levels = levels, .bits = { 16, color_depth, 0 } };
+    return pl_cuda_av1_tables_host(&data, &repr, sub_x, sub_y, tex_w, tex_h, gy, gcb, gcr, offsets,
+                                   scaling) ? 0 : -1;
+}
+
+API const void *shim_av1_fixture_ptr(void)
+{
+    static struct pl_av1_grain_data d;
+    d = shim_av1_fixture();
+    return &d;
+}
+
+/* pl_shader_film_grain (AV1, reference fixture) on one plane -> dst (src/tests/gpu_tests.c:787-835) */
+API int shim_film_grain(struct shim_ctx *c, void *tex, void *luma_tex, void *dst, int chroma,
+                        unsigned seed, int overlap, int color_depth, int levels, int sys)
+{
+    struct pl_color_repr repr = { .sys = sys, .levels = levels, .bits = { 16, color_depth, 0 } };
+    struct pl_film_grain_params par = {
+        .data = { .type = PL_FILM_GRAIN_AV1, .seed = seed, .params.av1 = shim_av1_fixture() },
+        .tex = tex,
+        .luma_tex = luma_tex,
+        .repr = &repr,
+        .components = chroma ? 2 : 1,
+        .component_mapping = { chroma ? PL_CHANNEL_CB : PL_CHANNEL_Y, PL_CHANNEL_CR },
+        .luma_comp = 0,
+    };
+    par.data.params.av1.overlap = overlap;
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    if (!pl_shader_film_grain(sh, &c->objs.grain[chroma ? 1 : 0], &par)) {
+        pl_dispatch_abort(c->dp, &sh);
+        return -1;
+    }
+    return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst )) ? 0 : -2;
 }
 
 API int shim_math_eval(struct shim_ctx *c, int fn, const float *a, const float *b, float *out,

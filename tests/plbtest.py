@@ -308,6 +308,33 @@ def dovi_fixture(variant=0):
     return DoviMeta.from_address(sh.shim_dovi_fixture_ptr(variant))
 
 
+class Av1GrainData(C.Structure):  # struct pl_av1_grain_data of the public header
+    _fields_ = [("num_points_y", C.c_int), ("points_y", (C.c_uint8 * 2) * 14),
+                ("chroma_scaling_from_luma", C.c_bool), ("num_points_uv", C.c_int * 2),
+                ("points_uv", ((C.c_uint8 * 2) * 10) * 2), ("scaling_shift", C.c_int),
+                ("ar_coeff_lag", C.c_int), ("ar_coeffs_y", C.c_int8 * 24),
+                ("ar_coeffs_uv", (C.c_int8 * 25) * 2), ("ar_coeff_shift", C.c_int),
+                ("grain_scale_shift", C.c_int), ("uv_mult", C.c_int8 * 2),
+                ("uv_mult_luma", C.c_int8 * 2), ("uv_offset", C.c_int16 * 2), ("overlap", C.c_bool)]
+
+
+class OrcAv1Grain(C.Structure):
+    _fields_ = [("grain", FP * 3), ("grain_w", C.c_int), ("grain_h", C.c_int),
+                ("offsets", C.POINTER(C.c_uint32)), ("offsets_w", C.c_int), ("offsets_h", C.c_int),
+                ("scaling", FP * 3), ("is_luma", C.c_int * 3), ("num_comps", C.c_int),
+                ("sub_x", C.c_int), ("sub_y", C.c_int), ("overlap", C.c_int),
+                ("chroma_scaling_from_luma", C.c_int), ("bit_depth", C.c_int), ("scale", C.c_float),
+                ("minValue", C.c_float), ("maxLuma", C.c_float), ("maxChroma", C.c_float),
+                ("scaling_shift", C.c_int), ("uv_mult", C.c_float * 3),
+                ("uv_mult_luma", C.c_float * 3), ("uv_offset", C.c_float * 3), ("luma_comp", C.c_int)]
+
+
+def av1_fixture():
+    sh = shim()
+    sh.shim_av1_fixture_ptr.restype = C.c_void_p
+    return Av1GrainData.from_address(sh.shim_av1_fixture_ptr())
+
+
 class OrcPeakBuf(C.Structure):
     _fields_ = [("frame_wg_count", C.c_uint32 * 12), ("frame_wg_active", C.c_uint32 * 12),
                 ("frame_sum_pq", C.c_uint32 * 12), ("frame_max_pq", C.c_uint32 * 12),
@@ -477,6 +504,14 @@ class Oracle:
         rgba = np.ascontiguousarray(rgba, f32).copy()
         self.lib.orc_encode_special(fp(rgba), C.c_size_t(rgba.size // 4), sys)
         return rgba
+
+    def av1_grain(self, plane, luma, params):
+        """plane: HxWxC float32 texel values (unorm/65535), luma likewise or None."""
+        t, keep = _tex(plane)
+        tl, keep2 = _tex(luma) if luma is not None else (None, None)
+        out = np.zeros((keep.shape[0], keep.shape[1], 4), f32)
+        self.lib.orc_av1_grain(C.byref(t), C.byref(tl) if tl is not None else None, C.byref(params), fp(out))
+        return out
 
     def dovi_reshape(self, rgba, meta):
         rgba = np.ascontiguousarray(rgba, f32).copy()
