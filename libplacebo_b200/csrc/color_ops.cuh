@@ -574,6 +574,59 @@ PLB_DEV void plb_dovi_reshape(float c[4])
     }
 }
 
+// "Light" programs contain only scale / matrix / alpha / swizzle / FBO-rounding steps (no
+// transcendental): cheap enough to run inline, register-resident, in the resampling kernels
+// (e.g. the output pass of an SDR upscale: 1/scale, swizzle). plb_prog_is_light() on the host
+// decides; the semantics are those of the corresponding cases of plb_run_color_ops.
+PLB_DEV void plb_run_light_ops(float c[4])
+{
+    const plb_color_prog &prog = plb_s_prog;
+    #pragma unroll 1
+    for (int i = 0; i < prog.n; i++) {
+        const plb_color_op &op = prog.ops[i];
+        const int kind = op.kind;
+        if (kind == PLB_OP_SCALE) {
+            const float s = op.u.scale.s;
+            c[0] *= s; c[1] *= s; c[2] *= s;
+            if (op.u.scale.with_alpha)
+                c[3] *= s;
+        } else if (kind == PLB_OP_MATRIX) {
+            plb_matv(op.u.matrix.m, c[0], c[1], c[2]);
+            if (op.u.matrix.has_c) {
+                c[0] += op.u.matrix.c[0]; c[1] += op.u.matrix.c[1]; c[2] += op.u.matrix.c[2];
+            }
+        } else if (kind == PLB_OP_ROUND_FBO) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++)
+                c[k] = plb_round_fbo(c[k], op.u.round_fbo.kind, op.u.round_fbo.bits);
+        } else if (kind == PLB_OP_ALPHA) {
+            if (op.u.alpha.to == PL_ALPHA_NONE && op.u.alpha.from == PL_ALPHA_UNKNOWN) {
+                c[3] = 1.0f;
+            } else if (op.u.alpha.from == PL_ALPHA_INDEPENDENT && op.u.alpha.to == PL_ALPHA_PREMULTIPLIED) {
+                c[0] *= c[3]; c[1] *= c[3]; c[2] *= c[3];
+            } else if (op.u.alpha.from == PL_ALPHA_PREMULTIPLIED && op.u.alpha.to != PL_ALPHA_PREMULTIPLIED) {
+                if (c[3] > 1e-6f) {
+                    c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3];
+                }
+                if (op.u.alpha.to == PL_ALPHA_NONE)
+                    c[3] = 1.0f;
+            }
+        } else if (kind == PLB_OP_SWIZZLE) {
+            const float o0 = c[0], o1 = c[1], o2 = c[2], o3 = c[3];
+            float r[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = op.u.swizzle.map[k];
+                if (k < op.u.swizzle.comps && m >= 0)
+                    r[k] = m == 0 ? o0 : m == 1 ? o1 : m == 2 ? o2 : o3;
+            }
+            if (op.u.swizzle.force_alpha)
+                r[3] = o3;
+            c[0] = r[0]; c[1] = r[1]; c[2] = r[2]; c[3] = r[3];
+        }
+    }
+}
+
 static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                                const plb_op_peak **peak_op, uint32_t *y_pq)
 {

@@ -397,6 +397,8 @@ void plb_gpu_before_use(pl_gpu gpu, pl_tex const *texs, int n)
         return;
     for (int i = 0; i < n; i++) {
         struct plb_tex *t = (struct plb_tex *) texs[i];
+        if (t && t->parents[0])
+            plb_gpu_before_use(gpu, t->parents, 2);
         if (t && t->xfer_pending) {
             CK(gpu, cudaStreamWaitEvent(STREAM(gpu), (cudaEvent_t) t->ev_xfer, 0));
             t->xfer_pending = false;
@@ -415,7 +417,40 @@ void plb_gpu_after_use(pl_gpu gpu, pl_tex const *texs, int n)
         struct plb_tex *t = (struct plb_tex *) texs[i];
         if (t)
             t->last_use = p->seq;
+        for (int k = 0; t && k < 2; k++) {
+            if (t->parents[k])
+                ((struct plb_tex *) t->parents[k])->last_use = p->seq;
+        }
     }
+}
+
+static int fmt_kind(pl_fmt fmt);
+
+// Read-only view presenting two single-component textures as one 2-component texture
+pl_tex plb_tex_view2(pl_gpu gpu, pl_tex a, pl_tex b, pl_fmt fmt)
+{
+    const struct plb_tex *ta = plb_tex_priv(a), *tb = plb_tex_priv(b);
+    if (ta->d.comps != 1 || tb->d.comps != 1 || ta->d.kind != tb->d.kind || ta->d.ptr2 ||
+        tb->d.ptr2 || ta->d.w != tb->d.w || ta->d.h != tb->d.h || fmt->num_components != 2 ||
+        fmt_kind(fmt) != ta->d.kind)
+        return NULL;
+    struct plb_tex *t = (struct plb_tex *) calloc(1, sizeof(*t));
+    if (!t)
+        return NULL;
+    t->pub.params = a->params;
+    t->pub.params.format = fmt;
+    t->pub.params.host_writable = t->pub.params.host_readable = false;
+    t->pub.params.renderable = t->pub.params.storable = t->pub.params.blit_dst = false;
+    t->pub.params.sampleable = true;
+    t->gpu = gpu;
+    t->d = ta->d;
+    t->d.comps = 2;
+    t->d.ptr2 = tb->d.ptr;
+    t->d.pitch2 = tb->d.pitch;
+    t->owned = false;
+    t->parents[0] = a;
+    t->parents[1] = b;
+    return &t->pub;
 }
 
 // stream for a host<->device transfer of `t`, ordered after everything that used it so far

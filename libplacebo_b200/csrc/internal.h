@@ -48,6 +48,12 @@ struct plb_tex_desc {
     int w, h;
     int comps;         // 1..4
     int kind;          // enum plb_fmt_kind
+    // planar pair view (read only): component 0 from `ptr`, component 1 from `ptr2`, both
+    // single-component planes of the same size and kind. Lets two chroma planes act as the
+    // 2-component texture the reference would first merge them into (renderer.c:1617-1699),
+    // without the copy pass: the values are identical.
+    void *ptr2;
+    size_t pitch2;
 };
 
 // The private object behind a pl_tex (public part first, like PL_PRIV in src/pl_alloc.h)
@@ -62,7 +68,10 @@ struct plb_tex {
     uint64_t last_use;
     void *ev_xfer;     // cudaEvent_t, created on first transfer
     bool xfer_pending; // main stream has not yet waited for ev_xfer
+    pl_tex parents[2]; // planar pair view: the textures it aliases
 };
+// Read-only 2-component view over two single-component textures (see plb_tex_desc.ptr2)
+pl_tex plb_tex_view2(pl_gpu gpu, pl_tex a, pl_tex b, pl_fmt fmt);
 static inline const struct plb_tex *plb_tex_priv(pl_tex tex) { return (const struct plb_tex *) tex; }
 
 struct plb_buf {

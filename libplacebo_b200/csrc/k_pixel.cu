@@ -100,10 +100,89 @@ static bool prog_has_peak(const plb_color_prog *prog)
     return false;
 }
 
+// Light passes (plane merges, FBO copies, 1:1 or bilinear resizes with at most scale / matrix /
+// swizzle steps) are pure data movement: no transcendental tables, every fetch of the thread's
+// four rows is issued before the first use (memory-level parallelism instead of four dependent
+// round trips), register-resident colour.
+__global__ void __launch_bounds__(256)
+k_pixel_light(const __grid_constant__ plb_tail_args ap)
+{
+    plb_tail_stage(ap);
+    __syncthreads();
+    const plb_tail_args &a = plb_s_tail;
+    const int gx = blockIdx.x * PIX_TILE + threadIdx.x;
+    const int gy0 = blockIdx.y * PIX_TILE + threadIdx.y;
+    if (gx >= a.out_w)
+        return;
+    float color[4][4];
+    #pragma unroll
+    for (int r = 0; r < 4; r++) {
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            color[r][k] = a.init[k];
+    }
+    #pragma unroll 1
+    for (int i = 0; i < a.nplanes; i++) {
+        const plb_plane_src &pl = a.planes[i];
+        float4 c4[4];
+        #pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int gy = min(gy0 + 8 * r, a.out_h - 1);
+            float posx, posy;
+            plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
+            c4[r] = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
+        }
+        #pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const float tmp[4] = { c4[r].x * pl.scale, c4[r].y * pl.scale, c4[r].z * pl.scale, c4[r].w * pl.scale };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = pl.map[k];
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    color[r][j] = m == j ? tmp[k] : color[r][j];
+            }
+        }
+    }
+    #pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int gy = gy0 + 8 * r;
+        if (gy >= a.out_h)
+            continue;
+        plb_run_light_ops(color[r]);
+        plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy,
+                  make_float4(color[r][0], color[r][1], color[r][2], color[r][3]));
+    }
+}
+
+static bool pixel_is_light(const struct plb_pixel_launch *p)
+{
+    if (!p->dst.ptr)
+        return false;
+    for (int i = 0; i < p->nplanes; i++) {
+        if (p->planes[i].kind != PLB_PLANE_DIRECT)
+            return false;
+    }
+    for (int i = 0; i < p->prog.n; i++) {
+        const int k = p->prog.ops[i].kind;
+        if (k != PLB_OP_SCALE && k != PLB_OP_MATRIX && k != PLB_OP_ROUND_FBO && k != PLB_OP_ALPHA &&
+            k != PLB_OP_SWIZZLE)
+            return false;
+    }
+    return true;
+}
+
 extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
 {
     static plb_tail_args t;
     plb_fill_tail(&t, p);
+    if (pixel_is_light(p)) {
+        dim3 block(32, 8);
+        dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
+        k_pixel_light<<<grid, block, 0, STREAM(gpu)>>>(t);
+        plb_gpu_priv(gpu)->launches++;
+        return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_light");
+    }
     if (prog_has_peak(&p->prog)) {
         if (PIX_TILE % t.wg_w || PIX_TILE % t.wg_h ||
             (PIX_TILE / t.wg_w) * (PIX_TILE / t.wg_h) > PLB_MAX_WG_PER_CTA) {

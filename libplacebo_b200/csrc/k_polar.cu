@@ -193,8 +193,8 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
             (4 * oy - up2_frac4(YM, py)) * (4 * oy - up2_frac4(YM, py))) < R2_16;
 }
 
-// PURE: a resampling pass with nothing to merge and no colour program (config C2's main
-// scaler): the tail collapses to a component swizzle and four-texel vector stores.
+// PURE: a resampling pass with nothing to merge and at most a light colour program (config
+// C2's main scaler: 1/scale + swizzle): register-resident tail and four-texel vector stores.
 template <int NC, int R2_16, int XM, int YM, bool PURE = false>
 __global__ void __launch_bounds__(UP2_TX * UP2_TY)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
@@ -289,6 +289,24 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
                     for (int j = 0; j < 4; j++)
                         color[j] = m == j ? prim[k] : color[j];
                 }
+                // directly sampled extra planes (e.g. the luma plane next to EWA-scaled chroma)
+                #pragma unroll 1
+                for (int i = 0; i < t.nplanes; i++) {
+                    const plb_plane_src &pl = t.planes[i];
+                    float posx, posy;
+                    plb_coord_pos(t.plane_cc[i], gx + oxo, gy, posx, posy);
+                    const float4 c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy)
+                                                : plb_tex_nearest(pl.tex, posx, posy);
+                    const float tmp[4] = { c4.x * pl.scale, c4.y * pl.scale, c4.z * pl.scale, c4.w * pl.scale };
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int m = pl.map[k];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            color[j] = m == j ? tmp[k] : color[j];
+                    }
+                }
+                plb_run_light_ops(color);
                 px4[oxo] = make_float4(color[0], color[1], color[2], color[3]);
             }
             if (gx + UP2_OX <= t.out_w) {
@@ -395,13 +413,20 @@ static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
     // the tile is a whole number of peak work groups, so this also covers overhanging ones
     dim3 grid((args.tail.out_w + UP2_TX * UP2_OX - 1) / (UP2_TX * UP2_OX),
               (args.tail.out_h + UP2_TY * UP2_OY - 1) / (UP2_TY * UP2_OY));
-    // pure resampling pass (nothing merged, empty colour program): centred phases only
-    const bool pure = XM == 0 && YM == 0 && args.tail.nplanes == 0 && args.tail.prog.n == 0 &&
-                      args.tail.dst.ptr;
+    // light pass: only directly sampled planes to merge and at most a "light" colour program
+    bool light = true;
+    for (int i = 0; i < args.tail.prog.n; i++) {
+        const int k = args.tail.prog.ops[i].kind;
+        light &= k == PLB_OP_SCALE || k == PLB_OP_MATRIX || k == PLB_OP_ROUND_FBO ||
+                 k == PLB_OP_ALPHA || k == PLB_OP_SWIZZLE;
+    }
+    for (int i = 0; i < args.tail.nplanes; i++)
+        light &= args.tail.planes[i].kind == PLB_PLANE_DIRECT;
+    const bool pure = light && args.tail.dst.ptr;
     if (pure) {
         switch (r2_class) {
-        case 160: k_polar_up2<NC, 160, 0, 0, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
-        default:  k_polar_up2<NC, 1000, 0, 0, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        case 160: k_polar_up2<NC, 160, XM, YM, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        default:  k_polar_up2<NC, 1000, XM, YM, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
         }
     } else {
         switch (r2_class) {

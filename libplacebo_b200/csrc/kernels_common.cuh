@@ -82,7 +82,7 @@ PLB_DEV float4 plb_load_t(const plb_tex_desc &t, int x, int y)
 }
 
 // Runtime-dispatched variant for the generic kernels (uniform branches)
-PLB_DEV float4 plb_load(const plb_tex_desc &t, int x, int y)
+PLB_DEV float4 plb_load1(const plb_tex_desc &t, int x, int y)
 {
 #define L(K) \
     switch (t.comps) { \
@@ -99,6 +99,21 @@ PLB_DEV float4 plb_load(const plb_tex_desc &t, int x, int y)
     }
 #undef L
 }
+
+PLB_DEV float4 plb_load(const plb_tex_desc &t, int x, int y)
+{
+    if (t.ptr2) { // planar pair view
+        plb_tex_desc a = t;
+        a.comps = 1;
+        const float4 va = plb_load1(a, x, y);
+        a.ptr = t.ptr2;
+        a.pitch = t.pitch2;
+        const float4 vb = plb_load1(a, x, y);
+        return make_float4(va.x, vb.x, 0.0f, 1.0f);
+    }
+    return plb_load1(t, x, y);
+}
+
 
 PLB_DEV float4 plb_load_clamped(const plb_tex_desc &t, int x, int y)
 {

@@ -44,10 +44,20 @@ struct pl_renderer_t {
     uint8_t frame_index;
     bool have_peak_override;
     struct pl_peak_state peak_override;
+    // planar pair views created for the current frame (freed when the frame has been recorded)
+    pl_tex views[4];
+    int num_views;
     // info_callback plumbing (renderer.c:3320-3345 `info_callback`)
     const struct pl_render_params *info_params;
     int info_index;
 };
+
+static void free_views(pl_renderer rr)
+{
+    for (int i = 0; i < rr->num_views; i++)
+        pl_tex_destroy(rr->gpu, &rr->views[i]);
+    rr->num_views = 0;
+}
 
 static void renderer_info_cb(void *priv, const struct pl_dispatch_info *dinfo)
 {
@@ -692,6 +702,22 @@ static bool pass_read_image(struct pass_state *pass)
                                      PL_FMT_CAP_SAMPLEABLE);
             if (!fmt)
                 continue;
+            // Two single-component planes of the target's component type: the merged texture
+            // would hold exactly the same values, so alias them instead of copying
+            if (sti->comps == 1 && stj->comps == 1 && num_comps == 2 && !sti->sh && !stj->sh &&
+                sti->plane.component_mapping[0] != PL_CHANNEL_NONE &&
+                stj->plane.component_mapping[0] != PL_CHANNEL_NONE && rr->num_views < 4) {
+                pl_tex view = plb_tex_view2(rr->gpu, sti->tex, stj->tex, fmt);
+                if (view) {
+                    rr->views[rr->num_views++] = view;
+                    sti->tex = view;
+                    sti->fmt = fmt;
+                    sti->comps = sti->plane.components = 2;
+                    sti->plane.component_mapping[1] = stj->plane.component_mapping[0];
+                    *stj = (struct plane_state) {0};
+                    continue;
+                }
+            }
             // one pass that copies both planes into adjacent components
             pl_shader sh = begin(pass), sa = begin(pass), sb = begin(pass);
             pl_shader_sample_direct(sa, pl_sample_src( .tex = sti->tex ));
@@ -1311,6 +1337,7 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
     bool ok = pass_read_image(&pass) && pass_scale_main(&pass) && pass_convert_colors(&pass) &&
               pass_output_target(&pass);
     rr->info_params = NULL;
+    free_views(rr);
     if (!ok) {
         PLB_ERR(rr->log, "Failed rendering image!");
         pl_dispatch_abort(rr->dp, &pass.sh);
@@ -1382,6 +1409,7 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
     }
 done:
     pl_dispatch_abort(rr->dp, &pass.sh);
+    free_views(rr);
     rr->have_peak_override = had_override;
     return ok;
 }

@@ -35,7 +35,8 @@ def oracle_params(descs, chroma, depth, overlap, keep):
         p.is_luma[i] = 0 if chroma else 1
         p.uv_mult[i] = fx.uv_mult[i] / 64.0
         p.uv_mult_luma[i] = fx.uv_mult_luma[i] / 64.0
-        p.uv_offset[i] = float(int(fx.uv_offset[i]) << (depth - 8)) / ((1 << depth) - 1)
+        # bits = repr.bits.color_depth AFTER pl_color_repr_normalize = the sample depth (16)
+        p.uv_offset[i] = float(int(fx.uv_offset[i]) << (16 - 8)) / ((1 << depth) - 1)
     p.offsets = off.ctypes.data_as(C.POINTER(C.c_uint32))
     p.offsets_w, p.offsets_h = descs[1][1], descs[1][2]
     p.num_comps = len(g)
@@ -43,10 +44,10 @@ def oracle_params(descs, chroma, depth, overlap, keep):
     p.chroma_scaling_from_luma = int(fx.chroma_scaling_from_luma)
     p.bit_depth = depth
     p.scale = float(np.float32((1 << 16) / (1 << depth)))  # limited range: 2^16 / 2^depth
-    out_scale = np.float32((1 << depth) / ((1 << depth) - 1.0))
-    p.minValue = float(np.float32(16 / 256.0 * out_scale))
-    p.maxLuma = float(np.float32(235 / 256.0 * out_scale))
-    p.maxChroma = float(np.float32(240 / 256.0 * out_scale))
+    out_scale = np.float32(65536 / 65535.0)  # film_grain_av1.c:866-872: normalised repr, 16 bits
+    p.minValue = float(np.float32(16 / 256.0 * float(out_scale)))
+    p.maxLuma = float(np.float32(235 / 256.0 * float(out_scale)))
+    p.maxChroma = float(np.float32(240 / 256.0 * float(out_scale)))
     p.scaling_shift = fx.scaling_shift
     p.luma_comp = 0
     return p
