@@ -60,6 +60,32 @@ PLB_DEV float plb_pq_eotf(float x, bool clamp0)
     return plm_powf(x, c_pq.inv_m1);
 }
 
+// three-channel forms (same per-element arithmetic, one plm_pow3 call per power)
+PLB_DEV void plb_pq_eotf3(float c[3], bool clamp0, float post_scale)
+{
+    float3 x = make_float3(clamp0 ? fmaxf(c[0], 0.0f) : c[0], clamp0 ? fmaxf(c[1], 0.0f) : c[1],
+                           clamp0 ? fmaxf(c[2], 0.0f) : c[2]);
+    x = plm_pow3(x, c_pq.inv_m2);
+    x.x = fmaxf(x.x - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.x);
+    x.y = fmaxf(x.y - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.y);
+    x.z = fmaxf(x.z - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.z);
+    x = plm_pow3(x, c_pq.inv_m1);
+    c[0] = x.x * post_scale; c[1] = x.y * post_scale; c[2] = x.z * post_scale;
+}
+
+PLB_DEV void plb_pq_oetf3(float c[3], bool clamp0, float pre_scale)
+{
+    float3 x = make_float3(c[0] * pre_scale, c[1] * pre_scale, c[2] * pre_scale);
+    if (clamp0)
+        x = make_float3(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f), fmaxf(x.z, 0.0f));
+    x = plm_pow3(x, c_pq.m1);
+    x.x = (c_pq.c1 + c_pq.c2 * x.x) / (1.0f + c_pq.c3 * x.x);
+    x.y = (c_pq.c1 + c_pq.c2 * x.y) / (1.0f + c_pq.c3 * x.y);
+    x.z = (c_pq.c1 + c_pq.c2 * x.z) / (1.0f + c_pq.c3 * x.z);
+    x = plm_pow3(x, c_pq.m2);
+    c[0] = x.x; c[1] = x.y; c[2] = x.z;
+}
+
 PLB_DEV float plb_pq_oetf(float x, bool clamp0)
 {
     x = plm_powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.m1);
@@ -84,10 +110,11 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
                                    : c[k] * (float) (1.0 / 12.92);
         post_scale = true;
         break;
-    case TRC_BT_1886:
-        for (int k = 0; k < 3; k++)
-            c[k] = t.a * plm_powf(c[k] + t.b, 2.4f);
+    case TRC_BT_1886: {
+        const float3 p = plm_pow3(make_float3(c[0] + t.b, c[1] + t.b, c[2] + t.b), 2.4f);
+        c[0] = t.a * p.x; c[1] = t.a * p.y; c[2] = t.a * p.z;
         break;
+    }
     case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 1.8f); post_scale = true; break;
     case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.0f); post_scale = true; break;
     case TRC_UNKNOWN:
@@ -106,9 +133,7 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
         post_scale = true;
         break;
     case TRC_PQ:
-        #pragma unroll
-        for (int k = 0; k < 3; k++)
-            c[k] = plb_pq_eotf(c[k], false) * c_pq.from_pq;
+        plb_pq_eotf3(c, false, c_pq.from_pq);
         break;
     case TRC_HLG: {
         // t.a = y, t.b = b
@@ -172,11 +197,11 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
             c[k] = 0.0031308f <= c[k] ? 1.055f * plm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
                                       : c[k] * 12.92f;
         break;
-    case TRC_BT_1886: // t.a = 1/a, t.b = b
-        #pragma unroll
-        for (int k = 0; k < 3; k++)
-            c[k] = plm_powf(t.a * c[k], (float) (1.0 / 2.4)) - t.b;
+    case TRC_BT_1886: { // t.a = 1/a, t.b = b
+        const float3 p = plm_pow3(make_float3(t.a * c[0], t.a * c[1], t.a * c[2]), (float) (1.0 / 2.4));
+        c[0] = p.x - t.b; c[1] = p.y - t.b; c[2] = p.z - t.b;
         break;
+    }
     case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 1.8)); break;
     case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.0)); break;
     case TRC_UNKNOWN:
@@ -193,9 +218,7 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
             c[k] = 0.001953f <= c[k] ? plm_powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
         break;
     case TRC_PQ:
-        #pragma unroll
-        for (int k = 0; k < 3; k++)
-            c[k] = plb_pq_oetf(c[k] * c_pq.inv_from_pq, false);
+        plb_pq_oetf3(c, false, c_pq.inv_from_pq);
         break;
     case TRC_HLG: {
         for (int k = 0; k < 3; k++)
@@ -364,9 +387,8 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
     float lms[3] = { px[0], px[1], px[2] };
     plb_matv(p.rgb2lms, lms[0], lms[1], lms[2]);
     float ipt[3];
-    #pragma unroll
-    for (int k = 0; k < 3; k++)
-        ipt[k] = plb_pq_oetf(c_pq.to_pq * lms[k], true);
+    ipt[0] = lms[0]; ipt[1] = lms[1]; ipt[2] = lms[2];
+    plb_pq_oetf3(ipt, true, c_pq.to_pq);
     plb_matv(lms2ipt, ipt[0], ipt[1], ipt[2]);
     const float i_orig = ipt[0];
 
@@ -400,9 +422,8 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
     }
 
     plb_matv(ipt2lms, ipt[0], ipt[1], ipt[2]);
-    #pragma unroll
-    for (int k = 0; k < 3; k++)
-        lms[k] = plb_pq_eotf(ipt[k], true) * c_pq.from_pq;
+    lms[0] = ipt[0]; lms[1] = ipt[1]; lms[2] = ipt[2];
+    plb_pq_eotf3(lms, true, c_pq.from_pq);
     plb_matv(p.lms2rgb, lms[0], lms[1], lms[2]);
     px[0] = lms[0]; px[1] = lms[1]; px[2] = lms[2];
 }
