@@ -827,11 +827,19 @@ static bool pass_read_image(struct pass_state *pass)
                     luma_comp = c;
             }
             pl_shader gsh = begin(pass);
-            struct pl_color_repr grepr = st->repr;
+            // renderer.c:1366-1376: the grain always sees the ORIGINAL colour depth; if the
+            // plane was already processed (normalised), only sample depth / shift follow it
+            struct pl_color_repr grepr = image->repr;
+            const bool is_orig_repr = pl_color_repr_equal(&st->repr, &image->repr);
+            if (!is_orig_repr) {
+                grepr.bits.sample_depth = st->repr.bits.sample_depth;
+                grepr.bits.bit_shift = grepr.bits.sample_depth - grepr.bits.color_depth;
+            }
             if (plb_plane_film_grain(rr, gsh, &rr->grain_state[i], image, &st->plane, st->tex,
                                      ref_tex, luma_comp, &grepr)) {
                 st->sh = gsh;
-                st->repr = grepr;
+                if (is_orig_repr)
+                    st->repr = grepr;
             } else {
                 const bool failed = pl_shader_is_failed(gsh);
                 pl_dispatch_abort(rr->dp, &gsh);

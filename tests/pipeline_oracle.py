@@ -13,6 +13,7 @@ Pass graph (file:line in /root/reference/src/renderer.c):
   output: encode_color, dither, 1/scale, store                               :2586-2964
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -70,10 +71,69 @@ def fix_bits(fmt_depth, bits):
     return sd, cd, sh
 
 
+# ---- AV1 film grain: LUTs come from the real reference shader (oracle/harvest.c) ---------------
+HARVEST_SO = os.path.join(T.ROOT, "oracle", "_ref", "libplref_harvest.so")
+
+
+def av1_harvest(plane, w, h, seed, depth, levels=1, sys_=2):
+    """LUT descriptors uploaded by pl_shader_film_grain for the reference's fixture.
+    plane 0: luma r16 w x h; plane 1: merged chroma rg16 (w/2 x h/2, luma tex w x h)."""
+    import tempfile
+    hv = C.CDLL(HARVEST_SO)
+    d = tempfile.mkdtemp()
+    assert hv.hvs_av1_grain(d.encode(), w, h, plane, seed, 1, depth, levels, sys_) == 0
+    descs = {}
+    for line in open(os.path.join(d, "meta.txt")):
+        f = line.split()
+        if f and f[0] == "desc" and f[-1] == "1":
+            descs[int(f[1])] = (f[4], int(f[5]), int(f[6]), os.path.join(d, f"desc_{f[1]}.bin"))
+    return descs
+
+
+def av1_oracle_params(descs, chroma, depth, overlap, keep, tex_scale):
+    """struct orc_av1_grain_params for the fixture; host constants as film_grain_av1.c:860-880
+    (limited range; `bits` there is the normalised repr's depth = 16)."""
+    fx = T.av1_fixture()
+    p = T.OrcAv1Grain()
+    if chroma:
+        uv = np.fromfile(descs[0][3], f32).reshape(-1, 2)
+        g = [np.ascontiguousarray(uv[:, 0]), np.ascontiguousarray(uv[:, 1])]
+        sc = [np.fromfile(descs[2][3], f32), np.fromfile(descs[3][3], f32)]
+        p.grain_w = p.grain_h = 32
+        p.sub_x = p.sub_y = 1
+    else:
+        g = [np.fromfile(descs[0][3], f32)]
+        sc = [np.fromfile(descs[2][3], f32)]
+        p.grain_w = p.grain_h = 64
+    off = np.fromfile(descs[1][3], np.uint32)
+    keep += g + sc + [off]
+    for i in range(len(g)):
+        p.grain[i] = T.fp(g[i])
+        p.scaling[i] = T.fp(sc[i])
+        p.is_luma[i] = 0 if chroma else 1
+        p.uv_mult[i] = fx.uv_mult[i] / 64.0
+        p.uv_mult_luma[i] = fx.uv_mult_luma[i] / 64.0
+        p.uv_offset[i] = float(int(fx.uv_offset[i]) << (16 - 8)) / ((1 << depth) - 1)
+    p.offsets = off.ctypes.data_as(C.POINTER(C.c_uint32))
+    p.offsets_w, p.offsets_h = descs[1][1], descs[1][2]
+    p.num_comps = len(g)
+    p.overlap = overlap
+    p.chroma_scaling_from_luma = int(fx.chroma_scaling_from_luma)
+    p.bit_depth = depth
+    p.scale = float(tex_scale)
+    out_scale = float(f32(65536 / 65535.0))
+    p.minValue = float(f32(16 / 256.0 * out_scale))
+    p.maxLuma = float(f32(235 / 256.0 * out_scale))
+    p.maxChroma = float(f32(240 / 256.0 * out_scale))
+    p.scaling_shift = fx.scaling_shift
+    p.luma_comp = 0
+    return p
+
+
 def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0,
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
            coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
-           error_diffusion=None):
+           error_diffusion=None, film_grain=None):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
     smoothed (avg, max) between frames like sh_color_map_obj.peak does."""
     t0, orc = T.t0(), T.oracle()
@@ -125,6 +185,26 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     else:
         luma_v = orc.sample_direct(Yf, W, H, scale=float(norm), coord_mode=coord_mode, ext=ext)[..., 0]
         ctex, cscale = UVf, float(norm)
+
+    # ---- film grain (AV1), per plane after the optional debanding (renderer.c:1355-1429)
+    if film_grain is not None:
+        seed, overlap = film_grain
+        depth = img.bits[1]
+        keep = []
+        if deband:
+            ltex, lscale = orc.store_round(luma[:H, :W, :1], 0), 1.0   # r16hf FBO of the debanded plane
+        else:
+            ltex, lscale = Yf, float(norm)
+        pl = av1_oracle_params(av1_harvest(0, W, H, seed, depth, img.levels, img.sys), 0, depth,
+                               overlap, keep, lscale)
+        lg = orc.av1_grain(ltex, None, pl)[..., 0]
+        luma_v = np.pad(lg, ((0, ext[1] - H), (0, ext[0] - W)), mode="edge")
+        pc = av1_oracle_params(av1_harvest(1, W, H, seed, depth, img.levels, img.sys), 1, depth,
+                               overlap, keep, cscale)
+        # quirk kept from the reference: the luma fetched for chroma scaling is the ORIGINAL
+        # (un-normalised) plane times this plane's texture scale
+        cg = orc.av1_grain(ctex, Yf, pc)
+        ctex, cscale = orc.store_round(cg[..., :2], 0), 1.0                 # rg16hf FBO
 
     # plane scaler (SAMPLER_PLANE)
     crect_f = tuple(f32(v) for v in crect)

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+import pipeline_oracle as P
 import plbtest as T
 from test_grain_tables import HARVEST, harvest
 
@@ -82,3 +83,19 @@ def test_av1_grain_plane(gpu, oracle, chroma, overlap):
     # the grain must actually have changed the plane
     base = plane[..., 0] * np.float32(64)
     assert np.mean(got[..., 0] != base) > 0.5
+
+
+@pytest.mark.parametrize("deband", [False, True])
+def test_render_with_av1_grain(gpu, deband):
+    """Config C4's plane stage at reduced size through pl_render_image: merged chroma planes,
+    grain per plane (after debanding when enabled), EWA chroma upscale from the grained FBO."""
+    import ctypes as C
+    from test_gpu_render import SDR, gpu_render
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(256, 144, seed=17)
+    img = P.Frame(planes, T.SYS["BT_709"], csp=SDR)
+    tgt = P.Target(256, 144, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    got, _ = gpu_render(gpu, img, tgt, upscaler="ewa_lanczos", deband=deband, grain=(1234, 1), frame_index=3)
+    want, _ = P.render(img, tgt, upscaler="ewa_lanczos", deband=deband, film_grain=(1234, 1), frame_index=3)
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    assert d.max() == 0, (d.max(), np.mean(d > 0))

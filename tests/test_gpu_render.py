@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, peak=0,
                allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, tone_fn=None,
-               gamut_fn=None, error_diffusion=None):
+               gamut_fn=None, error_diffusion=None, grain=None):
     Y, U, V = img.planes
     texs = [gpu.tex("r16", p.shape[1], p.shape[0], p) for p in (Y, U, V)]
     dst = gpu.tex(tgt.fmt, tgt.w, tgt.h)
@@ -28,6 +28,8 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
         opts[5] = P.CHROMA_ENUM[img.chroma_loc]
         opts[7] = frame_index
         opts[8] = T.ED_KERNELS.index(error_diffusion) + 1 if error_diffusion else 0
+        if grain is not None:
+            opts[12], opts[13] = 2 if grain[1] else 1, grain[0]
         opts[9] = T.TONE_FNS.index(tone_fn) + 1 if tone_fn else 0
         opts[10] = T.GAMUT_FNS.index(gamut_fn) + 1 if gamut_fn else 0
         peak_out = np.zeros(2, T.f32)
