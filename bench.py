@@ -72,6 +72,8 @@ def cpu_pipeline_fps(wl_name, sample, repeats=1):
     o = wl["opts"]
     kw = dict(upscaler=wl["upscaler"], deband=bool(o.get("deband")), peak=o.get("peak", 0),
               dither=o.get("dither", 0), cmap_hq=bool(o.get("cmap_hq")))
+    if o.get("grain"):
+        kw["film_grain"] = (1, 1 if o["grain"] > 1 else 0)
     P.render(img, tgt, **kw)  # warm caches (filter / gamut LUT generation)
     t0 = time.perf_counter()
     for i in range(repeats):

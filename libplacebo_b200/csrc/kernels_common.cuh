@@ -81,7 +81,8 @@ PLB_DEV float4 plb_load_t(const plb_tex_desc &t, int x, int y)
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// Runtime-dispatched variant for the generic kernels (uniform branches)
+// Runtime-dispatched fetch (uniform branches). Kept inline: as a real function the call
+// overhead cost 10-50 % in the fetch-heavy kernels (deband, plane merges) on B200.
 PLB_DEV float4 plb_load1(const plb_tex_desc &t, int x, int y)
 {
 #define L(K) \

@@ -147,8 +147,31 @@ enum {
     O_SRC_SYS, O_SRC_LEVELS, O_SRC_SAMPLE_DEPTH, O_SRC_COLOR_DEPTH, O_SRC_BIT_SHIFT,
     O_DST_SYS, O_DST_LEVELS, O_DST_SAMPLE_DEPTH, O_DST_COLOR_DEPTH,
     O_CHROMA_LOC, O_DEBAND, O_PEAK, O_ALLOW_DELAYED, O_DITHER, O_CMAP_HQ, O_RING,
-    O_TONE_FN, O_GAMUT_FN, O_COUNT
+    O_TONE_FN, O_GAMUT_FN, O_GRAIN, O_COUNT
 };
+
+// AV1 grain parameters of libplacebo's own test fixture (src/tests/utils.h:240-262): medium
+// luma grain with a 3-tap-lag AR filter, chroma grain scaled from luma.
+static struct pl_av1_grain_data demo_av1_grain(bool overlap)
+{
+    return (struct pl_av1_grain_data) {
+        .num_points_y = 6,
+        .points_y = {{0, 4}, {27, 33}, {54, 55}, {67, 61}, {108, 71}, {255, 72}},
+        .num_points_uv = {2, 2},
+        .points_uv = {{{0, 64}, {255, 64}}, {{0, 64}, {255, 64}}},
+        .scaling_shift = 11,
+        .ar_coeff_lag = 3,
+        .ar_coeffs_y = {4, 1, 3, 0, 1, -3, 8, -3, 7, -23, 1, -25,
+                        0, -10, 6, -17, -4, 53, 36, 5, -5, -17, 8, 66},
+        .ar_coeffs_uv = {
+            {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 127},
+            {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 127},
+        },
+        .ar_coeff_shift = 7,
+        .uv_mult_luma = {64, 64},
+        .overlap = overlap,
+    };
+}
 
 // Returns 0 on success. `iopts` follows the enum above; formats by name ("r16", "rgba8", ...)
 API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
@@ -190,6 +213,10 @@ API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
             .texture = s->planes[0][i], .components = 1, .component_mapping = { i } };
     }
     pl_frame_set_chroma_location(&s->image, o[O_CHROMA_LOC] ? o[O_CHROMA_LOC] : PL_CHROMA_LEFT);
+    if (o[O_GRAIN]) {
+        s->image.film_grain.type = PL_FILM_GRAIN_AV1;
+        s->image.film_grain.params.av1 = demo_av1_grain(o[O_GRAIN] > 1);
+    }
     s->target_frame = (struct pl_frame) {
         .num_planes = 1,
         .planes = {{ .texture = s->target[0], .components = df->num_components,
@@ -245,6 +272,8 @@ API int plg_render(struct plg_stream *s, int slot, int out_slot, int frame_index
     s->target_frame.planes[0].texture = s->target[out_slot];
     if (frame_index >= 0)
         pl_renderer_set_frame_index(s->rr, (uint8_t) frame_index);
+    if (s->image.film_grain.type) // AV1: a new random seed with every frame
+        s->image.film_grain.seed = (uint64_t) (frame_index >= 0 ? frame_index + 1 : 1);
     if (!pl_render_image(s->rr, &s->image, &s->target_frame, &s->params))
         return -1;
     return (int) pl_renderer_get_errors(s->rr).errors;
