@@ -122,8 +122,14 @@ static void pass_collect(pl_dispatch dp, struct plb_pass *p)
 static pl_timer pass_timer(pl_dispatch dp, struct plb_pass *p)
 {
     pass_collect(dp, p);
-    if (p->timer_head - p->timer_tail >= PLB_PASS_TIMERS)
-        return NULL; // all timers in flight: skip this sample rather than block
+    if (p->timer_head - p->timer_tail >= PLB_PASS_TIMERS) {
+        // every timer is in flight (the host runs far ahead of the GPU): wait for the oldest
+        // one, so that run i of a pass always produces sample i
+        plb_timer_wait(dp->gpu, p->timers[p->timer_tail % PLB_PASS_TIMERS]);
+        pass_collect(dp, p);
+        if (p->timer_head - p->timer_tail >= PLB_PASS_TIMERS)
+            return NULL;
+    }
     pl_timer *slot = &p->timers[p->timer_head % PLB_PASS_TIMERS];
     if (!*slot)
         *slot = pl_timer_create(dp->gpu);

@@ -933,6 +933,12 @@ void plb_timer_end(pl_gpu gpu, pl_timer t)
     }
 }
 
+void plb_timer_wait(pl_gpu gpu, pl_timer t)
+{
+    if (t && t->recorded)
+        CK(gpu, cudaEventSynchronize(t->stop));
+}
+
 // nanoseconds of the last recorded interval, 0 if not available yet
 uint64_t pl_timer_query(pl_gpu gpu, pl_timer t)
 {

@@ -266,6 +266,9 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
 
     const plb_tail_args &t = plb_s_tail;
     if (PURE) {
+        // launch-uniform: the usual identity component mapping needs no per-pixel selects
+        const bool ident = t.src_map[0] == 0 && (NC < 2 || t.src_map[1] == 1) &&
+                           (NC < 3 || t.src_map[2] == 2) && (NC < 4 || t.src_map[3] == 3);
         #pragma unroll
         for (int oyo = 0; oyo < UP2_OY; oyo++) {
             const int gy = Y0 + ty * UP2_OY + oyo;
@@ -281,13 +284,19 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
                 for (int k = 0; k < NC; k++)
                     prim[k] = norm * acc[oyo][oxo][k];
                 float color[4] = { t.init[0], t.init[1], t.init[2], t.init[3] };
-                #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    // src_map is launch-uniform; the selects below stay in registers
-                    const int m = t.src_map[k];
+                if (ident) {
                     #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        color[j] = m == j ? prim[k] : color[j];
+                    for (int k = 0; k < NC; k++)
+                        color[k] = prim[k];
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        // src_map is launch-uniform; the selects below stay in registers
+                        const int m = t.src_map[k];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            color[j] = m == j ? prim[k] : color[j];
+                    }
                 }
                 // directly sampled extra planes (e.g. the luma plane next to EWA-scaled chroma)
                 #pragma unroll 1

@@ -144,6 +144,7 @@ bool plb_shader_merge_plane(pl_shader sh, pl_shader sub, const int8_t map[4], fl
 
 void plb_timer_begin(pl_gpu gpu, pl_timer t);
 void plb_timer_end(pl_gpu gpu, pl_timer t);
+void plb_timer_wait(pl_gpu gpu, pl_timer t);
 
 #ifdef __cplusplus
 }
