@@ -1,0 +1,4 @@
+/* Forwarding header: the libplacebo API surface of the B200 hot path lives in one file
+ * (include/libplacebo_b200.h); this lets sources written against <libplacebo/gpu.h> compile
+ * unchanged. */
+#include "../libplacebo_b200.h"

@@ -293,10 +293,15 @@ API int plg_download(struct plg_stream *s, int out_slot, void *host)
 API void plg_join(struct plg_stream *s) { pl_cuda_join(s->gpu); }
 
 // ---- frame-parallel peak statistics (include/libplacebo_b200.h, "frame-parallel extensions")
-API int plg_measure_peak(struct plg_stream *s, int slot, void *out_buf /* PL_PEAK_BUF_SIZE */)
+API int plg_measure_peak(struct plg_stream *s, int slot, int frame_index,
+                         void *out_buf /* PL_PEAK_BUF_SIZE */)
 {
     for (int i = 0; i < 3; i++)
         s->image.planes[i].texture = s->planes[slot][i];
+    if (frame_index >= 0)
+        pl_renderer_set_frame_index(s->rr, (uint8_t) frame_index);
+    if (s->image.film_grain.type)
+        s->image.film_grain.seed = (uint64_t) (frame_index >= 0 ? frame_index + 1 : 1);
     return pl_renderer_measure_peak(s->rr, &s->image, &s->params, out_buf) ? 0 : -1;
 }
 

@@ -50,6 +50,20 @@ struct pl_renderer_t {
     // info_callback plumbing (renderer.c:3320-3345 `info_callback`)
     const struct pl_render_params *info_params;
     int info_index;
+    // Frame-parallel mode: pl_renderer_measure_peak materialises the merged source pass (the
+    // rgba16hf image the sequential same-frame flow would also produce) and the very next
+    // pl_render_image of the same planes continues from it instead of redoing the pass.
+    struct {
+        bool valid;
+        pl_tex tex;                 // one of rr->fbos, kept reserved while valid
+        pl_tex planes[4];
+        const struct pl_render_params *params;
+        uint8_t frame_index;
+        int w, h, comps;
+        pl_rect2df rect, ref_rect;
+        struct pl_color_repr repr;
+        struct pl_color_space color;
+    } measured;
 };
 
 static void free_views(pl_renderer rr)
@@ -1011,7 +1025,10 @@ static void hdr_update_peak(struct pass_state *pass)
     if (uses_ootf && pass->color.hdr.ootf.num_anchors)
         goto cleanup;
     if (rr->have_peak_override) {
-        // frame-parallel mode: the caller supplies the smoothed state (renderer.h extension)
+        // frame-parallel mode: the caller supplies the smoothed state (renderer.h extension);
+        // keep the FBO round trip of the sequential same-frame flow so that the pixels are
+        // identical to a single-GPU stream
+        pass->need_peak_fbo = !params->peak_detect_params->allow_delayed;
         goto cleanup_keep;
     }
     if (!pl_shader_detect_peak(img_sh(pass), pass->color, &rr->tone_map_state,
@@ -1321,6 +1338,29 @@ static bool pass_begin(struct pass_state *pass)
     return true;
 }
 
+static void reserve_measured_fbo(pl_renderer rr)
+{
+    for (int i = 0; rr->measured.valid && i < MAX_FBOS; i++) {
+        if (rr->fbos[i] == rr->measured.tex)
+            rr->fbo_used[i] = true;
+    }
+}
+
+// Does the image of this render call equal the one pl_renderer_measure_peak just processed?
+static bool measured_hit(pl_renderer rr, const struct pass_state *pass)
+{
+    if (!rr->measured.valid || !rr->have_peak_override || rr->measured.params != pass->params)
+        return false;
+    if (rr->have_frame_index && rr->measured.frame_index != rr->frame_index)
+        return false;
+    for (int i = 0; i < 4; i++) {
+        pl_tex t = i < pass->image.num_planes ? pass->image.planes[i].texture : NULL;
+        if (t != rr->measured.planes[i])
+            return false;
+    }
+    return true;
+}
+
 bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
                      const struct pl_frame *ptarget, const struct pl_render_params *params)
 {
@@ -1342,8 +1382,23 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
     rr->info_params = params;
     rr->info_index = 0;
     pl_dispatch_callback(rr->dp, rr, params->info_callback ? renderer_info_cb : NULL);
-    bool ok = pass_read_image(&pass) && pass_scale_main(&pass) && pass_convert_colors(&pass) &&
-              pass_output_target(&pass);
+    bool ok;
+    if (measured_hit(rr, &pass)) {
+        reserve_measured_fbo(rr);
+        pass.tex = rr->measured.tex;
+        pass.w = rr->measured.w;
+        pass.h = rr->measured.h;
+        pass.comps = rr->measured.comps;
+        pass.rect = rr->measured.rect;
+        pass.ref_rect = rr->measured.ref_rect;
+        pass.repr = rr->measured.repr;
+        pass.color = rr->measured.color;
+        ok = true;
+    } else {
+        ok = pass_read_image(&pass);
+    }
+    rr->measured.valid = false; // single use
+    ok = ok && pass_scale_main(&pass) && pass_convert_colors(&pass) && pass_output_target(&pass);
     rr->info_params = NULL;
     free_views(rr);
     if (!ok) {
@@ -1376,6 +1431,8 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
     rr->have_peak_override = false;
     bool ok = false;
     struct pl_render_params hacked = *params;
+    hacked.plane_upscaler = PLB_DEF(params->plane_upscaler, params->upscaler);
+    hacked.plane_downscaler = PLB_DEF(params->plane_downscaler, params->downscaler);
     hacked.upscaler = hacked.downscaler = NULL;
     pass.params = &hacked;
     if (!find_fbo_format(&pass))
@@ -1404,16 +1461,29 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
     if (!pl_shader_detect_peak(img_sh(&pass), pass.color, &rr->tone_map_state,
                                params->peak_detect_params))
         goto done;
-    {
-        pl_shader sh = pass.sh;
-        pass.sh = NULL;
-        ok = plb_dispatch_run(rr->dp, sh, NULL, (pl_rect2d) {0}, pass.w, pass.h, NULL);
-        pl_dispatch_abort(rr->dp, &sh);
-    }
+    // statistics + the image itself (rgba16hf FBO, exactly what the sequential same-frame flow
+    // stores between its two passes): the following pl_render_image continues from it
+    rr->measured.valid = false;
+    ok = img_tex(&pass) != NULL;
     if (ok) {
         struct plb_peak_state *pk = &rr->tone_map_state->u.cmap.peak;
         ok = plb_dev_download(rr->gpu, out_peak_buf, pk->dev_buf, PL_PEAK_BUF_SIZE);
         pk->pending = false;
+    }
+    if (ok) {
+        rr->measured.valid = true;
+        rr->measured.tex = pass.tex;
+        for (int i = 0; i < 4; i++)
+            rr->measured.planes[i] = i < pimage->num_planes ? pimage->planes[i].texture : NULL;
+        rr->measured.params = params;
+        rr->measured.frame_index = rr->frame_index;
+        rr->measured.w = pass.w;
+        rr->measured.h = pass.h;
+        rr->measured.comps = pass.comps;
+        rr->measured.rect = pass.rect;
+        rr->measured.ref_rect = pass.ref_rect;
+        rr->measured.repr = pass.repr;
+        rr->measured.color = pass.color;
     }
 done:
     pl_dispatch_abort(rr->dp, &pass.sh);

@@ -4,14 +4,16 @@ The path's only cross-frame state is the peak-detection IIR (shaders/colorspace.
 the reference): frame f's tone curve depends on the smoothed peak after frames 0..f. Frames are
 dealt round-robin (frame f = step * world + rank). Per step every rank
 
-  1. measures its frame: the pass graph up to the peak-detection tap, statistics only
-     (`pl_renderer_measure_peak`, raw `peak_buf_data`, 3264 bytes);
+  1. measures its frame: the pass graph up to the peak-detection tap (`pl_renderer_measure_peak`:
+     raw `peak_buf_data`, 3264 bytes; the rgba16hf image of that pass stays cached in the renderer,
+     it is exactly what the sequential same-frame flow stores between its two passes);
   2. all-gathers the statistics (NCCL over NVLink: 3264 B per rank — the one collective of the
      path; there is no pixel exchange);
   3. replays the recurrence over the gathered buffers in frame order
      (`pl_peak_state_update`, host arithmetic, identical on every rank), stopping at its own
      frame to obtain the state the sequential reference would have had;
-  4. renders its frame with that state (`pl_renderer_set_peak_state` + `pl_render_image`).
+  4. renders its frame with that state (`pl_renderer_set_peak_state` + `pl_render_image`, which
+     continues from the cached image: the source pass is not repeated).
 
 The output is bit-identical to rendering the stream on one GPU (tests/test_parallel.py checks
 the replay logic with the gloo backend on CPU, tests/test_gpu_parallel.py on GPUs).
@@ -52,9 +54,10 @@ class PeakExchange:
         return [allb[r] for r in range(self.world)]
 
     def render(self, slot, out_slot, step):
-        buf = self.st.measure_peak(slot)
+        frame_index = (step * self.world + self.rank) % 256
+        buf = self.st.measure_peak(slot, frame_index)
         bufs = self.exchange(buf)
         mine, last = replay(self.st.peak_update, self.state, bufs, self.rank)
         self.state = last
         self.st.set_peak(mine)
-        self.st.render(slot, out_slot, frame_index=(step * self.world + self.rank) % 256)
+        self.st.render(slot, out_slot, frame_index=frame_index)

@@ -167,9 +167,12 @@ class Stream:
         return int(self.lib.plg_launch_count(self.h))
 
     # ---- frame-parallel peak statistics ---------------------------------------------------
-    def measure_peak(self, slot):
+    def measure_peak(self, slot, frame_index=-1):
+        """Runs the source pass of the frame in `slot` (kept for the next render of the same
+        slot) and returns its raw peak statistics. `frame_index` must be the one the following
+        render() uses (it seeds the debanding noise and the grain)."""
         buf = np.zeros(PEAK_BUF_SIZE // 4, np.uint32)
-        if self.lib.plg_measure_peak(self.h, slot, C.c_void_p(_ptr(buf))):
+        if self.lib.plg_measure_peak(self.h, slot, frame_index, C.c_void_p(_ptr(buf))):
             raise RuntimeError("pl_renderer_measure_peak failed")
         return buf
 

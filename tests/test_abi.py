@@ -74,3 +74,17 @@ def test_python_enums_match_header():
                        (T.SYS, sys_h), (T.PRIM, prim_h), (T.TRC, trc_h)):
         for k, v in table.items():
             assert hdr[k] == v, (k, v, hdr[k])
+
+
+def test_forwarding_headers_compile(tmp_path):
+    """<libplacebo/*.h> forwarding headers: a translation unit written against the reference's
+    include paths compiles against this repository's include directory."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text("#include <libplacebo/log.h>\n#include <libplacebo/gpu.h>\n#include <libplacebo/cuda.h>\n"
+                   "#include <libplacebo/renderer.h>\n#include <libplacebo/dispatch.h>\n"
+                   "#include <libplacebo/shaders/sampling.h>\n#include <libplacebo/shaders/colorspace.h>\n"
+                   "#include <libplacebo/shaders/dithering.h>\n#include <libplacebo/shaders/film_grain.h>\n"
+                   "int f(void) { struct pl_render_params p = pl_render_default_params; return !!p.upscaler; }\n")
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(T.ROOT, "include"), "-c", str(src),
+                    "-o", str(tmp_path / "t.o")], check=True)

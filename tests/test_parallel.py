@@ -54,7 +54,7 @@ class FakeStream:
         self.state_for_render = None
         self.cursor = None
 
-    def measure_peak(self, slot):
+    def measure_peak(self, slot, frame_index=-1):
         return self.frames[slot].copy()
 
     def peak_update(self, state, buf):
