@@ -167,10 +167,19 @@ def pass_bytes(desc, wl):
     cw, ch = sw // 2, sh // 2
     out_bpp = {"rgba8": 4, "rgba16": 8, "rgba16hf": 8}[wl["dst_fmt"]]
     has = lambda s: s in desc  # noqa: E731
-    scaling = (dw, dh) != (sw, sh)
+    import re
+    m = re.search(r"\[(\d+)x(\d+)\]", desc)
+    pw, ph = (int(m.group(1)), int(m.group(2))) if m else (dw, dh)
+    if has("AV1 film grain") and not has("polar scaling"):
+        # one plane: r16 / r16hf / rg16hf in -> fp16 FBO out (+ luma for chroma grain)
+        if (pw, ph) == (cw, ch):
+            return cw * ch * 4 + cw * ch * 4 + sw * sh * 2 // 4, "chroma grain"
+        return pw * ph * 2 + pw * ph * 2, "luma grain"
     if has("debanding") and not has("polar scaling") and not has("color"):
-        # chroma planes U,V (r16) -> rg16hf FBO at chroma size
-        return 2 * cw * ch * 2 + cw * ch * 4, "chroma deband"
+        if (pw, ph) == (cw, ch):
+            # chroma planes U,V (r16) -> rg16hf FBO at chroma size
+            return 2 * cw * ch * 2 + cw * ch * 4, "chroma deband"
+        return pw * ph * 2 + pw * ph * 2, "luma deband"
     if has("polar scaling") and (has("color decoding") or has("color matrix") or has("linearization")):
         # merged plane pass: luma r16 + chroma (rg16 / rg16hf) -> rgba16hf FBO (or target)
         out = sw * sh * 8

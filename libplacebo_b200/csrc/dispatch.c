@@ -87,6 +87,8 @@ static struct plb_pass *find_pass(pl_dispatch dp, pl_shader sh, int w, int h)
         len += n;
         p->steps[p->info.num_steps++] = sh->steps[i];
     }
+    // output geometry, so that tools can tell passes with the same steps apart
+    snprintf(p->description + len, sizeof(p->description) - len, "%s[%dx%d]", len ? " " : "", w, h);
     p->info.params = sh->params;
     p->info.steps = p->steps;
     p->info.description = p->description;
