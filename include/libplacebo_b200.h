@@ -879,6 +879,8 @@ PL_API bool pl_cuda_av1_tables_host(const struct pl_film_grain_data *data,
                                     const struct pl_color_repr *repr, int sub_x, int sub_y,
                                     int tex_w, int tex_h, float *grain_y, float *grain_cb,
                                     float *grain_cr, uint32_t *offsets, float *scaling);
+// Diagnostics (host only): the H.274 grain data base, out[(13*64) * (13*64)] floats.
+PL_API bool pl_cuda_h274_database_host(float *out);
 PL_API bool pl_shader_film_grain(pl_shader sh, pl_shader_obj *grain_state,
                                  const struct pl_film_grain_params *params);
 

@@ -10,6 +10,7 @@
 // pl_shader_film_grain). The per-pixel part lives in pixel_core.cuh (plb_grain_av1).
 #include "shader_priv.h"
 #include "t0/av1_gaussian.h"
+#include "t0/h274_tables.h"
 
 enum {
     BLOCK_SIZE = 32,
@@ -23,6 +24,9 @@ enum {
     SUB_GRAIN_HEIGHT = 38,
     SUB_GRAIN_PAD_LUT = 6,
 };
+
+enum { H274_RING = 8, H274_DB = 13 * 64, H274_MAX_IV = 3 * 256 };
+#define H274_REC_SIZE (sizeof(struct plb_h274_plane) + H274_MAX_IV * sizeof(struct plb_h274_interval))
 
 struct plb_grain_obj {
     // parameters the cached tables were generated for
@@ -42,6 +46,10 @@ struct plb_grain_obj {
     float *dev_scaling[3];
     uint32_t *dev_offsets;
     size_t dev_offsets_size;
+    // H.274: the grain data base and a small ring of per-pass parameter records
+    float *dev_h274_db;
+    struct plb_h274_plane *dev_h274[H274_RING];
+    int h274_next;
 };
 
 void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g)
@@ -53,6 +61,9 @@ void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g)
         plb_dev_free(gpu, g->dev_scaling[i]);
     }
     plb_dev_free(gpu, g->dev_offsets);
+    plb_dev_free(gpu, g->dev_h274_db);
+    for (int i = 0; i < H274_RING; i++)
+        plb_dev_free(gpu, g->dev_h274[i]);
     free(g->offsets);
     free(g);
 }
@@ -95,11 +106,25 @@ static bool needs_av1(const struct pl_film_grain_params *params)
     return false;
 }
 
+// film_grain_h274.c:127-143
+static bool needs_h274(const struct pl_film_grain_params *params)
+{
+    const struct pl_h274_grain_data *data = &params->data.params.h274;
+    if (data->model_id != 0)
+        return false;
+    for (int i = 0; i < 3; i++) {
+        const enum pl_channel ch = channel_map(i, params);
+        if (ch >= 0 && ch < 3 && data->component_model_present[ch])
+            return true;
+    }
+    return false;
+}
+
 bool pl_needs_film_grain(const struct pl_film_grain_params *params)
 {
     switch (params->data.type) {
     case PL_FILM_GRAIN_AV1:  return needs_av1(params);
-    case PL_FILM_GRAIN_H274: return true; // decided (and rejected) in pl_shader_film_grain
+    case PL_FILM_GRAIN_H274: return needs_h274(params);
     default:                 return false;
     }
 }
@@ -466,6 +491,162 @@ static bool shader_fg_av1(pl_shader sh, struct plb_grain_obj *obj,
     return true;
 }
 
+
+// ---- H.274 / SMPTE RDD 5 (film_grain_h274.c) ------------------------------------------------
+// The grain data base: for every pair of cut-off frequencies (h, v) in 0..12 a 64x64 block of
+// band-limited Gaussian noise: LUT noise in the (4h+12)x(4v+12) low-frequency corner, inverse
+// 64x64 integer transform (R64T), horizontal-edge attenuation. Integer arithmetic throughout;
+// the final value is int / 255.0 rounded to float (film_grain_h274.c:33-105).
+static void h274_slice(float *out, size_t stride, int h, int v, int8_t (*grain)[64],
+                       int16_t (*tmp)[64])
+{
+    const int freq_h = ((h + 3) << 2) - 1, freq_v = ((v + 3) << 2) - 1;
+    uint32_t lfsr = plb_h274_seed[h + v * 13];
+    // column-major start image: grain[x][y]
+    for (int y = 0; y <= freq_v; y++) {
+        for (int x = 0; x <= freq_h; x += 4) {
+            const int at = lfsr % 2048;
+            for (int k = 0; k < 4; k++)
+                grain[x + k][y] = plb_h274_gaussian[at + k];
+            // x^31 + x^3 + 1
+            const uint32_t fb = 1u ^ (lfsr >> 2) ^ (lfsr >> 30);
+            lfsr = (lfsr << 1) | (fb & 1u);
+        }
+    }
+    grain[0][0] = 0;
+    for (int y = 0; y < 64; y++) {
+        for (int x = 0; x <= freq_h; x++) {
+            int32_t acc = 0;
+            for (int p = 0; p <= freq_v; p++)
+                acc += plb_h274_r64t[y][p] * grain[x][p];
+            tmp[y][x] = (acc + 128) >> 8;
+        }
+    }
+    for (int y = 0; y < 64; y++) {
+        for (int x = 0; x < 64; x++) {
+            int32_t acc = 0;
+            for (int p = 0; p <= freq_h; p++)
+                acc += tmp[y][p] * plb_h274_r64t[x][p];
+            acc = (acc + 128) >> 8;
+            grain[y][x] = PLB_CLAMP(acc, -127, 127);
+        }
+    }
+    static const uint8_t attenuate[13] = { 64, 71, 77, 84, 90, 96, 103, 109, 116, 122, 128, 128, 128 };
+    for (int y = 0; y < 64; y++, out += stride) {
+        const bool edge = (y & 7) == 0 || (y & 7) == 7;
+        for (int x = 0; x < 64; x++) {
+            const int g = edge ? (grain[y][x] * attenuate[v]) >> 7 : grain[y][x];
+            out[x] = g / 255.0;
+        }
+    }
+}
+
+// fill_grain_lut (film_grain_h274.c:107-125): slice (h, v) starts at row 64h, column 64v
+static void h274_database(float *db)
+{
+    int8_t (*grain)[64] = malloc(64 * 64);
+    int16_t (*tmp)[64] = malloc(64 * 64 * sizeof(int16_t));
+    for (int h = 0; h < 13 && grain && tmp; h++) {
+        for (int v = 0; v < 13; v++)
+            h274_slice(db + (size_t) (h * 64) * H274_DB + v * 64, H274_DB, h, v, grain, tmp);
+    }
+    free(grain);
+    free(tmp);
+}
+
+bool pl_cuda_h274_database_host(float *out)
+{
+    if (!out)
+        return false;
+    h274_database(out);
+    return true;
+}
+
+// pl_shader_fg_h274 (film_grain_h274.c:145-315)
+static bool shader_fg_h274(pl_shader sh, struct plb_grain_obj *obj,
+                           const struct pl_film_grain_params *params)
+{
+    pl_gpu gpu = sh->params.gpu;
+    const struct pl_h274_grain_data *data = &params->data.params.h274;
+    const int tex_w = params->tex->params.w, tex_h = params->tex->params.h;
+    if (!obj->dev_h274_db) {
+        float *db = malloc(sizeof(float) * H274_DB * H274_DB);
+        if (!db)
+            return false;
+        h274_database(db);
+        const bool ok = upload_f(gpu, &obj->dev_h274_db, db, (size_t) H274_DB * H274_DB);
+        free(db);
+        if (!ok) {
+            plb_shader_fail(sh, "H.274 film grain: uploading the grain data base failed");
+            return false;
+        }
+    }
+
+    struct plb_h274_plane *rec = calloc(1, H274_REC_SIZE);
+    if (!rec)
+        return false;
+    rec->db = obj->dev_h274_db;
+    rec->seed = (unsigned int) params->data.seed;
+    rec->tex_scale = pl_color_repr_normalize(params->repr);
+    rec->scale_factor = 1.0 / (1 << (data->log2_scale_factor + 6));
+    int niv = 0;
+    for (int idx = 0; idx < params->components; idx++) {
+        const enum pl_channel c = channel_map(idx, params);
+        if (c == PL_CHANNEL_NONE || !data->component_model_present[c])
+            continue;
+        const int e = rec->nent++;
+        rec->ent[e].channel = c;
+        rec->ent[e].first = niv;
+        const int count = PLB_MIN((int) data->num_intensity_intervals[c], 256);
+        for (int i = 0; i < count; i++, niv++) {
+            struct plb_h274_interval *iv = &rec->iv[niv];
+            iv->lo = data->intensity_interval_lower_bound[c][i] / 255.0;
+            iv->hi = data->intensity_interval_upper_bound[c][i] / 255.0;
+            const uint8_t nv = data->num_model_values[c];
+            uint8_t h = nv > 1 ? data->comp_model_value[c][i][1] : 8;
+            uint8_t v = nv > 2 ? data->comp_model_value[c][i][2] : h;
+            h = PLB_CLAMP(h, 2, 14) - 2;
+            v = PLB_CLAMP(v, 2, 14) - 2;
+            int16_t scale = data->comp_model_value[c][i][0];
+            if (c > 0 && pl_color_system_is_ycbcr_like(params->repr->sys))
+                scale >>= 1; // chroma gets half the strength
+            iv->value = (uint32_t) (uint16_t) scale << 16 | h << 8 | v;
+        }
+        rec->ent[e].count = count;
+    }
+    const int slot = obj->h274_next++ % H274_RING;
+    if (!obj->dev_h274[slot])
+        obj->dev_h274[slot] = plb_dev_alloc(gpu, H274_REC_SIZE);
+    const size_t used = sizeof(*rec) + niv * sizeof(struct plb_h274_interval);
+    const bool ok = obj->dev_h274[slot] && plb_dev_upload(gpu, obj->dev_h274[slot], rec, used);
+    free(rec);
+    if (!ok) {
+        plb_shader_fail(sh, "H.274 film grain: uploading the parameters failed");
+        return false;
+    }
+
+    sh->src = PLB_SRC_PLANES;
+    sh->is_compute = true;
+    sh->wg_w = sh->wg_h = 8;
+    sh->out_w = tex_w;
+    sh->out_h = tex_h;
+    plb_shader_describe(sh, "H.274 film grain");
+    plb_shader_use_tex(sh, params->tex);
+    struct plb_plane_src *pl = &sh->px.planes[0];
+    memset(pl, 0, sizeof(*pl));
+    sh->px.nplanes = 1;
+    sh->px.init[3] = 1.0f;
+    pl->kind = PLB_PLANE_GRAIN_H274;
+    pl->tex = plb_tex_priv(params->tex)->d;
+    pl->rect = (pl_rect2df) { 0, 0, tex_w, tex_h };
+    pl->scale = 1.0f;
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k;
+    pl->h274 = obj->dev_h274[slot];
+    sh->px.coord_mode = PLB_COORD_EXACT;
+    return true;
+}
+
 bool pl_shader_film_grain(pl_shader sh, pl_shader_obj *grain_state,
                           const struct pl_film_grain_params *params)
 {
@@ -478,16 +659,16 @@ bool pl_shader_film_grain(pl_shader sh, pl_shader_obj *grain_state,
                         "test with `pl_needs_film_grain` first!");
         return false;
     }
-    if (params->data.type == PL_FILM_GRAIN_H274) {
-        plb_shader_fail(sh, "H.274 film grain is not implemented on the CUDA backend yet");
-        return false;
-    }
     struct plb_grain_obj **pobj = (struct plb_grain_obj **) plb_shader_obj(sh, grain_state, PLB_OBJ_GRAIN);
     if (!pobj)
         return false;
     if (!*pobj)
         *pobj = calloc(1, sizeof(**pobj));
-    return *pobj && shader_fg_av1(sh, *pobj, params);
+    if (!*pobj)
+        return false;
+    if (params->data.type == PL_FILM_GRAIN_H274)
+        return shader_fg_h274(sh, *pobj, params);
+    return shader_fg_av1(sh, *pobj, params);
 }
 
 // renderer.c:1355-1429 `plane_film_grain`

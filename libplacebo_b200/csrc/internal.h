@@ -262,6 +262,24 @@ struct plb_av1_plane {
     int luma_comp;             // else component of the separate luma texture
 };
 
+// H.274 / SMPTE RDD 5 film grain for one plane pass (film_grain_h274.c:145-315). One device
+// record per recorded pass: this header followed by the intensity intervals of all entries.
+struct plb_h274_interval {
+    float lo, hi;              // bounds / 255
+    uint32_t value;            // scale << 16 | h << 8 | v
+};
+struct plb_h274_plane {
+    const float *db;           // (13*64)^2 grain data base, row length 13*64
+    int nent;                  // texture components that receive grain (in component order)
+    uint32_t seed;
+    float tex_scale, scale_factor;
+    struct {
+        int channel;           // PL_CHANNEL_*: indexes the colour vector and the pcg3d lanes
+        int first, count;      // its intervals in iv[]
+    } ent[3];
+    struct plb_h274_interval iv[];
+};
+
 struct plb_plane_src {
     int kind;
     struct plb_tex_desc tex;
@@ -277,6 +295,7 @@ struct plb_plane_src {
     // grain
     struct plb_av1_plane av1;
     struct plb_tex_desc luma;  // AV1 chroma needs the luma plane
+    const struct plb_h274_plane *h274; // device copy (rarely used: kept out of line)
 };
 
 // Dolby Vision reshaping tables as the reference packs them for the GPU

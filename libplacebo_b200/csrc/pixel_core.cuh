@@ -200,6 +200,72 @@ PLB_DEV void plb_grain_av1(const plb_plane_src &pl, int gx, int gy, float color[
     }
 }
 
+// pl_shader_fg_h274 (film_grain_h274.c:145-315). The reference runs 8x8 work groups: the block
+// mean of each component is a subgroupAdd over the (two) 32-wide subgroups of the group, merged
+// through an integer atomicAdd of int(sum * 1e7). GLSL leaves the order of subgroupAdd open; here
+// (and in the oracle) it is DEFINED as ascending invocation index. Every thread evaluates the
+// mean of its own block from the (L1-resident) texels, which needs no cross-thread exchange.
+PLB_DEV void plb_grain_h274(const plb_plane_src &pl, int gx, int gy, float color[4])
+{
+    const plb_h274_plane &g = *pl.h274;
+    const float4 t = plb_load_clamped(pl.tex, gx, gy);
+    color[0] = g.tex_scale * t.x;
+    color[1] = g.tex_scale * t.y;
+    color[2] = g.tex_scale * t.z;
+    color[3] = g.tex_scale * t.w;
+    const int bx = gx >> 3, by = gy >> 3;
+    // pcg3d of (seed, block pair)
+    uint32_t px = g.seed, py = (uint32_t) (bx >> 1), pz = (uint32_t) (by >> 1);
+    px = px * 1664525u + 1013904223u; py = py * 1664525u + 1013904223u; pz = pz * 1664525u + 1013904223u;
+    px += py * pz; py += pz * px; pz += px * py;
+    px ^= px >> 16; py ^= py >> 16; pz ^= pz >> 16;
+    px += py * pz; py += pz * px; pz += px * py;
+    const uint32_t pcg[3] = { px, py, pz };
+    for (int i = 0; i < g.nent; i++) {
+        const int c = g.ent[i].channel;
+        // block mean: two subgroups of 32 invocations (4 rows each), ascending order
+        int isum = 0;
+        #pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            float s = 0.0f;
+            for (int r = 0; r < 4; r++) {
+                for (int col = 0; col < 8; col++) {
+                    const int x = 8 * bx + col, y = 8 * by + 4 * half + r;
+                    float v = 0.0f; // texelFetch outside the image: robust-access zero
+                    if (x < pl.tex.w && y < pl.tex.h) {
+                        const float4 q = plb_load(pl.tex, x, y);
+                        const float qv[4] = { q.x, q.y, q.z, q.w };
+                        v = g.tex_scale * qv[c];
+                    }
+                    s += v / 64.0f;
+                }
+            }
+            isum += (int) (s * 10000000.0f);
+        }
+        const float avg = (float) isum / 10000000.0f;
+        uint32_t val = 0u;
+        const plb_h274_interval *iv = g.iv + g.ent[i].first;
+        for (int k = g.ent[i].count - 1; k >= 0; k--) {
+            // the GLSL is an if / else-if chain in ascending k: the first match wins
+            if (avg >= iv[k].lo && avg <= iv[k].hi)
+                val = iv[k].value;
+        }
+        uint32_t ox = (val & 0xFF00u) >> 2, oy = (val & 0xFFu) << 6;
+        float scale = g.scale_factor * (float) (int) (val >> 16);
+        const uint32_t rnd = pcg[c];
+        ox += (rnd >> 16) % 52u;
+        oy += (rnd & 0xFFFFu) % 56u;
+        ox &= 0xFFFCu;
+        oy &= 0xFFF8u;
+        if ((rnd & 1u) == 1u)
+            scale = -scale;
+        ox += 8u * (uint32_t) (bx & 1) + (uint32_t) (gx & 7);
+        oy += 8u * (uint32_t) (by & 1) + (uint32_t) (gy & 7);
+        const float grain = __ldg(g.db + (size_t) oy * (13 * 64) + ox);
+        color[c] = __fmaf_rn(scale, grain, color[c]);
+    }
+}
+
 // Sample plane `pl` at output pixel (gx, gy) -> vec4 (already multiplied by its scale)
 PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
                               uint32_t frame_index, float out[4])
@@ -214,6 +280,13 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
     out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
     if (pl.kind == PLB_PLANE_DEBAND)
         plb_deband(pl, cc, posx, posy, gx, gy, frame_index, out);
+    if (pl.kind == PLB_PLANE_GRAIN_H274) {
+        plb_grain_h274(pl, gx, gy, out);
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            out[k] *= pl.scale;
+        return;
+    }
     if (pl.kind == PLB_PLANE_GRAIN_AV1) {
         plb_grain_av1(pl, gx, gy, out);
         #pragma unroll

@@ -378,3 +378,43 @@ HV_API int hvs_av1_grain(const char *dir, int w, int h, int plane, unsigned seed
     pl_tex_destroy(hv_gpu, &luma);
     return ret;
 }
+
+// H.274 film grain on one plane with the reference test fixture (tests/utils.h:263-277):
+// `fmt` r16 / rg16 / rgba16 plane of `comps` components mapped to channels map[0..comps).
+// The dump holds the grain data base (desc 0) and the uniforms (seed, scale_factor, bounds,
+// comp_model_value) the shader was given.
+HV_API int hvs_h274_grain(const char *dir, const char *fmt, int w, int h, int comps,
+                          const int *map, unsigned seed, int bit_depth, int levels, int sys)
+{
+    hv_init();
+    struct pl_film_grain_data data = {
+        .type = PL_FILM_GRAIN_H274,
+        .seed = seed,
+        .params.h274 = h274_grain_data,
+    };
+    struct pl_color_repr repr = {
+        .sys = sys,
+        .levels = levels,
+        .bits = { 16, bit_depth, 0 },
+    };
+    pl_tex tex = placeholder(fmt, w, h);
+    struct pl_film_grain_params par = {
+        .data = data,
+        .tex = tex,
+        .repr = &repr,
+        .components = comps,
+    };
+    for (int i = 0; i < comps; i++)
+        par.component_mapping[i] = map[i];
+    int ret = -3;
+    if (pl_needs_film_grain(&par)) {
+        pl_shader_obj state = NULL;
+        pl_shader sh = pl_shader_alloc(hv_log, pl_shader_params( .gpu = hv_gpu ));
+        bool ok = pl_shader_film_grain(sh, &state, &par);
+        ret = ok && finish(sh, dir) ? 0 : -2;
+        pl_shader_free(&sh);
+        pl_shader_obj_destroy(&state);
+    }
+    pl_tex_destroy(hv_gpu, &tex);
+    return ret;
+}

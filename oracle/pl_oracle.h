@@ -253,6 +253,22 @@ struct orc_av1_grain_params {
 ORC_API void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *luma,
                            const struct orc_av1_grain_params *p, float *dst);
 
+// --- H.274 film grain (src/shaders/film_grain_h274.c) --------------------------------------
+struct orc_h274_grain_params {
+    const float *db;           // 832 x 832 grain data base (fill_grain_lut, :107-125)
+    int db_w;
+    uint32_t seed;
+    float scale;               // pl_color_repr_normalize
+    float scale_factor;        // 1 / (1 << (log2_scale_factor + 6))
+    int num_entries;           // texture components with component_model_present, in order
+    int channel[3];            // channel_map(idx)
+    int num_intervals[3];
+    const float *lower[3], *upper[3];   // bounds / 255
+    const uint32_t *value[3];           // scale << 16 | h << 8 | v  (:276-282)
+};
+ORC_API void orc_h274_grain(const struct orc_tex *plane, const struct orc_h274_grain_params *p,
+                            float *dst);
+
 // --- double-precision ideal resampler (config C1) ----------------------------------------
 // weight callback evaluates pl_filter_sample for distance x (from the reference via harvest)
 typedef double (*orc_weight_fn)(void *priv, double x);

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE — CPU oracle, never linked into the product.
 //
+// pl_shader_fg_h274 (src/shaders/film_grain_h274.c:145-315) is restated at the end of the file.
 // pl_shader_fg_av1, the per-pixel GLSL of src/shaders/film_grain_av1.c:827-1013, restated in C.
 // The LUTs (grain templates, block offsets, scaling functions) are INPUTS: tests feed the ones
 // harvested from the real reference shader (oracle/harvest.c hvs_av1_grain), so that only the
@@ -119,6 +120,88 @@ void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *luma,
             float *o = dst + ((size_t) gy * w + gx) * 4;
             for (int k = 0; k < 4; k++)
                 o[k] = color[k];
+        }
+    }
+}
+
+
+// ---- H.274 / SMPTE RDD 5 (src/shaders/film_grain_h274.c:145-315) ---------------------------
+// The shader runs 8x8 work groups on a device with 32-wide subgroups (NVIDIA: subgroup k holds
+// local invocation indices 32k .. 32k+31, i.e. rows 4k .. 4k+3 of the group). Per component:
+//   avg = color[c] / 64; avg = subgroupAdd(avg); one invocation per subgroup does
+//   atomicAdd(group_sum, int(avg * 10000000.0)); avg = float(group_sum) / 10000000.0   (:232-246)
+// GLSL leaves the association order of subgroupAdd open; this restatement fixes it as ascending
+// invocation index. Invocations outside the texture read (0,0,0,0) (robust access).
+// `db` is the 832x832 grain data base (harvested from the reference's sh_lut fill, :107-125),
+// fetched as db(offset) = texel (x = offset.x, y = offset.y).
+void orc_h274_grain(const struct orc_tex *plane, const struct orc_h274_grain_params *p, float *dst)
+{
+    const int w = plane->w, h = plane->h;
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < h; gy++) {
+        for (int gx = 0; gx < w; gx++) {
+            const int wx = gx / 8, wy = gy / 8;
+            const float *t = plane->data + ((size_t) gy * w + gx) * plane->comps;
+            float color[4] = { 0, 0, 0, 1 };
+            for (int k = 0; k < plane->comps; k++)
+                color[k] = t[k];
+            for (int k = 0; k < 4; k++)
+                color[k] = p->scale * color[k];
+            // pcg3d :197-206
+            uint32_t pcg[3] = { p->seed, (uint32_t) wx / 2u, (uint32_t) wy / 2u };
+            for (int k = 0; k < 3; k++)
+                pcg[k] = pcg[k] * 1664525u + 1013904223u;
+            pcg[0] += pcg[1] * pcg[2];
+            pcg[1] += pcg[2] * pcg[0];
+            pcg[2] += pcg[0] * pcg[1];
+            for (int k = 0; k < 3; k++)
+                pcg[k] ^= pcg[k] >> 16;
+            pcg[0] += pcg[1] * pcg[2];
+            pcg[1] += pcg[2] * pcg[0];
+            pcg[2] += pcg[0] * pcg[1];
+
+            for (int e = 0; e < p->num_entries; e++) {
+                const int c = p->channel[e];
+                int group_sum = 0;
+                for (int sg = 0; sg < 2; sg++) {
+                    float sum = 0.0f;
+                    for (int li = 32 * sg; li < 32 * sg + 32; li++) {
+                        const int x = 8 * wx + (li & 7), y = 8 * wy + (li >> 3);
+                        float v[4] = { 0, 0, 0, 0 };
+                        if (x < w && y < h) {
+                            const float *q = plane->data + ((size_t) y * w + x) * plane->comps;
+                            v[3] = 1.0f;
+                            for (int k = 0; k < plane->comps; k++)
+                                v[k] = q[k];
+                        }
+                        sum += (p->scale * v[c]) / 64.0f;
+                    }
+                    group_sum += (int) (sum * 10000000.0f);
+                }
+                const float avg = (float) group_sum / 10000000.0f;
+                uint32_t val = 0u;
+                for (int i = 0; i < p->num_intervals[e]; i++) {
+                    if (avg >= p->lower[e][i] && avg <= p->upper[e][i]) {
+                        val = p->value[e][i];
+                        break;
+                    }
+                }
+                uint32_t ox = (val & 0xFF00u) >> 2, oy = (val & 0xFFu) << 6;
+                float scale = p->scale_factor * (float) (int) (val >> 16);
+                const uint32_t rnd = pcg[c];
+                ox += (rnd >> 16) % 52u;
+                oy += (rnd & 0xFFFFu) % 56u;
+                ox &= 0xFFFCu;
+                oy &= 0xFFF8u;
+                if ((rnd & 1u) == 1u)
+                    scale = -scale;
+                ox += 8u * ((uint32_t) wx % 2u) + (uint32_t) (gx % 8);
+                oy += 8u * ((uint32_t) wy % 2u) + (uint32_t) (gy % 8);
+                const float grain = p->db[(size_t) oy * p->db_w + ox];
+                color[c] = fmaf(scale, grain, color[c]);
+            }
+            for (int k = 0; k < 4; k++)
+                dst[((size_t) gy * w + gx) * 4 + k] = color[k];
         }
     }
 }

@@ -397,7 +397,7 @@ done:
  *       [3] dither (0 off, 1 blue noise default, 2 ordered LUT, 3 ordered fixed, 4 white)
  *       [4] colour map preset (0 default, 1 hq without contrast recovery)  [5] chroma location
  *       [6] sigmoid  [7] frame index (-1: renderer counts)  [8] error diffusion kernel idx+1
- *       [9] tone fn idx+1  [10] gamut fn idx+1 [11] temporal dither [12] film grain (1 = AV1 fixture)
+ *       [9] tone fn idx+1  [10] gamut fn idx+1 [11] temporal dither [12] film grain (1 = AV1 fixture, 2 = + overlap, 3 = H.274 fixture)
  *       [13] grain seed
  */
 static struct pl_av1_grain_data shim_av1_fixture(void);
@@ -430,7 +430,22 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
             .component_mapping = { 0, 1, 2 },
         };
     }
-    if (opts[12]) {
+    if (opts[12] == 3) {
+        /* the reference's H.274 fixture (src/tests/utils.h:263-277): luma only */
+        static const uint8_t lo = 10, hi = 250;
+        static const int16_t vals[6] = { 16, 12, 14 };
+        image.film_grain.type = PL_FILM_GRAIN_H274;
+        image.film_grain.seed = (uint64_t) opts[13];
+        image.film_grain.params.h274 = (struct pl_h274_grain_data) {
+            .log2_scale_factor = 2,
+            .component_model_present = { true },
+            .num_intensity_intervals = { 1 },
+            .num_model_values = { 3 },
+            .intensity_interval_lower_bound = { &lo },
+            .intensity_interval_upper_bound = { &hi },
+            .comp_model_value = { &vals },
+        };
+    } else if (opts[12]) {
         image.film_grain.type = PL_FILM_GRAIN_AV1;
         image.film_grain.seed = (uint64_t) opts[13];
         image.film_grain.params.av1 = shim_av1_fixture();
@@ -561,6 +576,49 @@ API int shim_film_grain(struct shim_ctx *c, void *tex, void *luma_tex, void *dst
         return -1;
     }
     return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst )) ? 0 : -2;
+}
+
+/* pl_shader_film_grain (H.274) on one plane -> dst. The model arrives flat: per channel up to 8
+ * intensity intervals, `lower`/`upper` [3][8], `values` [3][8][6]. */
+API int shim_film_grain_h274(struct shim_ctx *c, void *tex, void *dst, int comps, const int *map,
+                             unsigned seed, int color_depth, int levels, int sys, int log2_scale,
+                             const int *present, const int *nint, const int *nvals,
+                             const uint8_t *lower, const uint8_t *upper, const int16_t *values,
+                             int state_slot)
+{
+    struct pl_color_repr repr = { .sys = sys, .levels = levels, .bits = { 16, color_depth, 0 } };
+    struct pl_film_grain_params par = {
+        .data = { .type = PL_FILM_GRAIN_H274, .seed = seed },
+        .tex = tex,
+        .repr = &repr,
+        .components = comps,
+    };
+    struct pl_h274_grain_data *d = &par.data.params.h274;
+    d->log2_scale_factor = log2_scale;
+    for (int ch = 0; ch < 3; ch++) {
+        d->component_model_present[ch] = present[ch];
+        d->num_intensity_intervals[ch] = nint[ch];
+        d->num_model_values[ch] = nvals[ch];
+        d->intensity_interval_lower_bound[ch] = lower + 8 * ch;
+        d->intensity_interval_upper_bound[ch] = upper + 8 * ch;
+        d->comp_model_value[ch] = (const int16_t (*)[6]) (values + 48 * ch);
+    }
+    for (int i = 0; i < comps; i++)
+        par.component_mapping[i] = map[i];
+    if (!pl_needs_film_grain(&par))
+        return 1;
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    if (!pl_shader_film_grain(sh, &c->objs.grain[state_slot & 1], &par)) {
+        pl_dispatch_abort(c->dp, &sh);
+        return -1;
+    }
+    return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst )) ? 0 : -2;
+}
+
+/* host-only: the H.274 grain data base (no GPU needed) */
+API int shim_h274_database(float *out)
+{
+    return pl_cuda_h274_database_host(out) ? 0 : -1;
 }
 
 API int shim_math_eval(struct shim_ctx *c, int fn, const float *a, const float *b, float *out,

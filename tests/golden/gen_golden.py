@@ -13,6 +13,7 @@ Contents
   gamut.npz       every 8th hue plane of the pl_gamut_map_generate 3DLUT (48x32x256), perceptual BT.2020 -> BT.709
   dither.npz      blue noise 64x64 (fresh-process result) and Bayer 64x64
   color.npz       pl_color_repr_decode matrices, raw primaries, RGB<->XYZ / LMS matrices
+  h274_db.npz     the 832x832 H.274 grain data base (as int8 = value * 255)
   av1_grain.npz   LUTs uploaded by the real pl_shader_film_grain for the reference's fixture
 """
 import ctypes as C
@@ -94,6 +95,13 @@ def main():
                 dt = np.uint32 if fl[4] == "r32u" else np.float32
                 g[f"plane{plane}_desc{fl[1]}"] = np.fromfile(os.path.join(d, f"desc_{fl[1]}.bin"), dt)
     np.savez_compressed(os.path.join(HERE, "av1_grain.npz"), **g)
+    # ---- H.274 grain data base filled by the real sh_lut callback (values are n / 255)
+    sys.path.insert(0, os.path.join(T.ROOT, "tests"))
+    from test_grain_tables import harvest_h274
+    db, _ = harvest_h274()
+    q = np.rint(db.astype(np.float64) * 255).astype(np.int8)
+    assert np.array_equal((q.astype(np.float64) / 255.0).astype(np.float32), db)
+    np.savez_compressed(os.path.join(HERE, "h274_db.npz"), db_times_255=q)
     print("golden fixtures written to", HERE)
 
 

@@ -187,7 +187,26 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         ctex, cscale = UVf, float(norm)
 
     # ---- film grain (AV1), per plane after the optional debanding (renderer.c:1355-1429)
-    if film_grain is not None:
+    if film_grain is not None and film_grain[1] == "h274":
+        # the reference's H.274 fixture models luma only: the chroma planes need no pass
+        # (pl_needs_film_grain, film_grain_h274.c:127-143)
+        from test_grain_tables import harvest_h274
+        db, _ = harvest_h274()
+        if deband:
+            ltex, lscale = orc.store_round(luma[:H, :W, :1], 0), 1.0
+        else:
+            ltex, lscale = Yf, float(norm)
+        hp = T.OrcH274Grain()
+        lo, hi = np.array([10 / 255.0], f32), np.array([250 / 255.0], f32)
+        val = np.array([16 << 16 | 10 << 8 | 12], np.uint32)
+        hp.db, hp.db_w, hp.seed = T.fp(db), 832, film_grain[0]
+        hp.scale, hp.scale_factor = lscale, 2.0 ** -8
+        hp.num_entries, hp.channel[0], hp.num_intervals[0] = 1, 0, 1
+        hp.lower[0], hp.upper[0] = T.fp(lo), T.fp(hi)
+        hp.value[0] = val.ctypes.data_as(C.POINTER(C.c_uint32))
+        lg = orc.h274_grain(ltex, hp)[..., 0]
+        luma_v = np.pad(lg, ((0, ext[1] - H), (0, ext[0] - W)), mode="edge")
+    elif film_grain is not None:
         seed, overlap = film_grain
         depth = img.bits[1]
         keep = []

@@ -329,6 +329,13 @@ class OrcAv1Grain(C.Structure):
                 ("uv_mult_luma", C.c_float * 3), ("uv_offset", C.c_float * 3), ("luma_comp", C.c_int)]
 
 
+class OrcH274Grain(C.Structure):
+    _fields_ = [("db", FP), ("db_w", C.c_int), ("seed", C.c_uint32), ("scale", C.c_float),
+                ("scale_factor", C.c_float), ("num_entries", C.c_int), ("channel", C.c_int * 3),
+                ("num_intervals", C.c_int * 3), ("lower", FP * 3), ("upper", FP * 3),
+                ("value", C.POINTER(C.c_uint32) * 3)]
+
+
 def av1_fixture():
     sh = shim()
     sh.shim_av1_fixture_ptr.restype = C.c_void_p
@@ -511,6 +518,13 @@ class Oracle:
         tl, keep2 = _tex(luma) if luma is not None else (None, None)
         out = np.zeros((keep.shape[0], keep.shape[1], 4), f32)
         self.lib.orc_av1_grain(C.byref(t), C.byref(tl) if tl is not None else None, C.byref(params), fp(out))
+        return out
+
+    def h274_grain(self, plane, params):
+        """plane: HxWxC float32 texel values; returns HxWx4."""
+        t, keep = _tex(plane)
+        out = np.zeros((keep.shape[0], keep.shape[1], 4), f32)
+        self.lib.orc_h274_grain(C.byref(t), C.byref(params), fp(out))
         return out
 
     def dovi_reshape(self, rgba, meta):

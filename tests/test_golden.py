@@ -81,3 +81,11 @@ def test_av1_grain_tables():
     assert np.array_equal(gcb, uv[:, 0]) and np.array_equal(gcr, uv[:, 1])
     assert np.array_equal(off_c.ravel(), g["plane1_desc1"])
     assert np.array_equal(sc_c[1], g["plane1_desc2"]) and np.array_equal(sc_c[2], g["plane1_desc3"])
+
+
+def test_h274_grain_database():
+    """The 169 band-limited noise blocks of SMPTE RDD 5 as the reference's sh_lut fill callback
+    produced them (film_grain_h274.c:33-125); golden stores value * 255 as int8."""
+    from test_grain_tables import product_h274_db
+    want = (load("h274_db.npz")["db_times_255"].astype(np.float64) / 255.0).astype(np.float32)
+    assert np.array_equal(product_h274_db().view(np.uint32), want.view(np.uint32))

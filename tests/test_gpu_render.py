@@ -29,7 +29,10 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
         opts[7] = frame_index
         opts[8] = T.ED_KERNELS.index(error_diffusion) + 1 if error_diffusion else 0
         if grain is not None:
-            opts[12], opts[13] = 2 if grain[1] else 1, grain[0]
+            if grain[1] == "h274":
+                opts[12], opts[13] = 3, grain[0]
+            else:
+                opts[12], opts[13] = 2 if grain[1] else 1, grain[0]
         opts[9] = T.TONE_FNS.index(tone_fn) + 1 if tone_fn else 0
         opts[10] = T.GAMUT_FNS.index(gamut_fn) + 1 if gamut_fn else 0
         peak_out = np.zeros(2, T.f32)

@@ -56,3 +56,37 @@ def test_av1_tables_match_reference(seed, depth):
     assert np.array_equal(off_c, np.fromfile(d[1][3], np.uint32).reshape(d[1][2], d[1][1]))
     assert np.array_equal(sc_c[1], np.fromfile(d[2][3], np.float32))
     assert np.array_equal(sc_c[2], np.fromfile(d[3][3], np.float32))
+
+
+# ---- H.274 / SMPTE RDD 5 grain data base (film_grain_h274.c:33-125) ------------------------
+def harvest_h274(fmt=b"r16", w=64, h=64, comps=1, cmap=(0, 0, 0, 0), seed=1234, depth=10, levels=1, sys_=2):
+    """(data base 832x832 float32, {uniform name: values}) of the real pl_shader_film_grain
+    (H.274) for the reference's fixture (src/tests/utils.h:263-277)."""
+    hv = C.CDLL(HARVEST)
+    d = tempfile.mkdtemp()
+    m = (C.c_int * 4)(*cmap)
+    rc = hv.hvs_h274_grain(d.encode(), fmt, w, h, comps, m, seed, depth, levels, sys_)
+    if rc == -3:
+        return None, None
+    assert rc == 0
+    uni = []
+    for line in open(os.path.join(d, "meta.txt")):
+        f = line.split()
+        if f and f[0] == "var":
+            uni.append([float(x) for x in f[f.index(":") + 1:]])
+    return np.fromfile(os.path.join(d, "desc_0.bin"), np.float32).reshape(832, 832), uni
+
+
+def product_h274_db():
+    db = np.zeros((832, 832), np.float32)
+    assert T.shim().shim_h274_database(db.ctypes.data_as(C.c_void_p)) == 0
+    return db
+
+
+def test_h274_database_matches_reference():
+    ref, uni = harvest_h274()
+    got = product_h274_db()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # the uniforms of the fixture: scale_factor 2^-8, seed, bounds / 255, scale<<16 | h<<8 | v
+    assert uni[0] == [2.0 ** -8] and uni[1] == [1234.0]
+    assert np.allclose(uni[2], [10 / 255, 250 / 255], rtol=1e-7) and uni[3] == [16 << 16 | 10 << 8 | 12]
