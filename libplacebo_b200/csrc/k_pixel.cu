@@ -13,7 +13,10 @@ PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_pixel)
 
 #define PIX_TILE 32
 
-__global__ void __launch_bounds__(256)
+// MINB = resident CTAs per SM the register allocation is tuned for (3 -> 80 registers,
+// 4 -> 64 registers): selectable at run time for measurements (PLB_PIXEL_MINB).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_pixel(const __grid_constant__ plb_tail_args ap)
 {
     __shared__ plb_peak_smem ps;
@@ -197,7 +200,20 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
         grid.x = ((p->out_w + t.wg_w - 1) / t.wg_w * t.wg_w + PIX_TILE - 1) / PIX_TILE;
         grid.y = ((p->out_h + t.wg_h - 1) / t.wg_h * t.wg_h + PIX_TILE - 1) / PIX_TILE;
     }
-    k_pixel<<<grid, block, 0, STREAM(gpu)>>>(t);
+    static int minb;
+    if (!minb) {
+        const char *e = getenv("PLB_PIXEL_MINB");
+        const int v = e ? atoi(e) : 3;
+        minb = v >= 2 && v <= 5 ? v : 3;
+    }
+    if (minb == 5)
+        k_pixel<5><<<grid, block, 0, STREAM(gpu)>>>(t);
+    else if (minb == 4)
+        k_pixel<4><<<grid, block, 0, STREAM(gpu)>>>(t);
+    else if (minb == 2)
+        k_pixel<2><<<grid, block, 0, STREAM(gpu)>>>(t);
+    else
+        k_pixel<3><<<grid, block, 0, STREAM(gpu)>>>(t);
     plb_gpu_priv(gpu)->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel");
 }

@@ -195,8 +195,11 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
 
 // PURE: a resampling pass with nothing to merge and at most a light colour program (config
 // C2's main scaler: 1/scale + swizzle): register-resident tail and four-texel vector stores.
+#ifndef PLB_UP2_MINB
+#define PLB_UP2_MINB 1      // resident CTAs per SM the heavy-tail variants are register-tuned for
+#endif
 template <int NC, int R2_16, int XM, int YM, bool PURE = false>
-__global__ void __launch_bounds__(UP2_TX * UP2_TY)
+__global__ void __launch_bounds__(UP2_TX * UP2_TY, PURE ? 1 : PLB_UP2_MINB)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
 {
     __shared__ __align__(16) float tile[NC][UP2_TILE_H][UP2_TILE_WP];
