@@ -648,6 +648,80 @@ PLB_DEV void plb_run_light_ops(float c[4])
     }
 }
 
+// The same program applied to N pixels in one pass over the op list: the kind dispatch and the
+// swizzle predicates are launch-uniform and evaluated once per step instead of once per pixel;
+// the per-pixel arithmetic of each step is exactly that of plb_run_light_ops. `prog` may live
+// in the kernel parameters (constant bank) or in shared memory.
+template <int N>
+PLB_DEV void plb_run_light_ops_n(const plb_color_prog &prog, float c[N][4])
+{
+    #pragma unroll 1
+    for (int i = 0; i < prog.n; i++) {
+        const plb_color_op &op = prog.ops[i];
+        const int kind = op.kind;
+        if (kind == PLB_OP_SCALE) {
+            const float s = op.u.scale.s;
+            const bool wa = op.u.scale.with_alpha;
+            #pragma unroll
+            for (int p = 0; p < N; p++) {
+                c[p][0] *= s; c[p][1] *= s; c[p][2] *= s;
+                if (wa)
+                    c[p][3] *= s;
+            }
+        } else if (kind == PLB_OP_MATRIX) {
+            #pragma unroll
+            for (int p = 0; p < N; p++) {
+                plb_matv(op.u.matrix.m, c[p][0], c[p][1], c[p][2]);
+                if (op.u.matrix.has_c) {
+                    c[p][0] += op.u.matrix.c[0]; c[p][1] += op.u.matrix.c[1]; c[p][2] += op.u.matrix.c[2];
+                }
+            }
+        } else if (kind == PLB_OP_ROUND_FBO) {
+            #pragma unroll
+            for (int p = 0; p < N; p++) {
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    c[p][k] = plb_round_fbo(c[p][k], op.u.round_fbo.kind, op.u.round_fbo.bits);
+            }
+        } else if (kind == PLB_OP_ALPHA) {
+            const int from = op.u.alpha.from, to = op.u.alpha.to;
+            #pragma unroll
+            for (int p = 0; p < N; p++) {
+                if (to == PL_ALPHA_NONE && from == PL_ALPHA_UNKNOWN) {
+                    c[p][3] = 1.0f;
+                } else if (from == PL_ALPHA_INDEPENDENT && to == PL_ALPHA_PREMULTIPLIED) {
+                    c[p][0] *= c[p][3]; c[p][1] *= c[p][3]; c[p][2] *= c[p][3];
+                } else if (from == PL_ALPHA_PREMULTIPLIED && to != PL_ALPHA_PREMULTIPLIED) {
+                    if (c[p][3] > 1e-6f) {
+                        c[p][0] /= c[p][3]; c[p][1] /= c[p][3]; c[p][2] /= c[p][3];
+                    }
+                    if (to == PL_ALPHA_NONE)
+                        c[p][3] = 1.0f;
+                }
+            }
+        } else if (kind == PLB_OP_SWIZZLE) {
+            int sel[4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = op.u.swizzle.map[k];
+                sel[k] = (k < op.u.swizzle.comps && m >= 0) ? m : -1;
+            }
+            const bool fa = op.u.swizzle.force_alpha;
+            #pragma unroll
+            for (int p = 0; p < N; p++) {
+                const float o0 = c[p][0], o1 = c[p][1], o2 = c[p][2], o3 = c[p][3];
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float dflt = k == 3 ? 1.0f : 0.0f;
+                    c[p][k] = sel[k] < 0 ? dflt : sel[k] == 0 ? o0 : sel[k] == 1 ? o1 : sel[k] == 2 ? o2 : o3;
+                }
+                if (fa)
+                    c[p][3] = o3;
+            }
+        }
+    }
+}
+
 static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                                const plb_op_peak **peak_op, uint32_t *y_pq)
 {

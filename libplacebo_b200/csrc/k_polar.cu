@@ -195,11 +195,13 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
 
 // PURE: a resampling pass with nothing to merge and at most a light colour program (config
 // C2's main scaler: 1/scale + swizzle): register-resident tail and four-texel vector stores.
-#ifndef PLB_UP2_MINB
-#define PLB_UP2_MINB 1      // resident CTAs per SM the heavy-tail variants are register-tuned for
+#ifdef PLB_UP2_MINB          // resident CTAs per SM the heavy-tail variants are register-tuned for
+#define UP2_BOUNDS(PURE) __launch_bounds__(UP2_TX * UP2_TY, (PURE) ? 4 : PLB_UP2_MINB)
+#else
+#define UP2_BOUNDS(PURE) __launch_bounds__(UP2_TX * UP2_TY, (PURE) ? 4 : 3)
 #endif
 template <int NC, int R2_16, int XM, int YM, bool PURE = false>
-__global__ void __launch_bounds__(UP2_TX * UP2_TY, PURE ? 1 : PLB_UP2_MINB)
+__global__ void UP2_BOUNDS(PURE)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
 {
     __shared__ __align__(16) float tile[NC][UP2_TILE_H][UP2_TILE_WP];
@@ -208,8 +210,12 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     const int X0 = blockIdx.x * (UP2_TX * UP2_OX), Y0 = blockIdx.y * (UP2_TY * UP2_OY);
     const int col0 = X0 / 2 - 4, row0 = Y0 / 2 - 4;
 
-    plm_tables_init(); // published by the barrier after the tile staging
-    plb_tail_stage(a.tail);
+    // PURE passes never touch the transcendental tables and read the launch description
+    // straight from the kernel parameters (constant bank): nothing to stage but the tile.
+    if (!PURE) {
+        plm_tables_init(); // published by the barrier after the tile staging
+        plb_tail_stage(a.tail);
+    }
     // Stage the source tile (clamp-to-edge) as planar fp32
     for (int i = ty * UP2_TX + tx; i < UP2_TILE_H * UP2_TILE_WP; i += UP2_TX * UP2_TY) {
         const int r = i / UP2_TILE_WP, c = i - r * UP2_TILE_WP;
@@ -267,72 +273,93 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
         }
     }
 
-    const plb_tail_args &t = plb_s_tail;
     if (PURE) {
+        const plb_tail_args &t = a.tail;
         // launch-uniform: the usual identity component mapping needs no per-pixel selects
         const bool ident = t.src_map[0] == 0 && (NC < 2 || t.src_map[1] == 1) &&
                            (NC < 3 || t.src_map[2] == 2) && (NC < 4 || t.src_map[3] == 3);
+        const int gx = X0 + tx * UP2_OX;
+        if (gx >= t.out_w)
+            return;
         #pragma unroll
         for (int oyo = 0; oyo < UP2_OY; oyo++) {
             const int gy = Y0 + ty * UP2_OY + oyo;
-            const int gx = X0 + tx * UP2_OX;
-            if (gy >= t.out_h || gx >= t.out_w)
+            if (gy >= t.out_h)
                 continue;
-            float4 px4[UP2_OX];
+            float col[UP2_OX][4];
             #pragma unroll
-            for (int oxo = 0; oxo < UP2_OX; oxo++) {
-                const float norm = a.norm[oyo][oxo & 1];
+            for (int p = 0; p < UP2_OX; p++) {
+                const float norm = a.norm[oyo][p & 1];
                 float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
                 #pragma unroll
                 for (int k = 0; k < NC; k++)
-                    prim[k] = norm * acc[oyo][oxo][k];
-                float color[4] = { t.init[0], t.init[1], t.init[2], t.init[3] };
+                    prim[k] = norm * acc[oyo][p][k];
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    col[p][j] = t.init[j];
                 if (ident) {
                     #pragma unroll
                     for (int k = 0; k < NC; k++)
-                        color[k] = prim[k];
+                        col[p][k] = prim[k];
                 } else {
                     #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        // src_map is launch-uniform; the selects below stay in registers
                         const int m = t.src_map[k];
                         #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            color[j] = m == j ? prim[k] : color[j];
+                            col[p][j] = m == j ? prim[k] : col[p][j];
                     }
                 }
-                // directly sampled extra planes (e.g. the luma plane next to EWA-scaled chroma)
-                #pragma unroll 1
-                for (int i = 0; i < t.nplanes; i++) {
-                    const plb_plane_src &pl = t.planes[i];
-                    float posx, posy;
-                    plb_coord_pos(t.plane_cc[i], gx + oxo, gy, posx, posy);
-                    const float4 c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy)
-                                                : plb_tex_nearest(pl.tex, posx, posy);
-                    const float tmp[4] = { c4.x * pl.scale, c4.y * pl.scale, c4.z * pl.scale, c4.w * pl.scale };
+            }
+            // directly sampled extra planes (e.g. the luma plane next to EWA-scaled chroma)
+            #pragma unroll 1
+            for (int i = 0; i < t.nplanes; i++) {
+                const plb_plane_src &pl = t.planes[i];
+                const plb_coord &cc = t.plane_cc[i];
+                const bool direct = cc.ident && !pl.linear;
+                const float sc = pl.scale;
+                int8_t map[4];
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    map[k] = pl.map[k];
+                #pragma unroll
+                for (int p = 0; p < UP2_OX; p++) {
+                    float4 c4;
+                    if (direct) {
+                        c4 = plb_load_clamped(pl.tex, gx + p, gy);
+                    } else {
+                        float posx, posy;
+                        plb_coord_pos(cc, gx + p, gy, posx, posy);
+                        c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy)
+                                       : plb_tex_nearest(pl.tex, posx, posy);
+                    }
+                    const float tmp[4] = { c4.x * sc, c4.y * sc, c4.z * sc, c4.w * sc };
                     #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int m = pl.map[k];
                         #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            color[j] = m == j ? tmp[k] : color[j];
+                            col[p][j] = map[k] == j ? tmp[k] : col[p][j];
                     }
                 }
-                plb_run_light_ops(color);
-                px4[oxo] = make_float4(color[0], color[1], color[2], color[3]);
             }
+            plb_run_light_ops_n<UP2_OX>(t.prog, col);
+            float4 px4[UP2_OX];
+            #pragma unroll
+            for (int p = 0; p < UP2_OX; p++)
+                px4[p] = make_float4(col[p][0], col[p][1], col[p][2], col[p][3]);
             if (gx + UP2_OX <= t.out_w) {
                 plb_store4(t.dst, t.dst_x0 + gx, t.dst_y0 + gy, px4);
             } else {
                 #pragma unroll
-                for (int oxo = 0; oxo < UP2_OX; oxo++) {
-                    if (gx + oxo < t.out_w)
-                        plb_store(t.dst, t.dst_x0 + gx + oxo, t.dst_y0 + gy, px4[oxo]);
+                for (int p = 0; p < UP2_OX; p++) {
+                    if (gx + p < t.out_w)
+                        plb_store(t.dst, t.dst_x0 + gx + p, t.dst_y0 + gy, px4[p]);
                 }
             }
         }
         return;
     }
+    const plb_tail_args &t = plb_s_tail;
     bool has_peak = false;
     for (int i = 0; i < plb_s_prog.n; i++)
         has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;

@@ -260,6 +260,7 @@ PLB_DEV void plb_store4(const plb_tex_desc &t, int x, int y, const float4 c[4])
 
 struct plb_coord {
     int mode;
+    int ident;      // EXACT mode, the rect is the whole texture and maps 1:1 onto the output
     float px0, px1, py0, py1;
     float osx, osy;
     float sizex, sizey;
@@ -281,6 +282,10 @@ static inline plb_coord plb_coord_init(int mode, const plb_tex_desc &src, pl_rec
     c.sizey = (float) src.h;
     c.dx0 = rc.x0; c.dxs = ((double) rc.x1 - rc.x0) / dw;
     c.dy0 = rc.y0; c.dys = ((double) rc.y1 - rc.y0) / dh;
+    // (gx + 0.5) / w lands inside texel gx for every w < 2^22: nearest fetches need no division
+    c.ident = mode != PLB_COORD_LITERAL && rc.x0 == 0.0f && rc.y0 == 0.0f && rc.x1 == (float) src.w &&
+              rc.y1 == (float) src.h && dw == src.w && dh == src.h && src.w < (1 << 22) &&
+              src.h < (1 << 22);
     return c;
 }
 

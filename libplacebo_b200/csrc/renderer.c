@@ -606,6 +606,16 @@ struct plane_state {
     int plane_w, plane_h;
 };
 
+// sh_subpass (src/shaders.c:676-686): a compute sub-shader can only be merged if its work group
+// geometry is acceptable to the parent (sh_try_compute). The caller materialises the sub-shader
+// into an FBO otherwise, exactly like pass_read_image does when sh_subpass returns NULL (:1868).
+static bool compute_compatible(const pl_shader sh, bool sub_compute, int bw, int bh, bool flex)
+{
+    if (!sub_compute || !sh->is_compute || sh->wg_flexible || flex)
+        return true;
+    return sh->wg_w == bw && sh->wg_h == bh;
+}
+
 // Move the (single) plane of sub-shader `sub` into the plane list of `sh`, mapping its
 // components into colour channels (sh_subpass + "color[map[c]] = tmp[c]", :1874-1891)
 static bool merge_plane_shader(pl_shader sh, pl_shader sub, const int map[4], int comps,
@@ -617,6 +627,10 @@ static bool merge_plane_shader(pl_shader sh, pl_shader sub, const int map[4], in
     }
     if (sh->px.nplanes >= 4) {
         plb_shader_fail(sh, "too many planes in one pass");
+        return false;
+    }
+    if (sub->is_compute && !plb_shader_try_compute(sh, sub->wg_w, sub->wg_h, sub->wg_flexible)) {
+        plb_shader_fail(sh, "internal: incompatible work group sizes (check compute_compatible first)");
         return false;
     }
     struct plb_plane_src *pl = &sh->px.planes[sh->px.nplanes++];
@@ -911,10 +925,24 @@ static bool pass_read_image(struct pass_state *pass)
         const pl_rect2d unscaled = { .x1 = out_w, .y1 = out_h };
         const bool aligned = st->w == out_w && st->h == out_h && pl_rect2d_eq(src.rect, unscaled);
         bool ok;
-        if (st->sh && aligned) {
+        if (st->sh && aligned && !compute_compatible(sh, st->sh->is_compute, st->sh->wg_w,
+                                                      st->sh->wg_h, st->sh->wg_flexible)) {
+            // sh_subpass refuses (work group clash): through an FBO, then a plain fetch
+            st->tex = shader_to_tex(pass, &st->sh, st->w, st->h, NULL, st->comps);
+            st->sh = NULL;
+            if (!st->tex)
+                goto error;
+            pl_shader psh = begin(pass);
+            ok = pl_shader_sample_direct(psh, pl_sample_src( .tex = st->tex )) &&
+                 merge_plane_shader(sh, psh, map, src.components, 1.0f);
+            if (sh->src == PLB_SRC_NONE)
+                sh->src = PLB_SRC_PLANES;
+            pl_dispatch_abort(rr->dp, &psh);
+        } else if (st->sh && aligned) {
             // pending 1:1 plane shader (deband / grain): merge as is
             ok = merge_plane_shader(sh, st->sh, map, src.components, src.scale);
-            sh->src = PLB_SRC_PLANES;
+            if (sh->src == PLB_SRC_NONE)
+                sh->src = PLB_SRC_PLANES;
             pl_dispatch_abort(rr->dp, &st->sh);
         } else {
             if (st->sh) {
@@ -925,7 +953,21 @@ static bool pass_read_image(struct pass_state *pass)
             }
             src.tex = st->tex;
             const struct sampler_info info = sample_src_info(pass, &src, SAMPLER_PLANE);
-            if (info.type == SAMPLER_COMPLEX && sh->src != PLB_SRC_POLAR && sh->src != PLB_SRC_ORTHO) {
+            // a polar sampler is a rigid 32x32 compute shader (sampling.c:668-699): it cannot
+            // join a pass that already has another rigid geometry (e.g. H.274 grain, 8x8)
+            const bool clash = info.type == SAMPLER_COMPLEX && info.config->polar &&
+                               !compute_compatible(sh, true, 32, 32, false);
+            if (clash) {
+                pl_shader psh = begin(pass);
+                ok = dispatch_sampler(pass, psh, &rr->samplers_src[i], SAMPLER_PLANE, &src);
+                pl_tex t = ok ? shader_to_tex(pass, &psh, out_w, out_h, NULL, st->comps) : NULL;
+                psh = begin(pass);
+                ok = t && pl_shader_sample_direct(psh, pl_sample_src( .tex = t )) &&
+                     merge_plane_shader(sh, psh, map, src.components, 1.0f);
+                if (sh->src == PLB_SRC_NONE)
+                    sh->src = PLB_SRC_PLANES;
+                pl_dispatch_abort(rr->dp, &psh);
+            } else if (info.type == SAMPLER_COMPLEX && sh->src != PLB_SRC_POLAR && sh->src != PLB_SRC_ORTHO) {
                 // this plane's scaler becomes the primary sampler of the merged pass
                 const enum plb_src_kind had = sh->src;
                 sh->src = PLB_SRC_NONE;

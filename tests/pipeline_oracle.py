@@ -172,7 +172,12 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     # detect_peak. Invocations past the image edge still execute (only the store is masked) and
     # peak detection counts them, so everything merged is evaluated on the padded extent.
     merged_has_polar = bool(plane_up) and (cw != W or ch != H) and plane_up.startswith("ewa")
-    wg = (32, 32) if merged_has_polar else (16, 16)
+    h274 = film_grain is not None and film_grain[1] == "h274"
+    # A merged grain sub-shader brings its own rigid geometry: 32x32 for AV1 luma
+    # (film_grain_av1.c:693), 8x8 for H.274 (film_grain_h274.c:164) -- and a rigid 8x8 pass
+    # cannot host the polar sampler's 32x32 (sh_subpass fails, renderer.c:1866-1875): the
+    # scaled chroma goes through an FBO instead.
+    wg = (8, 8) if h274 else (32, 32) if (merged_has_polar or film_grain is not None) else (16, 16)
     ext = (-(-W // wg[0]) * wg[0], -(-H // wg[1]) * wg[1])
     if deband:
         luma = orc.deband(Yf, 1, 3.0, 16.0, float(grain), (neutral_luma, 0, 0), float(norm), 1,
@@ -227,7 +232,14 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
 
     # plane scaler (SAMPLER_PLANE)
     crect_f = tuple(f32(v) for v in crect)
-    if plane_up and (cw != W or ch != H):
+    if plane_up and (cw != W or ch != H) and h274 and merged_has_polar:
+        rx, ry = W / (crect[2] - crect[0]), H / (crect[3] - crect[1])
+        filt = _filter_for(t0, plane_up, rx, ry)
+        cfbo = orc.sample_polar(ctex, W, H, filt, comp_mask=3, rect=crect_f, scale=cscale,
+                                coord_mode=coord_mode)
+        cfbo = orc.store_round(cfbo[..., :2], 0)                            # rg16hf FBO
+        chroma = np.pad(cfbo, ((0, ext[1] - H), (0, ext[0] - W), (0, 0)), mode="edge")
+    elif plane_up and (cw != W or ch != H):
         rx, ry = W / (crect[2] - crect[0]), H / (crect[3] - crect[1])
         filt = _filter_for(t0, plane_up, rx, ry)
         chroma = orc.sample_polar(ctex, W, H, filt, comp_mask=3, rect=crect_f, scale=cscale,
