@@ -1060,6 +1060,34 @@ PL_API void pl_frames_infer(pl_renderer rr, struct pl_frame *image, struct pl_fr
 PL_API bool pl_render_image(pl_renderer rr, const struct pl_frame *image,
                             const struct pl_frame *target, const struct pl_render_params *params);
 PL_API void pl_renderer_flush_cache(pl_renderer rr);
+
+/* ---- utils/upload.h: frame ingest (src/utils/upload.c) ------------------------------------ */
+struct pl_plane_data { /* utils/upload.h:33-73 */
+    enum pl_fmt_type type;      /* UNORM / SNORM / FLOAT */
+    int width, height;
+    int component_size[4];      /* bits per component, in memory order */
+    int component_pad[4];       /* ignored bits in front of each component */
+    int component_map[4];       /* colour channel (0..3) each component carries */
+    size_t pixel_stride;        /* bytes between pixels */
+    size_t row_stride;          /* bytes between rows (0 = tightly packed) */
+    bool swapped;               /* samples are in the non-native byte order */
+    const void *pixels;         /* either host memory ... */
+    pl_buf buf;                 /* ... or a buffer + offset */
+    size_t buf_offset;
+    void (*callback)(void *priv);
+    void *priv;
+};
+PL_API void pl_plane_data_from_mask(struct pl_plane_data *data, uint64_t mask[4]);
+PL_API void pl_plane_data_from_comps(struct pl_plane_data *data, int size[4], int shift[4]);
+PL_API bool pl_plane_data_align(struct pl_plane_data *data, struct pl_bit_encoding *out_bits);
+PL_API pl_fmt pl_plane_find_fmt(pl_gpu gpu, int out_map[4], const struct pl_plane_data *data);
+PL_API bool pl_upload_plane(pl_gpu gpu, struct pl_plane *out_plane, pl_tex *tex,
+                            const struct pl_plane_data *data);
+PL_API bool pl_recreate_plane(pl_gpu gpu, struct pl_plane *out_plane, pl_tex *tex,
+                              const struct pl_plane_data *data);
+/* Device-less object carrying only this backend's format table and limits, for format queries
+ * (pl_find_fmt, pl_find_named_fmt, pl_plane_find_fmt) without a GPU. Nothing else works on it. */
+PL_API pl_gpu pl_cuda_format_catalogue(void);
 PL_API bool pl_renderer_get_hdr_metadata(pl_renderer rr, struct pl_hdr_metadata *metadata);
 
 /* ---- frame-parallel multi-GPU support (no reference counterpart) ------------

@@ -203,6 +203,24 @@ static void setup_formats(struct plb_gpu *p)
     p->pub.num_formats = n;
 }
 
+// Device-less object that only carries the format table and limits: for format queries
+// (pl_find_fmt, pl_find_named_fmt, pl_plane_find_fmt) on machines without a GPU, e.g. when
+// planning an ingest layout. Everything else fails on it (no stream, no memory).
+pl_gpu pl_cuda_format_catalogue(void)
+{
+    static struct plb_gpu cat;
+    if (!cat.pub.num_formats) {
+        setup_formats(&cat);
+        cat.pub.limits.max_ssbo_size = (size_t) 1 << 30;
+        cat.pub.limits.max_tex_2d_dim = 65536;
+        cat.pub.limits.buf_transfer = true;
+        cat.pub.glsl.version = 450;
+        cat.pub.glsl.compute = true;
+        cat.pub.glsl.subgroup_size = 32;
+    }
+    return &cat.pub;
+}
+
 pl_fmt pl_find_named_fmt(pl_gpu gpu, const char *name)
 {
     if (!name)
@@ -882,6 +900,37 @@ void pl_buf_copy(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t s
     void *dp = (char *) (d->dptr ? d->dptr : d->hptr) + dst_offset;
     const void *sp = (const char *) (s->dptr ? s->dptr : s->hptr) + src_offset;
     CK(gpu, cudaMemcpyAsync(dp, sp, size, cudaMemcpyDefault, STREAM(gpu)));
+}
+
+// pl_buf_copy_swap (src/gpu.h:149-165, the reference runs it as a compute shader over SSBOs)
+__global__ void k_swap_words(const uint32_t *src, uint32_t *dst, size_t nwords, int wordsize)
+{
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < nwords;
+         i += (size_t) gridDim.x * blockDim.x) {
+        const uint32_t v = src[i];
+        // 16-bit words: swap the bytes of each half; 32-bit words: reverse all four
+        dst[i] = wordsize == 2 ? __byte_perm(v, 0, 0x2301) : __byte_perm(v, 0, 0x0123);
+    }
+}
+
+bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset,
+                       size_t size, int wordsize)
+{
+    struct plb_buf *d = (struct plb_buf *) dst, *s = (struct plb_buf *) src;
+    if ((wordsize != 2 && wordsize != 4) || size % 4 || dst_offset % 4 || src_offset % 4 ||
+        !d->dptr || !s->dptr || src_offset + size > s->pub.params.size ||
+        dst_offset + size > d->pub.params.size) {
+        PLB_ERR(gpu->log, "pl_buf_copy_swap: invalid arguments (word size %d, %zu bytes)", wordsize, size);
+        return false;
+    }
+    if (!size)
+        return true;
+    const size_t nwords = size / 4;
+    const int grid = (int) PLB_MIN((nwords + 255) / 256, (size_t) (plb_gpu_priv(gpu)->sm_count * 8));
+    k_swap_words<<<grid, 256, 0, STREAM(gpu)>>>((const uint32_t *) ((const char *) s->dptr + src_offset),
+                                                (uint32_t *) ((char *) d->dptr + dst_offset), nwords, wordsize);
+    plb_gpu_priv(gpu)->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_swap_words");
 }
 
 bool pl_buf_poll(pl_gpu gpu, pl_buf buf, uint64_t timeout)

@@ -118,6 +118,10 @@ void *plb_gpu_staging(pl_gpu gpu, size_t size);
 void *plb_dev_alloc(pl_gpu gpu, size_t size);
 void plb_dev_free(pl_gpu gpu, void *ptr);
 bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size);
+// byte-reverse every `wordsize`-byte word (2 or 4) of src[src_offset ..) into dst (src/gpu.h
+// pl_buf_copy_swap); offsets and size are multiples of 4
+bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset,
+                       size_t size, int wordsize);
 bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size);
 bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size);
 

@@ -35,6 +35,7 @@
 #include <libplacebo/shaders/dithering.h>
 #include <libplacebo/shaders/film_grain.h>
 #include <libplacebo/renderer.h>
+#include <libplacebo/utils/upload.h>
 
 #include <stdio.h>
 #include <string.h>
@@ -75,6 +76,7 @@ static void hv_init(void)
 #define T0_API HV_API
 #define T0_INIT() hv_init()
 #define T0_LOG hv_log
+#define T0_GPU hv_gpu
 #include "t0_flat.inc"
 
 // Raw bytes of the reference test fixtures, so that the golden generator can store them

@@ -40,6 +40,7 @@ static void shim_init(void)
 #define T0_API API
 #define T0_INIT() shim_init()
 #define T0_LOG shim_log
+#define T0_GPU pl_cuda_format_catalogue()
 #include "../../oracle/t0_flat.inc"
 
 /* ---- gpu / textures ---------------------------------------------------------------------- */
@@ -414,7 +415,14 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
                   .bits = { (int) img[2], (int) img[3], (int) img[4] } },
         .color = csp_from_flat(img + 5),
     };
-    if (nplanes == 3) {
+    if (nplanes == 2) {
+        /* semi-planar (NV12 / P010): Y + interleaved CbCr */
+        image.planes[0] = (struct pl_plane) { .texture = planes[0], .components = 1,
+                                              .component_mapping = { PL_CHANNEL_Y } };
+        image.planes[1] = (struct pl_plane) { .texture = planes[1], .components = 2,
+                                              .component_mapping = { PL_CHANNEL_CB, PL_CHANNEL_CR } };
+        pl_frame_set_chroma_location(&image, opts[5] ? opts[5] : PL_CHROMA_LEFT);
+    } else if (nplanes == 3) {
         for (int i = 0; i < 3; i++) {
             image.planes[i] = (struct pl_plane) {
                 .texture = planes[i],
@@ -613,6 +621,57 @@ API int shim_film_grain_h274(struct shim_ctx *c, void *tex, void *dst, int comps
         return -1;
     }
     return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst )) ? 0 : -2;
+}
+
+/* utils/upload.h: pl_upload_plane (via_buf: through a pl_buf instead of host memory) or
+ * pl_recreate_plane (pixels == NULL). layout = size[4], pad[4], map[4]; info out = components,
+ * component_mapping[4]. Returns the texture (destroy with shim_tex_destroy) or NULL. */
+API void *shim_upload_plane(struct shim_ctx *c, int type, const int *layout, int pixel_stride,
+                            int row_stride, int swapped, int w, int h, const void *pixels,
+                            size_t nbytes, int via_buf, int *info)
+{
+    struct pl_plane_data d = {
+        .type = type, .width = w, .height = h, .pixel_stride = pixel_stride,
+        .row_stride = row_stride, .swapped = swapped,
+    };
+    for (int i = 0; i < 4; i++) {
+        d.component_size[i] = layout[i];
+        d.component_pad[i] = layout[4 + i];
+        d.component_map[i] = layout[8 + i];
+    }
+    struct pl_plane plane = {0};
+    pl_tex tex = NULL;
+    pl_buf buf = NULL;
+    bool ok;
+    if (!pixels) {
+        ok = pl_recreate_plane(c->gpu, &plane, &tex, &d);
+    } else if (via_buf) {
+        /* offset the data inside the buffer to exercise buf_offset */
+        buf = pl_buf_create(c->gpu, pl_buf_params( .size = nbytes + 64, .host_writable = true,
+                                                   .storable = via_buf > 1 ));
+        if (!buf)
+            return NULL;
+        pl_buf_write(c->gpu, buf, 64, pixels, nbytes);
+        d.buf = buf;
+        d.buf_offset = 64;
+        ok = pl_upload_plane(c->gpu, &plane, &tex, &d);
+    } else {
+        d.pixels = pixels;
+        ok = pl_upload_plane(c->gpu, &plane, &tex, &d);
+    }
+    pl_gpu_finish(c->gpu);
+    pl_buf_destroy(c->gpu, &buf);
+    if (!ok) {
+        pl_tex_destroy(c->gpu, &tex);
+        return NULL;
+    }
+    info[0] = plane.components;
+    for (int i = 0; i < 4; i++)
+        info[1 + i] = plane.component_mapping[i];
+    info[5] = tex->params.format->num_components;
+    info[6] = (int) tex->params.format->texel_size;
+    info[7] = tex->params.renderable;
+    return (void *) tex;
 }
 
 /* host-only: the H.274 grain data base (no GPU needed) */
