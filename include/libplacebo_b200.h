@@ -343,6 +343,7 @@ struct pl_filter_params { /* filters.h:310-340 */
     float cutoff;
     int max_row_size;
     int row_stride_align;
+    float filter_scale;     /* deprecated in the reference (no effect); kept for layout */
 };
 #define pl_filter_params(...) (&(struct pl_filter_params) { __VA_ARGS__ })
 typedef const struct pl_filter_t {
@@ -388,6 +389,7 @@ struct pl_tone_map_params { /* tone_mapping.h:129-167 */
     float input_min, input_max, input_avg;
     float output_min, output_max;
     struct pl_hdr_metadata hdr;
+    float param;            /* deprecated in the reference (see constants); kept for layout */
 };
 PL_API bool pl_tone_map_params_equal(const struct pl_tone_map_params *a, const struct pl_tone_map_params *b);
 PL_API void pl_tone_map_params_infer(struct pl_tone_map_params *params);
@@ -531,6 +533,8 @@ struct pl_fmt_t { /* gpu.h:270-340 */
     int num_components;
     int component_depth[4];
     size_t internal_size;
+    struct pl_fmt_plane { pl_fmt format; uint8_t shift_x, shift_y; } planes[4]; /* planar formats: none here */
+    int num_planes;
     bool opaque;
     bool emulated;
     size_t texel_size;
@@ -538,6 +542,11 @@ struct pl_fmt_t { /* gpu.h:270-340 */
     int host_bits[4];
     int sample_order[4];
     bool gatherable;
+    const char *glsl_type;      /* GLSL / DRM interop members of the reference: NULL / 0 here */
+    const char *glsl_format;
+    uint32_t fourcc;
+    const uint64_t *modifiers;
+    int num_modifiers;
 };
 PL_API pl_fmt pl_find_fmt(pl_gpu gpu, enum pl_fmt_type type, int num_components,
                           int min_depth, int host_bits, enum pl_fmt_caps caps);
@@ -548,6 +557,22 @@ PL_API pl_timer pl_timer_create(pl_gpu gpu);
 PL_API void pl_timer_destroy(pl_gpu gpu, pl_timer *);
 PL_API uint64_t pl_timer_query(pl_gpu gpu, pl_timer);
 
+/* External memory handles (gpu.h:158-217). Members exist so that the parameter structs have the
+ * reference's layout; this backend imports CUDA device memory through pl_cuda_wrap() instead,
+ * and pl_buf_create / pl_tex_create fail loudly when an export / import handle type is set. */
+enum pl_handle_type {
+    PL_HANDLE_FD = 1 << 0, PL_HANDLE_WIN32 = 1 << 1, PL_HANDLE_WIN32_KMT = 1 << 2,
+    PL_HANDLE_DMA_BUF = 1 << 3, PL_HANDLE_HOST_PTR = 1 << 4, PL_HANDLE_MTL_TEX = 1 << 5,
+    PL_HANDLE_IOSURFACE = 1 << 6,
+};
+union pl_handle { int fd; void *handle; void *ptr; };
+struct pl_shared_mem {
+    union pl_handle handle;
+    size_t size, offset;
+    uint64_t drm_format_mod;
+    size_t stride_w, stride_h;
+    unsigned plane;
+};
 enum pl_buf_mem_type { PL_BUF_MEM_AUTO = 0, PL_BUF_MEM_HOST, PL_BUF_MEM_DEVICE, PL_BUF_MEM_TYPE_COUNT };
 struct pl_buf_params { /* gpu.h:441-520 */
     size_t size;
@@ -555,6 +580,8 @@ struct pl_buf_params { /* gpu.h:441-520 */
     bool uniform, storable, drawable;
     enum pl_buf_mem_type memory_type;
     pl_fmt format;
+    enum pl_handle_type export_handle, import_handle;   /* must be 0 */
+    struct pl_shared_mem shared_mem;
     const void *initial_data;
     void *user_data;
     pl_debug_tag debug_tag;
@@ -575,6 +602,8 @@ struct pl_tex_params { /* gpu.h:546-620 */
     int w, h, d;
     pl_fmt format;
     bool sampleable, renderable, storable, blit_src, blit_dst, host_writable, host_readable;
+    enum pl_handle_type export_handle, import_handle;   /* must be 0 */
+    struct pl_shared_mem shared_mem;
     const void *initial_data;
     void *user_data;
     pl_debug_tag debug_tag;
@@ -714,6 +743,8 @@ struct pl_sample_filter_params { /* sampling.h:153-178 */
     bool no_compute;
     bool no_widening;
     pl_shader_obj *lut;
+    int lut_entries;        /* deprecated in the reference (fixed at 256); kept for layout */
+    float cutoff;           /* deprecated in the reference (fixed at 1e-3); kept for layout */
 };
 #define pl_sample_filter_params(...) (&(struct pl_sample_filter_params) { __VA_ARGS__ })
 PL_API bool pl_shader_sample_polar(pl_shader sh, const struct pl_sample_src *src,
@@ -741,6 +772,7 @@ struct pl_peak_detect_params { /* shaders/colorspace.h:104-151 */
     float percentile;
     float black_cutoff;
     bool allow_delayed;
+    float minimum_peak;     /* deprecated in the reference; kept for layout */
 };
 #define PL_PEAK_DETECT_DEFAULTS \
     .smoothing_period = 20.0f, .scene_threshold_low = 1.0f, .scene_threshold_high = 3.0f, \
@@ -772,6 +804,13 @@ struct pl_color_map_params { /* shaders/colorspace.h:227-312 */
     float visualize_hue;
     float visualize_theta;
     bool show_clipping;
+    /* members the reference deprecated (shaders/colorspace.h:306-311); ignored, kept for layout */
+    int tone_mapping_mode;
+    float tone_mapping_param;
+    float tone_mapping_crosstalk;
+    int intent;
+    int gamut_mode;
+    float hybrid_mix;
 };
 #define PL_COLOR_MAP_DEFAULTS \
     .gamut_mapping = &pl_gamut_map_perceptual, .tone_mapping_function = &pl_tone_map_spline, \
@@ -1014,6 +1053,14 @@ struct pl_render_params { /* renderer.h:130-368; members outside the hot path ar
     bool dynamic_constants;
     void (*info_callback)(void *priv, const struct pl_render_info *info);
     void *info_priv;
+    /* members the reference deprecated (renderer.h:361-367); ignored, kept for layout */
+    bool allow_delayed_peak_detect;
+    const void *icc_params;
+    bool ignore_icc_profiles;
+    int lut_entries;
+    float polar_cutoff;
+    bool skip_target_clearing;
+    bool blend_against_tiles;
 };
 #define PL_RENDER_DEFAULTS \
     .color_map_params = &pl_color_map_default_params, \
@@ -1043,7 +1090,8 @@ struct pl_frame { /* renderer.h:528-655 */
     void (*release)(pl_gpu gpu, struct pl_frame *frame);
     struct pl_color_repr repr;
     struct pl_color_space color;
-    const void *icc;
+    const void *icc;            /* pl_icc_object: must be NULL (ICC is outside the hot path) */
+    struct pl_icc_profile { const void *data; size_t len; uint64_t signature; } profile; /* must be empty */
     const void *lut;
     enum pl_lut_type lut_type;
     pl_rect2df crop;

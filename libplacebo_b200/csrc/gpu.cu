@@ -549,6 +549,11 @@ pl_tex pl_tex_create(pl_gpu gpu, const struct pl_tex_params *params)
 {
     if (!tex_params_valid(gpu, params))
         return NULL;
+    if (params->export_handle || params->import_handle) {
+        PLB_ERR(gpu->log, "pl_tex_create: external memory handles are not supported on the CUDA "
+                "backend; wrap device memory with pl_cuda_wrap() instead");
+        return NULL;
+    }
     struct plb_tex *t = (struct plb_tex *) calloc(1, sizeof(*t));
     t->pub.params = *params;
     t->pub.params.initial_data = NULL;
@@ -795,6 +800,10 @@ pl_buf pl_buf_create(pl_gpu gpu, const struct pl_buf_params *params)
 {
     if (!params || !params->size) {
         PLB_ERR(gpu->log, "pl_buf_create: zero-sized buffer");
+        return NULL;
+    }
+    if (params->export_handle || params->import_handle) {
+        PLB_ERR(gpu->log, "pl_buf_create: external memory handles are not supported on the CUDA backend");
         return NULL;
     }
     struct plb_buf *b = (struct plb_buf *) calloc(1, sizeof(*b));

@@ -204,9 +204,11 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     if (!minb) {
         const char *e = getenv("PLB_PIXEL_MINB");
         const int v = e ? atoi(e) : 3;
-        minb = v >= 2 && v <= 5 ? v : 3;
+        minb = v >= 1 && v <= 5 ? v : 3;
     }
-    if (minb == 5)
+    if (minb == 1)
+        k_pixel<1><<<grid, block, 0, STREAM(gpu)>>>(t);
+    else if (minb == 5)
         k_pixel<5><<<grid, block, 0, STREAM(gpu)>>>(t);
     else if (minb == 4)
         k_pixel<4><<<grid, block, 0, STREAM(gpu)>>>(t);

@@ -21,6 +21,22 @@ PLB_DEV int plb_clampi(int x, int lo, int hi) { return min(max(x, lo), hi); }
 // and the oracle do), half -> exact widening.
 // ---------------------------------------------------------------------------------------
 
+// u / 255.0f and u / 65535.0f as three FP32 operations: q0 = u * fl(1/max), one residual
+// correction. Equal to the IEEE division for EVERY 8 / 16-bit code value (proved exhaustively
+// in tests/test_unorm_division.py); the division sequence costs about three times as much.
+PLB_DEV float plb_unorm8_to_float(unsigned u)
+{
+    const float uf = (float) u, c = 1.0f / 255.0f;
+    const float q0 = uf * c;
+    return __fmaf_rn(__fmaf_rn(-q0, 255.0f, uf), c, q0);
+}
+PLB_DEV float plb_unorm16_to_float(unsigned u)
+{
+    const float uf = (float) u, c = 1.0f / 65535.0f;
+    const float q0 = uf * c;
+    return __fmaf_rn(__fmaf_rn(-q0, 65535.0f, uf), c, q0);
+}
+
 template <int KIND, int COMPS>
 PLB_DEV float4 plb_load_t(const plb_tex_desc &t, int x, int y)
 {
@@ -30,24 +46,24 @@ PLB_DEV float4 plb_load_t(const plb_tex_desc &t, int x, int y)
         const uint8_t *p = (const uint8_t *) row + x * COMPS;
         if (COMPS == 4) {
             uchar4 u = *(const uchar4 *) p;
-            v[0] = u.x / 255.0f; v[1] = u.y / 255.0f; v[2] = u.z / 255.0f; v[3] = u.w / 255.0f;
+            v[0] = plb_unorm8_to_float(u.x); v[1] = plb_unorm8_to_float(u.y); v[2] = plb_unorm8_to_float(u.z); v[3] = plb_unorm8_to_float(u.w);
         } else {
             #pragma unroll
             for (int c = 0; c < COMPS; c++)
-                v[c] = p[c] / 255.0f;
+                v[c] = plb_unorm8_to_float(p[c]);
         }
     } else if (KIND == PLB_FK_UNORM16) {
         const uint16_t *p = (const uint16_t *) row + x * COMPS;
         if (COMPS == 4) {
             ushort4 u = *(const ushort4 *) p;
-            v[0] = u.x / 65535.0f; v[1] = u.y / 65535.0f; v[2] = u.z / 65535.0f; v[3] = u.w / 65535.0f;
+            v[0] = plb_unorm16_to_float(u.x); v[1] = plb_unorm16_to_float(u.y); v[2] = plb_unorm16_to_float(u.z); v[3] = plb_unorm16_to_float(u.w);
         } else if (COMPS == 2) {
             ushort2 u = *(const ushort2 *) p;
-            v[0] = u.x / 65535.0f; v[1] = u.y / 65535.0f;
+            v[0] = plb_unorm16_to_float(u.x); v[1] = plb_unorm16_to_float(u.y);
         } else {
             #pragma unroll
             for (int c = 0; c < COMPS; c++)
-                v[c] = p[c] / 65535.0f;
+                v[c] = plb_unorm16_to_float(p[c]);
         }
     } else if (KIND == PLB_FK_HALF) {
         const __half *p = (const __half *) row + x * COMPS;

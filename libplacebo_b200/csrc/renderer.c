@@ -1325,7 +1325,7 @@ static bool check_params(pl_renderer rr, const struct pl_render_params *p,
     REJECT(p->num_hooks, "user hooks");
     REJECT(p->lut, "custom LUTs");
     REJECT(image->lut || target->lut, "per-frame LUTs");
-    REJECT(image->icc || target->icc, "ICC profiles");
+    REJECT(image->icc || target->icc || image->profile.len || target->profile.len, "ICC profiles");
     REJECT(image->num_overlays || target->num_overlays, "overlays");
     REJECT(p->cone_params, "cone distortion");
     REJECT(p->blend_params, "blending");

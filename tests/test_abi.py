@@ -88,3 +88,26 @@ def test_forwarding_headers_compile(tmp_path):
                    "int f(void) { struct pl_render_params p = pl_render_default_params; return !!p.upscaler; }\n")
     subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(T.ROOT, "include"), "-c", str(src),
                     "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_struct_layouts_match_reference_headers():
+    """every parameter / state struct that crosses the boundary has the same
+    size and member offsets as in the reference's public headers, so that a caller built against
+    <libplacebo/*.h> can be relinked without recompiling. The same source (oracle/t0_flat.inc,
+    abi_layout) is compiled once against the reference headers and once against
+    include/libplacebo_b200.h; 46 structs / 335 members."""
+    import ctypes as C
+    harvest = os.path.join(T.ROOT, "oracle", "_ref", "libplref_harvest.so")
+    if not os.path.exists(harvest):
+        pytest.skip("reference not built")
+
+    def dump(lib, prefix):
+        buf = C.create_string_buffer(1 << 16)
+        n = getattr(lib, prefix + "abi_layout")(buf, len(buf))
+        assert 0 < n < len(buf)
+        return buf.value.decode().splitlines()
+
+    ref, mine = dump(C.CDLL(harvest), "hvt_"), dump(T.shim(), "plt_")
+    assert len(ref) == len(mine) > 300
+    diff = [(a, b) for a, b in zip(ref, mine) if a != b]
+    assert not diff, diff[:10]
