@@ -99,6 +99,7 @@ def test_struct_layouts_match_reference_headers():
     import ctypes as C
     harvest = os.path.join(T.ROOT, "oracle", "_ref", "libplref_harvest.so")
     if not os.path.exists(harvest):
+        import pytest
         pytest.skip("reference not built")
 
     def dump(lib, prefix):
