@@ -318,9 +318,16 @@ def run_ours(args, rank, world, local_rank):
     plist.sort(key=lambda p: -(p["mean_us"] * p["launches"]))
     top = plist[0] if plist else None
     roof = None
+    # DRAM bytes of the same kernel from the committed `ncu --set full` capture (tools/ncu_traffic.py)
+    traffic = None
+    try:
+        tdb = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tdb.get(args.workload, {}).get(top["pass"] if top else "", {}).get("dram_bytes")
+    except Exception:  # noqa: BLE001
+        pass
     if top and top["GBps"]:
         roof = {"bound": "hbm", "achieved": round(top["GBps"], 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(top["GBps"] / hbm_peak, 4), "traffic": None,
+                "frac": round(top["GBps"] / hbm_peak, 4), "traffic": traffic,
                 "kernel": top["pass"], "mean_us": round(top["mean_us"], 2),
                 "algorithmic_bytes_per_launch": int(top["algorithmic_MB"] * 1e6),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)",
