@@ -282,6 +282,7 @@ PL_API extern const struct pl_filter_function pl_filter_function_hermite;
 PL_API extern const struct pl_filter_function pl_filter_function_spline16;
 PL_API extern const struct pl_filter_function pl_filter_function_spline36;
 PL_API extern const struct pl_filter_function pl_filter_function_spline64;
+PL_API extern const struct pl_filter_function pl_filter_function_oversample;
 PL_API const struct pl_filter_function *pl_find_filter_function(const char *name);
 
 enum pl_filter_usage {
@@ -315,6 +316,7 @@ PL_API extern const struct pl_filter_config pl_filter_nearest;
 PL_API extern const struct pl_filter_config pl_filter_box;
 PL_API extern const struct pl_filter_config pl_filter_bilinear;
 PL_API extern const struct pl_filter_config pl_filter_gaussian;
+PL_API extern const struct pl_filter_config pl_filter_oversample;
 PL_API extern const struct pl_filter_config pl_filter_sinc;
 PL_API extern const struct pl_filter_config pl_filter_lanczos;
 PL_API extern const struct pl_filter_config pl_filter_ginseng;
@@ -737,6 +739,11 @@ PL_API void pl_shader_deband(pl_shader sh, const struct pl_sample_src *src,
 PL_API bool pl_shader_sample_direct(pl_shader sh, const struct pl_sample_src *src);
 PL_API bool pl_shader_sample_nearest(pl_shader sh, const struct pl_sample_src *src);
 PL_API bool pl_shader_sample_bilinear(pl_shader sh, const struct pl_sample_src *src);
+/* built-in fast scalers (sampling.h:120-150): a few bilinear fetches, for up-scaling */
+PL_API bool pl_shader_sample_bicubic(pl_shader sh, const struct pl_sample_src *src);
+PL_API bool pl_shader_sample_hermite(pl_shader sh, const struct pl_sample_src *src);
+PL_API bool pl_shader_sample_gaussian(pl_shader sh, const struct pl_sample_src *src);
+PL_API bool pl_shader_sample_oversample(pl_shader sh, const struct pl_sample_src *src, float threshold);
 struct pl_sample_filter_params { /* sampling.h:153-178 */
     struct pl_filter_config filter;
     float antiring;

@@ -241,6 +241,10 @@ enum plb_plane_kind {
     PLB_PLANE_DEBAND,      // pl_shader_deband
     PLB_PLANE_GRAIN_AV1,   // pl_shader_film_grain (AV1)
     PLB_PLANE_GRAIN_H274,
+    PLB_PLANE_BICUBIC,     // pl_shader_sample_bicubic   (sampling.c:319-366)
+    PLB_PLANE_HERMITE,     // pl_shader_sample_hermite   (sampling.c:368-393)
+    PLB_PLANE_GAUSSIAN,    // pl_shader_sample_gaussian  (sampling.c:395-440)
+    PLB_PLANE_OVERSAMPLE,  // pl_shader_sample_oversample (sampling.c:442-478)
 };
 
 struct plb_av1_dev;        // uploaded grain LUTs, see k_grain.cu
@@ -296,6 +300,8 @@ struct plb_plane_src {
     float threshold, radius, grain_str;
     float neutral[3];
     uint8_t comp_mask;
+    // oversample: scaling ratios and snapping threshold
+    float over_rx, over_ry, over_threshold;
     // grain
     struct plb_av1_plane av1;
     struct plb_tex_desc luma;  // AV1 chroma needs the luma plane

@@ -13,8 +13,9 @@ PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_pixel)
 
 #define PIX_TILE 32
 
-// MINB = resident CTAs per SM the register allocation is tuned for (3 -> 80 registers,
-// 4 -> 64 registers): selectable at run time for measurements (PLB_PIXEL_MINB).
+// MINB = resident CTAs per SM the register allocation is tuned for (2 -> 114 registers, 3 -> 80,
+// 4 -> 64, 5 -> 48). Measured on B200 with the HDR colour pass (µs): 1305 / 1186 / 1158 / 1138;
+// debanding: 106 / 98 / 93 / 103. Default 4; PLB_PIXEL_MINB selects another for measurements.
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_pixel(const __grid_constant__ plb_tail_args ap)
@@ -203,8 +204,8 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     static int minb;
     if (!minb) {
         const char *e = getenv("PLB_PIXEL_MINB");
-        const int v = e ? atoi(e) : 3;
-        minb = v >= 1 && v <= 5 ? v : 3;
+        const int v = e ? atoi(e) : 4;
+        minb = v >= 1 && v <= 5 ? v : 4;
     }
     if (minb == 1)
         k_pixel<1><<<grid, block, 0, STREAM(gpu)>>>(t);

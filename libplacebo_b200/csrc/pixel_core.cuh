@@ -267,6 +267,84 @@ static __device__ __noinline__ void plb_grain_h274(const plb_plane_src &pl, int 
     }
 }
 
+// Built-in fast scalers, restated operation by operation from the GLSL (sampling.c:319-478);
+// `u, v` = the interpolated normalised position `pos`, pt = 1 / texture size. Real functions:
+// they are rare and must not grow the common pixel tail.
+PLB_DEV float plb_fract(float x) { return x - floorf(x); }
+
+static __device__ __noinline__ float4 plb_sample_fast(const plb_plane_src &pl, const plb_coord &cc,
+                                                      float u, float v)
+{
+    const float sx = (float) pl.tex.w, sy = (float) pl.tex.h;
+    const float ptx = cc.ptx, pty = cc.pty; // (float) (1.0 / size), as the host passes `pt`
+    if (pl.kind == PLB_PLANE_HERMITE) {
+        const float fx = plb_fract(u * sx + 0.5f), fy = plb_fract(v * sy + 0.5f);
+        // smoothstep(0, 1, t) = t * t * (3 - 2 t) on the clamped argument
+        const float tx = plb_clamp(fx, 0.0f, 1.0f), ty = plb_clamp(fy, 0.0f, 1.0f);
+        const float smx = tx * tx * (3.0f - 2.0f * tx), smy = ty * ty * (3.0f - 2.0f * ty);
+        return plb_tex_linear(pl.tex, u + ptx * (smx - fx), v + pty * (smy - fy));
+    }
+    if (pl.kind == PLB_PLANE_OVERSAMPLE) {
+        const float fx = plb_fract(u * sx - 0.5f), fy = plb_fract(v * sy - 0.5f);
+        float cx = plb_clamp((fx - 0.5f) * pl.over_rx + 0.5f, 0.0f, 1.0f);
+        float cy = plb_clamp((fy - 0.5f) * pl.over_ry + 0.5f, 0.0f, 1.0f);
+        if (pl.over_threshold > 0.0f) {
+            const float th = pl.over_threshold;
+            // mix(coeff, 0, lessThan(coeff, th)), mix(coeff, 1, greaterThan(coeff, 1 - th))
+            cx = cx < th ? 0.0f : cx;
+            cy = cy < th ? 0.0f : cy;
+            cx = cx > 1.0f - th ? 1.0f : cx;
+            cy = cy > 1.0f - th ? 1.0f : cy;
+        }
+        return plb_tex_linear(pl.tex, u + (cx - fx) * ptx, v + (cy - fy) * pty);
+    }
+    // bicubic / gaussian: weights of the four taps per axis, folded into two bilinear fetches
+    float g[4], h[4]; // g = (x01, y01, x23, y23) sums, h = offsets in texels
+    float offx = 0.0f, offy = 0.0f;
+    if (pl.kind == PLB_PLANE_BICUBIC) {
+        const float f[2] = { plb_fract(u * sx + 0.5f), plb_fract(v * sy + 0.5f) };
+        #pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const float fr = f[a], fr2 = fr * fr, inv = 1.0f - fr, inv2 = inv * inv;
+            const float w0 = (1.0f / 6.0f) * inv2 * inv;
+            const float w1 = (2.0f / 3.0f) - 0.5f * fr2 * (2.0f - fr);
+            const float w2 = (2.0f / 3.0f) - 0.5f * inv2 * (2.0f - inv);
+            const float w3 = (1.0f / 6.0f) * fr2 * fr;
+            g[a] = w0 + w1;
+            g[2 + a] = w2 + w3;
+            h[a] = (w1 / g[a] + inv) - 2.0f;
+            h[2 + a] = w3 / g[2 + a] + inv;
+        }
+    } else { // gaussian
+        const float o[2] = { -plb_fract(u * sx + 0.5f), -plb_fract(v * sy + 0.5f) };
+        offx = o[0];
+        offy = o[1];
+        #pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const float off = o[a], off2 = -2.0f * off * off;
+            const float w0 = plm_expf((off2 + 4.0f * off) - 2.0f);
+            const float w1 = plm_expf(off2);
+            const float w2 = plm_expf((off2 - 4.0f * off) - 2.0f);
+            const float w3 = plm_expf((off2 - 8.0f * off) - 8.0f);
+            g[a] = w0 + w1;
+            g[2 + a] = w2 + w3;
+            h[a] = w1 / g[a] - 1.0f;
+            h[2 + a] = w3 / g[2 + a] + 1.0f;
+        }
+        g[0] = g[0] / (g[0] + g[2]); // explicit normalisation of the mixing weights
+        g[1] = g[1] / (g[1] + g[3]);
+        h[0] += offx; h[1] += offy; h[2] += offx; h[3] += offy;
+    }
+    const float px = u + ptx * h[0], py = v + pty * h[1], pz = u + ptx * h[2], pw = v + pty * h[3];
+    const float4 c00 = plb_tex_linear(pl.tex, px, py), c01 = plb_tex_linear(pl.tex, px, pw);
+    const float4 c10 = plb_tex_linear(pl.tex, pz, py), c11 = plb_tex_linear(pl.tex, pz, pw);
+    float4 r;
+#define MIX3(F) r.F = plb_mix(plb_mix(c11.F, c10.F, g[1]), plb_mix(c01.F, c00.F, g[1]), g[0]);
+    MIX3(x) MIX3(y) MIX3(z) MIX3(w)
+#undef MIX3
+    return r;
+}
+
 // Sample plane `pl` at output pixel (gx, gy) -> vec4 (already multiplied by its scale)
 PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
                               uint32_t frame_index, float out[4])
@@ -274,7 +352,9 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
     float posx, posy;
     plb_coord_pos(cc, gx, gy, posx, posy);
     float4 c4;
-    if (pl.kind == PLB_PLANE_DIRECT && pl.linear)
+    if (pl.kind >= PLB_PLANE_BICUBIC)
+        c4 = plb_sample_fast(pl, cc, posx, posy);
+    else if (pl.kind == PLB_PLANE_DIRECT && pl.linear)
         c4 = plb_tex_linear(pl.tex, posx, posy);
     else
         c4 = plb_tex_nearest(pl.tex, posx, posy);

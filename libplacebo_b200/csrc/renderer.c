@@ -477,7 +477,8 @@ static pl_shader img_sh(struct pass_state *pass)
 // samplers (renderer.c:597-789)
 // ---------------------------------------------------------------------------------------
 
-enum sampler_type { SAMPLER_DIRECT, SAMPLER_NEAREST, SAMPLER_COMPLEX };
+enum sampler_type { SAMPLER_DIRECT, SAMPLER_NEAREST, SAMPLER_BICUBIC, SAMPLER_HERMITE,
+                    SAMPLER_GAUSSIAN, SAMPLER_COMPLEX, SAMPLER_OVERSAMPLE };
 enum sampler_dir { SAMPLER_NOOP, SAMPLER_UP, SAMPLER_DOWN };
 enum sampler_usage { SAMPLER_MAIN, SAMPLER_PLANE };
 
@@ -525,13 +526,20 @@ static struct sampler_info sample_src_info(struct pass_state *pass,
     }
     if ((pass->rr->errors & PL_RENDER_ERR_SAMPLING) || !info.config) {
         info.type = SAMPLER_DIRECT;
+    } else if (info.config->kernel == &pl_filter_function_oversample) {
+        info.type = SAMPLER_OVERSAMPLE;
     } else {
         info.type = SAMPLER_COMPLEX;
         const bool can_fast = info.dir == SAMPLER_UP || params->skip_anti_aliasing;
         if (can_fast && !params->disable_builtin_scalers) {
-            // the reference's built-in fast paths: bilinear / nearest map onto the texture
-            // unit; bicubic/hermite/gaussian fast paths are not implemented here and take
-            // the generic separable path instead (same maths up to the linear-sampling trick)
+            // the reference's built-in fast paths (renderer.c:657-676; every format of this
+            // backend can be sampled linearly)
+            if (pl_filter_config_eq(info.config, &pl_filter_bicubic))
+                info.type = SAMPLER_BICUBIC;
+            if (pl_filter_config_eq(info.config, &pl_filter_hermite))
+                info.type = SAMPLER_HERMITE;
+            if (pl_filter_config_eq(info.config, &pl_filter_gaussian))
+                info.type = SAMPLER_GAUSSIAN;
             if (pl_filter_config_eq(info.config, &pl_filter_bilinear))
                 info.type = SAMPLER_DIRECT;
             if (pl_filter_config_eq(info.config, &pl_filter_nearest))
@@ -553,6 +561,14 @@ static bool dispatch_sampler(struct pass_state *pass, pl_shader sh, struct sampl
         return pl_shader_sample_direct(sh, src);
     if (info.type == SAMPLER_NEAREST)
         return pl_shader_sample_nearest(sh, src);
+    if (info.type == SAMPLER_BICUBIC)
+        return pl_shader_sample_bicubic(sh, src);
+    if (info.type == SAMPLER_HERMITE)
+        return pl_shader_sample_hermite(sh, src);
+    if (info.type == SAMPLER_GAUSSIAN)
+        return pl_shader_sample_gaussian(sh, src);
+    if (info.type == SAMPLER_OVERSAMPLE)
+        return pl_shader_sample_oversample(sh, src, info.config->kernel->params[0]);
 
     struct pl_sample_filter_params fp = {
         .filter = *info.config,
@@ -998,12 +1014,12 @@ static bool pass_read_image(struct pass_state *pass)
                     psh = begin(pass);
                     ok = t && pl_shader_sample_direct(psh, pl_sample_src( .tex = t ));
                     src.scale = 1.0;
-                } else if (info.type == SAMPLER_NEAREST) {
-                    ok = pl_shader_sample_nearest(psh, &(struct pl_sample_src) {
-                        .tex = src.tex, .rect = src.rect, .new_w = out_w, .new_h = out_h });
                 } else {
-                    ok = pl_shader_sample_direct(psh, &(struct pl_sample_src) {
-                        .tex = src.tex, .rect = src.rect, .new_w = out_w, .new_h = out_h });
+                    // texture-unit scalers and built-in fast paths; the plane's scale factor
+                    // is applied by the merge ("tmp = vec4(scale) * sub()")
+                    struct pl_sample_src plain = {
+                        .tex = src.tex, .rect = src.rect, .new_w = out_w, .new_h = out_h };
+                    ok = dispatch_sampler(pass, psh, &rr->samplers_src[i], SAMPLER_PLANE, &plain);
                 }
                 ok = ok && merge_plane_shader(sh, psh, map, src.components, src.scale);
                 if (sh->src == PLB_SRC_NONE)

@@ -371,6 +371,54 @@ bool pl_shader_sample_bilinear(pl_shader sh, const struct pl_sample_src *src)
     return sample_simple(sh, src, 1, "pl_shader_sample_bilinear");
 }
 
+// Built-in fast scalers (sampling.c:319-478): a handful of bilinear fetches at positions
+// computed from the sub-texel phase. All of them need a linearly sampleable texture.
+static bool sample_fast(pl_shader sh, const struct pl_sample_src *src, int kind, float threshold,
+                        const char *who, const char *step)
+{
+    struct src_info si;
+    if (!setup_src(sh, src, &si, true, true, who))
+        return false;
+    sh->src = PLB_SRC_PLANES;
+    plb_shader_describe(sh, step);
+    struct plb_plane_src *pl = &sh->px.planes[0];
+    memset(pl, 0, sizeof(*pl));
+    pl->kind = kind;
+    pl->tex = si.tex;
+    pl->rect = si.rect;
+    pl->linear = 1;
+    pl->scale = si.scale;
+    pl->over_rx = si.rx;
+    pl->over_ry = si.ry;
+    pl->over_threshold = PLB_CLAMP(threshold, 0.0f, 0.5f);
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k;
+    sh->px.nplanes = 1;
+    sh->px.coord_mode = coord_mode(sh);
+    return true;
+}
+
+bool pl_shader_sample_bicubic(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_fast(sh, src, PLB_PLANE_BICUBIC, 0.0f, "pl_shader_sample_bicubic", "bicubic");
+}
+
+bool pl_shader_sample_hermite(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_fast(sh, src, PLB_PLANE_HERMITE, 0.0f, "pl_shader_sample_hermite", "hermite");
+}
+
+bool pl_shader_sample_gaussian(pl_shader sh, const struct pl_sample_src *src)
+{
+    return sample_fast(sh, src, PLB_PLANE_GAUSSIAN, 0.0f, "pl_shader_sample_gaussian", "gaussian");
+}
+
+bool pl_shader_sample_oversample(pl_shader sh, const struct pl_sample_src *src, float threshold)
+{
+    return sample_fast(sh, src, PLB_PLANE_OVERSAMPLE, threshold, "pl_shader_sample_oversample",
+                       "oversample");
+}
+
 // ---------------------------------------------------------------------------------------
 // debanding
 // ---------------------------------------------------------------------------------------

@@ -162,6 +162,11 @@ FN(pl_filter_function_spline16,  "spline16",  k_spline16,  2.0);
 FN(pl_filter_function_spline36,  "spline36",  k_spline36,  3.0);
 FN(pl_filter_function_spline64,  "spline64",  k_spline64,  4.0);
 
+// "oversample" has no kernel: the name selects pl_shader_sample_oversample, params[0] is its
+// snapping threshold (filters.c:604-615)
+static double k_oversample(const struct pl_filter_ctx *f, double x) { (void) f; (void) x; return 0.0; }
+FN(pl_filter_function_oversample, "oversample", k_oversample, 0.0, .params = {0.0}, .tunable = {true}, .opaque = true);
+
 static const struct pl_filter_function *const all_functions[] = {
     &pl_filter_function_box, &pl_filter_function_triangle, &pl_filter_function_cosine,
     &pl_filter_function_hann, &pl_filter_function_hamming, &pl_filter_function_welch,
@@ -169,7 +174,7 @@ static const struct pl_filter_function *const all_functions[] = {
     &pl_filter_function_gaussian, &pl_filter_function_quadratic, &pl_filter_function_sinc,
     &pl_filter_function_jinc, &pl_filter_function_sphinx, &pl_filter_function_cubic,
     &pl_filter_function_hermite, &pl_filter_function_spline16, &pl_filter_function_spline36,
-    &pl_filter_function_spline64,
+    &pl_filter_function_spline64, &pl_filter_function_oversample,
 };
 
 const struct pl_filter_function *pl_find_filter_function(const char *name)
@@ -208,6 +213,7 @@ CFG(pl_filter_nearest, "nearest", "Nearest neighbor", box, UP, UP, .radius = 0.5
 CFG(pl_filter_box, "box", "Box averaging", box, SCALE, DOWN, .radius = 0.5);
 CFG(pl_filter_bilinear, "bilinear", "Bilinear", triangle, ALL, SCALE);
 CFG(pl_filter_gaussian, "gaussian", "Gaussian", gaussian, ALL, SCALE, .params = {1.0});
+CFG(pl_filter_oversample, "oversample", "Oversampling", oversample, UP | MIX, UP | MIX, .params = {0.0});
 CFG(pl_filter_sinc, "sinc", "Sinc (unwindowed)", sinc, ALL, 0, .radius = 2.0);
 CFG(pl_filter_lanczos, "lanczos", "Lanczos", sinc, ALL, SCALE,
     .window = &pl_filter_function_sinc, .radius = 3.0);
@@ -247,7 +253,7 @@ const struct pl_filter_config * const pl_filter_configs[] = {
     &pl_filter_bilinear, &pl_filter_nearest, &pl_filter_spline16, &pl_filter_spline36,
     &pl_filter_spline64, &pl_filter_lanczos, &pl_filter_ewa_lanczos,
     &pl_filter_ewa_lanczossharp, &pl_filter_ewa_lanczos4sharpest, &pl_filter_bicubic,
-    &pl_filter_hermite, &pl_filter_gaussian, &pl_filter_mitchell, &pl_filter_mitchell_clamp,
+    &pl_filter_hermite, &pl_filter_gaussian, &pl_filter_oversample, &pl_filter_mitchell, &pl_filter_mitchell_clamp,
     &pl_filter_sinc, &pl_filter_ginseng, &pl_filter_ewa_jinc, &pl_filter_ewa_ginseng,
     &pl_filter_ewa_hann, &pl_filter_catmull_rom, &pl_filter_robidoux,
     &pl_filter_robidouxsharp, &pl_filter_ewa_robidoux, &pl_filter_ewa_robidouxsharp,

@@ -375,6 +375,110 @@ void orc_sample_direct(const struct orc_tex *src, struct orc_rect rect, int dw, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Built-in fast scalers — src/shaders/sampling.c:319-478, the GLSL restated statement by
+// statement. kind: 0 bicubic (:319-366), 1 hermite (:368-393), 2 gaussian (:395-440),
+// 3 oversample (:442-478; rx, ry = scaling ratios, threshold already clamped to [0, 0.5]).
+// `pt` is the uniform the host passes: (float) (1.0 / size). textureLod = tex_linear.
+// ------------------------------------------------------------------------------------------
+
+static inline float fractf_(float x) { return x - floorf(x); }
+static inline float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+void orc_sample_fast(const struct orc_tex *src, struct orc_rect rect, int dw, int dh, int kind,
+                     float scale, float rx, float ry, float threshold, int coord_mode, float *dst)
+{
+    const struct coord_ctx cc = coord_init(coord_mode, src, rect, dw, dh);
+    const int ew = EXT_W(dw), eh = EXT_H(dh);
+    const float size[2] = { (float) src->w, (float) src->h };
+    const float pt[2] = { (float) (1.0 / src->w), (float) (1.0 / src->h) };
+    #pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < eh; gy++) {
+        for (int gx = 0; gx < ew; gx++) {
+            float pos[2];
+            coord_pos(&cc, gx, gy, &pos[0], &pos[1]);
+            float color[4] = {0, 0, 0, 1};
+            if (kind == 1) {
+                float p[2];
+                for (int a = 0; a < 2; a++) {
+                    const float frac = fractf_(pos[a] * size[a] + 0.5f);
+                    const float t = clamp01(frac); // smoothstep(0.0, 1.0, frac)
+                    const float sm = t * t * (3.0f - 2.0f * t);
+                    p[a] = pos[a] + pt[a] * (sm - frac);
+                }
+                tex_linear(src, p[0], p[1], color);
+            } else if (kind == 3) {
+                float p[2];
+                const float ratio[2] = { rx, ry };
+                for (int a = 0; a < 2; a++) {
+                    const float fcoord = fractf_(pos[a] * size[a] - 0.5f);
+                    float coeff = (fcoord - 0.5f) * ratio[a];
+                    coeff = clamp01(coeff + 0.5f);
+                    if (threshold > 0.0f) {
+                        if (coeff < threshold)
+                            coeff = 0.0f;
+                        if (coeff > 1.0f - threshold)
+                            coeff = 1.0f;
+                    }
+                    p[a] = pos[a] + (coeff - fcoord) * pt[a];
+                }
+                tex_linear(src, p[0], p[1], color);
+            } else {
+                float g[4], h[4], off[2] = {0, 0}; // vec4 order: (x, y, z, w) = (x01, y01, x23, y23)
+                for (int a = 0; a < 2; a++) {
+                    if (kind == 0) {
+                        const float frac = fractf_(pos[a] * size[a] + 0.5f);
+                        const float frac2 = frac * frac, inv = 1.0f - frac, inv2 = inv * inv;
+                        const float w0 = (1.0f / 6.0f) * inv2 * inv;
+                        const float w1 = (2.0f / 3.0f) - 0.5f * frac2 * (2.0f - frac);
+                        const float w2 = (2.0f / 3.0f) - 0.5f * inv2 * (2.0f - inv);
+                        const float w3 = (1.0f / 6.0f) * frac2 * frac;
+                        g[a] = w0 + w1;
+                        g[2 + a] = w2 + w3;
+                        h[a] = w1 / g[a] + inv;
+                        h[2 + a] = w3 / g[2 + a] + inv;
+                        h[a] -= 2.0f;
+                    } else {
+                        off[a] = -fractf_(pos[a] * size[a] + 0.5f);
+                        const float o = off[a], off2 = -2.0f * o * o;
+                        const float w0 = pm_expf(off2 + 4.0f * o - 2.0f);
+                        const float w1 = pm_expf(off2);
+                        const float w2 = pm_expf(off2 - 4.0f * o - 2.0f);
+                        const float w3 = pm_expf(off2 - 8.0f * o - 8.0f);
+                        g[a] = w0 + w1;
+                        g[2 + a] = w2 + w3;
+                        h[a] = w1 / g[a];
+                        h[2 + a] = w3 / g[2 + a];
+                        h[a] -= 1.0f;
+                        h[2 + a] += 1.0f;
+                    }
+                }
+                if (kind == 2) {
+                    g[0] /= g[0] + g[2];
+                    g[1] /= g[1] + g[3];
+                    for (int k = 0; k < 4; k++)
+                        h[k] = h[k] + off[k & 1];
+                }
+                const float px = pos[0] + pt[0] * h[0], py = pos[1] + pt[1] * h[1];
+                const float pz = pos[0] + pt[0] * h[2], pw = pos[1] + pt[1] * h[3];
+                float c00[4] = {0, 0, 0, 1}, c01[4] = {0, 0, 0, 1}, c10[4] = {0, 0, 0, 1}, c11[4] = {0, 0, 0, 1};
+                tex_linear(src, px, py, c00);
+                tex_linear(src, px, pw, c01);
+                tex_linear(src, pz, py, c10);
+                tex_linear(src, pz, pw, c11);
+                for (int k = 0; k < 4; k++) {
+                    const float c0 = mixf(c01[k], c00[k], g[1]);
+                    const float c1 = mixf(c11[k], c10[k], g[1]);
+                    color[k] = mixf(c1, c0, g[0]);
+                }
+            }
+            float *o = dst + ((size_t) gy * ew + gx) * 4;
+            for (int k = 0; k < 4; k++)
+                o[k] = scale * color[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // sh_prng — src/shaders.c:965-998 (pcg3d). float(0xFFFFFFFFu) rounds to 2^32.
 // ------------------------------------------------------------------------------------------
 

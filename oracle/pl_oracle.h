@@ -79,6 +79,11 @@ struct orc_polar_params {
 ORC_API void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
                               const struct orc_polar_params *p, float *dst);
 
+// built-in fast scalers (sampling.c:319-478); kind 0 bicubic, 1 hermite, 2 gaussian, 3 oversample
+ORC_API void orc_sample_fast(const struct orc_tex *src, struct orc_rect rect, int dw, int dh,
+                             int kind, float scale, float rx, float ry, float threshold,
+                             int coord_mode, float *dst);
+
 struct orc_ortho_params {
     const float *lut;     // filter weights, 256 rows of row_stride floats (after fill_ortho_lut)
     int lut_entries;

@@ -271,6 +271,10 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
                            : pl_shader_sample_ortho2(sh, &ssrc, &fp);
         break;
     }
+    case 6: ok = pl_shader_sample_bicubic(sh, &ssrc); break;
+    case 7: ok = pl_shader_sample_hermite(sh, &ssrc); break;
+    case 8: ok = pl_shader_sample_gaussian(sh, &ssrc); break;
+    case 9: ok = pl_shader_sample_oversample(sh, &ssrc, sargs[8]); break; /* [8] threshold */
     default:
         goto done;
     }

@@ -12,7 +12,8 @@ FMT = {
     "r32f": (np.float32, 1), "rg32f": (np.float32, 2), "rgba32f": (np.float32, 4),
 }
 
-SRC_KIND = dict(direct=0, nearest=1, bilinear=2, deband=3, polar=4, ortho=5)
+SRC_KIND = dict(direct=0, nearest=1, bilinear=2, deband=3, polar=4, ortho=5, bicubic=6, hermite=7,
+                gaussian=8, oversample=9)
 OP = dict(decode=1, encode=2, linearize=3, delinearize=4, color_map=5, dither=6, sigmoidize=7,
           unsigmoidize=8, detect_peak=9)
 

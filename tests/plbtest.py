@@ -442,6 +442,19 @@ class Oracle:
         self.lib.orc_set_eval_extent(0, 0)
         return out
 
+    def sample_fast(self, src, dw, dh, kind, rect=None, scale=1.0, threshold=0.0,
+                    coord_mode=COORD_LITERAL):
+        """kind: bicubic / hermite / gaussian / oversample (sampling.c:319-478)."""
+        t, keep = _tex(src)
+        rect = rect or (0, 0, keep.shape[1], keep.shape[0])
+        out = self._ext_out(dw, dh, None)
+        rx, ry = dw / abs(rect[2] - rect[0]), dh / abs(rect[3] - rect[1])
+        self.lib.orc_sample_fast(C.byref(t), OrcRect(*rect), dw, dh,
+                                 ["bicubic", "hermite", "gaussian", "oversample"].index(kind),
+                                 C.c_float(scale), C.c_float(rx), C.c_float(ry),
+                                 C.c_float(min(max(threshold, 0.0), 0.5)), coord_mode, fp(out))
+        return out
+
     def deband(self, src, iterations=1, threshold=3.0, radius=16.0, grain=4.0,
                neutral=(0, 0, 0), scale=1.0, comp_mask=None, frame_index=0, ext=None):
         t, keep = _tex(src)

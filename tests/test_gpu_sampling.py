@@ -188,3 +188,30 @@ def test_ortho_antiringing(gpu, oracle):
     src = rand_tex(45, 80, 4, seed=33)
     got, want = _ortho_case(gpu, oracle, "lanczos", src, 160, 45, 4, antiring=0.8)
     assert max_ulp32(got, want) <= 1
+
+
+# ---- built-in fast scalers (sampling.c:319-478) -------------------------------------------
+@pytest.mark.parametrize("kind", ["bicubic", "hermite", "gaussian", "oversample"])
+@pytest.mark.parametrize("size", [(160, 90), (211, 119), (57, 31)])
+def test_builtin_fast_scalers(gpu, oracle, kind, size):
+    """pl_shader_sample_bicubic / hermite / gaussian / oversample: up- and down-scaling of an
+    80x45 texture, whole and cropped source rects; same fp32 operation sequence on both sides,
+    so the comparison is exact (gaussian uses the shared exp definition)."""
+    src = rand_tex(45, 80, 4, seed=41)
+    extra = [0.2] if kind == "oversample" else []
+    for rect in ((0, 0, 0, 0), (3.25, 2.5, 70.0, 40.75)):
+        got = gpu.simple(kind, src, "rgba32f", size[0], size[1], comps=4, rect=rect, scale=1.5,
+                         sargs_extra=extra)
+        want = oracle.sample_fast(src.astype(np.float32), size[0], size[1], kind,
+                                  rect=None if not any(rect) else rect, scale=1.5,
+                                  threshold=0.2 if kind == "oversample" else 0.0,
+                                  coord_mode=T.COORD_EXACT)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+            (kind, size, rect, np.abs(got - want).max(), np.mean(got != want))
+
+
+def test_oversample_without_threshold_and_unorm_source(gpu, oracle):
+    src = (rand_tex(30, 40, 2, seed=42) * 65535).astype(np.uint16)
+    got = gpu.simple("oversample", src, "rg16", 100, 75, comps=2, sargs_extra=[0.0])
+    want = oracle.sample_fast(T.unorm16_to_float(src), 100, 75, "oversample", coord_mode=T.COORD_EXACT)
+    assert np.array_equal(got[..., :2].view(np.uint32), want[..., :2].view(np.uint32))
