@@ -766,6 +766,8 @@ PL_API void pl_shader_decode_color(pl_shader sh, struct pl_color_repr *repr,
                                    const struct pl_color_adjustment *params);
 PL_API void pl_shader_encode_color(pl_shader sh, const struct pl_color_repr *repr);
 PL_API void pl_shader_linearize(pl_shader sh, const struct pl_color_space *csp);
+/* shaders/colorspace.h:185-189: perceptual intensity of the (non-linear) input colour in `csp` */
+PL_API void pl_shader_extract_features(pl_shader sh, struct pl_color_space csp);
 PL_API void pl_shader_delinearize(pl_shader sh, const struct pl_color_space *csp);
 struct pl_sigmoid_params { float center, slope; };
 #define PL_SIGMOID_DEFAULTS .center = 0.75, .slope = 6.50,

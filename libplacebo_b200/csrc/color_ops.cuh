@@ -741,6 +741,15 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
             }
             break;
         }
+        case PLB_OP_FEATURES: {
+            // lms = (k * M) * rgb; PQ (clamped at 0); I = dot((0.4, 0.4, 0.2), lms)
+            float lms[3] = { c[0], c[1], c[2] };
+            plb_matv(op.u.features.m, lms[0], lms[1], lms[2]);
+            plb_pq_oetf3(lms, true, 1.0f);
+            c[0] = __fmaf_rn(0.2f, lms[2], __fmaf_rn(0.4f, lms[1], 0.4f * lms[0]));
+            c[1] = 0.0f; c[2] = 0.0f; c[3] = 1.0f;
+            break;
+        }
         case PLB_OP_LINEARIZE:   plb_linearize(op.u.trc, c); break;
         case PLB_OP_DELINEARIZE: plb_delinearize(op.u.trc, c); break;
         case PLB_OP_DECODE_SPECIAL: plb_decode_special(op.u.special.sys, c); break;

@@ -54,6 +54,9 @@ struct plb_tex_desc {
     // without the copy pass: the values are identical.
     void *ptr2;
     size_t pitch2;
+    // how fetches outside the texture resolve: enum pl_tex_address_mode of the sampling site
+    // (pl_sample_src.address_mode); 0 = clamp to edge
+    int addr;
 };
 
 // The private object behind a pl_tex (public part first, like PL_PRIV in src/pl_alloc.h)
@@ -149,6 +152,7 @@ enum plb_op_kind {
     PLB_OP_GAMMA,          // color adjustment gamma
     PLB_OP_PEAK,           // pl_shader_detect_peak tap (needs block-wide reduction)
     PLB_OP_SWIZZLE,        // swizzle_color (src/renderer.c:791-808)
+    PLB_OP_FEATURES,       // pl_shader_extract_features: linear RGB -> IPT intensity
 };
 
 struct plb_trc_consts {
@@ -207,6 +211,7 @@ struct plb_color_op {
         struct { float g; } gamma;
         struct plb_op_peak peak;
         struct { int8_t map[4]; int comps; int force_alpha; } swizzle;
+        struct { float m[9]; } features;  // (SDR_WHITE / 10000) * rgb2lms
     } u;
 };
 

@@ -132,9 +132,22 @@ PLB_DEV float4 plb_load(const plb_tex_desc &t, int x, int y)
 }
 
 
+// Texel index under the sampler's address mode (GL/Vulkan CLAMP_TO_EDGE, REPEAT,
+// MIRRORED_REPEAT); the mode is launch-uniform.
+PLB_DEV int plb_wrap_index(int i, int n, int mode)
+{
+    if (mode == 0)
+        return plb_clampi(i, 0, n - 1);
+    const int period = mode == 1 ? n : 2 * n;
+    i %= period;
+    if (i < 0)
+        i += period;
+    return i < n ? i : period - 1 - i;
+}
+
 PLB_DEV float4 plb_load_clamped(const plb_tex_desc &t, int x, int y)
 {
-    return plb_load(t, plb_clampi(x, 0, t.w - 1), plb_clampi(y, 0, t.h - 1));
+    return plb_load(t, plb_wrap_index(x, t.w, t.addr), plb_wrap_index(y, t.h, t.addr));
 }
 
 // textureLod(NEAREST) at normalised coords

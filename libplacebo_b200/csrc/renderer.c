@@ -557,7 +557,9 @@ static bool dispatch_sampler(struct pass_state *pass, pl_shader sh, struct sampl
     pl_renderer rr = pass->rr;
     const struct pl_render_params *params = pass->params;
     const struct sampler_info info = sample_src_info(pass, src, usage);
-    if (info.dir == SAMPLER_NOOP || info.type == SAMPLER_DIRECT)
+    // by type only (renderer.c:702-724): an unscaled source is SAMPLER_NEAREST, not a bilinear
+    // fetch at texel centres
+    if (info.type == SAMPLER_DIRECT)
         return pl_shader_sample_direct(sh, src);
     if (info.type == SAMPLER_NEAREST)
         return pl_shader_sample_nearest(sh, src);

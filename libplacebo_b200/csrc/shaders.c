@@ -314,6 +314,11 @@ static bool setup_src(pl_shader sh, const struct pl_sample_src *src, struct src_
         src->rect.x0, src->rect.y0, src->rect.x0 + o->src_w, src->rect.y0 + o->src_h,
     };
     o->tex = plb_tex_priv(tex)->d;
+    if ((int) src->address_mode < 0 || src->address_mode >= PL_TEX_ADDRESS_MODE_COUNT) {
+        plb_shader_fail(sh, "%s: invalid address mode %d", who, (int) src->address_mode);
+        return false;
+    }
+    o->tex.addr = src->address_mode;
     plb_shader_use_tex(sh, tex);
     if (!require_input_none(sh, resizable ? 0 : o->out_w, resizable ? 0 : o->out_h, who))
         return false;
@@ -1014,6 +1019,26 @@ void pl_shader_unsigmoidize(pl_shader sh, const struct pl_sigmoid_params *params
 {
     if (plb_shader_require_color(sh, "pl_shader_unsigmoidize"))
         push_sigmoid(sh, params, PLB_OP_UNSIGMOID);
+}
+
+// pl_shader_extract_features (shaders/colorspace.c:1383-1404): the perceptual intensity (the I
+// of IPT-PQ) of the colour, the input of the contrast-recovery low-pass. GLSL:
+//   lms = <0.020300> * M * color.rgb   -- scalar * mat3 first, then the vector product
+void pl_shader_extract_features(pl_shader sh, struct pl_color_space csp)
+{
+    if (!plb_shader_require_color(sh, "pl_shader_extract_features"))
+        return;
+    plb_shader_describe(sh, "feature extraction");
+    pl_shader_linearize(sh, &csp);
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_FEATURES);
+    if (!op)
+        return;
+    const pl_matrix3x3 m = pl_ipt_rgb2lms(pl_raw_primaries_get(csp.primaries));
+    const float k = (float) glsl6(PL_COLOR_SDR_WHITE / 10000);
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            op->u.features.m[3 * i + j] = k * (float) m.m[i][j];
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -121,10 +121,22 @@ static inline void coord_texel(const struct coord_ctx *c, int gx, int gy,
     }
 }
 
+// texel index under the sampler's address mode (CLAMP_TO_EDGE / REPEAT / MIRRORED_REPEAT)
+static inline int wrap_index(int i, int n, int mode)
+{
+    if (mode == 0)
+        return clampi(i, 0, n - 1);
+    const int period = mode == 1 ? n : 2 * n;
+    i %= period;
+    if (i < 0)
+        i += period;
+    return i < n ? i : period - 1 - i;
+}
+
 static inline const float *texel(const struct orc_tex *t, int x, int y)
 {
-    x = clampi(x, 0, t->w - 1);
-    y = clampi(y, 0, t->h - 1);
+    x = wrap_index(x, t->w, t->addr);
+    y = wrap_index(y, t->h, t->addr);
     return t->data + ((size_t) y * t->w + x) * t->comps;
 }
 
@@ -146,6 +158,13 @@ static inline void tex_linear(const struct orc_tex *t, float u, float v, float o
     const float *c = texel(t, x, y + 1), *d = texel(t, x + 1, y + 1);
     for (int k = 0; k < t->comps; k++)
         out[k] = mixf(mixf(a[k], b[k], fx), mixf(c[k], d[k], fx), fy);
+}
+
+float orc_tex_linear_r(const struct orc_tex *t, float u, float v)
+{
+    float out[4] = {0, 0, 0, 1};
+    tex_linear(t, u, v, out);
+    return out[0];
 }
 
 // ------------------------------------------------------------------------------------------

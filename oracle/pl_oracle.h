@@ -58,6 +58,7 @@ enum orc_coord_mode {
 struct orc_tex {
     int w, h, comps;
     const float *data;
+    int addr;   // sampler address mode: 0 clamp to edge, 1 repeat, 2 mirrored repeat
 };
 
 struct orc_rect { float x0, y0, x1, y1; };
@@ -216,7 +217,14 @@ struct orc_color_map_params {
     // gamut 3DLUT, rgba16 unorm texels as floats (v/65535), I fastest, then C, then h
     const float *gamut_lut; int lut_I, lut_C, lut_h;
     float gamut_min_luma, gamut_max_luma;
+    // contrast recovery (:1879-1921): low-pass feature map (1 component), strength, and the
+    // image geometry (pixels are row-major width x height) for the map's sampling position
+    const struct orc_tex *feature_map;
+    float contrast_recovery;
+    int width, height;
 };
+// bilinear fetch of component 0 (textureLod(...).r) under the texture's address mode
+float orc_tex_linear_r(const struct orc_tex *t, float u, float v);
 ORC_API void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *p);
 
 // --- dithering (src/shaders/dithering.c) -----------------------------------------------
@@ -257,6 +265,9 @@ struct orc_av1_grain_params {
 };
 ORC_API void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *luma,
                            const struct orc_av1_grain_params *p, float *dst);
+
+// pl_shader_extract_features (colorspace.c:1383-1404) on linear RGB; m = rgb2lms (float)
+ORC_API void orc_extract_features(float *rgba, size_t npix, const float m[9]);
 
 // --- H.274 film grain (src/shaders/film_grain_h274.c) --------------------------------------
 struct orc_h274_grain_params {

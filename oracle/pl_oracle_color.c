@@ -355,6 +355,34 @@ static inline float pq_oetf_lit(const struct pq_lit *q, float x, int clamp0)
     return pm_powf(x, q->m2);
 }
 
+// pl_shader_extract_features (src/shaders/colorspace.c:1383-1404), after pl_shader_linearize:
+//   vec3 lms = <0.020300> * M * color.rgb;  (scalar * mat3 evaluates first: `km` = k * M)
+//   lms = pow(max(lms, 0.0), vec3(M1)); lms = (c1 + c2 lms) / (1 + c3 lms); lms = pow(lms, M2);
+//   float I = dot(vec3(0.400000, 0.400000, 0.200000), lms);  color = vec4(I, 0.0, 0.0, 1.0);
+// `m` = the float rgb2lms matrix the host passes as a uniform (pl_ipt_rgb2lms).
+void orc_extract_features(float *rgba, size_t npix, const float m[9])
+{
+    const struct pq_lit q = pq_literal();
+    float km[9];
+    for (int i = 0; i < 9; i++)
+        km[i] = q.to_pq * m[i];
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < npix; i++) {
+        float *p = rgba + 4 * i;
+        float lms[3];
+        for (int k = 0; k < 3; k++) {
+            float v = km[3*k] * p[0];
+            v = fmaf(km[3*k + 1], p[1], v);
+            v = fmaf(km[3*k + 2], p[2], v);
+            lms[k] = pq_oetf_lit(&q, v, 1);
+        }
+        p[0] = fmaf(0.2f, lms[2], fmaf(0.4f, lms[1], 0.4f * lms[0]));
+        p[1] = 0.0f;
+        p[2] = 0.0f;
+        p[3] = 1.0f;
+    }
+}
+
 void orc_decode_special(float *rgba, size_t npix, int sys)
 {
     const struct pq_lit q = pq_literal();
@@ -729,6 +757,20 @@ static inline float lut1d_linear(const float *lut, int n, float x)
     return mixf(lut[(int) fbase], lut[(int) fceil], fpos - fbase);
 }
 
+// `tone_map(x)` of pl_shader_color_map_ex: clip / linear fast paths or the 1-D LUT (:1826-1876)
+static inline float tone_map_x(const struct orc_color_map_params *p, float x, float lin_a,
+                               float lin_b, float tone_a, float tone_b)
+{
+    if (p->tone_kind == 1)
+        return clampf(x, p->tone_input_min, p->tone_input_max);
+    if (p->tone_kind == 2) {
+        x = lin_a * x + lin_b;
+        x = clampf(x, 0.0f, 1.0f);
+        return (p->tone_output_max - p->tone_output_min) * x + p->tone_output_min;
+    }
+    return lut1d_linear(p->tone_lut, p->tone_lut_size, tone_a * x + tone_b);
+}
+
 void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *p)
 {
     const struct pq_lit q = pq_literal();
@@ -770,14 +812,46 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
 
         if (p->need_tone_map) {
             float x = ipt[0];
-            if (p->tone_kind == 1) {
-                x = clampf(x, p->tone_input_min, p->tone_input_max);
-            } else if (p->tone_kind == 2) {
-                x = lin_a * x + lin_b;
-                x = clampf(x, 0.0f, 1.0f);
-                x = (p->tone_output_max - p->tone_output_min) * x + p->tone_output_min;
+            // contrast recovery :1879-1921 (only when tone.input_max >= tone.output_max; the
+            // caller passes feature_map = NULL otherwise)
+            if (p->feature_map && p->contrast_recovery) {
+                const struct orc_tex *fm = p->feature_map;
+                // `pos` of sh_bind without a rect: the whole feature map over the output
+                const float lpos[2] = { (float) (((double) (n % p->width) + 0.5) / p->width),
+                                        (float) (((double) (n / p->width) + 0.5) / p->height) };
+                const float lpt[2] = { (float) (1.0 / fm->w), (float) (1.0 / fm->h) };
+                const float lsize[2] = { (float) fm->w, (float) fm->h };
+                float g[4], h[4];
+                for (int a = 0; a < 2; a++) {
+                    const float t = lpos[a] * lsize[a] + 0.5f;
+                    const float frac = t - floorf(t), frac2 = frac * frac;
+                    const float inv = 1.0f - frac, inv2 = inv * inv;
+                    const float w0 = (1.0f / 6.0f) * inv2 * inv;
+                    const float w1 = (2.0f / 3.0f) - 0.5f * frac2 * (2.0f - frac);
+                    const float w2 = (2.0f / 3.0f) - 0.5f * inv2 * (2.0f - inv);
+                    const float w3 = (1.0f / 6.0f) * frac2 * frac;
+                    g[a] = w0 + w1;
+                    g[2 + a] = w2 + w3;
+                    h[a] = w1 / g[a] + inv;
+                    h[2 + a] = w3 / g[2 + a] + inv;
+                    h[a] -= 2.0f;
+                }
+                const float px_ = lpos[0] + lpt[0] * h[0], py_ = lpos[1] + lpt[1] * h[1];
+                const float pz_ = lpos[0] + lpt[0] * h[2], pw_ = lpos[1] + lpt[1] * h[3];
+                const float l00 = orc_tex_linear_r(fm, px_, py_), l01 = orc_tex_linear_r(fm, px_, pw_);
+                const float l0 = l01 * (1.0f - g[1]) + l00 * g[1];
+                const float l10 = orc_tex_linear_r(fm, pz_, py_), l11 = orc_tex_linear_r(fm, pz_, pw_);
+                const float l1 = l11 * (1.0f - g[1]) + l10 * g[1];
+                const float luma = l1 * (1.0f - g[0]) + l0 * g[0];
+                const float highres = clampf(ipt[0], 0.0f, 1.0f);
+                const float lowres = clampf(luma, 0.0f, 1.0f);
+                const float detail = highres - lowres;
+                const float base = tone_map_x(p, highres, lin_a, lin_b, tone_a, tone_b);
+                const float sharp = tone_map_x(p, lowres, lin_a, lin_b, tone_a, tone_b) + detail;
+                x = base * (1.0f - p->contrast_recovery) + sharp * p->contrast_recovery;
+                x = clampf(x, p->tone_output_min, p->tone_output_max);
             } else {
-                x = lut1d_linear(p->tone_lut, p->tone_lut_size, tone_a * x + tone_b);
+                x = tone_map_x(p, x, lin_a, lin_b, tone_a, tone_b);
             }
             ipt[0] = x;
             // hull desaturation :1930-1932

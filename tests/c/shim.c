@@ -231,7 +231,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
 
     /* sargs: [0..3] rect (all zero = full), [4] new_w, [5] new_h, [6] components, [7] scale,
      *        deband: [8] iterations [9] threshold [10] radius [11] grain [12..14] neutral
-     *        scalers: [8] antiring (<0 = filter default) */
+     *        scalers: [8] antiring (<0 = filter default); all: [15] address mode */
     struct pl_sample_src ssrc = {
         .tex = src,
         .rect = { sargs[0], sargs[1], sargs[2], sargs[3] },
@@ -239,6 +239,7 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
         .new_h = (int) sargs[5],
         .components = (int) sargs[6],
         .scale = sargs[7],
+        .address_mode = (int) sargs[15],    /* enum pl_tex_address_mode */
     };
     bool ok = true;
     switch (src_kind) {
@@ -371,6 +372,12 @@ API int shim_run(struct shim_ctx *c, void *src_tex, void *dst_tex, int src_kind,
             };
             a += 3;
             pl_shader_decode_color(sh, &repr, NULL);
+            break;
+        }
+        case 12: { /* pl_shader_extract_features */
+            struct pl_color_space csp = csp_from_flat(a);
+            a += CSP_FLOATS;
+            pl_shader_extract_features(sh, csp);
             break;
         }
         default:

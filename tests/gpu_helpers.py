@@ -96,13 +96,14 @@ class Gpu:
             self.free(s, d)
 
     def simple(self, kind, src, src_fmt, dw, dh, out_fmt="rgba32f", sargs_extra=(), rect=(0, 0, 0, 0),
-               comps=4, scale=0.0, ops=(), oargs=(), filt=None, want_peak=False):
+               comps=4, scale=0.0, ops=(), oargs=(), filt=None, want_peak=False, address=0):
         h, w = src.shape[:2]
         s = self.tex(src_fmt, w, h, src)
         d = self.tex(out_fmt, dw, dh)
         try:
-            peak = self.run(s, d, kind, list(rect) + [dw, dh, comps, scale] + list(sargs_extra),
-                            filt, ops, oargs, want_peak)
+            sargs = list(rect) + [dw, dh, comps, scale] + list(sargs_extra)
+            sargs += [0.0] * (15 - len(sargs)) + [float(address)]
+            peak = self.run(s, d, kind, sargs, filt, ops, oargs, want_peak)
             out = self.download(d, out_fmt, dw, dh)
             return (out, peak) if want_peak else out
         finally:

@@ -258,7 +258,7 @@ class T0:
 # oracle bindings
 # ----------------------------------------------------------------------------------------
 class OrcTex(C.Structure):
-    _fields_ = [("w", C.c_int), ("h", C.c_int), ("comps", C.c_int), ("data", FP)]
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("comps", C.c_int), ("data", FP), ("addr", C.c_int)]
 
 
 class OrcRect(C.Structure):
@@ -371,7 +371,9 @@ class OrcColorMap(C.Structure):
                 ("tone_output_min", C.c_float), ("tone_output_max", C.c_float),
                 ("tone_exposure", C.c_float),
                 ("gamut_lut", FP), ("lut_I", C.c_int), ("lut_C", C.c_int), ("lut_h", C.c_int),
-                ("gamut_min_luma", C.c_float), ("gamut_max_luma", C.c_float)]
+                ("gamut_min_luma", C.c_float), ("gamut_max_luma", C.c_float),
+                ("feature_map", C.POINTER(OrcTex)), ("contrast_recovery", C.c_float),
+                ("width", C.c_int), ("height", C.c_int)]
 
 
 class OrcDither(C.Structure):
@@ -379,12 +381,12 @@ class OrcDither(C.Structure):
                 ("temporal", C.c_int), ("frame_index", C.c_uint32), ("gamma", C.c_float)]
 
 
-def _tex(a):
+def _tex(a, addr=0):
     a = np.ascontiguousarray(a, f32)
     if a.ndim == 2:
         a = a[:, :, None]
     h, w, c = a.shape
-    return OrcTex(w, h, c, fp(a)), a
+    return OrcTex(w, h, c, fp(a), addr), a
 
 
 class Oracle:
@@ -417,8 +419,8 @@ class Oracle:
         return out
 
     def sample_ortho(self, src, dw, dh, filt, pass_, comp_mask=None, rect=None, scale=1.0,
-                     coord_mode=COORD_LITERAL, antiring=None, ratio=None, lut=None):
-        t, keep = _tex(src)
+                     coord_mode=COORD_LITERAL, antiring=None, ratio=None, lut=None, address=0):
+        t, keep = _tex(src, address)
         comp_mask = (1 << keep.shape[2]) - 1 if comp_mask is None else comp_mask
         rect = rect or (0, 0, keep.shape[1], keep.shape[0])
         use_linear = filt["radius"] == filt["radius_zero"]
@@ -433,8 +435,8 @@ class Oracle:
         return out
 
     def sample_direct(self, src, dw, dh, linear=False, rect=None, scale=1.0,
-                      coord_mode=COORD_LITERAL, ext=None):
-        t, keep = _tex(src)
+                      coord_mode=COORD_LITERAL, ext=None, address=0):
+        t, keep = _tex(src, address)
         rect = rect or (0, 0, keep.shape[1], keep.shape[0])
         out = self._ext_out(dw, dh, ext)
         self.lib.orc_sample_direct(C.byref(t), OrcRect(*rect), dw, dh, int(linear),
@@ -443,9 +445,9 @@ class Oracle:
         return out
 
     def sample_fast(self, src, dw, dh, kind, rect=None, scale=1.0, threshold=0.0,
-                    coord_mode=COORD_LITERAL):
+                    coord_mode=COORD_LITERAL, address=0):
         """kind: bicubic / hermite / gaussian / oversample (sampling.c:319-478)."""
-        t, keep = _tex(src)
+        t, keep = _tex(src, address)
         rect = rect or (0, 0, keep.shape[1], keep.shape[0])
         out = self._ext_out(dw, dh, None)
         rx, ry = dw / abs(rect[2] - rect[0]), dh / abs(rect[3] - rect[1])
@@ -539,6 +541,13 @@ class Oracle:
         out = np.zeros((keep.shape[0], keep.shape[1], 4), f32)
         self.lib.orc_h274_grain(C.byref(t), C.byref(params), fp(out))
         return out
+
+    def extract_features(self, rgba, m):
+        """rgba: linear light; m: rgb2lms (9 floats). Returns (I, 0, 0, 1)."""
+        rgba = np.ascontiguousarray(rgba, f32).copy()
+        m = np.ascontiguousarray(m, f32)
+        self.lib.orc_extract_features(fp(rgba), C.c_size_t(rgba.size // 4), fp(m))
+        return rgba
 
     def dovi_reshape(self, rgba, meta):
         rgba = np.ascontiguousarray(rgba, f32).copy()

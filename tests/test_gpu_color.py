@@ -278,3 +278,20 @@ def test_error_diffusion_depths_and_tall_images(gpu, oracle, depth, size):
         gpu.free(s, d)
     want = oracle.error_diffusion(src, depth, k)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_extract_features(gpu, oracle):
+    """pl_shader_extract_features (colorspace.c:1383-1404) on an HDR10 PQ and an SDR source."""
+    src = rgb(3)
+    for csp in (T.csp(T.PRIM["BT_2020"], T.TRC["PQ"], max_luma=1000), T.csp(T.PRIM["BT_709"], T.TRC["BT_1886"])):
+        got = run_ops(gpu, src, [12], [csp])
+        t0 = T.t0()
+        c2 = t0.csp_infer(csp)
+        smin, smax, _ = t0.nominal_luma(c2, T.META["HDR10"], T.HDR["NORM"])
+        lin = oracle.linearize(src, int(c2[1]), smin, smax, P.luma_coeffs(t0, int(c2[0])))
+        want = oracle.extract_features(lin, t0.matrix(2, t0.raw_primaries(int(c2[0]))))
+        assert np.array_equal(got[..., 1:], want[..., 1:])
+        e = relerr(got[..., :1], want[..., :1], 1e-5)
+        assert e.max() < 2e-6, e.max()
+        if int(c2[1]) == T.TRC["PQ"]:  # no host-side libm constants on this path: exact
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

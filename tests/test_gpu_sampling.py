@@ -215,3 +215,35 @@ def test_oversample_without_threshold_and_unorm_source(gpu, oracle):
     got = gpu.simple("oversample", src, "rg16", 100, 75, comps=2, sargs_extra=[0.0])
     want = oracle.sample_fast(T.unorm16_to_float(src), 100, 75, "oversample", coord_mode=T.COORD_EXACT)
     assert np.array_equal(got[..., :2].view(np.uint32), want[..., :2].view(np.uint32))
+
+
+# ---- sampler address modes (pl_sample_src.address_mode) -------------------------------------
+@pytest.mark.parametrize("address", [1, 2])  # PL_TEX_ADDRESS_REPEAT, PL_TEX_ADDRESS_MIRROR
+@pytest.mark.parametrize("kind", ["bilinear", "nearest", "bicubic"])
+def test_address_modes_direct(gpu, oracle, kind, address):
+    """A source rect reaching far outside the texture: fetches wrap / mirror per texel index."""
+    src = rand_tex(20, 30, 4, seed=51)
+    rect = (-41.5, -27.25, 65.0, 52.5)
+    got = gpu.simple(kind, src, "rgba32f", 96, 64, comps=4, rect=rect, address=address)
+    if kind == "bicubic":
+        want = oracle.sample_fast(src.astype(np.float32), 96, 64, kind, rect=rect,
+                                  coord_mode=T.COORD_EXACT, address=address)
+    else:
+        want = oracle.sample_direct(src.astype(np.float32), 96, 64, linear=kind == "bilinear",
+                                    rect=rect, coord_mode=T.COORD_EXACT, address=address)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.mean(got != want)
+    clamped = oracle.sample_direct(src.astype(np.float32), 96, 64, linear=True, rect=rect,
+                                   coord_mode=T.COORD_EXACT)
+    assert np.mean(clamped != want) > 0.3  # the mode matters for this rect
+
+
+def test_address_mode_mirror_separable_downscale(gpu, oracle):
+    """The contrast-recovery low-pass of the reference (renderer.c:2126-2140): bicubic
+    downscaling with a widened kernel and PL_TEX_ADDRESS_MIRROR."""
+    src = rand_tex(45, 80, 1, seed=52)
+    f = T.t0().filter_generate("bicubic", blur=45 / 13, polar=False)
+    got = gpu.simple("ortho", src, "r32f", 80, 13, comps=1, filt="bicubic", sargs_extra=[-1.0], address=2)
+    want = oracle.sample_ortho(src.astype(np.float32), 80, 13, f, 0, comp_mask=1,
+                               coord_mode=T.COORD_EXACT, ratio=13 / 45, address=2)
+    d = np.abs(got[..., 0] - want[..., 0])
+    assert d.max() < 2e-6, d.max()

@@ -95,3 +95,26 @@ def test_pq_constants():
             y = pt.hdr_rescale(T.HDR["NORM"], T.HDR["PQ"], pt.hdr_rescale(T.HDR["PQ"], T.HDR["NORM"], float(x)))
             assert feq(float(x), y, 1e-5), (x, y)
             x = x_next
+
+
+@pytest.mark.parametrize("kind", ["bicubic", "hermite", "gaussian"])
+def test_fast_scalers_equal_their_filter_kernels(oracle, kind):
+    """The built-in fast scalers (sampling.c:319-440) fold the four taps of their kernel into
+    bilinear fetches; at an exact 2x ratio their result must equal the separable convolution with
+    the same pl_filter_config (cubic B-spline, Hermite, Gaussian) up to LUT / rounding noise.
+    Pins the oracle's restatement of the GLSL to the reference's filter definitions."""
+    rng = np.random.default_rng(0)
+    src = rng.random((24, 32, 4), dtype=np.float32)
+    fast = oracle.sample_fast(src, 64, 48, kind, coord_mode=T.COORD_EXACT)
+    f = T.t0().filter_generate(kind, polar=False)
+    v = oracle.sample_ortho(src, 32, 48, f, 0, comp_mask=15, coord_mode=T.COORD_EXACT, ratio=2.0)
+    sep = oracle.sample_ortho(v, 64, 48, f, 1, comp_mask=15, coord_mode=T.COORD_EXACT, ratio=2.0)
+    assert np.abs(fast - sep)[4:-4, 4:-4].max() < 2e-5
+
+
+def test_oversample_is_nearest_at_integer_ratios(oracle):
+    rng = np.random.default_rng(1)
+    src = rng.random((24, 32, 4), dtype=np.float32)
+    ov = oracle.sample_fast(src, 64, 48, "oversample", coord_mode=T.COORD_EXACT)
+    nn = oracle.sample_direct(src, 64, 48, linear=False, coord_mode=T.COORD_EXACT)
+    assert np.abs(ov - nn).max() < 2e-6
