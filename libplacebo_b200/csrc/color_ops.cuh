@@ -93,17 +93,19 @@ PLB_DEV float plb_pq_oetf(float x, bool clamp0)
     return plm_powf(x, c_pq.m2);
 }
 
-PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
+// `trc` is passed beside the constants so that a caller that knows it at compile time (the
+// specialised HDR output pass, k_pixel_hdr) gets the one case it needs and nothing else.
+PLB_DEV void plb_linearize(const int trc, const plb_trc_consts &t, float c[3])
 {
-    if (t.trc == TRC_LINEAR)
+    if (trc == TRC_LINEAR)
         return;
-    if (t.trc != TRC_SCRGB) {
+    if (trc != TRC_SCRGB) {
         #pragma unroll
         for (int k = 0; k < 3; k++)
             c[k] = fmaxf(c[k], 0.0f);
     }
     bool post_scale = false;
-    switch (t.trc) {
+    switch (trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
             c[k] = 0.04045f < c[k] ? plm_powf((c[k] + 0.055f) / 1.055f, 2.4f)
@@ -176,9 +178,9 @@ PLB_DEV void plb_linearize(const plb_trc_consts &t, float c[3])
     }
 }
 
-PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
+PLB_DEV void plb_delinearize(const int trc, const plb_trc_consts &t, float c[3])
 {
-    if (t.trc == TRC_LINEAR)
+    if (trc == TRC_LINEAR)
         return;
     if (t.black_scaled) {
         const float ps_a = 1 / (t.csp_max - t.csp_min), ps_b = -t.csp_min / (t.csp_max - t.csp_min);
@@ -186,12 +188,12 @@ PLB_DEV void plb_delinearize(const plb_trc_consts &t, float c[3])
         for (int k = 0; k < 3; k++)
             c[k] = ps_a * c[k] + ps_b;
     }
-    if (t.trc != TRC_SCRGB) {
+    if (trc != TRC_SCRGB) {
         #pragma unroll
         for (int k = 0; k < 3; k++)
             c[k] = fmaxf(c[k], 0.0f);
     }
-    switch (t.trc) {
+    switch (trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
             c[k] = 0.0031308f <= c[k] ? 1.055f * plm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
@@ -517,7 +519,7 @@ PLB_DEV float plb_round_fbo(float v, int kind, int bits)
 PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
 {
     float c[3] = { c_in[0], c_in[1], c_in[2] };
-    plb_linearize(p.lin, c);
+    plb_linearize(p.lin.trc, p.lin, c);
     float luma = plb_dot3_fma(p.lin.luma[0], p.lin.luma[1], p.lin.luma[2], c[0], c[1], c[2]);
     const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
                 PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
@@ -599,52 +601,84 @@ PLB_DEV void plb_dovi_reshape(float c[4])
 // transcendental): cheap enough to run inline, register-resident, in the resampling kernels
 // (e.g. the output pass of an SDR upscale: 1/scale, swizzle). plb_prog_is_light() on the host
 // decides; the semantics are those of the corresponding cases of plb_run_color_ops.
+PLB_DEV void plb_light_step(const plb_color_op &op, const int kind, float c[4])
+{
+    if (kind == PLB_OP_SCALE) {
+        const float s = op.u.scale.s;
+        c[0] *= s; c[1] *= s; c[2] *= s;
+        if (op.u.scale.with_alpha)
+            c[3] *= s;
+    } else if (kind == PLB_OP_MATRIX) {
+        plb_matv(op.u.matrix.m, c[0], c[1], c[2]);
+        if (op.u.matrix.has_c) {
+            c[0] += op.u.matrix.c[0]; c[1] += op.u.matrix.c[1]; c[2] += op.u.matrix.c[2];
+        }
+    } else if (kind == PLB_OP_ROUND_FBO) {
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            c[k] = plb_round_fbo(c[k], op.u.round_fbo.kind, op.u.round_fbo.bits);
+    } else if (kind == PLB_OP_ALPHA) {
+        if (op.u.alpha.to == PL_ALPHA_NONE && op.u.alpha.from == PL_ALPHA_UNKNOWN) {
+            c[3] = 1.0f;
+        } else if (op.u.alpha.from == PL_ALPHA_INDEPENDENT && op.u.alpha.to == PL_ALPHA_PREMULTIPLIED) {
+            c[0] *= c[3]; c[1] *= c[3]; c[2] *= c[3];
+        } else if (op.u.alpha.from == PL_ALPHA_PREMULTIPLIED && op.u.alpha.to != PL_ALPHA_PREMULTIPLIED) {
+            if (c[3] > 1e-6f) {
+                c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3];
+            }
+            if (op.u.alpha.to == PL_ALPHA_NONE)
+                c[3] = 1.0f;
+        }
+    } else if (kind == PLB_OP_SWIZZLE) {
+        const float o0 = c[0], o1 = c[1], o2 = c[2], o3 = c[3];
+        float r[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int m = op.u.swizzle.map[k];
+            if (k < op.u.swizzle.comps && m >= 0)
+                r[k] = m == 0 ? o0 : m == 1 ? o1 : m == 2 ? o2 : o3;
+        }
+        if (op.u.swizzle.force_alpha)
+            r[3] = o3;
+        c[0] = r[0]; c[1] = r[1]; c[2] = r[2]; c[3] = r[3];
+    }
+}
+
 PLB_DEV void plb_run_light_ops(float c[4])
 {
     const plb_color_prog &prog = plb_s_prog;
     #pragma unroll 1
     for (int i = 0; i < prog.n; i++) {
         const plb_color_op &op = prog.ops[i];
+        plb_light_step(op, op.kind, c);
+    }
+}
+
+// The output pass of an HDR -> SDR render (pass_convert_colors + pass_output_target,
+// renderer.c:2157-2279, 2586-2964) records: linearize (source transfer), tone / gamut mapping,
+// delinearize (target transfer), dither, and light steps around them. With the two transfer
+// functions fixed at compile time the step bodies are the single case each needs: ~1.5 k
+// instructions, register-resident colour and no local memory, against the general
+// interpreter's 6.9 k (which ncu shows stalling on instruction fetch, profiles/). Per-pixel
+// arithmetic is that of plb_run_color_ops, step for step.
+template <int LIN_TRC, int DELIN_TRC>
+PLB_DEV void plb_run_hdr_ops(int x, int y, float c[4])
+{
+    const plb_color_prog &prog = plb_s_prog;
+    #pragma unroll 1
+    for (int i = 0; i < prog.n; i++) {
+        const plb_color_op &op = prog.ops[i];
         const int kind = op.kind;
-        if (kind == PLB_OP_SCALE) {
-            const float s = op.u.scale.s;
-            c[0] *= s; c[1] *= s; c[2] *= s;
-            if (op.u.scale.with_alpha)
-                c[3] *= s;
-        } else if (kind == PLB_OP_MATRIX) {
-            plb_matv(op.u.matrix.m, c[0], c[1], c[2]);
-            if (op.u.matrix.has_c) {
-                c[0] += op.u.matrix.c[0]; c[1] += op.u.matrix.c[1]; c[2] += op.u.matrix.c[2];
-            }
-        } else if (kind == PLB_OP_ROUND_FBO) {
-            #pragma unroll
-            for (int k = 0; k < 4; k++)
-                c[k] = plb_round_fbo(c[k], op.u.round_fbo.kind, op.u.round_fbo.bits);
-        } else if (kind == PLB_OP_ALPHA) {
-            if (op.u.alpha.to == PL_ALPHA_NONE && op.u.alpha.from == PL_ALPHA_UNKNOWN) {
-                c[3] = 1.0f;
-            } else if (op.u.alpha.from == PL_ALPHA_INDEPENDENT && op.u.alpha.to == PL_ALPHA_PREMULTIPLIED) {
-                c[0] *= c[3]; c[1] *= c[3]; c[2] *= c[3];
-            } else if (op.u.alpha.from == PL_ALPHA_PREMULTIPLIED && op.u.alpha.to != PL_ALPHA_PREMULTIPLIED) {
-                if (c[3] > 1e-6f) {
-                    c[0] /= c[3]; c[1] /= c[3]; c[2] /= c[3];
-                }
-                if (op.u.alpha.to == PL_ALPHA_NONE)
-                    c[3] = 1.0f;
-            }
-        } else if (kind == PLB_OP_SWIZZLE) {
-            const float o0 = c[0], o1 = c[1], o2 = c[2], o3 = c[3];
-            float r[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int m = op.u.swizzle.map[k];
-                if (k < op.u.swizzle.comps && m >= 0)
-                    r[k] = m == 0 ? o0 : m == 1 ? o1 : m == 2 ? o2 : o3;
-            }
-            if (op.u.swizzle.force_alpha)
-                r[3] = o3;
-            c[0] = r[0]; c[1] = r[1]; c[2] = r[2]; c[3] = r[3];
-        }
+        if (kind == PLB_OP_LINEARIZE)
+            plb_linearize(LIN_TRC, op.u.trc, c);
+        else if (kind == PLB_OP_COLOR_MAP)
+            plb_color_map(op.u.cmap, c);
+        else if (kind == PLB_OP_DELINEARIZE)
+            plb_delinearize(DELIN_TRC, op.u.trc, c);
+        else if (kind == PLB_OP_DITHER)
+            plb_dither(op.u.dither, x, y, c);
+        else
+            plb_light_step(op, kind, c);
     }
 }
 
@@ -750,8 +784,8 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
             c[1] = 0.0f; c[2] = 0.0f; c[3] = 1.0f;
             break;
         }
-        case PLB_OP_LINEARIZE:   plb_linearize(op.u.trc, c); break;
-        case PLB_OP_DELINEARIZE: plb_delinearize(op.u.trc, c); break;
+        case PLB_OP_LINEARIZE:   plb_linearize(op.u.trc.trc, op.u.trc, c); break;
+        case PLB_OP_DELINEARIZE: plb_delinearize(op.u.trc.trc, op.u.trc, c); break;
         case PLB_OP_DECODE_SPECIAL: plb_decode_special(op.u.special.sys, c); break;
         case PLB_OP_ENCODE_SPECIAL: plb_encode_special(op.u.special.sys, c); break;
         case PLB_OP_SIGMOID:

@@ -176,6 +176,81 @@ static bool pixel_is_light(const struct plb_pixel_launch *p)
     return true;
 }
 
+// The HDR -> SDR output pass (linearize, tone / gamut mapping, delinearize, dither + light steps
+// on directly sampled planes): plb_run_hdr_ops with both transfer functions fixed at compile
+// time, everything but the transcendental functions inline, colour in registers.
+template <int LIN_TRC, int DELIN_TRC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_pixel_hdr(const __grid_constant__ plb_tail_args ap)
+{
+    plm_tables_init();
+    plb_tail_stage(ap);
+    __syncthreads();
+    const plb_tail_args &a = plb_s_tail;
+    const int gx = blockIdx.x * PIX_TILE + threadIdx.x;
+    if (gx >= a.out_w)
+        return;
+    #pragma unroll 1
+    for (int r = 0; r < PIX_TILE / 8; r++) {
+        const int gy = blockIdx.y * PIX_TILE + threadIdx.y + 8 * r;
+        if (gy >= a.out_h)
+            break;
+        float color[4] = { a.init[0], a.init[1], a.init[2], a.init[3] };
+        #pragma unroll 1
+        for (int i = 0; i < a.nplanes; i++) {
+            const plb_plane_src &pl = a.planes[i];
+            float posx, posy;
+            plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
+            const float4 c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
+            const float tmp[4] = { c4.x * pl.scale, c4.y * pl.scale, c4.z * pl.scale, c4.w * pl.scale };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = pl.map[k];
+                #pragma unroll
+                for (int j = 0; j < 4; j++)
+                    color[j] = m == j ? tmp[k] : color[j];
+            }
+        }
+        plb_run_hdr_ops<LIN_TRC, DELIN_TRC>(gx, gy, color);
+        plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy, make_float4(color[0], color[1], color[2], color[3]));
+    }
+}
+
+// Eligibility of k_pixel_hdr: direct planes only, a tone / gamut mapping step, PQ in and BT.1886
+// out wherever the program (de)linearizes, nothing that needs the general interpreter.
+static bool pixel_is_hdr(const struct plb_pixel_launch *p)
+{
+    if (!p->dst.ptr)
+        return false;
+    for (int i = 0; i < p->nplanes; i++) {
+        if (p->planes[i].kind != PLB_PLANE_DIRECT)
+            return false;
+    }
+    bool cmap = false;
+    for (int i = 0; i < p->prog.n; i++) {
+        const struct plb_color_op *op = &p->prog.ops[i];
+        switch (op->kind) {
+        case PLB_OP_SCALE: case PLB_OP_MATRIX: case PLB_OP_ROUND_FBO: case PLB_OP_ALPHA:
+        case PLB_OP_SWIZZLE: case PLB_OP_DITHER:
+            break;
+        case PLB_OP_COLOR_MAP:
+            cmap = true;
+            break;
+        case PLB_OP_LINEARIZE:
+            if (op->u.trc.trc != TRC_PQ)
+                return false;
+            break;
+        case PLB_OP_DELINEARIZE:
+            if (op->u.trc.trc != TRC_BT_1886)
+                return false;
+            break;
+        default:
+            return false;
+        }
+    }
+    return cmap;
+}
+
 extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
 {
     static plb_tail_args t;
@@ -186,6 +261,25 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
         k_pixel_light<<<grid, block, 0, STREAM(gpu)>>>(t);
         plb_gpu_priv(gpu)->launches++;
         return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_light");
+    }
+    static int hdr_mode = -1; // PLB_PIXEL_HDR=0 keeps the general kernel (measurements, A/B tests)
+    if (hdr_mode < 0) {
+        const char *e = getenv("PLB_PIXEL_HDR");
+        hdr_mode = e ? atoi(e) : 5;
+    }
+    if (hdr_mode > 0 && pixel_is_hdr(p)) {
+        dim3 block(32, 8);
+        dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
+        // measured on B200 (4K colour pass, µs): 3 CTAs/SM 923, 4: 930, 5 (48 registers): 909;
+        // the general kernel: 1260
+        if (hdr_mode == 3)
+            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 3><<<grid, block, 0, STREAM(gpu)>>>(t);
+        else if (hdr_mode == 4)
+            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 4><<<grid, block, 0, STREAM(gpu)>>>(t);
+        else
+            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 5><<<grid, block, 0, STREAM(gpu)>>>(t);
+        plb_gpu_priv(gpu)->launches++;
+        return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_hdr");
     }
     if (prog_has_peak(&p->prog)) {
         if (PIX_TILE % t.wg_w || PIX_TILE % t.wg_h ||

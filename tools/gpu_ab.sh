@@ -1,0 +1,22 @@
+#!/bin/bash
+# A/B measurement aid (run on the GPU box through gpurun): GPU parity tests with the default
+# build, then the HDR workload with each variant of the HDR output-pass kernel
+# (PLB_PIXEL_HDR = 0: general interpreter kernel; 3/4/5: k_pixel_hdr at that many CTAs per SM).
+export OMP_NUM_THREADS=16
+O=gpurun_out
+timeout 700 python -m pytest tests -q -m gpu -x --timeout 300 2>&1 | tail -4 > $O/ab_tests.log
+PLB_PIXEL_HDR=0 timeout 700 python -m pytest tests/test_gpu_render.py -q -m gpu -x --timeout 300 2>&1 | tail -2 >> $O/ab_tests.log
+for m in 4 0 3 5; do
+  PLB_PIXEL_HDR=$m timeout 200 python bench.py --steps 100 --no-cpu-baseline > $O/ab_c3_hdr$m.json 2>/dev/null
+done
+PLB_PIXEL_HDR=4 timeout 200 python bench.py --workload c4_4k_hdr10_to_sdr_av1_grain --steps 100 --no-cpu-baseline > $O/ab_c4_hdr4.json 2>/dev/null
+cat $O/ab_tests.log
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/ab_*.json")):
+    try:
+        j = json.load(open(f))
+        print(f, j["value"], j["ms_per_step"], [(p["pass"][:12], round(p["mean_us"])) for p in j["passes"]])
+    except Exception as e:
+        print(f, "ERR", e)
+PY
