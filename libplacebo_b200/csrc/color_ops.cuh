@@ -516,10 +516,10 @@ PLB_DEV float plb_round_fbo(float v, int kind, int bits)
 
 // PLB_OP_PEAK is handled by the kernel that owns the block-wide reduction; here we only
 // compute the per-pixel 14-bit PQ luma (colorspace.c:1279-1288, exact float constants)
-PLB_DEV uint32_t plb_peak_ypq(const plb_op_peak &p, const float c_in[4])
+PLB_DEV uint32_t plb_peak_ypq(const int trc, const plb_op_peak &p, const float c_in[4])
 {
     float c[3] = { c_in[0], c_in[1], c_in[2] };
-    plb_linearize(p.lin.trc, p.lin, c);
+    plb_linearize(trc, p.lin, c);
     float luma = plb_dot3_fma(p.lin.luma[0], p.lin.luma[1], p.lin.luma[2], c[0], c[1], c[2]);
     const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
                 PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
@@ -853,7 +853,7 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
         }
         case PLB_OP_PEAK:
             *peak_op = &op.u.peak;
-            *y_pq = plb_peak_ypq(op.u.peak, c);
+            *y_pq = plb_peak_ypq(op.u.peak.lin.trc, op.u.peak, c);
             break;
         default:
             break;

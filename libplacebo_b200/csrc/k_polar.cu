@@ -202,11 +202,22 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
 #define PLB_UP2_MINB 4
 #endif
 #define UP2_BOUNDS(PURE) __launch_bounds__(UP2_TX * UP2_TY, (PURE) ? 4 : PLB_UP2_MINB)
-template <int NC, int R2_16, int XM, int YM, bool PURE = false>
-__global__ void UP2_BOUNDS(PURE)
+//
+// MODE 0: general tail (any planes, any colour program; plb_tail_color, not inlined).
+// MODE 1 = PURE (above). MODE 2 = the merged plane pass of an HDR render: directly sampled or
+// debanded planes next to the EWA-scaled ones, light steps and the peak-detection tap with PQ
+// input. The normalised filter results go through shared memory so that (a) ONE inlined copy of
+// the tail serves the thread's eight outputs (the accumulators need compile-time indices, the
+// staged values do not) and (b) the tail runs x-fastest: a warp handles 32 consecutive pixels
+// of a row, so plane fetches and stores are contiguous. Per-pixel arithmetic is that of MODE 0.
+template <int NC, int R2_16, int XM, int YM, int MODE = 0>
+__global__ void UP2_BOUNDS(MODE == 1)
 k_polar_up2(const __grid_constant__ polar_up2_args a)
 {
+    constexpr bool PURE = MODE == 1;
+    constexpr int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
     __shared__ __align__(16) float tile[NC][UP2_TILE_H][UP2_TILE_WP];
+    __shared__ __align__(16) float stage[MODE == 2 ? NC : 1][MODE == 2 ? TH : 1][MODE == 2 ? TW : 4];
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int X0 = blockIdx.x * (UP2_TX * UP2_OX), Y0 = blockIdx.y * (UP2_TY * UP2_OY);
@@ -365,7 +376,6 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     bool has_peak = false;
     for (int i = 0; i < plb_s_prog.n; i++)
         has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
-    const int TW = UP2_TX * UP2_OX, TH = UP2_TY * UP2_OY;
     const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
     const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
     const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
@@ -373,6 +383,89 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     if (has_peak)
         plb_peak_begin(ps);
     const plb_op_peak *pk_any = nullptr;
+
+    if constexpr (MODE == 2) {
+        #pragma unroll
+        for (int oyo = 0; oyo < UP2_OY; oyo++) {
+            #pragma unroll
+            for (int k = 0; k < NC; k++) {
+                float4 v;
+                v.x = a.norm[oyo][0] * acc[oyo][0][k];
+                v.y = a.norm[oyo][1] * acc[oyo][1][k];
+                v.z = a.norm[oyo][0] * acc[oyo][2][k];
+                v.w = a.norm[oyo][1] * acc[oyo][3][k];
+                *(float4 *) &stage[k][ty * UP2_OY + oyo][tx * UP2_OX] = v;
+            }
+        }
+        __syncthreads();
+        const int tid = ty * UP2_TX + tx;
+        #pragma unroll 1
+        for (int j = 0; j < UP2_OX * UP2_OY; j++) {
+            const int idx = j * (UP2_TX * UP2_TY) + tid;
+            const int lx = idx % TW, ly = idx / TW;
+            const int gx = X0 + lx, gy = Y0 + ly;
+            const bool inside = gx < t.out_w && gy < t.out_h;
+            if (!has_peak && !inside)
+                continue;
+            float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+            #pragma unroll
+            for (int k = 0; k < NC; k++)
+                prim[k] = stage[k][ly][lx];
+            float color[4] = { t.init[0], t.init[1], t.init[2], t.init[3] };
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int m = t.src_map[k];
+                #pragma unroll
+                for (int q = 0; q < 4; q++)
+                    color[q] = m == q ? prim[k] : color[q];
+            }
+            #pragma unroll 1
+            for (int i = 0; i < t.nplanes; i++) {
+                const plb_plane_src &pl = t.planes[i];
+                float posx, posy;
+                plb_coord_pos(t.plane_cc[i], gx, gy, posx, posy);
+                const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear) ? plb_tex_linear(pl.tex, posx, posy)
+                                                                             : plb_tex_nearest(pl.tex, posx, posy);
+                float tmp[4] = { c4.x, c4.y, c4.z, c4.w };
+                if (pl.kind == PLB_PLANE_DEBAND)
+                    plb_deband(pl, t.plane_cc[i], posx, posy, gx, gy, t.frame_index, tmp);
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float v = tmp[k] * pl.scale;
+                    const int m = pl.map[k];
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        color[q] = m == q ? v : color[q];
+                }
+            }
+            uint32_t ypq = 0;
+            const plb_op_peak *pk = nullptr;
+            #pragma unroll 1
+            for (int i = 0; i < plb_s_prog.n; i++) {
+                const plb_color_op &op = plb_s_prog.ops[i];
+                const int kind = op.kind;
+                if (kind == PLB_OP_PEAK) {
+                    pk = &op.u.peak;
+                    ypq = plb_peak_ypq(TRC_PQ, op.u.peak, color);
+                } else {
+                    plb_light_step(op, kind, color);
+                }
+            }
+            if (has_peak) {
+                const int wlx = lx / t.wg_w, wly = ly / t.wg_h;
+                const bool valid = (X0 / t.wg_w + wlx) < nwgx && (Y0 / t.wg_h + wly) < nwgy;
+                pk_any = pk;
+                plb_peak_add(ps, *pk, valid, wly * wgs_x + wlx, ypq);
+            }
+            if (inside && t.dst.ptr)
+                plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy,
+                          make_float4(color[0], color[1], color[2], color[3]));
+        }
+        if (has_peak)
+            plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
+                            (uint32_t) (t.wg_w * t.wg_h));
+        return;
+    }
 
     #pragma unroll
     for (int oyo = 0; oyo < UP2_OY; oyo++) {
@@ -464,10 +557,31 @@ static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
     for (int i = 0; i < args.tail.nplanes; i++)
         light &= args.tail.planes[i].kind == PLB_PLANE_DIRECT;
     const bool pure = light && args.tail.dst.ptr;
+    // merged HDR plane pass (MODE 2): direct / debanded planes, light steps, peak tap on PQ input
+    bool hdr = NC == 2 && !pure;
+    for (int i = 0; i < args.tail.prog.n; i++) {
+        const plb_color_op &op = args.tail.prog.ops[i];
+        const int k = op.kind;
+        hdr &= k == PLB_OP_SCALE || k == PLB_OP_MATRIX || k == PLB_OP_ROUND_FBO ||
+               k == PLB_OP_ALPHA || k == PLB_OP_SWIZZLE ||
+               (k == PLB_OP_PEAK && op.u.peak.lin.trc == TRC_PQ);
+    }
+    for (int i = 0; i < args.tail.nplanes; i++)
+        hdr &= args.tail.planes[i].kind == PLB_PLANE_DIRECT || args.tail.planes[i].kind == PLB_PLANE_DEBAND;
+    static int hdr_on = -1; // PLB_UP2_HDR=0 keeps the general tail (A/B measurements)
+    if (hdr_on < 0) {
+        const char *e = getenv("PLB_UP2_HDR");
+        hdr_on = e ? atoi(e) != 0 : 1;
+    }
     if (pure) {
         switch (r2_class) {
-        case 160: k_polar_up2<NC, 160, XM, YM, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
-        default:  k_polar_up2<NC, 1000, XM, YM, true><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        case 160: k_polar_up2<NC, 160, XM, YM, 1><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        default:  k_polar_up2<NC, 1000, XM, YM, 1><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        }
+    } else if (hdr && hdr_on) {
+        switch (r2_class) {
+        case 160: k_polar_up2<NC, 160, XM, YM, NC == 2 ? 2 : 0><<<grid, block, 0, STREAM(gpu)>>>(args); break;
+        default:  k_polar_up2<NC, 1000, XM, YM, NC == 2 ? 2 : 0><<<grid, block, 0, STREAM(gpu)>>>(args); break;
         }
     } else {
         switch (r2_class) {
