@@ -205,7 +205,7 @@ __host__ __device__ constexpr bool up2_tap_on(int py, int px, int oy, int ox)
 //
 // MODE 0: general tail (any planes, any colour program; plb_tail_color, not inlined).
 // MODE 1 = PURE (above). MODE 2 = the merged plane pass of an HDR render: directly sampled or
-// debanded planes next to the EWA-scaled ones, light steps and the peak-detection tap with PQ
+// debanded / AV1-grained planes next to the EWA-scaled ones, light steps and the peak-detection tap with PQ
 // input. The normalised filter results go through shared memory so that (a) ONE inlined copy of
 // the tail serves the thread's eight outputs (the accumulators need compile-time indices, the
 // staged values do not) and (b) the tail runs x-fastest: a warp handles 32 consecutive pixels
@@ -429,6 +429,8 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
                 float tmp[4] = { c4.x, c4.y, c4.z, c4.w };
                 if (pl.kind == PLB_PLANE_DEBAND)
                     plb_deband(pl, t.plane_cc[i], posx, posy, gx, gy, t.frame_index, tmp);
+                else if (pl.kind == PLB_PLANE_GRAIN_AV1)
+                    plb_grain_av1(pl, gx, gy, tmp);
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float v = tmp[k] * pl.scale;
@@ -464,8 +466,7 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
         if (has_peak)
             plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
                             (uint32_t) (t.wg_w * t.wg_h));
-        return;
-    }
+    } else {
 
     #pragma unroll
     for (int oyo = 0; oyo < UP2_OY; oyo++) {
@@ -499,6 +500,7 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
     if (has_peak)
         plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
                         (uint32_t) (t.wg_w * t.wg_h));
+    } // MODE != 2
 }
 
 // ---------------------------------------------------------------------------------------
@@ -567,7 +569,8 @@ static bool launch_up2(pl_gpu gpu, const polar_up2_args &args, int r2_class)
                (k == PLB_OP_PEAK && op.u.peak.lin.trc == TRC_PQ);
     }
     for (int i = 0; i < args.tail.nplanes; i++)
-        hdr &= args.tail.planes[i].kind == PLB_PLANE_DIRECT || args.tail.planes[i].kind == PLB_PLANE_DEBAND;
+        hdr &= args.tail.planes[i].kind == PLB_PLANE_DIRECT || args.tail.planes[i].kind == PLB_PLANE_DEBAND ||
+               args.tail.planes[i].kind == PLB_PLANE_GRAIN_AV1;
     static int hdr_on = -1; // PLB_UP2_HDR=0 keeps the general tail (A/B measurements)
     if (hdr_on < 0) {
         const char *e = getenv("PLB_UP2_HDR");
