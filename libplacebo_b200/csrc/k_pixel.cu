@@ -238,15 +238,8 @@ k_pixel_planes(const __grid_constant__ plb_tail_args ap)
         #pragma unroll 1
         for (int i = 0; i < a.nplanes; i++) {
             const plb_plane_src &pl = a.planes[i];
-            float posx, posy;
-            plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
-            const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear) ? plb_tex_linear(pl.tex, posx, posy)
-                                                                         : plb_tex_nearest(pl.tex, posx, posy);
-            float tmp[4] = { c4.x, c4.y, c4.z, c4.w };
-            if (pl.kind == PLB_PLANE_DEBAND)
-                plb_deband(pl, a.plane_cc[i], posx, posy, gx, gy, a.frame_index, tmp);
-            else if (pl.kind == PLB_PLANE_GRAIN_AV1)
-                plb_grain_av1(pl, gx, gy, tmp);
+            float tmp[4];
+            plb_sample_plane_simple(pl, a.plane_cc[i], gx, gy, a.frame_index, tmp);
             #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const float v = tmp[k] * pl.scale;
@@ -328,18 +321,18 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     static int planes_mode = -1; // PLB_PIXEL_PLANES=0 keeps the general kernel (A/B tests)
     if (planes_mode < 0) {
         const char *e = getenv("PLB_PIXEL_PLANES");
-        planes_mode = e ? atoi(e) : 5;
+        planes_mode = e ? atoi(e) : 4;
     }
     if (planes_mode > 0 && pixel_is_planes(p)) {
         dim3 block(32, 8);
         dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
-        // measured on B200 (chroma deband of a 4K frame, µs): 3 CTAs/SM 82, 4: 74, 5: 71; general kernel 107
+        // measured on B200 (chroma deband of a 4K frame, µs): 4 CTAs/SM 62, 5: 64 (spills); general kernel 107
         if (planes_mode == 3)
             k_pixel_planes<3><<<grid, block, 0, STREAM(gpu)>>>(t);
-        else if (planes_mode == 4)
-            k_pixel_planes<4><<<grid, block, 0, STREAM(gpu)>>>(t);
-        else
+        else if (planes_mode == 5)
             k_pixel_planes<5><<<grid, block, 0, STREAM(gpu)>>>(t);
+        else
+            k_pixel_planes<4><<<grid, block, 0, STREAM(gpu)>>>(t);
         plb_gpu_priv(gpu)->launches++;
         return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_planes");
     }

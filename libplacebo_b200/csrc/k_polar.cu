@@ -399,6 +399,9 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
         }
         __syncthreads();
         const int tid = ty * UP2_TX + tx;
+        // the tile is a whole number of work groups (host check), so their sizes are powers of two
+        const int wg_sx = __ffs(t.wg_w) - 1, wg_sy = __ffs(t.wg_h) - 1;
+        const int wg0x = X0 >> wg_sx, wg0y = Y0 >> wg_sy;
         #pragma unroll 1
         for (int j = 0; j < UP2_OX * UP2_OY; j++) {
             const int idx = j * (UP2_TX * UP2_TY) + tid;
@@ -422,15 +425,8 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
             #pragma unroll 1
             for (int i = 0; i < t.nplanes; i++) {
                 const plb_plane_src &pl = t.planes[i];
-                float posx, posy;
-                plb_coord_pos(t.plane_cc[i], gx, gy, posx, posy);
-                const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear) ? plb_tex_linear(pl.tex, posx, posy)
-                                                                             : plb_tex_nearest(pl.tex, posx, posy);
-                float tmp[4] = { c4.x, c4.y, c4.z, c4.w };
-                if (pl.kind == PLB_PLANE_DEBAND)
-                    plb_deband(pl, t.plane_cc[i], posx, posy, gx, gy, t.frame_index, tmp);
-                else if (pl.kind == PLB_PLANE_GRAIN_AV1)
-                    plb_grain_av1(pl, gx, gy, tmp);
+                float tmp[4];
+                plb_sample_plane_simple(pl, t.plane_cc[i], gx, gy, t.frame_index, tmp);
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const float v = tmp[k] * pl.scale;
@@ -454,8 +450,8 @@ k_polar_up2(const __grid_constant__ polar_up2_args a)
                 }
             }
             if (has_peak) {
-                const int wlx = lx / t.wg_w, wly = ly / t.wg_h;
-                const bool valid = (X0 / t.wg_w + wlx) < nwgx && (Y0 / t.wg_h + wly) < nwgy;
+                const int wlx = lx >> wg_sx, wly = ly >> wg_sy;
+                const bool valid = (wg0x + wlx) < nwgx && (wg0y + wly) < nwgy;
                 pk_any = pk;
                 plb_peak_add(ps, *pk, valid, wly * wgs_x + wlx, ypq);
             }

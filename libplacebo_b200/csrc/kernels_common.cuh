@@ -157,6 +157,33 @@ PLB_DEV float4 plb_tex_nearest(const plb_tex_desc &t, float u, float v)
     return plb_load_clamped(t, x, y);
 }
 
+// The same fetch with the texture layout known at compile time. FAST 1: one r16 (unorm) plane,
+// clamp addressing; FAST 2: planar pair view of two r16 planes (plb_tex_desc.ptr2); FAST 0: any.
+// plb_tex_fast_kind() classifies a descriptor (launch-uniform). Values equal plb_tex_nearest's.
+PLB_DEV int plb_tex_fast_kind(const plb_tex_desc &t)
+{
+    if (t.kind != PLB_FK_UNORM16 || t.addr != 0)
+        return 0;
+    if (t.ptr2)
+        return 2;
+    return t.comps == 1 ? 1 : 0;
+}
+
+template <int FAST>
+PLB_DEV float4 plb_tex_nearest_t(const plb_tex_desc &t, float u, float v)
+{
+    if (FAST == 0)
+        return plb_tex_nearest(t, u, v);
+    int x = (int) floorf(u * (float) t.w), y = (int) floorf(v * (float) t.h);
+    x = plb_clampi(x, 0, t.w - 1);
+    y = plb_clampi(y, 0, t.h - 1);
+    const unsigned a = *(const uint16_t *) ((const char *) t.ptr + (size_t) y * t.pitch + 2 * x);
+    if (FAST == 1)
+        return make_float4(plb_unorm16_to_float(a), 0.0f, 0.0f, 1.0f);
+    const unsigned b = *(const uint16_t *) ((const char *) t.ptr2 + (size_t) y * t.pitch2 + 2 * x);
+    return make_float4(plb_unorm16_to_float(a), plb_unorm16_to_float(b), 0.0f, 1.0f);
+}
+
 PLB_DEV float4 plb_tex_linear(const plb_tex_desc &t, float u, float v)
 {
     float tx = u * (float) t.w - 0.5f, ty = v * (float) t.h - 0.5f;

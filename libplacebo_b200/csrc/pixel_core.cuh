@@ -69,6 +69,8 @@ struct plb_peak_smem {
 };
 
 // pl_shader_deband for one plane at output pixel (gx, gy); c = texel at pos (already loaded)
+// FAST: layout class of pl.tex (plb_tex_fast_kind), 0 = any
+template <int FAST = 0>
 PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx, float posy,
                         int gx, int gy, uint32_t frame_index, float color[4])
 {
@@ -88,8 +90,8 @@ PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx
         #pragma unroll
         for (int t = 0; t < 4; t++) {
             const float sx = (t == 0 || t == 3) ? 1.0f : -1.0f, sy = t < 2 ? 1.0f : -1.0f;
-            const float4 c = plb_tex_nearest(pl.tex, posx + cc.ptx * (sx * dx),
-                                             posy + cc.pty * (sy * dy));
+            const float4 c = plb_tex_nearest_t<FAST>(pl.tex, posx + cc.ptx * (sx * dx),
+                                                     posy + cc.pty * (sy * dy));
             avg[0] += c.x; avg[1] += c.y; avg[2] += c.z;
         }
         const float bound = pl.threshold / (float) i;
@@ -343,6 +345,36 @@ static __device__ __noinline__ float4 plb_sample_fast(const plb_plane_src &pl, c
     MIX3(x) MIX3(y) MIX3(z) MIX3(w)
 #undef MIX3
     return r;
+}
+
+// Directly sampled, debanded or AV1-grained plane at output pixel (gx, gy), BEFORE the plane's
+// scale factor (the specialised kernels' inline form of plb_sample_plane for these kinds; r16
+// planes take the compile-time-layout fetch).
+template <int FAST>
+PLB_DEV void plb_sample_plane_simple_t(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
+                                       uint32_t frame_index, float out[4])
+{
+    float posx, posy;
+    plb_coord_pos(cc, gx, gy, posx, posy);
+    const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear) ? plb_tex_linear(pl.tex, posx, posy)
+                                                                 : plb_tex_nearest_t<FAST>(pl.tex, posx, posy);
+    out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
+    if (pl.kind == PLB_PLANE_DEBAND)
+        plb_deband<FAST>(pl, cc, posx, posy, gx, gy, frame_index, out);
+    else if (pl.kind == PLB_PLANE_GRAIN_AV1)
+        plb_grain_av1(pl, gx, gy, out);
+}
+
+PLB_DEV void plb_sample_plane_simple(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
+                                     uint32_t frame_index, float out[4])
+{
+    const int fast = plb_tex_fast_kind(pl.tex); // launch-uniform
+    if (fast == 1)
+        plb_sample_plane_simple_t<1>(pl, cc, gx, gy, frame_index, out);
+    else if (fast == 2)
+        plb_sample_plane_simple_t<2>(pl, cc, gx, gy, frame_index, out);
+    else
+        plb_sample_plane_simple_t<0>(pl, cc, gx, gy, frame_index, out);
 }
 
 // Sample plane `pl` at output pixel (gx, gy) -> vec4 (already multiplied by its scale)
