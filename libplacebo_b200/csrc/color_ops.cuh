@@ -343,9 +343,7 @@ PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], flo
     float f[3];
     #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const float base = 0.5f / n[a], end = 1.0f - 0.5f / n[a];
-        const float scale = end - base;
-        float u = scale * idx[a] + base;
+        float u = p.g_scale[a] * idx[a] + p.g_base[a]; // scale = (1 - 0.5/n) - 0.5/n, base = 0.5/n (host)
         float t = u * (float) n[a] - 0.5f;
         float fl = floorf(t);
         // guard the int conversion against NaN/huge values
@@ -362,7 +360,7 @@ PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], flo
                 int i = plb_clampi(b[0] + dx, 0, n[0] - 1);
                 int cc = plb_clampi(b[1] + dy, 0, n[1] - 1);
                 int h = plb_clampi(b[2] + dz, 0, n[2] - 1);
-                const float4 t = __ldg((const float4 *) p.gamut_lut + ((size_t) h * n[1] + cc) * n[0] + i);
+                const float4 t = __ldg((const float4 *) p.gamut_lut + ((h * n[1] + cc) * n[0] + i));
                 c[dz][dy][dx][0] = t.x;
                 c[dz][dy][dx][1] = t.y;
                 c[dz][dy][dx][2] = t.z;
@@ -668,17 +666,18 @@ PLB_DEV void plb_run_hdr_ops(int x, int y, float c[4])
     #pragma unroll 1
     for (int i = 0; i < prog.n; i++) {
         const plb_color_op &op = prog.ops[i];
-        const int kind = op.kind;
-        if (kind == PLB_OP_LINEARIZE)
-            plb_linearize(LIN_TRC, op.u.trc, c);
-        else if (kind == PLB_OP_COLOR_MAP)
-            plb_color_map(op.u.cmap, c);
-        else if (kind == PLB_OP_DELINEARIZE)
-            plb_delinearize(DELIN_TRC, op.u.trc, c);
-        else if (kind == PLB_OP_DITHER)
-            plb_dither(op.u.dither, x, y, c);
-        else
-            plb_light_step(op, kind, c);
+        switch (op.kind) {
+        case PLB_OP_LINEARIZE:   plb_linearize(LIN_TRC, op.u.trc, c); break;
+        case PLB_OP_COLOR_MAP:   plb_color_map(op.u.cmap, c); break;
+        case PLB_OP_DELINEARIZE: plb_delinearize(DELIN_TRC, op.u.trc, c); break;
+        case PLB_OP_DITHER:      plb_dither(op.u.dither, x, y, c); break;
+        case PLB_OP_SCALE:       plb_light_step(op, PLB_OP_SCALE, c); break;
+        case PLB_OP_MATRIX:      plb_light_step(op, PLB_OP_MATRIX, c); break;
+        case PLB_OP_ROUND_FBO:   plb_light_step(op, PLB_OP_ROUND_FBO, c); break;
+        case PLB_OP_ALPHA:       plb_light_step(op, PLB_OP_ALPHA, c); break;
+        case PLB_OP_SWIZZLE:     plb_light_step(op, PLB_OP_SWIZZLE, c); break;
+        default: break;
+        }
     }
 }
 

@@ -174,6 +174,7 @@ struct plb_op_color_map {
     const float *gamut_lut;            // rgba32f texels (quantised to n/65535), I fastest
     int lut_I, lut_C, lut_h;
     float g_a, g_b;
+    float g_base[3], g_scale[3];       // LUT addressing per axis: 0.5/n and (1 - 0.5/n) - 0.5/n (lut.c:285-295)
 };
 
 struct plb_op_dither {

@@ -199,9 +199,15 @@ k_pixel_hdr(const __grid_constant__ plb_tail_args ap)
         #pragma unroll 1
         for (int i = 0; i < a.nplanes; i++) {
             const plb_plane_src &pl = a.planes[i];
-            float posx, posy;
-            plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
-            const float4 c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
+            float4 c4;
+            if (a.plane_cc[i].ident && !pl.linear && plb_tex_fast_kind(pl.tex) == 3) {
+                // the usual source: the rgba16hf image FBO, 1:1 (texel = pixel, always in range)
+                c4 = plb_load_rgba16hf(pl.tex, gx, gy);
+            } else {
+                float posx, posy;
+                plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
+                c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
+            }
             const float tmp[4] = { c4.x * pl.scale, c4.y * pl.scale, c4.z * pl.scale, c4.w * pl.scale };
             #pragma unroll
             for (int k = 0; k < 4; k++) {

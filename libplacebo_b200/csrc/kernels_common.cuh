@@ -162,6 +162,8 @@ PLB_DEV float4 plb_tex_nearest(const plb_tex_desc &t, float u, float v)
 // plb_tex_fast_kind() classifies a descriptor (launch-uniform). Values equal plb_tex_nearest's.
 PLB_DEV int plb_tex_fast_kind(const plb_tex_desc &t)
 {
+    if (t.kind == PLB_FK_HALF && t.comps == 4 && !t.ptr2)
+        return 3; // rgba16hf (FBOs); used for 1:1 fetches only, see plb_load_rgba16hf
     if (t.kind != PLB_FK_UNORM16 || t.addr != 0)
         return 0;
     if (t.ptr2)
@@ -169,10 +171,16 @@ PLB_DEV int plb_tex_fast_kind(const plb_tex_desc &t)
     return t.comps == 1 ? 1 : 0;
 }
 
+// texel (x, y) of an rgba16hf texture, in range (= plb_load_t<PLB_FK_HALF, 4>)
+PLB_DEV float4 plb_load_rgba16hf(const plb_tex_desc &t, int x, int y)
+{
+    return plb_load_t<PLB_FK_HALF, 4>(t, x, y);
+}
+
 template <int FAST>
 PLB_DEV float4 plb_tex_nearest_t(const plb_tex_desc &t, float u, float v)
 {
-    if (FAST == 0)
+    if (FAST == 0 || FAST == 3)
         return plb_tex_nearest(t, u, v);
     int x = (int) floorf(u * (float) t.w), y = (int) floorf(v * (float) t.h);
     x = plb_clampi(x, 0, t.w - 1);
