@@ -111,7 +111,7 @@ def run_reference(args, rank):
                          "graph with parameters from the compiled reference library"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -359,11 +359,29 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
                                     "sample": f"failed: {e}"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else printed during the
+    run (NCCL's version banner, library logs) has been redirected to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # native libraries (NCCL) print to fd 1
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -372,7 +390,7 @@ def main():
         run_reference(args, rank)
         return
     if world == 1 and args.gpus > 1:
-        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (one rank per GPU)"}))
+        emit({"error": f"--gpus {args.gpus} needs torchrun (one rank per GPU)"})
         sys.exit(2)
     run_ours(args, rank, world, local_rank)
 

@@ -262,6 +262,7 @@ struct pass_state {
     pl_rect2df ref_rect;
     pl_rect2d dst_rect;
     bool need_peak_fbo;
+    bool from_measured;    // pass->tex is the image pl_renderer_measure_peak stored (already an FBO)
     // current image
     pl_shader sh;       // pending shader (NULL if materialised in `tex`)
     pl_tex tex;
@@ -1088,7 +1089,8 @@ static void hdr_update_peak(struct pass_state *pass)
         // frame-parallel mode: the caller supplies the smoothed state (renderer.h extension);
         // keep the FBO round trip of the sequential same-frame flow so that the pixels are
         // identical to a single-GPU stream
-        pass->need_peak_fbo = !params->peak_detect_params->allow_delayed;
+        // (continuing from pl_renderer_measure_peak's image, that round trip has happened)
+        pass->need_peak_fbo = !params->peak_detect_params->allow_delayed && !pass->from_measured;
         goto cleanup_keep;
     }
     if (!pl_shader_detect_peak(img_sh(pass), pass->color, &rr->tone_map_state,
@@ -1445,6 +1447,7 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
     bool ok;
     if (measured_hit(rr, &pass)) {
         reserve_measured_fbo(rr);
+        pass.from_measured = true;
         pass.tex = rr->measured.tex;
         pass.w = rr->measured.w;
         pass.h = rr->measured.h;
@@ -1515,6 +1518,9 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
     else
         pl_dispatch_reset_frame(rr->dp);
     memset(rr->fbo_used, 0, sizeof(rr->fbo_used));
+    rr->info_params = params; // the measuring passes are reported like pl_render_image's
+    rr->info_index = 0;
+    pl_dispatch_callback(rr->dp, rr, params->info_callback ? renderer_info_cb : NULL);
     if (!pass_read_image(&pass))
         goto done;
     pl_reset_detected_peak(rr->tone_map_state);
@@ -1546,6 +1552,7 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
         rr->measured.color = pass.color;
     }
 done:
+    rr->info_params = NULL;
     pl_dispatch_abort(rr->dp, &pass.sh);
     free_views(rr);
     rr->have_peak_override = had_override;
