@@ -93,16 +93,19 @@ def run_reference(args, rank):
     steps = max(1, args.steps)
     # bounded: each step is one sample frame; cap the whole run at a few minutes
     fps, cores, desc, dt = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=1)
+    per_step = max(1, int(round(2.0 / max(dt, 1e-3))))   # sample frames per step: about 2 s of CPU work
     budget = 150.0
-    n = max(1, min(steps, int(budget / max(dt, 1e-3))))
-    t0 = time.perf_counter()
-    fps, cores, desc, dt = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=n)
+    n = max(1, min(steps, int(budget / max(per_step * dt, 1e-3))))
+    for _ in range(min(args.warmup, 2)):
+        cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=per_step)
+    fps, cores, desc, dt = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=n * per_step)
+    desc = f"{n} step(s) of {per_step} sample frame(s): " + desc
     from libplacebo_b200 import stream as S
     wl = S.WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": "4K HDR10->SDR EWA-Lanczos frames/sec", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
-        "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": per_step * dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"]},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -353,7 +356,9 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cfps, cores, desc, _ = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=1)
+            _, _, _, dt1 = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=1)
+            reps = max(1, min(400, int(round(12.0 / max(dt1, 1e-3)))))   # about 12 s of CPU work
+            cfps, cores, desc, _ = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=reps)
             line["cpu_baseline"] = {"value": round(cfps, 4), "unit": "frames/s", "cores": cores,
                                     "kind": "port", "sample": desc}
         except Exception as e:  # noqa: BLE001
