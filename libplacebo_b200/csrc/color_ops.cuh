@@ -628,17 +628,30 @@ PLB_DEV void plb_light_step(const plb_color_op &op, const int kind, float c[4])
                 c[3] = 1.0f;
         }
     } else if (kind == PLB_OP_SWIZZLE) {
-        const float o0 = c[0], o1 = c[1], o2 = c[2], o3 = c[3];
-        float r[4] = { 0.0f, 0.0f, 0.0f, 1.0f };
+        int sel[4]; // launch-uniform: source component of output k, -1 = default (0, 0, 0, 1)
+        bool ident = true;
         #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int m = op.u.swizzle.map[k];
-            if (k < op.u.swizzle.comps && m >= 0)
-                r[k] = m == 0 ? o0 : m == 1 ? o1 : m == 2 ? o2 : o3;
+            sel[k] = (k < op.u.swizzle.comps && m >= 0) ? m : -1;
+            ident &= sel[k] < 0 || sel[k] == k;
+        }
+        const float o0 = c[0], o1 = c[1], o2 = c[2], o3 = c[3];
+        if (ident) { // the usual RGB(A) target: nothing moves, absent components take defaults
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (sel[k] < 0)
+                    c[k] = k == 3 ? 1.0f : 0.0f;
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float dflt = k == 3 ? 1.0f : 0.0f;
+                c[k] = sel[k] < 0 ? dflt : sel[k] == 0 ? o0 : sel[k] == 1 ? o1 : sel[k] == 2 ? o2 : o3;
+            }
         }
         if (op.u.swizzle.force_alpha)
-            r[3] = o3;
-        c[0] = r[0]; c[1] = r[1]; c[2] = r[2]; c[3] = r[3];
+            c[3] = o3;
     }
 }
 
@@ -740,16 +753,34 @@ PLB_DEV void plb_run_light_ops_n(const plb_color_prog &prog, float c[N][4])
                 sel[k] = (k < op.u.swizzle.comps && m >= 0) ? m : -1;
             }
             const bool fa = op.u.swizzle.force_alpha;
+            bool ident = true;
             #pragma unroll
-            for (int p = 0; p < N; p++) {
-                const float o0 = c[p][0], o1 = c[p][1], o2 = c[p][2], o3 = c[p][3];
+            for (int k = 0; k < 4; k++)
+                ident &= sel[k] < 0 || sel[k] == k;
+            if (ident) { // the usual RGB(A) target: nothing moves, absent components take defaults
                 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float dflt = k == 3 ? 1.0f : 0.0f;
-                    c[p][k] = sel[k] < 0 ? dflt : sel[k] == 0 ? o0 : sel[k] == 1 ? o1 : sel[k] == 2 ? o2 : o3;
+                for (int p = 0; p < N; p++) {
+                    const float o3 = c[p][3];
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (sel[k] < 0)
+                            c[p][k] = k == 3 ? 1.0f : 0.0f;
+                    }
+                    if (fa)
+                        c[p][3] = o3;
                 }
-                if (fa)
-                    c[p][3] = o3;
+            } else {
+                #pragma unroll
+                for (int p = 0; p < N; p++) {
+                    const float o0 = c[p][0], o1 = c[p][1], o2 = c[p][2], o3 = c[p][3];
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float dflt = k == 3 ? 1.0f : 0.0f;
+                        c[p][k] = sel[k] < 0 ? dflt : sel[k] == 0 ? o0 : sel[k] == 1 ? o1 : sel[k] == 2 ? o2 : o3;
+                    }
+                    if (fa)
+                        c[p][3] = o3;
+                }
             }
         }
     }
