@@ -19,6 +19,11 @@ for w in c3:c3_4k_hdr10_to_sdr c2:c2_1080p_to_4k_ewa_fp16; do
   ncu -i /tmp/prof_$tag.ncu-rep --page raw --csv > $O/final_ncu_${tag}_raw.csv 2>/dev/null
   ncu -i /tmp/prof_$tag.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $O/final_ncu_${tag}_source.csv.gz
 done
+# 2-GPU line (only when the box has two GPUs: gpurun --gpus 2)
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus 2 --steps 100 --warmup 5 > $O/final_bench_c3_2gpu.json 2> $O/final_bench_c3_2gpu.err
+fi
 cat $O/final_tests.log $O/final_smoke.log
 python - <<'PY'
 import json, glob
