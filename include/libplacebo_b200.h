@@ -77,6 +77,8 @@ typedef const struct pl_log_t { struct pl_log_params params; } *pl_log;
 PL_API pl_log pl_log_create(int api_ver, const struct pl_log_params *params);
 PL_API void pl_log_destroy(pl_log *log);
 PL_API void pl_log_simple(void *stream, enum pl_log_level level, const char *msg);
+// log.h:105 — the same with ANSI colours per level
+PL_API void pl_log_color(void *stream, enum pl_log_level level, const char *msg);
 
 /* ---- colorspace.h ----------------------------------------------------------------------- */
 enum pl_color_system { /* colorspace.h:30-60 */
@@ -87,6 +89,10 @@ enum pl_color_system { /* colorspace.h:30-60 */
     PL_COLOR_SYSTEM_RGB, PL_COLOR_SYSTEM_XYZ, PL_COLOR_SYSTEM_COUNT
 };
 PL_API bool pl_color_system_is_ycbcr_like(enum pl_color_system sys);
+// colorspace.h:54-78 — names and the resolution heuristic
+PL_API extern const char *const pl_color_system_names[PL_COLOR_SYSTEM_COUNT];
+PL_API const char *pl_color_system_name(enum pl_color_system sys);
+PL_API enum pl_color_system pl_color_system_guess_ycbcr(int width, int height);
 PL_API bool pl_color_system_is_linear(enum pl_color_system sys);
 enum pl_channel {
     PL_CHANNEL_NONE = -1, PL_CHANNEL_A = 3, PL_CHANNEL_R = 0, PL_CHANNEL_G = 1,
@@ -125,6 +131,11 @@ struct pl_color_repr {
     const struct pl_dovi_metadata *dovi;
 };
 PL_API bool pl_color_repr_equal(const struct pl_color_repr *c1, const struct pl_color_repr *c2);
+// colorspace.h:176-215 — representation presets, merging (fields set in `orig` win)
+PL_API extern const struct pl_color_repr pl_color_repr_unknown, pl_color_repr_rgb, pl_color_repr_sdtv,
+                                         pl_color_repr_hdtv, pl_color_repr_uhdtv, pl_color_repr_jpeg;
+PL_API void pl_color_repr_merge(struct pl_color_repr *orig, const struct pl_color_repr *update);
+PL_API bool pl_bit_encoding_equal(const struct pl_bit_encoding *b1, const struct pl_bit_encoding *b2);
 PL_API float pl_color_repr_normalize(struct pl_color_repr *repr);
 PL_API enum pl_color_levels pl_color_levels_guess(const struct pl_color_repr *repr);
 
@@ -160,6 +171,13 @@ PL_API bool pl_raw_primaries_equal(const struct pl_raw_primaries *a, const struc
 PL_API bool pl_raw_primaries_similar(const struct pl_raw_primaries *a, const struct pl_raw_primaries *b);
 PL_API void pl_raw_primaries_merge(struct pl_raw_primaries *orig, const struct pl_raw_primaries *update);
 PL_API const struct pl_raw_primaries *pl_raw_primaries_get(enum pl_color_primaries prim);
+// colorspace.h:228-258, 262-266 — names, wide-gamut predicate, resolution heuristic
+PL_API extern const char *const pl_color_primaries_names[PL_COLOR_PRIM_COUNT];
+PL_API const char *pl_color_primaries_name(enum pl_color_primaries prim);
+PL_API bool pl_color_primaries_is_wide_gamut(enum pl_color_primaries prim);
+PL_API enum pl_color_primaries pl_color_primaries_guess(int width, int height);
+PL_API extern const char *const pl_color_transfer_names[PL_COLOR_TRC_COUNT];
+PL_API const char *pl_color_transfer_name(enum pl_color_transfer trc);
 
 enum pl_hdr_scaling { PL_HDR_NORM = 0, PL_HDR_SQRT, PL_HDR_NITS, PL_HDR_PQ, PL_HDR_SCALING_COUNT };
 PL_API float pl_hdr_rescale(enum pl_hdr_scaling from, enum pl_hdr_scaling to, float x);
@@ -202,6 +220,10 @@ struct pl_color_space {
 #define pl_color_space(...) (&(struct pl_color_space) { __VA_ARGS__ })
 PL_API bool pl_color_space_is_hdr(const struct pl_color_space *csp);
 PL_API bool pl_color_space_is_black_scaled(const struct pl_color_space *csp);
+// colorspace.h:566-574 — CPU transfer functions (in place, three channels; the same curves the
+// pixel kernels evaluate, here with libm like the reference)
+PL_API void pl_color_linearize(const struct pl_color_space *csp, float color[3]);
+PL_API void pl_color_delinearize(const struct pl_color_space *csp, float color[3]);
 struct pl_nominal_luma_params {
     const struct pl_color_space *color;
     enum pl_hdr_metadata_type metadata;
@@ -235,6 +257,28 @@ enum pl_chroma_location {
 PL_API void pl_chroma_location_offset(enum pl_chroma_location loc, float *x, float *y);
 PL_API pl_matrix3x3 pl_get_rgb2xyz_matrix(const struct pl_raw_primaries *prim);
 PL_API pl_matrix3x3 pl_get_xyz2rgb_matrix(const struct pl_raw_primaries *prim);
+// colorspace.h:615 — white point of a colour temperature (K)
+PL_API struct pl_cie_xy pl_white_from_temp(float temperature);
+
+// colorspace.h:665-709 — colour-vision deficiency model (cone distortion). pl_render_params.
+// cone_params itself is outside the CUDA hot path (rejected); the matrices are T0 host code.
+enum pl_cone {
+    PL_CONE_L = 1 << 0, PL_CONE_M = 1 << 1, PL_CONE_S = 1 << 2,
+    PL_CONE_NONE = 0,
+    PL_CONE_LM = PL_CONE_L | PL_CONE_M, PL_CONE_MS = PL_CONE_M | PL_CONE_S,
+    PL_CONE_LS = PL_CONE_L | PL_CONE_S, PL_CONE_LMS = PL_CONE_L | PL_CONE_M | PL_CONE_S,
+};
+struct pl_cone_params {
+    enum pl_cone cones; // cones affected by the vision model
+    float strength;     // 0 = complete loss, 1 = unaffected
+};
+#define pl_cone_params(...) (&(struct pl_cone_params) { __VA_ARGS__ })
+PL_API extern const struct pl_cone_params pl_vision_normal, pl_vision_protanomaly, pl_vision_protanopia,
+    pl_vision_deuteranomaly, pl_vision_deuteranopia, pl_vision_tritanomaly, pl_vision_tritanopia,
+    pl_vision_monochromacy, pl_vision_achromatopsia;
+PL_API pl_matrix3x3 pl_get_cone_matrix(const struct pl_cone_params *params,
+                                       const struct pl_raw_primaries *prim);
+
 PL_API pl_matrix3x3 pl_get_color_mapping_matrix(const struct pl_raw_primaries *src,
                                                 const struct pl_raw_primaries *dst,
                                                 enum pl_rendering_intent intent);
@@ -284,6 +328,9 @@ PL_API extern const struct pl_filter_function pl_filter_function_spline36;
 PL_API extern const struct pl_filter_function pl_filter_function_spline64;
 PL_API extern const struct pl_filter_function pl_filter_function_oversample;
 PL_API const struct pl_filter_function *pl_find_filter_function(const char *name);
+// filters.h:166-167 — NULL-terminated list of all kernels / windows
+PL_API extern const struct pl_filter_function * const pl_filter_functions[];
+PL_API extern const int pl_num_filter_functions;
 
 enum pl_filter_usage {
     PL_FILTER_UPSCALING = (1 << 0), PL_FILTER_DOWNSCALING = (1 << 1),

@@ -46,6 +46,16 @@ void pl_log_simple(void *stream, enum pl_log_level level, const char *msg)
     fprintf(h, "%5s: %s\n", prefix[level], msg);
 }
 
+void pl_log_color(void *stream, enum pl_log_level level, const char *msg)
+{
+    // fatal bright red, error red, warning yellow, info green, debug blue, trace bright black
+    static const char *sgr[] = { "0", "31;1", "31", "33", "32", "34", "30;1" };
+    FILE *h = stream ? (FILE *) stream : (level <= PL_LOG_WARN ? stderr : stdout);
+    fprintf(h, "\033[%sm%s\033[0m\n", sgr[level], msg);
+    if (level <= PL_LOG_WARN)
+        fflush(h);
+}
+
 void plb_msg(pl_log log, enum pl_log_level lev, const char *fmt, ...)
 {
     if (!log || !log->params.log_cb || lev > log->params.log_level)

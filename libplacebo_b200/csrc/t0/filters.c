@@ -167,7 +167,7 @@ FN(pl_filter_function_spline64,  "spline64",  k_spline64,  4.0);
 static double k_oversample(const struct pl_filter_ctx *f, double x) { (void) f; (void) x; return 0.0; }
 FN(pl_filter_function_oversample, "oversample", k_oversample, 0.0, .params = {0.0}, .tunable = {true}, .opaque = true);
 
-static const struct pl_filter_function *const all_functions[] = {
+const struct pl_filter_function * const pl_filter_functions[] = {
     &pl_filter_function_box, &pl_filter_function_triangle, &pl_filter_function_cosine,
     &pl_filter_function_hann, &pl_filter_function_hamming, &pl_filter_function_welch,
     &pl_filter_function_kaiser, &pl_filter_function_blackman, &pl_filter_function_bohman,
@@ -175,15 +175,17 @@ static const struct pl_filter_function *const all_functions[] = {
     &pl_filter_function_jinc, &pl_filter_function_sphinx, &pl_filter_function_cubic,
     &pl_filter_function_hermite, &pl_filter_function_spline16, &pl_filter_function_spline36,
     &pl_filter_function_spline64, &pl_filter_function_oversample,
+    NULL,
 };
+const int pl_num_filter_functions = PLB_ARRAY_SIZE(pl_filter_functions) - 1;
 
 const struct pl_filter_function *pl_find_filter_function(const char *name)
 {
     if (!name)
         return NULL;
-    for (size_t i = 0; i < PLB_ARRAY_SIZE(all_functions); i++) {
-        if (strcmp(name, all_functions[i]->name) == 0)
-            return all_functions[i];
+    for (int i = 0; i < pl_num_filter_functions; i++) {
+        if (strcmp(name, pl_filter_functions[i]->name) == 0)
+            return pl_filter_functions[i];
     }
     return NULL;
 }

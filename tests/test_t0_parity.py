@@ -2,6 +2,8 @@
 reference built into oracle/_ref (skipped where the reference tree was never available; the
 committed goldens in tests/golden cover that case, see test_golden.py). Everything is compared
 bit for bit."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -173,3 +175,89 @@ def test_dovi_repr_decode(ref, pt0):
         a, b = ref.repr_decode_dovi(*args), pt0.repr_decode_dovi(*args)
         for k in a:
             assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (variant, k)
+
+
+# ---- colorspace.h surface beyond the render path ---------------------------------------------
+
+def _both(ref, pt0, name, restype=None):
+    fr, fp_ = ref.f(name), pt0.f(name)
+    if restype is not None:
+        fr.restype = fp_.restype = restype
+    return fr, fp_
+
+
+@pytest.mark.parametrize("direction", [0, 1])
+def test_cpu_transfer_functions(ref, pt0, direction):
+    """pl_color_linearize / pl_color_delinearize: bit-identical with the compiled reference for
+    every transfer function, SDR and HDR display ranges, values below 0 and above 1."""
+    fr, fp_ = _both(ref, pt0, "color_transfer_cpu")
+    rng = np.random.default_rng(5 + direction)
+    base = np.concatenate([rng.random(3 * 400), rng.uniform(-0.5, 4.0, 3 * 200),
+                           [0, 0, 0, 1, 1, 1, 0.5, 0.04045, 0.0031308, 1e-7, 0.181, 0.030001]]).astype(T.f32)
+    for trc in range(len(T.TRC)):
+        for prim in (T.PRIM["BT_709"], T.PRIM["BT_2020"]):
+            for lo, hi in ((0.0, 0.0), (0.005, 600.0), (0.2, 100.0)):
+                a, b = base.copy(), base.copy()
+                fr(prim, trc, C.c_float(lo), C.c_float(hi), direction, T.fp(a), a.size // 3)
+                fp_(prim, trc, C.c_float(lo), C.c_float(hi), direction, T.fp(b), b.size // 3)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (trc, prim, lo, hi)
+
+
+def test_cone_matrices_and_vision_presets(ref, pt0):
+    fr, fp_ = _both(ref, pt0, "cone_matrix")
+    for cones in range(8):
+        for strength in (0.0, 0.25, 0.5, 1.0, 1.5):
+            for prim in (T.PRIM["BT_709"], T.PRIM["BT_2020"], T.PRIM["DCI_P3"]):
+                a, b = np.zeros(9, T.f32), np.zeros(9, T.f32)
+                fr(cones, C.c_float(strength), prim, T.fp(a))
+                fp_(cones, C.c_float(strength), prim, T.fp(b))
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (cones, strength, prim)
+    vr, vp = _both(ref, pt0, "vision_presets")
+    a, b = np.zeros(18, T.f32), np.zeros(18, T.f32)
+    vr(T.fp(a))
+    vp(T.fp(b))
+    assert np.array_equal(a, b)
+
+
+def test_white_point_guesses_names_and_repr_merge(ref, pt0):
+    wr, wp = _both(ref, pt0, "white_from_temp")
+    for temp in (1000, 1667, 2500, 3200, 4000, 5503, 6504, 9300, 25000, 40000):
+        a, b = np.zeros(2, T.f32), np.zeros(2, T.f32)
+        wr(C.c_float(temp), T.fp(a))
+        wp(C.c_float(temp), T.fp(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), temp
+    gr, gp = _both(ref, pt0, "guess_from_size")
+    for w, h in ((720, 480), (720, 486), (720, 576), (1024, 576), (1280, 720), (1920, 1080),
+                 (2000, 576), (200, 200), (1279, 577), (640, 360)):
+        a, b = np.zeros(2, np.int32), np.zeros(2, np.int32)
+        gr(w, h, T.ip(a))
+        gp(w, h, T.ip(b))
+        assert np.array_equal(a, b), (w, h)
+    nr, np_ = _both(ref, pt0, "enum_name", C.c_char_p)
+    for kind, count in ((0, len(T.SYS)), (1, len(T.PRIM)), (2, len(T.TRC))):
+        for v in range(count):
+            assert nr(kind, v) == np_(kind, v) and nr(kind, v), (kind, v)
+    gr2, gp2 = _both(ref, pt0, "primaries_is_wide_gamut")
+    for v in range(len(T.PRIM)):
+        assert bool(gr2(v)) == bool(gp2(v)), v
+    mr, mp = _both(ref, pt0, "repr_merge")
+    rng = np.random.default_rng(11)
+    for i in range(200):
+        a0 = (rng.integers(0, 3, 6) * rng.integers(0, 2, 6)).astype(np.int32)
+        b0 = rng.integers(0, 3, 6).astype(np.int32)
+        preset = int(rng.integers(-1, 6))
+        a, b = a0.copy(), a0.copy()
+        mr(T.ip(a), T.ip(b0), preset)
+        mp(T.ip(b), T.ip(b0), preset)
+        assert np.array_equal(a, b), (a0, b0, preset)
+
+
+def test_filter_function_table(ref, pt0):
+    """Every kernel / window the product exports exists under the same name in the reference
+    (the reference additionally keeps deprecated aliases of the cubic family)."""
+    cr, cp = _both(ref, pt0, "num_filter_functions")
+    nr, np_ = _both(ref, pt0, "filter_function_name", C.c_char_p)
+    ref_names = {nr(i) for i in range(cr())}
+    ours = [np_(i) for i in range(cp())]
+    assert len(ours) == len(set(ours)) >= 20
+    assert set(ours) <= ref_names, set(ours) - ref_names
