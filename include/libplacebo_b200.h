@@ -41,6 +41,7 @@ PL_API_BEGIN
 typedef struct pl_rect2d { int x0, y0, x1, y1; } pl_rect2d;
 typedef struct pl_rect3d { int x0, y0, z0, x1, y1, z1; } pl_rect3d;
 typedef struct pl_rect2df { float x0, y0, x1, y1; } pl_rect2df;
+typedef struct pl_rect3df { float x0, y0, z0, x1, y1, z1; } pl_rect3df;
 #define pl_rect_w(r) ((r).x1 - (r).x0)
 #define pl_rect_h(r) ((r).y1 - (r).y0)
 #define pl_rect_d(r) ((r).z1 - (r).z0)
@@ -60,6 +61,24 @@ PL_API void pl_transform3x3_apply(const pl_transform3x3 *t, float vec[3]);
 PL_API void pl_transform3x3_scale(pl_transform3x3 *t, float scale);
 PL_API void pl_transform3x3_invert(pl_transform3x3 *t);
 typedef int pl_rotation;
+enum { PL_ROTATION_0 = 0, PL_ROTATION_90 = 1, PL_ROTATION_180 = 2, PL_ROTATION_270 = 3, PL_ROTATION_360 = 4 };
+// common.h:117-240 — crop helpers callers use to fill pl_frame.crop: ordering, rounding, aspect
+// ratio with pan & scan, fitting one rect into another, centred scaling, offset, quarter turns
+PL_API void pl_rect2d_normalize(pl_rect2d *rc);
+PL_API void pl_rect3d_normalize(pl_rect3d *rc);
+PL_API void pl_rect2df_normalize(pl_rect2df *rc);
+PL_API void pl_rect3df_normalize(pl_rect3df *rc);
+PL_API pl_rect2d pl_rect2df_round(const pl_rect2df *rc);
+PL_API pl_rect3d pl_rect3df_round(const pl_rect3df *rc);
+PL_API float pl_rect2df_aspect(const pl_rect2df *rc);
+PL_API void pl_rect2df_aspect_set(pl_rect2df *rc, float aspect, float panscan);
+#define pl_rect2df_aspect_copy(rc, src, panscan) \
+    pl_rect2df_aspect_set((rc), pl_rect2df_aspect(src), (panscan))
+PL_API void pl_rect2df_aspect_fit(pl_rect2df *rc, const pl_rect2df *src, float panscan);
+PL_API void pl_rect2df_stretch(pl_rect2df *rc, float stretch_x, float stretch_y);
+#define pl_rect2df_zoom(rc, zoom) pl_rect2df_stretch((rc), (zoom), (zoom))
+PL_API void pl_rect2df_offset(pl_rect2df *rc, float offset_x, float offset_y);
+PL_API void pl_rect2df_rotate(pl_rect2df *rc, pl_rotation rot);
 
 /* ---- log.h:26-81 ------------------------------------------------------------------------ */
 enum pl_log_level {
@@ -77,6 +96,9 @@ typedef const struct pl_log_t { struct pl_log_params params; } *pl_log;
 PL_API pl_log pl_log_create(int api_ver, const struct pl_log_params *params);
 PL_API void pl_log_destroy(pl_log *log);
 PL_API void pl_log_simple(void *stream, enum pl_log_level level, const char *msg);
+// log.h:88-96 — replace the parameters / the level of a live log; return the previous ones
+PL_API struct pl_log_params pl_log_update(pl_log log, const struct pl_log_params *params);
+PL_API enum pl_log_level pl_log_level_update(pl_log log, enum pl_log_level level);
 // log.h:105 — the same with ANSI colours per level
 PL_API void pl_log_color(void *stream, enum pl_log_level level, const char *msg);
 

@@ -39,6 +39,27 @@ void pl_log_destroy(pl_log *plog)
     *plog = NULL;
 }
 
+struct pl_log_params pl_log_update(pl_log plog, const struct pl_log_params *params)
+{
+    static const struct pl_log_params none = {};
+    if (!plog)
+        return none;
+    struct pl_log_t *log = (struct pl_log_t *) plog;
+    const struct pl_log_params prev = log->params;
+    log->params = params ? *params : none;
+    return prev;
+}
+
+enum pl_log_level pl_log_level_update(pl_log plog, enum pl_log_level level)
+{
+    if (!plog)
+        return PL_LOG_NONE;
+    struct pl_log_t *log = (struct pl_log_t *) plog;
+    const enum pl_log_level prev = log->params.log_level;
+    log->params.log_level = level;
+    return prev;
+}
+
 void pl_log_simple(void *stream, enum pl_log_level level, const char *msg)
 {
     static const char *prefix[] = { "", "fatal", "error", "warn", "info", "debug", "trace" };

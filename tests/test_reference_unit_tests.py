@@ -1,5 +1,5 @@
 """The reference's OWN unit tests for the host code of the path (src/tests/filters.c,
-tone_mapping.c, colorspace.c) compiled in place from /root/reference — nothing is copied — against
+tone_mapping.c, colorspace.c, common.c) compiled in place from /root/reference — nothing is copied — against
 the reference's public headers and linked against libplacebo_b200.so instead of libplacebo:
 the drop-in claim of INTEGRATION.md, checked with the maintainers' own assertions (filter LUT
 accuracy and row sums, tone-curve monotonicity / clip identity / PQ constants, transfer-function
@@ -21,7 +21,7 @@ pytestmark = pytest.mark.skipif(
     reason="reference tree / oracle/_ref headers not present")
 
 
-@pytest.mark.parametrize("name", ["filters", "tone_mapping", "colorspace"])
+@pytest.mark.parametrize("name", ["filters", "tone_mapping", "colorspace", "common"])
 def test_reference_unit_test_passes_against_product_library(name, tmp_path):
     T.product_t0()  # makes sure libplacebo_b200.so is built
     exe = str(tmp_path / name)

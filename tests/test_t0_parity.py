@@ -261,3 +261,40 @@ def test_filter_function_table(ref, pt0):
     ours = [np_(i) for i in range(cp())]
     assert len(ours) == len(set(ours)) >= 20
     assert set(ours) <= ref_names, set(ours) - ref_names
+
+
+def test_crop_helpers(ref, pt0):
+    """common.h rect helpers (normalize / round / aspect_set / aspect_fit / stretch / offset /
+    rotate): bit-identical with the compiled reference on random and degenerate rects."""
+    fr, fp_ = _both(ref, pt0, "rect2df_op", C.c_float)
+    rng = np.random.default_rng(21)
+    rects = [np.array(r, T.f32) for r in ([0, 0, 1920, 1080], [0, 0, 1024, 768], [1920, 1080, 0, 0],
+                                         [5, 5, 5, 90], [0, 0, 0, 0], [-3.5, 2.25, 100.75, -40.5])]
+    rects += [rng.uniform(-2000, 4000, 4).astype(T.f32) for _ in range(60)]
+    for rc in rects:
+        for op in range(7):
+            for _ in range(6):
+                a = rng.uniform(-1.0, 3.0, 5).astype(T.f32)
+                if op == 2:
+                    a[:4] = rng.uniform(-500, 3000, 4)
+                    a[4] = rng.choice([0.0, 0.5, 1.0])
+                if op == 1:
+                    a[0] = abs(a[0]) * rng.choice([0.0, 1.0, 1.0])
+                    a[1] = rng.choice([0.0, 0.3, 1.0])
+                if op == 5:
+                    a[0] = rng.integers(-9, 10)
+                x, y = rc.copy(), rc.copy()
+                ra = fr(op, T.fp(x), T.fp(a))
+                rb = fp_(op, T.fp(y), T.fp(a))
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (op, rc, a)
+                assert np.float32(ra).view(np.uint32) == np.float32(rb).view(np.uint32), (op, rc, a)
+    gr, gp = _both(ref, pt0, "rect3_op")
+    for kind in range(4):
+        for _ in range(40):
+            v = (rng.uniform(-100, 100, 6) * (1 if kind in (1, 2) else 1)).astype(T.f32)
+            if kind in (0, 3):
+                v = np.round(v)
+            x, y = v.copy(), v.copy()
+            gr(kind, T.fp(x))
+            gp(kind, T.fp(y))
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (kind, v)
