@@ -406,6 +406,16 @@ PL_API extern const struct pl_filter_config pl_filter_ewa_robidoux;
 PL_API extern const struct pl_filter_config pl_filter_ewa_robidouxsharp;
 PL_API extern const struct pl_filter_config * const pl_filter_configs[];
 PL_API extern const int pl_num_filter_configs;
+// filters.h:316-329 — name -> configuration list of the older selection API ("none" = built-in
+// sampling, aliases have no description); terminated by {0}
+struct pl_filter_preset {
+    const char *name;
+    const struct pl_filter_config *filter;
+    const char *description;
+};
+PL_API extern const struct pl_filter_preset pl_filter_presets[];
+PL_API extern const int pl_num_filter_presets;
+PL_API const struct pl_filter_preset *pl_find_filter_preset(const char *name);
 PL_API const struct pl_filter_config *pl_find_filter_config(const char *name, enum pl_filter_usage usage);
 
 struct pl_filter_params { /* filters.h:310-340 */

@@ -442,3 +442,46 @@ void pl_filter_free(pl_filter *filter)
     free(p);
     *filter = NULL;
 }
+
+// Name -> configuration list of the older scaler-selection API (filters.h:316-329; what
+// vf_libplacebo and mpv's option tables walk): recommended filters first, then the rest, then
+// aliases without a description. "none" = the built-in texture sampling.
+const struct pl_filter_preset pl_filter_presets[] = {
+    { "none",                 NULL,                              "Built-in sampling" },
+    { "bilinear",             &pl_filter_bilinear,               "Bilinear" },
+    { "nearest",              &pl_filter_nearest,                "Nearest neighbour" },
+    { "bicubic",              &pl_filter_bicubic,                "Bicubic" },
+    { "lanczos",              &pl_filter_lanczos,                "Lanczos" },
+    { "ewa_lanczos",          &pl_filter_ewa_lanczos,            "Jinc (EWA Lanczos)" },
+    { "ewa_lanczossharp",     &pl_filter_ewa_lanczossharp,       "Sharpened Jinc" },
+    { "ewa_lanczos4sharpest", &pl_filter_ewa_lanczos4sharpest,   "Sharpened Jinc-AR, 4 taps" },
+    { "gaussian",             &pl_filter_gaussian,               "Gaussian" },
+    { "spline16",             &pl_filter_spline16,               "Spline (2 taps)" },
+    { "spline36",             &pl_filter_spline36,               "Spline (3 taps)" },
+    { "spline64",             &pl_filter_spline64,               "Spline (4 taps)" },
+    { "mitchell",             &pl_filter_mitchell,               "Mitchell-Netravali" },
+    { "sinc",                 &pl_filter_sinc,                   "Sinc (unwindowed)" },
+    { "ginseng",              &pl_filter_ginseng,                "Ginseng (Jinc-Sinc)" },
+    { "ewa_jinc",             &pl_filter_ewa_jinc,               "EWA Jinc (unwindowed)" },
+    { "ewa_ginseng",          &pl_filter_ewa_ginseng,            "EWA Ginseng" },
+    { "ewa_hann",             &pl_filter_ewa_hann,               "EWA Hann" },
+    { "hermite",              &pl_filter_hermite,                "Hermite" },
+    { "catmull_rom",          &pl_filter_catmull_rom,            "Catmull-Rom" },
+    { "robidoux",             &pl_filter_robidoux,               "Robidoux" },
+    { "robidouxsharp",        &pl_filter_robidouxsharp,          "RobidouxSharp" },
+    { "ewa_robidoux",         &pl_filter_ewa_robidoux,           "EWA Robidoux" },
+    { "ewa_robidouxsharp",    &pl_filter_ewa_robidouxsharp,      "EWA RobidouxSharp" },
+    { "triangle",             &pl_filter_bilinear,               NULL },
+    { "ewa_hanning",          &pl_filter_ewa_hann,               NULL },
+    { 0 },
+};
+const int pl_num_filter_presets = PLB_ARRAY_SIZE(pl_filter_presets) - 1;
+
+const struct pl_filter_preset *pl_find_filter_preset(const char *name)
+{
+    for (int i = 0; name && i < pl_num_filter_presets; i++) {
+        if (strcmp(pl_filter_presets[i].name, name) == 0)
+            return &pl_filter_presets[i];
+    }
+    return NULL;
+}

@@ -298,3 +298,20 @@ def test_crop_helpers(ref, pt0):
             gr(kind, T.fp(x))
             gp(kind, T.fp(y))
             assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (kind, v)
+
+
+def test_filter_presets(ref, pt0):
+    """pl_filter_presets: same names, order, configurations and descriptions as the reference;
+    pl_find_filter_preset finds each of them."""
+    fr, fp_ = _both(ref, pt0, "filter_preset")
+    i = 0
+    while True:
+        a, b = C.create_string_buffer(256), C.create_string_buffer(256)
+        ra, rb = fr(i, a, 256), fp_(i, b, 256)
+        assert (ra < 0) == (rb < 0), i
+        if ra < 0:
+            break
+        assert a.value == b.value and a.value.endswith(b"|1"), (i, a.value, b.value)
+        i += 1
+    assert i >= 26
+    assert not pt0.lib.plt_filter_preset(-1, b, 256) >= 0
