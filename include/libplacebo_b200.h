@@ -79,6 +79,28 @@ PL_API void pl_rect2df_stretch(pl_rect2df *rc, float stretch_x, float stretch_y)
 #define pl_rect2df_zoom(rc, zoom) pl_rect2df_stretch((rc), (zoom), (zoom))
 PL_API void pl_rect2df_offset(pl_rect2df *rc, float offset_x, float offset_y);
 PL_API void pl_rect2df_rotate(pl_rect2df *rc, pl_rotation rot);
+// common.h:64-116 — 2x2 matrices / affine transforms (rotation and offset of sampling rects) and the
+// rect forms of the 3x3 ones
+typedef struct pl_matrix2x2 { float m[2][2]; } pl_matrix2x2;
+typedef struct pl_transform2x2 { pl_matrix2x2 mat; float c[2]; } pl_transform2x2;
+PL_API extern const pl_matrix2x2 pl_matrix2x2_identity;
+PL_API extern const pl_transform2x2 pl_transform2x2_identity;
+PL_API pl_matrix2x2 pl_matrix2x2_rotation(float angle);
+PL_API void pl_matrix2x2_apply(const pl_matrix2x2 *mat, float vec[2]);
+PL_API void pl_matrix2x2_apply_rc(const pl_matrix2x2 *mat, pl_rect2df *rc);
+PL_API void pl_matrix2x2_mul(pl_matrix2x2 *a, const pl_matrix2x2 *b);
+PL_API void pl_matrix2x2_rmul(const pl_matrix2x2 *a, pl_matrix2x2 *b);
+PL_API void pl_matrix2x2_scale(pl_matrix2x2 *mat, float scale);
+PL_API void pl_matrix2x2_invert(pl_matrix2x2 *mat);
+PL_API void pl_transform2x2_apply(const pl_transform2x2 *t, float vec[2]);
+PL_API void pl_transform2x2_apply_rc(const pl_transform2x2 *t, pl_rect2df *rc);
+PL_API void pl_transform2x2_mul(pl_transform2x2 *a, const pl_transform2x2 *b);
+PL_API void pl_transform2x2_rmul(const pl_transform2x2 *a, pl_transform2x2 *b);
+PL_API void pl_transform2x2_scale(pl_transform2x2 *t, float scale);
+PL_API void pl_transform2x2_invert(pl_transform2x2 *t);
+PL_API pl_rect2df pl_transform2x2_bounds(const pl_transform2x2 *t, const pl_rect2df *rc);
+PL_API void pl_matrix3x3_apply_rc(const pl_matrix3x3 *mat, pl_rect3df *rc);
+PL_API void pl_transform3x3_apply_rc(const pl_transform3x3 *t, pl_rect3df *rc);
 
 /* ---- log.h:26-81 ------------------------------------------------------------------------ */
 enum pl_log_level {
@@ -281,6 +303,10 @@ PL_API pl_matrix3x3 pl_get_rgb2xyz_matrix(const struct pl_raw_primaries *prim);
 PL_API pl_matrix3x3 pl_get_xyz2rgb_matrix(const struct pl_raw_primaries *prim);
 // colorspace.h:615 — white point of a colour temperature (K)
 PL_API struct pl_cie_xy pl_white_from_temp(float temperature);
+// colorspace.h:607-613 — its two ingredients: Planckian locus (1667-25000 K) and CIE daylight
+// (2500-25000 K; both clamp the temperature)
+PL_API struct pl_cie_xy pl_blackbody_from_temp(float temperature);
+PL_API struct pl_cie_xy pl_daylight_from_temp(float temperature);
 
 // colorspace.h:665-709 — colour-vision deficiency model (cone distortion). pl_render_params.
 // cone_params itself is outside the CUDA hot path (rejected); the matrices are T0 host code.

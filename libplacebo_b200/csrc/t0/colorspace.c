@@ -1051,6 +1051,8 @@ void pl_color_repr_merge(struct pl_color_repr *orig, const struct pl_color_repr 
 }
 
 struct pl_cie_xy pl_white_from_temp(float temp) { return white_from_temp(temp); }
+struct pl_cie_xy pl_blackbody_from_temp(float temp) { return blackbody_from_temp(temp); }
+struct pl_cie_xy pl_daylight_from_temp(float temp) { return daylight_from_temp(temp); }
 
 // --- CPU transfer functions -------------------------------------------------------------
 

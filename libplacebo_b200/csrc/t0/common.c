@@ -136,3 +136,141 @@ void pl_rect2df_rotate(pl_rect2df *rc, pl_rotation rot)
         *rc = same;
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// 2x2 matrices / affine transforms (common.h:64-116: sampling-rect rotation and offsets) and
+// the rect forms of the 3x3 ones. Same operation order as src/common.c:115-128, 207-217,
+// 238-393 (bit-exact vs the compiled reference, tests/test_t0_parity.py::test_matrix2x2_family).
+// ---------------------------------------------------------------------------------------
+const pl_matrix2x2 pl_matrix2x2_identity = {{ {1, 0}, {0, 1} }};
+const pl_transform2x2 pl_transform2x2_identity = { .mat = {{ {1, 0}, {0, 1} }} };
+
+pl_matrix2x2 pl_matrix2x2_rotation(float angle)
+{
+    const pl_matrix2x2 r = {{ { cosf(angle), -sinf(angle) }, { sinf(angle), cosf(angle) } }};
+    return r;
+}
+
+void pl_matrix2x2_apply(const pl_matrix2x2 *mat, float vec[2])
+{
+    const float x = vec[0], y = vec[1];
+    vec[0] = mat->m[0][0] * x + mat->m[0][1] * y;
+    vec[1] = mat->m[1][0] * x + mat->m[1][1] * y;
+}
+
+// both corners of the rect are mapped as points
+void pl_matrix2x2_apply_rc(const pl_matrix2x2 *mat, pl_rect2df *rc)
+{
+    float p0[2] = { rc->x0, rc->y0 }, p1[2] = { rc->x1, rc->y1 };
+    pl_matrix2x2_apply(mat, p0);
+    pl_matrix2x2_apply(mat, p1);
+    rc->x0 = p0[0]; rc->y0 = p0[1];
+    rc->x1 = p1[0]; rc->y1 = p1[1];
+}
+
+void pl_matrix2x2_mul(pl_matrix2x2 *a, const pl_matrix2x2 *b) // a := a * b
+{
+    const pl_matrix2x2 l = *a;
+    for (int i = 0; i < 2; i++) {
+        for (int j = 0; j < 2; j++)
+            a->m[i][j] = l.m[i][0] * b->m[0][j] + l.m[i][1] * b->m[1][j];
+    }
+}
+
+void pl_matrix2x2_rmul(const pl_matrix2x2 *a, pl_matrix2x2 *b) // b := a * b
+{
+    pl_matrix2x2 m = *a;
+    pl_matrix2x2_mul(&m, b);
+    *b = m;
+}
+
+void pl_matrix2x2_scale(pl_matrix2x2 *mat, float scale)
+{
+    for (int i = 0; i < 4; i++)
+        (&mat->m[0][0])[i] *= scale;
+}
+
+void pl_matrix2x2_invert(pl_matrix2x2 *mat)
+{
+    const float a = mat->m[0][0], b = mat->m[0][1], c = mat->m[1][0], d = mat->m[1][1];
+    const float invdet = 1.0f / (d * a - c * b);
+    mat->m[0][0] =  d * invdet;
+    mat->m[0][1] = -b * invdet;
+    mat->m[1][0] = -c * invdet;
+    mat->m[1][1] =  a * invdet;
+}
+
+void pl_transform2x2_apply(const pl_transform2x2 *t, float vec[2])
+{
+    pl_matrix2x2_apply(&t->mat, vec);
+    vec[0] += t->c[0];
+    vec[1] += t->c[1];
+}
+
+void pl_transform2x2_apply_rc(const pl_transform2x2 *t, pl_rect2df *rc)
+{
+    pl_matrix2x2_apply_rc(&t->mat, rc);
+    rc->x0 += t->c[0]; rc->x1 += t->c[0];
+    rc->y0 += t->c[1]; rc->y1 += t->c[1];
+}
+
+void pl_transform2x2_mul(pl_transform2x2 *a, const pl_transform2x2 *b) // a := a o b
+{
+    float c[2] = { b->c[0], b->c[1] };
+    pl_transform2x2_apply(a, c);
+    a->c[0] = c[0];
+    a->c[1] = c[1];
+    pl_matrix2x2_mul(&a->mat, &b->mat);
+}
+
+void pl_transform2x2_rmul(const pl_transform2x2 *a, pl_transform2x2 *b) // b := a o b
+{
+    pl_transform2x2_apply(a, b->c);
+    pl_matrix2x2_rmul(&a->mat, &b->mat);
+}
+
+void pl_transform2x2_scale(pl_transform2x2 *t, float scale)
+{
+    pl_matrix2x2_scale(&t->mat, scale);
+    t->c[0] *= scale;
+    t->c[1] *= scale;
+}
+
+void pl_transform2x2_invert(pl_transform2x2 *t) // x = M^-1 y - M^-1 c
+{
+    pl_matrix2x2_invert(&t->mat);
+    const float c0 = t->c[0], c1 = t->c[1];
+    t->c[0] = -(t->mat.m[0][0] * c0 + t->mat.m[0][1] * c1);
+    t->c[1] = -(t->mat.m[1][0] * c0 + t->mat.m[1][1] * c1);
+}
+
+// axis-aligned bounding box of the transformed rect (its four corners)
+pl_rect2df pl_transform2x2_bounds(const pl_transform2x2 *t, const pl_rect2df *rc)
+{
+    float p[4][2] = { { rc->x0, rc->y0 }, { rc->x0, rc->y1 }, { rc->x1, rc->y0 }, { rc->x1, rc->y1 } };
+    for (int i = 0; i < 4; i++)
+        pl_transform2x2_apply(t, p[i]);
+    pl_rect2df out;
+    out.x0 = fminf(fminf(p[0][0], p[1][0]), fminf(p[2][0], p[3][0]));
+    out.x1 = fmaxf(fmaxf(p[0][0], p[1][0]), fmaxf(p[2][0], p[3][0]));
+    out.y0 = fminf(fminf(p[0][1], p[1][1]), fminf(p[2][1], p[3][1]));
+    out.y1 = fmaxf(fmaxf(p[0][1], p[1][1]), fmaxf(p[2][1], p[3][1]));
+    return out;
+}
+
+void pl_matrix3x3_apply_rc(const pl_matrix3x3 *mat, pl_rect3df *rc)
+{
+    float p0[3] = { rc->x0, rc->y0, rc->z0 }, p1[3] = { rc->x1, rc->y1, rc->z1 };
+    pl_matrix3x3_apply(mat, p0);
+    pl_matrix3x3_apply(mat, p1);
+    rc->x0 = p0[0]; rc->y0 = p0[1]; rc->z0 = p0[2];
+    rc->x1 = p1[0]; rc->y1 = p1[1]; rc->z1 = p1[2];
+}
+
+void pl_transform3x3_apply_rc(const pl_transform3x3 *t, pl_rect3df *rc)
+{
+    pl_matrix3x3_apply_rc(&t->mat, rc);
+    rc->x0 += t->c[0]; rc->x1 += t->c[0];
+    rc->y0 += t->c[1]; rc->y1 += t->c[1];
+    rc->z0 += t->c[2]; rc->z1 += t->c[2];
+}

@@ -315,3 +315,38 @@ def test_filter_presets(ref, pt0):
         i += 1
     assert i >= 26
     assert not pt0.lib.plt_filter_preset(-1, b, 256) >= 0
+
+
+def test_matrix2x2_family(ref, pt0):
+    """pl_matrix2x2_* / pl_transform2x2_* / *_apply_rc / pl_transform2x2_bounds and the two
+    colour-temperature loci: bit-identical with the compiled reference."""
+    fr, fp_ = _both(ref, pt0, "mat2_op")
+    rng = np.random.default_rng(31)
+    for op in range(14):
+        for _ in range(40):
+            t = rng.uniform(-3, 3, 6).astype(T.f32)
+            u = rng.uniform(-3, 3, 6).astype(T.f32)
+            rc = rng.uniform(-500, 2000, 4).astype(T.f32)
+            v = rng.uniform(-7, 7, 2).astype(T.f32)
+            a = [x.copy() for x in (t, u, rc, v)]
+            b = [x.copy() for x in (t, u, rc, v)]
+            fr(op, *[T.fp(x) for x in a])
+            fp_(op, *[T.fp(x) for x in b])
+            for x, y in zip(a, b):
+                assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (op, t, u, rc, v)
+    gr, gp = _both(ref, pt0, "mat3_apply_rc")
+    for off in (0, 1):
+        for _ in range(40):
+            m = rng.uniform(-2, 2, 12).astype(T.f32)
+            rc = rng.uniform(-1, 2, 6).astype(T.f32)
+            x, y = rc.copy(), rc.copy()
+            gr(T.fp(m), off, T.fp(x))
+            gp(T.fp(m), off, T.fp(y))
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (off, m, rc)
+    lr, lp = _both(ref, pt0, "locus_from_temp")
+    for kind in (0, 1):
+        for temp in (500, 1667, 2222, 2500, 4000, 5000, 6504, 7000, 12000, 25000, 60000):
+            x, y = np.zeros(2, T.f32), np.zeros(2, T.f32)
+            lr(kind, C.c_float(temp), T.fp(x))
+            lp(kind, C.c_float(temp), T.fp(y))
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (kind, temp)
