@@ -655,6 +655,9 @@ struct pl_fmt_t { /* gpu.h:270-340 */
     const uint64_t *modifiers;
     int num_modifiers;
 };
+// gpu.h:325-331 — components stored in RGBA order / floating-point texels
+PL_API bool pl_fmt_is_ordered(pl_fmt fmt);
+PL_API bool pl_fmt_is_float(pl_fmt fmt);
 PL_API pl_fmt pl_find_fmt(pl_gpu gpu, enum pl_fmt_type type, int num_components,
                           int min_depth, int host_bits, enum pl_fmt_caps caps);
 PL_API pl_fmt pl_find_named_fmt(pl_gpu gpu, const char *name);
@@ -731,6 +734,14 @@ PL_API void pl_tex_destroy(pl_gpu gpu, pl_tex *tex);
 PL_API bool pl_tex_recreate(pl_gpu gpu, pl_tex *tex, const struct pl_tex_params *params);
 PL_API void pl_tex_invalidate(pl_gpu gpu, pl_tex tex);
 PL_API void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4]);
+// gpu.h:815-826 — clear with a typed colour; on this backend every clearable format is unorm /
+// float (color.f); integer formats are rejected with an error message
+union pl_clear_color {
+    float f[4];
+    int32_t i[4];
+    uint32_t u[4];
+};
+PL_API void pl_tex_clear_ex(pl_gpu gpu, pl_tex dst, const union pl_clear_color color);
 struct pl_tex_transfer_params { /* gpu.h:852-919 */
     pl_tex tex;
     pl_rect3d rc;

@@ -697,6 +697,29 @@ void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4])
     plb_gpu_after_use(gpu, &dst, 1);
 }
 
+void pl_tex_clear_ex(pl_gpu gpu, pl_tex dst, const union pl_clear_color color)
+{
+    const enum pl_fmt_type type = dst->params.format->type;
+    if (type == PL_FMT_UINT || type == PL_FMT_SINT) {
+        PLB_ERR(gpu->log, "pl_tex_clear_ex: integer formats are not clearable on the CUDA backend");
+        return;
+    }
+    pl_tex_clear(gpu, dst, color.f);
+}
+
+bool pl_fmt_is_ordered(pl_fmt fmt)
+{
+    bool ordered = true;
+    for (int i = 0; i < fmt->num_components; i++)
+        ordered &= fmt->sample_order[i] == i;
+    return ordered;
+}
+
+bool pl_fmt_is_float(pl_fmt fmt)
+{
+    return fmt->type != PL_FMT_UINT && fmt->type != PL_FMT_SINT; // unknown counts as float (gpu.c:61-75)
+}
+
 static void CUDART_CB host_cb_trampoline(void *data)
 {
     void **pair = (void **) data;
