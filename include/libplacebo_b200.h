@@ -800,10 +800,18 @@ PL_API uint64_t pl_cuda_launch_count(pl_gpu gpu);
 // copy-engine streams — e.g. before recording an event that should cover a whole frame.
 PL_API void pl_cuda_join(pl_gpu gpu);
 // Diagnostics: evaluates the kernels' deterministic transcendental functions (plb_math.cuh) on
-// host arrays of n floats. fn: 0 pow(a,b) 1 exp(a) 2 log(a) 3 sin(a) 4 cos(a) 5 atan2(a,b).
+// host arrays of n floats. fn: 0 pow(a,b) 1 exp(a) 2 log(a) 3 sin(a) 4 cos(a) 5 atan2(a,b)
+// (binary64 definitions); 6 sin 7 cos 8 atan2 (fp32 hot-path definitions); 16 + id: transfer curve
+// `id` of pl_cuda_curve_table with its exact fallback outside the tabulated domain.
 // Returns false on a CUDA error. Lets integrators check cross-machine reproducibility.
 PL_API bool pl_cuda_math_eval(pl_gpu gpu, int fn, const float *a, const float *b, float *out,
                               size_t n);
+// Diagnostics (host only, no GPU needed): the piecewise-cubic table that defines transfer curve
+// `id` (csrc/curves.h: PQ EOTF / OETF, BT.1886 powers) exactly as the kernels receive it.
+// Segment 0 is the constant below the domain; segment i >= 1 covers the float bit patterns
+// [(base + i) << (23 - mbits), (base + i + 1) << (23 - mbits)). `coef` may be NULL to query the
+// sizes, else it receives 4 * (*nseg + 1) floats (c0..c3 per segment).
+PL_API bool pl_cuda_curve_table(int id, int *base, int *nseg, int *mbits, float *coef);
 
 /* ---- shaders.h -------------------------------------------------------------------------- */
 typedef struct pl_shader_t *pl_shader;

@@ -13,14 +13,6 @@
 #include "kernels_common.cuh"
 #include "plb_math.cuh"
 
-// One copy of the PQ/HLG literal table per translation unit (no relocatable device code);
-// every .cu that includes this header instantiates PLB_DEFINE_PQ_UPLOAD(name) and
-// plb_upload_pq_consts() (shaders.cpp) calls them all at pl_cuda_create time.
-static __constant__ plb_pq_consts c_pq;
-#define PLB_DEFINE_PQ_UPLOAD(name) \
-    extern "C" bool name(const plb_pq_consts *q) \
-    { return cudaMemcpyToSymbol(c_pq, q, sizeof(*q)) == cudaSuccess; }
-
 enum {
     TRC_UNKNOWN = 0, TRC_BT_1886, TRC_SRGB, TRC_LINEAR, TRC_GAMMA18, TRC_GAMMA20,
     TRC_GAMMA22, TRC_GAMMA24, TRC_GAMMA26, TRC_GAMMA28, TRC_PRO_PHOTO, TRC_ST428,
@@ -53,44 +45,57 @@ PLB_DEV void plb_mat3_lit(const float *m, float &r, float &g, float &b)
     b = plb_dot3_fma(m[2], m[5], m[8], x, y, z);
 }
 
-PLB_DEV float plb_pq_eotf(float x, bool clamp0)
+// PQ EOTF / OETF (colorspace.c:662-668, :778-784). The composite function is a transfer curve
+// (curves.h); arguments outside its domain take the exact pow / divide / pow chain, out of line.
+static __device__ __noinline__ float plb_pq_eotf_slow(float x)
 {
-    x = plm_powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.inv_m2);
+    x = plm_powf(x, c_pq.inv_m2);
     x = fmaxf(x - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x);
     return plm_powf(x, c_pq.inv_m1);
 }
 
-// three-channel forms (same per-element arithmetic, one plm_pow3 call per power)
-PLB_DEV void plb_pq_eotf3(float c[3], bool clamp0, float post_scale)
+static __device__ __noinline__ float plb_pq_oetf_slow(float x)
 {
-    float3 x = make_float3(clamp0 ? fmaxf(c[0], 0.0f) : c[0], clamp0 ? fmaxf(c[1], 0.0f) : c[1],
-                           clamp0 ? fmaxf(c[2], 0.0f) : c[2]);
-    x = plm_pow3(x, c_pq.inv_m2);
-    x.x = fmaxf(x.x - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.x);
-    x.y = fmaxf(x.y - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.y);
-    x.z = fmaxf(x.z - c_pq.c1, 0.0f) / (c_pq.c2 - c_pq.c3 * x.z);
-    x = plm_pow3(x, c_pq.inv_m1);
-    c[0] = x.x * post_scale; c[1] = x.y * post_scale; c[2] = x.z * post_scale;
+    x = plm_powf(x, c_pq.m1);
+    x = (c_pq.c1 + c_pq.c2 * x) / (1.0f + c_pq.c3 * x);
+    return plm_powf(x, c_pq.m2);
 }
 
-PLB_DEV void plb_pq_oetf3(float c[3], bool clamp0, float pre_scale)
+// CV = PLB_CV_PQ_EOTF (plain) or PLB_CV_PQ_EOTF_SDR (result * from_pq, the "203 nits = 1" scale)
+template <int CV>
+PLB_DEV float plb_pq_eotf_cv(float x)
 {
-    float3 x = make_float3(c[0] * pre_scale, c[1] * pre_scale, c[2] * pre_scale);
+    float y;
+    if (plm_curve<CV>(x, y))
+        return y;
+    y = plb_pq_eotf_slow(x);
+    return CV == PLB_CV_PQ_EOTF_SDR ? y * c_pq.from_pq : y;
+}
+
+// CV = PLB_CV_PQ_OETF (plain), _SDR (argument * to_pq) or _DELIN (argument * 1/from_pq)
+template <int CV>
+PLB_DEV float plb_pq_oetf_cv(float x, bool clamp0)
+{
+    float y;
     if (clamp0)
-        x = make_float3(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f), fmaxf(x.z, 0.0f));
-    x = plm_pow3(x, c_pq.m1);
-    x.x = (c_pq.c1 + c_pq.c2 * x.x) / (1.0f + c_pq.c3 * x.x);
-    x.y = (c_pq.c1 + c_pq.c2 * x.y) / (1.0f + c_pq.c3 * x.y);
-    x.z = (c_pq.c1 + c_pq.c2 * x.z) / (1.0f + c_pq.c3 * x.z);
-    x = plm_pow3(x, c_pq.m2);
-    c[0] = x.x; c[1] = x.y; c[2] = x.z;
+        x = fmaxf(x, 0.0f);
+    if (plm_curve<CV>(x, y))
+        return y;
+    if (CV == PLB_CV_PQ_OETF_SDR)
+        x *= c_pq.to_pq;
+    if (CV == PLB_CV_PQ_OETF_DELIN)
+        x *= c_pq.inv_from_pq;
+    return plb_pq_oetf_slow(x);
+}
+
+PLB_DEV float plb_pq_eotf(float x, bool clamp0)
+{
+    return plb_pq_eotf_cv<PLB_CV_PQ_EOTF>(clamp0 ? fmaxf(x, 0.0f) : x);
 }
 
 PLB_DEV float plb_pq_oetf(float x, bool clamp0)
 {
-    x = plm_powf(clamp0 ? fmaxf(x, 0.0f) : x, c_pq.m1);
-    x = (c_pq.c1 + c_pq.c2 * x) / (1.0f + c_pq.c3 * x);
-    return plm_powf(x, c_pq.m2);
+    return plb_pq_oetf_cv<PLB_CV_PQ_OETF>(x, clamp0);
 }
 
 // `trc` is passed beside the constants so that a caller that knows it at compile time (the
@@ -108,20 +113,21 @@ PLB_DEV void plb_linearize(const int trc, const plb_trc_consts &t, float c[3])
     switch (trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.04045f < c[k] ? plm_powf((c[k] + 0.055f) / 1.055f, 2.4f)
+            c[k] = 0.04045f < c[k] ? plm_pow_cv<PLB_CV_POW_24>((c[k] + 0.055f) / 1.055f)
                                    : c[k] * (float) (1.0 / 12.92);
         post_scale = true;
         break;
     case TRC_BT_1886: {
-        const float3 p = plm_pow3(make_float3(c[0] + t.b, c[1] + t.b, c[2] + t.b), 2.4f);
-        c[0] = t.a * p.x; c[1] = t.a * p.y; c[2] = t.a * p.z;
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = t.a * plm_pow_cv<PLB_CV_POW_24>(c[k] + t.b);
         break;
     }
     case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 1.8f); post_scale = true; break;
     case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.0f); post_scale = true; break;
     case TRC_UNKNOWN:
-    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.2f); post_scale = true; break;
-    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.4f); post_scale = true; break;
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_pow_cv<PLB_CV_POW_22>(c[k]); post_scale = true; break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_pow_cv<PLB_CV_POW_24>(c[k]); post_scale = true; break;
     case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.6f); post_scale = true; break;
     case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], 2.8f); post_scale = true; break;
     case TRC_PRO_PHOTO:
@@ -135,7 +141,9 @@ PLB_DEV void plb_linearize(const int trc, const plb_trc_consts &t, float c[3])
         post_scale = true;
         break;
     case TRC_PQ:
-        plb_pq_eotf3(c, false, c_pq.from_pq);
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_eotf_cv<PLB_CV_PQ_EOTF_SDR>(c[k]);
         break;
     case TRC_HLG: {
         // t.a = y, t.b = b
@@ -196,19 +204,20 @@ PLB_DEV void plb_delinearize(const int trc, const plb_trc_consts &t, float c[3])
     switch (trc) {
     case TRC_SRGB:
         for (int k = 0; k < 3; k++)
-            c[k] = 0.0031308f <= c[k] ? 1.055f * plm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
+            c[k] = 0.0031308f <= c[k] ? 1.055f * plm_pow_cv<PLB_CV_POW_INV24>(c[k]) - 0.055f
                                       : c[k] * 12.92f;
         break;
     case TRC_BT_1886: { // t.a = 1/a, t.b = b
-        const float3 p = plm_pow3(make_float3(t.a * c[0], t.a * c[1], t.a * c[2]), (float) (1.0 / 2.4));
-        c[0] = p.x - t.b; c[1] = p.y - t.b; c[2] = p.z - t.b;
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = plm_pow_cv<PLB_CV_POW_INV24>(t.a * c[k]) - t.b;
         break;
     }
     case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 1.8)); break;
     case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.0)); break;
     case TRC_UNKNOWN:
-    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.2)); break;
-    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.4)); break;
+    case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = plm_pow_cv<PLB_CV_POW_INV22>(c[k]); break;
+    case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = plm_pow_cv<PLB_CV_POW_INV24>(c[k]); break;
     case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.6)); break;
     case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = plm_powf(c[k], (float) (1.0 / 2.8)); break;
     case TRC_ST428:
@@ -220,7 +229,9 @@ PLB_DEV void plb_delinearize(const int trc, const plb_trc_consts &t, float c[3])
             c[k] = 0.001953f <= c[k] ? plm_powf(c[k], (float) (1.0 / 1.8)) : c[k] * 16.0f;
         break;
     case TRC_PQ:
-        plb_pq_oetf3(c, false, c_pq.inv_from_pq);
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = plb_pq_oetf_cv<PLB_CV_PQ_OETF_DELIN>(c[k], false);
         break;
     case TRC_HLG: {
         for (int k = 0; k < 3; k++)
@@ -387,8 +398,9 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
     float lms[3] = { px[0], px[1], px[2] };
     plb_matv(p.rgb2lms, lms[0], lms[1], lms[2]);
     float ipt[3];
-    ipt[0] = lms[0]; ipt[1] = lms[1]; ipt[2] = lms[2];
-    plb_pq_oetf3(ipt, true, c_pq.to_pq);
+    #pragma unroll
+    for (int k = 0; k < 3; k++)
+        ipt[k] = plb_pq_oetf_cv<PLB_CV_PQ_OETF_SDR>(lms[k], true);
     plb_matv(lms2ipt, ipt[0], ipt[1], ipt[2]);
     const float i_orig = ipt[0];
 
@@ -415,15 +427,16 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
         float idx[3];
         idx[0] = p.g_a * ipt[0] + p.g_b;
         idx[1] = 2.0f * sqrtf(__fmaf_rn(ipt[1], ipt[1], ipt[2] * ipt[2]));
-        idx[2] = c_pq.inv_2pi * plm_atan2f(ipt[2], ipt[1]) + 0.5f;
+        idx[2] = c_pq.inv_2pi * plm_atan2_fast(ipt[2], ipt[1]) + 0.5f;
         plb_gamut_sample(p, idx, ipt);
         ipt[1] -= (float) (32768.0 / 65535.0);
         ipt[2] -= (float) (32768.0 / 65535.0);
     }
 
     plb_matv(ipt2lms, ipt[0], ipt[1], ipt[2]);
-    lms[0] = ipt[0]; lms[1] = ipt[1]; lms[2] = ipt[2];
-    plb_pq_eotf3(lms, true, c_pq.from_pq);
+    #pragma unroll
+    for (int k = 0; k < 3; k++)
+        lms[k] = plb_pq_eotf_cv<PLB_CV_PQ_EOTF_SDR>(fmaxf(ipt[k], 0.0f));
     plb_matv(p.lms2rgb, lms[0], lms[1], lms[2]);
     px[0] = lms[0]; px[1] = lms[1]; px[2] = lms[2];
 }
@@ -522,9 +535,15 @@ PLB_DEV uint32_t plb_peak_ypq(const int trc, const plb_op_peak &p, const float c
     const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
                 PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
     luma *= 203.0f / 10000.0f;
-    luma = plm_powf(plb_clamp(luma, 0.0f, 1.0f), PQ_M1);
-    luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
-    luma = plm_powf(luma, PQ_M2);
+    luma = plb_clamp(luma, 0.0f, 1.0f);
+    float pqv;
+    if (plm_curve<PLB_CV_PQX_OETF>(luma, pqv)) {
+        luma = pqv;
+    } else {
+        luma = plm_powf(luma, PQ_M1);
+        luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
+        luma = plm_powf(luma, PQ_M2);
+    }
     if (p.cutoff != 0.0f) {
         float t = plb_clamp((luma - 0.0f) / (p.cutoff - 0.0f), 0.0f, 1.0f);
         luma *= t * t * (3.0f - 2.0f * t);
@@ -809,7 +828,9 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
             // lms = (k * M) * rgb; PQ (clamped at 0); I = dot((0.4, 0.4, 0.2), lms)
             float lms[3] = { c[0], c[1], c[2] };
             plb_matv(op.u.features.m, lms[0], lms[1], lms[2]);
-            plb_pq_oetf3(lms, true, 1.0f);
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                lms[k] = plb_pq_oetf(lms[k], true);
             c[0] = __fmaf_rn(0.2f, lms[2], __fmaf_rn(0.4f, lms[1], 0.4f * lms[0]));
             c[1] = 0.0f; c[2] = 0.0f; c[3] = 1.0f;
             break;

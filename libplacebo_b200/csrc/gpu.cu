@@ -374,6 +374,8 @@ error:
     return NULL;
 }
 
+static void bank_release(int device);
+
 void pl_cuda_destroy(pl_gpu *pgpu)
 {
     if (!pgpu || !*pgpu)
@@ -382,6 +384,8 @@ void pl_cuda_destroy(pl_gpu *pgpu)
     cudaSetDevice(p->device);
     if (p->stream)
         cudaStreamSynchronize((cudaStream_t) p->stream);
+    if (p->bank_ref)
+        bank_release(p->device);
     if (p->h2d_stream) {
         cudaStreamSynchronize((cudaStream_t) p->h2d_stream);
         cudaStreamDestroy((cudaStream_t) p->h2d_stream);
@@ -412,11 +416,68 @@ bool plb_pq_upload_polar(const plb_pq_consts *q);
 bool plb_pq_upload_pixel(const plb_pq_consts *q);
 bool plb_pq_upload_ortho(const plb_pq_consts *q);
 
+// Transfer-curve tables (curves.h) live once per device, shared by every pl_gpu on it: the
+// descriptors sit in __constant__ memory, which is per device, not per pl_gpu.
+#include <pthread.h>
+#define PLB_MAX_DEVICES 64
+static struct {
+    int refs;
+    void *tables[PLB_CV_COUNT];
+} g_bank[PLB_MAX_DEVICES];
+static pthread_mutex_t g_bank_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void bank_release(int device)
+{
+    pthread_mutex_lock(&g_bank_lock);
+    if (g_bank[device].refs > 0 && --g_bank[device].refs == 0) {
+        for (int i = 0; i < PLB_CV_COUNT; i++) {
+            cudaFree(g_bank[device].tables[i]);
+            g_bank[device].tables[i] = NULL;
+        }
+    }
+    pthread_mutex_unlock(&g_bank_lock);
+}
+
 bool plb_upload_pq_consts(pl_gpu gpu)
 {
-    struct plb_pq_consts q;
-    plb_pq_literal(&q);
-    bool ok = plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (p->device < 0 || p->device >= PLB_MAX_DEVICES)
+        return false;
+    pthread_mutex_lock(&g_bank_lock);
+    bool ok = true;
+    if (g_bank[p->device].refs == 0) {
+        struct plb_pq_consts q;
+        plb_pq_literal(&q);
+        const char *e = getenv("PLB_EXACT_MATH");
+        q.exact_math = e && atoi(e) != 0;
+        for (int i = 0; i < PLB_CV_COUNT && ok; i++) {
+            struct plb_curve_host h;
+            ok = plb_curve_generate(i, &q, &h);
+            if (!ok)
+                break;
+            const size_t bytes = (size_t) (h.nseg + 1) * 4 * sizeof(float);
+            void *d = NULL;
+            ok = cudaMalloc(&d, bytes) == cudaSuccess &&
+                 cudaMemcpy(d, h.coef, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+            free(h.coef);
+            g_bank[p->device].tables[i] = d;
+            q.cv[i].coef = d;
+            q.cv[i].base = h.base;
+            q.cv[i].nseg = q.exact_math ? -1 : h.nseg; // -1: even the segment below the domain misses
+        }
+        ok = ok && plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
+        if (!ok) {
+            for (int i = 0; i < PLB_CV_COUNT; i++) {
+                cudaFree(g_bank[p->device].tables[i]);
+                g_bank[p->device].tables[i] = NULL;
+            }
+        }
+    }
+    if (ok) {
+        g_bank[p->device].refs++;
+        p->bank_ref = true;
+    }
+    pthread_mutex_unlock(&g_bank_lock);
     if (!ok)
         PLB_ERR(gpu->log, "failed uploading constant tables");
     return ok;

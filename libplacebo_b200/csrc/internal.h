@@ -4,6 +4,7 @@
 #define PLB_INTERNAL_H_
 
 #include "../../include/libplacebo_b200.h"
+#include "curves.h"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -95,6 +96,7 @@ struct plb_gpu {
     bool own_stream;
     bool failed;
     bool no_timers;
+    bool bank_ref;         // holds a reference on the device's transfer-curve tables
     int coord_mode;        // enum plb_coord_mode used by samplers
     uint64_t launches;     // kernels launched (pl_cuda_launch_count)
     int sm_count;
@@ -225,6 +227,9 @@ struct plb_color_prog {
 // PQ constants as the reference's GLSL text carries them ("%f" = 6 decimals), computed on
 // the host once (csrc/shaders.cpp: plb_pq_literal) and handed to kernels in constant memory
 struct plb_pq_consts {
+    // transfer curves (curves.h), filled by gpu.cu after the tables are uploaded
+    struct plb_curve cv[PLB_CV_COUNT];
+    int exact_math;        // PLB_EXACT_MATH=1: round-1 binary64 definitions everywhere
     float m1, m2, c1, c2, c3, inv_m1, inv_m2, to_pq, from_pq, inv_from_pq;
     float hlg_a, hlg_b, hlg_c, hlg_inv_a;
     float inv_2pi;
@@ -379,6 +384,7 @@ struct plb_errdiff_launch {
 bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p);
 
 void plb_pq_literal(struct plb_pq_consts *q);
+bool plb_curve_generate(int id, const struct plb_pq_consts *q, struct plb_curve_host *out);
 bool plb_upload_pq_consts(pl_gpu gpu);
 bool plb_gpu_no_timers(pl_gpu gpu);
 

@@ -412,6 +412,28 @@ __global__ void k_math_eval(int fn, const float *a, const float *b, float *out, 
         case 3: plm_sincosf(a[i], &s, &c); r = s; break;
         case 4: plm_sincosf(a[i], &s, &c); r = c; break;
         case 5: r = plm_atan2f(a[i], b[i]); break;
+        case 6: plm_sincos_fast(a[i], &s, &c); r = s; break;
+        case 7: plm_sincos_fast(a[i], &s, &c); r = c; break;
+        case 8: r = plm_atan2_fast(a[i], b[i]); break;
+        case 16 + PLB_CV_PQ_EOTF_SDR:   r = plb_pq_eotf_cv<PLB_CV_PQ_EOTF_SDR>(a[i]); break;
+        case 16 + PLB_CV_PQ_EOTF:       r = plb_pq_eotf_cv<PLB_CV_PQ_EOTF>(a[i]); break;
+        case 16 + PLB_CV_PQ_OETF_SDR:   r = plb_pq_oetf_cv<PLB_CV_PQ_OETF_SDR>(a[i], false); break;
+        case 16 + PLB_CV_PQ_OETF_DELIN: r = plb_pq_oetf_cv<PLB_CV_PQ_OETF_DELIN>(a[i], false); break;
+        case 16 + PLB_CV_PQ_OETF:       r = plb_pq_oetf_cv<PLB_CV_PQ_OETF>(a[i], false); break;
+        case 16 + PLB_CV_PQX_OETF: {
+            const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
+                        PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
+            if (!plm_curve<PLB_CV_PQX_OETF>(a[i], r)) {
+                r = plm_powf(a[i], PQ_M1);
+                r = (PQ_C1 + PQ_C2 * r) / (1.0f + PQ_C3 * r);
+                r = plm_powf(r, PQ_M2);
+            }
+            break;
+        }
+        case 16 + PLB_CV_POW_24:        r = plm_pow_cv<PLB_CV_POW_24>(a[i]); break;
+        case 16 + PLB_CV_POW_INV24:     r = plm_pow_cv<PLB_CV_POW_INV24>(a[i]); break;
+        case 16 + PLB_CV_POW_22:        r = plm_pow_cv<PLB_CV_POW_22>(a[i]); break;
+        case 16 + PLB_CV_POW_INV22:     r = plm_pow_cv<PLB_CV_POW_INV22>(a[i]); break;
         default: r = __int_as_float(0x7fc00000);
         }
         out[i] = r;

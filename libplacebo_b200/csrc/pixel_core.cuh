@@ -84,7 +84,7 @@ PLB_DEV void plb_deband(const plb_plane_src &pl, const plb_coord &cc, float posx
         const float dist = rnd.x * ((float) i * pl.radius);
         const float dir = rnd.y * 6.283185f;
         float sn, cs;
-        plm_sincosf(dir, &sn, &cs);
+        plm_sincos_fast(dir, &sn, &cs);
         const float dx = dist * cs, dy = dist * sn;
         float avg[3] = {0.0f, 0.0f, 0.0f};
         #pragma unroll

@@ -649,6 +649,7 @@ static const float HLG_REF = 1000.0 / PL_COLOR_SDR_WHITE;
 
 void plb_pq_literal(struct plb_pq_consts *q)
 {
+    memset(q, 0, sizeof(*q));
     q->m1 = (float) glsl6(PQ_M1);
     q->m2 = (float) glsl6(PQ_M2);
     q->c1 = (float) glsl6(PQ_C1);

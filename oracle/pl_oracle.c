@@ -567,7 +567,7 @@ void orc_deband(const struct orc_tex *src, const struct orc_deband_params *p, fl
                 float dist = rnd[0] * ((float) i * radius);
                 float dir = rnd[1] * two_pi_lit;
                 float sn, cs;
-                pm_sincosf(dir, &sn, &cs);
+                pf_sincosf(dir, &sn, &cs);
                 float dx = dist * cs, dy = dist * sn;
                 const float sgx[4] = {+1, -1, -1, +1}, sgy[4] = {+1, +1, -1, -1};
                 for (int k = 0; k < 4; k++)
@@ -689,10 +689,16 @@ void orc_polar_ideal(const struct orc_tex *src, int dw, int dh, double radius,
 // ------------------------------------------------------------------------------------------
 // Array front-end to the portable math definitions (pl_oracle_math.h), for the tests that pin
 // them against libm and against the CUDA restatement.
-//   fn: 0 pow(a,b)  1 exp(a)  2 log(a)  3 sin(a)  4 cos(a)  5 atan2(a,b)  6 log2(a)
+//   fn: 0 pow(a,b)  1 exp(a)  2 log(a)  3 sin(a)  4 cos(a)  5 atan2(a,b)  (binary64 definitions)
+//       6 sin(a)  7 cos(a)  8 atan2(a,b)  (fp32 hot-path definitions)  9 log2(a)
+//       16 + id: transfer curve `id` with its exact fallback (pl_oracle_color.c)
 // ------------------------------------------------------------------------------------------
 void orc_math(int fn, const float *a, const float *b, float *out, size_t n)
 {
+    if (fn >= 16) {
+        orc_curve_apply(fn - 16, a, out, n);
+        return;
+    }
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; i++) {
         float s, c;
@@ -703,7 +709,10 @@ void orc_math(int fn, const float *a, const float *b, float *out, size_t n)
         case 3: pm_sincosf(a[i], &s, &c); out[i] = s; break;
         case 4: pm_sincosf(a[i], &s, &c); out[i] = c; break;
         case 5: out[i] = pm_atan2f(a[i], b[i]); break;
-        case 6: out[i] = pm_log2f(a[i]); break;
+        case 6: pf_sincosf(a[i], &s, &c); out[i] = s; break;
+        case 7: pf_sincosf(a[i], &s, &c); out[i] = c; break;
+        case 8: out[i] = pf_atan2f(a[i], b[i]); break;
+        case 9: out[i] = pm_log2f(a[i]); break;
         default: out[i] = NAN;
         }
     }

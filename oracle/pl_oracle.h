@@ -299,8 +299,13 @@ ORC_API int orc_num_threads(void);
 #endif
 
 // Array front-end to the portable math definitions of pl_oracle_math.h:
-// fn 0 pow(a,b), 1 exp(a), 2 log(a), 3 sin(a), 4 cos(a), 5 atan2(a,b), 6 log2(a)
+// fn 0 pow(a,b), 1 exp(a), 2 log(a), 3 sin(a), 4 cos(a), 5 atan2(a,b) (binary64 definitions),
+// 6 sin, 7 cos, 8 atan2 (fp32 hot-path definitions), 9 log2(a), 16 + id: transfer curve `id`
+// (pl_oracle_curve.h) with its exact fallback
 void orc_math(int fn, const float *a, const float *b, float *out, size_t n);
+ORC_API void orc_curve_apply(int id, const float *x, float *out, size_t n);
+ORC_API void orc_set_exact_math(int on);
+ORC_API int orc_curve_table(int id, int *base, int *nseg, int *mbits, float *coef);
 
 // Evaluate ew x eh invocations (>= the output size) in orc_sample_polar / orc_sample_direct /
 // orc_deband: the overhang of the last work groups, which peak detection counts. 0,0 = off.

@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include "pl_oracle_math.h"
+#include "pl_oracle_curve.h"
 #include <string.h>
 
 static inline float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
@@ -66,6 +67,72 @@ static struct pq_lit pq_literal(void)
     q.from_pq = (float) glsl6(10000 / SDR_WHITE);
     return q;
 }
+
+// ------------------------------------------------------------------------------------------
+// Transfer curves (pl_oracle_curve.h): built once, on first use
+// ------------------------------------------------------------------------------------------
+
+int orc_math_exact = 0;
+static struct orc_curve g_curves[ORC_CV_COUNT];
+static int g_curves_ready;
+
+static void curves_init(void)
+{
+    if (g_curves_ready)
+        return;
+    #pragma omp critical(orc_curves)
+    if (!g_curves_ready) {
+        const struct pq_lit l = pq_literal();
+        const struct orc_pq_consts lit = { l.m1, l.m2, l.c1, l.c2, l.c3, l.inv_m1, l.inv_m2 };
+        const struct orc_pq_consts exact = { PQ_M1, PQ_M2, PQ_C1, PQ_C2, PQ_C3, 0, 0 };
+        const double pq_pre = (float) (1.0 / glsl6(10000 / SDR_WHITE));
+        const struct orc_curve_spec specs[ORC_CV_COUNT] = {
+            [ORC_CV_PQ_EOTF_SDR]   = { 0, lit, l.from_pq, 0, -21, 0x3FC00000u }, // < 1.5
+            [ORC_CV_PQ_EOTF]       = { 0, lit, 1.0, 0, -21, 0x3FC00000u },
+            [ORC_CV_PQ_OETF_SDR]   = { 1, lit, l.to_pq, 0, -58, 0x43800000u },   // < 256
+            [ORC_CV_PQ_OETF_DELIN] = { 1, lit, pq_pre, 0, -58, 0x43800000u },
+            [ORC_CV_PQ_OETF]       = { 1, lit, 1.0, 0, -64, 0x41000000u },       // < 8
+            [ORC_CV_PQX_OETF]      = { 1, exact, 1.0, 0, -64, 0x40000000u },     // < 2
+            [ORC_CV_POW_24]        = { 2, lit, 1.0, 2.4f, -20, 0x41000000u },
+            [ORC_CV_POW_INV24]     = { 2, lit, 1.0, (float) (1.0 / 2.4), -96, 0x41800000u }, // < 16
+            [ORC_CV_POW_22]        = { 2, lit, 1.0, 2.2f, -20, 0x41000000u },
+            [ORC_CV_POW_INV22]     = { 2, lit, 1.0, (float) (1.0 / 2.2), -96, 0x41800000u },
+        };
+        for (int i = 0; i < ORC_CV_COUNT; i++)
+            orc_curve_build(&g_curves[i], i, &specs[i]);
+        g_curves_ready = 1;
+    }
+}
+
+ORC_API void orc_set_exact_math(int on) { orc_math_exact = on; }
+
+// the table of curve `id` (tests/test_curves.py compares it with the product's)
+ORC_API int orc_curve_table(int id, int *base, int *nseg, int *mbits, float *coef)
+{
+    if (id < 0 || id >= ORC_CV_COUNT)
+        return 0;
+    curves_init();
+    *base = g_curves[id].base;
+    *nseg = g_curves[id].nseg;
+    *mbits = g_curves[id].mbits;
+    if (coef)
+        memcpy(coef, g_curves[id].coef, (size_t) (g_curves[id].nseg + 1) * 4 * sizeof(float));
+    return 1;
+}
+
+static inline int curve(int id, float x, float *y)
+{
+    return !orc_math_exact && orc_curve_eval(&g_curves[id], x, y);
+}
+
+// x^g for the tabulated exponents; exact pow outside the domain
+static inline float pow_cv(int id, float x, float g)
+{
+    float y;
+    return curve(id, x, &y) ? y : pm_powf(x, g);
+}
+
+__attribute__((constructor)) static void curves_ctor(void) { curves_init(); }
 
 // ------------------------------------------------------------------------------------------
 
@@ -128,6 +195,7 @@ void orc_linearize(float *rgba, size_t npix, int trc, float csp_min, float csp_m
     const float slog_inv_k2 = (float) (1.0 / glsl6(SLOG_K2));
     const float scrgb = (float) glsl6(80.0f / SDR_WHITE);
     const bool scale_out = csp_max != 1 || csp_min != 0;
+    curves_init();
 
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < npix; i++) {
@@ -141,19 +209,19 @@ void orc_linearize(float *rgba, size_t npix, int trc, float csp_min, float csp_m
         switch (trc) {
         case TRC_SRGB:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.04045f < c[k] ? pm_powf((c[k] + 0.055f) / 1.055f, 2.4f)
+                c[k] = 0.04045f < c[k] ? pow_cv(ORC_CV_POW_24, (c[k] + 0.055f) / 1.055f, 2.4f)
                                        : c[k] * (float) (1.0 / 12.92);
             post_scale = true;
             break;
         case TRC_BT_1886:
             for (int k = 0; k < 3; k++)
-                c[k] = bt_a * pm_powf(c[k] + bt_b, 2.4f);
+                c[k] = bt_a * pow_cv(ORC_CV_POW_24, c[k] + bt_b, 2.4f);
             break;
         case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 1.8f); post_scale = true; break;
         case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.0f); post_scale = true; break;
         case TRC_UNKNOWN:
-        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.2f); post_scale = true; break;
-        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.4f); post_scale = true; break;
+        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pow_cv(ORC_CV_POW_22, c[k], 2.2f); post_scale = true; break;
+        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pow_cv(ORC_CV_POW_24, c[k], 2.4f); post_scale = true; break;
         case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.6f); post_scale = true; break;
         case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], 2.8f); post_scale = true; break;
         case TRC_PRO_PHOTO:
@@ -168,7 +236,12 @@ void orc_linearize(float *rgba, size_t npix, int trc, float csp_min, float csp_m
             break;
         case TRC_PQ:
             for (int k = 0; k < 3; k++) {
-                float x = pm_powf(c[k], q.inv_m2);
+                float x;
+                if (curve(ORC_CV_PQ_EOTF_SDR, c[k], &x)) {
+                    c[k] = x;
+                    continue;
+                }
+                x = pm_powf(c[k], q.inv_m2);
                 x = fmaxf(x - q.c1, 0.0f) / (q.c2 - q.c3 * x);
                 x = pm_powf(x, q.inv_m1);
                 c[k] = x * q.from_pq;
@@ -241,6 +314,7 @@ void orc_delinearize(float *rgba, size_t npix, int trc, float csp_min, float csp
     const float pq_pre = (float) (1.0 / glsl6(10000 / SDR_WHITE));
     const bool pre_scale = black_scaled && trc != TRC_HLG && (csp_max != 1 || csp_min != 0);
     const float ps_a = 1 / (csp_max - csp_min), ps_b = -csp_min / (csp_max - csp_min);
+    curves_init();
 
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < npix; i++) {
@@ -257,18 +331,18 @@ void orc_delinearize(float *rgba, size_t npix, int trc, float csp_min, float csp
         switch (trc) {
         case TRC_SRGB:
             for (int k = 0; k < 3; k++)
-                c[k] = 0.0031308f <= c[k] ? 1.055f * pm_powf(c[k], (float) (1.0 / 2.4)) - 0.055f
+                c[k] = 0.0031308f <= c[k] ? 1.055f * pow_cv(ORC_CV_POW_INV24, c[k], (float) (1.0 / 2.4)) - 0.055f
                                           : c[k] * 12.92f;
             break;
         case TRC_BT_1886:
             for (int k = 0; k < 3; k++)
-                c[k] = pm_powf(bt_inv_a * c[k], (float) (1.0 / 2.4)) - bt_b;
+                c[k] = pow_cv(ORC_CV_POW_INV24, bt_inv_a * c[k], (float) (1.0 / 2.4)) - bt_b;
             break;
         case TRC_GAMMA18: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 1.8)); break;
         case TRC_GAMMA20: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.0)); break;
         case TRC_UNKNOWN:
-        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.2)); break;
-        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.4)); break;
+        case TRC_GAMMA22: for (int k = 0; k < 3; k++) c[k] = pow_cv(ORC_CV_POW_INV22, c[k], (float) (1.0 / 2.2)); break;
+        case TRC_GAMMA24: for (int k = 0; k < 3; k++) c[k] = pow_cv(ORC_CV_POW_INV24, c[k], (float) (1.0 / 2.4)); break;
         case TRC_GAMMA26: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.6)); break;
         case TRC_GAMMA28: for (int k = 0; k < 3; k++) c[k] = pm_powf(c[k], (float) (1.0 / 2.8)); break;
         case TRC_ST428:
@@ -281,7 +355,12 @@ void orc_delinearize(float *rgba, size_t npix, int trc, float csp_min, float csp
             break;
         case TRC_PQ:
             for (int k = 0; k < 3; k++) {
-                float x = c[k] * pq_pre;
+                float x;
+                if (curve(ORC_CV_PQ_OETF_DELIN, c[k], &x)) {
+                    c[k] = x;
+                    continue;
+                }
+                x = c[k] * pq_pre;
                 x = pm_powf(x, q.m1);
                 x = (q.c1 + q.c2 * x) / (1.0f + q.c3 * x);
                 c[k] = pm_powf(x, q.m2);
@@ -343,16 +422,66 @@ static void mat3_mul(const float m[9], float v[3])
 
 static inline float pq_eotf_lit(const struct pq_lit *q, float x)
 {
-    x = pm_powf(fmaxf(x, 0.0f), q->inv_m2);
+    float y;
+    x = fmaxf(x, 0.0f);
+    if (curve(ORC_CV_PQ_EOTF, x, &y))
+        return y;
+    x = pm_powf(x, q->inv_m2);
     x = fmaxf(x - q->c1, 0.0f) / (q->c2 - q->c3 * x);
     return pm_powf(x, q->inv_m1);
 }
 
 static inline float pq_oetf_lit(const struct pq_lit *q, float x, int clamp0)
 {
-    x = pm_powf(clamp0 ? fmaxf(x, 0.0f) : x, q->m1);
+    float y;
+    x = clamp0 ? fmaxf(x, 0.0f) : x;
+    if (curve(ORC_CV_PQ_OETF, x, &y))
+        return y;
+    x = pm_powf(x, q->m1);
     x = (q->c1 + q->c2 * x) / (1.0f + q->c3 * x);
     return pm_powf(x, q->m2);
+}
+
+// Test front-end: the function behind curve `id` with its exact fallback, like
+// pl_cuda_math_eval(fn = 16 + id) on the product side.
+ORC_API void orc_curve_apply(int id, const float *x, float *out, size_t n)
+{
+    const struct pq_lit q = pq_literal();
+    const float pq_pre = (float) (1.0 / glsl6(10000 / SDR_WHITE));
+    for (size_t i = 0; i < n; i++) {
+        float y, v = x[i];
+        if (curve(id, v, &y)) {
+            out[i] = y;
+            continue;
+        }
+        switch (id) {
+        case ORC_CV_PQ_EOTF_SDR:
+        case ORC_CV_PQ_EOTF:
+            y = pm_powf(v, q.inv_m2);
+            y = fmaxf(y - q.c1, 0.0f) / (q.c2 - q.c3 * y);
+            y = pm_powf(y, q.inv_m1);
+            out[i] = id == ORC_CV_PQ_EOTF_SDR ? y * q.from_pq : y;
+            break;
+        case ORC_CV_PQ_OETF_SDR:
+        case ORC_CV_PQ_OETF_DELIN:
+        case ORC_CV_PQ_OETF:
+            y = id == ORC_CV_PQ_OETF_SDR ? v * q.to_pq : id == ORC_CV_PQ_OETF_DELIN ? v * pq_pre : v;
+            y = pm_powf(y, q.m1);
+            y = (q.c1 + q.c2 * y) / (1.0f + q.c3 * y);
+            out[i] = pm_powf(y, q.m2);
+            break;
+        case ORC_CV_PQX_OETF:
+            y = pm_powf(v, PQ_M1);
+            y = (PQ_C1 + PQ_C2 * y) / (1.0f + PQ_C3 * y);
+            out[i] = pm_powf(y, PQ_M2);
+            break;
+        case ORC_CV_POW_24:    out[i] = pm_powf(v, 2.4f); break;
+        case ORC_CV_POW_INV24: out[i] = pm_powf(v, (float) (1.0 / 2.4)); break;
+        case ORC_CV_POW_22:    out[i] = pm_powf(v, 2.2f); break;
+        case ORC_CV_POW_INV22: out[i] = pm_powf(v, (float) (1.0 / 2.2)); break;
+        default:               out[i] = NAN; break;
+        }
+    }
 }
 
 // pl_shader_extract_features (src/shaders/colorspace.c:1383-1404), after pl_shader_linearize:
@@ -549,9 +678,15 @@ void orc_detect_peak(const float *rgba, int w, int h, const struct orc_peak_para
                     luma = fmaf(p->luma_coeffs[1], px[1], luma);
                     luma = fmaf(p->luma_coeffs[2], px[2], luma);
                     luma *= to_pq;
-                    luma = pm_powf(clampf(luma, 0.0f, 1.0f), PQ_M1);
-                    luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
-                    luma = pm_powf(luma, PQ_M2);
+                    luma = clampf(luma, 0.0f, 1.0f);
+                    float pqv;
+                    if (curve(ORC_CV_PQX_OETF, luma, &pqv)) {
+                        luma = pqv;
+                    } else {
+                        luma = pm_powf(luma, PQ_M1);
+                        luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
+                        luma = pm_powf(luma, PQ_M2);
+                    }
                     if (cutoff)
                         luma *= smoothstepf(0.0f, cutoff, luma);
                     unsigned y_pq = (unsigned) ((float) PQ_MAXV * luma);
@@ -795,6 +930,7 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
     const float g_a = 1.0f / g_range, g_b = -p->gamut_min_luma / g_range;
     const float inv_2pi = (float) glsl6(0.5f / M_PI);
     const float chroma_bias = (float) (32768.0 / 65535.0);
+    curves_init();
 
     #pragma omp parallel for schedule(static)
     for (size_t n = 0; n < npix; n++) {
@@ -802,8 +938,10 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
         float lms[3], lmspq[3], ipt[3];
         matv(p->rgb2lms, px, lms);
         for (int k = 0; k < 3; k++) {
-            float x = q.to_pq * lms[k];
-            x = pm_powf(fmaxf(x, 0.0f), q.m1);
+            float x = fmaxf(lms[k], 0.0f);
+            if (curve(ORC_CV_PQ_OETF_SDR, x, &lmspq[k]))
+                continue;
+            x = pm_powf(x * q.to_pq, q.m1);
             x = (q.c1 + q.c2 * x) / (1.0f + q.c3 * x);
             lmspq[k] = pm_powf(x, q.m2);
         }
@@ -866,7 +1004,7 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
             float idx[3];
             idx[0] = g_a * ipt[0] + g_b;
             idx[1] = 2.0f * sqrtf(fmaf(ipt[1], ipt[1], ipt[2] * ipt[2]));
-            idx[2] = inv_2pi * pm_atan2f(ipt[2], ipt[1]) + 0.5f;
+            idx[2] = inv_2pi * pf_atan2f(ipt[2], ipt[1]) + 0.5f;
             gamut_sample(p, idx, ipt);
             ipt[1] -= chroma_bias;
             ipt[2] -= chroma_bias;
@@ -874,7 +1012,10 @@ void orc_color_map(float *rgba, size_t npix, const struct orc_color_map_params *
 
         matv(IPT2LMS, ipt, lmspq);
         for (int k = 0; k < 3; k++) {
-            float x = pm_powf(fmaxf(lmspq[k], 0.0f), q.inv_m2);
+            float x = fmaxf(lmspq[k], 0.0f);
+            if (curve(ORC_CV_PQ_EOTF_SDR, x, &lms[k]))
+                continue;
+            x = pm_powf(x, q.inv_m2);
             x = fmaxf(x - q.c1, 0.0f) / (q.c2 - q.c3 * x);
             x = pm_powf(x, q.inv_m1);
             lms[k] = x * q.from_pq;

@@ -219,4 +219,65 @@ static inline float pm_atan2f(float y, float x)
     return (float) (signbit(y) ? -t : t);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Round 2: fp32 definitions used by the per-pixel hot path (deband's sin/cos, the hue angle of
+// the gamut-mapping LUT). Only IEEE + - * / fma in a fixed order: same bits on any machine; the
+// kernels restate them in csrc/plb_math.cuh (plm_atan2_fast, plm_sincos_fast). Accuracy against
+// the real functions: atan2 <= 2e-7 absolute, sin/cos <= 1.2e-7 (tests/test_curves.py).
+// orc_math_exact != 0 (orc_set_exact_math) selects the binary64 definitions above instead.
+// ---------------------------------------------------------------------------------------------
+extern int orc_math_exact;
+
+// ratio folded to |z| <= tan(pi/8); atan z = z + z^3 P(z^2), P of degree 4 (minimax fit)
+static inline float pf_atan2f(float y, float x)
+{
+    const float a = fabsf(y), b = fabsf(x);
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    if (orc_math_exact || !(hi > 0.0f && hi < INFINITY) || a != a || b != b)
+        return pm_atan2f(y, x); // zeros, infinities, NaN
+    const int fold = lo > 0.41421357f * hi;
+    const float num = fold ? lo - hi : lo, den = fold ? lo + hi : hi;
+    const float z = num / den, w = z * z;
+    float p = -0.060332417f;
+    p = fmaf(p, w, 0.10572814f);
+    p = fmaf(p, w, -0.14239983f);
+    p = fmaf(p, w, 0.19998211f);
+    p = fmaf(p, w, -0.33333308f);
+    float t = fmaf(z * w, p, z);
+    if (fold)
+        t += 0.78539819f;
+    if (a > b)
+        t = 1.5707964f - t;
+    if (signbit(x))
+        t = 3.1415927f - t;
+    return signbit(y) ? -t : t;
+}
+
+// |x| <= 64: k = nearest quadrant, r = x - k pi/2 with a two-term constant
+static inline void pf_sincosf(float x, float *sn, float *cs)
+{
+    if (orc_math_exact || !(fabsf(x) <= 64.0f)) {
+        pm_sincosf(x, sn, cs);
+        return;
+    }
+    const float k = floorf(fmaf(x, 0.63661975f, 0.5f));
+    float r = fmaf(-k, 1.5707964f, x);
+    r = fmaf(-k, -4.3711388e-8f, r);
+    const float z = r * r;
+    float ps = -0.00019503963f;
+    ps = fmaf(ps, z, 0.0083320364f);
+    ps = fmaf(ps, z, -0.16666651f);
+    const float sr = fmaf(r * z, ps, r);
+    float pc = 2.437988e-05f;
+    pc = fmaf(pc, z, -0.0013886619f);
+    pc = fmaf(pc, z, 0.041666616f);
+    pc = fmaf(pc, z, -0.5f);
+    const float cr = fmaf(z, pc, 1.0f);
+    const int q = (int) k & 3;
+    const float s = (q & 1) ? cr : sr, c = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s : s;
+    *cs = ((q + 1) & 2) ? -c : c;
+}
+
 #endif
