@@ -361,32 +361,25 @@ PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], flo
         b[a] = (int) fminf(fmaxf(fl, -2.0f), (float) n[a]);
         f[a] = t - fl;
     }
-    float c[2][2][2][3];
-    #pragma unroll
-    for (int dz = 0; dz < 2; dz++) {
-        #pragma unroll
-        for (int dy = 0; dy < 2; dy++) {
-            #pragma unroll
-            for (int dx = 0; dx < 2; dx++) {
-                int i = plb_clampi(b[0] + dx, 0, n[0] - 1);
-                int cc = plb_clampi(b[1] + dy, 0, n[1] - 1);
-                int h = plb_clampi(b[2] + dz, 0, n[2] - 1);
-                const float4 t = __ldg((const float4 *) p.gamut_lut + ((h * n[1] + cc) * n[0] + i));
-                c[dz][dy][dx][0] = t.x;
-                c[dz][dy][dx][1] = t.y;
-                c[dz][dy][dx][2] = t.z;
-            }
-        }
-    }
-    #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float x00 = plb_mix(c[0][0][0][k], c[0][0][1][k], f[0]);
-        float x01 = plb_mix(c[0][1][0][k], c[0][1][1][k], f[0]);
-        float x10 = plb_mix(c[1][0][0][k], c[1][0][1][k], f[0]);
-        float x11 = plb_mix(c[1][1][0][k], c[1][1][1][k], f[0]);
-        float y0 = plb_mix(x00, x01, f[1]), y1 = plb_mix(x10, x11, f[1]);
-        out[k] = plb_mix(y0, y1, f[2]);
-    }
+    // the two texels along I are adjacent in memory; each (C, h) row pair is mixed along I as
+    // soon as it arrives (same mix order as the GLSL trilinear filter: I, then C, then h)
+    const int i0 = plb_clampi(b[0], 0, n[0] - 1), i1 = plb_clampi(b[0] + 1, 0, n[0] - 1);
+    const int c0 = plb_clampi(b[1], 0, n[1] - 1), c1 = plb_clampi(b[1] + 1, 0, n[1] - 1);
+    const int h0 = plb_clampi(b[2], 0, n[2] - 1), h1 = plb_clampi(b[2] + 1, 0, n[2] - 1);
+    const float4 *lut = (const float4 *) p.gamut_lut;
+    const int r00 = (h0 * n[1] + c0) * n[0], r01 = (h0 * n[1] + c1) * n[0];
+    const int r10 = (h1 * n[1] + c0) * n[0], r11 = (h1 * n[1] + c1) * n[0];
+    const float4 t000 = __ldg(lut + r00 + i0), t001 = __ldg(lut + r00 + i1);
+    const float4 t010 = __ldg(lut + r01 + i0), t011 = __ldg(lut + r01 + i1);
+    const float4 t100 = __ldg(lut + r10 + i0), t101 = __ldg(lut + r10 + i1);
+    const float4 t110 = __ldg(lut + r11 + i0), t111 = __ldg(lut + r11 + i1);
+#define PLB_TRI(F, k) { \
+        const float x00 = plb_mix(t000.F, t001.F, f[0]), x01 = plb_mix(t010.F, t011.F, f[0]); \
+        const float x10 = plb_mix(t100.F, t101.F, f[0]), x11 = plb_mix(t110.F, t111.F, f[0]); \
+        const float y0 = plb_mix(x00, x01, f[1]), y1 = plb_mix(x10, x11, f[1]); \
+        out[k] = plb_mix(y0, y1, f[2]); }
+    PLB_TRI(x, 0) PLB_TRI(y, 1) PLB_TRI(z, 2)
+#undef PLB_TRI
 }
 
 PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])

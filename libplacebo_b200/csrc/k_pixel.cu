@@ -132,6 +132,10 @@ k_pixel_light(const __grid_constant__ plb_tail_args ap)
         #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int gy = min(gy0 + 8 * r, a.out_h - 1);
+            if (a.plane_cc[i].ident) { // sample positions are the texel centres
+                c4[r] = plb_load_clamped(pl.tex, gx, gy);
+                continue;
+            }
             float posx, posy;
             plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
             c4[r] = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
@@ -176,50 +180,139 @@ static bool pixel_is_light(const struct plb_pixel_launch *p)
     return true;
 }
 
-// The HDR -> SDR output pass (linearize, tone / gamut mapping, delinearize, dither + light steps
-// on directly sampled planes): plb_run_hdr_ops with both transfer functions fixed at compile
-// time, everything but the transcendental functions inline, colour in registers.
-template <int LIN_TRC, int DELIN_TRC, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_pixel_hdr(const __grid_constant__ plb_tail_args ap)
+// The HDR -> SDR output pass (pass_convert_colors + pass_output_target, renderer.c:2157-2279,
+// 2586-2964): the rgba16hf image FBO 1:1 -> [light steps] -> linearize (PQ) -> tone / gamut mapping
+// -> delinearize (BT.1886) -> [light steps] -> [dither] -> [light steps] -> target.
+// Straight-line code: no op loop around the four heavy steps, the launch description is read from
+// the kernel parameters (constant bank operands, no shared-memory staging), transfer functions are
+// curve evaluations (plb_math.cuh). Per-pixel arithmetic is that of plb_run_color_ops, step for
+// step, so the general kernel (PLB_PIXEL_HDR=0) produces the same bytes.
+#define HDR_MAX_LIGHT 6
+struct plb_hdr_args {
+    plb_tex_desc src, dst;
+    int dst_x0, dst_y0, out_w, out_h;
+    float src_scale;
+    int n_pre, n_mid, n_post;          // light steps before linearize / before dither / at the end
+    int has_dither;
+    plb_trc_consts lin, delin;
+    plb_op_color_map cmap;
+    plb_op_dither dither;
+    plb_color_op light[HDR_MAX_LIGHT];
+};
+
+PLB_DEV float4 hdr_unpack(uint2 raw)
 {
-    plm_tables_init();
-    plb_tail_stage(ap);
+    const float2 a = __half22float2(*(__half2 *) &raw.x), b = __half22float2(*(__half2 *) &raw.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
+{
+    plm_tables_init(); // operands of the exact (out-of-domain) paths
     __syncthreads();
-    const plb_tail_args &a = plb_s_tail;
     const int gx = blockIdx.x * PIX_TILE + threadIdx.x;
-    if (gx >= a.out_w)
+    const int gy0 = blockIdx.y * PIX_TILE + threadIdx.y;
+    if (gx >= a.out_w || gy0 >= a.out_h)
         return;
+    const char *src = (const char *) a.src.ptr + (size_t) gx * 8;
+    uint2 raw = *(const uint2 *) (src + (size_t) gy0 * a.src.pitch);
     #pragma unroll 1
     for (int r = 0; r < PIX_TILE / 8; r++) {
-        const int gy = blockIdx.y * PIX_TILE + threadIdx.y + 8 * r;
+        const int gy = gy0 + 8 * r;
         if (gy >= a.out_h)
             break;
-        float color[4] = { a.init[0], a.init[1], a.init[2], a.init[3] };
+        const float4 t = hdr_unpack(raw);
+        if (gy + 8 < a.out_h && r + 1 < PIX_TILE / 8) // next row's texel while this one computes
+            raw = *(const uint2 *) (src + (size_t) (gy + 8) * a.src.pitch);
+        float c[4] = { t.x * a.src_scale, t.y * a.src_scale, t.z * a.src_scale, t.w * a.src_scale };
+        int li = 0;
         #pragma unroll 1
-        for (int i = 0; i < a.nplanes; i++) {
-            const plb_plane_src &pl = a.planes[i];
-            float4 c4;
-            if (a.plane_cc[i].ident && !pl.linear && plb_tex_fast_kind(pl.tex) == 3) {
-                // the usual source: the rgba16hf image FBO, 1:1 (texel = pixel, always in range)
-                c4 = plb_load_rgba16hf(pl.tex, gx, gy);
-            } else {
-                float posx, posy;
-                plb_coord_pos(a.plane_cc[i], gx, gy, posx, posy);
-                c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy) : plb_tex_nearest(pl.tex, posx, posy);
-            }
-            const float tmp[4] = { c4.x * pl.scale, c4.y * pl.scale, c4.z * pl.scale, c4.w * pl.scale };
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int m = pl.map[k];
-                #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    color[j] = m == j ? tmp[k] : color[j];
-            }
-        }
-        plb_run_hdr_ops<LIN_TRC, DELIN_TRC>(gx, gy, color);
-        plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy, make_float4(color[0], color[1], color[2], color[3]));
+        for (int i = 0; i < a.n_pre; i++, li++)
+            plb_light_step(a.light[li], a.light[li].kind, c);
+        plb_linearize(TRC_PQ, a.lin, c);
+        plb_color_map(a.cmap, c);
+        plb_delinearize(TRC_BT_1886, a.delin, c);
+        #pragma unroll 1
+        for (int i = 0; i < a.n_mid; i++, li++)
+            plb_light_step(a.light[li], a.light[li].kind, c);
+        if (a.has_dither)
+            plb_dither(a.dither, gx, gy, c);
+        #pragma unroll 1
+        for (int i = 0; i < a.n_post; i++, li++)
+            plb_light_step(a.light[li], a.light[li].kind, c);
+        plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy, make_float4(c[0], c[1], c[2], c[3]));
     }
+}
+
+static bool op_is_light(int k)
+{
+    return k == PLB_OP_SCALE || k == PLB_OP_MATRIX || k == PLB_OP_ROUND_FBO || k == PLB_OP_ALPHA ||
+           k == PLB_OP_SWIZZLE;
+}
+
+// Eligibility of k_pixel_hdr and its argument block: one rgba16hf plane sampled 1:1 with the
+// identity component map; program = light* LINEARIZE(PQ) COLOR_MAP DELINEARIZE(BT.1886) light*
+// [DITHER] light*.
+static bool pixel_hdr_args(const struct plb_pixel_launch *p, const plb_tail_args *t, plb_hdr_args *h)
+{
+    if (!p->dst.ptr || p->nplanes != 1)
+        return false;
+    const plb_plane_src &pl = p->planes[0];
+    if (pl.kind != PLB_PLANE_DIRECT || !t->plane_cc[0].ident || pl.tex.ptr2 || pl.tex.addr ||
+        pl.tex.kind != PLB_FK_HALF || pl.tex.comps != 4)
+        return false;
+    for (int k = 0; k < 4; k++) {
+        if (pl.map[k] != k)
+            return false;
+    }
+    memset(h, 0, sizeof(*h));
+    const plb_color_prog &pr = p->prog;
+    int i = 0, nl = 0;
+    for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
+        if (nl == HDR_MAX_LIGHT)
+            return false;
+        h->light[nl++] = pr.ops[i];
+        h->n_pre++;
+    }
+    if (i + 3 > pr.n || pr.ops[i].kind != PLB_OP_LINEARIZE || pr.ops[i].u.trc.trc != TRC_PQ ||
+        pr.ops[i + 1].kind != PLB_OP_COLOR_MAP || pr.ops[i + 2].kind != PLB_OP_DELINEARIZE ||
+        pr.ops[i + 2].u.trc.trc != TRC_BT_1886)
+        return false;
+    h->lin = pr.ops[i].u.trc;
+    h->cmap = pr.ops[i + 1].u.cmap;
+    h->delin = pr.ops[i + 2].u.trc;
+    i += 3;
+    for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
+        if (nl == HDR_MAX_LIGHT)
+            return false;
+        h->light[nl++] = pr.ops[i];
+        h->n_mid++;
+    }
+    if (i < pr.n && pr.ops[i].kind == PLB_OP_DITHER) {
+        h->dither = pr.ops[i].u.dither;
+        h->has_dither = 1;
+        i++;
+    } else {
+        h->n_post = h->n_mid; // no dither: one run of light steps
+        h->n_mid = 0;
+    }
+    for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
+        if (nl == HDR_MAX_LIGHT)
+            return false;
+        h->light[nl++] = pr.ops[i];
+        h->n_post++;
+    }
+    if (i != pr.n)
+        return false;
+    h->src = pl.tex;
+    h->dst = p->dst;
+    h->dst_x0 = p->dst_rect.x0;
+    h->dst_y0 = p->dst_rect.y0;
+    h->out_w = p->out_w;
+    h->out_h = p->out_h;
+    h->src_scale = pl.scale;
+    return true;
 }
 
 // Plane passes without a heavy colour program: debanding and AV1 grain synthesis into an FBO
@@ -278,44 +371,9 @@ static bool pixel_is_planes(const struct plb_pixel_launch *p)
     return true; // all-direct launches were taken by k_pixel_light before
 }
 
-// Eligibility of k_pixel_hdr: direct planes only, a tone / gamut mapping step, PQ in and BT.1886
-// out wherever the program (de)linearizes, nothing that needs the general interpreter.
-static bool pixel_is_hdr(const struct plb_pixel_launch *p)
-{
-    if (!p->dst.ptr)
-        return false;
-    for (int i = 0; i < p->nplanes; i++) {
-        if (p->planes[i].kind != PLB_PLANE_DIRECT)
-            return false;
-    }
-    bool cmap = false;
-    for (int i = 0; i < p->prog.n; i++) {
-        const struct plb_color_op *op = &p->prog.ops[i];
-        switch (op->kind) {
-        case PLB_OP_SCALE: case PLB_OP_MATRIX: case PLB_OP_ROUND_FBO: case PLB_OP_ALPHA:
-        case PLB_OP_SWIZZLE: case PLB_OP_DITHER:
-            break;
-        case PLB_OP_COLOR_MAP:
-            cmap = true;
-            break;
-        case PLB_OP_LINEARIZE:
-            if (op->u.trc.trc != TRC_PQ)
-                return false;
-            break;
-        case PLB_OP_DELINEARIZE:
-            if (op->u.trc.trc != TRC_BT_1886)
-                return false;
-            break;
-        default:
-            return false;
-        }
-    }
-    return cmap;
-}
-
 extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
 {
-    static plb_tail_args t;
+    plb_tail_args t; // on the stack: two pl_gpu may launch from two threads
     plb_fill_tail(&t, p);
     if (pixel_is_light(p)) {
         dim3 block(32, 8);
@@ -345,19 +403,13 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     static int hdr_mode = -1; // PLB_PIXEL_HDR=0 keeps the general kernel (measurements, A/B tests)
     if (hdr_mode < 0) {
         const char *e = getenv("PLB_PIXEL_HDR");
-        hdr_mode = e ? atoi(e) : 5;
+        hdr_mode = e ? atoi(e) : 1;
     }
-    if (hdr_mode > 0 && pixel_is_hdr(p)) {
+    plb_hdr_args h;
+    if (hdr_mode > 0 && pixel_hdr_args(p, &t, &h)) {
         dim3 block(32, 8);
         dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
-        // measured on B200 (4K colour pass, µs): 3 CTAs/SM 923, 4: 930, 5 (48 registers): 909;
-        // the general kernel: 1260
-        if (hdr_mode == 3)
-            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 3><<<grid, block, 0, STREAM(gpu)>>>(t);
-        else if (hdr_mode == 4)
-            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 4><<<grid, block, 0, STREAM(gpu)>>>(t);
-        else
-            k_pixel_hdr<TRC_PQ, TRC_BT_1886, 5><<<grid, block, 0, STREAM(gpu)>>>(t);
+        k_pixel_hdr<<<grid, block, 0, STREAM(gpu)>>>(h);
         plb_gpu_priv(gpu)->launches++;
         return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_hdr");
     }

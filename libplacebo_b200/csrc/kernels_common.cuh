@@ -324,7 +324,10 @@ PLB_DEV void plb_store4(const plb_tex_desc &t, int x, int y, const float4 c[4])
 
 struct plb_coord {
     int mode;
-    int ident;      // EXACT mode, the rect is the whole texture and maps 1:1 onto the output
+    // EXACT mode, the rect is the whole texture and maps 1:1 onto the output: sample positions
+    // are exactly the texel centres, where a bilinear fetch returns the texel itself (texture
+    // units quantise the weights to 1/256: 1, 0, 0, 0) — direct and bilinear sampling coincide
+    int ident;
     float px0, px1, py0, py1;
     float osx, osy;
     float sizex, sizey;
@@ -361,6 +364,12 @@ PLB_DEV void plb_coord_pos(const plb_coord &c, int gx, int gy, float &posx, floa
         float mx = plb_mix(c.px0, c.px1, fx);
         posx = plb_mix(mx, mx, fy);
         posy = plb_mix(plb_mix(c.py0, c.py0, fx), plb_mix(c.py1, c.py1, fx), fy);
+    } else if (c.ident) {
+        // (gx + 0.5) / w: the fp32 quotient of two exactly representable operands is the float
+        // nearest to the binary64 quotient below (a ratio of integers < 2^24 never comes within
+        // 2^-53 of a float midpoint), and costs a quarter of the binary64 division
+        posx = __fdiv_rn((float) gx + 0.5f, c.sizex);
+        posy = __fdiv_rn((float) gy + 0.5f, c.sizey);
     } else {
         posx = (float) ((c.dx0 + c.dxs * (gx + 0.5)) / c.sizex);
         posy = (float) ((c.dy0 + c.dys * (gy + 0.5)) / c.sizey);

@@ -356,7 +356,7 @@ PLB_DEV void plb_sample_plane_simple_t(const plb_plane_src &pl, const plb_coord 
 {
     float posx, posy;
     plb_coord_pos(cc, gx, gy, posx, posy);
-    const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear) ? plb_tex_linear(pl.tex, posx, posy)
+    const float4 c4 = (pl.kind == PLB_PLANE_DIRECT && pl.linear && !cc.ident) ? plb_tex_linear(pl.tex, posx, posy)
                                                                  : plb_tex_nearest_t<FAST>(pl.tex, posx, posy);
     out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
     if (pl.kind == PLB_PLANE_DEBAND)
@@ -386,7 +386,7 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
     float4 c4;
     if (pl.kind >= PLB_PLANE_BICUBIC)
         c4 = plb_sample_fast(pl, cc, posx, posy);
-    else if (pl.kind == PLB_PLANE_DIRECT && pl.linear)
+    else if (pl.kind == PLB_PLANE_DIRECT && pl.linear && !cc.ident)
         c4 = plb_tex_linear(pl.tex, posx, posy);
     else
         c4 = plb_tex_nearest(pl.tex, posx, posy);

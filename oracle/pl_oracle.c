@@ -372,6 +372,11 @@ void orc_sample_direct(const struct orc_tex *src, struct orc_rect rect, int dw, 
 {
     const struct coord_ctx cc = coord_init(coord_mode, src, rect, dw, dh);
     const int ew = EXT_W(dw), eh = EXT_H(dh);
+    // 1:1 mapping of the whole texture: the sample positions are the texel centres, where a
+    // texture unit's bilinear filter (weights quantised to 1/256) returns the texel itself
+    if (coord_mode != ORC_COORD_LITERAL && rect.x0 == 0 && rect.y0 == 0 && rect.x1 == src->w &&
+        rect.y1 == src->h && dw == src->w && dh == src->h)
+        linear = 0;
     #pragma omp parallel for schedule(static)
     for (int gy = 0; gy < eh; gy++) {
         for (int gx = 0; gx < ew; gx++) {
