@@ -15,12 +15,18 @@ peak detection + tone/gamut mapping + blue-noise dither), the configuration the 
             planes, render, download of the RGBA result, all inside the timed region.
   roofline  dominant kernel: algorithmic bytes per launch / mean launch duration (cudaEvent
             intervals delivered by the library's info_callback during the timed region).
+  extra_workloads  the same measurement (shorter) for configs[1] (C2, the north-star roofline
+            configuration: 1080p -> 4K EWA-Lanczos fp16) and configs[3] (C4: C3 + AV1 grain),
+            each with its own `roofline` — on N ranks when launched under torchrun.
+  parity    one frame of the timed configuration rendered from a fresh renderer and compared
+            with the CPU oracle (max difference in LSB of the target); rank 0, N = 1.
   cpu_baseline / --impl reference: the CPU restatement of the same pass graph
             (tests/pipeline_oracle.py over oracle/libpl_oracle.so, parameters from the compiled
-            reference when oracle/_ref is present) on a bounded sample.
+            reference when oracle/_ref is present) on whole frames of the workload, OpenMP
+            threads pinned to the physical cores; value = 1 / median frame time.
 
 Multi-GPU (torchrun, one rank per GPU): frames of a stream are independent -> each rank renders
-its own frames (weak scaling); the only exchange is the 3264-byte peak statistics all-gather
+its own frames (weak scaling); the only exchange is the peak statistics all-gather
 (libplacebo_b200/parallel.py), which is part of every timed step when N > 1.
 """
 import argparse
@@ -35,6 +41,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L2_BYTES = 126e6
+METRIC = "4K HDR10->SDR EWA-Lanczos frames/sec"
+EXTRA = ["c2_1080p_to_4k_ewa_fp16", "c4_4k_hdr10_to_sdr_av1_grain"]
 
 
 def parse():
@@ -44,75 +52,117 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_4k_hdr10_to_sdr")
-    ap.add_argument("--cpu-sample", default="960x540", help="frame size of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads and parity")
     return ap.parse_args()
+
+
+def physical_cores():
+    """Physical cores this process may run on (OpenMP threads of the CPU arm are pinned to them)."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        seen = set()
+        for cpu in allowed:
+            base = f"/sys/devices/system/cpu/cpu{cpu}/topology"
+            with open(base + "/physical_package_id") as f:
+                pkg = f.read().strip()
+            with open(base + "/core_id") as f:
+                core = f.read().strip()
+            seen.add((pkg, core))
+        return max(1, len(seen))
+    except Exception:  # noqa: BLE001
+        return max(1, (os.cpu_count() or 2) // 2)
+
+
+def pin_openmp():
+    """The CPU arm uses every physical core, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1). Must run before the oracle library (libgomp) is loaded."""
+    n = physical_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["OMP_PROC_BIND"] = "spread"
+    os.environ["OMP_PLACES"] = "cores"
+    os.environ["OMP_DYNAMIC"] = "false"
+    return n
+
+
+def workload_config(wl_name, world):
+    """The `config` object: identical in both arms."""
+    from libplacebo_b200 import stream as S
+    wl = S.WORKLOADS[wl_name]
+    return {"workload": wl_name, "desc": wl["desc"], "src": list(wl["src"]), "dst": list(wl["dst"]),
+            "dst_fmt": wl["dst_fmt"], "frames_per_gpu_per_step": 1,
+            "parallelism": f"frame-parallel x{world}"}
 
 
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the pass graph (test infrastructure used as a baseline)
 # --------------------------------------------------------------------------------------------
-def cpu_pipeline_fps(wl_name, sample, repeats=1):
-    """Times the CPU restatement on one `sample`-sized frame and scales by the pixel ratio to
-    workload frames/s. Returns (fps, cores, description)."""
+def oracle_render_args(wl_name, seed=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import pipeline_oracle as P
-    import plbtest as T
     from libplacebo_b200 import stream as S
 
     wl = S.WORKLOADS[wl_name]
-    sw, sh = (int(v) for v in sample.split("x"))
-    scale = wl["dst"][0] / wl["src"][0]
-    planes = S.synth_yuv420p10(sw, sh, seed=0)
+    sw, sh = wl["src"]
+    planes = S.synth_yuv420p10(sw, sh, seed=seed)
     img = P.Frame(planes, S.SYS[wl["src_sys"]], csp=np.array(wl["src_csp"], np.float32))
     depth = wl["dst_depth"]
-    tgt = P.Target(int(sw * scale), int(sh * scale), wl["dst_fmt"], sample_depth=depth,
+    tgt = P.Target(wl["dst"][0], wl["dst"][1], wl["dst_fmt"], sample_depth=depth,
                    color_depth=depth, csp=np.array(wl["dst_csp"], np.float32))
     o = wl["opts"]
     kw = dict(upscaler=wl["upscaler"], deband=bool(o.get("deband")), peak=o.get("peak", 0),
               dither=o.get("dither", 0), cmap_hq=bool(o.get("cmap_hq")))
-    if o.get("grain"):
-        kw["film_grain"] = (1, 1 if o["grain"] > 1 else 0)
-    P.render(img, tgt, **kw)  # warm caches (filter / gamut LUT generation)
-    t0 = time.perf_counter()
-    for i in range(repeats):
-        P.render(img, tgt, frame_index=i, **kw)
-    dt = (time.perf_counter() - t0) / repeats
-    frac = (sw * sh) / (wl["src"][0] * wl["src"][1])
-    fps = frac / dt
-    cores = T.oracle().num_threads()
-    desc = (f"{repeats} frame(s) of {sw}x{sh} ({frac:.4f} of the workload's pixels), "
-            f"{dt:.2f} s each, scaled by pixel count")
-    return fps, cores, desc, dt
+    return P, img, tgt, kw, bool(o.get("grain"))
 
 
-def run_reference(args, rank):
+def cpu_frames(wl_name, n, warm=1):
+    """Times n whole frames of the workload on the CPU restatement. Returns the list of frame
+    times (s), the thread count and a description."""
+    P, img, tgt, kw, grain = oracle_render_args(wl_name)
+    import plbtest  # tests/ is on sys.path after oracle_render_args
+    times = []
+    for i in range(warm + n):
+        k = dict(kw, frame_index=i)
+        if grain:
+            k["film_grain"] = (i + 1, 1)
+        t0 = time.perf_counter()
+        P.render(img, tgt, **k)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times, plbtest.oracle().num_threads()
+
+
+def cpu_arm_line(wl_name, times, cores):
+    s = sorted(times)
+    med = s[len(s) // 2]
+    return {"value": round(1.0 / med, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "frame_s_median": round(med, 4), "frame_s_min": round(s[0], 4), "frame_s_max": round(s[-1], 4),
+            "sample": f"{len(s)} whole frame(s) of {wl_name} (no scaling), median frame time; OpenMP over "
+                      f"rows, {cores} threads pinned to physical cores (OMP_PROC_BIND=spread, "
+                      "OMP_PLACES=cores); libplacebo has no CPU pixel path (its shaders are GLSL), "
+                      "so this is the oracle's C/OpenMP restatement of the same pass graph with "
+                      "parameters from the compiled reference library"}
+
+
+def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    # bounded: each step is one sample frame; cap the whole run at a few minutes
-    fps, cores, desc, dt = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=1)
-    per_step = max(1, int(round(2.0 / max(dt, 1e-3))))   # sample frames per step: about 2 s of CPU work
-    budget = 150.0
-    n = max(1, min(steps, int(budget / max(per_step * dt, 1e-3))))
-    for _ in range(min(args.warmup, 2)):
-        cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=per_step)
-    fps, cores, desc, dt = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=n * per_step)
-    desc = f"{n} step(s) of {per_step} sample frame(s): " + desc
-    from libplacebo_b200 import stream as S
-    wl = S.WORKLOADS[args.workload]
+    # bounded: the whole run ends within a few minutes whatever K is
+    t1, cores = cpu_frames(args.workload, 1, warm=1)
+    n = max(5, min(steps, int(150.0 / max(t1[0], 1e-3))))
+    times, cores = cpu_frames(args.workload, n, warm=min(max(args.warmup, 0), 2))
+    cb = cpu_arm_line(args.workload, times, cores)
     line = {
-        "impl": "reference", "metric": "4K HDR10->SDR EWA-Lanczos frames/sec", "value": fps,
+        "impl": "reference", "metric": METRIC, "value": cb["value"],
         "unit": "frames/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
-        "ms_per_step": per_step * dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"]},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": desc + "; libplacebo has no CPU pixel path (its shaders are "
-                         "GLSL), so this is the oracle's C/OpenMP restatement of the same pass "
-                         "graph with parameters from the compiled reference library"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_step": round(cb["frame_s_median"] * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
@@ -196,22 +246,18 @@ def pass_bytes(desc, wl):
     return (sw * sh * 2 + 2 * cw * ch * 2) + dw * dh * out_bpp, "other"
 
 
-def run_ours(args, rank, world, local_rank):
-    import numpy as np
+class Ctx:
+    pass
+
+
+def measure(cx, wl_name, steps, warmup, with_e2e=True):
+    """One workload on this rank's GPU (all ranks take part). Returns a dict on every rank."""
     import torch
 
     from libplacebo_b200 import stream as S
+    torch, dist, rank, world, local_rank = cx.torch, cx.dist, cx.rank, cx.world, cx.local_rank
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libplacebo_b200 has no CPU fallback "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    wl = S.WORKLOADS[args.workload]
+    wl = S.WORKLOADS[wl_name]
     sw, sh = wl["src"]
     dw, dh = wl["dst"]
     out_bpp = {"rgba8": 4, "rgba16": 8, "rgba16hf": 8}[wl["dst_fmt"]]
@@ -219,7 +265,6 @@ def run_ours(args, rank, world, local_rank):
     out_bytes = dw * dh * out_bpp
     ring = max(2, int(L2_BYTES * 2 / (in_bytes + out_bytes)) + 1)
     ring = min(ring, 16)
-    steps, warmup = args.steps, max(args.warmup, 3)
     # (exactly `steps` frames are timed; the per-pass timers keep the first 256 runs of each pass,
     # so with more steps the pass table averages over the first 256 - warmup of them)
 
@@ -294,27 +339,35 @@ def run_ours(args, rank, world, local_rank):
         st.finish()
     passes = st.passes()
 
-    for i in range(3):
-        frame(i, True)
-    st.finish()
-    e2e_steps = max(5, steps // 2)
-    ms_e2e, _ = timed(e2e_steps, True, False)
+    res = {"wl": wl, "ring": ring, "in_bytes": in_bytes, "out_bytes": out_bytes, "ms": ms,
+           "launches": launches, "passes": passes, "clocks": clk.summary(), "steps": steps}
+    if with_e2e:
+        for i in range(3):
+            frame(i, True)
+        st.finish()
+        e2e_steps = max(5, steps // 2)
+        ms_e2e, _ = timed(e2e_steps, True, False)
+        res["ms_e2e"], res["e2e_steps"] = ms_e2e, e2e_steps
 
-    if rank != 0:
-        return
-    fps = world * steps / (ms / 1e3)
-    fps_e2e = world * e2e_steps / (ms_e2e / 1e3)
+    # parity of one frame of this configuration (fresh renderer: no peak history), rank 0 only
+    res["parity_frame"] = None
+    if cx.want_parity and rank == 0 and world == 1:
+        st.finish()
+        st.reset()
+        st.render(0, 0, frame_index=0)
+        out = st.out_array()
+        st.download(0, out)
+        st.join()
+        st.finish()
+        res["parity_frame"] = out
+    st.close()
+    return res
 
-    # roofline of the dominant pass
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:  # noqa: BLE001
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6560.6))
+
+def roofline_of(res, wl_name, hbm_peak):
     plist = []
-    for cnt, ns, desc in passes:
-        b, label = pass_bytes(desc, wl)
+    for cnt, ns, desc in res["passes"]:
+        b, label = pass_bytes(desc, res["wl"])
         plist.append({"pass": label, "steps": desc, "launches": cnt, "mean_us": ns / 1e3,
                       "algorithmic_MB": b / 1e6,
                       "GBps": (b / (ns * 1e-9) / 1e9) if ns else None})
@@ -325,42 +378,129 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     try:
         tdb = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tdb.get(args.workload, {}).get(top["pass"] if top else "", {}).get("dram_bytes")
+        traffic = tdb.get(wl_name, {}).get(top["pass"] if top else "", {}).get("dram_bytes")
     except Exception:  # noqa: BLE001
         pass
     if top and top["GBps"]:
         roof = {"bound": "hbm", "achieved": round(top["GBps"], 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(top["GBps"] / hbm_peak, 4), "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of the same kernel, "
+                                  "committed; not measured in this run)",
                 "kernel": top["pass"], "mean_us": round(top["mean_us"], 2),
                 "algorithmic_bytes_per_launch": int(top["algorithmic_MB"] * 1e6),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)",
-                "note": "kernel is FP32/FP64-issue bound, not HBM bound; see DESIGN.md"}
+                "note": "instruction-issue bound (fp32 + integer), not HBM bound; see DESIGN.md"}
+    # whole frame by SURVEY.md 8(d): compulsory reads + writes of the frame / frame time
+    return roof, plist
 
+
+def parity_block(wl_name, frame):
+    import numpy as np
+    P, img, tgt, kw, grain = oracle_render_args(wl_name)
+    k = dict(kw, frame_index=0)
+    if grain:
+        k["film_grain"] = (1, 1)
+    want, _ = P.render(img, tgt, **k)
+    if frame.dtype == np.uint16 and tgt.fmt == "rgba16hf":
+        import plbtest as T
+        d = T.ulp_diff_half(frame.view(np.float16), want)
+        unit = "ULP of the fp16 target"
+    else:
+        d = np.abs(frame[..., :3].astype(np.int64) - want[..., :3].astype(np.int64))
+        unit = "LSB of the target"
+    return {"frame": f"{wl_name}, synthetic frame 0, fresh renderer", "max_diff": int(d.max()),
+            "differing_fraction": float(np.mean(d > 0)), "unit": unit,
+            "against": "CPU oracle (tests/pipeline_oracle.py over oracle/libpl_oracle.so)"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libplacebo_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cx = Ctx()
+    cx.torch, cx.dist, cx.rank, cx.world, cx.local_rank = torch, dist, rank, world, local_rank
+    cx.want_parity = not args.no_extra
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    res = measure(cx, args.workload, steps, warmup)
+    extras = {}
+    if not args.no_extra:
+        for name in EXTRA:
+            if name != args.workload:
+                extras[name] = measure(cx, name, min(steps, 100), warmup)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6560.6))
+
+    def summarise(name, r):
+        fps = world * r["steps"] / (r["ms"] / 1e3)
+        roof, plist = roofline_of(r, name, hbm_peak)
+        frame_bytes = r["in_bytes"] * (2 if r["wl"]["opts"].get("peak") else 1) + r["out_bytes"]
+        d = {"value": round(fps, 2), "unit": "frames/s", "steps": r["steps"],
+             "ms_per_step": round(r["ms"] / r["steps"], 4), "roofline": roof, "passes": plist,
+             "frame_roofline": {"algorithmic_bytes_per_frame": frame_bytes,
+                                "achieved_GBps": round(frame_bytes * fps / world / 1e9, 1),
+                                "frac": round(frame_bytes * fps / world / 1e9 / hbm_peak, 4),
+                                "note": "SURVEY.md 8(d): compulsory reads + writes of one frame / frame time"},
+             "gpu_launches": r["launches"], "clocks": r["clocks"],
+             "l2": f"ring of {r['ring']} resident input/output texture sets "
+                   f"({r['ring'] * (r['in_bytes'] + r['out_bytes']) / 1e6:.0f} MB > 126 MB L2)"}
+        if "ms_e2e" in r:
+            d["e2e"] = {"value": round(world * r["e2e_steps"] / (r["ms_e2e"] / 1e3), 2), "unit": "frames/s",
+                        "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
+                        "steps": r["e2e_steps"], "ms_per_step": round(r["ms_e2e"] / r["e2e_steps"], 4)}
+        if r.get("parity_frame") is not None:
+            try:
+                d["parity"] = parity_block(name, r["parity_frame"])
+            except Exception as e:  # noqa: BLE001
+                d["parity"] = {"error": str(e)}
+        return d
+
+    main = summarise(args.workload, res)
+    cfg = workload_config(args.workload, world)
+    cfg["l2"] = main.pop("l2")
     line = {
-        "metric": "4K HDR10->SDR EWA-Lanczos frames/sec", "value": round(fps, 2), "unit": "frames/s",
-        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4),
+        "metric": METRIC, "value": main["value"], "unit": "frames/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"], "src": [sw, sh], "dst": [dw, dh],
-                   "dst_fmt": wl["dst_fmt"], "frames_per_gpu_per_step": 1,
-                   "l2": f"ring of {ring} resident input/output texture sets "
-                         f"({ring * (in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
-                   "parallelism": f"frame-parallel x{world}"},
-        "roofline": roof,
-        "passes": plist,
-        "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
-                "ms_per_step": round(ms_e2e / e2e_steps, 4)},
-        "gpu_launches": launches,
-        "clocks": clk.summary(),
+        "config": cfg,
+        "roofline": main["roofline"], "frame_roofline": main["frame_roofline"],
+        "passes": main["passes"],
+        "e2e": main.get("e2e"),
+        "gpu_launches": main["gpu_launches"],
+        "clocks": main["clocks"],
     }
+    if "parity" in main:
+        line["parity"] = main["parity"]
+    if extras:
+        line["extra_workloads"] = {}
+        for name, r in extras.items():
+            d = summarise(name, r)
+            d["config"] = dict(workload_config(name, world), l2=d.pop("l2"))
+            line["extra_workloads"][name] = d
     if world == 1 and not args.no_cpu_baseline:
         try:
-            _, _, _, dt1 = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=1)
-            reps = max(1, min(400, int(round(12.0 / max(dt1, 1e-3)))))   # about 12 s of CPU work
-            cfps, cores, desc, _ = cpu_pipeline_fps(args.workload, args.cpu_sample, repeats=reps)
-            line["cpu_baseline"] = {"value": round(cfps, 4), "unit": "frames/s", "cores": cores,
-                                    "kind": "port", "sample": desc}
+            t1, cores = cpu_frames(args.workload, 1, warm=1)
+            n = max(5, min(15, int(20.0 / max(t1[0], 1e-3))))  # about 20 s of CPU work, >= 5 frames
+            times, cores = cpu_frames(args.workload, n, warm=0)
+            line["cpu_baseline"] = cpu_arm_line(args.workload, times, cores)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
                                     "sample": f"failed: {e}"}
@@ -391,8 +531,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if rank == 0:
+        pin_openmp()  # before libgomp is loaded (oracle library)
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     if world == 1 and args.gpus > 1:
         emit({"error": f"--gpus {args.gpus} needs torchrun (one rank per GPU)"})

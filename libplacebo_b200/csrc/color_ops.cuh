@@ -61,31 +61,78 @@ static __device__ __noinline__ float plb_pq_oetf_slow(float x)
     return plm_powf(x, c_pq.m2);
 }
 
+// The exact chain behind curve CV (what an argument outside the tabulated domain evaluates to)
+template <int CV>
+static __device__ __noinline__ float plb_curve_exact(float x)
+{
+    if (CV == PLB_CV_PQ_EOTF_SDR)
+        return plb_pq_eotf_slow(x) * c_pq.from_pq;
+    if (CV == PLB_CV_PQ_EOTF)
+        return plb_pq_eotf_slow(x);
+    if (CV == PLB_CV_PQ_OETF_SDR)
+        return plb_pq_oetf_slow(x * c_pq.to_pq);
+    if (CV == PLB_CV_PQ_OETF_DELIN)
+        return plb_pq_oetf_slow(x * c_pq.inv_from_pq);
+    if (CV == PLB_CV_PQ_OETF)
+        return plb_pq_oetf_slow(x);
+    if (CV == PLB_CV_PQX_OETF) { // exact float constants (colorspace.c:1279-1288)
+        const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
+                    PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
+        x = plm_powf(x, PQ_M1);
+        x = (PQ_C1 + PQ_C2 * x) / (1.0f + PQ_C3 * x);
+        return plm_powf(x, PQ_M2);
+    }
+    const float g = CV == PLB_CV_POW_24 ? 2.4f : CV == PLB_CV_POW_INV24 ? (float) (1.0 / 2.4)
+                  : CV == PLB_CV_POW_22 ? 2.2f : (float) (1.0 / 2.2);
+    return plm_powf(x, g);
+}
+
+// General kernels: descriptor-driven curve (honours exact-math mode), exact chain on a miss
+template <int CV>
+PLB_DEV float plb_curve(float x)
+{
+    float y;
+    return plm_curve<CV>(x, y) ? y : plb_curve_exact<CV>(x);
+}
+
+// Hot-path kernels: three channels, immediates, ONE (cold) fix-up branch for the group
+template <int CV>
+PLB_DEV void plb_curve3_s(float c[3])
+{
+    float y[3];
+    bool hit = true;
+    #pragma unroll
+    for (int k = 0; k < 3; k++)
+        hit &= plm_curve_s<CV>(c[k], y[k]);
+    if (!hit) {
+        #pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            float t;
+            y[k] = plm_curve_s<CV>(c[k], t) ? t : plb_curve_exact<CV>(c[k]);
+        }
+    }
+    c[0] = y[0]; c[1] = y[1]; c[2] = y[2];
+}
+
+template <int CV>
+PLB_DEV float plb_curve1_s(float x)
+{
+    float y;
+    return plm_curve_s<CV>(x, y) ? y : plb_curve_exact<CV>(x);
+}
+
 // CV = PLB_CV_PQ_EOTF (plain) or PLB_CV_PQ_EOTF_SDR (result * from_pq, the "203 nits = 1" scale)
 template <int CV>
 PLB_DEV float plb_pq_eotf_cv(float x)
 {
-    float y;
-    if (plm_curve<CV>(x, y))
-        return y;
-    y = plb_pq_eotf_slow(x);
-    return CV == PLB_CV_PQ_EOTF_SDR ? y * c_pq.from_pq : y;
+    return plb_curve<CV>(x);
 }
 
 // CV = PLB_CV_PQ_OETF (plain), _SDR (argument * to_pq) or _DELIN (argument * 1/from_pq)
 template <int CV>
 PLB_DEV float plb_pq_oetf_cv(float x, bool clamp0)
 {
-    float y;
-    if (clamp0)
-        x = fmaxf(x, 0.0f);
-    if (plm_curve<CV>(x, y))
-        return y;
-    if (CV == PLB_CV_PQ_OETF_SDR)
-        x *= c_pq.to_pq;
-    if (CV == PLB_CV_PQ_OETF_DELIN)
-        x *= c_pq.inv_from_pq;
-    return plb_pq_oetf_slow(x);
+    return plb_curve<CV>(clamp0 ? fmaxf(x, 0.0f) : x);
 }
 
 PLB_DEV float plb_pq_eotf(float x, bool clamp0)
@@ -346,42 +393,45 @@ PLB_DEV void plb_encode_special(int sys, float c[3])
     }
 }
 
-// trilinear fetch from the gamut 3DLUT (rgba16 values pre-converted to float); addressing = lut.c:285-295 per axis
+// Trilinear fetch from the gamut 3DLUT (rgba16 values pre-converted to float). Addressing as
+// lut.c:285-295 (texel centres at (i + 0.5) / n, clamp to edge) in its reduced form: with the
+// index saturated to [0, 1] the texel-space coordinate is x (n - 1); lerp(a, b, t) = fma(t, b - a, a).
+// (The reference samples a hardware-filtered 3D texture: 8-bit interpolation weights.)
+PLB_DEV float plb_lerp(float a, float b, float t) { return __fmaf_rn(t, b - a, a); }
+
 PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], float out[3])
 {
     const int n[3] = { p.lut_I, p.lut_C, p.lut_h };
-    int b[3];
+    int i0[3], i1[3];
     float f[3];
     #pragma unroll
     for (int a = 0; a < 3; a++) {
-        float u = p.g_scale[a] * idx[a] + p.g_base[a]; // scale = (1 - 0.5/n) - 0.5/n, base = 0.5/n (host)
-        float t = u * (float) n[a] - 0.5f;
-        float fl = floorf(t);
-        // guard the int conversion against NaN/huge values
-        b[a] = (int) fminf(fmaxf(fl, -2.0f), (float) n[a]);
+        const float t = __saturatef(idx[a]) * p.g_nm1[a]; // NaN -> 0
+        const float fl = floorf(t);
+        i0[a] = (int) fl;
+        i1[a] = min(i0[a] + 1, n[a] - 1);
         f[a] = t - fl;
     }
     // the two texels along I are adjacent in memory; each (C, h) row pair is mixed along I as
-    // soon as it arrives (same mix order as the GLSL trilinear filter: I, then C, then h)
-    const int i0 = plb_clampi(b[0], 0, n[0] - 1), i1 = plb_clampi(b[0] + 1, 0, n[0] - 1);
-    const int c0 = plb_clampi(b[1], 0, n[1] - 1), c1 = plb_clampi(b[1] + 1, 0, n[1] - 1);
-    const int h0 = plb_clampi(b[2], 0, n[2] - 1), h1 = plb_clampi(b[2] + 1, 0, n[2] - 1);
+    // soon as it arrives (same order as the GLSL trilinear filter: I, then C, then h)
     const float4 *lut = (const float4 *) p.gamut_lut;
-    const int r00 = (h0 * n[1] + c0) * n[0], r01 = (h0 * n[1] + c1) * n[0];
-    const int r10 = (h1 * n[1] + c0) * n[0], r11 = (h1 * n[1] + c1) * n[0];
-    const float4 t000 = __ldg(lut + r00 + i0), t001 = __ldg(lut + r00 + i1);
-    const float4 t010 = __ldg(lut + r01 + i0), t011 = __ldg(lut + r01 + i1);
-    const float4 t100 = __ldg(lut + r10 + i0), t101 = __ldg(lut + r10 + i1);
-    const float4 t110 = __ldg(lut + r11 + i0), t111 = __ldg(lut + r11 + i1);
+    const int r00 = (i0[2] * n[1] + i0[1]) * n[0], r01 = (i0[2] * n[1] + i1[1]) * n[0];
+    const int r10 = (i1[2] * n[1] + i0[1]) * n[0], r11 = (i1[2] * n[1] + i1[1]) * n[0];
+    const float4 t000 = __ldg(lut + r00 + i0[0]), t001 = __ldg(lut + r00 + i1[0]);
+    const float4 t010 = __ldg(lut + r01 + i0[0]), t011 = __ldg(lut + r01 + i1[0]);
+    const float4 t100 = __ldg(lut + r10 + i0[0]), t101 = __ldg(lut + r10 + i1[0]);
+    const float4 t110 = __ldg(lut + r11 + i0[0]), t111 = __ldg(lut + r11 + i1[0]);
 #define PLB_TRI(F, k) { \
-        const float x00 = plb_mix(t000.F, t001.F, f[0]), x01 = plb_mix(t010.F, t011.F, f[0]); \
-        const float x10 = plb_mix(t100.F, t101.F, f[0]), x11 = plb_mix(t110.F, t111.F, f[0]); \
-        const float y0 = plb_mix(x00, x01, f[1]), y1 = plb_mix(x10, x11, f[1]); \
-        out[k] = plb_mix(y0, y1, f[2]); }
+        const float x00 = plb_lerp(t000.F, t001.F, f[0]), x01 = plb_lerp(t010.F, t011.F, f[0]); \
+        const float x10 = plb_lerp(t100.F, t101.F, f[0]), x11 = plb_lerp(t110.F, t111.F, f[0]); \
+        const float y0 = plb_lerp(x00, x01, f[1]), y1 = plb_lerp(x10, x11, f[1]); \
+        out[k] = plb_lerp(y0, y1, f[2]); }
     PLB_TRI(x, 0) PLB_TRI(y, 1) PLB_TRI(z, 2)
 #undef PLB_TRI
 }
 
+// HOT: static curve evaluation (specialised kernels); else descriptor-driven
+template <bool HOT = false>
 PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
 {
     const float lms2ipt[9] = { 0.4000f, 0.4000f, 0.2000f, 4.4550f, -4.8510f, 0.3960f,
@@ -393,7 +443,14 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
     float ipt[3];
     #pragma unroll
     for (int k = 0; k < 3; k++)
-        ipt[k] = plb_pq_oetf_cv<PLB_CV_PQ_OETF_SDR>(lms[k], true);
+        ipt[k] = fmaxf(lms[k], 0.0f);
+    if (HOT) {
+        plb_curve3_s<PLB_CV_PQ_OETF_SDR>(ipt);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            ipt[k] = plb_curve<PLB_CV_PQ_OETF_SDR>(ipt[k]);
+    }
     plb_matv(lms2ipt, ipt[0], ipt[1], ipt[2]);
     const float i_orig = ipt[0];
 
@@ -429,13 +486,29 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
     plb_matv(ipt2lms, ipt[0], ipt[1], ipt[2]);
     #pragma unroll
     for (int k = 0; k < 3; k++)
-        lms[k] = plb_pq_eotf_cv<PLB_CV_PQ_EOTF_SDR>(fmaxf(ipt[k], 0.0f));
+        lms[k] = fmaxf(ipt[k], 0.0f);
+    if (HOT) {
+        plb_curve3_s<PLB_CV_PQ_EOTF_SDR>(lms);
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            lms[k] = plb_curve<PLB_CV_PQ_EOTF_SDR>(lms[k]);
+    }
     plb_matv(p.lms2rgb, lms[0], lms[1], lms[2]);
     px[0] = lms[0]; px[1] = lms[1]; px[2] = lms[2];
 }
 
 PLB_DEV void plb_dither(const plb_op_dither &p, int x, int y, float c[4])
 {
+    if (p.fast_pow2) {
+        // LUT of power-of-two size, no temporal rotation, plain rounding: (x + 0.5) / size,
+        // fract and * size are exact in fp32, i.e. the LUT index is x mod size, y mod size
+        const float bias = __ldg(p.lut + (y & (p.lut_size - 1)) * p.lut_size + (x & (p.lut_size - 1)));
+        #pragma unroll
+        for (int k = 0; k < 4; k++)
+            c[k] = floorf(p.scale * c[k] + bias) * p.inv_scale;
+        return;
+    }
     int size = 0;
     if (p.method == PL_DITHER_BLUE_NOISE || p.method == PL_DITHER_ORDERED_LUT)
         size = p.lut_size;
@@ -519,24 +592,24 @@ PLB_DEV float plb_round_fbo(float v, int kind, int bits)
 }
 
 // PLB_OP_PEAK is handled by the kernel that owns the block-wide reduction; here we only
-// compute the per-pixel 14-bit PQ luma (colorspace.c:1279-1288, exact float constants)
+// compute the per-pixel 14-bit PQ luma (colorspace.c:1279-1288, exact float constants).
+// HOT: PQ source, static curve evaluation (specialised kernels).
+template <bool HOT = false>
 PLB_DEV uint32_t plb_peak_ypq(const int trc, const plb_op_peak &p, const float c_in[4])
 {
     float c[3] = { c_in[0], c_in[1], c_in[2] };
-    plb_linearize(trc, p.lin, c);
+    if (HOT) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = fmaxf(c[k], 0.0f);
+        plb_curve3_s<PLB_CV_PQ_EOTF_SDR>(c);
+    } else {
+        plb_linearize(trc, p.lin, c);
+    }
     float luma = plb_dot3_fma(p.lin.luma[0], p.lin.luma[1], p.lin.luma[2], c[0], c[1], c[2]);
-    const float PQ_M1 = 2610.f / 4096 * 1.f / 4, PQ_M2 = 2523.f / 4096 * 128,
-                PQ_C1 = 3424.f / 4096, PQ_C2 = 2413.f / 4096 * 32, PQ_C3 = 2392.f / 4096 * 32;
     luma *= 203.0f / 10000.0f;
     luma = plb_clamp(luma, 0.0f, 1.0f);
-    float pqv;
-    if (plm_curve<PLB_CV_PQX_OETF>(luma, pqv)) {
-        luma = pqv;
-    } else {
-        luma = plm_powf(luma, PQ_M1);
-        luma = (PQ_C1 + PQ_C2 * luma) / (1.0f + PQ_C3 * luma);
-        luma = plm_powf(luma, PQ_M2);
-    }
+    luma = HOT ? plb_curve1_s<PLB_CV_PQX_OETF>(luma) : plb_curve<PLB_CV_PQX_OETF>(luma);
     if (p.cutoff != 0.0f) {
         float t = plb_clamp((luma - 0.0f) / (p.cutoff - 0.0f), 0.0f, 1.0f);
         luma *= t * t * (3.0f - 2.0f * t);
@@ -847,7 +920,7 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                        op.u.sigmoid.offset / op.u.sigmoid.scale;
             }
             break;
-        case PLB_OP_COLOR_MAP: plb_color_map(op.u.cmap, c); break;
+        case PLB_OP_COLOR_MAP: plb_color_map<false>(op.u.cmap, c); break;
         case PLB_OP_DITHER:    plb_dither(op.u.dither, x, y, c); break;
         case PLB_OP_DOVI_RESHAPE: plb_dovi_reshape(c); break;
         case PLB_OP_DOVI_LMS:
@@ -897,7 +970,7 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
         }
         case PLB_OP_PEAK:
             *peak_op = &op.u.peak;
-            *y_pq = plb_peak_ypq(op.u.peak.lin.trc, op.u.peak, c);
+            *y_pq = plb_peak_ypq<false>(op.u.peak.lin.trc, op.u.peak, c);
             break;
         default:
             break;

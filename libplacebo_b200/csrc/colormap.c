@@ -506,11 +506,8 @@ void pl_shader_color_map_ex(pl_shader sh, const struct pl_color_map_params *para
         cm->g_a = 1.0f / lut_range;
         cm->g_b = -gamut.min_luma / lut_range;
         const int lut_n[3] = { cm->lut_I, cm->lut_C, cm->lut_h };
-        for (int a = 0; a < 3; a++) { // the shader's per-pixel fp32 expressions, evaluated once
-            const float base = 0.5f / (float) lut_n[a], end = 1.0f - 0.5f / (float) lut_n[a];
-            cm->g_base[a] = base;
-            cm->g_scale[a] = end - base;
-        }
+        for (int a = 0; a < 3; a++)
+            cm->g_nm1[a] = (float) (lut_n[a] - 1);
     }
 
     plb_record_delinearize(sh, &dst);

@@ -61,7 +61,6 @@ struct cv_def {
     double m1, m2, c1, c2, c3, inv_m1, inv_m2;
     double scale;       // EOTF: output factor; OETF: input factor
     double gamma;
-    int emin, ehi_bits; // domain [2^emin, hi), hi given by its float bits
 };
 
 static double cv_eval(const struct cv_def *d, double x)
@@ -97,33 +96,32 @@ static bool cv_define(int id, const struct plb_pq_consts *q, struct cv_def *d)
         d->scale = q->from_pq;
         // fall through
     case PLB_CV_PQ_EOTF:
-        // zero below c1^m2 = 2^-20.4; the denominator c2 - c3 x^(1/m2) has its root at 1.99
-        d->kind = 0; d->emin = -21; d->ehi_bits = 0x3FC00000; // 1.5
+        d->kind = 0;
         return true;
     case PLB_CV_PQ_OETF_SDR:
-        d->kind = 1; d->scale = q->to_pq; d->emin = -58; d->ehi_bits = 0x43800000; // 256
+        d->kind = 1; d->scale = q->to_pq;
         return true;
     case PLB_CV_PQ_OETF_DELIN:
-        d->kind = 1; d->scale = q->inv_from_pq; d->emin = -58; d->ehi_bits = 0x43800000;
+        d->kind = 1; d->scale = q->inv_from_pq;
         return true;
     case PLB_CV_PQ_OETF:
-        d->kind = 1; d->emin = -64; d->ehi_bits = 0x41000000; // 8
+        d->kind = 1;
         return true;
     case PLB_CV_PQX_OETF:
-        d->kind = 1; d->emin = -64; d->ehi_bits = 0x40000000; // 2
+        d->kind = 1;
         d->m1 = PQ_M1; d->m2 = PQ_M2; d->c1 = PQ_C1; d->c2 = PQ_C2; d->c3 = PQ_C3;
         return true;
     case PLB_CV_POW_24:
-        d->kind = 2; d->gamma = 2.4f; d->emin = -20; d->ehi_bits = 0x41000000;
+        d->kind = 2; d->gamma = 2.4f;
         return true;
     case PLB_CV_POW_INV24:
-        d->kind = 2; d->gamma = (float) (1.0 / 2.4); d->emin = -96; d->ehi_bits = 0x41800000; // 16
+        d->kind = 2; d->gamma = (float) (1.0 / 2.4);
         return true;
     case PLB_CV_POW_22:
-        d->kind = 2; d->gamma = 2.2f; d->emin = -20; d->ehi_bits = 0x41000000;
+        d->kind = 2; d->gamma = 2.2f;
         return true;
     case PLB_CV_POW_INV22:
-        d->kind = 2; d->gamma = (float) (1.0 / 2.2); d->emin = -96; d->ehi_bits = 0x41800000;
+        d->kind = 2; d->gamma = (float) (1.0 / 2.2);
         return true;
     }
     return false;
@@ -137,11 +135,11 @@ bool plb_curve_generate(int id, const struct plb_pq_consts *q, struct plb_curve_
     if (!cv_define(id, q, &d))
         return false;
     const int M = PLB_CV_MBITS(id), shift = 23 - M;
-    const int seg_lo = (d.emin + 127) << M, seg_hi = d.ehi_bits >> shift; // [seg_lo, seg_hi)
+    const int seg_lo = PLB_CV_BASE(id) + 1;
     out->mbits = M;
-    out->base = seg_lo - 1;
-    out->nseg = seg_hi - seg_lo;
-    out->coef = malloc((size_t) (out->nseg + 1) * 4 * sizeof(float));
+    out->base = PLB_CV_BASE(id);
+    out->nseg = PLB_CV_NSEG(id);
+    out->coef = calloc((size_t) PLB_CV_ENTRIES(id) * 4, sizeof(float)); // last entry: padding
     if (!out->coef)
         return false;
     const double a = 0.46193976625564337, b = 0.19134171618254489;
@@ -177,7 +175,7 @@ PL_API bool pl_cuda_curve_table(int id, int *base, int *nseg, int *mbits, float 
     if (nseg) *nseg = h.nseg;
     if (mbits) *mbits = h.mbits;
     if (coef)
-        memcpy(coef, h.coef, (size_t) (h.nseg + 1) * 4 * sizeof(float));
+        memcpy(coef, h.coef, (size_t) (h.nseg + 1) * 4 * sizeof(float)); // without the padding entry
     free(h.coef);
     return true;
 }

@@ -40,13 +40,44 @@ enum plb_curve_id {
     ((id) <= PLB_CV_PQ_EOTF ? 7 : (id) <= PLB_CV_PQX_OETF ? 4 : \
      ((id) == PLB_CV_POW_24 || (id) == PLB_CV_POW_22) ? 6 : 4)
 
+// Domain of each curve: [2^EMIN, float with bits HIBITS). Compile-time so that the specialised
+// kernels slice the argument with immediates (plm_curve_s); the generator uses the same numbers.
+//   PQ EOTF: zero below c1^m2 = 2^-20.4; the denominator c2 - c3 x^(1/m2) has its root at 1.99
+#define PLB_CV_EMIN(id) \
+    ((id) <= PLB_CV_PQ_EOTF ? -21 : (id) <= PLB_CV_PQ_OETF_DELIN ? -58 : (id) <= PLB_CV_PQX_OETF ? -64 : \
+     ((id) == PLB_CV_POW_24 || (id) == PLB_CV_POW_22) ? -20 : -96)
+#define PLB_CV_HIBITS(id) \
+    ((id) <= PLB_CV_PQ_EOTF ? 0x3FC00000u /* 1.5 */ : (id) <= PLB_CV_PQ_OETF_DELIN ? 0x43800000u /* 256 */ : \
+     (id) == PLB_CV_PQ_OETF ? 0x41000000u /* 8 */ : (id) == PLB_CV_PQX_OETF ? 0x40000000u /* 2 */ : \
+     ((id) == PLB_CV_POW_24 || (id) == PLB_CV_POW_22) ? 0x41000000u : 0x41800000u /* 16 */)
+// first segment index - 1 (= index of the constant segment below the domain) and segment count
+#define PLB_CV_BASE(id) (((PLB_CV_EMIN(id) + 127) << PLB_CV_MBITS(id)) - 1)
+#define PLB_CV_NSEG(id) ((int) (PLB_CV_HIBITS(id) >> (23 - PLB_CV_MBITS(id))) - (PLB_CV_BASE(id) + 1))
+// table entries: [0] constant below the domain, [1 .. nseg] the segments, [nseg + 1] unused
+// padding that clamped out-of-domain indices land on
+#define PLB_CV_ENTRIES(id) (PLB_CV_NSEG(id) + 2)
+
 // Device-side descriptor. Segment 0 is the constant f(0) used for every argument below the
 // domain; segment i >= 1 covers float bits [(base + i) << (23 - M), (base + i + 1) << (23 - M)).
 struct plb_curve {
-    const void *coef;   // float4[nseg + 1]: (c0, c1, c2, c3)
+    const void *coef;   // float4[nseg + 2]: (c0, c1, c2, c3)
     int base;
-    int nseg;           // 0: empty domain (everything takes the exact path)
+    int nseg;           // -1: empty domain (everything takes the exact path)
 };
+
+// All tables live in ONE device allocation, curve `id` starting at entry PLB_CV_OFFSET(id), so
+// that a specialised kernel needs a single base pointer and immediate offsets.
+static inline
+#ifdef __CUDACC__
+__host__ __device__ constexpr
+#endif
+int plb_cv_offset(int id)
+{
+    int off = 0;
+    for (int j = 0; j < id; j++)
+        off += PLB_CV_ENTRIES(j);
+    return off;
+}
 
 // Host-side table as generated
 struct plb_curve_host {

@@ -422,7 +422,8 @@ bool plb_pq_upload_ortho(const plb_pq_consts *q);
 #define PLB_MAX_DEVICES 64
 static struct {
     int refs;
-    void *tables[PLB_CV_COUNT];
+    void *tables;
+    bool exact;
 } g_bank[PLB_MAX_DEVICES];
 static pthread_mutex_t g_bank_lock = PTHREAD_MUTEX_INITIALIZER;
 
@@ -430,10 +431,8 @@ static void bank_release(int device)
 {
     pthread_mutex_lock(&g_bank_lock);
     if (g_bank[device].refs > 0 && --g_bank[device].refs == 0) {
-        for (int i = 0; i < PLB_CV_COUNT; i++) {
-            cudaFree(g_bank[device].tables[i]);
-            g_bank[device].tables[i] = NULL;
-        }
+        cudaFree(g_bank[device].tables);
+        g_bank[device].tables = NULL;
     }
     pthread_mutex_unlock(&g_bank_lock);
 }
@@ -450,32 +449,36 @@ bool plb_upload_pq_consts(pl_gpu gpu)
         plb_pq_literal(&q);
         const char *e = getenv("PLB_EXACT_MATH");
         q.exact_math = e && atoi(e) != 0;
+        const size_t total = (size_t) plb_cv_offset(PLB_CV_COUNT) * 4 * sizeof(float);
+        float *host = (float *) calloc(1, total);
+        void *d = NULL;
+        ok = host && cudaMalloc(&d, total) == cudaSuccess;
         for (int i = 0; i < PLB_CV_COUNT && ok; i++) {
             struct plb_curve_host h;
             ok = plb_curve_generate(i, &q, &h);
             if (!ok)
                 break;
-            const size_t bytes = (size_t) (h.nseg + 1) * 4 * sizeof(float);
-            void *d = NULL;
-            ok = cudaMalloc(&d, bytes) == cudaSuccess &&
-                 cudaMemcpy(d, h.coef, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+            memcpy(host + (size_t) plb_cv_offset(i) * 4, h.coef, (size_t) PLB_CV_ENTRIES(i) * 4 * sizeof(float));
             free(h.coef);
-            g_bank[p->device].tables[i] = d;
-            q.cv[i].coef = d;
+            q.cv[i].coef = (const char *) d + (size_t) plb_cv_offset(i) * 16;
             q.cv[i].base = h.base;
             q.cv[i].nseg = q.exact_math ? -1 : h.nseg; // -1: even the segment below the domain misses
         }
-        ok = ok && plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
-        if (!ok) {
-            for (int i = 0; i < PLB_CV_COUNT; i++) {
-                cudaFree(g_bank[p->device].tables[i]);
-                g_bank[p->device].tables[i] = NULL;
-            }
+        q.cv_bank = d;
+        ok = ok && cudaMemcpy(d, host, total, cudaMemcpyHostToDevice) == cudaSuccess &&
+             plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
+        free(host);
+        if (ok) {
+            g_bank[p->device].tables = d;
+            g_bank[p->device].exact = q.exact_math;
+        } else {
+            cudaFree(d);
         }
     }
     if (ok) {
         g_bank[p->device].refs++;
         p->bank_ref = true;
+        p->exact_math = g_bank[p->device].exact;
     }
     pthread_mutex_unlock(&g_bank_lock);
     if (!ok)

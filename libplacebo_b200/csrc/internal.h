@@ -97,6 +97,7 @@ struct plb_gpu {
     bool failed;
     bool no_timers;
     bool bank_ref;         // holds a reference on the device's transfer-curve tables
+    bool exact_math;       // PLB_EXACT_MATH=1 at creation: specialised (curve-only) kernels are off
     int coord_mode;        // enum plb_coord_mode used by samplers
     uint64_t launches;     // kernels launched (pl_cuda_launch_count)
     int sm_count;
@@ -176,7 +177,7 @@ struct plb_op_color_map {
     const float *gamut_lut;            // rgba32f texels (quantised to n/65535), I fastest
     int lut_I, lut_C, lut_h;
     float g_a, g_b;
-    float g_base[3], g_scale[3];       // LUT addressing per axis: 0.5/n and (1 - 0.5/n) - 0.5/n (lut.c:285-295)
+    float g_nm1[3];                    // LUT addressing per axis: (float) (n - 1)
 };
 
 struct plb_op_dither {
@@ -187,6 +188,9 @@ struct plb_op_dither {
     uint32_t frame_index;
     float gamma;
     float rot[4];
+    // derived on the host: power-of-two LUT, no temporal rotation, plain (not gamma-aware) rounding
+    int fast_pow2;
+    float scale, inv_scale;            // 2^depth - 1 and its reciprocal
 };
 
 struct plb_op_peak {
@@ -229,6 +233,7 @@ struct plb_color_prog {
 struct plb_pq_consts {
     // transfer curves (curves.h), filled by gpu.cu after the tables are uploaded
     struct plb_curve cv[PLB_CV_COUNT];
+    const void *cv_bank;   // all tables, curve id at entry plb_cv_offset(id) (float4 units)
     int exact_math;        // PLB_EXACT_MATH=1: round-1 binary64 definitions everywhere
     float m1, m2, c1, c2, c3, inv_m1, inv_m2, to_pq, from_pq, inv_from_pq;
     float hlg_a, hlg_b, hlg_c, hlg_inv_a;

@@ -192,8 +192,13 @@ struct plb_hdr_args {
     plb_tex_desc src, dst;
     int dst_x0, dst_y0, out_w, out_h;
     float src_scale;
-    int n_pre, n_mid, n_post;          // light steps before linearize / before dither / at the end
+    // light steps between delinearize and dither / after dither that are not folded below
+    int n_mid, n_post;
     int has_dither;
+    // folded tail: [scale] -> swizzle (identity selection: absent components take 0, 0, 0, 1)
+    int fold_post;                     // n_post == 0 and the fields below describe the tail
+    float post_scale; int post_scale_alpha, has_post_scale;
+    int swz_keep, has_swz, swz_force_alpha;
     plb_trc_consts lin, delin;
     plb_op_color_map cmap;
     plb_op_dither dither;
@@ -226,22 +231,64 @@ k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
         if (gy + 8 < a.out_h && r + 1 < PIX_TILE / 8) // next row's texel while this one computes
             raw = *(const uint2 *) (src + (size_t) (gy + 8) * a.src.pitch);
         float c[4] = { t.x * a.src_scale, t.y * a.src_scale, t.z * a.src_scale, t.w * a.src_scale };
-        int li = 0;
-        #pragma unroll 1
-        for (int i = 0; i < a.n_pre; i++, li++)
-            plb_light_step(a.light[li], a.light[li].kind, c);
-        plb_linearize(TRC_PQ, a.lin, c);
-        plb_color_map(a.cmap, c);
-        plb_delinearize(TRC_BT_1886, a.delin, c);
-        #pragma unroll 1
-        for (int i = 0; i < a.n_mid; i++, li++)
-            plb_light_step(a.light[li], a.light[li].kind, c);
+
+        // pl_shader_linearize, PQ (colorspace.c:662-668): clamp, EOTF scaled to 203 nits = 1
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = fmaxf(c[k], 0.0f);
+        plb_curve3_s<PLB_CV_PQ_EOTF_SDR>(c);
+        plb_color_map<true>(a.cmap, c);
+        // pl_shader_delinearize, BT.1886 (colorspace.c:759-767)
+        if (a.delin.black_scaled) {
+            const float ps_a = 1 / (a.delin.csp_max - a.delin.csp_min),
+                        ps_b = -a.delin.csp_min / (a.delin.csp_max - a.delin.csp_min);
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                c[k] = ps_a * c[k] + ps_b;
+        }
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = a.delin.a * fmaxf(c[k], 0.0f);
+        plb_curve3_s<PLB_CV_POW_INV24>(c);
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] -= a.delin.b;
+
+        if (a.n_mid) {
+            #pragma unroll 1
+            for (int i = 0; i < a.n_mid; i++)
+                plb_light_step(a.light[i], a.light[i].kind, c);
+        }
         if (a.has_dither)
             plb_dither(a.dither, gx, gy, c);
-        #pragma unroll 1
-        for (int i = 0; i < a.n_post; i++, li++)
-            plb_light_step(a.light[li], a.light[li].kind, c);
-        plb_store(a.dst, a.dst_x0 + gx, a.dst_y0 + gy, make_float4(c[0], c[1], c[2], c[3]));
+        if (a.fold_post) {
+            if (a.has_post_scale) {
+                c[0] *= a.post_scale; c[1] *= a.post_scale; c[2] *= a.post_scale;
+                if (a.post_scale_alpha)
+                    c[3] *= a.post_scale;
+            }
+            if (a.has_swz) {
+                const float o3 = c[3];
+                if (!(a.swz_keep & 1)) c[0] = 0.0f;
+                if (!(a.swz_keep & 2)) c[1] = 0.0f;
+                if (!(a.swz_keep & 4)) c[2] = 0.0f;
+                if (!(a.swz_keep & 8)) c[3] = 1.0f;
+                if (a.swz_force_alpha)
+                    c[3] = o3;
+            }
+        } else {
+            #pragma unroll 1
+            for (int i = 0; i < a.n_post; i++)
+                plb_light_step(a.light[a.n_mid + i], a.light[a.n_mid + i].kind, c);
+        }
+        const int ox = a.dst_x0 + gx, oy = a.dst_y0 + gy;
+        if (a.dst.kind == PLB_FK_UNORM8 && a.dst.comps == 4) {
+            *(uint32_t *) ((char *) a.dst.ptr + (size_t) oy * a.dst.pitch + (size_t) ox * 4) =
+                plb_unorm(c[0], 255.0f) | (plb_unorm(c[1], 255.0f) << 8) |
+                (plb_unorm(c[2], 255.0f) << 16) | (plb_unorm(c[3], 255.0f) << 24);
+        } else {
+            plb_store(a.dst, ox, oy, make_float4(c[0], c[1], c[2], c[3]));
+        }
     }
 }
 
@@ -252,11 +299,11 @@ static bool op_is_light(int k)
 }
 
 // Eligibility of k_pixel_hdr and its argument block: one rgba16hf plane sampled 1:1 with the
-// identity component map; program = light* LINEARIZE(PQ) COLOR_MAP DELINEARIZE(BT.1886) light*
-// [DITHER] light*.
-static bool pixel_hdr_args(const struct plb_pixel_launch *p, const plb_tail_args *t, plb_hdr_args *h)
+// identity component map; program = LINEARIZE(PQ) COLOR_MAP DELINEARIZE(BT.1886) light*
+// [DITHER] light*. The usual tail (scale, identity swizzle) is folded into flags.
+static bool pixel_hdr_args(pl_gpu gpu, const struct plb_pixel_launch *p, const plb_tail_args *t, plb_hdr_args *h)
 {
-    if (!p->dst.ptr || p->nplanes != 1)
+    if (!p->dst.ptr || p->nplanes != 1 || plb_gpu_priv(gpu)->exact_math)
         return false;
     const plb_plane_src &pl = p->planes[0];
     if (pl.kind != PLB_PLANE_DIRECT || !t->plane_cc[0].ident || pl.tex.ptr2 || pl.tex.addr ||
@@ -269,20 +316,14 @@ static bool pixel_hdr_args(const struct plb_pixel_launch *p, const plb_tail_args
     memset(h, 0, sizeof(*h));
     const plb_color_prog &pr = p->prog;
     int i = 0, nl = 0;
-    for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
-        if (nl == HDR_MAX_LIGHT)
-            return false;
-        h->light[nl++] = pr.ops[i];
-        h->n_pre++;
-    }
-    if (i + 3 > pr.n || pr.ops[i].kind != PLB_OP_LINEARIZE || pr.ops[i].u.trc.trc != TRC_PQ ||
-        pr.ops[i + 1].kind != PLB_OP_COLOR_MAP || pr.ops[i + 2].kind != PLB_OP_DELINEARIZE ||
-        pr.ops[i + 2].u.trc.trc != TRC_BT_1886)
+    if (pr.n < 3 || pr.ops[0].kind != PLB_OP_LINEARIZE || pr.ops[0].u.trc.trc != TRC_PQ ||
+        pr.ops[1].kind != PLB_OP_COLOR_MAP || pr.ops[2].kind != PLB_OP_DELINEARIZE ||
+        pr.ops[2].u.trc.trc != TRC_BT_1886)
         return false;
-    h->lin = pr.ops[i].u.trc;
-    h->cmap = pr.ops[i + 1].u.cmap;
-    h->delin = pr.ops[i + 2].u.trc;
-    i += 3;
+    h->lin = pr.ops[0].u.trc;
+    h->cmap = pr.ops[1].u.cmap;
+    h->delin = pr.ops[2].u.trc;
+    i = 3;
     for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
         if (nl == HDR_MAX_LIGHT)
             return false;
@@ -297,6 +338,7 @@ static bool pixel_hdr_args(const struct plb_pixel_launch *p, const plb_tail_args
         h->n_post = h->n_mid; // no dither: one run of light steps
         h->n_mid = 0;
     }
+    const int post0 = i;
     for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {
         if (nl == HDR_MAX_LIGHT)
             return false;
@@ -305,6 +347,37 @@ static bool pixel_hdr_args(const struct plb_pixel_launch *p, const plb_tail_args
     }
     if (i != pr.n)
         return false;
+    // fold "[scale] [identity swizzle]" (what pass_output_target records)
+    if (h->has_dither || h->n_post == pr.n - post0) {
+        int j = post0;
+        plb_hdr_args f = *h;
+        f.fold_post = 1;
+        if (j < pr.n && pr.ops[j].kind == PLB_OP_SCALE) {
+            f.has_post_scale = 1;
+            f.post_scale = pr.ops[j].u.scale.s;
+            f.post_scale_alpha = pr.ops[j].u.scale.with_alpha;
+            j++;
+        }
+        bool ok = true;
+        if (j < pr.n && pr.ops[j].kind == PLB_OP_SWIZZLE) {
+            const plb_color_op &op = pr.ops[j];
+            f.has_swz = 1;
+            f.swz_force_alpha = op.u.swizzle.force_alpha;
+            for (int k = 0; k < 4; k++) {
+                const int m = op.u.swizzle.map[k];
+                const int sel = (k < op.u.swizzle.comps && m >= 0) ? m : -1;
+                if (sel == k)
+                    f.swz_keep |= 1 << k;
+                else if (sel >= 0)
+                    ok = false; // a real permutation: generic step
+            }
+            j++;
+        }
+        if (ok && j == pr.n) {
+            f.n_post = 0;
+            *h = f;
+        }
+    }
     h->src = pl.tex;
     h->dst = p->dst;
     h->dst_x0 = p->dst_rect.x0;
@@ -406,7 +479,7 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
         hdr_mode = e ? atoi(e) : 1;
     }
     plb_hdr_args h;
-    if (hdr_mode > 0 && pixel_hdr_args(p, &t, &h)) {
+    if (hdr_mode > 0 && pixel_hdr_args(gpu, p, &t, &h)) {
         dim3 block(32, 8);
         dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
         k_pixel_hdr<<<grid, block, 0, STREAM(gpu)>>>(h);

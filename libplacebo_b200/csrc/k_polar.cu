@@ -271,7 +271,8 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
     // straight from the kernel parameters (constant bank): nothing to stage but the tile.
     if (!PURE) {
         plm_tables_init(); // published by the barrier after the tile staging
-        plb_tail_stage(a.tail);
+        if (MODE != 2)
+            plb_tail_stage(a.tail);
     }
 
     const bool interior = SRC != UP2_SRC_ANY && a.use_tma && col0 >= 0 && row0 >= 0 &&
@@ -465,19 +466,13 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
         }
         return;
     }
-    const plb_tail_args &t = plb_s_tail;
-    bool has_peak = false;
-    for (int i = 0; i < plb_s_prog.n; i++)
-        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
-    const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
-    const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
-    const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
-    __shared__ plb_peak_smem ps;
-    if (has_peak)
-        plb_peak_begin(ps);
-    const plb_op_peak *pk_any = nullptr;
-
     if constexpr (MODE == 2) {
+        // Canonical merged plane pass of a YUV 4:2:0 HDR frame (host-checked, launch_up2):
+        // chroma = the two EWA results -> colour[1], colour[2]; one r16 luma plane (direct,
+        // debanded or AV1-grained) -> colour[0]; program = MATRIX (pl_shader_decode_color)
+        // [+ peak-detection tap on PQ]; rgba16hf target. Straight-line, launch description
+        // straight from the kernel parameters.
+        const plb_tail_args &t = a.tail;
         float (*stage)[TH][TW] = (float (*)[TH][TW]) aux;
         #pragma unroll
         for (int oyo = 0; oyo < UP2_OY; oyo++) {
@@ -494,10 +489,21 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                 }
             }
         }
-        __syncthreads();
+        const bool has_peak = t.prog.n > 1;
+        const plb_op_peak &pk = t.prog.ops[1].u.peak;
+        const plb_color_op &mat = t.prog.ops[0];
+        __shared__ plb_peak_smem ps;
+        if (has_peak)
+            plb_peak_begin(ps); // ends with a barrier
+        else
+            __syncthreads();
+        const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
+        const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
+        const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
         // the tile is a whole number of work groups (host check), so their sizes are powers of two
         const int wg_sx = __ffs(t.wg_w) - 1, wg_sy = __ffs(t.wg_h) - 1;
         const int wg0x = X0 >> wg_sx, wg0y = Y0 >> wg_sy;
+        const plb_plane_src &pl = t.planes[0];
         #pragma unroll 1
         for (int j = 0; j < UP2_OX * UP2_OY; j++) {
             const int idx = j * (UP2_TX * UP2_TY) + tid;
@@ -506,60 +512,48 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
             const bool inside = gx < t.out_w && gy < t.out_h;
             if (!has_peak && !inside)
                 continue;
-            float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
-            #pragma unroll
-            for (int k = 0; k < NC; k++)
-                prim[k] = stage[k][ly][lx];
-            float color[4] = { t.init[0], t.init[1], t.init[2], t.init[3] };
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int m = t.src_map[k];
-                #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    color[q] = m == q ? prim[k] : color[q];
-            }
-            #pragma unroll 1
-            for (int i = 0; i < t.nplanes; i++) {
-                const plb_plane_src &pl = t.planes[i];
-                float tmp[4];
-                plb_sample_plane_simple(pl, t.plane_cc[i], gx, gy, t.frame_index, tmp);
-                #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float v = tmp[k] * pl.scale;
-                    const int m = pl.map[k];
-                    #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        color[q] = m == q ? v : color[q];
-                }
-            }
-            uint32_t ypq = 0;
-            const plb_op_peak *pk = nullptr;
-            #pragma unroll 1
-            for (int i = 0; i < plb_s_prog.n; i++) {
-                const plb_color_op &op = plb_s_prog.ops[i];
-                const int kind = op.kind;
-                if (kind == PLB_OP_PEAK) {
-                    pk = &op.u.peak;
-                    ypq = plb_peak_ypq(TRC_PQ, op.u.peak, color);
-                } else {
-                    plb_light_step(op, kind, color);
-                }
+            float tmp[4];
+            if (pl.kind == PLB_PLANE_GRAIN_AV1)
+                plb_sample_plane_simple_t<0>(pl, t.plane_cc[0], gx, gy, t.frame_index, tmp);
+            else
+                plb_sample_plane_simple_t<1>(pl, t.plane_cc[0], gx, gy, t.frame_index, tmp);
+            float color[4] = { tmp[0] * pl.scale, stage[0][ly][lx], stage[1][ly][lx], t.init[3] };
+            plb_matv(mat.u.matrix.m, color[0], color[1], color[2]);
+            if (mat.u.matrix.has_c) {
+                color[0] += mat.u.matrix.c[0]; color[1] += mat.u.matrix.c[1]; color[2] += mat.u.matrix.c[2];
             }
             if (has_peak) {
+                const uint32_t ypq = plb_peak_ypq<true>(TRC_PQ, pk, color);
                 const int wlx = lx >> wg_sx, wly = ly >> wg_sy;
                 const bool valid = (wg0x + wlx) < nwgx && (wg0y + wly) < nwgy;
-                pk_any = pk;
-                plb_peak_add(ps, *pk, valid, wly * wgs_x + wlx, ypq);
+                plb_peak_add(ps, pk, valid, wly * wgs_x + wlx, ypq);
             }
-            if (inside && t.dst.ptr)
-                plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy,
-                          make_float4(color[0], color[1], color[2], color[3]));
+            if (inside) {
+                const __half2 lo = __floats2half2_rn(color[0], color[1]), hi = __floats2half2_rn(color[2], color[3]);
+                uint2 raw;
+                raw.x = *(const uint32_t *) &lo;
+                raw.y = *(const uint32_t *) &hi;
+                *(uint2 *) ((char *) t.dst.ptr + (size_t) (t.dst_y0 + gy) * t.dst.pitch +
+                            (size_t) (t.dst_x0 + gx) * 8) = raw;
+            }
         }
         if (has_peak)
-            plb_peak_finish(ps, *pk_any, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
+            plb_peak_finish(ps, pk, wgs_x, wgs_y, X0 / t.wg_w, Y0 / t.wg_h, nwgx, nwgy,
                             (uint32_t) (t.wg_w * t.wg_h));
+        return;
     } else {
 
+    const plb_tail_args &t = plb_s_tail;
+    bool has_peak = false;
+    for (int i = 0; i < plb_s_prog.n; i++)
+        has_peak |= plb_s_prog.ops[i].kind == PLB_OP_PEAK;
+    const int wgs_x = has_peak ? TW / t.wg_w : 1, wgs_y = has_peak ? TH / t.wg_h : 1;
+    const int nwgx = has_peak ? (t.out_w + t.wg_w - 1) / t.wg_w : 1;
+    const int nwgy = has_peak ? (t.out_h + t.wg_h - 1) / t.wg_h : 1;
+    __shared__ plb_peak_smem ps;
+    if (has_peak)
+        plb_peak_begin(ps);
+    const plb_op_peak *pk_any = nullptr;
     #pragma unroll
     for (int oyo = 0; oyo < UP2_OY; oyo++) {
         const int gy = Y0 + ty * UP2_OY + oyo;
@@ -715,18 +709,23 @@ static bool launch_up2(pl_gpu gpu, polar_up2_args &args)
     for (int i = 0; i < args.tail.nplanes; i++)
         light &= args.tail.planes[i].kind == PLB_PLANE_DIRECT;
     const bool pure = light && args.tail.dst.ptr;
-    // merged HDR plane pass (MODE 2): direct / debanded planes, light steps, peak tap on PQ input
-    bool hdr = NC == 2 && !pure;
-    for (int i = 0; i < args.tail.prog.n; i++) {
-        const plb_color_op &op = args.tail.prog.ops[i];
-        const int k = op.kind;
-        hdr &= k == PLB_OP_SCALE || k == PLB_OP_MATRIX || k == PLB_OP_ROUND_FBO ||
-               k == PLB_OP_ALPHA || k == PLB_OP_SWIZZLE ||
-               (k == PLB_OP_PEAK && op.u.peak.lin.trc == TRC_PQ);
+    // canonical merged YUV 4:2:0 plane pass (MODE 2, see the kernel): EWA chroma -> colour[1..2],
+    // one r16 luma plane (direct 1:1 / debanded / AV1-grained) -> colour[0], program = MATRIX
+    // [PEAK on PQ], rgba16hf target; not in exact-math mode (static curves)
+    const plb_tail_args &tl = args.tail;
+    bool hdr = NC == 2 && !pure && tl.dst.ptr && tl.dst.kind == PLB_FK_HALF && tl.dst.comps == 4 &&
+               !plb_gpu_priv(gpu)->exact_math && tl.nplanes == 1 &&
+               tl.src_map[0] == 1 && tl.src_map[1] == 2 &&
+               tl.planes[0].map[0] == 0 && tl.planes[0].map[1] < 0 && tl.planes[0].map[2] < 0 &&
+               tl.planes[0].map[3] < 0 && (tl.prog.n == 1 || tl.prog.n == 2) &&
+               tl.prog.ops[0].kind == PLB_OP_MATRIX &&
+               (tl.prog.n == 1 || (tl.prog.ops[1].kind == PLB_OP_PEAK && tl.prog.ops[1].u.peak.lin.trc == TRC_PQ));
+    if (hdr) {
+        const plb_plane_src &pl = tl.planes[0];
+        const bool r16 = pl.tex.kind == PLB_FK_UNORM16 && pl.tex.comps == 1 && !pl.tex.ptr2 && !pl.tex.addr;
+        hdr = (pl.kind == PLB_PLANE_DIRECT && r16 && tl.plane_cc[0].ident) ||
+              (pl.kind == PLB_PLANE_DEBAND && r16) || pl.kind == PLB_PLANE_GRAIN_AV1;
     }
-    for (int i = 0; i < args.tail.nplanes; i++)
-        hdr &= args.tail.planes[i].kind == PLB_PLANE_DIRECT || args.tail.planes[i].kind == PLB_PLANE_DEBAND ||
-               args.tail.planes[i].kind == PLB_PLANE_GRAIN_AV1;
     static int hdr_on = -1; // PLB_UP2_HDR=0 keeps the general tail (A/B measurements)
     if (hdr_on < 0) {
         const char *e = getenv("PLB_UP2_HDR");

@@ -1146,4 +1146,9 @@ void pl_shader_dither(pl_shader sh, int new_depth, pl_shader_obj *dither_state,
         d->rot[2] = sin(r) * m;
         d->rot[3] = cos(r) * m;
     }
+    d->scale = (float) ((1ull << new_depth) - 1);
+    d->inv_scale = 1.0f / d->scale;
+    d->fast_pow2 = (method == PL_DITHER_BLUE_NOISE || method == PL_DITHER_ORDERED_LUT) &&
+                   !params->temporal && lut_size > 0 && !(lut_size & (lut_size - 1)) &&
+                   !(d->gamma != 1.0f && new_depth <= 4);
 }

@@ -60,6 +60,13 @@ WORKLOADS = {
         src_sys="BT_2020_NC", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
         dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
         upscaler="ewa_lanczos", opts=dict(deband=1, peak=2, dither=1, cmap_hq=1, grain=2)),
+    # reduced-size C3 for the CPU-only contract tests of bench.py (not a benchmark configuration)
+    "test_c3_480x270": dict(
+        desc="config C3 at 480x270 (bench.py contract tests)",
+        src=(480, 270), dst=(480, 270), dst_fmt="rgba8",
+        src_sys="BT_2020_NC", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
+        dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
+        upscaler="ewa_lanczos", opts=dict(deband=1, peak=2, dither=1, cmap_hq=1)),
 }
 
 

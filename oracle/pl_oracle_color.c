@@ -843,45 +843,40 @@ ORC_API void orc_get_ipt_matrices(float lms2ipt[9], float ipt2lms[9])
     memcpy(ipt2lms, IPT2LMS, sizeof(IPT2LMS));
 }
 
-static inline void gamut_fetch(const struct orc_color_map_params *p, int i, int c, int h,
-                               float out[3])
+static inline const float *gamut_texel(const struct orc_color_map_params *p, int i, int c, int h)
 {
-    i = i < 0 ? 0 : i > p->lut_I - 1 ? p->lut_I - 1 : i;
-    c = c < 0 ? 0 : c > p->lut_C - 1 ? p->lut_C - 1 : c;
-    h = h < 0 ? 0 : h > p->lut_h - 1 ? p->lut_h - 1 : h;
-    const float *t = p->gamut_lut + (((size_t) h * p->lut_C + c) * p->lut_I + i) * 4;
-    out[0] = t[0]; out[1] = t[1]; out[2] = t[2];
+    return p->gamut_lut + (((size_t) h * p->lut_C + c) * p->lut_I + i) * 4;
 }
 
-// trilinear 3DLUT fetch with the position macros of lut.c:285-295 on each axis:
-// texel-space coordinate = idx * (n-1), clamp-to-edge
+static inline float satf(float x) { return x > 0.0f ? (x < 1.0f ? x : 1.0f) : 0.0f; } // NaN -> 0
+static inline float lerpf(float a, float b, float t) { return fmaf(t, b - a, a); }
+
+// Trilinear 3DLUT fetch. The reference binds the LUT as a linearly filtered 3D texture and
+// addresses texel centres through LUT_POS (lut.c:285-295: x -> mix(0.5/n, 1 - 0.5/n, x)), which
+// in texel space is x (n - 1); the hardware filter clamps to the edge and interpolates with
+// 8-bit weights. Restated in fp32: saturate the index, t = x (n - 1), lerp(a, b, t) =
+// fma(t, b - a, a), axes in the order I, C, h.
 static void gamut_sample(const struct orc_color_map_params *p, const float idx[3], float out[3])
 {
     const int n[3] = { p->lut_I, p->lut_C, p->lut_h };
-    int b[3];
+    int i0[3], i1[3];
     float f[3];
     for (int a = 0; a < 3; a++) {
-        // LUT_SCALE(x) = scale*x + base in normalised coords; * n - 0.5 in texel space
-        const float base = 0.5f / n[a], end = 1.0f - 0.5f / n[a];
-        const float scale = end - base;
-        float u = scale * idx[a] + base;
-        float t = u * (float) n[a] - 0.5f;
-        float fl = floorf(t);
-        b[a] = (int) fl;
+        const float t = satf(idx[a]) * (float) (n[a] - 1);
+        const float fl = floorf(t);
+        i0[a] = (int) fl;
+        i1[a] = i0[a] + 1 < n[a] - 1 ? i0[a] + 1 : n[a] - 1;
         f[a] = t - fl;
     }
-    float c[2][2][2][3];
-    for (int dz = 0; dz < 2; dz++)
-        for (int dy = 0; dy < 2; dy++)
-            for (int dx = 0; dx < 2; dx++)
-                gamut_fetch(p, b[0] + dx, b[1] + dy, b[2] + dz, c[dz][dy][dx]);
+    const float *t000 = gamut_texel(p, i0[0], i0[1], i0[2]), *t001 = gamut_texel(p, i1[0], i0[1], i0[2]);
+    const float *t010 = gamut_texel(p, i0[0], i1[1], i0[2]), *t011 = gamut_texel(p, i1[0], i1[1], i0[2]);
+    const float *t100 = gamut_texel(p, i0[0], i0[1], i1[2]), *t101 = gamut_texel(p, i1[0], i0[1], i1[2]);
+    const float *t110 = gamut_texel(p, i0[0], i1[1], i1[2]), *t111 = gamut_texel(p, i1[0], i1[1], i1[2]);
     for (int k = 0; k < 3; k++) {
-        float x00 = mixf(c[0][0][0][k], c[0][0][1][k], f[0]);
-        float x01 = mixf(c[0][1][0][k], c[0][1][1][k], f[0]);
-        float x10 = mixf(c[1][0][0][k], c[1][0][1][k], f[0]);
-        float x11 = mixf(c[1][1][0][k], c[1][1][1][k], f[0]);
-        float y0 = mixf(x00, x01, f[1]), y1 = mixf(x10, x11, f[1]);
-        out[k] = mixf(y0, y1, f[2]);
+        const float x00 = lerpf(t000[k], t001[k], f[0]), x01 = lerpf(t010[k], t011[k], f[0]);
+        const float x10 = lerpf(t100[k], t101[k], f[0]), x11 = lerpf(t110[k], t111[k], f[0]);
+        const float y0 = lerpf(x00, x01, f[1]), y1 = lerpf(x10, x11, f[1]);
+        out[k] = lerpf(y0, y1, f[2]);
     }
 }
 

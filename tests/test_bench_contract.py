@@ -18,7 +18,7 @@ def run(args, env=None, timeout=600):
 
 
 def test_reference_arm_prints_one_json_line():
-    r = run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "320x180"])
+    r = run(["--impl", "reference", "--steps", "6", "--warmup", "1", "--workload", "test_c3_480x270"])
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -31,7 +31,8 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
-    assert j["config"]["workload"] == "c3_4k_hdr10_to_sdr"
+    assert j["config"]["workload"] == "test_c3_480x270" and j["config"]["src"] == [480, 270]
+    assert j["steps"] >= 5 and "median" in cb["sample"]
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -1,0 +1,125 @@
+"""Parity at the CONFIGURED sizes of BASELINE.json: the frames bench.py times
+are rendered once through the C ABI and compared with the CPU oracle over the whole frame —
+every CTA, every border, the real grid sizes (60 x 68 tiles of k_pixel_hdr, 30 x 68 of the EWA
+kernel, TMA interior tiles and clamped border tiles alike).
+
+Tolerance (north_star): +-1 LSB of the 16-bit output / +-1 ULP of an fp16 output, written in each
+test; achieved: identical bits.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import pipeline_oracle as P
+import plbtest as T
+from test_gpu_render import HDR10, SDR, gpu_render
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bench_frame(w, h, seed=0):
+    """The synthetic frame bench.py renders (libplacebo_b200/stream.py synth_yuv420p10)."""
+    from libplacebo_b200 import stream as S
+    return S.synth_yuv420p10(w, h, seed=seed)
+
+
+def border_report(d):
+    """max difference in the interior and on each 32-pixel border band"""
+    return dict(top=int(d[:32].max()), bottom=int(d[-32:].max()), left=int(d[:, :32].max()),
+                right=int(d[:, -32:].max()), interior=int(d[32:-32, 32:-32].max()))
+
+
+@pytest.mark.parametrize("fmt,depth", [("rgba8", 8), ("rgba16", 16)])
+def test_c3_full_4k_frame(gpu, fmt, depth):
+    """Config C3, 3840x2160: deband, EWA chroma, same-frame HQ peak detection, spline tone map,
+    perceptual gamut map, blue-noise dither. rgba8 is the benchmarked target, rgba16 exposes
+    every LSB of the colour chain."""
+    import ctypes as C
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    img = P.Frame(bench_frame(3840, 2160), T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(3840, 2160, fmt, sample_depth=depth, color_depth=depth, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", deband=True, peak=2, dither=1, cmap_hq=True, frame_index=0)
+    got, peak = gpu_render(gpu, img, tgt, **kw)
+    want, pstate = P.render(img, tgt, **kw)
+    assert np.float32(peak[0]) == np.float32(pstate[0]) and np.float32(peak[1]) == np.float32(pstate[1])
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    scale = 1 if depth == 16 else 1  # LSB of the target itself
+    assert d.max() <= 1 * scale, border_report(d)        # stated tolerance
+    assert d.max() == 0, (border_report(d), float(np.mean(d > 0)))  # achieved
+
+
+def test_c2_full_1080p_to_4k(gpu):
+    """Config C2 (the north-star roofline configuration): 1920x1080 -> 3840x2160 rgba16hf,
+    EWA-Lanczos chroma and main scaler."""
+    img = P.Frame(bench_frame(1920, 1080), T.SYS["BT_709"], csp=SDR)
+    tgt = P.Target(3840, 2160, "rgba16hf", csp=SDR)
+    got, _ = gpu_render(gpu, img, tgt, upscaler="ewa_lanczos")
+    want, _ = P.render(img, tgt, upscaler="ewa_lanczos")
+    ulp = T.ulp_diff_half(got, want)
+    assert ulp.max() <= 1, border_report(ulp)
+    assert ulp.max() == 0, (border_report(ulp), float(np.mean(ulp > 0)))
+
+
+def test_c4_full_4k_frame_with_av1_grain(gpu):
+    """Config C4: C3 + AV1 film grain (reference fixture, block overlap) on every plane."""
+    import ctypes as C
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    img = P.Frame(bench_frame(3840, 2160, seed=3), T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(3840, 2160, "rgba8", sample_depth=8, color_depth=8, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", deband=True, peak=2, dither=1, cmap_hq=True, frame_index=7)
+    got, peak = gpu_render(gpu, img, tgt, grain=(7, 1), **kw)
+    want, pstate = P.render(img, tgt, film_grain=(7, 1), **kw)
+    assert np.float32(peak[0]) == np.float32(pstate[0]) and np.float32(peak[1]) == np.float32(pstate[1])
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    assert d.max() == 0, (border_report(d), float(np.mean(d > 0)))
+
+
+_EXACT_SCRIPT = r"""
+import sys
+sys.path.insert(0, {tests!r}); sys.path.insert(0, {root!r})
+import numpy as np
+import gpu_helpers as G, pipeline_oracle as P, plbtest as T
+from test_gpu_render import HDR10, SDR, gpu_render
+planes = T.yuv420p10(512, 288, seed=6)
+img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+tgt = P.Target(512, 288, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+kw = dict(upscaler="ewa_lanczos", deband=True, peak=2, cmap_hq=True, frame_index=0)
+with G.Gpu() as g:
+    got, peak = gpu_render(g, img, tgt, **kw)
+T.oracle().lib.orc_set_exact_math(1)
+want, _ = P.render(img, tgt, **kw)
+assert np.array_equal(got[..., :3], want[..., :3]), "exact-math GPU != exact-math oracle"
+np.save({out!r}, got)
+"""
+
+
+def test_fast_math_within_one_lsb16_of_exact_math(gpu, tmp_path):
+    """The round-2 hot-path arithmetic (transfer curves, fp32 atan2 / sin / cos) against the
+    round-1 definitions (correctly rounded binary64 pow etc., PLB_EXACT_MATH=1) on the whole
+    C3 chain with a 16-bit target. The exact run happens in a fresh process (the mode is fixed
+    when the first pl_gpu of a device is created) and is itself checked bit for bit against the
+    oracle in exact mode."""
+    import ctypes as C
+    out = str(tmp_path / "exact.npy")
+    script = _EXACT_SCRIPT.format(tests=os.path.join(ROOT, "tests"), root=ROOT, out=out)
+    env = dict(os.environ, PLB_EXACT_MATH="1")
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    exact = np.load(out)
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(512, 288, seed=6)
+    img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(512, 288, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", deband=True, peak=2, cmap_hq=True, frame_index=0)
+    fast, _ = gpu_render(gpu, img, tgt, **kw)
+    d = np.abs(fast[..., :3].astype(np.int32) - exact[..., :3].astype(np.int32))
+    # the two definitions of the same real-valued functions agree to the last bit of a 16-bit
+    # output almost everywhere; the exact chain's own fp32 cancellation error (PQ EOTF) shows up
+    # as isolated +-1
+    assert d.max() <= 1, (int(d.max()), float(np.mean(d > 0)))
+    assert np.mean(d > 0) < 0.05, float(np.mean(d > 0))
