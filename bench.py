@@ -284,17 +284,23 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
 
     use_peak = bool(wl["opts"].get("peak"))
     par = None
+    e2e_mode = [False]
     if world > 1 and use_peak:
         from libplacebo_b200 import parallel
-        par = parallel.PeakExchange(st, dist, rank, world)
+        # statistics exchange pipelined one frame ahead (side-stream NCCL all-gather): the
+        # frame's upload (end-to-end mode) happens right before it is measured
+        par = parallel.PeakPipeline(st, dist, rank, world, ring,
+                                    before_measure=lambda j: st.upload(j % ring, *host_in[j % ring])
+                                    if e2e_mode[0] else None)
 
-    def frame(i, e2e):
+    def frame(i, e2e, last=False):
         slot = i % ring
-        if e2e:
-            st.upload(slot, *host_in[slot])
         if par is not None:
-            par.render(slot, slot, i)
+            e2e_mode[0] = e2e
+            par.render(i, last=last)
         else:
+            if e2e:
+                st.upload(slot, *host_in[slot])
             st.render(slot, slot, frame_index=i % 256)
         if e2e:
             st.download(slot, host_out[i % 2])
@@ -312,7 +318,7 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
         l0 = st.launch_count()
         ev0.record(lib_stream)
         for i in range(n):
-            frame(i, e2e)
+            frame(i, e2e, last=i == n - 1)
         if e2e:
             st.join()  # the timed interval ends when the last download has landed
         ev1.record(lib_stream)
@@ -329,13 +335,13 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
         return ms, launches
 
     for i in range(warmup):
-        frame(i, False)
+        frame(i, False, last=i == warmup - 1)
     st.finish()
     with Clocks(local_rank) as clk:
         ms, launches = timed(steps, False, True)
     # deliver the last in-window pass samples (untimed flush frames)
     for i in range(2):
-        frame(i, False)
+        frame(i, False, last=True)
         st.finish()
     passes = st.passes()
 
@@ -343,7 +349,7 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
            "launches": launches, "passes": passes, "clocks": clk.summary(), "steps": steps}
     if with_e2e:
         for i in range(3):
-            frame(i, True)
+            frame(i, True, last=i == 2)
         st.finish()
         e2e_steps = max(5, steps // 2)
         ms_e2e, _ = timed(e2e_steps, True, False)

@@ -785,6 +785,9 @@ PL_API void pl_cuda_destroy(pl_gpu *gpu);
 PL_API void *pl_cuda_stream(pl_gpu gpu); // the cudaStream_t all work is ordered on
 // Wrap device memory that the caller owns (e.g. an NVDEC surface or a framework tensor) as a
 // pl_tex without copying; counterpart of pl_vulkan_wrap (vulkan.h). pitch in bytes.
+// Alignment: `ptr` and `pitch` must be multiples of 16 bytes (the kernels access texels as whole
+// vectors and store runs of four texels as 16-byte words); anything from cudaMalloc /
+// cudaMallocPitch / NVDEC qualifies. Misaligned surfaces are rejected (NULL).
 struct pl_cuda_wrap_params {
     void *ptr;
     size_t pitch;
@@ -1283,6 +1286,14 @@ struct pl_peak_state { float avg_pq, max_pq; };
 PL_API bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *image,
                                      const struct pl_render_params *params,
                                      void *out_peak_buf /* PL_PEAK_BUF_SIZE bytes, host */);
+/* Same, but the statistics stay on the device: `dev_peak_buf` (PL_PEAK_BUF_SIZE bytes of device
+ * memory, e.g. the send buffer of an NCCL all-gather) is filled by an asynchronous copy on the
+ * gpu's stream; the host does not wait. Up to four measured images may be pending (measured
+ * ahead of their pl_render_image), which lets a pipeline overlap the exchange of frame N's
+ * statistics with the measurement of frame N+1. */
+PL_API bool pl_renderer_measure_peak_dev(pl_renderer rr, const struct pl_frame *image,
+                                         const struct pl_render_params *params,
+                                         void *dev_peak_buf /* PL_PEAK_BUF_SIZE bytes, device */);
 PL_API bool pl_peak_state_update(struct pl_peak_state *state, const void *peak_buf,
                                  const struct pl_peak_detect_params *params);
 PL_API void pl_renderer_set_peak_state(pl_renderer rr, const struct pl_peak_state *state);

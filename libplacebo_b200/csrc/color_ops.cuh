@@ -99,19 +99,14 @@ PLB_DEV float plb_curve(float x)
 template <int CV>
 PLB_DEV void plb_curve3_s(float c[3])
 {
-    float y[3];
-    bool hit = true;
-    #pragma unroll
-    for (int k = 0; k < 3; k++)
-        hit &= plm_curve_s<CV>(c[k], y[k]);
-    if (!hit) {
-        #pragma unroll 1
-        for (int k = 0; k < 3; k++) {
-            float t;
-            y[k] = plm_curve_s<CV>(c[k], t) ? t : plb_curve_exact<CV>(c[k]);
-        }
+    float y0, y1, y2;
+    const bool h0 = plm_curve_s<CV>(c[0], y0), h1 = plm_curve_s<CV>(c[1], y1), h2 = plm_curve_s<CV>(c[2], y2);
+    if (!(h0 & h1 & h2)) { // cold; static indices only (a dynamic one would put c[] in local memory)
+        if (!h0) y0 = plb_curve_exact<CV>(c[0]);
+        if (!h1) y1 = plb_curve_exact<CV>(c[1]);
+        if (!h2) y2 = plb_curve_exact<CV>(c[2]);
     }
-    c[0] = y[0]; c[1] = y[1]; c[2] = y[2];
+    c[0] = y0; c[1] = y1; c[2] = y2;
 }
 
 template <int CV>

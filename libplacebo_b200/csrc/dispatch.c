@@ -244,6 +244,9 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         texs[ntexs++] = target;
     plb_gpu_before_use(gpu, texs, ntexs);
 
+    extern int plb_gpu_enter(pl_gpu gpu);
+    extern void plb_gpu_leave(int prev);
+    const int prev_dev = plb_gpu_enter(gpu); // launches go to the gpu's device, whatever is current
     plb_timer_begin(gpu, timer);
     bool ok = false;
     switch (sh->src) {
@@ -266,6 +269,7 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
     }
     plb_timer_end(gpu, timer);
     plb_gpu_after_use(gpu, texs, ntexs);
+    plb_gpu_leave(prev_dev);
     if (ok && pass && dp->info_callback) {
         pass_collect(dp, pass);
         dp->info_callback(dp->info_priv, &pass->stats);

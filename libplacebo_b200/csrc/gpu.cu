@@ -110,8 +110,45 @@ bool plb_cuda_check(pl_gpu gpu, int err, const char *what)
 #define CK(gpu, call) plb_cuda_check(gpu, (int) (call), #call)
 #define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
 
+// Every entry point that allocates, copies or launches first makes the gpu's device current and
+// restores the caller's on return: two pl_gpu on different devices may live in one process, and
+// the host application may switch the current device between calls (e.g. torch.cuda.set_device).
+struct dev_guard {
+    int prev;
+    bool switched;
+    explicit dev_guard(pl_gpu gpu) : prev(-1), switched(false)
+    {
+        const int want = plb_gpu_priv(gpu)->device;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != want)
+            switched = cudaSetDevice(want) == cudaSuccess;
+    }
+    ~dev_guard()
+    {
+        if (switched)
+            cudaSetDevice(prev);
+    }
+};
+#define DEV_GUARD(gpu) dev_guard dev_guard_(gpu)
+
+// C entry points for the host code (dispatch.c wraps every kernel launch)
+extern "C" int plb_gpu_enter(pl_gpu gpu)
+{
+    int prev = -1;
+    const int want = plb_gpu_priv(gpu)->device;
+    if (cudaGetDevice(&prev) != cudaSuccess || prev == want)
+        return -1;
+    return cudaSetDevice(want) == cudaSuccess ? prev : -1;
+}
+
+extern "C" void plb_gpu_leave(int prev)
+{
+    if (prev >= 0)
+        cudaSetDevice(prev);
+}
+
 void *plb_gpu_staging(pl_gpu gpu, size_t size)
 {
+    DEV_GUARD(gpu);
     struct plb_gpu *p = plb_gpu_priv(gpu);
     if (p->staging_size >= size)
         return p->staging;
@@ -129,6 +166,7 @@ void *plb_gpu_staging(pl_gpu gpu, size_t size)
 
 void *plb_dev_alloc(pl_gpu gpu, size_t size)
 {
+    DEV_GUARD(gpu);
     void *ptr = NULL;
     if (!CK(gpu, cudaMalloc(&ptr, size)))
         return NULL;
@@ -137,6 +175,7 @@ void *plb_dev_alloc(pl_gpu gpu, size_t size)
 
 void plb_dev_free(pl_gpu gpu, void *ptr)
 {
+    DEV_GUARD(gpu);
     if (!ptr)
         return;
     // work that still reads the allocation is ordered before the free on the same stream
@@ -145,6 +184,7 @@ void plb_dev_free(pl_gpu gpu, void *ptr)
 
 bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
 {
+    DEV_GUARD(gpu);
     // LUT-sized payloads: go through the pinned staging area so that the source may be
     // freed/modified by the caller right after we return
     void *st = plb_gpu_staging(gpu, size);
@@ -159,6 +199,7 @@ bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
 
 bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size)
 {
+    DEV_GUARD(gpu);
     void *st = plb_gpu_staging(gpu, size);
     if (!st)
         return false;
@@ -170,8 +211,16 @@ bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size)
     return true;
 }
 
+// device -> device, asynchronous on the gpu's stream
+bool plb_dev_copy(pl_gpu gpu, void *dst, const void *src, size_t size)
+{
+    DEV_GUARD(gpu);
+    return CK(gpu, cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToDevice, STREAM(gpu)));
+}
+
 bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size)
 {
+    DEV_GUARD(gpu);
     return CK(gpu, cudaMemsetAsync(dst, val, size, STREAM(gpu)));
 }
 
@@ -415,6 +464,9 @@ bool plb_gpu_no_timers(pl_gpu gpu) { return plb_gpu_priv(gpu)->no_timers; }
 bool plb_pq_upload_polar(const plb_pq_consts *q);
 bool plb_pq_upload_pixel(const plb_pq_consts *q);
 bool plb_pq_upload_ortho(const plb_pq_consts *q);
+bool plb_pq_upload_up2a(const plb_pq_consts *q);
+bool plb_pq_upload_up2b(const plb_pq_consts *q);
+bool plb_pq_upload_up2c(const plb_pq_consts *q);
 
 // Transfer-curve tables (curves.h) live once per device, shared by every pl_gpu on it: the
 // descriptors sit in __constant__ memory, which is per device, not per pl_gpu.
@@ -466,7 +518,8 @@ bool plb_upload_pq_consts(pl_gpu gpu)
         }
         q.cv_bank = d;
         ok = ok && cudaMemcpy(d, host, total, cudaMemcpyHostToDevice) == cudaSuccess &&
-             plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q);
+             plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q) &&
+             plb_pq_upload_up2a(&q) && plb_pq_upload_up2b(&q) && plb_pq_upload_up2c(&q);
         free(host);
         if (ok) {
             g_bank[p->device].tables = d;
@@ -491,6 +544,7 @@ void pl_gpu_flush(pl_gpu gpu) { (void) gpu; }
 
 void pl_gpu_finish(pl_gpu gpu)
 {
+    DEV_GUARD(gpu);
     struct plb_gpu *p = plb_gpu_priv(gpu);
     CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
     if (p->async_xfer) {
@@ -642,6 +696,7 @@ static bool tex_params_valid(pl_gpu gpu, const struct pl_tex_params *params)
 
 pl_tex pl_tex_create(pl_gpu gpu, const struct pl_tex_params *params)
 {
+    DEV_GUARD(gpu);
     if (!tex_params_valid(gpu, params))
         return NULL;
     if (params->export_handle || params->import_handle) {
@@ -691,6 +746,14 @@ pl_tex pl_cuda_wrap(pl_gpu gpu, const struct pl_cuda_wrap_params *params)
                 params->pitch, params->w, params->format->name);
         return NULL;
     }
+    // The kernels access texels as whole vectors (uchar4 / ushort4 / uint2 / float4) and store
+    // runs of four texels as 16-byte words: the base address and the pitch must be multiples
+    // of 16 bytes (cudaMalloc / cudaMallocPitch / NVDEC surfaces are 256-byte aligned).
+    if (((uintptr_t) params->ptr & 15) || (params->pitch & 15)) {
+        PLB_ERR(gpu->log, "pl_cuda_wrap: pointer %p / pitch %zu must be 16-byte aligned",
+                params->ptr, params->pitch);
+        return NULL;
+    }
     struct plb_tex *t = (struct plb_tex *) calloc(1, sizeof(*t));
     t->pub.params.w = params->w;
     t->pub.params.h = params->h;
@@ -719,6 +782,7 @@ void *pl_cuda_tex_ptr(pl_tex tex, size_t *out_pitch)
 
 void pl_tex_destroy(pl_gpu gpu, pl_tex *ptex)
 {
+    DEV_GUARD(gpu);
     if (!ptex || !*ptex)
         return;
     struct plb_tex *t = (struct plb_tex *) *ptex;
@@ -740,9 +804,15 @@ bool pl_tex_recreate(pl_gpu gpu, pl_tex *tex, const struct pl_tex_params *params
         return false;
     }
     if (*tex) {
+        // pl_tex_params_superset (src/gpu.c:276-304): same size and format, and every usage the
+        // caller asks for is already available
         const struct pl_tex_params *cur = &(*tex)->params;
+        const bool usage_ok = cur->sampleable >= params->sampleable && cur->renderable >= params->renderable &&
+                              cur->storable >= params->storable && cur->blit_src >= params->blit_src &&
+                              cur->blit_dst >= params->blit_dst && cur->host_writable >= params->host_writable &&
+                              cur->host_readable >= params->host_readable;
         if (cur->w == params->w && cur->h == params->h && cur->d == params->d &&
-            cur->format == params->format)
+            cur->format == params->format && usage_ok)
             return true;
         pl_tex_destroy(gpu, tex);
     }
@@ -756,6 +826,7 @@ extern bool plb_launch_clear(pl_gpu gpu, const struct plb_tex_desc *dst, const f
 
 void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4])
 {
+    DEV_GUARD(gpu);
     plb_gpu_before_use(gpu, &dst, 1);
     plb_launch_clear(gpu, &plb_tex_priv(dst)->d, color);
     plb_gpu_after_use(gpu, &dst, 1);
@@ -825,6 +896,7 @@ static bool fix_transfer(pl_gpu gpu, const struct pl_tex_transfer_params *params
 
 bool pl_tex_upload(pl_gpu gpu, const struct pl_tex_transfer_params *params)
 {
+    DEV_GUARD(gpu);
     pl_rect3d rc;
     size_t row_pitch;
     if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_upload"))
@@ -855,12 +927,18 @@ bool pl_tex_upload(pl_gpu gpu, const struct pl_tex_transfer_params *params)
         pair[0] = (void *) params->callback;
         pair[1] = params->priv;
         ok = CK(gpu, cudaLaunchHostFunc(s, host_cb_trampoline, pair));
+    } else if (ok && !params->buf) {
+        // gpu.h:885-888: without a callback the caller may reuse or free `ptr` on return. The
+        // copy from pinned memory is a DMA still in flight here, so wait for it (pageable
+        // memory was staged by the driver already). Pass a callback for asynchronous uploads.
+        ok = CK(gpu, cudaStreamSynchronize(s));
     }
     return ok;
 }
 
 bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
 {
+    DEV_GUARD(gpu);
     pl_rect3d rc;
     size_t row_pitch;
     if (!fix_transfer(gpu, params, &rc, &row_pitch, "pl_tex_download"))
@@ -902,6 +980,7 @@ bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
 
 bool pl_tex_poll(pl_gpu gpu, pl_tex tex, uint64_t timeout)
 {
+    DEV_GUARD(gpu);
     (void) tex;
     if (timeout) {
         CK(gpu, cudaStreamSynchronize(STREAM(gpu)));
@@ -916,6 +995,7 @@ bool pl_tex_poll(pl_gpu gpu, pl_tex tex, uint64_t timeout)
 
 pl_buf pl_buf_create(pl_gpu gpu, const struct pl_buf_params *params)
 {
+    DEV_GUARD(gpu);
     if (!params || !params->size) {
         PLB_ERR(gpu->log, "pl_buf_create: zero-sized buffer");
         return NULL;
@@ -964,6 +1044,7 @@ error:
 
 void pl_buf_destroy(pl_gpu gpu, pl_buf *pbuf)
 {
+    DEV_GUARD(gpu);
     if (!pbuf || !*pbuf)
         return;
     struct plb_buf *b = (struct plb_buf *) *pbuf;
@@ -988,6 +1069,7 @@ bool pl_buf_recreate(pl_gpu gpu, pl_buf *buf, const struct pl_buf_params *params
 
 void pl_buf_write(pl_gpu gpu, pl_buf buf, size_t buf_offset, const void *data, size_t size)
 {
+    DEV_GUARD(gpu);
     struct plb_buf *b = (struct plb_buf *) buf;
     if (buf_offset + size > buf->params.size) {
         PLB_ERR(gpu->log, "pl_buf_write: out of bounds");
@@ -1007,6 +1089,7 @@ void pl_buf_write(pl_gpu gpu, pl_buf buf, size_t buf_offset, const void *data, s
 
 bool pl_buf_read(pl_gpu gpu, pl_buf buf, size_t buf_offset, void *dest, size_t size)
 {
+    DEV_GUARD(gpu);
     struct plb_buf *b = (struct plb_buf *) buf;
     if (buf_offset + size > buf->params.size) {
         PLB_ERR(gpu->log, "pl_buf_read: out of bounds");
@@ -1023,6 +1106,7 @@ bool pl_buf_read(pl_gpu gpu, pl_buf buf, size_t buf_offset, void *dest, size_t s
 void pl_buf_copy(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset,
                  size_t size)
 {
+    DEV_GUARD(gpu);
     struct plb_buf *d = (struct plb_buf *) dst, *s = (struct plb_buf *) src;
     void *dp = (char *) (d->dptr ? d->dptr : d->hptr) + dst_offset;
     const void *sp = (const char *) (s->dptr ? s->dptr : s->hptr) + src_offset;
@@ -1043,6 +1127,7 @@ __global__ void k_swap_words(const uint32_t *src, uint32_t *dst, size_t nwords, 
 bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset,
                        size_t size, int wordsize)
 {
+    DEV_GUARD(gpu);
     struct plb_buf *d = (struct plb_buf *) dst, *s = (struct plb_buf *) src;
     if ((wordsize != 2 && wordsize != 4) || size % 4 || dst_offset % 4 || src_offset % 4 ||
         !d->dptr || !s->dptr || src_offset + size > s->pub.params.size ||
@@ -1062,6 +1147,7 @@ bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, si
 
 bool pl_buf_poll(pl_gpu gpu, pl_buf buf, uint64_t timeout)
 {
+    DEV_GUARD(gpu);
     return pl_tex_poll(gpu, NULL, timeout) && buf;
 }
 
@@ -1076,6 +1162,7 @@ struct pl_timer_t {
 
 pl_timer pl_timer_create(pl_gpu gpu)
 {
+    DEV_GUARD(gpu);
     struct pl_timer_t *t = (struct pl_timer_t *) calloc(1, sizeof(*t));
     if (!CK(gpu, cudaEventCreate(&t->start)) || !CK(gpu, cudaEventCreate(&t->stop))) {
         free(t);
@@ -1086,6 +1173,7 @@ pl_timer pl_timer_create(pl_gpu gpu)
 
 void pl_timer_destroy(pl_gpu gpu, pl_timer *pt)
 {
+    DEV_GUARD(gpu);
     (void) gpu;
     if (!pt || !*pt)
         return;
@@ -1097,12 +1185,14 @@ void pl_timer_destroy(pl_gpu gpu, pl_timer *pt)
 
 void plb_timer_begin(pl_gpu gpu, pl_timer t)
 {
+    DEV_GUARD(gpu);
     if (t)
         CK(gpu, cudaEventRecord(t->start, STREAM(gpu)));
 }
 
 void plb_timer_end(pl_gpu gpu, pl_timer t)
 {
+    DEV_GUARD(gpu);
     if (t) {
         CK(gpu, cudaEventRecord(t->stop, STREAM(gpu)));
         t->recorded = true;
@@ -1111,6 +1201,7 @@ void plb_timer_end(pl_gpu gpu, pl_timer t)
 
 void plb_timer_wait(pl_gpu gpu, pl_timer t)
 {
+    DEV_GUARD(gpu);
     if (t && t->recorded)
         CK(gpu, cudaEventSynchronize(t->stop));
 }
@@ -1118,6 +1209,7 @@ void plb_timer_wait(pl_gpu gpu, pl_timer t)
 // nanoseconds of the last recorded interval, 0 if not available yet
 uint64_t pl_timer_query(pl_gpu gpu, pl_timer t)
 {
+    DEV_GUARD(gpu);
     (void) gpu;
     if (!t || !t->recorded)
         return 0;

@@ -130,6 +130,7 @@ bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, si
                        size_t size, int wordsize);
 bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size);
 bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size);
+bool plb_dev_copy(pl_gpu gpu, void *dst, const void *src, size_t size);
 
 // ---------------------------------------------------------------------------------------
 // Colour op program: the typed replacement of the GLSL text a pl_shader accumulates.

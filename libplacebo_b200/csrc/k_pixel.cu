@@ -254,14 +254,9 @@ k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
         for (int k = 0; k < 3; k++)
             c[k] -= a.delin.b;
 
-        if (a.n_mid) {
-            #pragma unroll 1
-            for (int i = 0; i < a.n_mid; i++)
-                plb_light_step(a.light[i], a.light[i].kind, c);
-        }
         if (a.has_dither)
             plb_dither(a.dither, gx, gy, c);
-        if (a.fold_post) {
+        {
             if (a.has_post_scale) {
                 c[0] *= a.post_scale; c[1] *= a.post_scale; c[2] *= a.post_scale;
                 if (a.post_scale_alpha)
@@ -276,16 +271,17 @@ k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
                 if (a.swz_force_alpha)
                     c[3] = o3;
             }
-        } else {
-            #pragma unroll 1
-            for (int i = 0; i < a.n_post; i++)
-                plb_light_step(a.light[a.n_mid + i], a.light[a.n_mid + i].kind, c);
         }
         const int ox = a.dst_x0 + gx, oy = a.dst_y0 + gy;
         if (a.dst.kind == PLB_FK_UNORM8 && a.dst.comps == 4) {
             *(uint32_t *) ((char *) a.dst.ptr + (size_t) oy * a.dst.pitch + (size_t) ox * 4) =
                 plb_unorm(c[0], 255.0f) | (plb_unorm(c[1], 255.0f) << 8) |
                 (plb_unorm(c[2], 255.0f) << 16) | (plb_unorm(c[3], 255.0f) << 24);
+        } else if (a.dst.kind == PLB_FK_UNORM16 && a.dst.comps == 4) {
+            uint2 v;
+            v.x = plb_unorm(c[0], 65535.0f) | (plb_unorm(c[1], 65535.0f) << 16);
+            v.y = plb_unorm(c[2], 65535.0f) | (plb_unorm(c[3], 65535.0f) << 16);
+            *(uint2 *) ((char *) a.dst.ptr + (size_t) oy * a.dst.pitch + (size_t) ox * 8) = v;
         } else {
             plb_store(a.dst, ox, oy, make_float4(c[0], c[1], c[2], c[3]));
         }
@@ -378,6 +374,10 @@ static bool pixel_hdr_args(pl_gpu gpu, const struct plb_pixel_launch *p, const p
             *h = f;
         }
     }
+    // anything else between delinearize and the target (encode matrices, permutations, alpha
+    // conversions) takes the general kernel: this one keeps the colour in registers throughout
+    if (h->n_mid || h->n_post || !h->fold_post)
+        return false;
     h->src = pl.tex;
     h->dst = p->dst;
     h->dst_x0 = p->dst_rect.x0;

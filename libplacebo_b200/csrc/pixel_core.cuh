@@ -361,8 +361,8 @@ PLB_DEV void plb_sample_plane_simple_t(const plb_plane_src &pl, const plb_coord 
     out[0] = c4.x; out[1] = c4.y; out[2] = c4.z; out[3] = c4.w;
     if (pl.kind == PLB_PLANE_DEBAND)
         plb_deband<FAST>(pl, cc, posx, posy, gx, gy, frame_index, out);
-    else if (pl.kind == PLB_PLANE_GRAIN_AV1)
-        plb_grain_av1(pl, gx, gy, out);
+    else if (pl.kind == PLB_PLANE_GRAIN_AV1) // overhanging invocations: the edge pixel's value
+        plb_grain_av1(pl, min(gx, pl.tex.w - 1), min(gy, pl.tex.h - 1), out);
 }
 
 PLB_DEV void plb_sample_plane_simple(const plb_plane_src &pl, const plb_coord &cc, int gx, int gy,
@@ -401,7 +401,9 @@ PLB_DEV void plb_sample_plane(const plb_plane_src &pl, const plb_coord &cc, int 
         return;
     }
     if (pl.kind == PLB_PLANE_GRAIN_AV1) {
-        plb_grain_av1(pl, gx, gy, out);
+        // invocations beyond the plane (work-group overhang, counted by peak detection) take the
+        // edge pixel's value, as if the grain pass had gone through an FBO sampled with clamping
+        plb_grain_av1(pl, min(gx, pl.tex.w - 1), min(gy, pl.tex.h - 1), out);
         #pragma unroll
         for (int k = 0; k < 4; k++)
             out[k] *= pl.scale; // the renderer's "tmp = vec4(scale) * sub()"

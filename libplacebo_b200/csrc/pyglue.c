@@ -254,12 +254,17 @@ API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
 
 // Host -> device copy of one frame into ring slot `slot` (asynchronous on the gpu's stream;
 // the host buffers must stay valid until plg_finish or a later synchronising call).
+static void noop_cb(void *priv) { (void) priv; }
+
+// Asynchronous uploads (a callback makes pl_tex_upload non-blocking, gpu.h:879-896): the host
+// planes must stay valid until plg_finish (bench.py keeps a ring of pinned frames).
 API int plg_upload(struct plg_stream *s, int slot, const void *y, const void *u, const void *v)
 {
     const void *ptr[3] = { y, u, v };
     for (int i = 0; i < 3; i++) {
         if (!pl_tex_upload(s->gpu, pl_tex_transfer_params( .tex = s->planes[slot][i],
-                                                           .ptr = (void *) ptr[i] )))
+                                                           .ptr = (void *) ptr[i],
+                                                           .callback = noop_cb )))
             return -1;
     }
     return 0;
@@ -278,8 +283,6 @@ API int plg_render(struct plg_stream *s, int slot, int out_slot, int frame_index
         return -1;
     return (int) pl_renderer_get_errors(s->rr).errors;
 }
-
-static void noop_cb(void *priv) { (void) priv; }
 
 // Asynchronous download (a callback makes pl_tex_download non-blocking, gpu.h:879-910): `host`
 // must stay valid until plg_finish / plg_join + stream synchronisation.
@@ -303,6 +306,18 @@ API int plg_measure_peak(struct plg_stream *s, int slot, int frame_index,
     if (s->image.film_grain.type)
         s->image.film_grain.seed = (uint64_t) (frame_index >= 0 ? frame_index + 1 : 1);
     return pl_renderer_measure_peak(s->rr, &s->image, &s->params, out_buf) ? 0 : -1;
+}
+
+// asynchronous variant: statistics are copied into `dev_buf` (device memory) on the gpu's stream
+API int plg_measure_peak_dev(struct plg_stream *s, int slot, int frame_index, void *dev_buf)
+{
+    for (int i = 0; i < 3; i++)
+        s->image.planes[i].texture = s->planes[slot][i];
+    if (frame_index >= 0)
+        pl_renderer_set_frame_index(s->rr, (uint8_t) frame_index);
+    if (s->image.film_grain.type)
+        s->image.film_grain.seed = (uint64_t) (frame_index >= 0 ? frame_index + 1 : 1);
+    return pl_renderer_measure_peak_dev(s->rr, &s->image, &s->params, dev_buf) ? 0 : -1;
 }
 
 API int plg_peak_update(struct plg_stream *s, float state[2], const void *buf, int *scene_change)

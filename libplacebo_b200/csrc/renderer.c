@@ -53,17 +53,28 @@ struct pl_renderer_t {
     // Frame-parallel mode: pl_renderer_measure_peak materialises the merged source pass (the
     // rgba16hf image the sequential same-frame flow would also produce) and the very next
     // pl_render_image of the same planes continues from it instead of redoing the pass.
-    struct {
+    // Several frames may be measured ahead of their render (the multi-GPU pipeline keeps the next
+    // frame's measurement in flight while the statistics of the current one are exchanged).
+    struct measured_image {
         bool valid;
+        uint64_t seq;               // measurement counter when stored (stale entries expire)
         pl_tex tex;                 // one of rr->fbos, kept reserved while valid
         pl_tex planes[4];
-        const struct pl_render_params *params;
+        // everything that determines the stored image: a later pl_render_image only continues
+        // from it when all of this matches
+        struct pl_render_params params;
+        const struct pl_render_params *params_ptr;
+        pl_rect2df crop;
+        struct pl_color_repr in_repr;
+        struct pl_color_space in_color;
+        struct pl_film_grain_data grain;
         uint8_t frame_index;
         int w, h, comps;
         pl_rect2df rect, ref_rect;
         struct pl_color_repr repr;
         struct pl_color_space color;
-    } measured;
+    } measured[4];
+    uint64_t measure_seq;
 };
 
 static void free_views(pl_renderer rr)
@@ -1400,27 +1411,53 @@ static bool pass_begin(struct pass_state *pass)
     return true;
 }
 
-static void reserve_measured_fbo(pl_renderer rr)
+#define MEASURED_SLOTS 4
+
+// keep the FBOs of all pending measured images out of the pool
+static void reserve_measured_fbos(pl_renderer rr)
 {
-    for (int i = 0; rr->measured.valid && i < MAX_FBOS; i++) {
-        if (rr->fbos[i] == rr->measured.tex)
-            rr->fbo_used[i] = true;
+    for (int m = 0; m < MEASURED_SLOTS; m++) {
+        if (!rr->measured[m].valid)
+            continue;
+        if (rr->measure_seq - rr->measured[m].seq >= MEASURED_SLOTS) { // never consumed
+            rr->measured[m].valid = false;
+            continue;
+        }
+        for (int i = 0; i < MAX_FBOS; i++) {
+            if (rr->fbos[i] == rr->measured[m].tex)
+                rr->fbo_used[i] = true;
+        }
     }
 }
 
-// Does the image of this render call equal the one pl_renderer_measure_peak just processed?
-static bool measured_hit(pl_renderer rr, const struct pass_state *pass)
+// Does the image of this render call equal one pl_renderer_measure_peak has processed? Compares
+// what determines the stored image (planes, crop, representation, colour space, grain, frame
+// index, render parameters by value), not just pointers.
+static struct measured_image *measured_find(pl_renderer rr, const struct pl_frame *image,
+                                            const struct pl_render_params *params)
 {
-    if (!rr->measured.valid || !rr->have_peak_override || rr->measured.params != pass->params)
-        return false;
-    if (rr->have_frame_index && rr->measured.frame_index != rr->frame_index)
-        return false;
-    for (int i = 0; i < 4; i++) {
-        pl_tex t = i < pass->image.num_planes ? pass->image.planes[i].texture : NULL;
-        if (t != rr->measured.planes[i])
-            return false;
+    if (!rr->have_peak_override)
+        return NULL;
+    for (int m = 0; m < MEASURED_SLOTS; m++) {
+        struct measured_image *mi = &rr->measured[m];
+        if (!mi->valid || mi->params_ptr != params || memcmp(&mi->params, params, sizeof(*params)))
+            continue;
+        if (rr->have_frame_index && mi->frame_index != rr->frame_index)
+            continue;
+        bool same = true;
+        for (int i = 0; i < 4; i++) {
+            pl_tex t = i < image->num_planes ? image->planes[i].texture : NULL;
+            same &= t == mi->planes[i];
+        }
+        same = same && !memcmp(&mi->crop, &image->crop, sizeof(mi->crop)) &&
+               pl_color_repr_equal(&mi->in_repr, &image->repr) &&
+               pl_color_space_equal(&mi->in_color, &image->color) &&
+               mi->grain.type == image->film_grain.type &&
+               (!mi->grain.type || !memcmp(&mi->grain, &image->film_grain, sizeof(mi->grain)));
+        if (same)
+            return mi;
     }
-    return true;
+    return NULL;
 }
 
 bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
@@ -1445,22 +1482,23 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
     rr->info_index = 0;
     pl_dispatch_callback(rr->dp, rr, params->info_callback ? renderer_info_cb : NULL);
     bool ok;
-    if (measured_hit(rr, &pass)) {
-        reserve_measured_fbo(rr);
+    reserve_measured_fbos(rr);
+    struct measured_image *mi = measured_find(rr, pimage, params);
+    if (mi) {
         pass.from_measured = true;
-        pass.tex = rr->measured.tex;
-        pass.w = rr->measured.w;
-        pass.h = rr->measured.h;
-        pass.comps = rr->measured.comps;
-        pass.rect = rr->measured.rect;
-        pass.ref_rect = rr->measured.ref_rect;
-        pass.repr = rr->measured.repr;
-        pass.color = rr->measured.color;
+        pass.tex = mi->tex;
+        pass.w = mi->w;
+        pass.h = mi->h;
+        pass.comps = mi->comps;
+        pass.rect = mi->rect;
+        pass.ref_rect = mi->ref_rect;
+        pass.repr = mi->repr;
+        pass.color = mi->color;
+        mi->valid = false; // single use (its FBO stays reserved for this frame)
         ok = true;
     } else {
         ok = pass_read_image(&pass);
     }
-    rr->measured.valid = false; // single use
     ok = ok && pass_scale_main(&pass) && pass_convert_colors(&pass) && pass_output_target(&pass);
     rr->info_params = NULL;
     free_views(rr);
@@ -1473,13 +1511,24 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
 
 // Phase 1 of the frame-parallel scheme: run the path up to (and including) the peak detection
 // tap, keep only the raw statistics
-bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
-                              const struct pl_render_params *params, void *out_peak_buf)
+static bool measure_peak(pl_renderer rr, const struct pl_frame *pimage,
+                         const struct pl_render_params *params, void *out_peak_buf, bool to_device)
 {
     params = params ? params : &pl_render_default_params;
     if (!params->peak_detect_params) {
         PLB_ERR(rr->log, "pl_renderer_measure_peak: peak_detect_params required");
         return false;
+    }
+    if (!pimage || !pimage->num_planes || !pimage->planes[0].texture || !out_peak_buf) {
+        PLB_ERR(rr->log, "pl_renderer_measure_peak: image with at least one plane and an output "
+                "buffer are required");
+        return false;
+    }
+    for (int i = 0; i < pimage->num_planes; i++) {
+        if (!pimage->planes[i].texture) {
+            PLB_ERR(rr->log, "pl_renderer_measure_peak: plane %d has no texture", i);
+            return false;
+        }
     }
     // a dummy target of the same size/space as the image: only its colour space matters
     struct pl_frame target = {
@@ -1518,6 +1567,8 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
     else
         pl_dispatch_reset_frame(rr->dp);
     memset(rr->fbo_used, 0, sizeof(rr->fbo_used));
+    rr->measure_seq++;
+    reserve_measured_fbos(rr); // images measured earlier and not rendered yet stay intact
     rr->info_params = params; // the measuring passes are reported like pl_render_image's
     rr->info_index = 0;
     pl_dispatch_callback(rr->dp, rr, params->info_callback ? renderer_info_cb : NULL);
@@ -1529,27 +1580,43 @@ bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
         goto done;
     // statistics + the image itself (rgba16hf FBO, exactly what the sequential same-frame flow
     // stores between its two passes): the following pl_render_image continues from it
-    rr->measured.valid = false;
     ok = img_tex(&pass) != NULL;
     if (ok) {
         struct plb_peak_state *pk = &rr->tone_map_state->u.cmap.peak;
-        ok = plb_dev_download(rr->gpu, out_peak_buf, pk->dev_buf, PL_PEAK_BUF_SIZE);
+        ok = to_device ? plb_dev_copy(rr->gpu, out_peak_buf, pk->dev_buf, PL_PEAK_BUF_SIZE)
+                       : plb_dev_download(rr->gpu, out_peak_buf, pk->dev_buf, PL_PEAK_BUF_SIZE);
         pk->pending = false;
     }
     if (ok) {
-        rr->measured.valid = true;
-        rr->measured.tex = pass.tex;
+        // the slot of the oldest (or an invalid) entry
+        struct measured_image *mi = &rr->measured[0];
+        for (int m = 0; m < MEASURED_SLOTS; m++) {
+            if (!rr->measured[m].valid) {
+                mi = &rr->measured[m];
+                break;
+            }
+            if (rr->measured[m].seq < mi->seq)
+                mi = &rr->measured[m];
+        }
+        mi->valid = true;
+        mi->seq = rr->measure_seq;
+        mi->tex = pass.tex;
         for (int i = 0; i < 4; i++)
-            rr->measured.planes[i] = i < pimage->num_planes ? pimage->planes[i].texture : NULL;
-        rr->measured.params = params;
-        rr->measured.frame_index = rr->frame_index;
-        rr->measured.w = pass.w;
-        rr->measured.h = pass.h;
-        rr->measured.comps = pass.comps;
-        rr->measured.rect = pass.rect;
-        rr->measured.ref_rect = pass.ref_rect;
-        rr->measured.repr = pass.repr;
-        rr->measured.color = pass.color;
+            mi->planes[i] = i < pimage->num_planes ? pimage->planes[i].texture : NULL;
+        mi->params = *params;
+        mi->params_ptr = params;
+        mi->crop = pimage->crop;
+        mi->in_repr = pimage->repr;
+        mi->in_color = pimage->color;
+        mi->grain = pimage->film_grain;
+        mi->frame_index = rr->frame_index;
+        mi->w = pass.w;
+        mi->h = pass.h;
+        mi->comps = pass.comps;
+        mi->rect = pass.rect;
+        mi->ref_rect = pass.ref_rect;
+        mi->repr = pass.repr;
+        mi->color = pass.color;
     }
 done:
     rr->info_params = NULL;
@@ -1557,4 +1624,18 @@ done:
     free_views(rr);
     rr->have_peak_override = had_override;
     return ok;
+}
+
+bool pl_renderer_measure_peak(pl_renderer rr, const struct pl_frame *pimage,
+                              const struct pl_render_params *params, void *out_peak_buf)
+{
+    return measure_peak(rr, pimage, params, out_peak_buf, false);
+}
+
+// The same, but the statistics stay on the device: `dev_peak_buf` (PL_PEAK_BUF_SIZE bytes of
+// device memory) is filled by an asynchronous copy on the gpu's stream, the host does not wait.
+bool pl_renderer_measure_peak_dev(pl_renderer rr, const struct pl_frame *pimage,
+                                  const struct pl_render_params *params, void *dev_peak_buf)
+{
+    return measure_peak(rr, pimage, params, dev_peak_buf, true);
 }

@@ -61,3 +61,72 @@ class PeakExchange:
         self.state = last
         self.st.set_peak(mine)
         self.st.render(slot, out_slot, frame_index=frame_index)
+
+
+class PeakPipeline:
+    """The same scheme with the host latency hidden (CUDA ranks, NCCL): while the statistics of
+    frame i are all-gathered on a side stream and replayed on the host, the GPU already measures
+    frame i+1 on the library's stream; only the few-hundred-byte exchange is ever waited for,
+    never the render queue.
+
+        pipe = PeakPipeline(stream, dist, rank, world, ring)
+        for i in range(n): pipe.render(i)          # frame i of this rank, slot = i % ring
+        pipe.drain()
+
+    `before_measure(j)` (optional) runs right before frame j is measured — bench.py uploads the
+    frame's planes there in its end-to-end mode."""
+
+    def __init__(self, stream, dist, rank, world, ring, before_measure=None):
+        import torch
+        self.st, self.dist, self.rank, self.world, self.ring = stream, dist, rank, world, ring
+        self.torch = torch
+        self.before = before_measure
+        self.state = (0.0, 0.0)
+        self.main = torch.cuda.ExternalStream(stream.cuda_stream)
+        self.side = torch.cuda.Stream()
+        n = PEAK_BUF_SIZE // 4
+        self.send = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(2)]
+        self.recv = [torch.zeros(world * n, dtype=torch.int32, device="cuda") for _ in range(2)]
+        self.host = [torch.zeros(world * n, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.ev_meas = [torch.cuda.Event() for _ in range(2)]
+        self.ev_xchg = [torch.cuda.Event() for _ in range(2)]
+        self.inflight = None   # index of the frame whose measurement / exchange is in flight
+
+    def _frame_index(self, i):
+        return (i * self.world + self.rank) % 256
+
+    def _submit(self, i):
+        b = i & 1
+        if self.before is not None:
+            self.before(i)
+        self.st.measure_peak_dev(i % self.ring, self._frame_index(i), self.send[b].data_ptr())
+        self.ev_meas[b].record(self.main)
+        with self.torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_meas[b])
+            self.dist.all_gather_into_tensor(self.recv[b], self.send[b])
+            self.host[b].copy_(self.recv[b], non_blocking=True)
+            self.ev_xchg[b].record(self.side)
+        self.inflight = i
+
+    def render(self, i, out_slot=None, last=False):
+        if self.inflight != i:
+            self._submit(i)
+        b = i & 1
+        if not last:
+            self._submit(i + 1)          # the GPU has work while the host waits below
+            self.inflight = i + 1
+        else:
+            self.inflight = None
+        self.ev_xchg[b].synchronize()     # waits for the exchange of frame i only
+        allb = self.host[b].numpy().view(np.uint32).reshape(self.world, -1)
+        mine, last_state = replay(self.st.peak_update, self.state, [allb[r] for r in range(self.world)],
+                                  self.rank)
+        self.state = last_state
+        self.st.set_peak(mine)
+        slot = i % self.ring
+        self.st.render(slot, slot if out_slot is None else out_slot, frame_index=self._frame_index(i))
+
+    def drain(self):
+        """Forget a measurement submitted ahead (its image simply expires in the renderer)."""
+        self.side.synchronize()
+        self.inflight = None

@@ -183,6 +183,12 @@ class Stream:
             raise RuntimeError("pl_renderer_measure_peak failed")
         return buf
 
+    def measure_peak_dev(self, slot, frame_index, dev_ptr):
+        """Asynchronous measure_peak: the statistics are copied to device memory at `dev_ptr`
+        (PEAK_BUF_SIZE bytes) on the library's stream; nothing waits on the host."""
+        if self.lib.plg_measure_peak_dev(self.h, slot, frame_index, C.c_void_p(dev_ptr)):
+            raise RuntimeError("pl_renderer_measure_peak_dev failed")
+
     def peak_update(self, state, buf):
         st = np.array(state, np.float32)
         used = self.lib.plg_peak_update(self.h, C.c_void_p(_ptr(st)), C.c_void_p(_ptr(buf)), None)
