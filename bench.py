@@ -85,6 +85,31 @@ def pin_openmp():
     return n
 
 
+def numa_pin(local_rank):
+    """Run this rank on the CPUs local to its GPU (pinned staging memory is then allocated on the
+    GPU's NUMA node: host->device copies do not cross the socket interconnect). Returns the
+    previous affinity, or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                              str(local_rank)], capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return prev
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def workload_config(wl_name, world):
     """The `config` object: identical in both arms."""
     from libplacebo_b200 import stream as S
@@ -293,6 +318,8 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
                                     before_measure=lambda j: st.upload(j % ring, *host_in[j % ring])
                                     if e2e_mode[0] else None)
 
+    uploaded = [-1]  # end-to-end mode: index of the newest frame whose upload has been enqueued
+
     def frame(i, e2e, last=False):
         slot = i % ring
         if par is not None:
@@ -300,7 +327,15 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
             par.render(i, last=last)
         else:
             if e2e:
-                st.upload(slot, *host_in[slot])
+                # Like a player, upload the NEXT frame before rendering this one: pl_render_image
+                # waits on the host for this frame's peak statistics (same-frame peak detection),
+                # and the copy engine should not idle meanwhile. One upload per step.
+                if uploaded[0] < i:
+                    st.upload(slot, *host_in[slot])
+                    uploaded[0] = i
+                if not last and uploaded[0] < i + 1:
+                    st.upload((i + 1) % ring, *host_in[(i + 1) % ring])
+                    uploaded[0] = i + 1
             st.render(slot, slot, frame_index=i % 256)
         if e2e:
             st.download(slot, host_out[i % 2])
@@ -316,6 +351,7 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
         if collect:
             st.collect(True)
         l0 = st.launch_count()
+        uploaded[0] = -1
         ev0.record(lib_stream)
         for i in range(n):
             frame(i, e2e, last=i == n - 1)
@@ -348,6 +384,7 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
     res = {"wl": wl, "ring": ring, "in_bytes": in_bytes, "out_bytes": out_bytes, "ms": ms,
            "launches": launches, "passes": passes, "clocks": clk.summary(), "steps": steps}
     if with_e2e:
+        uploaded[0] = -1
         for i in range(3):
             frame(i, True, last=i == 2)
         st.finish()
@@ -426,6 +463,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; libplacebo_b200 has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    prev_affinity = numa_pin(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -444,6 +482,8 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)  # the CPU arm below uses every core again
     if rank != 0:
         return
 

@@ -918,8 +918,12 @@ bool pl_tex_upload(pl_gpu gpu, const struct pl_tex_transfer_params *params)
         plb_gpu_after_use(gpu, &one, 1);
     } else {
         s = xfer_begin(gpu, t, true);
-        ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, params->ptr, row_pitch, wbytes,
-                                       rc.y1 - rc.y0, cudaMemcpyHostToDevice, s));
+        if (row_pitch == wbytes && t->d.pitch == wbytes) // contiguous on both sides: one linear DMA
+            ok = CK(gpu, cudaMemcpyAsync(dst, params->ptr, wbytes * (size_t) (rc.y1 - rc.y0),
+                                         cudaMemcpyHostToDevice, s));
+        else
+            ok = CK(gpu, cudaMemcpy2DAsync(dst, t->d.pitch, params->ptr, row_pitch, wbytes,
+                                           rc.y1 - rc.y0, cudaMemcpyHostToDevice, s));
         ok = ok && xfer_end(gpu, t, s);
     }
     if (ok && params->callback) {
@@ -960,8 +964,12 @@ bool pl_tex_download(pl_gpu gpu, const struct pl_tex_transfer_params *params)
         plb_gpu_after_use(gpu, &one, 1);
     } else {
         s = xfer_begin(gpu, t, false);
-        ok = CK(gpu, cudaMemcpy2DAsync(params->ptr, row_pitch, src, t->d.pitch, wbytes,
-                                       rc.y1 - rc.y0, cudaMemcpyDeviceToHost, s));
+        if (row_pitch == wbytes && t->d.pitch == wbytes)
+            ok = CK(gpu, cudaMemcpyAsync(params->ptr, src, wbytes * (size_t) (rc.y1 - rc.y0),
+                                         cudaMemcpyDeviceToHost, s));
+        else
+            ok = CK(gpu, cudaMemcpy2DAsync(params->ptr, row_pitch, src, t->d.pitch, wbytes,
+                                           rc.y1 - rc.y0, cudaMemcpyDeviceToHost, s));
         ok = ok && xfer_end(gpu, t, s);
     }
     if (!ok)

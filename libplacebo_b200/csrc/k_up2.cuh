@@ -43,7 +43,14 @@ PLB_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 // Source layouts with a dedicated loader (launch-uniform; 0 = any, through plb_load_clamped)
-enum { UP2_SRC_ANY = 0, UP2_SRC_HALF4 = 1, UP2_SRC_HALF2 = 2 };
+enum { UP2_SRC_ANY = 0, UP2_SRC_HALF4 = 1, UP2_SRC_HALF2 = 2, UP2_SRC_R16X2 = 3 /* planar pair of r16 */ };
+
+// the generic fetch is large (run-time format / address-mode dispatch): out of line, so that the
+// tile loader of the hot layouts stays small
+static __device__ __noinline__ float4 up2_load_any(const plb_tex_desc &t, int x, int y)
+{
+    return plb_load_clamped(t, x, y);
+}
 
 template <int NC, int MODE>
 constexpr int up2_smem_bytes()
@@ -96,7 +103,7 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
             plb_tail_stage(a.tail);
     }
 
-    const bool interior = SRC != UP2_SRC_ANY && a.use_tma && col0 >= 0 && row0 >= 0 &&
+    const bool interior = a.use_tma && col0 >= 0 && row0 >= 0 &&
                           col0 + UP2_TILE_W <= a.src.w && row0 + UP2_TILE_H <= a.src.h;
     if (interior) {
         if (tid == 0) {
@@ -138,8 +145,13 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                 const int x = plb_clampi(col0 + c, 0, a.src.w - 1), y = plb_clampi(row0 + r, 0, a.src.h - 1);
                 const float2 f = __half22float2(*(const __half2 *) ((const char *) a.src.ptr + (size_t) y * a.src.pitch + (size_t) x * 4));
                 v = make_float4(f.x, f.y, 0.0f, 1.0f);
+            } else if (SRC == UP2_SRC_R16X2) {
+                const int x = plb_clampi(col0 + c, 0, a.src.w - 1), y = plb_clampi(row0 + r, 0, a.src.h - 1);
+                const unsigned u0 = *(const uint16_t *) ((const char *) a.src.ptr + (size_t) y * a.src.pitch + 2 * x);
+                const unsigned u1 = *(const uint16_t *) ((const char *) a.src.ptr2 + (size_t) y * a.src.pitch2 + 2 * x);
+                v = make_float4(plb_unorm16_to_float(u0), plb_unorm16_to_float(u1), 0.0f, 1.0f);
             } else {
-                v = plb_load_clamped(a.src, col0 + c, row0 + r);
+                v = up2_load_any(a.src, col0 + c, row0 + r);
             }
             tile[0][r][c] = v.x;
             if (NC > 1) tile[1 % NC][r][c] = v.y;
@@ -198,10 +210,10 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
     }
 
     if (PURE) {
+        // Canonical light pass (host-checked, launch_up2): the NC results go to colour[base ..
+        // base + NC), optionally one directly sampled r16 luma plane to colour[0]; the colour
+        // program is [matrix] [scale] [identity swizzle], folded into flags; vector stores.
         const plb_tail_args &t = a.tail;
-        // launch-uniform: the usual identity component mapping needs no per-pixel selects
-        const bool ident = t.src_map[0] == 0 && (NC < 2 || t.src_map[1] == 1) &&
-                           (NC < 3 || t.src_map[2] == 2) && (NC < 4 || t.src_map[3] == 3);
         const int gx = X0 + tx * UP2_OX;
         if (gx >= t.out_w)
             return;
@@ -212,64 +224,62 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                 continue;
             #pragma unroll
             for (int half = 0; half < UP2_OX / 4; half++) {
+                const int gxh = gx + 4 * half;
                 float col[4][4];
+                float luma[4] = { t.init[0], t.init[0], t.init[0], t.init[0] };
+                if (a.ep_luma) {
+                    // four consecutive texels of the r16 plane (gxh % 4 == 0: one 8-byte load)
+                    const plb_plane_src &pl = t.planes[0];
+                    const uint16_t *row = (const uint16_t *) ((const char *) pl.tex.ptr + (size_t) gy * pl.tex.pitch);
+                    if (gxh + 4 <= pl.tex.w) {
+                        const uint2 raw = *(const uint2 *) (row + gxh);
+                        luma[0] = plb_unorm16_to_float(raw.x & 0xFFFFu) * pl.scale;
+                        luma[1] = plb_unorm16_to_float(raw.x >> 16) * pl.scale;
+                        luma[2] = plb_unorm16_to_float(raw.y & 0xFFFFu) * pl.scale;
+                        luma[3] = plb_unorm16_to_float(raw.y >> 16) * pl.scale;
+                    } else {
+                        #pragma unroll
+                        for (int p = 0; p < 4; p++)
+                            luma[p] = plb_unorm16_to_float(row[min(gxh + p, pl.tex.w - 1)]) * pl.scale;
+                    }
+                }
                 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     const float norm = a.norm[oyo][p & 1];
-                    float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
-                    #pragma unroll
-                    for (int k = 0; k < NC; k++)
-                        prim[k] = norm * acc[oyo][4 * half + p][k];
                     #pragma unroll
                     for (int j = 0; j < 4; j++)
                         col[p][j] = t.init[j];
-                    if (ident) {
+                    if (a.ep_base) { // chroma pair next to a luma plane
+                        col[p][0] = luma[p];
                         #pragma unroll
-                        for (int k = 0; k < NC; k++)
-                            col[p][k] = prim[k];
+                        for (int k = 0; k < NC && k < 3; k++)
+                            col[p][1 + k] = norm * acc[oyo][4 * half + p][k];
                     } else {
                         #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int m = t.src_map[k];
-                            #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                col[p][j] = m == j ? prim[k] : col[p][j];
+                        for (int k = 0; k < NC; k++)
+                            col[p][k] = norm * acc[oyo][4 * half + p][k];
+                    }
+                    if (a.ep_has_mat) {
+                        plb_matv(a.ep_mat, col[p][0], col[p][1], col[p][2]);
+                        if (a.ep_mat_has_c) {
+                            col[p][0] += a.ep_mat_c[0]; col[p][1] += a.ep_mat_c[1]; col[p][2] += a.ep_mat_c[2];
                         }
                     }
-                }
-                const int gxh = gx + 4 * half;
-                // directly sampled extra planes (e.g. the luma plane next to EWA-scaled chroma)
-                #pragma unroll 1
-                for (int i = 0; i < t.nplanes; i++) {
-                    const plb_plane_src &pl = t.planes[i];
-                    const plb_coord &cc = t.plane_cc[i];
-                    const bool direct = cc.ident; // texel centres: bilinear == the texel
-                    const float sc = pl.scale;
-                    int8_t map[4];
-                    #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        map[k] = pl.map[k];
-                    #pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        float4 c4;
-                        if (direct) {
-                            c4 = plb_load_clamped(pl.tex, gxh + p, gy);
-                        } else {
-                            float posx, posy;
-                            plb_coord_pos(cc, gxh + p, gy, posx, posy);
-                            c4 = pl.linear ? plb_tex_linear(pl.tex, posx, posy)
-                                           : plb_tex_nearest(pl.tex, posx, posy);
-                        }
-                        const float tmp[4] = { c4.x * sc, c4.y * sc, c4.z * sc, c4.w * sc };
-                        #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                col[p][j] = map[k] == j ? tmp[k] : col[p][j];
-                        }
+                    if (a.ep_has_scale) {
+                        col[p][0] *= a.ep_scale; col[p][1] *= a.ep_scale; col[p][2] *= a.ep_scale;
+                        if (a.ep_scale_alpha)
+                            col[p][3] *= a.ep_scale;
+                    }
+                    if (a.ep_has_swz) {
+                        const float o3 = col[p][3];
+                        if (!(a.ep_swz_keep & 1)) col[p][0] = 0.0f;
+                        if (!(a.ep_swz_keep & 2)) col[p][1] = 0.0f;
+                        if (!(a.ep_swz_keep & 4)) col[p][2] = 0.0f;
+                        if (!(a.ep_swz_keep & 8)) col[p][3] = 1.0f;
+                        if (a.ep_swz_force_alpha)
+                            col[p][3] = o3;
                     }
                 }
-                plb_run_light_ops_n<4>(t.prog, col);
                 float4 px4[4];
                 #pragma unroll
                 for (int p = 0; p < 4; p++)
@@ -455,7 +465,9 @@ static void launch_up2_m(pl_gpu gpu, dim3 grid, dim3 block, polar_up2_args &args
 {
     // dedicated loaders (and TMA for interior tiles) for the two FBO layouts of the hot path
     const plb_tex_desc &s = args.src;
-    args.src_kind = s.ptr2 || s.addr ? UP2_SRC_ANY
+    args.src_kind = s.addr ? UP2_SRC_ANY
+                  : (s.ptr2 && s.kind == PLB_FK_UNORM16 && NC == 2) ? UP2_SRC_R16X2
+                  : s.ptr2 ? UP2_SRC_ANY
                   : (s.kind == PLB_FK_HALF && s.comps == 4) ? UP2_SRC_HALF4
                   : (s.kind == PLB_FK_HALF && s.comps == 2 && NC <= 2) ? UP2_SRC_HALF2 : UP2_SRC_ANY;
     static int tma_on = -1; // PLB_UP2_TMA=0: manual loader everywhere (A/B measurements)
@@ -465,7 +477,7 @@ static void launch_up2_m(pl_gpu gpu, dim3 grid, dim3 block, polar_up2_args &args
     }
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    args.use_tma = args.src_kind != UP2_SRC_ANY && tma_on &&
+    args.use_tma = (args.src_kind == UP2_SRC_HALF4 || args.src_kind == UP2_SRC_HALF2) && tma_on &&
                    make_tile_map(&map, s, args.src_kind == UP2_SRC_HALF4 ? 8 : 4);
     constexpr int smem = up2_smem_bytes<NC, MODE>();
     static bool attr_set; // per instantiation; the attribute is per function and device-wide
@@ -483,16 +495,61 @@ static bool launch_up2(pl_gpu gpu, polar_up2_args &args)
     dim3 block(UP2_TX, UP2_TY);
     // the tile is a whole number of peak work groups, so this also covers overhanging ones
     dim3 grid((args.tail.out_w + UP2_TW - 1) / UP2_TW, (args.tail.out_h + UP2_TH - 1) / UP2_TH);
-    // light pass: only directly sampled planes to merge and at most a "light" colour program
-    bool light = true;
-    for (int i = 0; i < args.tail.prog.n; i++) {
-        const int k = args.tail.prog.ops[i].kind;
-        light &= k == PLB_OP_SCALE || k == PLB_OP_MATRIX || k == PLB_OP_ROUND_FBO ||
-                 k == PLB_OP_ALPHA || k == PLB_OP_SWIZZLE;
+    // canonical light pass (MODE 1, see the kernel): results -> colour[base .. base + NC), at most
+    // one directly sampled r16 luma plane -> colour[0], program = [matrix] [scale] [identity swizzle]
+    bool pure = args.tail.dst.ptr != NULL;
+    {
+        const plb_tail_args &tl = args.tail;
+        int base = -1;
+        for (int b0 = 0; b0 < 2 && base < 0; b0++) {
+            bool m = b0 + NC <= 4;
+            for (int k = 0; k < 4; k++)
+                m &= tl.src_map[k] == (k < NC ? b0 + k : -1);
+            if (m)
+                base = b0;
+        }
+        pure &= base >= 0 && tl.nplanes <= 1 && (base == 0 ? tl.nplanes == 0 : true);
+        if (pure && tl.nplanes == 1) {
+            const plb_plane_src &pl = tl.planes[0];
+            pure = base == 1 && pl.kind == PLB_PLANE_DIRECT && tl.plane_cc[0].ident &&
+                   pl.tex.kind == PLB_FK_UNORM16 && pl.tex.comps == 1 && !pl.tex.ptr2 && !pl.tex.addr &&
+                   !((uintptr_t) pl.tex.ptr & 7) && !(pl.tex.pitch & 7) &&
+                   pl.map[0] == 0 && pl.map[1] < 0 && pl.map[2] < 0 && pl.map[3] < 0;
+            args.ep_luma = pure;
+        } else if (pure && base == 1) {
+            pure = false; // chroma without its luma plane: general tail
+        }
+        args.ep_base = base == 1;
+        int i = 0;
+        if (pure && i < tl.prog.n && tl.prog.ops[i].kind == PLB_OP_MATRIX) {
+            args.ep_has_mat = 1;
+            memcpy(args.ep_mat, tl.prog.ops[i].u.matrix.m, sizeof(args.ep_mat));
+            memcpy(args.ep_mat_c, tl.prog.ops[i].u.matrix.c, sizeof(args.ep_mat_c));
+            args.ep_mat_has_c = tl.prog.ops[i].u.matrix.has_c;
+            i++;
+        }
+        if (pure && i < tl.prog.n && tl.prog.ops[i].kind == PLB_OP_SCALE) {
+            args.ep_has_scale = 1;
+            args.ep_scale = tl.prog.ops[i].u.scale.s;
+            args.ep_scale_alpha = tl.prog.ops[i].u.scale.with_alpha;
+            i++;
+        }
+        if (pure && i < tl.prog.n && tl.prog.ops[i].kind == PLB_OP_SWIZZLE) {
+            const plb_color_op &op = tl.prog.ops[i];
+            args.ep_has_swz = 1;
+            args.ep_swz_force_alpha = op.u.swizzle.force_alpha;
+            for (int k = 0; k < 4; k++) {
+                const int m = op.u.swizzle.map[k];
+                const int sel = (k < op.u.swizzle.comps && m >= 0) ? m : -1;
+                if (sel == k)
+                    args.ep_swz_keep |= 1 << k;
+                else if (sel >= 0)
+                    pure = false; // a real permutation
+            }
+            i++;
+        }
+        pure &= i == tl.prog.n;
     }
-    for (int i = 0; i < args.tail.nplanes; i++)
-        light &= args.tail.planes[i].kind == PLB_PLANE_DIRECT;
-    const bool pure = light && args.tail.dst.ptr;
     // canonical merged YUV 4:2:0 plane pass (MODE 2, see the kernel): EWA chroma -> colour[1..2],
     // one r16 luma plane (direct 1:1 / debanded / AV1-grained) -> colour[0], program = MATRIX
     // [PEAK on PQ], rgba16hf target; not in exact-math mode (static curves)
