@@ -258,6 +258,11 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                         #pragma unroll
                         for (int k = 0; k < NC; k++)
                             col[p][k] = norm * acc[oyo][4 * half + p][k];
+                        #pragma unroll
+                        for (int k = NC; k < 4; k++) { // unsampled components mapped onto the colour
+                            if (a.ep_fill & (1 << k))
+                                col[p][k] = k == 3 ? 1.0f : 0.0f;
+                        }
                     }
                     if (a.ep_has_mat) {
                         plb_matv(a.ep_mat, col[p][0], col[p][1], col[p][2]);
@@ -500,13 +505,26 @@ static bool launch_up2(pl_gpu gpu, polar_up2_args &args)
     bool pure = args.tail.dst.ptr != NULL;
     {
         const plb_tail_args &tl = args.tail;
+        // component k of the sampler goes to colour[src_map[k]]; components beyond the sampled
+        // ones carry the defaults (0, 0, 0, 1). Accepted: base + k for the sampled ones, and for the
+        // rest "unused" or (base 0 only) the identity, which stores the default into the colour.
         int base = -1;
         for (int b0 = 0; b0 < 2 && base < 0; b0++) {
             bool m = b0 + NC <= 4;
-            for (int k = 0; k < 4; k++)
-                m &= tl.src_map[k] == (k < NC ? b0 + k : -1);
-            if (m)
+            int fill = 0;
+            for (int k = 0; k < 4; k++) {
+                if (k < NC) {
+                    m &= tl.src_map[k] == b0 + k;
+                } else if (tl.src_map[k] == k && b0 == 0) {
+                    fill |= 1 << k;
+                } else {
+                    m &= tl.src_map[k] < 0;
+                }
+            }
+            if (m) {
                 base = b0;
+                args.ep_fill = fill;
+            }
         }
         pure &= base >= 0 && tl.nplanes <= 1 && (base == 0 ? tl.nplanes == 0 : true);
         if (pure && tl.nplanes == 1) {

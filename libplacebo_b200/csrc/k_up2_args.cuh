@@ -19,7 +19,7 @@ struct polar_up2_args {
     int use_tma;            // interior tiles come in through the tensor map
     int src_kind;           // UP2_SRC_*: source layout with a dedicated tile loader
     // folded tail of the canonical light pass (MODE 1)
-    int ep_base, ep_luma;
+    int ep_base, ep_luma, ep_fill;
     int ep_has_mat, ep_mat_has_c; float ep_mat[9], ep_mat_c[3];
     int ep_has_scale, ep_scale_alpha; float ep_scale;
     int ep_has_swz, ep_swz_keep, ep_swz_force_alpha;
