@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--workload", default="c3_4k_hdr10_to_sdr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads and parity")
+    ap.add_argument("--c5-lanes", type=int, default=8, help="frames in flight per GPU for config C5 (0 = skip)")
     return ap.parse_args()
 
 
@@ -407,6 +408,77 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
     return res
 
 
+def measure_lanes(cx, wl_name, lanes, frames_per_lane):
+    """Config C5: error diffusion is a serial wavefront (ONE thread block per frame, w + (h-1) *
+    shift barrier steps), so a single frame cannot fill the GPU; throughput comes from frames in
+    flight. `lanes` independent pl_gpu + pl_renderer pairs on this rank's device (one CUDA stream
+    each) render different frames concurrently: the single-block passes of some frames overlap
+    the wide passes of others. Device-timed from a common start event to the last lane's end."""
+    from libplacebo_b200 import stream as S
+    torch, rank, local_rank = cx.torch, cx.rank, cx.local_rank
+    wl = S.WORKLOADS[wl_name]
+    sw, sh = wl["src"]
+    y, u, v = S.synth_yuv420p10(sw, sh, seed=rank)
+    pin = [torch.from_numpy(p).pin_memory() for p in (y, u, v)]
+    sts = []
+    try:
+        for _ in range(lanes):
+            st = S.Stream(device=local_rank).configure(wl, ring=1)
+            st.upload(0, *pin)
+            sts.append(st)
+        for st in sts:
+            st.finish()
+        ext = [torch.cuda.ExternalStream(st.cuda_stream, device=local_rank) for st in sts]
+
+        def run(nl, nf):
+            for st in sts[:nl]:   # warm-up: allocates the FBOs, builds the LUTs
+                st.render(0, 0, frame_index=0)
+            for st in sts[:nl]:
+                st.finish()
+            if cx.dist is not None:
+                cx.dist.barrier()
+            torch.cuda.synchronize()
+            l0 = sum(st.launch_count() for st in sts[:nl])
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record(ext[0])
+            for f in range(nf):
+                for st in sts[:nl]:
+                    st.render(0, 0, frame_index=(f + 1) % 256)
+            ends = []
+            for e in ext[:nl]:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(e)
+                ends.append(ev)
+            for st in sts[:nl]:
+                st.finish()
+            torch.cuda.synchronize()
+            ms = max(ev0.elapsed_time(ev) for ev in ends)
+            if cx.dist is not None:
+                t = torch.tensor([ms], device="cuda")
+                cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, sum(st.launch_count() for st in sts[:nl]) - l0
+
+        ms1, _ = run(1, 2)
+        msn, launches = run(lanes, frames_per_lane)
+    finally:
+        for st in sts:
+            st.close()
+    steps_per_frame = wl["dst"][0] + (wl["dst"][1] - 1) * 2  # sierra-lite: shift 2
+    fps1 = cx.world * 2 / (ms1 / 1e3)
+    fpsn = cx.world * lanes * frames_per_lane / (msn / 1e3)
+    return {"value": round(fpsn, 2), "unit": "frames/s", "frames_in_flight_per_gpu": lanes,
+            "frames_per_lane": frames_per_lane, "ms_total": round(msn, 2),
+            "one_frame_at_a_time": {"value": round(fps1, 2), "unit": "frames/s",
+                                    "ms_per_frame": round(ms1 / 2, 2)},
+            "error_diffusion_steps_per_frame": steps_per_frame,
+            "column_steps_per_s": round(fpsn * steps_per_frame, 0),
+            "gpu_launches": launches,
+            "config": dict(workload_config(wl_name, cx.world), lanes=lanes),
+            "note": "latency-bound: the error-diffusion pass is one thread block per frame; frames in "
+                    "flight are the unit of parallelism (SURVEY.md 8e: not shardable within a frame)"}
+
+
 def roofline_of(res, wl_name, hbm_peak):
     plist = []
     for cnt, ns, desc in res["passes"]:
@@ -479,6 +551,12 @@ def run_ours(args, rank, world, local_rank):
         for name in EXTRA:
             if name != args.workload:
                 extras[name] = measure(cx, name, min(steps, 100), warmup)
+    c5 = None
+    if not args.no_extra and args.c5_lanes > 0:
+        try:
+            c5 = measure_lanes(cx, "c5_8k_dovi_errdiff", args.c5_lanes, 3)
+        except Exception as e:  # noqa: BLE001
+            c5 = {"error": str(e)}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -541,6 +619,8 @@ def run_ours(args, rank, world, local_rank):
             d = summarise(name, r)
             d["config"] = dict(workload_config(name, world), l2=d.pop("l2"))
             line["extra_workloads"][name] = d
+    if c5 is not None:
+        line.setdefault("extra_workloads", {})["c5_8k_dovi_errdiff"] = c5
     if world == 1 and not args.no_cpu_baseline:
         try:
             t1, cores = cpu_frames(args.workload, 1, warm=1)

@@ -147,7 +147,7 @@ enum {
     O_SRC_SYS, O_SRC_LEVELS, O_SRC_SAMPLE_DEPTH, O_SRC_COLOR_DEPTH, O_SRC_BIT_SHIFT,
     O_DST_SYS, O_DST_LEVELS, O_DST_SAMPLE_DEPTH, O_DST_COLOR_DEPTH,
     O_CHROMA_LOC, O_DEBAND, O_PEAK, O_ALLOW_DELAYED, O_DITHER, O_CMAP_HQ, O_RING,
-    O_TONE_FN, O_GAMUT_FN, O_GRAIN, O_COUNT
+    O_TONE_FN, O_GAMUT_FN, O_GRAIN, O_DOVI, O_ERRDIFF, O_COUNT
 };
 
 // AV1 grain parameters of libplacebo's own test fixture (src/tests/utils.h:240-262): medium
@@ -174,6 +174,53 @@ static struct pl_av1_grain_data demo_av1_grain(bool overlap)
 }
 
 // Returns 0 on success. `iopts` follows the enum above; formats by name ("r16", "rgba8", ...)
+// Dolby Vision RPU data with the shape of a profile-5 stream: 8-piece polynomial luma reshaping,
+// order-3 MMR chroma (the values are those of libplacebo's own test fixture, src/tests/utils.h:
+// 279-323), with non-trivial YCC -> RGB / RGB -> LMS matrices and offsets.
+static const struct pl_dovi_metadata *demo_dovi(void)
+{
+    static struct pl_dovi_metadata m;
+    static bool init;
+    if (!init) {
+        m = (struct pl_dovi_metadata) {
+            .nonlinear_offset = { 0.0625f, 0.5f, 0.5f },
+            .nonlinear = {{{1.0f, 0.0f, 1.5f}, {1.0f, -0.17f, -0.58f}, {1.0f, 1.88f, 0.0f}}},
+            .linear = {{{0.95f, 0.04f, 0.01f}, {0.02f, 0.96f, 0.02f}, {0.0f, 0.03f, 0.97f}}},
+            .comp = {
+                {
+                    .num_pivots = 9,
+                    .pivots = {0.0615835786, 0.129032254, 0.353861183, 0.604105592, 0.854349971,
+                               0.890518069, 0.906158328, 0.913978517, 0.92082113},
+                    .poly_coeffs = {
+                        {-0.0488376617, 1.99335372, -2.41716385}, {-0.0141925812, 1.61829138, -1.53397191},
+                        {0.157061458, 0.63640213, -0.11302495}, {0.25272119, 0.246226311, 0.27281332},
+                        {0.951621532, -1.35507894, 1.18898678}, {6.41251612, -13.6188488, 8.07336903},
+                        {13.467535, -29.1869125, 16.6612244}, {28.2321472, -61.8516273, 34.7264938},
+                    },
+                }, {
+                    .num_pivots = 2, .pivots = {0.0, 1.0}, .method = {1}, .mmr_order = {3},
+                    .mmr_constant = {-0.500733018},
+                    .mmr_coeffs = {{
+                        {1.08411026, 3.80807829, 0.0881733894, -3.23097038, -0.409078479, -1.31310081, 2.71297002},
+                        {-0.241833091, -3.57880807, -0.108109117, 3.13198471, 0.869203091, 1.96561158, -9.30871677},
+                        {-0.177356839, 1.48970401, 0.0908923149, -0.510447979, -0.687603354, -0.934977889, 12.3544884},
+                    }},
+                }, {
+                    .num_pivots = 2, .pivots = {0.0, 1.0}, .method = {1}, .mmr_order = {3},
+                    .mmr_constant = {-1.23833287},
+                    .mmr_coeffs = {{
+                        {3.52909589, 0.383154511, 5.50820637, -1.02094889, -6.36386824, 0.194121242, 0.64683497},
+                        {-2.57899785, -0.626081586, -6.05729723, 2.29143763, 9.14653015, -0.0507702827, -4.17724133},
+                        {0.705404401, 0.341412306, 2.98387456, -1.71712542, -4.91501331, 0.1465137, 6.38665438},
+                    }},
+                },
+            },
+        };
+        init = true;
+    }
+    return &m;
+}
+
 API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
                       const float *dst_csp, const char *plane_fmt, const char *dst_fmt,
                       const char *upscaler, const char *plane_upscaler)
@@ -213,6 +260,10 @@ API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
             .texture = s->planes[0][i], .components = 1, .component_mapping = { i } };
     }
     pl_frame_set_chroma_location(&s->image, o[O_CHROMA_LOC] ? o[O_CHROMA_LOC] : PL_CHROMA_LEFT);
+    if (o[O_DOVI]) {
+        s->image.repr.sys = PL_COLOR_SYSTEM_DOLBYVISION;
+        s->image.repr.dovi = demo_dovi();
+    }
     if (o[O_GRAIN]) {
         s->image.film_grain.type = PL_FILM_GRAIN_AV1;
         s->image.film_grain.params.av1 = demo_av1_grain(o[O_GRAIN] > 1);
@@ -246,6 +297,7 @@ API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
         .peak_detect_params = o[O_PEAK] ? &s->peak : NULL,
         .dither_params = o[O_DITHER] ? &s->dither : NULL,
         .color_map_params = &s->cmap,
+        .error_diffusion = o[O_ERRDIFF] ? pl_error_diffusion_kernels[o[O_ERRDIFF] - 1] : NULL,
         .info_callback = info_cb,
         .info_priv = s,
     };

@@ -24,7 +24,10 @@ CHROMA = dict(left=1, center=2, top_left=3)
 _OPT_ORDER = ["src_w", "src_h", "chroma_w", "chroma_h", "dst_w", "dst_h", "src_sys", "src_levels",
               "src_sample_depth", "src_color_depth", "src_bit_shift", "dst_sys", "dst_levels",
               "dst_sample_depth", "dst_color_depth", "chroma_loc", "deband", "peak",
-              "allow_delayed", "dither", "cmap_hq", "ring", "tone_fn", "gamut_fn", "grain"]
+              "allow_delayed", "dither", "cmap_hq", "ring", "tone_fn", "gamut_fn", "grain", "dovi", "errdiff"]
+# pl_error_diffusion_kernels[] order (dither.c)
+ERRDIFF = ["simple", "false-fs", "sierra-lite", "floyd-steinberg", "atkinson", "jarvis-judice-ninke",
+           "stucki", "burkes", "sierra-2", "sierra-3"]
 _FMT_DTYPE = {"rgba8": (np.uint8, 4), "rgba16": (np.uint16, 4), "rgba16hf": (np.uint16, 4),
               "rgba32f": (np.float32, 4)}
 
@@ -60,6 +63,14 @@ WORKLOADS = {
         src_sys="BT_2020_NC", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
         dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
         upscaler="ewa_lanczos", opts=dict(deband=1, peak=2, dither=1, cmap_hq=1, grain=2)),
+    "c5_8k_dovi_errdiff": dict(
+        desc="8K YUV420P10 Dolby Vision (8-piece polynomial luma + order-3 MMR chroma reshaping, RPU "
+             "matrices) PQ BT.2020 -> 8K rgba8 BT.709: EWA-Lanczos chroma upscale + spline tone map + "
+             "perceptual gamut map + sierra-lite error diffusion to 8 bits",
+        src=(7680, 4320), dst=(7680, 4320), dst_fmt="rgba8",
+        src_sys="BT_2020_NC", src_levels="FULL", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
+        dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
+        upscaler="ewa_lanczos", opts=dict(dither=1, cmap_hq=1, dovi=1, errdiff=ERRDIFF.index("sierra-lite") + 1)),
     # reduced-size C3 for the CPU-only contract tests of bench.py (not a benchmark configuration)
     "test_c3_480x270": dict(
         desc="config C3 at 480x270 (bench.py contract tests)",
@@ -118,11 +129,12 @@ class Stream:
         """`wl`: a WORKLOADS entry (or equivalent dict)."""
         o = dict(src_w=wl["src"][0], src_h=wl["src"][1], chroma_w=wl["src"][0] // 2,
                  chroma_h=wl["src"][1] // 2, dst_w=wl["dst"][0], dst_h=wl["dst"][1],
-                 src_sys=SYS[wl["src_sys"]], src_levels=LEVELS["LIMITED"], src_sample_depth=16,
+                 src_sys=SYS[wl["src_sys"]], src_levels=LEVELS[wl.get("src_levels", "LIMITED")],
+                 src_sample_depth=16,
                  src_color_depth=10, src_bit_shift=0, dst_sys=SYS["RGB"], dst_levels=LEVELS["FULL"],
                  dst_sample_depth=wl["dst_depth"], dst_color_depth=wl["dst_depth"],
                  chroma_loc=CHROMA["left"], deband=0, peak=0, allow_delayed=0, dither=0,
-                 cmap_hq=0, ring=ring, tone_fn=0, gamut_fn=0, grain=0)
+                 cmap_hq=0, ring=ring, tone_fn=0, gamut_fn=0, grain=0, dovi=0, errdiff=0)
         o.update(wl.get("opts", {}))
         o.update(over)
         arr = np.array([o[k] for k in _OPT_ORDER], np.int32)

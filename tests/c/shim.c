@@ -449,6 +449,10 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
             .component_mapping = { 0, 1, 2 },
         };
     }
+    if (opts[14]) { /* Dolby Vision: the reference's dovi_meta fixture, variant opts[14] - 1 */
+        image.repr.sys = PL_COLOR_SYSTEM_DOLBYVISION;
+        image.repr.dovi = shim_dovi_fixture(opts[14] - 1);
+    }
     if (opts[12] == 3) {
         /* the reference's H.274 fixture (src/tests/utils.h:263-277): luma only */
         static const uint8_t lo = 10, hi = 250;

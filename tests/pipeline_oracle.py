@@ -39,8 +39,9 @@ def luma_coeffs(t0, prim):
 
 class Frame:
     def __init__(self, planes, sys, levels=T.LEVELS["LIMITED"], sample_depth=16, color_depth=10,
-                 bit_shift=0, csp=None, chroma_loc="left"):
+                 bit_shift=0, csp=None, chroma_loc="left", dovi=None):
         self.planes = planes
+        self.dovi = dovi  # Dolby Vision: variant of the reference's dovi_meta fixture (0 / 1)
         self.sys, self.levels = sys, levels
         self.bits = (sample_depth, color_depth, bit_shift)
         self.csp = csp if csp is not None else T.csp()
@@ -152,7 +153,10 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     tdepth = {"rgba8": 8, "rgba16": 16}.get(tgt.fmt, 0)
     tbits = fix_bits(tdepth, tgt.bits)
 
-    norm = t0.repr_decode(img.sys, img.levels, *sbits)["scale"]  # pl_color_repr_normalize
+    # pl_color_repr_normalize depends on the bit depths only (a Dolby Vision repr needs its
+    # metadata for anything else, so ask with a neutral system)
+    norm_sys = T.SYS["BT_2020_NC"] if img.dovi is not None else img.sys
+    norm = t0.repr_decode(norm_sys, img.levels, *sbits)["scale"]  # pl_color_repr_normalize
     ycbcr = img.sys not in (T.SYS["UNKNOWN"], T.SYS["RGB"], T.SYS["XYZ"])
     limited = (img.levels or (T.LEVELS["LIMITED"] if ycbcr else T.LEVELS["FULL"])) == T.LEVELS["LIMITED"]
     out_scale = f32(2.0 ** sbits[0]) / (f32(2.0 ** sbits[0]) - f32(1.0))
@@ -254,10 +258,23 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     color[..., 1] = chroma[..., 0]
     color[..., 2] = chroma[..., 1]
     color[..., 3] = 1.0
-    dec = t0.repr_decode(img.sys, img.levels, sbits[0], sbits[0], 0)  # repr already normalised
-    color = orc.apply_matrix(color, dec["m"], dec["c"])
-    if img.sys in (T.SYS["BT_2020_C"], T.SYS["BT_2100_PQ"], T.SYS["BT_2100_HLG"]):
-        color = orc.decode_special(color, img.sys)
+    if img.dovi is not None:
+        # pl_shader_decode_color for PL_COLOR_SYSTEM_DOLBYVISION (colorspace.c:285-310, 392-422):
+        # residual scale of the normalised repr, reshape, RPU matrix + offsets, PQ EOTF, LMS -> RGB,
+        # PQ OETF
+        meta = T.dovi_fixture(img.dovi)
+        d = t0.repr_decode_dovi(sbits[0], sbits[0], list(meta.nonlinear_offset), list(meta.nonlinear),
+                                list(meta.linear))
+        if float(d["scale"]) != 1.0:
+            color = orc.scale(color, float(d["scale"]), with_alpha=False)
+        color = orc.dovi_reshape(color, meta)
+        color = orc.apply_matrix(color, d["m"], d["c"])
+        color = orc.dovi_lms(color, d["lms2rgb"])
+    else:
+        dec = t0.repr_decode(img.sys, img.levels, sbits[0], sbits[0], 0)  # repr already normalised
+        color = orc.apply_matrix(color, dec["m"], dec["c"])
+        if img.sys in (T.SYS["BT_2020_C"], T.SYS["BT_2100_PQ"], T.SYS["BT_2100_HLG"]):
+            color = orc.decode_special(color, img.sys)
 
     src_trc = int(src_csp[1])
     src_hdr = src_csp[11] > 203.0 or src_trc in (T.TRC["PQ"], T.TRC["HLG"], T.TRC["V_LOG"],

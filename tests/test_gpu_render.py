@@ -33,6 +33,8 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
                 opts[12], opts[13] = 3, grain[0]
             else:
                 opts[12], opts[13] = 2 if grain[1] else 1, grain[0]
+        if getattr(img, "dovi", None) is not None:
+            opts[14] = img.dovi + 1
         opts[9] = T.TONE_FNS.index(tone_fn) + 1 if tone_fn else 0
         opts[10] = T.GAMUT_FNS.index(gamut_fn) + 1 if gamut_fn else 0
         peak_out = np.zeros(2, T.f32)
@@ -167,3 +169,21 @@ def test_render_with_error_diffusion(gpu, kernel):
     got, _ = gpu_render(gpu, img, tgt, dither=1, error_diffusion=kernel)
     want, _ = P.render(img, tgt, dither=1, error_diffusion=kernel)
     assert np.array_equal(got[..., :3], want[..., :3]), np.mean(got[..., :3] != want[..., :3])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_c5_dolby_vision_gamut_error_diffusion_pipeline(gpu, variant):
+    """Config C5 at reduced size, as ONE pipeline: Dolby Vision profile-5-style source (reshaping
+    curves + RPU matrices of the reference's dovi_meta fixture), EWA chroma upscale, perceptual
+    gamut mapping / tone mapping to BT.709, error diffusion (sierra-lite) to 8 bits."""
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(320, 180, seed=31 + variant)
+    img = P.Frame(planes, T.SYS["DOLBYVISION"], levels=T.LEVELS["FULL"], csp=HDR10, dovi=variant)
+    tgt = P.Target(320, 180, "rgba8", sample_depth=8, color_depth=8, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", dither=1, cmap_hq=True, error_diffusion="sierra-lite")
+    got, _ = gpu_render(gpu, img, tgt, **kw)
+    want, _ = P.render(img, tgt, **kw)
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    # stated tolerance: +-1 LSB of the output; error diffusion propagates any difference, so the
+    # achieved result must be (and is) identical
+    assert d.max() == 0, (int(d.max()), float(np.mean(d > 0)))
