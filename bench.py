@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--workload", default="c3_4k_hdr10_to_sdr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads and parity")
-    ap.add_argument("--c5-lanes", type=int, default=8, help="frames in flight per GPU for config C5 (0 = skip)")
+    ap.add_argument("--c5-lanes", type=int, default=16, help="frames in flight per GPU for config C5 (0 = skip)")
     return ap.parse_args()
 
 
@@ -554,7 +554,7 @@ def run_ours(args, rank, world, local_rank):
     c5 = None
     if not args.no_extra and args.c5_lanes > 0:
         try:
-            c5 = measure_lanes(cx, "c5_8k_dovi_errdiff", args.c5_lanes, 3)
+            c5 = measure_lanes(cx, "c5_8k_dovi_errdiff", args.c5_lanes, 2)
         except Exception as e:  # noqa: BLE001
             c5 = {"error": str(e)}
     if dist is not None:

@@ -62,45 +62,6 @@ PL_API void pl_transform3x3_scale(pl_transform3x3 *t, float scale);
 PL_API void pl_transform3x3_invert(pl_transform3x3 *t);
 typedef int pl_rotation;
 enum { PL_ROTATION_0 = 0, PL_ROTATION_90 = 1, PL_ROTATION_180 = 2, PL_ROTATION_270 = 3, PL_ROTATION_360 = 4 };
-// common.h:117-240 — crop helpers callers use to fill pl_frame.crop: ordering, rounding, aspect
-// ratio with pan & scan, fitting one rect into another, centred scaling, offset, quarter turns
-PL_API void pl_rect2d_normalize(pl_rect2d *rc);
-PL_API void pl_rect3d_normalize(pl_rect3d *rc);
-PL_API void pl_rect2df_normalize(pl_rect2df *rc);
-PL_API void pl_rect3df_normalize(pl_rect3df *rc);
-PL_API pl_rect2d pl_rect2df_round(const pl_rect2df *rc);
-PL_API pl_rect3d pl_rect3df_round(const pl_rect3df *rc);
-PL_API float pl_rect2df_aspect(const pl_rect2df *rc);
-PL_API void pl_rect2df_aspect_set(pl_rect2df *rc, float aspect, float panscan);
-#define pl_rect2df_aspect_copy(rc, src, panscan) \
-    pl_rect2df_aspect_set((rc), pl_rect2df_aspect(src), (panscan))
-PL_API void pl_rect2df_aspect_fit(pl_rect2df *rc, const pl_rect2df *src, float panscan);
-PL_API void pl_rect2df_stretch(pl_rect2df *rc, float stretch_x, float stretch_y);
-#define pl_rect2df_zoom(rc, zoom) pl_rect2df_stretch((rc), (zoom), (zoom))
-PL_API void pl_rect2df_offset(pl_rect2df *rc, float offset_x, float offset_y);
-PL_API void pl_rect2df_rotate(pl_rect2df *rc, pl_rotation rot);
-// common.h:64-116 — 2x2 matrices / affine transforms (rotation and offset of sampling rects) and the
-// rect forms of the 3x3 ones
-typedef struct pl_matrix2x2 { float m[2][2]; } pl_matrix2x2;
-typedef struct pl_transform2x2 { pl_matrix2x2 mat; float c[2]; } pl_transform2x2;
-PL_API extern const pl_matrix2x2 pl_matrix2x2_identity;
-PL_API extern const pl_transform2x2 pl_transform2x2_identity;
-PL_API pl_matrix2x2 pl_matrix2x2_rotation(float angle);
-PL_API void pl_matrix2x2_apply(const pl_matrix2x2 *mat, float vec[2]);
-PL_API void pl_matrix2x2_apply_rc(const pl_matrix2x2 *mat, pl_rect2df *rc);
-PL_API void pl_matrix2x2_mul(pl_matrix2x2 *a, const pl_matrix2x2 *b);
-PL_API void pl_matrix2x2_rmul(const pl_matrix2x2 *a, pl_matrix2x2 *b);
-PL_API void pl_matrix2x2_scale(pl_matrix2x2 *mat, float scale);
-PL_API void pl_matrix2x2_invert(pl_matrix2x2 *mat);
-PL_API void pl_transform2x2_apply(const pl_transform2x2 *t, float vec[2]);
-PL_API void pl_transform2x2_apply_rc(const pl_transform2x2 *t, pl_rect2df *rc);
-PL_API void pl_transform2x2_mul(pl_transform2x2 *a, const pl_transform2x2 *b);
-PL_API void pl_transform2x2_rmul(const pl_transform2x2 *a, pl_transform2x2 *b);
-PL_API void pl_transform2x2_scale(pl_transform2x2 *t, float scale);
-PL_API void pl_transform2x2_invert(pl_transform2x2 *t);
-PL_API pl_rect2df pl_transform2x2_bounds(const pl_transform2x2 *t, const pl_rect2df *rc);
-PL_API void pl_matrix3x3_apply_rc(const pl_matrix3x3 *mat, pl_rect3df *rc);
-PL_API void pl_transform3x3_apply_rc(const pl_transform3x3 *t, pl_rect3df *rc);
 
 /* ---- log.h:26-81 ------------------------------------------------------------------------ */
 enum pl_log_level {
@@ -134,9 +95,6 @@ enum pl_color_system { /* colorspace.h:30-60 */
 };
 PL_API bool pl_color_system_is_ycbcr_like(enum pl_color_system sys);
 // colorspace.h:54-78 — names and the resolution heuristic
-PL_API extern const char *const pl_color_system_names[PL_COLOR_SYSTEM_COUNT];
-PL_API const char *pl_color_system_name(enum pl_color_system sys);
-PL_API enum pl_color_system pl_color_system_guess_ycbcr(int width, int height);
 PL_API bool pl_color_system_is_linear(enum pl_color_system sys);
 enum pl_channel {
     PL_CHANNEL_NONE = -1, PL_CHANNEL_A = 3, PL_CHANNEL_R = 0, PL_CHANNEL_G = 1,
@@ -176,10 +134,6 @@ struct pl_color_repr {
 };
 PL_API bool pl_color_repr_equal(const struct pl_color_repr *c1, const struct pl_color_repr *c2);
 // colorspace.h:176-215 — representation presets, merging (fields set in `orig` win)
-PL_API extern const struct pl_color_repr pl_color_repr_unknown, pl_color_repr_rgb, pl_color_repr_sdtv,
-                                         pl_color_repr_hdtv, pl_color_repr_uhdtv, pl_color_repr_jpeg;
-PL_API void pl_color_repr_merge(struct pl_color_repr *orig, const struct pl_color_repr *update);
-PL_API bool pl_bit_encoding_equal(const struct pl_bit_encoding *b1, const struct pl_bit_encoding *b2);
 PL_API float pl_color_repr_normalize(struct pl_color_repr *repr);
 PL_API enum pl_color_levels pl_color_levels_guess(const struct pl_color_repr *repr);
 
@@ -216,12 +170,6 @@ PL_API bool pl_raw_primaries_similar(const struct pl_raw_primaries *a, const str
 PL_API void pl_raw_primaries_merge(struct pl_raw_primaries *orig, const struct pl_raw_primaries *update);
 PL_API const struct pl_raw_primaries *pl_raw_primaries_get(enum pl_color_primaries prim);
 // colorspace.h:228-258, 262-266 — names, wide-gamut predicate, resolution heuristic
-PL_API extern const char *const pl_color_primaries_names[PL_COLOR_PRIM_COUNT];
-PL_API const char *pl_color_primaries_name(enum pl_color_primaries prim);
-PL_API bool pl_color_primaries_is_wide_gamut(enum pl_color_primaries prim);
-PL_API enum pl_color_primaries pl_color_primaries_guess(int width, int height);
-PL_API extern const char *const pl_color_transfer_names[PL_COLOR_TRC_COUNT];
-PL_API const char *pl_color_transfer_name(enum pl_color_transfer trc);
 
 enum pl_hdr_scaling { PL_HDR_NORM = 0, PL_HDR_SQRT, PL_HDR_NITS, PL_HDR_PQ, PL_HDR_SCALING_COUNT };
 PL_API float pl_hdr_rescale(enum pl_hdr_scaling from, enum pl_hdr_scaling to, float x);
@@ -266,8 +214,6 @@ PL_API bool pl_color_space_is_hdr(const struct pl_color_space *csp);
 PL_API bool pl_color_space_is_black_scaled(const struct pl_color_space *csp);
 // colorspace.h:566-574 — CPU transfer functions (in place, three channels; the same curves the
 // pixel kernels evaluate, here with libm like the reference)
-PL_API void pl_color_linearize(const struct pl_color_space *csp, float color[3]);
-PL_API void pl_color_delinearize(const struct pl_color_space *csp, float color[3]);
 struct pl_nominal_luma_params {
     const struct pl_color_space *color;
     enum pl_hdr_metadata_type metadata;
@@ -301,15 +247,9 @@ enum pl_chroma_location {
 PL_API void pl_chroma_location_offset(enum pl_chroma_location loc, float *x, float *y);
 PL_API pl_matrix3x3 pl_get_rgb2xyz_matrix(const struct pl_raw_primaries *prim);
 PL_API pl_matrix3x3 pl_get_xyz2rgb_matrix(const struct pl_raw_primaries *prim);
-// colorspace.h:615 — white point of a colour temperature (K)
-PL_API struct pl_cie_xy pl_white_from_temp(float temperature);
-// colorspace.h:607-613 — its two ingredients: Planckian locus (1667-25000 K) and CIE daylight
-// (2500-25000 K; both clamp the temperature)
-PL_API struct pl_cie_xy pl_blackbody_from_temp(float temperature);
-PL_API struct pl_cie_xy pl_daylight_from_temp(float temperature);
 
 // colorspace.h:665-709 — colour-vision deficiency model (cone distortion). pl_render_params.
-// cone_params itself is outside the CUDA hot path (rejected); the matrices are T0 host code.
+// cone_params is outside the CUDA hot path (rejected); only the parameter type is declared.
 enum pl_cone {
     PL_CONE_L = 1 << 0, PL_CONE_M = 1 << 1, PL_CONE_S = 1 << 2,
     PL_CONE_NONE = 0,
@@ -321,11 +261,6 @@ struct pl_cone_params {
     float strength;     // 0 = complete loss, 1 = unaffected
 };
 #define pl_cone_params(...) (&(struct pl_cone_params) { __VA_ARGS__ })
-PL_API extern const struct pl_cone_params pl_vision_normal, pl_vision_protanomaly, pl_vision_protanopia,
-    pl_vision_deuteranomaly, pl_vision_deuteranopia, pl_vision_tritanomaly, pl_vision_tritanopia,
-    pl_vision_monochromacy, pl_vision_achromatopsia;
-PL_API pl_matrix3x3 pl_get_cone_matrix(const struct pl_cone_params *params,
-                                       const struct pl_raw_primaries *prim);
 
 PL_API pl_matrix3x3 pl_get_color_mapping_matrix(const struct pl_raw_primaries *src,
                                                 const struct pl_raw_primaries *dst,

@@ -25,11 +25,43 @@ struct errdiff_args {
     int ring_rows, ring_size;
     int ntaps;
     int tap_dividend[EDF_MAX_TAPS];
-    int tap_delta[EDF_MAX_TAPS];   // shifted_x * ring_rows + dy
+    int tap_sx[EDF_MAX_TAPS], tap_dy[EDF_MAX_TAPS]; // shifted column offset (>= 0) and row offset
     int tap_min_x[EDF_MAX_TAPS];   // pixel must satisfy x >= this (errors leaving the left edge)
     int cols;               // shifted columns = w + (h-1)*shift
 };
 
+// texel fetch / store of the usual FBO layout (rgba16hf) without the run-time format dispatch
+template <bool HALF4>
+PLB_DEV float4 edf_load(const plb_tex_desc &t, int x, int y)
+{
+    if (HALF4) {
+        const uint2 raw = *(const uint2 *) ((const char *) t.ptr + (size_t) y * t.pitch + (size_t) x * 8);
+        const float2 lo = __half22float2(*(const __half2 *) &raw.x), hi = __half22float2(*(const __half2 *) &raw.y);
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return plb_load_clamped(t, x, y);
+}
+
+template <bool HALF4>
+PLB_DEV void edf_store(const plb_tex_desc &t, int x, int y, float4 c)
+{
+    if (HALF4) {
+        const __half2 lo = __floats2half2_rn(c.x, c.y), hi = __floats2half2_rn(c.z, c.w);
+        uint2 raw;
+        raw.x = *(const uint32_t *) &lo;
+        raw.y = *(const uint32_t *) &hi;
+        *(uint2 *) ((char *) t.ptr + (size_t) y * t.pitch + (size_t) x * 8) = raw;
+    } else {
+        plb_store(t, x, y, c);
+    }
+}
+
+// Rows are dealt to threads as y = tid + j * blockDim (j < NJ). The ring slot of shifted column
+// xs is xs mod ring_cols, tracked incrementally (no integer division per pixel), and the texels
+// of column xs + 1 are fetched before column xs is processed, so that their global-memory
+// latency overlaps the arithmetic and the shared-memory atomics of the current column.
+#define EDF_NJ 5
+template <bool HALF4>
 __global__ void __launch_bounds__(1024)
 k_errdiff(const __grid_constant__ errdiff_args a)
 {
@@ -40,13 +72,31 @@ k_errdiff(const __grid_constant__ errdiff_args a)
     __syncthreads();
 
     const float fq = (float) a.quant;
+    const int ring_cols = a.ring_size / a.ring_rows;
+    float4 nxt[EDF_NJ];
+    #pragma unroll
+    for (int j = 0; j < EDF_NJ; j++) {
+        const int y = tid + j * nt, x = 0 - y * a.shift;
+        nxt[j] = (y < a.h && x >= 0 && x < a.w) ? edf_load<HALF4>(a.src, x, y) : make_float4(0, 0, 0, 0);
+    }
+    int slot = 0; // xs mod ring_cols
     for (int xs = 0; xs < a.cols; xs++) {
-        for (int y = tid; y < a.h; y += nt) {
+        float4 cur[EDF_NJ];
+        #pragma unroll
+        for (int j = 0; j < EDF_NJ; j++) {
+            cur[j] = nxt[j];
+            const int y = tid + j * nt, x = xs + 1 - y * a.shift;
+            if (y < a.h && x >= 0 && x < a.w && xs + 1 < a.cols)
+                nxt[j] = edf_load<HALF4>(a.src, x, y);
+        }
+        #pragma unroll
+        for (int j = 0; j < EDF_NJ; j++) {
+            const int y = tid + j * nt;
             const int x = xs - y * a.shift;
-            if (x < 0 || x >= a.w)
+            if (y >= a.h || x < 0 || x >= a.w)
                 continue;
-            const uint32_t idx = (uint32_t) (xs * a.ring_rows + y) % (uint32_t) a.ring_size;
-            const float4 po = plb_load_clamped(a.src, x, y);
+            const uint32_t idx = (uint32_t) (slot * a.ring_rows + y);
+            const float4 po = cur[j];
             float pix[3] = { po.x, po.y, po.z };
             const uint32_t e = atomicExch(&err[idx], 0u) + ((128u << 24) | (128u << 12) | 128u);
             const int er = (int) ((e >> 24) & 0xFFu) - 128, eg = (int) ((e >> 12) & 0xFFu) - 128,
@@ -60,7 +110,7 @@ k_errdiff(const __grid_constant__ errdiff_args a)
                 dith[k] = roundf(pix[k]);
                 ed[k] = (pix[k] - dith[k]) * 254.0f / a.divisor;
             }
-            plb_store(a.dst, x, y, make_float4(dith[0] / fq, dith[1] / fq, dith[2] / fq, po.w));
+            edf_store<HALF4>(a.dst, x, y, make_float4(dith[0] / fq, dith[1] / fq, dith[2] / fq, po.w));
             int last = 0;
             uint32_t packed = 0;
             for (int t = 0; t < a.ntaps; t++) {
@@ -72,11 +122,17 @@ k_errdiff(const __grid_constant__ errdiff_args a)
                     packed = ((uint32_t) (tr & 0xFF) << 24) | ((uint32_t) (tg & 0xFF) << 12) |
                              (uint32_t) (tb & 0xFF);
                 }
-                if (x >= a.tap_min_x[t])
-                    atomicAdd(&err[(idx + (uint32_t) a.tap_delta[t]) % (uint32_t) a.ring_size], packed);
+                if (x >= a.tap_min_x[t]) {
+                    int c = slot + a.tap_sx[t]; // tap's column slot, (xs + sx) mod ring_cols
+                    if (c >= ring_cols)
+                        c -= ring_cols;
+                    atomicAdd(&err[c * a.ring_rows + y + a.tap_dy[t]], packed);
+                }
             }
         }
         __syncthreads();
+        if (++slot == ring_cols)
+            slot = 0;
     }
 }
 
@@ -85,7 +141,7 @@ k_errdiff(const __grid_constant__ errdiff_args a)
 extern "C" bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *p)
 {
     struct plb_gpu *g = plb_gpu_priv(gpu);
-    static errdiff_args a;
+    errdiff_args a;
     memset(&a, 0, sizeof(a));
     a.src = p->src;
     a.dst = p->dst;
@@ -108,7 +164,8 @@ extern "C" bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *
                 }
                 const int sx = dx + dy * p->shift;
                 a.tap_dividend[a.ntaps] = dividend;
-                a.tap_delta[a.ntaps] = sx * a.ring_rows + dy;
+                a.tap_sx[a.ntaps] = sx;
+                a.tap_dy[a.ntaps] = dy;
                 a.tap_min_x[a.ntaps] = dx < 0 ? -dx : 0;
                 a.ntaps++;
             }
@@ -127,15 +184,24 @@ extern "C" bool plb_launch_errdiff(pl_gpu gpu, const struct plb_errdiff_launch *
         PLB_ERR(gpu->log, "error diffusion: image too tall for the shared-memory ring (%zu B)", shmem);
         return false;
     }
-    static size_t configured = 0;
-    if (shmem > 48 * 1024 && shmem > configured) {
-        if (!plb_cuda_check(gpu, cudaFuncSetAttribute(k_errdiff, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const bool half4 = a.src.kind == PLB_FK_HALF && a.src.comps == 4 && !a.src.ptr2 &&
+                       a.dst.kind == PLB_FK_HALF && a.dst.comps == 4;
+    if (shmem > 48 * 1024) { // (per function and device; cheap enough to repeat per launch)
+        if (!plb_cuda_check(gpu, cudaFuncSetAttribute(half4 ? k_errdiff<true> : k_errdiff<false>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       (int) shmem), "cudaFuncSetAttribute"))
             return false;
-        configured = shmem;
     }
+    // every thread owns at most EDF_NJ rows
     int threads = PLB_MIN(1024, (p->h + 31) / 32 * 32);
-    k_errdiff<<<1, threads, shmem, STREAM(gpu)>>>(a);
+    if ((p->h + threads - 1) / threads > EDF_NJ) {
+        PLB_ERR(gpu->log, "error diffusion: image too tall (%d rows)", p->h);
+        return false;
+    }
+    if (half4)
+        k_errdiff<true><<<1, threads, shmem, STREAM(gpu)>>>(a);
+    else
+        k_errdiff<false><<<1, threads, shmem, STREAM(gpu)>>>(a);
     g->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_errdiff");
 }

@@ -73,9 +73,15 @@ constexpr int up2_smem_bytes()
 // handles 32 consecutive pixels of a row, so plane fetches and stores are contiguous. Per-pixel
 // arithmetic is that of MODE 0.
 //
-// Thread = 8 x 2 outputs (four source cells) from a 12 x 9 source window: per window row three
-// LDS.128 per component, then the row's taps as FFMAs whose weights are constant-bank operands.
-// 48 accumulators (NC = 3) give the FMA pipe independent work without many resident warps.
+// Thread = 8 x 2 outputs (four source cells) from a 12 x 9 source window. Components are
+// processed in PAIRS with the packed fp32 FMA of sm_100 (FFMA2: two IEEE fmas per instruction,
+// the weight broadcast from a uniform register): NC = 2 -> one FFMA2 per tap, 3 -> FFMA2 + FFMA,
+// 4 -> two FFMA2 — the kernel is bound by instruction fetch / issue, not by the FMA pipe, so
+// halving the instruction stream is what counts; results are bit-identical to scalar fmas.
+// The source tile is staged as float2 planes (component pairs) plus a float plane for an odd
+// component. A float2 row is split into even and odd 16-byte chunks (texel pairs 0-1, 4-5, ...
+// and 2-3, 6-7, ...): thread tx reads chunks 2 tx + q, so within each half consecutive lanes
+// read consecutive 16 bytes (conflict-free LDS.128).
 template <int NC, int XM, int YM, int MODE>
 __global__ void __launch_bounds__(UP2_TX * UP2_TY, 2)
 k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CUtensorMap tmap)
@@ -84,12 +90,26 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
     constexpr bool PURE = MODE == 1;
     constexpr int TW = UP2_TW, TH = UP2_TH;
     constexpr int TILE_BYTES = NC * UP2_TILE_H * UP2_TILE_W * 4;
+    constexpr int NP2 = NC / 2, NP1 = NC & 1;          // float2 planes, float planes
+    constexpr int ROW2 = UP2_TILE_W * 8, HALF2 = ROW2 / 2; // bytes of a float2 row / of its even half
     const int SRC = a.src_kind; // launch-uniform
     // the raw TMA tile is dead once converted; the MODE 2 staging buffer reuses its space
     extern __shared__ __align__(128) unsigned char smem[]; // up2_smem_bytes<NC, MODE>()
     __shared__ __align__(8) uint64_t bar;
-    float (*tile)[UP2_TILE_H][UP2_TILE_W] = (float (*)[UP2_TILE_H][UP2_TILE_W]) smem;
+    unsigned char *tile2 = smem;                                    // [NP2][TILE_H] rows of ROW2 bytes
+    float (*tile1)[UP2_TILE_W] = (float (*)[UP2_TILE_W]) (smem + NP2 * UP2_TILE_H * ROW2); // [TILE_H][TILE_W]
     unsigned char *aux = smem + TILE_BYTES;
+    // texel (r, c) of the tile <- the NC components of v
+    auto put = [&](int r, int c, float4 v) {
+        const int j = c >> 1;
+        unsigned char *row = tile2 + (size_t) r * ROW2 + ((j & 1) ? HALF2 : 0) + (j >> 1) * 16 + (c & 1) * 8;
+        if (NP2 >= 1)
+            *(float2 *) row = make_float2(v.x, v.y);
+        if (NP2 >= 2)
+            *(float2 *) (row + (size_t) UP2_TILE_H * ROW2) = make_float2(v.z, v.w);
+        if (NP1)
+            tile1[r][c] = NC == 1 ? v.x : v.z;
+    };
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * UP2_TX + tx;
     const int X0 = blockIdx.x * TW, Y0 = blockIdx.y * TH;
@@ -120,14 +140,10 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                 const uint2 raw = ((const uint2 *) aux)[i];
                 const float2 lo = __half22float2(*(const __half2 *) &raw.x);
                 const float2 hi = __half22float2(*(const __half2 *) &raw.y);
-                tile[0][r][c] = lo.x;
-                if (NC > 1) tile[1 % NC][r][c] = lo.y;
-                if (NC > 2) tile[2 % NC][r][c] = hi.x;
-                if (NC > 3) tile[3 % NC][r][c] = hi.y;
+                put(r, c, make_float4(lo.x, lo.y, hi.x, hi.y));
             } else {
                 const float2 v = __half22float2(((const __half2 *) aux)[i]);
-                tile[0][r][c] = v.x;
-                if (NC > 1) tile[1 % NC][r][c] = v.y;
+                put(r, c, make_float4(v.x, v.y, 0.0f, 1.0f));
             }
         }
     } else {
@@ -153,39 +169,54 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
             } else {
                 v = up2_load_any(a.src, col0 + c, row0 + r);
             }
-            tile[0][r][c] = v.x;
-            if (NC > 1) tile[1 % NC][r][c] = v.y;
-            if (NC > 2) tile[2 % NC][r][c] = v.z;
-            if (NC > 3) tile[3 % NC][r][c] = v.w;
+            put(r, c, v);
         }
     }
     __syncthreads();
 
-    float acc[UP2_OY][UP2_OX][NC];
+    float2 acc2[UP2_OY][UP2_OX][NP2 ? NP2 : 1];
+    float acc1[UP2_OY][UP2_OX];
     #pragma unroll
     for (int i = 0; i < UP2_OY; i++)
         #pragma unroll
-        for (int j = 0; j < UP2_OX; j++)
+        for (int j = 0; j < UP2_OX; j++) {
             #pragma unroll
-            for (int k = 0; k < NC; k++)
-                acc[i][j][k] = 0.0f;
+            for (int k = 0; k < (NP2 ? NP2 : 1); k++)
+                acc2[i][j][k] = make_float2(0.0f, 0.0f);
+            acc1[i][j] = 0.0f;
+        }
+    // component k of output (i, j)
+#define ACC(i, j, k) ((k) < 2 * NP2 ? (((k) & 1) ? acc2[i][j][(k) >> 1].y : acc2[i][j][(k) >> 1].x) : acc1[i][j])
 
     // thread's source cells: columns i0 = X0/2 + 4*tx (+0..3), row jj = Y0/2 + ty
     // window column wx <-> source column i0 - 4 + wx  (tile column 4*tx + wx)
     // window row    wy <-> source row    jj - 4 + wy  (tile row    ty + wy)
     #pragma unroll
     for (int wy = 0; wy < 9; wy++) {
-        float v[NC][12];
+        float2 v2[NP2 ? NP2 : 1][12];
+        float v1[12];
         #pragma unroll
-        for (int k = 0; k < NC; k++) {
-            const float4 *rowp = (const float4 *) &tile[k][ty + wy][4 * tx];
+        for (int p = 0; p < NP2; p++) {
+            const unsigned char *row = tile2 + (size_t) (p * UP2_TILE_H + ty + wy) * ROW2 + tx * 16;
+            #pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float4 e = *(const float4 *) (row + q * 16);         // texels 4 q, 4 q + 1
+                const float4 o = *(const float4 *) (row + HALF2 + q * 16); // texels 4 q + 2, 4 q + 3
+                v2[p][4 * q] = make_float2(e.x, e.y);
+                v2[p][4 * q + 1] = make_float2(e.z, e.w);
+                v2[p][4 * q + 2] = make_float2(o.x, o.y);
+                v2[p][4 * q + 3] = make_float2(o.z, o.w);
+            }
+        }
+        if (NP1) {
+            const float4 *rowp = (const float4 *) &tile1[ty + wy][4 * tx];
             #pragma unroll
             for (int q = 0; q < 3; q++) {
                 const float4 f = rowp[q];
-                v[k][4 * q] = f.x;
-                v[k][4 * q + 1] = f.y;
-                v[k][4 * q + 2] = f.z;
-                v[k][4 * q + 3] = f.w;
+                v1[4 * q] = f.x;
+                v1[4 * q + 1] = f.y;
+                v1[4 * q + 2] = f.z;
+                v1[4 * q + 3] = f.w;
             }
         }
         #pragma unroll
@@ -201,8 +232,10 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                     if (up2_tap_on<R2_16, XM, YM>(oyo, px, oy, ox)) {
                         const float w = a.w[oyo][px][oy + 3][ox + 3];
                         #pragma unroll
-                        for (int k = 0; k < NC; k++)
-                            acc[oyo][oxo][k] = __fmaf_rn(w, v[k][wx], acc[oyo][oxo][k]);
+                        for (int p = 0; p < NP2; p++)
+                            acc2[oyo][oxo][p] = __ffma2_rn(make_float2(w, w), v2[p][wx], acc2[oyo][oxo][p]);
+                        if (NP1)
+                            acc1[oyo][oxo] = __fmaf_rn(w, v1[wx], acc1[oyo][oxo]);
                     }
                 }
             }
@@ -253,11 +286,11 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                         col[p][0] = luma[p];
                         #pragma unroll
                         for (int k = 0; k < NC && k < 3; k++)
-                            col[p][1 + k] = norm * acc[oyo][4 * half + p][k];
+                            col[p][1 + k] = norm * ACC(oyo, 4 * half + p, k);
                     } else {
                         #pragma unroll
                         for (int k = 0; k < NC; k++)
-                            col[p][k] = norm * acc[oyo][4 * half + p][k];
+                            col[p][k] = norm * ACC(oyo, 4 * half + p, k);
                         #pragma unroll
                         for (int k = NC; k < 4; k++) { // unsampled components mapped onto the colour
                             if (a.ep_fill & (1 << k))
@@ -317,10 +350,10 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
                 #pragma unroll
                 for (int half = 0; half < UP2_OX / 4; half++) {
                     float4 v;
-                    v.x = a.norm[oyo][0] * acc[oyo][4 * half + 0][k];
-                    v.y = a.norm[oyo][1] * acc[oyo][4 * half + 1][k];
-                    v.z = a.norm[oyo][0] * acc[oyo][4 * half + 2][k];
-                    v.w = a.norm[oyo][1] * acc[oyo][4 * half + 3][k];
+                    v.x = a.norm[oyo][0] * ACC(oyo, 4 * half + 0, k);
+                    v.y = a.norm[oyo][1] * ACC(oyo, 4 * half + 1, k);
+                    v.z = a.norm[oyo][0] * ACC(oyo, 4 * half + 2, k);
+                    v.w = a.norm[oyo][1] * ACC(oyo, 4 * half + 3, k);
                     *(float4 *) &stage[k][ty * UP2_OY + oyo][tx * UP2_OX + 4 * half] = v;
                 }
             }
@@ -403,7 +436,7 @@ k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CU
             float prim[4] = {0.0f, 0.0f, 0.0f, 1.0f};
             #pragma unroll
             for (int k = 0; k < NC; k++)
-                prim[k] = norm * acc[oyo][oxo][k];
+                prim[k] = norm * ACC(oyo, oxo, k);
             float color[4];
             uint32_t ypq = 0;
             const plb_op_peak *pk = nullptr;

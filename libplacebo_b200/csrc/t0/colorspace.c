@@ -915,452 +915,3 @@ pl_transform3x3 pl_color_repr_decode(struct pl_color_repr *repr,
     repr->levels = PL_COLOR_LEVELS_FULL;
     return out;
 }
-
-// ---------------------------------------------------------------------------------------
-// Remaining public colorspace.h surface used by the reference's own unit tests
-// (src/tests/colorspace.c): names, resolution heuristics, representation presets, the CPU
-// transfer functions and the cone-distortion matrices. Arithmetic types and operation order
-// follow the reference statement by statement (colorspace.c:76-330, 565-740, 1051-1062,
-// 1398-1540) so that results are bit-identical with the compiled reference
-// (tests/test_t0_parity.py::test_cpu_transfer_functions and friends).
-// ---------------------------------------------------------------------------------------
-
-const char *const pl_color_system_names[PL_COLOR_SYSTEM_COUNT] = {
-    [PL_COLOR_SYSTEM_UNKNOWN]     = "Auto (unknown)",
-    [PL_COLOR_SYSTEM_BT_601]      = "ITU-R Rec. BT.601 (SD)",
-    [PL_COLOR_SYSTEM_BT_709]      = "ITU-R Rec. BT.709 (HD)",
-    [PL_COLOR_SYSTEM_SMPTE_240M]  = "SMPTE-240M",
-    [PL_COLOR_SYSTEM_BT_2020_NC]  = "ITU-R Rec. BT.2020 (non-constant luminance)",
-    [PL_COLOR_SYSTEM_BT_2020_C]   = "ITU-R Rec. BT.2020 (constant luminance)",
-    [PL_COLOR_SYSTEM_BT_2100_PQ]  = "ITU-R Rec. BT.2100 ICtCp PQ variant",
-    [PL_COLOR_SYSTEM_BT_2100_HLG] = "ITU-R Rec. BT.2100 ICtCp HLG variant",
-    [PL_COLOR_SYSTEM_DOLBYVISION] = "Dolby Vision (invalid for output)",
-    [PL_COLOR_SYSTEM_YCGCO]       = "YCgCo (derived from RGB)",
-    [PL_COLOR_SYSTEM_YCGCO_RE]    = "YCgCo-R, even addition of bits",
-    [PL_COLOR_SYSTEM_YCGCO_RO]    = "YCgCo-R, odd addition of bits",
-    [PL_COLOR_SYSTEM_RGB]         = "Red, Green and Blue",
-    [PL_COLOR_SYSTEM_XYZ]         = "Digital Cinema Distribution Master (XYZ)",
-};
-
-const char *const pl_color_primaries_names[PL_COLOR_PRIM_COUNT] = {
-    [PL_COLOR_PRIM_UNKNOWN]    = "Auto (unknown)",
-    [PL_COLOR_PRIM_BT_601_525] = "ITU-R Rec. BT.601 (525-line = NTSC, SMPTE-C)",
-    [PL_COLOR_PRIM_BT_601_625] = "ITU-R Rec. BT.601 (625-line = PAL, SECAM)",
-    [PL_COLOR_PRIM_BT_709]     = "ITU-R Rec. BT.709 (HD), also sRGB",
-    [PL_COLOR_PRIM_BT_470M]    = "ITU-R Rec. BT.470 M",
-    [PL_COLOR_PRIM_EBU_3213]   = "EBU Tech. 3213-E / JEDEC P22 phosphors",
-    [PL_COLOR_PRIM_BT_2020]    = "ITU-R Rec. BT.2020 (Ultra HD)",
-    [PL_COLOR_PRIM_APPLE]      = "Apple RGB",
-    [PL_COLOR_PRIM_ADOBE]      = "Adobe RGB (1998)",
-    [PL_COLOR_PRIM_PRO_PHOTO]  = "ProPhoto RGB (ROMM)",
-    [PL_COLOR_PRIM_CIE_1931]   = "CIE 1931 RGB primaries",
-    [PL_COLOR_PRIM_DCI_P3]     = "DCI-P3 (Digital Cinema)",
-    [PL_COLOR_PRIM_DISPLAY_P3] = "DCI-P3 (Digital Cinema) with D65 white point",
-    [PL_COLOR_PRIM_V_GAMUT]    = "Panasonic V-Gamut (VARICAM)",
-    [PL_COLOR_PRIM_S_GAMUT]    = "Sony S-Gamut",
-    [PL_COLOR_PRIM_FILM_C]     = "Traditional film primaries with Illuminant C",
-    [PL_COLOR_PRIM_ACES_AP0]   = "ACES Primaries #0",
-    [PL_COLOR_PRIM_ACES_AP1]   = "ACES Primaries #1",
-};
-
-const char *const pl_color_transfer_names[PL_COLOR_TRC_COUNT] = {
-    [PL_COLOR_TRC_UNKNOWN]   = "Auto (unknown SDR)",
-    [PL_COLOR_TRC_BT_1886]   = "ITU-R Rec. BT.1886 (CRT emulation + OOTF)",
-    [PL_COLOR_TRC_SRGB]      = "IEC 61966-2-4 sRGB (CRT emulation)",
-    [PL_COLOR_TRC_LINEAR]    = "Linear light content",
-    [PL_COLOR_TRC_GAMMA18]   = "Pure power gamma 1.8",
-    [PL_COLOR_TRC_GAMMA20]   = "Pure power gamma 2.0",
-    [PL_COLOR_TRC_GAMMA22]   = "Pure power gamma 2.2",
-    [PL_COLOR_TRC_GAMMA24]   = "Pure power gamma 2.4",
-    [PL_COLOR_TRC_GAMMA26]   = "Pure power gamma 2.6",
-    [PL_COLOR_TRC_GAMMA28]   = "Pure power gamma 2.8",
-    [PL_COLOR_TRC_PRO_PHOTO] = "ProPhoto RGB (ROMM)",
-    [PL_COLOR_TRC_ST428]     = "Digital Cinema Distribution Master (XYZ)",
-    [PL_COLOR_TRC_PQ]        = "ITU-R BT.2100 PQ (perceptual quantizer), aka SMPTE ST2048",
-    [PL_COLOR_TRC_HLG]       = "ITU-R BT.2100 HLG (hybrid log-gamma), aka ARIB STD-B67",
-    [PL_COLOR_TRC_V_LOG]     = "Panasonic V-Log (VARICAM)",
-    [PL_COLOR_TRC_S_LOG1]    = "Sony S-Log1",
-    [PL_COLOR_TRC_S_LOG2]    = "Sony S-Log2",
-    [PL_COLOR_TRC_SCRGB]     = "IEC 61966-2-2 scRGB (extended linear BT.709)",
-};
-
-static const char *name_of(const char *const *table, int count, int idx)
-{
-    return idx >= 0 && idx < count ? table[idx] : NULL;
-}
-
-const char *pl_color_system_name(enum pl_color_system sys)
-{
-    return name_of(pl_color_system_names, PL_COLOR_SYSTEM_COUNT, (int) sys);
-}
-
-const char *pl_color_primaries_name(enum pl_color_primaries prim)
-{
-    return name_of(pl_color_primaries_names, PL_COLOR_PRIM_COUNT, (int) prim);
-}
-
-const char *pl_color_transfer_name(enum pl_color_transfer trc)
-{
-    return name_of(pl_color_transfer_names, PL_COLOR_TRC_COUNT, (int) trc);
-}
-
-// HD material is anything at least 1280 wide or taller than 576 lines
-static bool looks_hd(int width, int height) { return width >= 1280 || height > 576; }
-
-enum pl_color_system pl_color_system_guess_ycbcr(int width, int height)
-{
-    return looks_hd(width, height) ? PL_COLOR_SYSTEM_BT_709 : PL_COLOR_SYSTEM_BT_601;
-}
-
-enum pl_color_primaries pl_color_primaries_guess(int width, int height)
-{
-    if (looks_hd(width, height))
-        return PL_COLOR_PRIM_BT_709;
-    if (height == 576)                  // PAL, also anamorphic / squared
-        return PL_COLOR_PRIM_BT_601_625;
-    if (height == 480 || height == 486) // NTSC, NTSC Pro
-        return PL_COLOR_PRIM_BT_601_525;
-    return PL_COLOR_PRIM_BT_709;        // no good metric
-}
-
-bool pl_color_primaries_is_wide_gamut(enum pl_color_primaries prim) { return wide_gamut(prim); }
-
-const struct pl_color_repr pl_color_repr_unknown = {0};
-const struct pl_color_repr pl_color_repr_rgb   = { .sys = PL_COLOR_SYSTEM_RGB,        .levels = PL_COLOR_LEVELS_FULL };
-const struct pl_color_repr pl_color_repr_sdtv  = { .sys = PL_COLOR_SYSTEM_BT_601,     .levels = PL_COLOR_LEVELS_LIMITED };
-const struct pl_color_repr pl_color_repr_hdtv  = { .sys = PL_COLOR_SYSTEM_BT_709,     .levels = PL_COLOR_LEVELS_LIMITED };
-const struct pl_color_repr pl_color_repr_uhdtv = { .sys = PL_COLOR_SYSTEM_BT_2020_NC, .levels = PL_COLOR_LEVELS_LIMITED };
-const struct pl_color_repr pl_color_repr_jpeg  = { .sys = PL_COLOR_SYSTEM_BT_601,     .levels = PL_COLOR_LEVELS_FULL };
-
-bool pl_bit_encoding_equal(const struct pl_bit_encoding *a, const struct pl_bit_encoding *b)
-{
-    return a->sample_depth == b->sample_depth && a->color_depth == b->color_depth &&
-           a->bit_shift == b->bit_shift;
-}
-
-// fields already set in `orig` win, unset (zero) ones are taken from `update`
-void pl_color_repr_merge(struct pl_color_repr *orig, const struct pl_color_repr *update)
-{
-    if (!orig->sys)    orig->sys = update->sys;
-    if (!orig->levels) orig->levels = update->levels;
-    if (!orig->alpha)  orig->alpha = update->alpha;
-    if (!orig->dovi)   orig->dovi = update->dovi;
-    if (!orig->bits.sample_depth) orig->bits.sample_depth = update->bits.sample_depth;
-    if (!orig->bits.color_depth)  orig->bits.color_depth = update->bits.color_depth;
-    if (!orig->bits.bit_shift)    orig->bits.bit_shift = update->bits.bit_shift;
-}
-
-struct pl_cie_xy pl_white_from_temp(float temp) { return white_from_temp(temp); }
-struct pl_cie_xy pl_blackbody_from_temp(float temp) { return blackbody_from_temp(temp); }
-struct pl_cie_xy pl_daylight_from_temp(float temp) { return daylight_from_temp(temp); }
-
-// --- CPU transfer functions -------------------------------------------------------------
-
-static const float HLG_A = 0.17883277, HLG_B = 0.28466892, HLG_C = 0.55991073,
-                   HLG_REF = 1000.0 / PL_COLOR_SDR_WHITE;
-static const float VLOG_B = 0.00873, VLOG_C = 0.241514, VLOG_D = 0.598206;
-static const float SLOG_A = 0.432699, SLOG_B = 0.037584, SLOG_C = 0.616596 + 0.03,
-                   SLOG_P = 3.538813, SLOG_Q = 0.030001, SLOG_K2 = 155.0 / 219.0;
-
-// pure power curves: exponent of the EOTF, 0 for everything that is not a plain power
-static float pure_gamma(enum pl_color_transfer trc)
-{
-    switch (trc) {
-    case PL_COLOR_TRC_GAMMA18: return 1.8f;
-    case PL_COLOR_TRC_GAMMA20: return 2.0f;
-    case PL_COLOR_TRC_UNKNOWN:
-    case PL_COLOR_TRC_GAMMA22: return 2.2f;
-    case PL_COLOR_TRC_GAMMA24: return 2.4f;
-    case PL_COLOR_TRC_GAMMA26: return 2.6f;
-    case PL_COLOR_TRC_GAMMA28: return 2.8f;
-    default: return 0.0f;
-    }
-}
-
-static void nominal_range(const struct pl_color_space *csp, float *lo, float *hi)
-{
-    pl_color_space_nominal_luma_ex(pl_nominal_luma_params(
-        .color = csp, .metadata = PL_HDR_METADATA_HDR10, .scaling = PL_HDR_NORM,
-        .out_min = lo, .out_max = hi));
-}
-
-// system gamma and black-level lift of the HLG OOTF for this display range
-static void hlg_params(const struct pl_color_space *csp, float lo, float hi, float *y, float *b,
-                       float luma_coef[3])
-{
-    *y = 1.2f * powf(1.111f, log2f(hi / HLG_REF));
-    *b = sqrtf(3 * powf(lo / hi, 1 / *y));
-    const pl_matrix3x3 rgb2xyz = pl_get_rgb2xyz_matrix(pl_raw_primaries_get(csp->primaries));
-    for (int i = 0; i < 3; i++)
-        luma_coef[i] = rgb2xyz.m[1][i];
-}
-
-// BT.1886 gain and lift for a display with the given black and white level
-static void bt1886_params(float lo, float hi, float *a, float *b)
-{
-    const float lb = powf(lo, 1/2.4f), lw = powf(hi, 1/2.4f);
-    *a = powf(lw - lb, 2.4f);
-    *b = lb / (lw - lb);
-}
-
-void pl_color_linearize(const struct pl_color_space *csp, float color[3])
-{
-    const enum pl_color_transfer trc = csp->transfer;
-    if (trc == PL_COLOR_TRC_LINEAR)
-        return;
-    float lo, hi;
-    nominal_range(csp, &lo, &hi);
-    float *const c = color;
-
-    if (trc == PL_COLOR_TRC_SCRGB) { // signed, no clamping, no output scaling
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] * (PL_COLOR_SCRGB_WHITE / PL_COLOR_SDR_WHITE);
-        return;
-    }
-    for (int i = 0; i < 3; i++)
-        c[i] = fmaxf(c[i], 0);
-
-    const float g = pure_gamma(trc);
-    if (g) {
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(c[i], g);
-    } else switch (trc) {
-    case PL_COLOR_TRC_SRGB:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] > 0.04045f ? powf((c[i] + 0.055f) / 1.055f, 2.4f) : c[i] / 12.92f;
-        break;
-    case PL_COLOR_TRC_BT_1886: {
-        float a, b;
-        bt1886_params(lo, hi, &a, &b);
-        for (int i = 0; i < 3; i++)
-            c[i] = a * powf(c[i] + b, 2.4f);
-        return; // absolute: already spans [lo, hi]
-    }
-    case PL_COLOR_TRC_PRO_PHOTO:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] > 0.03125f ? powf(c[i], 1.8f) : c[i] / 16;
-        break;
-    case PL_COLOR_TRC_ST428:
-        for (int i = 0; i < 3; i++)
-            c[i] = 52.37f/48 * powf(c[i], 2.6f);
-        break;
-    case PL_COLOR_TRC_PQ:
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(c[i], 1 / PQ_M2);
-        for (int i = 0; i < 3; i++)
-            c[i] = fmaxf(c[i] - PQ_C1, 0) / (PQ_C2 - PQ_C3 * c[i]);
-        for (int i = 0; i < 3; i++)
-            c[i] = 10000 / PL_COLOR_SDR_WHITE * powf(c[i], 1 / PQ_M1);
-        break;
-    case PL_COLOR_TRC_HLG: {
-        float y, b, coef[3];
-        hlg_params(csp, lo, hi, &y, &b, coef);
-        for (int i = 0; i < 3; i++) // inverse OETF on the lifted signal
-            c[i] = (1 - b) * c[i] + b;
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] > 0.5f ? expf((c[i] - HLG_C) / HLG_A) + HLG_B : 4 * c[i] * c[i];
-        float luma = coef[0] * c[0] + coef[1] * c[1] + coef[2] * c[2]; // OOTF
-        luma = powf(fmaxf(luma / 12, 0), y - 1);
-        for (int i = 0; i < 3; i++)
-            c[i] = luma * c[i] / 12;
-        break;
-    }
-    case PL_COLOR_TRC_V_LOG:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= 0.181f ? powf(10, (c[i] - VLOG_D) / VLOG_C) - VLOG_B
-                                  : (c[i] - 0.125f) / 5.6f;
-        break;
-    case PL_COLOR_TRC_S_LOG1:
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(10, (c[i] - SLOG_C) / SLOG_A) - SLOG_B;
-        break;
-    case PL_COLOR_TRC_S_LOG2:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= SLOG_Q ? (powf(10, (c[i] - SLOG_C) / SLOG_A) - SLOG_B) / SLOG_K2
-                                  : (c[i] - SLOG_Q) / SLOG_P;
-        break;
-    default:
-        return;
-    }
-
-    // relative curves are stretched onto the display's [lo, hi] (HLG did that in its OOTF)
-    if (pl_color_space_is_black_scaled(csp) && trc != PL_COLOR_TRC_HLG) {
-        for (int i = 0; i < 3; i++)
-            c[i] = (hi - lo) * c[i] + lo;
-    }
-}
-
-void pl_color_delinearize(const struct pl_color_space *csp, float color[3])
-{
-    const enum pl_color_transfer trc = csp->transfer;
-    if (trc == PL_COLOR_TRC_LINEAR)
-        return;
-    float lo, hi;
-    nominal_range(csp, &lo, &hi);
-    float *const c = color;
-
-    if (pl_color_space_is_black_scaled(csp) && trc != PL_COLOR_TRC_HLG) {
-        for (int i = 0; i < 3; i++)
-            c[i] = (c[i] - lo) / (hi - lo);
-    }
-    if (trc == PL_COLOR_TRC_SCRGB) {
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] * (PL_COLOR_SDR_WHITE / PL_COLOR_SCRGB_WHITE);
-        return;
-    }
-    for (int i = 0; i < 3; i++)
-        c[i] = fmaxf(c[i], 0);
-
-    switch (trc) {
-    case PL_COLOR_TRC_GAMMA18: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/1.8f); return;
-    case PL_COLOR_TRC_GAMMA20: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/2.0f); return;
-    case PL_COLOR_TRC_UNKNOWN:
-    case PL_COLOR_TRC_GAMMA22: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/2.2f); return;
-    case PL_COLOR_TRC_GAMMA24: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/2.4f); return;
-    case PL_COLOR_TRC_GAMMA26: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/2.6f); return;
-    case PL_COLOR_TRC_GAMMA28: for (int i = 0; i < 3; i++) c[i] = powf(c[i], 1/2.8f); return;
-    case PL_COLOR_TRC_SRGB:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= 0.0031308f ? 1.055f * powf(c[i], 1/2.4f) - 0.055f : 12.92f * c[i];
-        return;
-    case PL_COLOR_TRC_BT_1886: {
-        float a, b;
-        bt1886_params(lo, hi, &a, &b);
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(c[i] / a, 1/2.4f) - b;
-        return;
-    }
-    case PL_COLOR_TRC_ST428:
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(c[i] * 48/52.37f, 1/2.6f);
-        return;
-    case PL_COLOR_TRC_PRO_PHOTO:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= 0.001953f ? powf(c[i], 1/1.8f) : 16 * c[i];
-        return;
-    case PL_COLOR_TRC_PQ:
-        for (int i = 0; i < 3; i++)
-            c[i] = powf(c[i] * PL_COLOR_SDR_WHITE / 10000, PQ_M1);
-        for (int i = 0; i < 3; i++)
-            c[i] = powf((PQ_C1 + PQ_C2 * c[i]) / (1 + PQ_C3 * c[i]), PQ_M2);
-        return;
-    case PL_COLOR_TRC_HLG: {
-        float y, b, coef[3];
-        hlg_params(csp, lo, hi, &y, &b, coef);
-        float luma = coef[0] * c[0] + coef[1] * c[1] + coef[2] * c[2]; // inverse OOTF
-        luma = fmaxf(1e-6f, powf(luma / hi, (1 - y) / y));
-        for (int i = 0; i < 3; i++)
-            c[i] = 12 / hi * luma * c[i];
-        for (int i = 0; i < 3; i++) // OETF
-            c[i] = c[i] > 1 ? HLG_A * logf(c[i] - HLG_B) + HLG_C : 0.5f * sqrtf(c[i]);
-        for (int i = 0; i < 3; i++)
-            c[i] = (c[i] - b) / (1 - b);
-        return;
-    }
-    case PL_COLOR_TRC_V_LOG:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= 0.01f ? VLOG_C * log10f(c[i] + VLOG_B) + VLOG_D : 5.6f * c[i] + 0.125f;
-        return;
-    case PL_COLOR_TRC_S_LOG1:
-        for (int i = 0; i < 3; i++)
-            c[i] = SLOG_A * log10f(c[i] + SLOG_B) + SLOG_C;
-        return;
-    case PL_COLOR_TRC_S_LOG2:
-        for (int i = 0; i < 3; i++)
-            c[i] = c[i] >= 0 ? SLOG_A * log10f(SLOG_B * c[i] + SLOG_C) : SLOG_P * c[i] + SLOG_Q;
-        return;
-    default:
-        return;
-    }
-}
-
-// --- cone distortion (colour-vision deficiency simulation) ---------------------------------
-
-const struct pl_cone_params pl_vision_normal        = { PL_CONE_NONE, 1.0 };
-const struct pl_cone_params pl_vision_protanomaly   = { PL_CONE_L,    0.5 };
-const struct pl_cone_params pl_vision_protanopia    = { PL_CONE_L,    0.0 };
-const struct pl_cone_params pl_vision_deuteranomaly = { PL_CONE_M,    0.5 };
-const struct pl_cone_params pl_vision_deuteranopia  = { PL_CONE_M,    0.0 };
-const struct pl_cone_params pl_vision_tritanomaly   = { PL_CONE_S,    0.5 };
-const struct pl_cone_params pl_vision_tritanopia    = { PL_CONE_S,    0.0 };
-const struct pl_cone_params pl_vision_monochromacy  = { PL_CONE_LM,   0.0 };
-const struct pl_cone_params pl_vision_achromatopsia = { PL_CONE_LMS,  0.0 };
-
-// One missing cone `t` is reconstructed from the other two (p, q) as a*p + b*q such that white
-// `w` and one anchor primary `k` keep their response:  a*k[p] + b*k[q] = k[t], same for w.
-static void solve_missing_cone(const float k[3], const float w[3], int t, int p, int q,
-                               float *a, float *b)
-{
-    *a = (k[t] - k[q] * w[t] / w[q]) / (k[p] - k[q] * w[p] / w[q]);
-    *b = (k[t] - k[p] * w[t] / w[p]) / (k[q] - k[p] * w[q] / w[p]);
-}
-
-pl_matrix3x3 pl_get_cone_matrix(const struct pl_cone_params *params,
-                                const struct pl_raw_primaries *prim)
-{
-    pl_matrix3x3 rgb2lms = cat16; // LMS <- XYZ <- RGB
-    pl_matrix3x3 rgb2xyz = pl_get_rgb2xyz_matrix(prim);
-    pl_matrix3x3_mul(&rgb2lms, &rgb2xyz);
-
-    float red[3] = {1.0, 0.0, 0.0}, blue[3] = {0.0, 0.0, 1.0}, white[3] = {1.0, 1.0, 1.0};
-    pl_matrix3x3_apply(&rgb2lms, red);
-    pl_matrix3x3_apply(&rgb2lms, blue);
-    pl_matrix3x3_apply(&rgb2lms, white);
-
-    const float c = params->strength;
-    float a, b;
-    pl_matrix3x3 d = pl_matrix3x3_identity;
-    switch (params->cones) {
-    case PL_CONE_NONE:
-        return pl_matrix3x3_identity;
-    case PL_CONE_L: // keep neutral and blue
-        solve_missing_cone(blue, white, 0, 1, 2, &a, &b);
-        d.m[0][0] = c; d.m[0][1] = (1.0 - c) * a; d.m[0][2] = (1.0 - c) * b;
-        break;
-    case PL_CONE_M: // keep neutral and blue
-        solve_missing_cone(blue, white, 1, 0, 2, &a, &b);
-        d.m[1][0] = (1.0 - c) * a; d.m[1][1] = c; d.m[1][2] = (1.0 - c) * b;
-        break;
-    case PL_CONE_S: // keep neutral and red
-        solve_missing_cone(red, white, 2, 0, 1, &a, &b);
-        d.m[2][0] = (1.0 - c) * a; d.m[2][1] = (1.0 - c) * b; d.m[2][2] = c;
-        break;
-    case PL_CONE_LM: // only S left: keep neutral
-        a = white[0] / white[2];
-        b = white[1] / white[2];
-        d.m[0][0] = c; d.m[0][2] = (1.0 - c) * a;
-        d.m[1][1] = c; d.m[1][2] = (1.0 - c) * b;
-        break;
-    case PL_CONE_MS: // only L left
-        a = white[1] / white[0];
-        b = white[2] / white[0];
-        d.m[1][0] = (1.0 - c) * a; d.m[1][1] = c;
-        d.m[2][0] = (1.0 - c) * b; d.m[2][2] = c;
-        break;
-    case PL_CONE_LS: // only M left
-        a = white[0] / white[1];
-        b = white[2] / white[1];
-        d.m[0][0] = c; d.m[0][1] = (1.0 - c) * a;
-        d.m[2][1] = (1.0 - c) * b; d.m[2][2] = c;
-        break;
-    case PL_CONE_LMS: { // rods only: a fixed mixture of the cone responses
-        const float w[3] = {0.3605, 0.6415, -0.002};
-        for (int i = 0; i < 3; i++) {
-            for (int j = 0; j < 3; j++) {
-                d.m[i][j] = (1.0 - c) * w[j] * white[i] / white[j];
-                if (i == j)
-                    d.m[i][j] += c;
-            }
-        }
-        break;
-    }
-    default:
-        return pl_matrix3x3_identity;
-    }
-
-    pl_matrix3x3 out = rgb2lms; // RGB <- LMS * distortion * LMS <- RGB
-    pl_matrix3x3_invert(&out);
-    pl_matrix3x3_mul(&out, &d);
-    pl_matrix3x3_mul(&out, &rgb2lms);
-    return out;
-}

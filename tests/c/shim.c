@@ -36,6 +36,7 @@ static void shim_init(void)
         ));
 }
 
+#define T0_HOT_PATH_ONLY 1
 #define T0_FN(n) plt_##n
 #define T0_API API
 #define T0_INIT() shim_init()

@@ -1,9 +1,10 @@
 """The reference's OWN unit tests for the host code of the path (src/tests/filters.c,
-tone_mapping.c, colorspace.c, common.c) compiled in place from /root/reference — nothing is copied — against
+tone_mapping.c) compiled in place from /root/reference — nothing is copied — against
 the reference's public headers and linked against libplacebo_b200.so instead of libplacebo:
 the drop-in claim of INTEGRATION.md, checked with the maintainers' own assertions (filter LUT
-accuracy and row sums, tone-curve monotonicity / clip identity / PQ constants, transfer-function
-and colour-system round trips, pl_color_repr_decode matrices, primaries, cone matrices).
+accuracy and row sums, tone-curve monotonicity / clip identity / PQ constants). The reference's
+colorspace.c / common.c unit tests exercise API surface outside SURVEY.md section 8 (names, crop
+helpers, CPU transfer functions, cone matrices), which this library no longer carries.
 Skipped where the reference tree is absent (the GPU box)."""
 import os
 import subprocess
@@ -21,7 +22,7 @@ pytestmark = pytest.mark.skipif(
     reason="reference tree / oracle/_ref headers not present")
 
 
-@pytest.mark.parametrize("name", ["filters", "tone_mapping", "colorspace", "common"])
+@pytest.mark.parametrize("name", ["filters", "tone_mapping"])
 def test_reference_unit_test_passes_against_product_library(name, tmp_path):
     T.product_t0()  # makes sure libplacebo_b200.so is built
     exe = str(tmp_path / name)
