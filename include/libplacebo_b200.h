@@ -677,6 +677,15 @@ union pl_clear_color {
     uint32_t u[4];
 };
 PL_API void pl_tex_clear_ex(pl_gpu gpu, pl_tex dst, const union pl_clear_color color);
+struct pl_tex_blit_params { /* gpu.h:820-845 */
+    pl_tex src;             // needs params.blit_src
+    pl_tex dst;             // needs params.blit_dst and a format of the same internal size
+    pl_rect3d src_rc;       // region to copy (optional: whole texture); may be flipped
+    pl_rect3d dst_rc;       // region to write (optional); the rest of dst is preserved
+    enum pl_tex_sample_mode sample_mode; // used when the regions differ in size
+};
+#define pl_tex_blit_params(...) (&(struct pl_tex_blit_params) { __VA_ARGS__ })
+PL_API void pl_tex_blit(pl_gpu gpu, const struct pl_tex_blit_params *params); /* gpu.h:849; 2D float / unorm textures */
 struct pl_tex_transfer_params { /* gpu.h:852-919 */
     pl_tex tex;
     pl_rect3d rc;
@@ -1175,6 +1184,14 @@ struct pl_frame { /* renderer.h:528-655 */
 };
 PL_API void pl_frame_set_chroma_location(struct pl_frame *frame, enum pl_chroma_location chroma_loc);
 PL_API bool pl_frame_is_cropped(const struct pl_frame *frame);
+/* renderer.h:675-687: reset every plane of a frame to an sRGB colour (non-premultiplied), converted
+ * to the frame's colour space and representation */
+PL_API void pl_frame_clear_rgba(pl_gpu gpu, const struct pl_frame *frame, const float clear_color[4]);
+static inline void pl_frame_clear(pl_gpu gpu, const struct pl_frame *frame, const float clear_color[3])
+{
+    const float rgba[4] = { clear_color[0], clear_color[1], clear_color[2], 1.0f };
+    pl_frame_clear_rgba(gpu, frame, rgba);
+}
 PL_API void pl_frames_infer(pl_renderer rr, struct pl_frame *image, struct pl_frame *target);
 PL_API bool pl_render_image(pl_renderer rr, const struct pl_frame *image,
                             const struct pl_frame *target, const struct pl_render_params *params);

@@ -842,6 +842,72 @@ void pl_tex_clear_ex(pl_gpu gpu, pl_tex dst, const union pl_clear_color color)
     pl_tex_clear(gpu, dst, color.f);
 }
 
+// pl_tex_blit (gpu.h:820-849): copy / scale a sub-rectangle between textures of loosely
+// compatible formats. Lowered to one pixel-pass launch: the source rectangle is sampled (texel
+// exact for equal sizes, nearest / bilinear otherwise) onto the destination rectangle; flipped
+// rectangles sample in reverse. Everything outside dst_rc is preserved.
+void pl_tex_blit(pl_gpu gpu, const struct pl_tex_blit_params *params)
+{
+    DEV_GUARD(gpu);
+    pl_tex src = params ? params->src : NULL, dst = params ? params->dst : NULL;
+    if (!src || !dst) {
+        PLB_ERR(gpu->log, "pl_tex_blit: src and dst are required");
+        return;
+    }
+    pl_fmt sf = src->params.format, df = dst->params.format;
+    if (sf->internal_size != df->internal_size || (sf->type == PL_FMT_UINT) != (df->type == PL_FMT_UINT) ||
+        (sf->type == PL_FMT_SINT) != (df->type == PL_FMT_SINT) || !src->params.blit_src ||
+        !dst->params.blit_dst ||
+        (params->sample_mode == PL_TEX_SAMPLE_LINEAR && !(sf->caps & PL_FMT_CAP_LINEAR))) {
+        PLB_ERR(gpu->log, "pl_tex_blit: incompatible textures (%s -> %s) or missing blit usage",
+                sf->name, df->name);
+        return;
+    }
+    if (sf->type == PL_FMT_UINT || sf->type == PL_FMT_SINT || src->params.d || dst->params.d) {
+        PLB_ERR(gpu->log, "pl_tex_blit: integer and 3D textures are not blittable on the CUDA backend");
+        return;
+    }
+    pl_rect3d sr = params->src_rc, dr = params->dst_rc;
+    if (!sr.x0 && !sr.x1) sr.x1 = src->params.w;
+    if (!sr.y0 && !sr.y1) sr.y1 = src->params.h;
+    if (!dr.x0 && !dr.x1) dr.x1 = dst->params.w;
+    if (!dr.y0 && !dr.y1) dr.y1 = dst->params.h;
+    const bool in_src = PLB_MIN(sr.x0, sr.x1) >= 0 && PLB_MAX(sr.x0, sr.x1) <= src->params.w &&
+                        PLB_MIN(sr.y0, sr.y1) >= 0 && PLB_MAX(sr.y0, sr.y1) <= src->params.h;
+    const bool in_dst = PLB_MIN(dr.x0, dr.x1) >= 0 && PLB_MAX(dr.x0, dr.x1) <= dst->params.w &&
+                        PLB_MIN(dr.y0, dr.y1) >= 0 && PLB_MAX(dr.y0, dr.y1) <= dst->params.h;
+    if (!in_src || !in_dst || sr.x0 == sr.x1 || sr.y0 == sr.y1 || dr.x0 == dr.x1 || dr.y0 == dr.y1) {
+        PLB_ERR(gpu->log, "pl_tex_blit: rectangles out of bounds or empty");
+        return;
+    }
+    // a flipped destination rectangle = an upright one sampled in reverse
+    if (dr.x0 > dr.x1) { int t = dr.x0; dr.x0 = dr.x1; dr.x1 = t; t = sr.x0; sr.x0 = sr.x1; sr.x1 = t; }
+    if (dr.y0 > dr.y1) { int t = dr.y0; dr.y0 = dr.y1; dr.y1 = t; t = sr.y0; sr.y0 = sr.y1; sr.y1 = t; }
+
+    struct plb_pixel_launch *px = (struct plb_pixel_launch *) calloc(1, sizeof(*px));
+    struct plb_plane_src *pl = &px->planes[0];
+    px->nplanes = 1;
+    pl->kind = PLB_PLANE_DIRECT;
+    pl->tex = plb_tex_priv(src)->d;
+    pl->rect = (pl_rect2df) { (float) sr.x0, (float) sr.y0, (float) sr.x1, (float) sr.y1 };
+    const bool same_size = abs(sr.x1 - sr.x0) == dr.x1 - dr.x0 && abs(sr.y1 - sr.y0) == dr.y1 - dr.y0;
+    pl->linear = !same_size && params->sample_mode == PL_TEX_SAMPLE_LINEAR;
+    pl->scale = 1.0f;
+    for (int k = 0; k < 4; k++)
+        pl->map[k] = k;
+    px->init[3] = 1.0f;
+    px->dst = plb_tex_priv(dst)->d;
+    px->dst_rect = (pl_rect2d) { dr.x0, dr.y0, dr.x1, dr.y1 };
+    px->out_w = dr.x1 - dr.x0;
+    px->out_h = dr.y1 - dr.y0;
+    px->coord_mode = PLB_COORD_EXACT;
+    pl_tex texs[2] = { src, dst };
+    plb_gpu_before_use(gpu, texs, 2);
+    plb_launch_pixel(gpu, px);
+    plb_gpu_after_use(gpu, texs, 2);
+    free(px);
+}
+
 bool pl_fmt_is_ordered(pl_fmt fmt)
 {
     bool ordered = true;

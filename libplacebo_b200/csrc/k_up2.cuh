@@ -83,7 +83,7 @@ constexpr int up2_smem_bytes()
 // and 2-3, 6-7, ...): thread tx reads chunks 2 tx + q, so within each half consecutive lanes
 // read consecutive 16 bytes (conflict-free LDS.128).
 template <int NC, int XM, int YM, int MODE>
-__global__ void __launch_bounds__(UP2_TX * UP2_TY, 2)
+__global__ void __launch_bounds__(UP2_TX * UP2_TY, MODE == 1 ? 3 : 2)
 k_polar_up2(const __grid_constant__ polar_up2_args a, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int R2_16 = 160; // taps beyond radius^2 = 10 never contribute (host check)

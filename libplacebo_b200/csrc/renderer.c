@@ -1639,3 +1639,120 @@ bool pl_renderer_measure_peak_dev(pl_renderer rr, const struct pl_frame *pimage,
 {
     return measure_peak(rr, pimage, params, dev_peak_buf, true);
 }
+
+
+// ---------------------------------------------------------------------------------------
+// pl_frame_clear_rgba (renderer.h:675, src/renderer.c:4169-4192): an sRGB colour is taken to
+// the frame's colour space (translate_srgb_color :2555-2584: same transfer curve for the
+// BT.1886 / sRGB / gamma 2.2 family, else infinite-contrast sRGB; relative colorimetric
+// primaries change), encoded with the inverse of pl_color_repr_decode and written to every
+// plane with pl_tex_clear. Host arithmetic on one colour; the transfer functions below are this
+// library's own statement of pl_shader_linearize / delinearize for a single float triple.
+// ---------------------------------------------------------------------------------------
+
+struct trc_ctx { float lo, hi; }; // nominal black / peak of the space, relative to SDR white
+
+static float pq_to_linear(float e)
+{
+    const double m1 = 2610.0 / 16384, m2 = 2523.0 / 32, c1 = 3424.0 / 4096, c2 = 2413.0 / 128, c3 = 2392.0 / 128;
+    const double p = pow(fmax(e, 0.0), 1.0 / m2);
+    return (float) (pow(fmax(p - c1, 0.0) / (c2 - c3 * p), 1.0 / m1) * 10000.0 / PL_COLOR_SDR_WHITE);
+}
+
+static float linear_to_pq(float l)
+{
+    const double m1 = 2610.0 / 16384, m2 = 2523.0 / 32, c1 = 3424.0 / 4096, c2 = 2413.0 / 128, c3 = 2392.0 / 128;
+    const double y = pow(fmax(l, 0.0) * PL_COLOR_SDR_WHITE / 10000.0, m1);
+    return (float) pow((c1 + c2 * y) / (1.0 + c3 * y), m2);
+}
+
+static void clear_trc(const struct pl_color_space *csp, float c[3], bool to_linear)
+{
+    struct trc_ctx t;
+    pl_color_space_nominal_luma_ex(pl_nominal_luma_params(
+        .color = csp, .metadata = PL_HDR_METADATA_HDR10, .scaling = PL_HDR_NORM,
+        .out_min = &t.lo, .out_max = &t.hi));
+    const float span = t.hi - t.lo;
+    for (int k = 0; k < 3; k++) {
+        float x = c[k];
+        switch (csp->transfer) {
+        case PL_COLOR_TRC_LINEAR:
+            break;
+        case PL_COLOR_TRC_PQ:
+            x = to_linear ? pq_to_linear(x) : linear_to_pq(x);
+            break;
+        case PL_COLOR_TRC_BT_1886: {
+            const float lb = powf(t.lo, 1 / 2.4f), lw = powf(t.hi, 1 / 2.4f);
+            const float a = powf(lw - lb, 2.4f), b = lb / (lw - lb);
+            x = to_linear ? a * powf(fmaxf(x, 0) + b, 2.4f) : powf(fmaxf(x, 0) / a, 1 / 2.4f) - b;
+            break;
+        }
+        case PL_COLOR_TRC_SRGB:
+            if (to_linear) {
+                x = fmaxf(x, 0);
+                x = x > 0.04045f ? powf((x + 0.055f) / 1.055f, 2.4f) : x / 12.92f;
+                x = span * x + t.lo;
+            } else {
+                x = fmaxf((x - t.lo) / span, 0);
+                x = x >= 0.0031308f ? 1.055f * powf(x, 1 / 2.4f) - 0.055f : 12.92f * x;
+            }
+            break;
+        default: { // pure power curves and the remaining spaces: gamma 2.2 unless a plain gamma
+            float g = 2.2f;
+            switch (csp->transfer) {
+            case PL_COLOR_TRC_GAMMA18: g = 1.8f; break;
+            case PL_COLOR_TRC_GAMMA20: g = 2.0f; break;
+            case PL_COLOR_TRC_GAMMA24: g = 2.4f; break;
+            case PL_COLOR_TRC_GAMMA26: g = 2.6f; break;
+            case PL_COLOR_TRC_GAMMA28: g = 2.8f; break;
+            default: break;
+            }
+            x = to_linear ? span * powf(fmaxf(x, 0), g) + t.lo : powf(fmaxf((x - t.lo) / span, 0), 1 / g);
+            break;
+        }
+        }
+        c[k] = x;
+    }
+}
+
+void pl_frame_clear_rgba(pl_gpu gpu, const struct pl_frame *frame, const float rgba[4])
+{
+    if (!frame || !rgba)
+        return;
+    struct pl_color_space dst = frame->color;
+    pl_color_space_infer(&dst);
+    struct pl_color_space srgb = pl_color_space_srgb;
+    if (dst.transfer == PL_COLOR_TRC_BT_1886 || dst.transfer == PL_COLOR_TRC_SRGB ||
+        dst.transfer == PL_COLOR_TRC_GAMMA22) {
+        srgb.transfer = dst.transfer; // re-use the curve: no small adaptations
+        srgb.hdr.min_luma = dst.hdr.min_luma;
+    } else {
+        srgb.hdr.min_luma = PL_COLOR_HDR_BLACK;
+    }
+    pl_color_space_infer(&srgb);
+    float enc[3] = { rgba[0], rgba[1], rgba[2] };
+    clear_trc(&srgb, enc, true);
+    const pl_matrix3x3 prim = pl_get_color_mapping_matrix(pl_raw_primaries_get(srgb.primaries),
+                                                          pl_raw_primaries_get(dst.primaries),
+                                                          PL_INTENT_RELATIVE_COLORIMETRIC);
+    pl_matrix3x3_apply(&prim, enc);
+    clear_trc(&dst, enc, false);
+
+    struct pl_color_repr repr = frame->repr;
+    pl_transform3x3 tr = pl_color_repr_decode(&repr, NULL);
+    pl_transform3x3_invert(&tr);
+    pl_transform3x3_apply(&tr, enc);
+
+    const float mult = frame->repr.alpha == PL_ALPHA_PREMULTIPLIED ? rgba[3] : 1.0f;
+    for (int p = 0; p < frame->num_planes; p++) {
+        const struct pl_plane *plane = &frame->planes[p];
+        float clear[4] = { 0.0f, 0.0f, 0.0f, rgba[3] };
+        for (int c = 0; c < plane->components; c++) {
+            const int ch = plane->component_mapping[c];
+            if (ch >= 0 && ch < 3)
+                clear[c] = mult * enc[ch];
+        }
+        if (plane->texture)
+            pl_tex_clear(gpu, plane->texture, clear);
+    }
+}

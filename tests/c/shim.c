@@ -108,8 +108,46 @@ API void *shim_tex_create(struct shim_ctx *c, const char *fmt, int w, int h, con
         .storable = true,
         .host_writable = true,
         .host_readable = true,
+        .blit_src = true,
+        .blit_dst = true,
         .initial_data = data,
     ));
+}
+
+/* pl_tex_blit: rc = x0, y0, x1, y1 (all zero = whole texture) */
+API void shim_tex_blit(struct shim_ctx *c, void *src, void *dst, const int *src_rc, const int *dst_rc,
+                       int linear)
+{
+    pl_tex_blit(c->gpu, pl_tex_blit_params(
+        .src = src, .dst = dst,
+        .src_rc = { .x0 = src_rc[0], .y0 = src_rc[1], .x1 = src_rc[2], .y1 = src_rc[3] },
+        .dst_rc = { .x0 = dst_rc[0], .y0 = dst_rc[1], .x1 = dst_rc[2], .y1 = dst_rc[3] },
+        .sample_mode = linear ? PL_TEX_SAMPLE_LINEAR : PL_TEX_SAMPLE_NEAREST,
+    ));
+}
+
+/* pl_frame_clear_rgba on a 3-plane YCbCr frame (sys / levels / depth given) or a packed RGB one */
+API void shim_frame_clear(struct shim_ctx *c, int nplanes, void **planes, int sys, int levels,
+                          int depth, const float *csp, const float *rgba)
+{
+    struct pl_frame f = {
+        .num_planes = nplanes,
+        .repr = { .sys = sys, .levels = levels, .bits = { depth, depth, 0 } },
+        .color = csp_from_flat(csp),
+    };
+    for (int i = 0; i < nplanes; i++) {
+        f.planes[i].texture = planes[i];
+        if (nplanes == 1) {
+            f.planes[i].components = 3;
+            f.planes[i].component_mapping[0] = 0;
+            f.planes[i].component_mapping[1] = 1;
+            f.planes[i].component_mapping[2] = 2;
+        } else {
+            f.planes[i].components = 1;
+            f.planes[i].component_mapping[0] = i;
+        }
+    }
+    pl_frame_clear_rgba(c->gpu, &f, rgba);
 }
 
 API void shim_tex_destroy(struct shim_ctx *c, void *tex)
