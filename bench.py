@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 
 L2_BYTES = 126e6
 METRIC = "4K HDR10->SDR EWA-Lanczos frames/sec"
-EXTRA = ["c2_1080p_to_4k_ewa_fp16", "c4_4k_hdr10_to_sdr_av1_grain"]
+EXTRA = ["c2_1080p_to_4k_ewa_fp16", "c4_4k_hdr10_to_sdr_av1_grain", "c3_4k_hdr10_to_sdr_hq_preset"]
 
 
 def parse():
@@ -139,6 +139,8 @@ def oracle_render_args(wl_name, seed=0):
     o = wl["opts"]
     kw = dict(upscaler=wl["upscaler"], deband=bool(o.get("deband")), peak=o.get("peak", 0),
               dither=o.get("dither", 0), cmap_hq=bool(o.get("cmap_hq")))
+    if o.get("contrast"):
+        kw["contrast_recovery"] = 0.3
     return P, img, tgt, kw, bool(o.get("grain"))
 
 
@@ -267,6 +269,10 @@ def pass_bytes(desc, wl):
         # main scaler: rgba16hf FBO at source size -> output size
         last = not has("peak detection")
         return sw * sh * 8 + dw * dh * (out_bpp if last and not wl["opts"].get("peak") else 8), "main EWA scaler"
+    if has("feature extraction"):
+        return dw * dh * 8 + dw * dh * 2, "feature extraction"
+    if has("ortho") or has("separable"):
+        return pw * ph * 2 * 2, "feature low-pass"
     if has("tone / gamut mapping") or has("dithering") or has("delinearization"):
         return dw * dh * 8 + dw * dh * out_bpp, "colour map + output"
     return (sw * sh * 2 + 2 * cw * ch * 2) + dw * dh * out_bpp, "other"

@@ -425,9 +425,42 @@ PLB_DEV void plb_gamut_sample(const plb_op_color_map &p, const float idx[3], flo
 #undef PLB_TRI
 }
 
-// HOT: static curve evaluation (specialised kernels); else descriptor-driven
+// Bilinear fetch from the single-component fp16 feature map (textureLod on a linearly filtered
+// texture, clamp to edge): the general texel path, or direct half loads when HOT.
+template <bool HOT>
+PLB_DEV float plb_fmap_linear(const plb_tex_desc &t, float u, float v)
+{
+    if (!HOT || t.kind != PLB_FK_HALF || t.comps != 1)
+        return plb_tex_linear(t, u, v).x;
+    const float tx = u * (float) t.w - 0.5f, ty = v * (float) t.h - 0.5f;
+    const float bx = floorf(tx), by = floorf(ty);
+    const float fx = tx - bx, fy = ty - by;
+    const int x0 = plb_clampi((int) bx, 0, t.w - 1), x1 = plb_clampi((int) bx + 1, 0, t.w - 1);
+    const int y0 = plb_clampi((int) by, 0, t.h - 1), y1 = plb_clampi((int) by + 1, 0, t.h - 1);
+    const __half *r0 = (const __half *) ((const char *) t.ptr + (size_t) y0 * t.pitch);
+    const __half *r1 = (const __half *) ((const char *) t.ptr + (size_t) y1 * t.pitch);
+    const float a = __half2float(r0[x0]), b = __half2float(r0[x1]);
+    const float c = __half2float(r1[x0]), d = __half2float(r1[x1]);
+    return plb_mix(plb_mix(a, b, fx), plb_mix(c, d, fx), fy);
+}
+
+// `tone_map(x)` of pl_shader_color_map_ex: clip / linear fast paths or the 1-D LUT (:1826-1876)
+PLB_DEV float plb_tone_map_x(const plb_op_color_map &p, float x)
+{
+    if (p.tone_kind == 1)
+        return plb_clamp(x, p.in_min, p.in_max);
+    if (p.tone_kind == 2) {
+        x = p.lin_a * x + p.lin_b;
+        x = plb_clamp(x, 0.0f, 1.0f);
+        return (p.out_max - p.out_min) * x + p.out_min;
+    }
+    return plb_lut1d(p.tone_lut, p.tone_lut_size, p.tone_a * x + p.tone_b);
+}
+
+// HOT: static curve evaluation (specialised kernels); else descriptor-driven.
+// (gx, gy): the invocation, for the feature-map position.
 template <bool HOT = false>
-PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
+PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3], int gx, int gy)
 {
     const float lms2ipt[9] = { 0.4000f, 0.4000f, 0.2000f, 4.4550f, -4.8510f, 0.3960f,
                                0.8056f, 0.3572f, -1.1628f };
@@ -451,14 +484,42 @@ PLB_DEV void plb_color_map(const plb_op_color_map &p, float px[3])
 
     if (p.need_tone) {
         float x = ipt[0];
-        if (p.tone_kind == 1) {
-            x = plb_clamp(x, p.in_min, p.in_max);
-        } else if (p.tone_kind == 2) {
-            x = p.lin_a * x + p.lin_b;
-            x = plb_clamp(x, 0.0f, 1.0f);
-            x = (p.out_max - p.out_min) * x + p.out_min;
+        if (p.has_fmap) {
+            // HF detail from a bicubic interpolation of the low-pass map (colorspace.c:1886-1917)
+            const float lpos[2] = { __fdiv_rn((float) gx + 0.5f, (float) p.out_w),
+                                    __fdiv_rn((float) gy + 0.5f, (float) p.out_h) };
+            float g[4], h[4];
+            #pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const float t = lpos[a] * p.fm_size[a] + 0.5f;
+                const float frac = t - floorf(t), frac2 = frac * frac;
+                const float inv = 1.0f - frac, inv2 = inv * inv;
+                const float w0 = (1.0f / 6.0f) * inv2 * inv;
+                const float w1 = (2.0f / 3.0f) - 0.5f * frac2 * (2.0f - frac);
+                const float w2 = (2.0f / 3.0f) - 0.5f * inv2 * (2.0f - inv);
+                const float w3 = (1.0f / 6.0f) * frac2 * frac;
+                g[a] = w0 + w1;
+                g[2 + a] = w2 + w3;
+                h[a] = w1 / g[a] + inv;
+                h[2 + a] = w3 / g[2 + a] + inv;
+                h[a] -= 2.0f;
+            }
+            const float ax = lpos[0] + p.fm_pt[0] * h[0], ay = lpos[1] + p.fm_pt[1] * h[1];
+            const float bx = lpos[0] + p.fm_pt[0] * h[2], by = lpos[1] + p.fm_pt[1] * h[3];
+            const float l00 = plb_fmap_linear<HOT>(p.fmap, ax, ay), l01 = plb_fmap_linear<HOT>(p.fmap, ax, by);
+            const float l0 = l01 * (1.0f - g[1]) + l00 * g[1];
+            const float l10 = plb_fmap_linear<HOT>(p.fmap, bx, ay), l11 = plb_fmap_linear<HOT>(p.fmap, bx, by);
+            const float l1 = l11 * (1.0f - g[1]) + l10 * g[1];
+            const float luma = l1 * (1.0f - g[0]) + l0 * g[0];
+            const float highres = plb_clamp(ipt[0], 0.0f, 1.0f);
+            const float lowres = plb_clamp(luma, 0.0f, 1.0f);
+            const float detail = highres - lowres;
+            const float base = plb_tone_map_x(p, highres);
+            const float sharp = plb_tone_map_x(p, lowres) + detail;
+            x = base * (1.0f - p.recovery) + sharp * p.recovery;
+            x = plb_clamp(x, p.out_min, p.out_max);
         } else {
-            x = plb_lut1d(p.tone_lut, p.tone_lut_size, p.tone_a * x + p.tone_b);
+            x = plb_tone_map_x(p, x);
         }
         ipt[0] = x;
         float h0 = ((i_orig - 6.0f) * i_orig + 9.0f) * i_orig;
@@ -745,35 +806,6 @@ PLB_DEV void plb_run_light_ops(float c[4])
     }
 }
 
-// The output pass of an HDR -> SDR render (pass_convert_colors + pass_output_target,
-// renderer.c:2157-2279, 2586-2964) records: linearize (source transfer), tone / gamut mapping,
-// delinearize (target transfer), dither, and light steps around them. With the two transfer
-// functions fixed at compile time the step bodies are the single case each needs: ~1.5 k
-// instructions, register-resident colour and no local memory, against the general
-// interpreter's 6.9 k (which ncu shows stalling on instruction fetch, profiles/). Per-pixel
-// arithmetic is that of plb_run_color_ops, step for step.
-template <int LIN_TRC, int DELIN_TRC>
-PLB_DEV void plb_run_hdr_ops(int x, int y, float c[4])
-{
-    const plb_color_prog &prog = plb_s_prog;
-    #pragma unroll 1
-    for (int i = 0; i < prog.n; i++) {
-        const plb_color_op &op = prog.ops[i];
-        switch (op.kind) {
-        case PLB_OP_LINEARIZE:   plb_linearize(LIN_TRC, op.u.trc, c); break;
-        case PLB_OP_COLOR_MAP:   plb_color_map(op.u.cmap, c); break;
-        case PLB_OP_DELINEARIZE: plb_delinearize(DELIN_TRC, op.u.trc, c); break;
-        case PLB_OP_DITHER:      plb_dither(op.u.dither, x, y, c); break;
-        case PLB_OP_SCALE:       plb_light_step(op, PLB_OP_SCALE, c); break;
-        case PLB_OP_MATRIX:      plb_light_step(op, PLB_OP_MATRIX, c); break;
-        case PLB_OP_ROUND_FBO:   plb_light_step(op, PLB_OP_ROUND_FBO, c); break;
-        case PLB_OP_ALPHA:       plb_light_step(op, PLB_OP_ALPHA, c); break;
-        case PLB_OP_SWIZZLE:     plb_light_step(op, PLB_OP_SWIZZLE, c); break;
-        default: break;
-        }
-    }
-}
-
 // The same program applied to N pixels in one pass over the op list: the kind dispatch and the
 // swizzle predicates are launch-uniform and evaluated once per step instead of once per pixel;
 // the per-pixel arithmetic of each step is exactly that of plb_run_light_ops. `prog` may live
@@ -915,7 +947,7 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
                        op.u.sigmoid.offset / op.u.sigmoid.scale;
             }
             break;
-        case PLB_OP_COLOR_MAP: plb_color_map<false>(op.u.cmap, c); break;
+        case PLB_OP_COLOR_MAP: plb_color_map<false>(op.u.cmap, c, x, y); break;
         case PLB_OP_DITHER:    plb_dither(op.u.dither, x, y, c); break;
         case PLB_OP_DOVI_RESHAPE: plb_dovi_reshape(c); break;
         case PLB_OP_DOVI_LMS:

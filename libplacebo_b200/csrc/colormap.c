@@ -404,11 +404,6 @@ void pl_shader_color_map_ex(pl_shader sh, const struct pl_color_map_params *para
         return;
     }
 
-    if (params->contrast_recovery && args->feature_map) {
-        plb_shader_fail(sh, "pl_shader_color_map: contrast recovery feature maps are not "
-                        "implemented on the CUDA backend (SURVEY.md §8f)");
-        return;
-    }
 
     struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_COLOR_MAP);
     if (!op)
@@ -460,6 +455,24 @@ void pl_shader_color_map_ex(pl_shader sh, const struct pl_color_map_params *para
             cm->tone_a = 1.0f / lut_range;
             cm->tone_b = -tone.input_min / lut_range;
         }
+    }
+
+    // contrast recovery (colorspace.c:1879-1921): only when the curve compresses
+    if (need_tone_map && tone.input_max >= tone.output_max && params->contrast_recovery &&
+        args->feature_map) {
+        pl_tex fm = args->feature_map;
+        if (!fm->params.sampleable) {
+            plb_shader_fail(sh, "pl_shader_color_map: feature map is not sampleable");
+            return;
+        }
+        cm->has_fmap = 1;
+        cm->fmap = plb_tex_priv(fm)->d;
+        cm->recovery = params->contrast_recovery;
+        cm->fm_size[0] = (float) fm->params.w;
+        cm->fm_size[1] = (float) fm->params.h;
+        cm->fm_pt[0] = (float) (1.0 / fm->params.w);
+        cm->fm_pt[1] = (float) (1.0 / fm->params.h);
+        plb_shader_use_tex(sh, fm);
     }
 
     if (need_gamut_map) {

@@ -179,6 +179,13 @@ struct plb_op_color_map {
     int lut_I, lut_C, lut_h;
     float g_a, g_b;
     float g_nm1[3];                    // LUT addressing per axis: (float) (n - 1)
+    // contrast recovery (colorspace.c:1879-1921): low-pass feature map (r16hf, PQ intensity),
+    // bicubic through four bilinear fetches; positions relative to the pass's output size
+    int has_fmap;
+    struct plb_tex_desc fmap;
+    float recovery;
+    float fm_size[2], fm_pt[2];        // (float) size and (float) (1.0 / size) of the map
+    int out_w, out_h;                  // size of the pass's output (set at launch)
 };
 
 struct plb_op_dither {

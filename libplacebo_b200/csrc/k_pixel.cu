@@ -91,6 +91,12 @@ void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p)
     t->wg_w = PLB_DEF(p->wg_w, 16);
     t->wg_h = PLB_DEF(p->wg_h, 16);
     t->prog = p->prog;
+    for (int i = 0; i < t->prog.n; i++) { // the feature-map position is relative to the output
+        if (t->prog.ops[i].kind == PLB_OP_COLOR_MAP) {
+            t->prog.ops[i].u.cmap.out_w = p->out_w;
+            t->prog.ops[i].u.cmap.out_h = p->out_h;
+        }
+    }
     if (p->has_dovi)
         t->dovi = p->dovi;
 }
@@ -237,7 +243,7 @@ k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
         for (int k = 0; k < 3; k++)
             c[k] = fmaxf(c[k], 0.0f);
         plb_curve3_s<PLB_CV_PQ_EOTF_SDR>(c);
-        plb_color_map<true>(a.cmap, c);
+        plb_color_map<true>(a.cmap, c, gx, gy);
         // pl_shader_delinearize, BT.1886 (colorspace.c:759-767)
         if (a.delin.black_scaled) {
             const float ps_a = 1 / (a.delin.csp_max - a.delin.csp_min),
@@ -317,7 +323,7 @@ static bool pixel_hdr_args(pl_gpu gpu, const struct plb_pixel_launch *p, const p
         pr.ops[2].u.trc.trc != TRC_BT_1886)
         return false;
     h->lin = pr.ops[0].u.trc;
-    h->cmap = pr.ops[1].u.cmap;
+    h->cmap = t->prog.ops[1].u.cmap; // (with the output size filled in by plb_fill_tail)
     h->delin = pr.ops[2].u.trc;
     i = 3;
     for (; i < pr.n && op_is_light(pr.ops[i].kind); i++) {

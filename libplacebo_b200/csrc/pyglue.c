@@ -147,7 +147,7 @@ enum {
     O_SRC_SYS, O_SRC_LEVELS, O_SRC_SAMPLE_DEPTH, O_SRC_COLOR_DEPTH, O_SRC_BIT_SHIFT,
     O_DST_SYS, O_DST_LEVELS, O_DST_SAMPLE_DEPTH, O_DST_COLOR_DEPTH,
     O_CHROMA_LOC, O_DEBAND, O_PEAK, O_ALLOW_DELAYED, O_DITHER, O_CMAP_HQ, O_RING,
-    O_TONE_FN, O_GAMUT_FN, O_GRAIN, O_DOVI, O_ERRDIFF, O_COUNT
+    O_TONE_FN, O_GAMUT_FN, O_GRAIN, O_DOVI, O_ERRDIFF, O_CONTRAST, O_COUNT
 };
 
 // AV1 grain parameters of libplacebo's own test fixture (src/tests/utils.h:240-262): medium
@@ -284,7 +284,8 @@ API int plg_configure(struct plg_stream *s, const int *o, const float *src_csp,
     if (o[O_DITHER] > 1)
         s->dither.method = o[O_DITHER] - 1;
     s->cmap = o[O_CMAP_HQ] ? pl_color_map_high_quality_params : pl_color_map_default_params;
-    s->cmap.contrast_recovery = 0; // outside the hot path
+    if (!o[O_CONTRAST]) // 1: keep the preset's contrast recovery (HQ: 0.3 with the low-pass feature map)
+        s->cmap.contrast_recovery = 0;
     if (o[O_TONE_FN])
         s->cmap.tone_mapping_function = pl_tone_map_functions[o[O_TONE_FN] - 1];
     if (o[O_GAMUT_FN])

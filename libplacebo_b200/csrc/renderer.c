@@ -37,7 +37,7 @@ struct pl_renderer_t {
     pl_fmt fbofmt[5];
     pl_tex fbos[MAX_FBOS];
     bool fbo_used[MAX_FBOS];
-    struct sampler_state sampler_main, samplers_src[4];
+    struct sampler_state sampler_main, sampler_contrast, samplers_src[4];
     pl_shader_obj tone_map_state, dither_state, grain_state[4];
     int prev_dither;
     bool have_frame_index;
@@ -138,6 +138,8 @@ void pl_renderer_destroy(pl_renderer *prr)
         pl_tex_destroy(rr->gpu, &rr->fbos[i]);
     pl_shader_obj_destroy(&rr->sampler_main.up);
     pl_shader_obj_destroy(&rr->sampler_main.down);
+    pl_shader_obj_destroy(&rr->sampler_contrast.up);
+    pl_shader_obj_destroy(&rr->sampler_contrast.down);
     for (int i = 0; i < 4; i++) {
         pl_shader_obj_destroy(&rr->samplers_src[i].up);
         pl_shader_obj_destroy(&rr->samplers_src[i].down);
@@ -492,7 +494,7 @@ static pl_shader img_sh(struct pass_state *pass)
 enum sampler_type { SAMPLER_DIRECT, SAMPLER_NEAREST, SAMPLER_BICUBIC, SAMPLER_HERMITE,
                     SAMPLER_GAUSSIAN, SAMPLER_COMPLEX, SAMPLER_OVERSAMPLE };
 enum sampler_dir { SAMPLER_NOOP, SAMPLER_UP, SAMPLER_DOWN };
-enum sampler_usage { SAMPLER_MAIN, SAMPLER_PLANE };
+enum sampler_usage { SAMPLER_MAIN, SAMPLER_PLANE, SAMPLER_LOWPASS };
 
 struct sampler_info {
     const struct pl_filter_config *config;
@@ -525,7 +527,8 @@ static struct sampler_info sample_src_info(struct pass_state *pass,
     info.dir = PLB_MAX(info.dir_sep[0], info.dir_sep[1]);
     switch (info.dir) {
     case SAMPLER_DOWN:
-        info.config = usage == SAMPLER_PLANE && params->plane_downscaler
+        info.config = usage == SAMPLER_LOWPASS ? &pl_filter_bicubic // renderer.c:630-631
+                    : usage == SAMPLER_PLANE && params->plane_downscaler
                     ? params->plane_downscaler : params->downscaler;
         break;
     case SAMPLER_UP:
@@ -587,7 +590,7 @@ static bool dispatch_sampler(struct pass_state *pass, pl_shader sh, struct sampl
     struct pl_sample_filter_params fp = {
         .filter = *info.config,
         .antiring = params->antiringing_strength,
-        .no_widening = params->skip_anti_aliasing,
+        .no_widening = params->skip_anti_aliasing && usage != SAMPLER_LOWPASS,
         .lut = info.dir == SAMPLER_UP ? &st->up : &st->down,
     };
     bool ok;
@@ -1195,6 +1198,63 @@ done:
 // pass_convert_colors (renderer.c:2157-2279)
 // ---------------------------------------------------------------------------------------
 
+// get_feature_map (renderer.c:2089-2154): the low-pass "feature map" of contrast recovery — the
+// image's PQ intensity (pl_shader_extract_features) at full size into a one-component FBO, then
+// a bicubic down-scaling (widened kernel, mirrored borders) by contrast_smoothness.
+static pl_tex get_feature_map(struct pass_state *pass)
+{
+    const struct pl_render_params *params = pass->params;
+    pl_renderer rr = pass->rr;
+    const struct pl_color_map_params *cparams = PLB_DEF(params->color_map_params, &pl_color_map_default_params);
+    if (!cparams->contrast_recovery || cparams->contrast_smoothness <= 1)
+        return NULL;
+    if (!pl_color_space_is_hdr(&pass->color))
+        return NULL;
+    if (rr->errors & (PL_RENDER_ERR_SAMPLING | PL_RENDER_ERR_CONTRAST_RECOVERY))
+        return NULL;
+    if (pass->color.hdr.max_luma <= pass->target.color.hdr.max_luma + 1e-6)
+        return NULL; // no adaptation needed
+    pl_tex img = img_tex(pass);
+    if (!img)
+        return NULL;
+
+    const float ratio = cparams->contrast_smoothness;
+    const int cr_w = ceilf(abs(pl_rect_w(pass->dst_rect)) / ratio);
+    const int cr_h = ceilf(abs(pl_rect_h(pass->dst_rect)) / ratio);
+    pl_tex inter_tex = get_fbo(pass, pass->w, pass->h, NULL, 1);
+    pl_tex out_tex = get_fbo(pass, cr_w, cr_h, NULL, 1);
+    if (!inter_tex || !out_tex)
+        goto error;
+
+    pl_shader sh = begin(pass);
+    pl_shader_sample_direct(sh, pl_sample_src( .tex = img ));
+    pl_shader_extract_features(sh, pass->color);
+    if (!pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = &sh, .target = inter_tex )))
+        goto error;
+
+    const struct pl_sample_src src = {
+        .tex = inter_tex,
+        .rect = pass->rect,
+        .address_mode = PL_TEX_ADDRESS_MIRROR,
+        .components = 1,
+        .new_w = cr_w,
+        .new_h = cr_h,
+    };
+    sh = begin(pass);
+    if (!dispatch_sampler(pass, sh, &rr->sampler_contrast, SAMPLER_LOWPASS, &src)) {
+        pl_dispatch_abort(rr->dp, &sh);
+        goto error;
+    }
+    if (!pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = &sh, .target = out_tex )))
+        goto error;
+    return out_tex;
+
+error:
+    PLB_ERR(rr->log, "Failed extracting luma for contrast recovery, disabling");
+    rr->errors |= PL_RENDER_ERR_CONTRAST_RECOVERY;
+    return NULL;
+}
+
 static bool pass_convert_colors(struct pass_state *pass)
 {
     pl_renderer rr = pass->rr;
@@ -1219,6 +1279,7 @@ static bool pass_convert_colors(struct pass_state *pass)
 
     if (pass->need_peak_fbo && !img_tex(pass))
         return false;
+    pl_tex feature_map = get_feature_map(pass); // dispatches the pending image shader
     sh = img_sh(pass);
 
     struct pl_color_space src_csp = image->color;
@@ -1234,6 +1295,7 @@ static bool pass_convert_colors(struct pass_state *pass)
         .dst = target->color,
         .prelinearized = prelinearized,
         .state = state,
+        .feature_map = feature_map,
     ));
     pass->color = target->color;
     return !pl_shader_is_failed(sh);

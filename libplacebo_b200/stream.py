@@ -24,7 +24,7 @@ CHROMA = dict(left=1, center=2, top_left=3)
 _OPT_ORDER = ["src_w", "src_h", "chroma_w", "chroma_h", "dst_w", "dst_h", "src_sys", "src_levels",
               "src_sample_depth", "src_color_depth", "src_bit_shift", "dst_sys", "dst_levels",
               "dst_sample_depth", "dst_color_depth", "chroma_loc", "deband", "peak",
-              "allow_delayed", "dither", "cmap_hq", "ring", "tone_fn", "gamut_fn", "grain", "dovi", "errdiff"]
+              "allow_delayed", "dither", "cmap_hq", "ring", "tone_fn", "gamut_fn", "grain", "dovi", "errdiff", "contrast"]
 # pl_error_diffusion_kernels[] order (dither.c)
 ERRDIFF = ["simple", "false-fs", "sierra-lite", "floyd-steinberg", "atkinson", "jarvis-judice-ninke",
            "stucki", "burkes", "sierra-2", "sierra-3"]
@@ -56,6 +56,13 @@ WORKLOADS = {
         src_sys="BT_2020_NC", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
         dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
         upscaler="ewa_lanczos", opts=dict(deband=1, peak=2, dither=1, cmap_hq=1)),
+    "c3_4k_hdr10_to_sdr_hq_preset": dict(
+        desc="config C3 with pl_color_map_high_quality_params unchanged: contrast recovery 0.3 (PQ "
+             "intensity feature map, bicubic low-pass by 3.5, bicubic detail fetch in the tone map)",
+        src=(3840, 2160), dst=(3840, 2160), dst_fmt="rgba8",
+        src_sys="BT_2020_NC", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
+        dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
+        upscaler="ewa_lanczos", opts=dict(deband=1, peak=2, dither=1, cmap_hq=1, contrast=1)),
     "c4_4k_hdr10_to_sdr_av1_grain": dict(
         desc="config C3 + AV1 film grain synthesis (libplacebo test-fixture parameters, block "
              "overlap, new seed every frame) on every plane before scaling",
@@ -134,7 +141,7 @@ class Stream:
                  src_color_depth=10, src_bit_shift=0, dst_sys=SYS["RGB"], dst_levels=LEVELS["FULL"],
                  dst_sample_depth=wl["dst_depth"], dst_color_depth=wl["dst_depth"],
                  chroma_loc=CHROMA["left"], deband=0, peak=0, allow_delayed=0, dither=0,
-                 cmap_hq=0, ring=ring, tone_fn=0, gamut_fn=0, grain=0, dovi=0, errdiff=0)
+                 cmap_hq=0, ring=ring, tone_fn=0, gamut_fn=0, grain=0, dovi=0, errdiff=0, contrast=0)
         o.update(wl.get("opts", {}))
         o.update(over)
         arr = np.array([o[k] for k in _OPT_ORDER], np.int32)

@@ -536,7 +536,8 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
     dither.temporal = opts[11];
     struct pl_color_map_params cmap = opts[4] ? pl_color_map_high_quality_params
                                               : pl_color_map_default_params;
-    cmap.contrast_recovery = 0;
+    if (!opts[15]) /* opts[15]: keep the preset's contrast recovery (HQ: 0.3, smoothness 3.5) */
+        cmap.contrast_recovery = 0;
     if (opts[9])
         cmap.tone_mapping_function = pl_tone_map_functions[opts[9] - 1];
     if (opts[10])

@@ -134,7 +134,7 @@ def av1_oracle_params(descs, chroma, depth, overlap, keep, tex_scale):
 def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0,
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
            coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
-           error_diffusion=None, film_grain=None):
+           error_diffusion=None, film_grain=None, contrast_recovery=0.0, contrast_smoothness=3.5):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
     smoothed (avg, max) between frames like sh_color_map_obj.peak does."""
     t0, orc = T.t0(), T.oracle()
@@ -325,12 +325,36 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
             ext = (-(-out_w // 16) * 16, -(-out_h // 16) * 16)
             color = orc.sample_direct(img_fbo, out_w, out_h, linear=True, coord_mode=coord_mode,
                                       ext=ext)
+    in_fbo = False
     if not measured and want_peak():
         run_peak(color, wg)
         measured = True
         if not allow_delayed:
             color = orc.store_round(color, 0)  # need_peak_fbo: rgba16hf at output size
+            in_fbo = True
     color = np.ascontiguousarray(color[:out_h, :out_w])
+
+    # ---- contrast recovery feature map (get_feature_map, renderer.c:2089-2154)
+    feature = None
+    if (contrast_recovery and contrast_smoothness > 1 and src_hdr
+            and not (src_csp[11] <= dst_csp[11] + 1e-6)):
+        if not in_fbo:
+            color = orc.store_round(color, 0)  # img_tex: the image goes through its rgba16hf FBO
+        lin = orc.linearize(color, src_trc, smin, smax, src_luma)
+        feat = orc.extract_features(lin, t0.matrix(2, t0.raw_primaries(int(src_csp[0]))))
+        inter = orc.store_round(np.ascontiguousarray(feat[..., :1]), 0)  # r16hf FBO, full size
+        cr_w = int(np.ceil(out_w / f32(contrast_smoothness)))
+        cr_h = int(np.ceil(out_h / f32(contrast_smoothness)))
+        # bicubic down-scaling, kernel widened by the scaling ratio, mirrored borders: vertical
+        # pass into an FBO, then the horizontal pass (dispatch_sampler, renderer.c:742-768)
+        fv = t0.filter_generate("bicubic", blur=out_h / cr_h, polar=False)
+        v = orc.sample_ortho(inter, out_w, cr_h, fv, 0, comp_mask=1, coord_mode=coord_mode,
+                             ratio=cr_h / out_h, address=2)
+        v = orc.store_round(np.ascontiguousarray(v[..., :1]), 0)
+        fh = t0.filter_generate("bicubic", blur=out_w / cr_w, polar=False)
+        hh = orc.sample_ortho(v, cr_w, cr_h, fh, 1, comp_mask=1, coord_mode=coord_mode,
+                              ratio=cr_w / out_w, address=2)
+        feature = orc.store_round(np.ascontiguousarray(hh[..., :1]), 0)
 
     # ---- colour mapping (pl_shader_color_map_ex host logic, colorspace.c:1618-1790)
     src2 = src_csp.copy()
@@ -339,7 +363,14 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         src2[19], src2[18] = use[0], use[1]
     cm = color_map_params(t0, src2, dst_csp, hq=cmap_hq, tone_fn=tone_fn, gamut_fn=gamut_fn)
     if cm is not None:
-        color = orc.color_map(color, cm["params"])
+        p = cm["params"]
+        if (feature is not None and p.need_tone_map
+                and float(p.tone_input_max) >= float(p.tone_output_max)):
+            ftex, fkeep = T._tex(feature)
+            p.feature_map = C.pointer(ftex)
+            p.contrast_recovery = float(contrast_recovery)
+            p.width, p.height = out_w, out_h
+        color = orc.color_map(color, p)
 
     # ---- output: encode, dither, scale, store
     enc_skip = (tgt.sys in (T.SYS["UNKNOWN"], T.SYS["RGB"]) and tgt.levels in (0, T.LEVELS["FULL"])

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, peak=0,
                allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, tone_fn=None,
-               gamut_fn=None, error_diffusion=None, grain=None):
+               gamut_fn=None, error_diffusion=None, grain=None, contrast_recovery=0.0):
     Y, U, V = img.planes
     texs = [gpu.tex("r16", p.shape[1], p.shape[0], p) for p in (Y, U, V)]
     dst = gpu.tex(tgt.fmt, tgt.w, tgt.h)
@@ -33,6 +33,7 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
                 opts[12], opts[13] = 3, grain[0]
             else:
                 opts[12], opts[13] = 2 if grain[1] else 1, grain[0]
+        opts[15] = 1 if contrast_recovery else 0
         if getattr(img, "dovi", None) is not None:
             opts[14] = img.dovi + 1
         opts[9] = T.TONE_FNS.index(tone_fn) + 1 if tone_fn else 0
@@ -187,3 +188,26 @@ def test_c5_dolby_vision_gamut_error_diffusion_pipeline(gpu, variant):
     # stated tolerance: +-1 LSB of the output; error diffusion propagates any difference, so the
     # achieved result must be (and is) identical
     assert d.max() == 0, (int(d.max()), float(np.mean(d > 0)))
+
+
+@pytest.mark.parametrize("peak", [0, 2])
+def test_c3_with_contrast_recovery(gpu, peak):
+    """pl_render_high_quality_params' colour mapping as the reference defines it: contrast
+    recovery 0.3 with the low-pass feature map (renderer.c:2089-2154 — feature extraction,
+    widened bicubic down-scaling by 3.5 with mirrored borders — and the bicubic detail fetch of
+    colorspace.c:1879-1921)."""
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(320, 180, seed=41)
+    img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(320, 180, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    kw = dict(upscaler="ewa_lanczos", deband=True, peak=peak, cmap_hq=True, frame_index=0,
+              contrast_recovery=0.3)
+    got, _ = gpu_render(gpu, img, tgt, **kw)
+    want, _ = P.render(img, tgt, **kw)
+    without, _ = P.render(img, tgt, **dict(kw, contrast_recovery=0.0))
+    assert np.mean(want[..., :3] != without[..., :3]) > 0.2  # the feature really changes the picture
+    d = np.abs(got[..., :3].astype(np.int32) - want[..., :3].astype(np.int32))
+    # the separable passes evaluate their sample positions in a different (equally valid) fp32
+    # order than the oracle (1 ULP), which the fp16 feature map mostly absorbs: stated tolerance
+    # +-1 LSB of the 16-bit output, rare pixels
+    assert d.max() <= 1 and np.mean(d > 0) < 1e-3, (int(d.max()), float(np.mean(d > 0)))
