@@ -4,6 +4,14 @@
 // through linear fetches; radius == radius_zero filters use the linear-sampling trick
 // (sampling.c:919-936, 1062-1088: two taps per fetch). Same per-pixel tail as every sampler.
 //
+// Tap fetches: the coordinate of a tap is a texel centre along the filtered axis by construction;
+// when the other axis maps 1:1 onto the whole texture (every pass the renderer's separated
+// scaling issues, renderer.c:745-775) it is a texel centre there too, and a LINEAR fetch at a
+// texel centre returns the texel (texture units quantise the weights to 1/256). Such passes
+// (`aligned`) fetch the nearest texel; with the linear-sampling trick (fractional position along
+// the filtered axis) they interpolate along that axis only. The oracle follows the same rule
+// (orc_sample_ortho).
+//
 // CTA = 32x8 threads over a 32x32 output tile (4 rows per thread); the N <= 2*ceil(R) taps of a
 // warp walk one row segment (horizontal pass) or N rows (vertical pass), so every fetch of a
 // warp is a contiguous, L1-resident segment. Bound: HBM for small N (lanczos N = 6: 6 fetches
@@ -16,6 +24,7 @@ struct ortho_args {
     const float *lut;
     int lut_entries, row_size, row_stride;
     int use_linear;
+    int aligned;     // the unfiltered axis maps 1:1 onto the whole texture (texel centres)
     float antiring, ratio, scale;
     uint8_t comp_mask;
     int pass;
@@ -58,7 +67,10 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
         float off = (float) n;
         if (a.use_linear)
             off += ws[n % 4 + 1];
-        const float4 c4 = plb_tex_linear(a.src, basex + ptx * off, basey + pty * off);
+        const float tu = basex + ptx * off, tv = basey + pty * off;
+        const float4 c4 = !a.aligned ? plb_tex_linear(a.src, tu, tv)
+                        : a.use_linear ? plb_tex_linear_axis(a.src, tu, tv, a.pass == 1 ? 0 : 1)
+                        : plb_tex_nearest(a.src, tu, tv);
         const float c[4] = {c4.x, c4.y, c4.z, c4.w};
         if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
             #pragma unroll
@@ -134,6 +146,71 @@ k_ortho(const __grid_constant__ ortho_args a)
                         (uint32_t) (t.wg_w * t.wg_h));
 }
 
+// The same pass for a one-component half-float plane, aligned taps, no tail (the
+// contrast-recovery low-pass, renderer.c:2133-2150): the value equals ortho_pixel()'s.
+PLB_DEV float ortho_h1_texel(const ortho_args &a, int x, int y)
+{
+    return __half2float(*(const __half *) ((const char *) a.src.ptr + (size_t) y * a.src.pitch + 2 * (size_t) x));
+}
+
+template <int PASS, bool LIN>
+__global__ void __launch_bounds__(256)
+k_ortho_h1(const __grid_constant__ ortho_args a)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x;
+    if (gx >= a.tail.out_w)
+        return;
+    const int N = a.row_size;
+    const int sw = a.src.w, sh = a.src.h, mode = a.src.addr;
+    #pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+        const int gy = blockIdx.y * 32 + threadIdx.y + 8 * r;
+        if (gy >= a.tail.out_h)
+            break;
+        float posx, posy;
+        plb_coord_pos(a.cc, gx, gy, posx, posy);
+        const float f2x = plb_fractf(posx * a.cc.sizex - 0.5f), f2y = plb_fractf(posy * a.cc.sizey - 0.5f);
+        const float dirx = PASS == 1 ? 1.0f : 0.0f, diry = PASS == 0 ? 1.0f : 0.0f;
+        const float fcoord = f2x * dirx + f2y * diry;
+        const float ptx = a.cc.ptx * dirx, pty = a.cc.pty * diry;
+        const float off0 = (float) (N / 2 - 1);
+        const float basex = posx - fcoord * ptx - ptx * off0;
+        const float basey = posy - fcoord * pty - pty * off0;
+        // the coordinate of the unfiltered axis does not depend on the tap (pt = 0)
+        const int fixed = PASS == 0 ? plb_wrap_index((int) floorf(basex * (float) sw), sw, mode)
+                                    : plb_wrap_index((int) floorf(basey * (float) sh), sh, mode);
+        float ca = 0.0f;
+        float ws[4] = {0, 0, 0, 0};
+        for (int n0 = 0; n0 < N; n0 += 4) {
+            ortho_weights(a, n0 / 4, fcoord, ws);
+            #pragma unroll
+            for (int j = 0; j < 4; j += LIN ? 2 : 1) {
+                if (n0 + j >= N)
+                    break;
+                float off = (float) (n0 + j);
+                if (LIN)
+                    off += ws[(j + 1) & 3];
+                const float t = PASS == 0 ? (basey + pty * off) * (float) sh : (basex + ptx * off) * (float) sw;
+                const int lim = PASS == 0 ? sh : sw;
+                float c;
+                if (LIN) {
+                    const float tt = t - 0.5f, b = floorf(tt), f = tt - b;
+                    const int i0 = plb_wrap_index((int) b, lim, mode), i1 = plb_wrap_index((int) b + 1, lim, mode);
+                    const float c0 = PASS == 0 ? ortho_h1_texel(a, fixed, i0) : ortho_h1_texel(a, i0, fixed);
+                    const float c1 = PASS == 0 ? ortho_h1_texel(a, fixed, i1) : ortho_h1_texel(a, i1, fixed);
+                    c = plb_mix(c0, c1, f);
+                } else {
+                    const int i = plb_wrap_index((int) floorf(t), lim, mode);
+                    c = PASS == 0 ? ortho_h1_texel(a, fixed, i) : ortho_h1_texel(a, i, fixed);
+                }
+                ca = __fmaf_rn(ws[j], c, ca);
+            }
+        }
+        *(__half *) ((char *) a.tail.dst.ptr + (size_t) (a.tail.dst_y0 + gy) * a.tail.dst.pitch +
+                     2 * (size_t) (a.tail.dst_x0 + gx)) = __float2half_rn(a.scale * ca);
+    }
+}
+
 #define STREAM(gpu) ((cudaStream_t) plb_gpu_priv(gpu)->stream)
 void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p);
 PLB_DEFINE_PQ_UPLOAD(plb_pq_upload_ortho)
@@ -172,8 +249,29 @@ extern "C" bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p)
     a.tail.wg_w = wg_w;
     a.tail.wg_h = wg_h;
     memcpy(a.tail.src_map, p->src_map, sizeof(p->src_map));
+    // taps on texel centres of both axes (see the header): nearest fetches
+    const bool aligned = tl->coord_mode != PLB_COORD_LITERAL &&
+        (p->pass == 0 ? (p->rect.x0 == 0.0f && p->rect.x1 == (float) p->src.w && tl->out_w == p->src.w)
+                      : (p->rect.y0 == 0.0f && p->rect.y1 == (float) p->src.h && tl->out_h == p->src.h));
+    a.aligned = aligned;
     dim3 block(32, 8);
     dim3 grid((tl->out_w + 31) / 32, (tl->out_h + 31) / 32);
+    const bool use_ar = p->antiring > 0.0f && p->ratio > 1.0f && !p->use_linear;
+    if (aligned && !use_ar && !has_peak && tl->prog.n == 0 && tl->nplanes == 0 && tl->dst.ptr &&
+        p->src.kind == PLB_FK_HALF && p->src.comps == 1 && !p->src.ptr2 &&
+        tl->dst.kind == PLB_FK_HALF && tl->dst.comps == 1 && !tl->dst.ptr2 &&
+        (p->comp_mask & 1) && p->src_map[0] == 0) {
+        if (p->pass == 0 && p->use_linear)
+            k_ortho_h1<0, true><<<grid, block, 0, STREAM(gpu)>>>(a);
+        else if (p->pass == 0)
+            k_ortho_h1<0, false><<<grid, block, 0, STREAM(gpu)>>>(a);
+        else if (p->use_linear)
+            k_ortho_h1<1, true><<<grid, block, 0, STREAM(gpu)>>>(a);
+        else
+            k_ortho_h1<1, false><<<grid, block, 0, STREAM(gpu)>>>(a);
+        g->launches++;
+        return plb_cuda_check(gpu, cudaGetLastError(), "k_ortho_h1");
+    }
     if (has_peak) {
         grid.x = ((tl->out_w + wg_w - 1) / wg_w * wg_w + 31) / 32;
         grid.y = ((tl->out_h + wg_h - 1) / wg_h * wg_h + 31) / 32;

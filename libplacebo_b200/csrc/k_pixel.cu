@@ -217,7 +217,8 @@ PLB_DEV float4 hdr_unpack(uint2 raw)
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
-__global__ void __launch_bounds__(256, 4)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_pixel_hdr(const __grid_constant__ plb_hdr_args a)
 {
     plm_tables_init(); // operands of the exact (out-of-domain) paths
@@ -394,6 +395,85 @@ static bool pixel_hdr_args(pl_gpu gpu, const struct plb_pixel_launch *p, const p
     return true;
 }
 
+// Feature extraction of contrast recovery (get_feature_map, renderer.c:2089-2154): rgba16hf image
+// sampled 1:1 -> [LINEARIZE(PQ)] FEATURES -> r16hf intensity plane. Same arithmetic as the
+// general kernel's steps (color_ops.cuh), curves with immediates.
+struct plb_feat_args {
+    plb_tex_desc src, dst;
+    int dst_x0, dst_y0, out_w, out_h;
+    float src_scale;
+    int linearize;
+    float m[9];
+};
+
+__global__ void __launch_bounds__(256)
+k_pixel_feat(const __grid_constant__ plb_feat_args a)
+{
+    plm_tables_init();
+    __syncthreads();
+    const int gx = blockIdx.x * PIX_TILE + threadIdx.x;
+    const int gy0 = blockIdx.y * PIX_TILE + threadIdx.y;
+    if (gx >= a.out_w || gy0 >= a.out_h)
+        return;
+    const char *src = (const char *) a.src.ptr + (size_t) gx * 8;
+    #pragma unroll 2
+    for (int r = 0; r < PIX_TILE / 8; r++) {
+        const int gy = gy0 + 8 * r;
+        if (gy >= a.out_h)
+            break;
+        const float4 t = hdr_unpack(*(const uint2 *) (src + (size_t) gy * a.src.pitch));
+        float c[3] = { t.x * a.src_scale, t.y * a.src_scale, t.z * a.src_scale };
+        if (a.linearize) {
+            #pragma unroll
+            for (int k = 0; k < 3; k++)
+                c[k] = fmaxf(c[k], 0.0f);
+            plb_curve3_s<PLB_CV_PQ_EOTF_SDR>(c);
+        }
+        plb_matv(a.m, c[0], c[1], c[2]);
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            c[k] = fmaxf(c[k], 0.0f);
+        plb_curve3_s<PLB_CV_PQ_OETF>(c);
+        const float I = __fmaf_rn(0.2f, c[2], __fmaf_rn(0.4f, c[1], 0.4f * c[0]));
+        *(__half *) ((char *) a.dst.ptr + (size_t) (a.dst_y0 + gy) * a.dst.pitch +
+                     (size_t) (a.dst_x0 + gx) * 2) = __float2half_rn(I);
+    }
+}
+
+static bool pixel_feat_args(pl_gpu gpu, const struct plb_pixel_launch *p, const plb_tail_args *t, plb_feat_args *h)
+{
+    if (!p->dst.ptr || p->nplanes != 1 || plb_gpu_priv(gpu)->exact_math)
+        return false;
+    const plb_plane_src &pl = p->planes[0];
+    if (pl.kind != PLB_PLANE_DIRECT || !t->plane_cc[0].ident || pl.tex.ptr2 || pl.tex.addr ||
+        pl.tex.kind != PLB_FK_HALF || pl.tex.comps != 4)
+        return false;
+    for (int k = 0; k < 3; k++) {
+        if (pl.map[k] != k)
+            return false;
+    }
+    if (p->dst.kind != PLB_FK_HALF || p->dst.comps != 1 || p->dst.ptr2)
+        return false;
+    const plb_color_prog &pr = p->prog;
+    memset(h, 0, sizeof(*h));
+    int i = 0;
+    if (pr.n >= 1 && pr.ops[0].kind == PLB_OP_LINEARIZE && pr.ops[0].u.trc.trc == TRC_PQ) {
+        h->linearize = 1;
+        i = 1;
+    }
+    if (pr.n != i + 1 || pr.ops[i].kind != PLB_OP_FEATURES)
+        return false;
+    memcpy(h->m, pr.ops[i].u.features.m, sizeof(h->m));
+    h->src = pl.tex;
+    h->dst = p->dst;
+    h->dst_x0 = p->dst_rect.x0;
+    h->dst_y0 = p->dst_rect.y0;
+    h->out_w = p->out_w;
+    h->out_h = p->out_h;
+    h->src_scale = pl.scale;
+    return true;
+}
+
 // Plane passes without a heavy colour program: debanding and AV1 grain synthesis into an FBO
 // (renderer.c:1276-1551), with at most light steps behind. Sampling, debanding and grain are
 // inline (one pixel at a time, x fastest); only sin/cos is a call.
@@ -488,9 +568,25 @@ extern "C" bool plb_launch_pixel(pl_gpu gpu, const struct plb_pixel_launch *p)
     if (hdr_mode > 0 && pixel_hdr_args(gpu, p, &t, &h)) {
         dim3 block(32, 8);
         dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
-        k_pixel_hdr<<<grid, block, 0, STREAM(gpu)>>>(h);
+        static int hdr_minb; // PLB_HDR_MINB=4|5: resident CTAs per SM the registers are capped for
+        if (!hdr_minb) {
+            const char *e = getenv("PLB_HDR_MINB");
+            hdr_minb = e && atoi(e) == 4 ? 4 : 5;
+        }
+        if (hdr_minb == 4)
+            k_pixel_hdr<4><<<grid, block, 0, STREAM(gpu)>>>(h);
+        else
+            k_pixel_hdr<5><<<grid, block, 0, STREAM(gpu)>>>(h);
         plb_gpu_priv(gpu)->launches++;
         return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_hdr");
+    }
+    plb_feat_args fa;
+    if (hdr_mode > 0 && pixel_feat_args(gpu, p, &t, &fa)) {
+        dim3 block(32, 8);
+        dim3 grid((p->out_w + PIX_TILE - 1) / PIX_TILE, (p->out_h + PIX_TILE - 1) / PIX_TILE);
+        k_pixel_feat<<<grid, block, 0, STREAM(gpu)>>>(fa);
+        plb_gpu_priv(gpu)->launches++;
+        return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_feat");
     }
     if (prog_has_peak(&p->prog)) {
         if (PIX_TILE % t.wg_w || PIX_TILE % t.wg_h ||

@@ -138,6 +138,10 @@ PLB_DEV int plb_wrap_index(int i, int n, int mode)
 {
     if (mode == 0)
         return plb_clampi(i, 0, n - 1);
+    if ((unsigned) i < (unsigned) n)
+        return i;
+    if (mode == 2 && i >= -n && i < 2 * n) // first reflection: no division
+        return i < 0 ? -1 - i : 2 * n - 1 - i;
     const int period = mode == 1 ? n : 2 * n;
     i %= period;
     if (i < 0)
@@ -206,6 +210,29 @@ PLB_DEV float4 plb_tex_linear(const plb_tex_desc &t, float u, float v)
     r.z = plb_mix(plb_mix(a.z, b.z, fx), plb_mix(c.z, d.z, fx), fy);
     r.w = plb_mix(plb_mix(a.w, b.w, fx), plb_mix(c.w, d.w, fx), fy);
     return r;
+}
+
+// LINEAR fetch whose coordinate is a texel centre along one axis (the other axis of a separable
+// pass that maps 1:1): that axis takes its texel (weights quantised to 1/256 by a texture unit:
+// 1, 0), the filtered axis interpolates. axis = 0: interpolate along x; 1: along y.
+PLB_DEV float4 plb_tex_linear_axis(const plb_tex_desc &t, float u, float v, int axis)
+{
+    float4 a, b;
+    float f;
+    if (axis == 0) {
+        const float tx = u * (float) t.w - 0.5f, bx = floorf(tx);
+        const int y = (int) floorf(v * (float) t.h);
+        f = tx - bx;
+        a = plb_load_clamped(t, (int) bx, y);
+        b = plb_load_clamped(t, (int) bx + 1, y);
+    } else {
+        const float ty = v * (float) t.h - 0.5f, by = floorf(ty);
+        const int x = (int) floorf(u * (float) t.w);
+        f = ty - by;
+        a = plb_load_clamped(t, x, (int) by);
+        b = plb_load_clamped(t, x, (int) by + 1);
+    }
+    return make_float4(plb_mix(a.x, b.x, f), plb_mix(a.y, b.y, f), plb_mix(a.z, b.z, f), plb_mix(a.w, b.w, f));
 }
 
 // Store one texel. unorm: round-to-nearest-even of clamp(v)*max (GL/Vulkan conversion rule);

@@ -489,7 +489,10 @@ PLB_DEV void plb_peak_add(plb_peak_smem &s, const plb_op_peak &p, bool valid, in
     const unsigned full = 0xFFFFFFFFu;
     const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
     const int key = valid ? wg_local : -1;
-    const unsigned m = __match_any_sync(full, key);
+    // usual case: the warp's 32 pixels lie in one work group (row segments of tiles whose work
+    // groups are >= 32 wide): one vote instead of a match
+    const int key0 = __shfl_sync(full, key, 0);
+    const unsigned m = __all_sync(full, key == key0) ? full : __match_any_sync(full, key);
     if (valid) {
         const uint32_t gsum = __reduce_add_sync(m, ypq);
         const uint32_t gmax = __reduce_max_sync(m, ypq);

@@ -160,6 +160,29 @@ static inline void tex_linear(const struct orc_tex *t, float u, float v, float o
         out[k] = mixf(mixf(a[k], b[k], fx), mixf(c[k], d[k], fx), fy);
 }
 
+// LINEAR fetch at a texel centre along one axis: that axis takes its texel, the other one
+// interpolates (axis 0: along x, 1: along y)
+static inline void tex_linear_axis(const struct orc_tex *t, float u, float v, int axis, float out[4])
+{
+    const float *a, *b;
+    float f;
+    if (axis == 0) {
+        float tx = u * (float) t->w - 0.5f, bx = floorf(tx);
+        int y = (int) floorf(v * (float) t->h);
+        f = tx - bx;
+        a = texel(t, (int) bx, y);
+        b = texel(t, (int) bx + 1, y);
+    } else {
+        float ty = v * (float) t->h - 0.5f, by = floorf(ty);
+        int x = (int) floorf(u * (float) t->w);
+        f = ty - by;
+        a = texel(t, x, (int) by);
+        b = texel(t, x, (int) by + 1);
+    }
+    for (int k = 0; k < t->comps; k++)
+        out[k] = mixf(a[k], b[k], f);
+}
+
 float orc_tex_linear_r(const struct orc_tex *t, float u, float v)
 {
     float out[4] = {0, 0, 0, 1};
@@ -304,6 +327,9 @@ void orc_sample_ortho(const struct orc_tex *src, struct orc_rect rect, int dw, i
     const int N = p->row_size;
     const int dirx = p->pass == 1, diry = p->pass == 0;
     const bool use_ar = p->antiring > 0 && p->ratio > 1.0f && !p->use_linear;
+    const bool aligned = p->coord_mode != ORC_COORD_LITERAL &&
+        (p->pass == 0 ? (rect.x0 == 0.0f && rect.x1 == (float) src->w && dw == src->w)
+                      : (rect.y0 == 0.0f && rect.y1 == (float) src->h && dh == src->h));
 
     #pragma omp parallel for schedule(static)
     for (int gy = 0; gy < dh; gy++) {
@@ -329,14 +355,24 @@ void orc_sample_ortho(const struct orc_tex *src, struct orc_rect rect, int dw, i
                     off += ws[n % 4 + 1];
                     u = basex + ptx * off;
                     v = basey + pty * off;
-                    tex_linear(src, u, v, c);
+                    if (aligned) // texel centre along the unfiltered axis: interpolate along dir
+                        tex_linear_axis(src, u, v, p->pass == 1 ? 0 : 1, c);
+                    else
+                        tex_linear(src, u, v, c);
                 } else {
                     u = basex + ptx * off;
                     v = basey + pty * off;
                     // setup_src(LINEAR): the texture is bound with linear filtering, but the
-                    // coordinate sits on a texel centre along `dir` and on pos along the
-                    // other axis, which for the 1:1 axis is also a texel centre
-                    tex_linear(src, u, v, c);
+                    // coordinate sits on a texel centre along `dir`; when the other axis maps
+                    // 1:1 onto the whole texture it is a texel centre there too, and a LINEAR
+                    // fetch at a texel centre is the texel (weights quantised to 1/256)
+                    if (aligned) {
+                        const float *px = tex_nearest(src, u, v);
+                        for (int k = 0; k < src->comps; k++)
+                            c[k] = px[k];
+                    } else {
+                        tex_linear(src, u, v, c);
+                    }
                 }
                 if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
                     for (int k = 0; k < src->comps; k++) {
