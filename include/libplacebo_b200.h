@@ -536,24 +536,47 @@ struct pl_glsl_version { /* gpu.h:55-79 — kept so callers can probe compute li
     uint32_t subgroup_size;
     int16_t min_gather_offset, max_gather_offset;
 };
-struct pl_gpu_limits { /* gpu.h:93-141, the members the hot path consults */
+struct pl_gpu_limits { /* gpu.h:93-147, member for member (callers read it through pl_gpu) */
     bool thread_safe;
     bool callbacks;
     size_t max_buf_size;
+    size_t max_ubo_size;
     size_t max_ssbo_size;
+    size_t max_vbo_size;
+    size_t max_mapped_size;
+    uint64_t max_buffer_texels;
+    bool host_cached;
+    bool host_ptr_slow;
+    size_t max_mapped_vram;
+    size_t align_host_ptr;
     uint32_t max_tex_1d_dim, max_tex_2d_dim, max_tex_3d_dim;
+    bool blittable_1d_3d;
     bool buf_transfer;
     size_t align_tex_xfer_pitch;
     size_t align_tex_xfer_offset;
+    size_t max_variable_comps;
+    size_t max_constants;
+    bool array_size_constants;
+    size_t max_pushc_size;
+    size_t align_vertex_stride;
     uint32_t max_dispatch[3];
+    uint32_t fragment_queues;
+    uint32_t compute_queues;
 };
+typedef uint64_t pl_handle_caps;
+struct pl_gpu_handle_caps { pl_handle_caps tex, buf, sync; };    /* gpu.h:166-170: none here */
+struct pl_gpu_pci_address { uint32_t domain, bus, device, function; };
 typedef const struct pl_fmt_t *pl_fmt;
-typedef const struct pl_gpu_t {
+typedef const struct pl_gpu_t { /* gpu.h:213-235 */
     pl_log log;
     struct pl_glsl_version glsl;
     struct pl_gpu_limits limits;
+    struct pl_gpu_handle_caps export_caps;
+    struct pl_gpu_handle_caps import_caps;
+    uint8_t uuid[16];
     pl_fmt *formats;
     int num_formats;
+    struct pl_gpu_pci_address pci;
 } *pl_gpu;
 
 enum pl_fmt_type {
@@ -632,7 +655,11 @@ struct pl_buf_params { /* gpu.h:441-520 */
     pl_debug_tag debug_tag;
 };
 #define pl_buf_params(...) (&(struct pl_buf_params) { __VA_ARGS__ })
-typedef const struct pl_buf_t { struct pl_buf_params params; uint8_t *data; } *pl_buf;
+typedef const struct pl_buf_t { /* gpu.h:524-534 */
+    struct pl_buf_params params;
+    uint8_t *data;
+    struct pl_shared_mem shared_mem;
+} *pl_buf;
 PL_API pl_buf pl_buf_create(pl_gpu gpu, const struct pl_buf_params *params);
 PL_API void pl_buf_destroy(pl_gpu gpu, pl_buf *buf);
 PL_API bool pl_buf_recreate(pl_gpu gpu, pl_buf *buf, const struct pl_buf_params *params);
@@ -640,6 +667,18 @@ PL_API void pl_buf_write(pl_gpu gpu, pl_buf buf, size_t buf_offset, const void *
 PL_API bool pl_buf_read(pl_gpu gpu, pl_buf buf, size_t buf_offset, void *dest, size_t size);
 PL_API void pl_buf_copy(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, size_t src_offset, size_t size);
 PL_API bool pl_buf_poll(pl_gpu gpu, pl_buf buf, uint64_t timeout);
+/* src/gpu.h:145-165 — endian swapping between storable buffers (wordsize 2 or 4; src == dst
+ * allowed for in-place). Library-internal in the reference, exported here because pl_upload_plane
+ * uses it for `pl_plane_data.swapped` and the reference's conformance test calls it. */
+struct pl_buf_copy_swap_params {
+    pl_buf src;
+    size_t src_offset;
+    pl_buf dst;
+    size_t dst_offset;
+    size_t size;
+    int wordsize;
+};
+PL_API bool pl_buf_copy_swap(pl_gpu gpu, const struct pl_buf_copy_swap_params *params);
 
 enum pl_tex_sample_mode { PL_TEX_SAMPLE_NEAREST, PL_TEX_SAMPLE_LINEAR, PL_TEX_SAMPLE_MODE_COUNT };
 enum pl_tex_address_mode { PL_TEX_ADDRESS_CLAMP, PL_TEX_ADDRESS_REPEAT, PL_TEX_ADDRESS_MIRROR, PL_TEX_ADDRESS_MODE_COUNT };
@@ -660,8 +699,11 @@ static inline int pl_tex_params_dimension(const struct pl_tex_params params)
 }
 enum pl_sampler_type { PL_SAMPLER_NORMAL, PL_SAMPLER_RECT, PL_SAMPLER_EXTERNAL, PL_SAMPLER_TYPE_COUNT };
 typedef const struct pl_tex_t *pl_tex;
-struct pl_tex_t {
+struct pl_tex_t { /* gpu.h:755-781 */
     struct pl_tex_params params;
+    pl_tex planes[4];               /* planar formats: none on this backend */
+    pl_tex parent;
+    struct pl_shared_mem shared_mem;
     enum pl_sampler_type sampler_type;
 };
 PL_API pl_tex pl_tex_create(pl_gpu gpu, const struct pl_tex_params *params);

@@ -397,6 +397,7 @@ pl_gpu pl_cuda_create(pl_log log, const struct pl_cuda_params *params)
         p->pub.glsl.min_gather_offset = -32;
         p->pub.glsl.max_gather_offset = 31;
         p->pub.limits.thread_safe = false;
+        p->pub.limits.compute_queues = 1; // the stream runs compute (reference: > 0 excludes dummy GPUs)
         p->pub.limits.callbacks = true;
         p->pub.limits.max_buf_size = prop.totalGlobalMem;
         p->pub.limits.max_ssbo_size = prop.totalGlobalMem;
@@ -832,11 +833,41 @@ void pl_tex_clear(pl_gpu gpu, pl_tex dst, const float color[4])
     plb_gpu_after_use(gpu, &dst, 1);
 }
 
+} // extern "C"
+
+// 32-bit words of an integer texture <- the clear value of their component
+__global__ void k_fill_words(char *ptr, size_t pitch, int words, int rows, int comps, uint4 v)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= words || y >= rows)
+        return;
+    const int c = x % comps;
+    ((uint32_t *) (ptr + (size_t) y * pitch))[x] = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+}
+
+extern "C" {
+
 void pl_tex_clear_ex(pl_gpu gpu, pl_tex dst, const union pl_clear_color color)
 {
     const enum pl_fmt_type type = dst->params.format->type;
     if (type == PL_FMT_UINT || type == PL_FMT_SINT) {
-        PLB_ERR(gpu->log, "pl_tex_clear_ex: integer formats are not clearable on the CUDA backend");
+        // integer texels take the value itself (gpu.h:792-806); 32-bit components
+        DEV_GUARD(gpu);
+        pl_fmt fmt = dst->params.format;
+        const struct plb_tex *t = plb_tex_priv(dst);
+        if (fmt->texel_size != 4u * fmt->num_components) {
+            PLB_ERR(gpu->log, "pl_tex_clear_ex: unsupported integer format %s", fmt->name);
+            return;
+        }
+        plb_gpu_before_use(gpu, &dst, 1);
+        const int words = t->d.w * fmt->num_components;
+        dim3 block(64, 4), grid((words + 63) / 64, (t->d.h + 3) / 4);
+        k_fill_words<<<grid, block, 0, STREAM(gpu)>>>((char *) t->d.ptr, t->d.pitch, words, t->d.h,
+                                                      fmt->num_components,
+                                                      make_uint4(color.u[0], color.u[1], color.u[2], color.u[3]));
+        plb_gpu_priv(gpu)->launches++;
+        plb_cuda_check(gpu, cudaGetLastError(), "k_fill_words");
+        plb_gpu_after_use(gpu, &dst, 1);
         return;
     }
     pl_tex_clear(gpu, dst, color.f);
@@ -863,15 +894,36 @@ void pl_tex_blit(pl_gpu gpu, const struct pl_tex_blit_params *params)
                 sf->name, df->name);
         return;
     }
-    if (sf->type == PL_FMT_UINT || sf->type == PL_FMT_SINT || src->params.d || dst->params.d) {
-        PLB_ERR(gpu->log, "pl_tex_blit: integer and 3D textures are not blittable on the CUDA backend");
+    if (src->params.d || dst->params.d) {
+        PLB_ERR(gpu->log, "pl_tex_blit: 3D textures are not blittable on the CUDA backend");
         return;
     }
     pl_rect3d sr = params->src_rc, dr = params->dst_rc;
     if (!sr.x0 && !sr.x1) sr.x1 = src->params.w;
-    if (!sr.y0 && !sr.y1) sr.y1 = src->params.h;
+    if (!sr.y0 && !sr.y1) sr.y1 = PLB_MAX(src->params.h, 1);
     if (!dr.x0 && !dr.x1) dr.x1 = dst->params.w;
-    if (!dr.y0 && !dr.y1) dr.y1 = dst->params.h;
+    if (!dr.y0 && !dr.y1) dr.y1 = PLB_MAX(dst->params.h, 1);
+    // same format, same size, upright: a plain copy of the texels' bytes (any format, any bits)
+    if (sf == df && sr.x1 - sr.x0 == dr.x1 - dr.x0 && sr.y1 - sr.y0 == dr.y1 - dr.y0 &&
+        sr.x1 > sr.x0 && sr.y1 > sr.y0 && dr.x1 > dr.x0 && dr.y1 > dr.y0 && sr.x0 >= 0 && sr.y0 >= 0 &&
+        dr.x0 >= 0 && dr.y0 >= 0 && sr.x1 <= src->params.w && sr.y1 <= PLB_MAX(src->params.h, 1) &&
+        dr.x1 <= dst->params.w && dr.y1 <= PLB_MAX(dst->params.h, 1)) {
+        const struct plb_tex *st = plb_tex_priv(src), *dt = plb_tex_priv(dst);
+        const size_t ts = sf->texel_size;
+        pl_tex texs[2] = { src, dst };
+        plb_gpu_before_use(gpu, texs, 2);
+        CK(gpu, cudaMemcpy2DAsync((char *) dt->d.ptr + (size_t) dr.y0 * dt->d.pitch + dr.x0 * ts, dt->d.pitch,
+                                  (const char *) st->d.ptr + (size_t) sr.y0 * st->d.pitch + sr.x0 * ts, st->d.pitch,
+                                  (size_t) (sr.x1 - sr.x0) * ts, (size_t) (sr.y1 - sr.y0),
+                                  cudaMemcpyDeviceToDevice, STREAM(gpu)));
+        plb_gpu_after_use(gpu, texs, 2);
+        return;
+    }
+    if (sf->type == PL_FMT_UINT || sf->type == PL_FMT_SINT) {
+        PLB_ERR(gpu->log, "pl_tex_blit: scaled / converting blits of integer textures are not "
+                "supported on the CUDA backend");
+        return;
+    }
     const bool in_src = PLB_MIN(sr.x0, sr.x1) >= 0 && PLB_MAX(sr.x0, sr.x1) <= src->params.w &&
                         PLB_MIN(sr.y0, sr.y1) >= 0 && PLB_MAX(sr.y0, sr.y1) <= src->params.h;
     const bool in_dst = PLB_MIN(dr.x0, dr.x1) >= 0 && PLB_MAX(dr.x0, dr.x1) <= dst->params.w &&
@@ -941,6 +993,21 @@ static bool fix_transfer(pl_gpu gpu, const struct pl_tex_transfer_params *params
     // src/gpu.c strip_coords / infer_rc: empty rect = whole texture
     if (!rc->x0 && !rc->x1) rc->x1 = tex->params.w;
     if (!rc->y0 && !rc->y1) rc->y1 = PLB_MAX(tex->params.h, 1);
+    if (tex->params.d) {
+        // 3D textures are d slices of h rows: whole-slice transfers with the default depth pitch
+        // are runs of rows; anything else is outside what the path needs
+        if (!rc->z0 && !rc->z1) rc->z1 = tex->params.d;
+        const int h = tex->params.h;
+        const size_t rp = params->row_pitch ? params->row_pitch
+                        : (size_t) (rc->x1 - rc->x0) * tex->params.format->texel_size;
+        if (rc->y0 != 0 || rc->y1 != h || rc->z0 < 0 || rc->z1 > tex->params.d || rc->z1 <= rc->z0 ||
+            (params->depth_pitch && params->depth_pitch != rp * h)) {
+            PLB_ERR(gpu->log, "%s: only whole slices of a 3D texture can be transferred", what);
+            return false;
+        }
+        rc->y0 = rc->z0 * h;
+        rc->y1 = rc->z1 * h;
+    }
     if (rc->x0 < 0 || rc->y0 < 0 || rc->x1 > tex->params.w ||
         rc->y1 > PLB_MAX(tex->params.h, 1) * PLB_MAX(tex->params.d, 1) ||
         rc->x1 <= rc->x0 || rc->y1 <= rc->y0) {
@@ -1217,6 +1284,13 @@ bool plb_buf_copy_swap(pl_gpu gpu, pl_buf dst, size_t dst_offset, pl_buf src, si
                                                 (uint32_t *) ((char *) d->dptr + dst_offset), nwords, wordsize);
     plb_gpu_priv(gpu)->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_swap_words");
+}
+
+// src/gpu.h:145-165 (library-internal in the reference; its conformance test calls it)
+bool pl_buf_copy_swap(pl_gpu gpu, const struct pl_buf_copy_swap_params *params)
+{
+    return plb_buf_copy_swap(gpu, params->dst, params->dst_offset, params->src, params->src_offset,
+                             params->size, params->wordsize);
 }
 
 bool pl_buf_poll(pl_gpu gpu, pl_buf buf, uint64_t timeout)

@@ -37,7 +37,7 @@ struct pl_renderer_t {
     pl_fmt fbofmt[5];
     pl_tex fbos[MAX_FBOS];
     bool fbo_used[MAX_FBOS];
-    struct sampler_state sampler_main, sampler_contrast, samplers_src[4];
+    struct sampler_state sampler_main, sampler_contrast, samplers_src[4], samplers_dst[4];
     pl_shader_obj tone_map_state, dither_state, grain_state[4];
     int prev_dither;
     bool have_frame_index;
@@ -140,6 +140,10 @@ void pl_renderer_destroy(pl_renderer *prr)
     pl_shader_obj_destroy(&rr->sampler_main.down);
     pl_shader_obj_destroy(&rr->sampler_contrast.up);
     pl_shader_obj_destroy(&rr->sampler_contrast.down);
+    for (int i = 0; i < 4; i++) {
+        pl_shader_obj_destroy(&rr->samplers_dst[i].up);
+        pl_shader_obj_destroy(&rr->samplers_dst[i].down);
+    }
     for (int i = 0; i < 4; i++) {
         pl_shader_obj_destroy(&rr->samplers_src[i].up);
         pl_shader_obj_destroy(&rr->samplers_src[i].down);
@@ -1321,21 +1325,21 @@ static bool pass_output_target(struct pass_state *pass)
     pl_renderer rr = pass->rr;
     const struct pl_render_params *params = pass->params;
     const struct pl_frame *target = &pass->target;
-    if (target->num_planes != 1) {
-        PLB_ERR(rr->log, "pl_render_image: planar targets are not implemented on the CUDA "
-                "backend yet (single packed RGB(A) plane only)");
-        return false;
-    }
+    const struct pl_plane *ref = &target->planes[pass->dst_ref];
     if (pl_frame_is_cropped(target) && params->border != PL_CLEAR_SKIP) {
         // clear the target to the background colour first (clear_target :2516-2584); only
-        // black / the configured solid colour is supported
+        // black / the configured solid colour is supported, packed targets only
+        if (target->num_planes != 1) {
+            PLB_ERR(rr->log, "pl_render_image: cropped planar targets need border clearing in the "
+                    "target's colour system, which is outside the CUDA hot path (use PL_CLEAR_SKIP)");
+            return false;
+        }
         float bg[4] = { params->background_color[0], params->background_color[1],
                         params->background_color[2], 1.0 - params->background_transparency };
         pl_tex_clear(rr->gpu, target->planes[0].texture, bg);
     }
 
     pl_shader sh = img_sh(pass);
-    const struct pl_plane *plane = &target->planes[0];
 
     // alpha handling for opaque sources / targets (:2713-2761): the hot path has no alpha
     if (pass->comps == 4) {
@@ -1351,56 +1355,117 @@ static bool pass_output_target(struct pass_state *pass)
         pass->color.transfer = PL_COLOR_TRC_ST428;
         pl_shader_delinearize(sh, &pass->color);
     }
+    sh = NULL;
 
-    const int rx0 = pass->dst_rect.x0, ry0 = pass->dst_rect.y0,
-              rx1 = pass->dst_rect.x1, ry1 = pass->dst_rect.y1;
+    // one pass per target plane (:2796-2961)
+    for (int p = 0; p < target->num_planes; p++) {
+        const struct pl_plane *plane = &target->planes[p];
+        const float rx = (float) plane->texture->params.w / ref->texture->params.w,
+                    ry = (float) plane->texture->params.h / ref->texture->params.h;
+        // only integer scaling ratios: fractionally subsampled planes are rounded up to the
+        // next integer size and over-rendered
+        const float rrx = rx >= 1 ? roundf(rx) : 1.0 / roundf(1.0 / rx),
+                    rry = ry >= 1 ? roundf(ry) : 1.0 / roundf(1.0 / ry);
+        const float sx = plane->shift_x, sy = plane->shift_y;
+        pl_rect2df plane_rectf = {
+            .x0 = (pass->dst_rect.x0 - sx) * rrx,
+            .y0 = (pass->dst_rect.y0 - sy) * rry,
+            .x1 = (pass->dst_rect.x1 - sx) * rrx,
+            .y1 = (pass->dst_rect.y1 - sy) * rry,
+        };
+        const int rx0 = floorf(plane_rectf.x0), ry0 = floorf(plane_rectf.y0),
+                  rx1 = ceilf(plane_rectf.x1), ry1 = ceilf(plane_rectf.y1);
+        if (plane->flipped) {
+            PLB_ERR(rr->log, "pl_render_image: flipped target planes are outside the CUDA hot path");
+            return false;
+        }
 
-    const int depth = target->repr.bits.color_depth;
-    int applied_dither = 0;
-    if (depth && (depth < 16 || params->force_dither)) {
-        if (params->error_diffusion && !(rr->errors & PL_RENDER_ERR_ERROR_DIFFUSION)) {
-            pass->sh = NULL;
-            if (plb_pass_error_diffusion(rr, rr->dp, &sh, depth, plane->components, rx1 - rx0,
-                                         ry1 - ry0, rr->fbofmt[4], params->error_diffusion,
-                                         get_fbo_cb, pass)) {
-                applied_dither = depth;
-            } else {
-                rr->errors |= PL_RENDER_ERR_ERROR_DIFFUSION;
-                if (!sh)
-                    return false;
+        if (target->num_planes > 1) {
+            // planar output: every plane samples the encoded image from an intermediate FBO
+            pl_tex tex = img_tex(pass);
+            if (!tex) {
+                PLB_ERR(rr->log, "Output requires multiple planes, but FBOs are unavailable. "
+                        "This combination is unsupported.");
+                return false;
             }
-            pass->sh = sh;
+            uint8_t mask = 0;
+            for (int c = 0; c < plane->components; c++) {
+                if (plane->component_mapping[c] >= 0)
+                    mask |= 1 << plane->component_mapping[c];
+            }
+            const struct pl_sample_src src = {
+                .tex = tex,
+                .new_w = rx1 - rx0,
+                .new_h = ry1 - ry0,
+                .rect = {
+                    .x0 = (rx0 - plane_rectf.x0) / rrx,
+                    .x1 = (rx1 - plane_rectf.x0) / rrx,
+                    .y0 = (ry0 - plane_rectf.y0) / rry,
+                    .y1 = (ry1 - plane_rectf.y0) / rry,
+                },
+                .component_mask = mask,
+            };
+            sh = begin(pass);
+            if (!dispatch_sampler(pass, sh, &rr->samplers_dst[p], SAMPLER_PLANE, &src)) {
+                pl_dispatch_abort(rr->dp, &sh);
+                return false;
+            }
+        } else {
+            sh = img_sh(pass);
+            pass->sh = NULL;
         }
-        if (!applied_dither && params->dither_params) {
-            struct pl_dither_params dparams = *params->dither_params;
-            if (!params->disable_dither_gamma_correction)
-                dparams.transfer = target->color.transfer;
-            pl_shader_dither(sh, depth, &rr->dither_state, &dparams);
-            applied_dither = depth;
+
+        const int depth = target->repr.bits.color_depth;
+        int applied_dither = 0;
+        if (depth && (depth < 16 || params->force_dither)) {
+            if (params->error_diffusion && !(rr->errors & PL_RENDER_ERR_ERROR_DIFFUSION)) {
+                if (plb_pass_error_diffusion(rr, rr->dp, &sh, depth, plane->components, rx1 - rx0,
+                                             ry1 - ry0, rr->fbofmt[4], params->error_diffusion,
+                                             get_fbo_cb, pass)) {
+                    applied_dither = depth;
+                } else {
+                    rr->errors |= PL_RENDER_ERR_ERROR_DIFFUSION;
+                    if (!sh)
+                        return false;
+                }
+            }
+            if (!applied_dither && params->dither_params) {
+                struct pl_dither_params dparams = *params->dither_params;
+                if (!params->disable_dither_gamma_correction)
+                    dparams.transfer = target->color.transfer;
+                pl_shader_dither(sh, depth, &rr->dither_state, &dparams);
+                applied_dither = depth;
+            }
         }
-    }
-    if (applied_dither != rr->prev_dither) {
-        if (applied_dither)
-            PLB_INFO(rr->log, "Dithering to %d bit depth", applied_dither);
-        else
-            PLB_INFO(rr->log, "Dithering disabled");
-        rr->prev_dither = applied_dither;
-    }
+        if (applied_dither != rr->prev_dither) {
+            if (applied_dither)
+                PLB_INFO(rr->log, "Dithering to %d bit depth", applied_dither);
+            else
+                PLB_INFO(rr->log, "Dithering disabled");
+            rr->prev_dither = applied_dither;
+        }
 
-    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
-    if (!op)
-        return false;
-    op->u.scale.s = (float) (1.0 / scale);
-    op->u.scale.with_alpha = 1;
-    if (!plb_record_swizzle(sh, plane->components, plane->component_mapping, false))
-        return false;
-
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
+        if (!op) {
+            pl_dispatch_abort(rr->dp, &sh);
+            return false;
+        }
+        op->u.scale.s = (float) (1.0 / scale);
+        op->u.scale.with_alpha = 1;
+        if (!plb_record_swizzle(sh, plane->components, plane->component_mapping, false)) {
+            pl_dispatch_abort(rr->dp, &sh);
+            return false;
+        }
+        if (!pl_dispatch_finish(rr->dp, pl_dispatch_params(
+                .shader = &sh,
+                .target = plane->texture,
+                .rect = { rx0, ry0, rx1, ry1 },
+            )))
+            return false;
+    }
     pass->sh = NULL;
-    return pl_dispatch_finish(rr->dp, pl_dispatch_params(
-        .shader = &sh,
-        .target = plane->texture,
-        .rect = { rx0, ry0, rx1, ry1 },
-    ));
+    pass->tex = NULL;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@
  * It is the checker for the CUDA kernels in libplacebo_b200/csrc and the "port" CPU baseline
  * of bench.py. It is NOT shipped and nothing under libplacebo_b200/ may include or link it.
  *
- * Pinning status (see DESIGN.md §oracle): the reference's pixel arithmetic exists only as
+ * Pinning status (see DESIGN.md 3.3): the reference's pixel arithmetic exists only as
  * GLSL that cannot execute in this environment, and its own tests do not pin pixel outputs of
  * polar/ortho/deband/grain/dither (src/tests/gpu_tests.c:912-997 are run-only). So:
  *   - every PARAMETER the oracle consumes (filter LUTs, tone/gamut LUTs, matrices, dither
@@ -25,11 +25,16 @@
  *     separately rounded; mix(a,b,t) = a*(1-t) + b*t; length() = sqrtf(x*x + y*y) with the
  *     sum formed as fmaf(x, x, y*y); division by a shader constant is a true division
  *     unless stated otherwise;
- *   - transcendental functions are libm's float versions (powf, expf, logf, sinf, cosf,
- *     atan2f);
+ *   - transcendental functions are DEFINED, not libm's: the transfer curves of
+ *     the hot path are the tabulated cubic composites of pl_oracle_curve.h (byte-identical
+ *     generator in the product, csrc/curves.c), atan2 / sincos the fp32 polynomials of
+ *     pl_oracle_math.h (pf_atan2f, pf_sincosf), everything else the binary64 algorithms of
+ *     pl_oracle_math.h; orc_set_exact_math(1) routes the curves through the latter as well;
  *   - textures hold already-decoded float texel values (unorm: v/(2^n-1) by IEEE division;
- *     fp16: exact widening); nearest sampling picks floor(u*size) clamped to the edge,
- *     linear sampling is an exact fp32 lerp at texel centres +0.5, clamp-to-edge;
+ *     fp16: exact widening); nearest sampling picks floor(u*size) under the address mode,
+ *     linear sampling is an fp32 mix of the four texels around (u*size - 0.5) — except at texel
+ *     centres (1:1 direct sampling of a whole texture, taps of a separable pass whose other axis
+ *     maps 1:1), where it is the texel itself, as on texture hardware;
  *   - linear 1-D LUTs follow the array form of src/shaders/lut.c:700-715.
  */
 #ifndef PL_ORACLE_H_

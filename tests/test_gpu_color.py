@@ -1,7 +1,8 @@
 """Colour shaders (decode, linearize/delinearize, sigmoid, colour map, dither, peak detection)
 through the C ABI against the CPU oracle. Input and output are rgba32f so any difference is
-arithmetic, not storage rounding. Tolerances (written per test) cover the different powf /
-expf / log implementations (CUDA libdevice vs glibc), both within 2 ULP of the true value."""
+arithmetic, not storage rounding. Kernels and oracle share one definition of every
+transcendental function, so most cases are bit-identical; the tolerance written
+in each test is the stated bound (+-1 LSB of a 16-bit output), not an allowance for libm."""
 import numpy as np
 import pytest
 
