@@ -960,6 +960,28 @@ void pl_tex_blit(pl_gpu gpu, const struct pl_tex_blit_params *params)
     free(px);
 }
 
+// Raw texel copy between two textures of the same format (renderer: over-rendered planes)
+bool plb_tex_copy_region(pl_gpu gpu, pl_tex dst, int dx, int dy, pl_tex src, int sx, int sy, int w, int h)
+{
+    DEV_GUARD(gpu);
+    if (src->params.format != dst->params.format || w <= 0 || h <= 0 || dx < 0 || dy < 0 || sx < 0 ||
+        sy < 0 || dx + w > dst->params.w || dy + h > PLB_MAX(dst->params.h, 1) ||
+        sx + w > src->params.w || sy + h > PLB_MAX(src->params.h, 1)) {
+        PLB_ERR(gpu->log, "internal texture copy: bad region");
+        return false;
+    }
+    const struct plb_tex *st = plb_tex_priv(src), *dt = plb_tex_priv(dst);
+    const size_t ts = src->params.format->texel_size;
+    pl_tex texs[2] = { src, dst };
+    plb_gpu_before_use(gpu, texs, 2);
+    const bool ok = CK(gpu, cudaMemcpy2DAsync((char *) dt->d.ptr + (size_t) dy * dt->d.pitch + dx * ts, dt->d.pitch,
+                                              (const char *) st->d.ptr + (size_t) sy * st->d.pitch + sx * ts,
+                                              st->d.pitch, (size_t) w * ts, (size_t) h,
+                                              cudaMemcpyDeviceToDevice, STREAM(gpu)));
+    plb_gpu_after_use(gpu, texs, 2);
+    return ok;
+}
+
 bool pl_fmt_is_ordered(pl_fmt fmt)
 {
     bool ordered = true;

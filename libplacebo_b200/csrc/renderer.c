@@ -1456,12 +1456,33 @@ static bool pass_output_target(struct pass_state *pass)
             pl_dispatch_abort(rr->dp, &sh);
             return false;
         }
-        if (!pl_dispatch_finish(rr->dp, pl_dispatch_params(
-                .shader = &sh,
-                .target = plane->texture,
-                .rect = { rx0, ry0, rx1, ry1 },
-            )))
+        // The rounded rect of a subsampled plane may overhang its texture by a pixel (the
+        // reference over-renders and lets the rasteriser clip, dispatch.c:1290-1296): render
+        // such planes into a scratch texture of the plane's format and copy the visible part.
+        const int tw = plane->texture->params.w, th = plane->texture->params.h;
+        const bool overhang = rx0 < 0 || ry0 < 0 || rx1 > tw || ry1 > th;
+        pl_tex out = plane->texture;
+        pl_rect2d rc = { rx0, ry0, rx1, ry1 };
+        if (overhang) {
+            out = get_fbo(pass, rx1 - rx0, ry1 - ry0, plane->texture->params.format, 0);
+            if (!out) {
+                pl_dispatch_abort(rr->dp, &sh);
+                return false;
+            }
+            rc = (pl_rect2d) { 0, 0, rx1 - rx0, ry1 - ry0 };
+        }
+        if (!pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = &sh, .target = out, .rect = rc )))
             return false;
+        if (overhang) {
+            extern bool plb_tex_copy_region(pl_gpu gpu, pl_tex dst, int dx, int dy, pl_tex src,
+                                            int sx, int sy, int w, int h);
+            const int cx0 = PLB_MAX(rx0, 0), cy0 = PLB_MAX(ry0, 0),
+                      cx1 = PLB_MIN(rx1, tw), cy1 = PLB_MIN(ry1, th);
+            if (cx1 > cx0 && cy1 > cy0 &&
+                !plb_tex_copy_region(rr->gpu, plane->texture, cx0, cy0, out, cx0 - rx0, cy0 - ry0,
+                                     cx1 - cx0, cy1 - cy0))
+                return false;
+        }
     }
     pass->sh = NULL;
     pass->tex = NULL;

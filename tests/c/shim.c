@@ -56,6 +56,9 @@ struct shim_ctx {
     pl_dispatch dp;
     pl_renderer rr;
     struct shim_objs objs;
+    /* planar target of the next shim_render call (shim_set_target_planes) */
+    int tgt_nplanes, tgt_chroma_loc;
+    pl_tex tgt_planes[3];
 };
 
 API void *shim_create(int literal_coords)
@@ -453,6 +456,17 @@ done:
  */
 static struct pl_av1_grain_data shim_av1_fixture(void);
 
+/* The next shim_render writes a planar target instead of `dst`: n = 3 one-component planes
+ * (Y, Cb, Cr) or n = 2 (Y + interleaved CbCr, NV12 / P010 style); chroma planes may be
+ * subsampled, sited at `chroma_loc`. */
+API void shim_set_target_planes(struct shim_ctx *c, int n, void **texs, int chroma_loc)
+{
+    c->tgt_nplanes = n;
+    c->tgt_chroma_loc = chroma_loc;
+    for (int i = 0; i < n && i < 3; i++)
+        c->tgt_planes[i] = texs[i];
+}
+
 API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, const float *img,
                     const float *tgt, const int *opts, const char *upscaler,
                     const char *plane_upscaler, const char *downscaler, float *out_peak)
@@ -525,6 +539,21 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
                   .bits = { (int) tgt[2], (int) tgt[3], (int) tgt[4] } },
         .color = csp_from_flat(tgt + 5),
     };
+    if (c->tgt_nplanes > 1) {
+        target.num_planes = c->tgt_nplanes;
+        target.planes[0] = (struct pl_plane) { .texture = c->tgt_planes[0], .components = 1,
+                                               .component_mapping = { PL_CHANNEL_Y } };
+        if (c->tgt_nplanes == 2) {
+            target.planes[1] = (struct pl_plane) { .texture = c->tgt_planes[1], .components = 2,
+                                                   .component_mapping = { PL_CHANNEL_CB, PL_CHANNEL_CR } };
+        } else {
+            for (int i = 1; i < 3; i++)
+                target.planes[i] = (struct pl_plane) { .texture = c->tgt_planes[i], .components = 1,
+                                                       .component_mapping = { i } };
+        }
+        pl_frame_set_chroma_location(&target, c->tgt_chroma_loc ? c->tgt_chroma_loc : PL_CHROMA_LEFT);
+        c->tgt_nplanes = 0;
+    }
 
     struct pl_deband_params deband = pl_deband_default_params;
     struct pl_peak_detect_params peak = opts[1] == 2 ? pl_peak_detect_high_quality_params

@@ -49,12 +49,21 @@ class Frame:
 
 
 class Target:
+    """`planes`: None for one packed plane of format `fmt`, else a list of (format, component
+    indices, (sub_x, sub_y)) — e.g. yuv420p16 = [("r16", (0,), (1, 1)), ("r16", (1,), (2, 2)),
+    ("r16", (2,), (2, 2))], P016 = [("r16", (0,), (1, 1)), ("rg16", (1, 2), (2, 2))]; subsampled
+    planes are sited at `chroma_loc`."""
     def __init__(self, w, h, fmt="rgba16hf", sys=T.SYS["RGB"], levels=T.LEVELS["FULL"],
-                 sample_depth=0, color_depth=0, csp=None):
+                 sample_depth=0, color_depth=0, csp=None, planes=None, chroma_loc="left"):
         self.w, self.h, self.fmt = w, h, fmt
         self.sys, self.levels = sys, levels
         self.bits = (sample_depth, color_depth, 0)
         self.csp = csp if csp is not None else T.csp()
+        self.planes, self.chroma_loc = planes, chroma_loc
+
+    def plane_size(self, i):
+        sx, sy = self.planes[i][2]
+        return (self.w + sx - 1) // sx, (self.h + sy - 1) // sy
 
 
 CHROMA_SHIFT = {"left": (-0.5, 0.0), "center": (0.0, 0.0), "top_left": (-0.5, -0.5)}
@@ -380,6 +389,9 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         enc = t0.repr_encode(tgt.sys, tgt.levels, tbits[0], tbits[0], 0)
         color = orc.apply_matrix(color, enc["m"], enc["c"])
     depth = tbits[1]
+    if tgt.planes:
+        return planar_output(orc, t0, color, tgt, tnorm, depth, dither, int(dst_csp[1]), frame_index,
+                             coord_mode), new_state
     if depth and depth < 16 and error_diffusion:
         # pass_error_diffusion (renderer.c:2282-2343): image -> rgba16hf FBO -> single work
         # group diffusion -> rgba16hf FBO -> sampled 1:1
@@ -394,6 +406,41 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     color = orc.scale(color, float(f32(1.0 / tnorm)), True)
     color[..., 3] = 1.0  # swizzle_color leaves alpha = 1 for opaque images
     return store(orc, color, tgt.fmt), new_state
+
+
+def planar_output(orc, t0, color, tgt, tnorm, depth, dither, dst_trc, frame_index, coord_mode):
+    """pass_output_target with several target planes (renderer.c:2796-2961): the encoded image
+    goes to an rgba16hf FBO; every plane samples it (1:1 -> nearest; subsampled planes through
+    the plane down-scaler, none configured = bilinear pl_shader_sample_direct) over its rounded,
+    possibly over-rendered rect, dithers, scales, swizzles and stores the part inside the plane."""
+    H, W = color.shape[:2]
+    fbo = orc.store_round(color, 0)
+    outs = []
+    for i, (fmt, comps, (ssx, ssy)) in enumerate(tgt.planes):
+        pw, ph = tgt.plane_size(i)
+        rrx, rry = f32(1.0 / ssx), f32(1.0 / ssy)
+        sx, sy = CHROMA_SHIFT[tgt.chroma_loc] if (ssx > 1 or ssy > 1) else (0.0, 0.0)
+        sx, sy = f32(sx), f32(sy)
+        x0f, y0f = (f32(0) - sx) * rrx, (f32(0) - sy) * rry
+        x1f, y1f = (f32(W) - sx) * rrx, (f32(H) - sy) * rry
+        rx0, ry0 = int(np.floor(x0f)), int(np.floor(y0f))
+        rx1, ry1 = int(np.ceil(x1f)), int(np.ceil(y1f))
+        rect = (float((f32(rx0) - x0f) / rrx), float((f32(ry0) - y0f) / rry),
+                float((f32(rx1) - x0f) / rrx), float((f32(ry1) - y0f) / rry))
+        nw, nh = rx1 - rx0, ry1 - ry0
+        unscaled = ssx == 1 and ssy == 1
+        c = orc.sample_direct(fbo, nw, nh, linear=not unscaled, rect=rect, coord_mode=coord_mode)
+        if depth and depth < 16 and dither:
+            lut = t0.dither_matrix(0 if dither == 1 else 1, 64) if dither in (1, 2) else None
+            method = {1: 0, 2: 1, 3: 2, 4: 3}[dither]
+            c = orc.dither(c, depth, method, lut, False, frame_index, approx_gamma(dst_trc))
+        c = orc.scale(c, float(f32(1.0 / tnorm)), True)
+        c = c[max(-ry0, 0):max(-ry0, 0) + min(ry1, ph) - max(ry0, 0),
+              max(-rx0, 0):max(-rx0, 0) + min(rx1, pw) - max(rx0, 0)][..., list(comps)]
+        bits = 8 if fmt.endswith("8") else 16
+        o = orc.store_unorm(np.ascontiguousarray(c), bits)
+        outs.append(o.astype(np.uint8) if bits == 8 else o)
+    return outs
 
 
 def approx_gamma(trc):

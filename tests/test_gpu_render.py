@@ -19,6 +19,11 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
     Y, U, V = img.planes
     texs = [gpu.tex("r16", p.shape[1], p.shape[0], p) for p in (Y, U, V)]
     dst = gpu.tex(tgt.fmt, tgt.w, tgt.h)
+    ptex = []
+    if tgt.planes:  # planar target: shim_set_target_planes overrides `dst` for the next render
+        ptex = [gpu.tex(fmt, *tgt.plane_size(i)) for i, (fmt, _, _) in enumerate(tgt.planes)]
+        gpu.lib.shim_set_target_planes(C.c_void_p(gpu.ctx), len(ptex), (C.c_void_p * len(ptex))(*ptex),
+                                       P.CHROMA_ENUM[tgt.chroma_loc])
     try:
         planes = (C.c_void_p * 3)(*texs)
         iarr = np.concatenate([[img.sys, img.levels, *img.bits], img.csp]).astype(T.f32)
@@ -43,9 +48,12 @@ def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, p
                                 T.fp(tarr), T.ip(opts), upscaler.encode(),
                                 plane_upscaler.encode(), b"", T.fp(peak_out))
         assert r == 0, f"pl_render_image failed / degraded: {r}"
+        if tgt.planes:
+            return [gpu.download(t, fmt, *tgt.plane_size(i))
+                    for i, (t, (fmt, _, _)) in enumerate(zip(ptex, tgt.planes))], peak_out
         return gpu.download(dst, tgt.fmt, tgt.w, tgt.h), peak_out
     finally:
-        gpu.free(dst, *texs)
+        gpu.free(dst, *texs, *ptex)
 
 
 SDR = T.csp(T.PRIM["BT_709"], T.TRC["BT_1886"])
@@ -211,3 +219,30 @@ def test_c3_with_contrast_recovery(gpu, peak):
     # order than the oracle (1 ULP), which the fp16 feature map mostly absorbs: stated tolerance
     # +-1 LSB of the 16-bit output, rare pixels
     assert d.max() <= 1 and np.mean(d > 0) < 1e-3, (int(d.max()), float(np.mean(d > 0)))
+
+
+YUV420P16 = [("r16", (0,), (1, 1)), ("r16", (1,), (2, 2)), ("r16", (2,), (2, 2))]
+P016 = [("r16", (0,), (1, 1)), ("rg16", (1, 2), (2, 2))]
+
+
+@pytest.mark.parametrize("layout,loc,depth", [(YUV420P16, "left", 10), (YUV420P16, "center", 16),
+                                              (P016, "top_left", 10), (P016, "left", 16)])
+def test_planar_yuv_target(gpu, layout, loc, depth):
+    """Planar render targets (pass_output_target with several planes, renderer.c:2796-2961):
+    HDR10 4:2:0 in -> tone / gamut mapped BT.709 limited-range YCbCr 4:2:0 out, as three planes
+    (yuv420p) or two (NV12 / P010 layout), chroma sited left / centre / top-left, dithered to 10
+    bits or full 16-bit. Every plane must equal the oracle's (bit-exact)."""
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(160, 90, seed=21, kind="noise")
+    img = P.Frame(planes, T.SYS["BT_2020_NC"], csp=HDR10)
+    tgt = P.Target(160, 90, "rgba16", sys=T.SYS["BT_709"], levels=T.LEVELS["LIMITED"],
+                   sample_depth=16, color_depth=depth, csp=SDR, planes=layout, chroma_loc=loc)
+    kw = dict(plane_upscaler="ewa_lanczos", deband=True, peak=2, dither=1, cmap_hq=True, frame_index=2)
+    got, _ = gpu_render(gpu, img, tgt, **kw)
+    want, _ = P.render(img, tgt, **kw)
+    assert len(got) == len(want) == len(layout)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.shape == w.shape, (i, g.shape, w.shape)
+        d = np.abs(g.astype(np.int64) - w.astype(np.int64))
+        # stated tolerance +-1 LSB of the 16-bit plane; achieved: bit-exact
+        assert d.max() == 0, (i, int(d.max()), float(np.mean(d > 0)))
