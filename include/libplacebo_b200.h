@@ -882,6 +882,20 @@ PL_API void pl_shader_linearize(pl_shader sh, const struct pl_color_space *csp);
 /* shaders/colorspace.h:185-189: perceptual intensity of the (non-linear) input colour in `csp` */
 PL_API void pl_shader_extract_features(pl_shader sh, struct pl_color_space csp);
 PL_API void pl_shader_delinearize(pl_shader sh, const struct pl_color_space *csp);
+/* shaders/lut.h:30-78 — custom 1-D / 3-D LUTs (.cube files). `data` holds size[0] (x size[1] x
+ * size[2]) RGB triples, red fastest; all-zero shaper matrices are skipped. */
+struct pl_custom_lut {
+    uint64_t signature;
+    int size[3];
+    const float *data;
+    pl_matrix3x3 shaper_in, shaper_out;
+    struct pl_color_repr repr_in, repr_out;
+    struct pl_color_space color_in, color_out;
+};
+PL_API struct pl_custom_lut *pl_lut_parse_cube(pl_log log, const char *str, size_t str_len);
+PL_API void pl_lut_free(struct pl_custom_lut **lut);
+PL_API void pl_shader_custom_lut(pl_shader sh, const struct pl_custom_lut *lut,
+                                 pl_shader_obj *lut_state);
 struct pl_sigmoid_params { float center, slope; };
 #define PL_SIGMOID_DEFAULTS .center = 0.75, .slope = 6.50,
 PL_API extern const struct pl_sigmoid_params pl_sigmoid_default_params;
@@ -1152,7 +1166,7 @@ struct pl_render_params { /* renderer.h:130-368; members outside the hot path ar
     const void *distort_params;
     const void * const *hooks;
     int num_hooks;
-    const void *lut;
+    const struct pl_custom_lut *lut;    /* renderer.h:259-270 */
     enum pl_lut_type lut_type;
     enum pl_clear_mode background;
     enum pl_clear_mode border;
@@ -1214,7 +1228,7 @@ struct pl_frame { /* renderer.h:528-655 */
     struct pl_color_space color;
     const void *icc;            /* pl_icc_object: must be NULL (ICC is outside the hot path) */
     struct pl_icc_profile { const void *data; size_t len; uint64_t signature; } profile; /* must be empty */
-    const void *lut;
+    const struct pl_custom_lut *lut;    /* renderer.h:590-600 */
     enum pl_lut_type lut_type;
     pl_rect2df crop;
     pl_rotation rotation;

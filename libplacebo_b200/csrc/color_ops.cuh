@@ -444,6 +444,65 @@ PLB_DEV float plb_fmap_linear(const plb_tex_desc &t, float u, float v)
     return plb_mix(plb_mix(a, b, fx), plb_mix(c, d, fx), fy);
 }
 
+// pl_shader_custom_lut (shaders/lut.c:212-280). 1-D: every channel through its own component,
+// linear in the table (lut.c:700-715 form); 3-D: tetrahedral interpolation (lut.c:773-809):
+// the cube cell is cut into six tetrahedra along the black-white diagonal, the four vertices
+// are fetched as texels and blended with barycentric weights in the order the GLSL adds them.
+PLB_DEV float4 plb_lut3_texel(const float *lut, const int size[3], int x, int y, int z)
+{
+    return __ldg((const float4 *) lut + ((size_t) z * size[1] + y) * size[0] + x);
+}
+
+static __device__ __noinline__ void plb_custom_lut(const plb_color_op &op, float c[4])
+{
+    const float *lut = op.u.custom_lut.lut;
+    const int *size = op.u.custom_lut.size;
+    if (op.u.custom_lut.has_in)
+        plb_matv(op.u.custom_lut.shaper_in, c[0], c[1], c[2]);
+    if (!size[1]) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float fpos = plb_clamp(c[k], 0.0f, 1.0f) * (float) (size[0] - 1);
+            const float fbase = floorf(fpos), fceil = ceilf(fpos);
+            c[k] = plb_mix(lut[4 * (int) fbase + k], lut[4 * (int) fceil + k], fpos - fbase);
+        }
+    } else {
+        float pos[3], base[3], f[3];
+        int v0[3], v3[3], v1[3], v2[3];
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            pos[k] = plb_clamp(c[k], 0.0f, 1.0f) * (float) (size[k] - 1);
+            base[k] = floorf(pos[k]);
+            f[k] = pos[k] - base[k];
+            v0[k] = v1[k] = (int) base[k];
+            v3[k] = v2[k] = (int) ceilf(pos[k]);
+        }
+        // c_ab = fpart.a >= fpart.b for (x,y), (y,z), (z,x); the reversed tests are their negations
+        const bool cxy = f[0] >= f[1], cyz = f[1] >= f[2], czx = f[2] >= f[0];
+        const bool cyx = !cxy, czy = !cyz, cxz = !czx;
+        float s[3] = { f[0], f[1], f[2] };
+#define TETRA(X, Y, Z, CA, CB) \
+        if ((CA) && (CB)) { s[0] = f[X]; s[1] = f[Y]; s[2] = f[Z]; v1[X] = v3[X]; v2[Z] = v0[Z]; }
+        TETRA(0, 1, 2, cxy, cyz)
+        TETRA(0, 2, 1, cxz, czy)
+        TETRA(2, 0, 1, czx, cxy)
+        TETRA(2, 1, 0, czy, cyx)
+        TETRA(1, 2, 0, cyz, czx)
+        TETRA(1, 0, 2, cyx, cxz)
+#undef TETRA
+        const float4 t0 = plb_lut3_texel(lut, size, v0[0], v0[1], v0[2]);
+        const float4 t1 = plb_lut3_texel(lut, size, v1[0], v1[1], v1[2]);
+        const float4 t2 = plb_lut3_texel(lut, size, v2[0], v2[1], v2[2]);
+        const float4 t3 = plb_lut3_texel(lut, size, v3[0], v3[1], v3[2]);
+        const float w0 = 1.0f - s[0], w1 = s[0] - s[1], w2 = s[1] - s[2], w3 = s[2];
+        c[0] = w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
+        c[1] = w0 * t0.y + w1 * t1.y + w2 * t2.y + w3 * t3.y;
+        c[2] = w0 * t0.z + w1 * t1.z + w2 * t2.z + w3 * t3.z;
+    }
+    if (op.u.custom_lut.has_out)
+        plb_matv(op.u.custom_lut.shaper_out, c[0], c[1], c[2]);
+}
+
 // `tone_map(x)` of pl_shader_color_map_ex: clip / linear fast paths or the 1-D LUT (:1826-1876)
 PLB_DEV float plb_tone_map_x(const plb_op_color_map &p, float x)
 {
@@ -928,6 +987,7 @@ static __device__ __noinline__ void plb_run_color_ops(int x, int y, float c[4],
             c[1] = 0.0f; c[2] = 0.0f; c[3] = 1.0f;
             break;
         }
+        case PLB_OP_CUSTOM_LUT: plb_custom_lut(op, c); break;
         case PLB_OP_LINEARIZE:   plb_linearize(op.u.trc.trc, op.u.trc, c); break;
         case PLB_OP_DELINEARIZE: plb_delinearize(op.u.trc.trc, op.u.trc, c); break;
         case PLB_OP_DECODE_SPECIAL: plb_decode_special(op.u.special.sys, c); break;

@@ -157,6 +157,7 @@ enum plb_op_kind {
     PLB_OP_PEAK,           // pl_shader_detect_peak tap (needs block-wide reduction)
     PLB_OP_SWIZZLE,        // swizzle_color (src/renderer.c:791-808)
     PLB_OP_FEATURES,       // pl_shader_extract_features: linear RGB -> IPT intensity
+    PLB_OP_CUSTOM_LUT,     // pl_shader_custom_lut (1-D per channel, 3-D tetrahedral)
 };
 
 struct plb_trc_consts {
@@ -227,6 +228,12 @@ struct plb_color_op {
         struct plb_op_peak peak;
         struct { int8_t map[4]; int comps; int force_alpha; } swizzle;
         struct { float m[9]; } features;  // (SDR_WHITE / 10000) * rgb2lms
+        struct {                          // pl_shader_custom_lut
+            const float *lut;             // device, 4 floats per entry (r fastest)
+            int size[3];                  // size[1] == 0: 1-D
+            int has_in, has_out;
+            float shaper_in[9], shaper_out[9];
+        } custom_lut;
     } u;
 };
 

@@ -39,6 +39,7 @@ struct pl_renderer_t {
     bool fbo_used[MAX_FBOS];
     struct sampler_state sampler_main, sampler_contrast, samplers_src[4], samplers_dst[4];
     pl_shader_obj tone_map_state, dither_state, grain_state[4];
+    pl_shader_obj lut_state[3];     // LUT_IMAGE, LUT_TARGET, LUT_PARAMS (renderer.c:96-100)
     int prev_dither;
     bool have_frame_index;
     uint8_t frame_index;
@@ -140,6 +141,8 @@ void pl_renderer_destroy(pl_renderer *prr)
     pl_shader_obj_destroy(&rr->sampler_main.down);
     pl_shader_obj_destroy(&rr->sampler_contrast.up);
     pl_shader_obj_destroy(&rr->sampler_contrast.down);
+    for (int i = 0; i < 3; i++)
+        pl_shader_obj_destroy(&rr->lut_state[i]);
     for (int i = 0; i < 4; i++) {
         pl_shader_obj_destroy(&rr->samplers_dst[i].up);
         pl_shader_obj_destroy(&rr->samplers_dst[i].down);
@@ -288,6 +291,28 @@ struct pass_state {
     struct pl_color_repr repr;
     struct pl_color_space color;
 };
+
+enum { LUT_IMAGE, LUT_TARGET, LUT_PARAMS };
+
+// renderer.c:1447-1469
+static enum pl_lut_type guess_frame_lut_type(const struct pl_frame *frame, bool reversed)
+{
+    if (!frame->lut)
+        return PL_LUT_UNKNOWN;
+    if (frame->lut_type)
+        return frame->lut_type;
+    enum pl_color_system sys_in = frame->lut->repr_in.sys, sys_out = frame->lut->repr_out.sys;
+    if (reversed) {
+        const enum pl_color_system t = sys_in;
+        sys_in = sys_out;
+        sys_out = t;
+    }
+    if (sys_in == PL_COLOR_SYSTEM_RGB && sys_out == sys_in)
+        return PL_LUT_NORMALIZED;
+    if (sys_in == frame->repr.sys && sys_out == PL_COLOR_SYSTEM_RGB)
+        return PL_LUT_CONVERSION;
+    return PL_LUT_NATIVE; // unknown: the default
+}
 
 static bool fix_refs_and_rects(struct pass_state *pass)
 {
@@ -1062,11 +1087,33 @@ static bool pass_read_image(struct pass_state *pass)
     pass->rect = (pl_rect2df) { off_x, off_y, off_x + pl_rect_w(ref_rc), off_y + pl_rect_h(ref_rc) };
     pass->ref_rect = pass->rect;
 
-    if (pass->repr.sys == PL_COLOR_SYSTEM_XYZ) {
-        pl_shader_linearize(sh, &pass->color);
-        pass->color.transfer = PL_COLOR_TRC_LINEAR;
+    // LUT logic and colour decoding (renderer.c:1919-1946)
+    const enum pl_lut_type lut_type = guess_frame_lut_type(image, false);
+    bool needs_conversion = true;
+    if (lut_type == PL_LUT_NATIVE || lut_type == PL_LUT_CONVERSION) {
+        // fix the bit depth normalisation before applying the LUT
+        const float scale = pl_color_repr_normalize(&pass->repr);
+        struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_SCALE);
+        if (!op)
+            goto error;
+        op->u.scale.s = scale;
+        op->u.scale.with_alpha = 1;
+        pl_shader_custom_lut(sh, image->lut, &rr->lut_state[LUT_IMAGE]);
+        if (lut_type == PL_LUT_CONVERSION) {
+            pass->repr.sys = PL_COLOR_SYSTEM_RGB;
+            pass->repr.levels = PL_COLOR_LEVELS_FULL;
+            needs_conversion = false;
+        }
     }
-    pl_shader_decode_color(sh, &pass->repr, params->color_adjustment);
+    if (needs_conversion) {
+        if (pass->repr.sys == PL_COLOR_SYSTEM_XYZ) {
+            pl_shader_linearize(sh, &pass->color);
+            pass->color.transfer = PL_COLOR_TRC_LINEAR;
+        }
+        pl_shader_decode_color(sh, &pass->repr, params->color_adjustment);
+    }
+    if (lut_type == PL_LUT_NORMALIZED)
+        pl_shader_custom_lut(sh, image->lut, &rr->lut_state[LUT_IMAGE]);
     pl_shader_set_alpha(sh, &pass->repr, PL_ALPHA_PREMULTIPLIED);
     return !pl_shader_is_failed(sh);
 
@@ -1096,6 +1143,8 @@ static void hdr_update_peak(struct pass_state *pass)
         goto cleanup; // nothing to adapt
     if (pass->color.hdr.avg_pq_y)
         goto cleanup; // dynamic metadata already present
+    if (params->lut && params->lut_type == PL_LUT_CONVERSION)
+        goto cleanup; // LUT handles tone mapping
     const struct pl_color_map_params *cpars = params->color_map_params;
     const enum pl_hdr_metadata_type metadata = cpars ? cpars->metadata : PL_HDR_METADATA_ANY;
     if (metadata && metadata != PL_HDR_METADATA_CIE_Y)
@@ -1218,6 +1267,8 @@ static pl_tex get_feature_map(struct pass_state *pass)
         return NULL;
     if (pass->color.hdr.max_luma <= pass->target.color.hdr.max_luma + 1e-6)
         return NULL; // no adaptation needed
+    if (params->lut && params->lut_type == PL_LUT_CONVERSION)
+        return NULL; // LUT handles tone mapping
     pl_tex img = img_tex(pass);
     if (!img)
         return NULL;
@@ -1281,26 +1332,80 @@ static bool pass_convert_colors(struct pass_state *pass)
     }
     pl_shader_set_alpha(sh, &pass->repr, PL_ALPHA_INDEPENDENT);
 
-    if (pass->need_peak_fbo && !img_tex(pass))
-        return false;
-    pl_tex feature_map = get_feature_map(pass); // dispatches the pending image shader
-    sh = img_sh(pass);
-
-    struct pl_color_space src_csp = image->color;
-    pl_shader_obj override_state = NULL, *state = &rr->tone_map_state;
-    (void) override_state;
-    if (rr->have_peak_override) {
-        // the reference would read these from its own smoothed state (colorspace.c:1620-1621)
-        src_csp.hdr.max_pq_y = rr->peak_override.max_pq;
-        src_csp.hdr.avg_pq_y = rr->peak_override.avg_pq;
+    // the main LUT (renderer.c:2198-2247): image colour space -> LUT input, the LUT, LUT output ->
+    // image colour space again (a CONVERSION LUT replaces the conversion to the target instead)
+    bool need_conversion = true;
+    if (params->lut) {
+        struct pl_color_space lut_in = params->lut->color_in, lut_out = params->lut->color_out;
+        switch (params->lut_type) {
+        case PL_LUT_UNKNOWN:
+        case PL_LUT_NATIVE:
+            pl_color_space_merge(&lut_in, &image->color);
+            pl_color_space_merge(&lut_out, &image->color);
+            break;
+        case PL_LUT_CONVERSION:
+            pl_color_space_merge(&lut_in, &image->color);
+            need_conversion = false; // conversion LUT the highest priority
+            break;
+        case PL_LUT_NORMALIZED:
+            if (!prelinearized) {
+                pl_shader_linearize(sh, &pass->color); // PL_LUT_NORMALIZED wants linear input data
+                pass->color.transfer = PL_COLOR_TRC_LINEAR;
+                prelinearized = true;
+            }
+            pl_color_space_merge(&lut_in, &pass->color);
+            pl_color_space_merge(&lut_out, &pass->color);
+            break;
+        }
+        pl_shader_color_map_ex(sh, params->color_map_params, pl_color_map_args(
+            .src = image->color,
+            .dst = lut_in,
+            .prelinearized = prelinearized,
+        ));
+        struct plb_color_op *op;
+        if (params->lut_type == PL_LUT_NORMALIZED) {
+            if (!(op = plb_shader_push_op(sh, PLB_OP_SCALE)))
+                return false;
+            op->u.scale.s = 1.0f / pl_color_transfer_nominal_peak(lut_in.transfer);
+        }
+        pl_shader_custom_lut(sh, params->lut, &rr->lut_state[LUT_PARAMS]);
+        if (params->lut_type == PL_LUT_NORMALIZED) {
+            if (!(op = plb_shader_push_op(sh, PLB_OP_SCALE)))
+                return false;
+            op->u.scale.s = pl_color_transfer_nominal_peak(lut_out.transfer);
+        }
+        if (params->lut_type != PL_LUT_CONVERSION) {
+            pl_shader_color_map_ex(sh, params->color_map_params, pl_color_map_args(
+                .src = lut_out,
+                .dst = pass->color,
+            ));
+        }
     }
-    pl_shader_color_map_ex(sh, params->color_map_params, pl_color_map_args(
-        .src = src_csp,
-        .dst = target->color,
-        .prelinearized = prelinearized,
-        .state = state,
-        .feature_map = feature_map,
-    ));
+
+    if (need_conversion) {
+        if (pass->need_peak_fbo && !img_tex(pass))
+            return false;
+        pl_tex feature_map = get_feature_map(pass); // dispatches the pending image shader
+        sh = img_sh(pass);
+
+        struct pl_color_space src_csp = image->color;
+        if (rr->have_peak_override) {
+            // the reference would read these from its own smoothed state (colorspace.c:1620-1621)
+            src_csp.hdr.max_pq_y = rr->peak_override.max_pq;
+            src_csp.hdr.avg_pq_y = rr->peak_override.avg_pq;
+        }
+        pl_shader_color_map_ex(sh, params->color_map_params, pl_color_map_args(
+            .src = src_csp,
+            .dst = target->color,
+            .prelinearized = prelinearized,
+            .state = &rr->tone_map_state,
+            .feature_map = feature_map,
+        ));
+    }
+
+    const enum pl_lut_type tlut = guess_frame_lut_type(target, true);
+    if (tlut == PL_LUT_NORMALIZED || tlut == PL_LUT_CONVERSION)
+        pl_shader_custom_lut(sh, target->lut, &rr->lut_state[LUT_TARGET]);
     pass->color = target->color;
     return !pl_shader_is_failed(sh);
 }
@@ -1350,11 +1455,16 @@ static bool pass_output_target(struct pass_state *pass)
     struct pl_color_repr repr = target->repr;
     const float scale = pl_color_repr_normalize(&repr);
     repr.alpha = PL_ALPHA_NONE; // img->comps < 4
-    pl_shader_encode_color(sh, &repr);
-    if (repr.sys == PL_COLOR_SYSTEM_XYZ) {
-        pass->color.transfer = PL_COLOR_TRC_ST428;
-        pl_shader_delinearize(sh, &pass->color);
+    const enum pl_lut_type lut_type = guess_frame_lut_type(target, true);
+    if (lut_type != PL_LUT_CONVERSION) {
+        pl_shader_encode_color(sh, &repr);
+        if (repr.sys == PL_COLOR_SYSTEM_XYZ) {
+            pass->color.transfer = PL_COLOR_TRC_ST428;
+            pl_shader_delinearize(sh, &pass->color);
+        }
     }
+    if (lut_type == PL_LUT_NATIVE)
+        pl_shader_custom_lut(sh, target->lut, &rr->lut_state[LUT_TARGET]);
     sh = NULL;
 
     // one pass per target plane (:2796-2961)
@@ -1502,8 +1612,6 @@ static bool check_params(pl_renderer rr, const struct pl_render_params *p,
         return false; \
     }
     REJECT(p->num_hooks, "user hooks");
-    REJECT(p->lut, "custom LUTs");
-    REJECT(image->lut || target->lut, "per-frame LUTs");
     REJECT(image->icc || target->icc || image->profile.len || target->profile.len, "ICC profiles");
     REJECT(image->num_overlays || target->num_overlays, "overlays");
     REJECT(p->cone_params, "cone distortion");

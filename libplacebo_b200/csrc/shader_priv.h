@@ -21,6 +21,7 @@ enum plb_obj_type {
     PLB_OBJ_COLOR_MAP,  // tone LUT, gamut 3DLUT, peak detection state
     PLB_OBJ_DITHER,
     PLB_OBJ_GRAIN,
+    PLB_OBJ_LUT,        // PL_SHADER_OBJ_LUT: custom 1-D / 3-D LUT
 };
 
 struct plb_sampler_obj {
@@ -58,6 +59,12 @@ struct plb_dither_obj {
 
 struct plb_grain_obj;      // k_grain / film_grain.cpp
 
+struct plb_lut_obj {
+    float *dev_lut;
+    uint64_t signature;
+    int size[3];
+};
+
 struct pl_shader_obj_t {
     enum plb_obj_type type;
     pl_gpu gpu;
@@ -67,6 +74,7 @@ struct pl_shader_obj_t {
         struct plb_color_map_obj cmap;
         struct plb_dither_obj dither;
         struct plb_grain_obj *grain;
+        struct plb_lut_obj lut;
     } u;
 };
 

@@ -114,6 +114,9 @@ void pl_shader_obj_destroy(pl_shader_obj *ptr)
     case PLB_OBJ_DITHER:
         plb_dev_free(gpu, obj->u.dither.dev_lut);
         break;
+    case PLB_OBJ_LUT:
+        plb_dev_free(gpu, obj->u.lut.dev_lut);
+        break;
     case PLB_OBJ_GRAIN: {
         extern void plb_grain_obj_free(pl_gpu gpu, struct plb_grain_obj *g);
         plb_grain_obj_free(gpu, obj->u.grain);
@@ -179,6 +182,7 @@ struct plb_color_op *plb_shader_push_op(pl_shader sh, int kind)
         [PLB_OP_DOVI_RESHAPE] = "reshaping",
         [PLB_OP_DOVI_LMS] = "color decoding",
         [PLB_OP_PEAK] = "peak detection",
+        [PLB_OP_CUSTOM_LUT] = "custom LUT",
     };
     if (kind >= 0 && kind < (int) PLB_ARRAY_SIZE(names) && names[kind])
         plb_shader_describe(sh, names[kind]);
@@ -1039,6 +1043,266 @@ void pl_shader_extract_features(pl_shader sh, struct pl_color_space csp)
     for (int i = 0; i < 3; i++) {
         for (int j = 0; j < 3; j++)
             op->u.features.m[3 * i + j] = k * (float) m.m[i][j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// custom LUTs (shaders/lut.c:35-280, include/libplacebo/shaders/lut.h)
+// ---------------------------------------------------------------------------------------
+
+// 64-bit FNV-1a of the text: only identity matters (the reference hashes with its own function;
+// the value is opaque to callers and merely keys the upload)
+static uint64_t lut_text_hash(const char *s, size_t n)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < n; i++)
+        h = (h ^ (uint8_t) s[i]) * 0x100000001b3ull;
+    return h;
+}
+
+struct cube_cursor { const char *p, *end; };
+
+static bool cube_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+static void cube_skip_space(struct cube_cursor *c)
+{
+    while (c->p < c->end && cube_space(*c->p))
+        c->p++;
+}
+
+// next line without its terminator, stripped; advances past it
+static void cube_line(struct cube_cursor *c, const char **beg, const char **end)
+{
+    const char *b = c->p, *e = b;
+    while (e < c->end && *e != '\n')
+        e++;
+    c->p = e < c->end ? e + 1 : e;
+    while (b < e && cube_space(*b))
+        b++;
+    while (e > b && cube_space(e[-1]))
+        e--;
+    *beg = b;
+    *end = e;
+}
+
+// keyword followed by a blank or the end of the line (pl_str_eatstart0)
+static bool cube_key(const char **b, const char *e, const char *key)
+{
+    const size_t n = strlen(key);
+    if ((size_t) (e - *b) < n || memcmp(*b, key, n))
+        return false;
+    *b += n;
+    return true;
+}
+
+static bool cube_float(const char *b, const char *e, float *out)
+{
+    char buf[64];
+    while (b < e && cube_space(*b))
+        b++;
+    while (e > b && cube_space(e[-1]))
+        e--;
+    const size_t n = e - b;
+    if (!n || n >= sizeof(buf))
+        return false;
+    memcpy(buf, b, n);
+    buf[n] = 0;
+    char *endp;
+    *out = strtof(buf, &endp); // correctly rounded decimal -> binary32, as the reference's parser
+    return endp == buf + n;
+}
+
+static bool cube_int(const char *b, const char *e, int *out)
+{
+    char buf[32];
+    const size_t n = e - b;
+    if (!n || n >= sizeof(buf))
+        return false;
+    memcpy(buf, b, n);
+    buf[n] = 0;
+    char *endp;
+    const long v = strtol(buf, &endp, 10);
+    *out = (int) v;
+    return endp == buf + n;
+}
+
+static bool cube_triple(const char *b, const char *e, float v[3])
+{
+    for (int i = 0; i < 3; i++) {
+        const char *t = b;
+        while (t < e && *t != ' ')
+            t++;
+        if (!cube_float(b, i < 2 ? t : e, &v[i]))
+            return false;
+        b = t < e ? t + 1 : e;
+    }
+    return true;
+}
+
+struct pl_custom_lut *pl_lut_parse_cube(pl_log log, const char *cstr, size_t cstr_len)
+{
+    struct pl_custom_lut *lut = calloc(1, sizeof(*lut));
+    struct cube_cursor c = { cstr, cstr + cstr_len };
+    lut->signature = lut_text_hash(cstr, cstr_len);
+    int entries = 0;
+    float min[3] = { 0.0, 0.0, 0.0 }, max[3] = { 1.0, 1.0, 1.0 };
+    float *data = NULL;
+
+    // header: everything up to the first line that starts with a digit or '-'
+    while (c.p < c.end && !((*c.p >= '0' && *c.p <= '9') || *c.p == '-')) {
+        const char *b, *e;
+        cube_line(&c, &b, &e);
+        if (b == e)
+            continue;
+        if (cube_key(&b, e, "TITLE")) {
+            PLB_INFO(log, "Loading LUT: %.*s", (int) (e - b), b);
+            continue;
+        }
+        const bool is3d = cube_key(&b, e, "LUT_3D_SIZE");
+        if (is3d || cube_key(&b, e, "LUT_1D_SIZE")) {
+            while (b < e && cube_space(*b))
+                b++;
+            int size;
+            if (!cube_int(b, e, &size)) {
+                PLB_ERR(log, "Failed parsing dimension '%.*s'", (int) (e - b), b);
+                goto error;
+            }
+            if (size <= 0 || size > (is3d ? 1024 : 65536)) {
+                PLB_ERR(log, "Invalid %s size: %d", is3d ? "3DLUT" : "1DLUT", size);
+                goto error;
+            }
+            lut->size[0] = size;
+            lut->size[1] = lut->size[2] = is3d ? size : 0;
+            entries = is3d ? size * size * size : size;
+            continue;
+        }
+        const bool is_min = cube_key(&b, e, "DOMAIN_MIN");
+        if (is_min || cube_key(&b, e, "DOMAIN_MAX")) {
+            while (b < e && cube_space(*b))
+                b++;
+            if (!cube_triple(b, e, is_min ? min : max)) {
+                PLB_ERR(log, "Failed parsing domain: '%.*s'", (int) (e - b), b);
+                goto error;
+            }
+            continue;
+        }
+        if (cube_key(&b, e, "#"))
+            continue;
+        PLB_WARN(log, "Unhandled .cube line: %.*s", (int) (e - b), b);
+    }
+    if (!entries) {
+        PLB_ERR(log, "Missing LUT size specification?");
+        goto error;
+    }
+    for (int i = 0; i < 3; i++) {
+        if (max[i] - min[i] < 1e-6) {
+            PLB_ERR(log, "Invalid domain range: [%f, %f]", min[i], max[i]);
+            goto error;
+        }
+    }
+
+    data = malloc(sizeof(float[3]) * entries);
+    lut->data = data;
+    for (int n = 0; n < entries; n++) {
+        for (int ch = 0; ch < 3; ch++) {
+            const char *b = c.p;
+            while (c.p < c.end && strchr("0123456789.-+e", *c.p) && *c.p)
+                c.p++;
+            float num;
+            if (b == c.p) {
+                if (c.p == c.end)
+                    PLB_ERR(log, "Failed parsing LUT: Unexpected EOF, expected %d entries, got %d",
+                            entries * 3, n * 3 + ch + 1);
+                else
+                    PLB_ERR(log, "Failed parsing LUT: Unexpected '%c', expected digit", *c.p);
+                goto error;
+            }
+            if (!cube_float(b, c.p, &num)) {
+                PLB_ERR(log, "Failed parsing float value '%.*s'", (int) (c.p - b), b);
+                goto error;
+            }
+            data[3 * n + ch] = (num - min[ch]) / (max[ch] - min[ch]); // rescale to 0.0 - 1.0
+            cube_skip_space(&c);
+        }
+    }
+    cube_skip_space(&c);
+    if (c.p < c.end)
+        PLB_WARN(log, "Extra data after LUT?... ignoring '%c'", *c.p);
+    return lut;
+
+error:
+    free(data);
+    free(lut);
+    return NULL;
+}
+
+void pl_lut_free(struct pl_custom_lut **lut)
+{
+    if (!lut || !*lut)
+        return;
+    free((void *) (*lut)->data);
+    free(*lut);
+    *lut = NULL;
+}
+
+// pl_shader_custom_lut (shaders/lut.c:212-280): optional shaper matrix, the LUT (1-D: each channel
+// through its own component with linear interpolation; 3-D: tetrahedral interpolation between
+// four texels, lut.c:773-809), optional output matrix. The table is uploaded once per signature
+// as 4 floats per entry (the reference's rgba32f texture, fill_lut :196-210).
+void pl_shader_custom_lut(pl_shader sh, const struct pl_custom_lut *lut, pl_shader_obj *lut_state)
+{
+    if (!lut)
+        return;
+    int dims;
+    if (lut->size[0] > 0 && lut->size[1] > 0 && lut->size[2] > 0) {
+        dims = 3;
+    } else if (lut->size[0] > 0 && !lut->size[1] && !lut->size[2]) {
+        dims = 1;
+    } else {
+        plb_shader_fail(sh, "Invalid dimensions %dx%dx%d for pl_custom_lut, must be 1D or 3D!",
+                        lut->size[0], lut->size[1], lut->size[2]);
+        return;
+    }
+    if (!plb_shader_require_color(sh, "pl_shader_custom_lut"))
+        return;
+    struct plb_lut_obj *obj = plb_shader_obj(sh, lut_state, PLB_OBJ_LUT);
+    if (!obj)
+        return;
+    pl_gpu gpu = sh->params.gpu;
+    const size_t entries = (size_t) lut->size[0] * PLB_DEF(lut->size[1], 1) * PLB_DEF(lut->size[2], 1);
+    if (!obj->dev_lut || obj->signature != lut->signature || memcmp(obj->size, lut->size, sizeof(obj->size))) {
+        float *tmp = malloc(entries * 4 * sizeof(float));
+        for (size_t i = 0; i < entries; i++) {
+            tmp[4 * i + 0] = lut->data[3 * i + 0];
+            tmp[4 * i + 1] = lut->data[3 * i + 1];
+            tmp[4 * i + 2] = lut->data[3 * i + 2];
+            tmp[4 * i + 3] = 0.0f;
+        }
+        plb_dev_free(gpu, obj->dev_lut);
+        obj->dev_lut = plb_dev_alloc(gpu, entries * 4 * sizeof(float));
+        const bool ok = obj->dev_lut && plb_dev_upload(gpu, obj->dev_lut, tmp, entries * 4 * sizeof(float));
+        free(tmp);
+        if (!ok) {
+            plb_shader_fail(sh, "pl_shader_custom_lut: failed generating LUT object");
+            return;
+        }
+        obj->signature = lut->signature;
+        memcpy(obj->size, lut->size, sizeof(obj->size));
+    }
+    struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_CUSTOM_LUT);
+    if (!op)
+        return;
+    plb_shader_describe(sh, dims == 3 ? "custom 3DLUT" : "custom 1DLUT");
+    op->u.custom_lut.lut = obj->dev_lut;
+    memcpy(op->u.custom_lut.size, lut->size, sizeof(lut->size));
+    static const pl_matrix3x3 zero = {0};
+    op->u.custom_lut.has_in = memcmp(&lut->shaper_in, &zero, sizeof(zero)) != 0;
+    op->u.custom_lut.has_out = memcmp(&lut->shaper_out, &zero, sizeof(zero)) != 0;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) {
+            op->u.custom_lut.shaper_in[3 * i + j] = lut->shaper_in.m[i][j];
+            op->u.custom_lut.shaper_out[3 * i + j] = lut->shaper_out.m[i][j];
+        }
     }
 }
 

@@ -34,6 +34,7 @@
 #include <libplacebo/shaders/colorspace.h>
 #include <libplacebo/shaders/dithering.h>
 #include <libplacebo/shaders/film_grain.h>
+#include <libplacebo/shaders/lut.h>
 #include <libplacebo/renderer.h>
 #include <libplacebo/utils/upload.h>
 

@@ -273,6 +273,9 @@ ORC_API void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *lu
 
 // pl_shader_extract_features (colorspace.c:1383-1404) on linear RGB; m = rgb2lms (float)
 ORC_API void orc_extract_features(float *rgba, size_t npix, const float m[9]);
+// pl_shader_custom_lut (shaders/lut.c:212-280); data = RGB triples (red fastest), size[1] == 0: 1-D
+ORC_API void orc_custom_lut(float *rgba, size_t npix, const float *data, const int size[3],
+                            const float *shaper_in, const float *shaper_out);
 
 // --- H.274 film grain (src/shaders/film_grain_h274.c) --------------------------------------
 struct orc_h274_grain_params {

@@ -152,6 +152,63 @@ void orc_apply_matrix(float *rgba, size_t npix, const float m[9], const float c[
     }
 }
 
+// pl_shader_custom_lut (shaders/lut.c:212-280): [shaper_in] -> LUT -> [shaper_out]. `data`: RGB
+// triples, red fastest (struct pl_custom_lut). 1-D: channel k through component k, linear
+// (lut.c:700-715 form); 3-D: tetrahedral interpolation, GLSL of lut.c:773-809 statement by
+// statement (six sequential conditional updates, barycentric sum in the written order).
+void orc_custom_lut(float *rgba, size_t npix, const float *data, const int size[3],
+                    const float *shaper_in, const float *shaper_out)
+{
+    if (shaper_in)
+        orc_apply_matrix(rgba, npix, shaper_in, NULL);
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < npix; i++) {
+        float *c = rgba + 4 * i;
+        if (!size[1]) {
+            for (int k = 0; k < 3; k++) {
+                float fpos = clampf(c[k], 0.0f, 1.0f) * (float) (size[0] - 1);
+                float fbase = floorf(fpos), fceil = ceilf(fpos);
+                c[k] = mixf(data[3 * (int) fbase + k], data[3 * (int) fceil + k], fpos - fbase);
+            }
+            continue;
+        }
+        float f[3];
+        int v0[3], v1[3], v2[3], v3[3];
+        for (int k = 0; k < 3; k++) {
+            float pos = clampf(c[k], 0.0f, 1.0f) * (float) (size[k] - 1);
+            float base = floorf(pos);
+            f[k] = pos - base;
+            v0[k] = v1[k] = (int) base;
+            v3[k] = v2[k] = (int) ceilf(pos);
+        }
+        // bvec3 c = greaterThanEqual(fpart.xyz, fpart.yzx)
+        const bool cmp[3][3] = {
+            //           x                y                z
+            /* x */ { false,          f[0] >= f[1],  !(f[2] >= f[0]) },
+            /* y */ { !(f[0] >= f[1]), false,         f[1] >= f[2]   },
+            /* z */ { f[2] >= f[0],   !(f[1] >= f[2]), false         },
+        };
+        static const int idx[6][3] = { {0,1,2}, {0,2,1}, {2,0,1}, {2,1,0}, {1,2,0}, {1,0,2} };
+        float s[3] = { f[0], f[1], f[2] };
+        for (int t = 0; t < 6; t++) {
+            const int x = idx[t][0], y = idx[t][1], z = idx[t][2];
+            if (cmp[x][y] && cmp[y][z]) {
+                s[0] = f[x]; s[1] = f[y]; s[2] = f[z];
+                v1[x] = v3[x];
+                v2[z] = v0[z];
+            }
+        }
+#define TEXEL(v) (data + 3 * (((size_t) (v)[2] * size[1] + (v)[1]) * size[0] + (v)[0]))
+        const float *t0 = TEXEL(v0), *t1 = TEXEL(v1), *t2 = TEXEL(v2), *t3 = TEXEL(v3);
+#undef TEXEL
+        const float w0 = 1.0f - s[0], w1 = s[0] - s[1], w2 = s[1] - s[2], w3 = s[2];
+        for (int k = 0; k < 3; k++)
+            c[k] = w0 * t0[k] + w1 * t1[k] + w2 * t2[k] + w3 * t3[k];
+    }
+    if (shaper_out)
+        orc_apply_matrix(rgba, npix, shaper_out, NULL);
+}
+
 void orc_scale(float *rgba, size_t npix, float scale, int with_alpha)
 {
     #pragma omp parallel for schedule(static)

@@ -59,6 +59,10 @@ struct shim_ctx {
     /* planar target of the next shim_render call (shim_set_target_planes) */
     int tgt_nplanes, tgt_chroma_loc;
     pl_tex tgt_planes[3];
+    /* custom LUTs of the next shim_render call (shim_set_lut): 0 params, 1 image, 2 target */
+    struct pl_custom_lut lut[3];
+    int lut_type[3];
+    pl_shader_obj lut_obj;
 };
 
 API void *shim_create(int literal_coords)
@@ -444,6 +448,52 @@ done:
     return ret;
 }
 
+/* ---- custom LUTs ----------------------------------------------------------------------------
+ * shim_custom_lut: sample_direct + pl_shader_custom_lut. data: RGB triples (red fastest);
+ * size[1] == 0: 1-D; shaper_in / shaper_out: 9 floats (row major) or NULL. */
+static struct pl_custom_lut make_lut(const float *data, const int size[3], const float *shaper_in,
+                                     const float *shaper_out, uint64_t signature)
+{
+    struct pl_custom_lut lut = { .signature = signature, .size = { size[0], size[1], size[2] }, .data = data };
+    for (int i = 0; i < 9; i++) {
+        if (shaper_in)
+            lut.shaper_in.m[i / 3][i % 3] = shaper_in[i];
+        if (shaper_out)
+            lut.shaper_out.m[i / 3][i % 3] = shaper_out[i];
+    }
+    return lut;
+}
+
+API int shim_custom_lut(struct shim_ctx *c, void *src_tex, void *dst_tex, const float *data,
+                        const int *size, const float *shaper_in, const float *shaper_out,
+                        unsigned long long signature)
+{
+    const struct pl_custom_lut lut = make_lut(data, size, shaper_in, shaper_out, signature);
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    pl_shader_sample_direct(sh, pl_sample_src( .tex = src_tex ));
+    pl_shader_custom_lut(sh, &lut, &c->lut_obj);
+    return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst_tex )) ? 0 : -1;
+}
+
+/* which: 0 pl_render_params.lut, 1 image.lut, 2 target.lut; type: enum pl_lut_type; the data
+ * pointer must stay valid until the next shim_render returns. sys_in / sys_out: repr_in.sys /
+ * repr_out.sys (frame LUT type guessing); trc_in/out, prim_in/out: color_in / color_out. */
+API void shim_set_lut(struct shim_ctx *c, int which, int type, const float *data, const int *size,
+                      const float *shaper_in, const float *shaper_out, unsigned long long signature,
+                      const int *csp /* prim_in, trc_in, prim_out, trc_out, sys_in, sys_out */)
+{
+    c->lut[which] = make_lut(data, size, shaper_in, shaper_out, signature);
+    c->lut_type[which] = type;
+    if (csp) {
+        c->lut[which].color_in.primaries = csp[0];
+        c->lut[which].color_in.transfer = csp[1];
+        c->lut[which].color_out.primaries = csp[2];
+        c->lut[which].color_out.transfer = csp[3];
+        c->lut[which].repr_in.sys = csp[4];
+        c->lut[which].repr_out.sys = csp[5];
+    }
+}
+
 /* ---- pl_render_image driver ------------------------------------------------------------------
  * planes: up to 3 source textures (Y, U, V) or a single packed one (nplanes = 1, RGB)
  * img / tgt: repr (sys, levels, sample_depth, color_depth, bit_shift) followed by csp[20]
@@ -583,9 +633,23 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
         .error_diffusion = opts[8] ? pl_error_diffusion_kernels[opts[8] - 1] : NULL,
     };
     par.color_map_params = &cmap;
+    if (c->lut[0].data) {
+        par.lut = &c->lut[0];
+        par.lut_type = c->lut_type[0];
+    }
+    if (c->lut[1].data) {
+        image.lut = &c->lut[1];
+        image.lut_type = c->lut_type[1];
+    }
+    if (c->lut[2].data) {
+        target.lut = &c->lut[2];
+        target.lut_type = c->lut_type[2];
+    }
     if (opts[7] >= 0)
         pl_renderer_set_frame_index(c->rr, (uint8_t) opts[7]);
-    if (!pl_render_image(c->rr, &image, &target, &par))
+    const bool rendered = pl_render_image(c->rr, &image, &target, &par);
+    memset(c->lut, 0, sizeof(c->lut));
+    if (!rendered)
         return -1;
     if (out_peak) {
         struct pl_hdr_metadata md = {0};

@@ -143,9 +143,23 @@ def av1_oracle_params(descs, chroma, depth, overlap, keep, tex_scale):
 def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0,
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
            coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
-           error_diffusion=None, film_grain=None, contrast_recovery=0.0, contrast_smoothness=3.5):
+           error_diffusion=None, film_grain=None, contrast_recovery=0.0, contrast_smoothness=3.5,
+           luts=None):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
-    smoothed (avg, max) between frames like sh_color_map_obj.peak does."""
+    smoothed (avg, max) between frames like sh_color_map_obj.peak does.
+    luts: {"params": (type, data, size), "image": (...), "target": (...)} with type in
+    "native" / "normalized" / "conversion" (custom LUTs; the combinations the renderer tests use:
+    params native / conversion, image normalized, target native)."""
+    luts = luts or {}
+
+    def apply_lut(which, c):
+        _, data, size = luts[which]
+        return orc.custom_lut(c, data, size)
+
+    plut = luts.get("params")
+    if plut and plut[0] == "conversion":
+        peak = 0                      # LUT handles tone mapping (renderer.c:1224, :2105)
+        contrast_recovery = 0.0
     t0, orc = T.t0(), T.oracle()
     Y, U, V = img.planes
     H, W = Y.shape
@@ -285,6 +299,10 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         if img.sys in (T.SYS["BT_2020_C"], T.SYS["BT_2100_PQ"], T.SYS["BT_2100_HLG"]):
             color = orc.decode_special(color, img.sys)
 
+    if "image" in luts:
+        assert luts["image"][0] == "normalized"   # RGB -> RGB, after decoding (renderer.c:1945)
+        color = apply_lut("image", color)
+
     src_trc = int(src_csp[1])
     src_hdr = src_csp[11] > 203.0 or src_trc in (T.TRC["PQ"], T.TRC["HLG"], T.TRC["V_LOG"],
                                                  T.TRC["S_LOG1"], T.TRC["S_LOG2"], T.TRC["SCRGB"])
@@ -335,13 +353,22 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
             color = orc.sample_direct(img_fbo, out_w, out_h, linear=True, coord_mode=coord_mode,
                                       ext=ext)
     in_fbo = False
+    lut_done = False
     if not measured and want_peak():
         run_peak(color, wg)
         measured = True
         if not allow_delayed:
+            if plut:  # the LUT is recorded into the image shader before it becomes the FBO
+                assert plut[0] == "native"
+                color = apply_lut("params", color)
+                lut_done = True
             color = orc.store_round(color, 0)  # need_peak_fbo: rgba16hf at output size
             in_fbo = True
     color = np.ascontiguousarray(color[:out_h, :out_w])
+    if plut and not lut_done:
+        # native: image colour space in and out (both colour maps around it are no-ops);
+        # conversion: the LUT output is the target colour
+        color = apply_lut("params", color)
 
     # ---- contrast recovery feature map (get_feature_map, renderer.c:2089-2154)
     feature = None
@@ -371,6 +398,8 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     if peak and use and use[0]:
         src2[19], src2[18] = use[0], use[1]
     cm = color_map_params(t0, src2, dst_csp, hq=cmap_hq, tone_fn=tone_fn, gamut_fn=gamut_fn)
+    if plut and plut[0] == "conversion":
+        cm = None
     if cm is not None:
         p = cm["params"]
         if (feature is not None and p.need_tone_map
@@ -388,6 +417,9 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     if not enc_skip:
         enc = t0.repr_encode(tgt.sys, tgt.levels, tbits[0], tbits[0], 0)
         color = orc.apply_matrix(color, enc["m"], enc["c"])
+    if "target" in luts:
+        assert luts["target"][0] == "native"      # after encoding (renderer.c:2784-2785)
+        color = apply_lut("target", color)
     depth = tbits[1]
     if tgt.planes:
         return planar_output(orc, t0, color, tgt, tnorm, depth, dither, int(dst_csp[1]), frame_index,

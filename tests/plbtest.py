@@ -549,6 +549,16 @@ class Oracle:
         self.lib.orc_extract_features(fp(rgba), C.c_size_t(rgba.size // 4), fp(m))
         return rgba
 
+    def custom_lut(self, rgba, data, size, shaper_in=None, shaper_out=None):
+        """pl_shader_custom_lut: data = RGB triples (red fastest); size = (n, 0, 0) or (r, g, b)."""
+        rgba = np.ascontiguousarray(rgba, f32).copy()
+        d = np.ascontiguousarray(data, f32)
+        sz = (C.c_int * 3)(*size)
+        si = None if shaper_in is None else fp(np.ascontiguousarray(shaper_in, f32))
+        so = None if shaper_out is None else fp(np.ascontiguousarray(shaper_out, f32))
+        self.lib.orc_custom_lut(fp(rgba), C.c_size_t(rgba.size // 4), fp(d), sz, si, so)
+        return rgba
+
     def dovi_reshape(self, rgba, meta):
         rgba = np.ascontiguousarray(rgba, f32).copy()
         comps = (OrcDoviComp * 3)()

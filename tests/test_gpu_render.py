@@ -15,8 +15,16 @@ pytestmark = pytest.mark.gpu
 
 def gpu_render(gpu, img, tgt, *, upscaler="", plane_upscaler="", deband=False, peak=0,
                allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, tone_fn=None,
-               gamut_fn=None, error_diffusion=None, grain=None, contrast_recovery=0.0):
+               gamut_fn=None, error_diffusion=None, grain=None, contrast_recovery=0.0, luts=None):
     Y, U, V = img.planes
+    keep = []
+    for which, (kind, data, size) in (luts or {}).items():
+        d = np.ascontiguousarray(data, np.float32)
+        keep.append(d)
+        gpu.lib.shim_set_lut(C.c_void_p(gpu.ctx), {"params": 0, "image": 1, "target": 2}[which],
+                             {"native": 1, "normalized": 2, "conversion": 3}[kind], T.fp(d),
+                             (C.c_int * 3)(*size), None, None,
+                             C.c_ulonglong(hash((which, d.tobytes())) & (2 ** 63 - 1)), None)
     texs = [gpu.tex("r16", p.shape[1], p.shape[0], p) for p in (Y, U, V)]
     dst = gpu.tex(tgt.fmt, tgt.w, tgt.h)
     ptex = []
