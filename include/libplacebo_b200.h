@@ -788,6 +788,11 @@ PL_API uint64_t pl_cuda_launch_count(pl_gpu gpu);
 // Makes the main stream (pl_cuda_stream) wait for every transfer enqueued so far on the
 // copy-engine streams — e.g. before recording an event that should cover a whole frame.
 PL_API void pl_cuda_join(pl_gpu gpu);
+/* Copy up to 256 KiB between device memory and/or pinned host memory with a kernel on `stream`
+ * (a cudaStream_t; NULL = pl_cuda_stream(gpu)) instead of a DMA engine: small control payloads
+ * (peak statistics, LUTs) do not queue behind frame-sized transfers of the copy engines. The
+ * host side must be pinned (cudaMallocHost / cudaHostRegister); completion = stream order. */
+PL_API bool pl_cuda_small_copy(pl_gpu gpu, void *dst, const void *src, size_t size, void *stream);
 // Diagnostics: evaluates the kernels' deterministic transcendental functions (plb_math.cuh) on
 // host arrays of n floats. fn: 0 pow(a,b) 1 exp(a) 2 log(a) 3 sin(a) 4 cos(a) 5 atan2(a,b)
 // (binary64 definitions); 6 sin 7 cos 8 atan2 (fp32 hot-path definitions); 16 + id: transfer curve

@@ -182,6 +182,34 @@ void plb_dev_free(pl_gpu gpu, void *ptr)
     CK(gpu, cudaFreeAsync(ptr, STREAM(gpu)));
 }
 
+} // extern "C"
+
+// Small host <-> device payloads (LUTs, per-frame statistics) move through a copy KERNEL that
+// reads / writes the pinned staging area directly (unified addressing) instead of the DMA
+// engines: a 1 KB tone-curve upload or the 3264-byte peak statistics would otherwise queue
+// behind the frame-sized transfers of the asynchronous upload / download streams on the same
+// copy engine, and the render stream (resp. the host) would wait for a whole frame's DMA.
+#define PLB_SMALL_XFER (256u << 10)
+
+__global__ void k_copy_bytes(unsigned char *dst, const unsigned char *src, size_t size)
+{
+    const size_t nvec = (((uintptr_t) dst | (uintptr_t) src) & 15) ? 0 : size / 16;
+    const size_t tid = (size_t) blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t) gridDim.x * blockDim.x;
+    for (size_t i = tid; i < nvec; i += nt)
+        ((uint4 *) dst)[i] = ((const uint4 *) src)[i];
+    for (size_t i = nvec * 16 + tid; i < size; i += nt)
+        dst[i] = src[i];
+}
+
+extern "C" {
+
+static bool small_copy(pl_gpu gpu, void *dst, const void *src, size_t size)
+{
+    const int blocks = (int) PLB_MIN((size / 16 + 255) / 256 + 1, (size_t) 64);
+    k_copy_bytes<<<blocks, 256, 0, STREAM(gpu)>>>((unsigned char *) dst, (const unsigned char *) src, size);
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_copy_bytes");
+}
+
 bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
 {
     DEV_GUARD(gpu);
@@ -194,6 +222,8 @@ bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
     if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
         return false;
     memcpy(st, src, size);
+    if (size <= PLB_SMALL_XFER)
+        return small_copy(gpu, dst, st, size);
     return CK(gpu, cudaMemcpyAsync(dst, st, size, cudaMemcpyHostToDevice, STREAM(gpu)));
 }
 
@@ -203,8 +233,12 @@ bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size)
     void *st = plb_gpu_staging(gpu, size);
     if (!st)
         return false;
-    if (!CK(gpu, cudaMemcpyAsync(st, src, size, cudaMemcpyDeviceToHost, STREAM(gpu))))
+    if (size <= PLB_SMALL_XFER) {
+        if (!small_copy(gpu, st, src, size))
+            return false;
+    } else if (!CK(gpu, cudaMemcpyAsync(st, src, size, cudaMemcpyDeviceToHost, STREAM(gpu)))) {
         return false;
+    }
     if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
         return false;
     memcpy(dst, st, size);
@@ -215,7 +249,24 @@ bool plb_dev_download(pl_gpu gpu, void *dst, const void *src, size_t size)
 bool plb_dev_copy(pl_gpu gpu, void *dst, const void *src, size_t size)
 {
     DEV_GUARD(gpu);
+    if (size <= PLB_SMALL_XFER)
+        return small_copy(gpu, dst, src, size);
     return CK(gpu, cudaMemcpyAsync(dst, src, size, cudaMemcpyDeviceToDevice, STREAM(gpu)));
+}
+
+// Copy a small payload between device memory and/or pinned host memory with a kernel on
+// `stream` (NULL: the gpu's stream) — no DMA engine involved, see k_copy_bytes.
+bool pl_cuda_small_copy(pl_gpu gpu, void *dst, const void *src, size_t size, void *stream)
+{
+    DEV_GUARD(gpu);
+    if (!dst || !src || size > PLB_SMALL_XFER) {
+        PLB_ERR(gpu->log, "pl_cuda_small_copy: invalid arguments (%zu bytes)", size);
+        return false;
+    }
+    const int blocks = (int) PLB_MIN((size / 16 + 255) / 256 + 1, (size_t) 64);
+    k_copy_bytes<<<blocks, 256, 0, stream ? (cudaStream_t) stream : STREAM(gpu)>>>(
+        (unsigned char *) dst, (const unsigned char *) src, size);
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_copy_bytes");
 }
 
 bool plb_dev_memset(pl_gpu gpu, void *dst, int val, size_t size)

@@ -35,7 +35,7 @@ struct polar_generic_args {
     plb_coord cc;
     const float *lut;
     int lut_entries;
-    float radius, inv_radius, radius_zero, antiring, scale;
+    float radius, radius_zero, antiring, scale;
     uint8_t comp_mask;
     int ntaps;
     int8_t tap_x[MAX_TAPS], tap_y[MAX_TAPS];
@@ -60,7 +60,7 @@ PLB_DEV void polar_pixel(const polar_generic_args &a, int gx, int gy, float out[
         const float d = sqrtf(__fmaf_rn(dx, dx, dy * dy));
         if ((a.tap_flags[t] & 1) && !(d < a.radius))
             continue;
-        const float w = plb_lut1d(a.lut, a.lut_entries, d * a.inv_radius);
+        const float w = plb_lut1d(a.lut, a.lut_entries, d * 1.0f / a.radius); // sampling.c:529, a division
         wsum += w;
         const float4 c4 = plb_load_clamped(a.src, jx + a.tap_x[t], jy + a.tap_y[t]);
         const float c[4] = {c4.x, c4.y, c4.z, c4.w};
@@ -236,7 +236,6 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
         int8_t tx[MAX_TAPS], ty[MAX_TAPS];
         uint8_t fl[MAX_TAPS];
         const int ntaps = build_taps(p->radius, p->radius_zero, false, tx, ty, fl);
-        const float inv_radius = 1.0f / p->radius;
         int max_d16 = 0;
         for (int py = 0; py < 2; py++) {
             for (int px = 0; px < 2; px++) {
@@ -247,7 +246,7 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
                     const float d = sqrtf(fmaf(dx, dx, dy * dy));
                     if ((fl[t] & 1) && !(d < p->radius))
                         continue;
-                    const float w = host_lut1d(p->host_lut, p->lut_entries, d * inv_radius);
+                    const float w = host_lut1d(p->host_lut, p->lut_entries, d * 1.0f / p->radius);
                     wsum += w;
                     args.w[py][px][ty[t] + 3][tx[t] + 3] = w;
                     if (w != 0.0f) {
@@ -285,7 +284,6 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
     a.lut = p->lut;
     a.lut_entries = p->lut_entries;
     a.radius = p->radius;
-    a.inv_radius = 1.0f / p->radius;
     a.radius_zero = p->radius_zero;
     a.antiring = p->antiring;
     a.scale = p->scale;

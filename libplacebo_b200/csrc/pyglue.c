@@ -373,6 +373,11 @@ API int plg_measure_peak_dev(struct plg_stream *s, int slot, int frame_index, vo
     return pl_renderer_measure_peak_dev(s->rr, &s->image, &s->params, dev_buf) ? 0 : -1;
 }
 
+API int plg_small_copy(struct plg_stream *s, void *dst, const void *src, size_t size, void *stream)
+{
+    return pl_cuda_small_copy(s->gpu, dst, src, size, stream) ? 0 : -1;
+}
+
 API int plg_peak_update(struct plg_stream *s, float state[2], const void *buf, int *scene_change)
 {
     struct pl_peak_state st = { .avg_pq = state[0], .max_pq = state[1] };

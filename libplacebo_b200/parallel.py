@@ -104,7 +104,10 @@ class PeakPipeline:
         with self.torch.cuda.stream(self.side):
             self.side.wait_event(self.ev_meas[b])
             self.dist.all_gather_into_tensor(self.recv[b], self.send[b])
-            self.host[b].copy_(self.recv[b], non_blocking=True)
+            # kernel copy into the pinned buffer: a DMA copy of these few KB would queue behind the
+            # frame-sized downloads on the device-to-host copy engine
+            self.st.small_copy(self.host[b].data_ptr(), self.recv[b].data_ptr(),
+                               self.recv[b].numel() * 4, self.side.cuda_stream)
             self.ev_xchg[b].record(self.side)
         self.inflight = i
 

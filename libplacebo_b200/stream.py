@@ -208,6 +208,12 @@ class Stream:
         if self.lib.plg_measure_peak_dev(self.h, slot, frame_index, C.c_void_p(dev_ptr)):
             raise RuntimeError("pl_renderer_measure_peak_dev failed")
 
+    def small_copy(self, dst_ptr, src_ptr, nbytes, cuda_stream=0):
+        """pl_cuda_small_copy: kernel copy (device / pinned host memory) on `cuda_stream`."""
+        if self.lib.plg_small_copy(self.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes),
+                                   C.c_void_p(cuda_stream)):
+            raise RuntimeError("pl_cuda_small_copy failed")
+
     def peak_update(self, state, buf):
         st = np.array(state, np.float32)
         used = self.lib.plg_peak_update(self.h, C.c_void_p(_ptr(st)), C.c_void_p(_ptr(buf)), None)

@@ -214,7 +214,6 @@ void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, i
     const struct coord_ctx cc = coord_init(p->coord_mode, src, rect, dw, dh);
     const int bound = (int) ceilf(p->radius);        // sampling.c:661
     const float radius = p->radius;
-    const float inv_radius = 1.0f / radius;          // `d * 1.0 / radius`, constant-folded
     const bool use_ar_global = p->antiring > 0.0f;
     const float ar_radius = p->radius_zero;
 
@@ -252,7 +251,7 @@ void orc_sample_polar(const struct orc_tex *src, struct orc_rect rect, int dw, i
                 float d = lengthf2(ox - fx, oy - fy);
                 if (tap_guard[t] && !(d < radius))
                     continue;
-                float w = lut1d_linear(p->lut, p->lut_entries, d * inv_radius);
+                float w = lut1d_linear(p->lut, p->lut_entries, d * 1.0f / radius); // sampling.c:529
                 wsum += w;
                 const float *c = texel(src, jx + tap_x[t], jy + tap_y[t]);
                 for (int k = 0; k < 4; k++) {
