@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--workload", default="c3_4k_hdr10_to_sdr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads and parity")
-    ap.add_argument("--c5-lanes", type=int, default=16, help="frames in flight per GPU for config C5 (0 = skip)")
+    ap.add_argument("--c5-lanes", type=int, default=8, help="frames in flight per GPU for config C5 (0 = skip)")
     return ap.parse_args()
 
 
@@ -415,10 +415,10 @@ def measure(cx, wl_name, steps, warmup, with_e2e=True):
 
 
 def measure_lanes(cx, wl_name, lanes, frames_per_lane):
-    """Config C5: error diffusion is a serial wavefront (ONE thread block per frame, w + (h-1) *
-    shift barrier steps), so a single frame cannot fill the GPU; throughput comes from frames in
+    """Config C5: error diffusion is a serial wavefront (one 8-CTA thread-block cluster per frame,
+    w + (h-1) * shift barrier steps), so a single frame cannot fill the GPU; throughput comes from frames in
     flight. `lanes` independent pl_gpu + pl_renderer pairs on this rank's device (one CUDA stream
-    each) render different frames concurrently: the single-block passes of some frames overlap
+    each) render different frames concurrently: the wavefront passes of some frames overlap
     the wide passes of others. Device-timed from a common start event to the last lane's end."""
     from libplacebo_b200 import stream as S
     torch, rank, local_rank = cx.torch, cx.rank, cx.local_rank
@@ -481,7 +481,7 @@ def measure_lanes(cx, wl_name, lanes, frames_per_lane):
             "column_steps_per_s": round(fpsn * steps_per_frame, 0),
             "gpu_launches": launches,
             "config": dict(workload_config(wl_name, cx.world), lanes=lanes),
-            "note": "latency-bound: the error-diffusion pass is one thread block per frame; frames in "
+            "note": "latency-bound: the error-diffusion pass is one 8-CTA cluster (8 SMs) per frame; frames in "
                     "flight are the unit of parallelism (SURVEY.md 8e: not shardable within a frame)"}
 
 

@@ -263,17 +263,23 @@ def test_error_diffusion_kernels(gpu, oracle, name):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.mean(got != want)
 
 
-@pytest.mark.parametrize("depth,size", [(8, (33, 1100)), (6, (64, 64)), (1, (40, 40))])
-def test_error_diffusion_depths_and_tall_images(gpu, oracle, depth, size):
-    """More rows than threads (1100 > 1024): a column is split over several rows per thread."""
+@pytest.mark.parametrize("depth,size,kernel", [
+    (8, (33, 1100), "sierra-lite"), (6, (64, 64), "sierra-lite"), (1, (40, 40), "sierra-lite"),
+    (8, (50, 2161), "sierra-lite"), (8, (24, 4320), "sierra-lite"), (8, (40, 1500), "floyd-steinberg"),
+    (7, (31, 1300), "jarvis-judice-ninke"), (8, (37, 1201), "atkinson")])
+def test_error_diffusion_depths_and_tall_images(gpu, oracle, depth, size, kernel):
+    """More rows than one thread block has threads (> 1024): the thread-block-cluster kernel
+    (one row per thread, error ring split over the CTAs' shared memories, errors crossing a band
+    boundary through distributed shared memory) at 4K / 8K heights, odd heights and kernels with
+    three-row footprints."""
     import ctypes as C
-    k = T.t0().error_diffusion_kernel("sierra-lite")
+    k = T.t0().error_diffusion_kernel(kernel)
     w, h = size
     src = np.random.default_rng(6).random((h, w, 4), dtype=np.float32)
     s = gpu.tex("rgba32f", w, h, src)
     d = gpu.tex("rgba32f", w, h)
     try:
-        assert gpu.lib.shim_error_diffusion(C.c_void_p(gpu.ctx), C.c_void_p(s), C.c_void_p(d), depth, b"sierra-lite") == 0
+        assert gpu.lib.shim_error_diffusion(C.c_void_p(gpu.ctx), C.c_void_p(s), C.c_void_p(d), depth, kernel.encode()) == 0
         got = gpu.download(d, "rgba32f", w, h)
     finally:
         gpu.free(s, d)
