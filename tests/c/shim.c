@@ -84,6 +84,7 @@ API void shim_destroy(struct shim_ctx *c)
     if (!c)
         return;
     shim_reset_objs(c);
+    pl_shader_obj_destroy(&c->lut_obj);
     pl_renderer_destroy(&c->rr);
     pl_dispatch_destroy(&c->dp);
     pl_cuda_destroy(&c->gpu);
