@@ -190,6 +190,8 @@ void plb_dev_free(pl_gpu gpu, void *ptr)
 // behind the frame-sized transfers of the asynchronous upload / download streams on the same
 // copy engine, and the render stream (resp. the host) would wait for a whole frame's DMA.
 #define PLB_SMALL_XFER (256u << 10)
+#define PLB_UP_SLOTS 8
+#define PLB_UP_SLOT_BYTES (128u << 10)
 
 __global__ void k_copy_bytes(unsigned char *dst, const unsigned char *src, size_t size)
 {
@@ -215,6 +217,28 @@ bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
     DEV_GUARD(gpu);
     // LUT-sized payloads: go through the pinned staging area so that the source may be
     // freed/modified by the caller right after we return
+    struct plb_gpu *p = plb_gpu_priv(gpu);
+    if (size <= PLB_UP_SLOT_BYTES) {
+        // small payload: next slot of the pinned ring; wait only for that slot's previous copy
+        if (!p->up_ring) {
+            if (!CK(gpu, cudaMallocHost(&p->up_ring, (size_t) PLB_UP_SLOTS * PLB_UP_SLOT_BYTES)))
+                return false;
+            for (int i = 0; i < PLB_UP_SLOTS; i++) {
+                cudaEvent_t e;
+                if (!CK(gpu, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)))
+                    return false;
+                p->up_event[i] = e;
+            }
+        }
+        const int slot = p->up_next;
+        p->up_next = (slot + 1) % PLB_UP_SLOTS;
+        if (!CK(gpu, cudaEventSynchronize((cudaEvent_t) p->up_event[slot])))
+            return false;
+        void *st = (char *) p->up_ring + (size_t) slot * PLB_UP_SLOT_BYTES;
+        memcpy(st, src, size);
+        return small_copy(gpu, dst, st, size) &&
+               CK(gpu, cudaEventRecord((cudaEvent_t) p->up_event[slot], STREAM(gpu)));
+    }
     void *st = plb_gpu_staging(gpu, size);
     if (!st)
         return false;
@@ -222,8 +246,6 @@ bool plb_dev_upload(pl_gpu gpu, void *dst, const void *src, size_t size)
     if (!CK(gpu, cudaStreamSynchronize(STREAM(gpu))))
         return false;
     memcpy(st, src, size);
-    if (size <= PLB_SMALL_XFER)
-        return small_copy(gpu, dst, st, size);
     return CK(gpu, cudaMemcpyAsync(dst, st, size, cudaMemcpyHostToDevice, STREAM(gpu)));
 }
 
@@ -501,6 +523,13 @@ void pl_cuda_destroy(pl_gpu *pgpu)
     }
     if (p->staging)
         cudaFreeHost(p->staging);
+    if (p->up_ring) {
+        cudaFreeHost(p->up_ring);
+        for (int i = 0; i < PLB_UP_SLOTS; i++) {
+            if (p->up_event[i])
+                cudaEventDestroy((cudaEvent_t) p->up_event[i]);
+        }
+    }
     if (p->own_stream && p->stream)
         cudaStreamDestroy((cudaStream_t) p->stream);
     free(p->fmts);

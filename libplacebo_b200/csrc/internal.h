@@ -105,6 +105,11 @@ struct plb_gpu {
     pl_fmt *fmt_list;
     void *staging;         // pinned staging buffer for pl_tex_upload/download
     size_t staging_size;
+    // ring of small pinned staging slots for LUT-sized uploads (no stream synchronisation per
+    // upload: a slot is reused only after the event recorded behind its copy kernel)
+    void *up_ring;         // PLB_UP_SLOTS x PLB_UP_SLOT_BYTES, pinned
+    void *up_event[8];
+    int up_next;
     // Asynchronous transfers: uploads and downloads run on their own streams (the two copy
     // engines) and are ordered against the kernels by events, so that frame N+1 uploads and
     // frame N-1 downloads while frame N renders.

@@ -77,3 +77,21 @@ def test_render_with_custom_lut(gpu, which, kind):
     # and the LUT really took part
     base, _ = P.render(img, tgt, **dict(kw, luts=None))
     assert np.any(base != want)
+
+
+def test_render_with_normalized_main_lut_identity(gpu):
+    """PL_LUT_NORMALIZED main LUT (renderer.c:2213-2239): the image is linearised, mapped to the
+    LUT's input space, scaled to the nominal peak, sent through the LUT, and mapped back before
+    the main colour conversion runs on the linear image. With an identity table on an SDR frame
+    the whole detour must reproduce the plain render up to the rounding of the extra
+    linearise / delinearise round trip (<= 2 LSB16; no oracle restatement of this flow)."""
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    planes = T.yuv420p10(160, 90, seed=41, kind="rings")
+    img = P.Frame(planes, T.SYS["BT_709"], csp=SDR)
+    tgt = P.Target(160, 90, "rgba16", sample_depth=16, color_depth=16, csp=SDR)
+    kw = dict(plane_upscaler="ewa_lanczos", dither=0, frame_index=1)
+    base, _ = gpu_render(gpu, img, tgt, **kw)
+    gpu.lib.shim_renderer_reset(C.c_void_p(gpu.ctx))
+    got, _ = gpu_render(gpu, img, tgt, luts={"params": ("normalized", identity_lut(33), (33, 33, 33))}, **kw)
+    d = np.abs(got[..., :3].astype(np.int64) - base[..., :3].astype(np.int64))
+    assert d.max() <= 2, (int(d.max()), float(np.mean(d > 0)))
