@@ -272,7 +272,9 @@ def pass_bytes(desc, wl):
     if has("feature extraction"):
         return dw * dh * 8 + dw * dh * 2, "feature extraction"
     if has("ortho") or has("separable"):
-        return pw * ph * 2 * 2, "feature low-pass"
+        if wl["opts"].get("contrast"):
+            return pw * ph * 2 * 2, "feature low-pass"
+        return sw * sh * 8 + pw * ph * 8, "separable scaler pass"
     if has("tone / gamut mapping") or has("dithering") or has("delinearization"):
         return dw * dh * 8 + dw * dh * out_bpp, "colour map + output"
     return (sw * sh * 2 + 2 * cw * ch * 2) + dw * dh * out_bpp, "other"

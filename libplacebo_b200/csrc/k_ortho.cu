@@ -46,6 +46,55 @@ PLB_DEV void ortho_weights(const ortho_args &a, int quad, float fcoord, float ws
     ws[3] = plb_mix(r0.w, r1.w, fc);
 }
 
+// Tap fetch. FETCH 0: bilinear (general position); 1: nearest texel (aligned pass, see the
+// header); 2: interpolation along the filtered axis only (aligned pass with the linear-sampling
+// trick). HALF4: rgba16hf source (the image FBO), fetched without the run-time format dispatch —
+// the same texels and the same arithmetic as the general functions.
+template <int FETCH, bool HALF4>
+PLB_DEV float4 ortho_fetch(const ortho_args &a, float tu, float tv)
+{
+    if (!HALF4) {
+        return FETCH == 0 ? plb_tex_linear(a.src, tu, tv)
+             : FETCH == 2 ? plb_tex_linear_axis(a.src, tu, tv, a.pass == 1 ? 0 : 1)
+             : plb_tex_nearest(a.src, tu, tv);
+    }
+    const int w = a.src.w, h = a.src.h, m = a.src.addr;
+    if (FETCH == 1) {
+        const int x = (int) floorf(tu * (float) w), y = (int) floorf(tv * (float) h);
+        return plb_load_rgba16hf(a.src, plb_wrap_index(x, w, m), plb_wrap_index(y, h, m));
+    }
+    if (FETCH == 2) {
+        float4 p, q;
+        float f;
+        if (a.pass == 1) {
+            const float tx = tu * (float) w - 0.5f, bx = floorf(tx);
+            const int y = plb_wrap_index((int) floorf(tv * (float) h), h, m);
+            f = tx - bx;
+            p = plb_load_rgba16hf(a.src, plb_wrap_index((int) bx, w, m), y);
+            q = plb_load_rgba16hf(a.src, plb_wrap_index((int) bx + 1, w, m), y);
+        } else {
+            const float ty = tv * (float) h - 0.5f, by = floorf(ty);
+            const int x = plb_wrap_index((int) floorf(tu * (float) w), w, m);
+            f = ty - by;
+            p = plb_load_rgba16hf(a.src, x, plb_wrap_index((int) by, h, m));
+            q = plb_load_rgba16hf(a.src, x, plb_wrap_index((int) by + 1, h, m));
+        }
+        return make_float4(plb_mix(p.x, q.x, f), plb_mix(p.y, q.y, f), plb_mix(p.z, q.z, f), plb_mix(p.w, q.w, f));
+    }
+    const float tx = tu * (float) w - 0.5f, ty = tv * (float) h - 0.5f;
+    const float bx = floorf(tx), by = floorf(ty);
+    const float fx = tx - bx, fy = ty - by;
+    const int x0 = plb_wrap_index((int) bx, w, m), x1 = plb_wrap_index((int) bx + 1, w, m);
+    const int y0 = plb_wrap_index((int) by, h, m), y1 = plb_wrap_index((int) by + 1, h, m);
+    const float4 p = plb_load_rgba16hf(a.src, x0, y0), q = plb_load_rgba16hf(a.src, x1, y0);
+    const float4 r = plb_load_rgba16hf(a.src, x0, y1), t = plb_load_rgba16hf(a.src, x1, y1);
+    return make_float4(plb_mix(plb_mix(p.x, q.x, fx), plb_mix(r.x, t.x, fx), fy),
+                       plb_mix(plb_mix(p.y, q.y, fx), plb_mix(r.y, t.y, fx), fy),
+                       plb_mix(plb_mix(p.z, q.z, fx), plb_mix(r.z, t.z, fx), fy),
+                       plb_mix(plb_mix(p.w, q.w, fx), plb_mix(r.w, t.w, fx), fy));
+}
+
+template <int FETCH, bool HALF4>
 PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
 {
     const int N = a.row_size;
@@ -61,31 +110,35 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
     const float basey = posy - fcoord * pty - pty * off0;
     float ca[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, lo[4] = {1e9f, 1e9f, 1e9f, 1e9f};
     float ws[4] = {0, 0, 0, 0};
-    for (int n = 0; n < N; n += a.use_linear ? 2 : 1) {
-        if (n % 4 == 0)
-            ortho_weights(a, n / 4, fcoord, ws);
-        float off = (float) n;
-        if (a.use_linear)
-            off += ws[n % 4 + 1];
-        const float tu = basex + ptx * off, tv = basey + pty * off;
-        const float4 c4 = !a.aligned ? plb_tex_linear(a.src, tu, tv)
-                        : a.use_linear ? plb_tex_linear_axis(a.src, tu, tv, a.pass == 1 ? 0 : 1)
-                        : plb_tex_nearest(a.src, tu, tv);
-        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
-        if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k < a.src.comps) {
-                    lo[k] = fminf(lo[k], c[k]);
-                    hi[k] = fmaxf(hi[k], c[k]);
+    // taps in groups of four (one LUT quad): static indices into ws[] keep it in registers
+    for (int n0 = 0; n0 < N; n0 += 4) {
+        ortho_weights(a, n0 / 4, fcoord, ws);
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + j;
+            if (n >= N || (a.use_linear && (j & 1)))
+                continue;
+            float off = (float) n;
+            if (a.use_linear)
+                off += ws[(j + 1) & 3];
+            const float tu = basex + ptx * off, tv = basey + pty * off;
+            const float4 c4 = ortho_fetch<FETCH, HALF4>(a, tu, tv);
+            const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+            if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < a.src.comps) {
+                        lo[k] = fminf(lo[k], c[k]);
+                        hi[k] = fmaxf(hi[k], c[k]);
+                    }
                 }
             }
-        }
-        const float w = ws[n % 4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (k < a.src.comps)
-                ca[k] = __fmaf_rn(w, c[k], ca[k]);
+            const float w = ws[j];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < a.src.comps)
+                    ca[k] = __fmaf_rn(w, c[k], ca[k]);
+            }
         }
     }
     out[0] = out[1] = out[2] = 0.0f;
@@ -101,6 +154,7 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
     }
 }
 
+template <int FETCH, bool HALF4>
 __global__ void __launch_bounds__(256)
 k_ortho(const __grid_constant__ ortho_args a)
 {
@@ -127,7 +181,7 @@ k_ortho(const __grid_constant__ ortho_args a)
         if (!has_peak && !inside)
             continue;
         float prim[4], color[4];
-        ortho_pixel(a, gx, gy, prim);
+        ortho_pixel<FETCH, HALF4>(a, gx, gy, prim);
         uint32_t ypq = 0;
         const plb_op_peak *pk = nullptr;
         plb_tail_color(gx, gy, prim, color, &ypq, &pk);
@@ -276,7 +330,15 @@ extern "C" bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p)
         grid.x = ((tl->out_w + wg_w - 1) / wg_w * wg_w + 31) / 32;
         grid.y = ((tl->out_h + wg_h - 1) / wg_h * wg_h + 31) / 32;
     }
-    k_ortho<<<grid, block, 0, STREAM(gpu)>>>(a);
+    const int fetch = !a.aligned ? 0 : a.use_linear ? 2 : 1;
+    const bool half4 = p->src.kind == PLB_FK_HALF && p->src.comps == 4 && !p->src.ptr2;
+#define ORTHO(F, H) k_ortho<F, H><<<grid, block, 0, STREAM(gpu)>>>(a)
+    if (half4) {
+        if (fetch == 0) ORTHO(0, true); else if (fetch == 1) ORTHO(1, true); else ORTHO(2, true);
+    } else {
+        if (fetch == 0) ORTHO(0, false); else if (fetch == 1) ORTHO(1, false); else ORTHO(2, false);
+    }
+#undef ORTHO
     g->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_ortho");
 }

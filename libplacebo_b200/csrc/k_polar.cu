@@ -43,6 +43,38 @@ struct polar_generic_args {
     plb_tail_args tail;
 };
 
+// The same sum for the usual image source — an rgba16hf texture with clamp addressing, no
+// anti-ringing: format-specialised fetch, no per-component tests. Same operations in the same
+// order as polar_pixel(), hence the same values.
+PLB_DEV void polar_pixel_half4(const polar_generic_args &a, int gx, int gy, float out[4])
+{
+    int jx, jy;
+    float fx, fy;
+    plb_coord_texel(a.cc, gx, gy, jx, jy, fx, fy);
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f, wsum = 0.0f;
+    const int wm1 = a.src.w - 1, hm1 = a.src.h - 1;
+    #pragma unroll 2
+    for (int t = 0; t < a.ntaps; t++) {
+        const int tx = a.tap_x[t], ty = a.tap_y[t];
+        const float dx = (float) tx - fx, dy = (float) ty - fy;
+        const float d = sqrtf(__fmaf_rn(dx, dx, dy * dy));
+        if ((a.tap_flags[t] & 1) && !(d < a.radius))
+            continue;
+        const float w = plb_lut1d(a.lut, a.lut_entries, d * 1.0f / a.radius);
+        wsum += w;
+        const float4 c = plb_load_rgba16hf(a.src, plb_clampi(jx + tx, 0, wm1), plb_clampi(jy + ty, 0, hm1));
+        c0 = __fmaf_rn(w, c.x, c0);
+        c1 = __fmaf_rn(w, c.y, c1);
+        c2 = __fmaf_rn(w, c.z, c2);
+        c3 = __fmaf_rn(w, c.w, c3);
+    }
+    const float norm = a.scale / wsum;
+    out[0] = (a.comp_mask & 1) ? norm * c0 : 0.0f;
+    out[1] = (a.comp_mask & 2) ? norm * c1 : 0.0f;
+    out[2] = (a.comp_mask & 4) ? norm * c2 : 0.0f;
+    out[3] = (a.comp_mask & 8) ? norm * c3 : 1.0f;
+}
+
 // the EWA sum for one output pixel; out = vec4 as pl_shader_sample_polar leaves `color`
 PLB_DEV void polar_pixel(const polar_generic_args &a, int gx, int gy, float out[4])
 {
@@ -107,6 +139,7 @@ PLB_DEV void polar_pixel(const polar_generic_args &a, int gx, int gy, float out[
 }
 
 // CTA = 32x8 threads over a 32x32 output tile, like k_pixel
+template <bool HALF4>
 __global__ void __launch_bounds__(256)
 k_polar_generic(const __grid_constant__ polar_generic_args a)
 {
@@ -133,7 +166,10 @@ k_polar_generic(const __grid_constant__ polar_generic_args a)
         if (!has_peak && !inside)
             continue;
         float prim[4], color[4];
-        polar_pixel(a, gx, gy, prim);
+        if (HALF4)
+            polar_pixel_half4(a, gx, gy, prim);
+        else
+            polar_pixel(a, gx, gy, prim);
         uint32_t ypq = 0;
         const plb_op_peak *pk = nullptr;
         plb_tail_color(gx, gy, prim, color, &ypq, &pk);
@@ -303,7 +339,10 @@ extern "C" bool plb_launch_polar(pl_gpu gpu, const struct plb_polar_launch *p)
         grid.x = ((tl->out_w + wg_w - 1) / wg_w * wg_w + 31) / 32;
         grid.y = ((tl->out_h + wg_h - 1) / wg_h * wg_h + 31) / 32;
     }
-    k_polar_generic<<<grid, block, 0, STREAM(gpu)>>>(a);
+    if (a.src.kind == PLB_FK_HALF && a.src.comps == 4 && !a.src.ptr2 && a.src.addr == 0 && !(a.antiring > 0.0f))
+        k_polar_generic<true><<<grid, block, 0, STREAM(gpu)>>>(a);
+    else
+        k_polar_generic<false><<<grid, block, 0, STREAM(gpu)>>>(a);
     g->launches++;
     return plb_cuda_check(gpu, cudaGetLastError(), "k_polar_generic");
 }

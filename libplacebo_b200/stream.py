@@ -78,6 +78,21 @@ WORKLOADS = {
         src_sys="BT_2020_NC", src_levels="FULL", src_csp=csp(PRIM["BT_2020"], TRC["PQ"], max_luma=1000),
         dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=8,
         upscaler="ewa_lanczos", opts=dict(dither=1, cmap_hq=1, dovi=1, errdiff=ERRDIFF.index("sierra-lite") + 1)),
+    # profiling workloads for the kernel families the BASELINE configs do not reach (generic-ratio
+    # EWA, separable scalers); not benchmark configurations
+    "p1_1080p_to_1440p_ewa_generic": dict(
+        desc="1080p YUV420P10 BT.709 -> 2560x1440 rgba16hf, EWA-Lanczos at ratio 4/3 (generic polar kernel)",
+        src=(1920, 1080), dst=(2560, 1440), dst_fmt="rgba16hf",
+        src_sys="BT_709", src_csp=csp(PRIM["BT_709"], TRC["BT_1886"]),
+        dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=0,
+        upscaler="ewa_lanczos", opts=dict()),
+    "p2_1080p_to_1440p_lanczos_ortho": dict(
+        desc="1080p YUV420P10 BT.709 -> 2560x1440 rgba16hf, separable Lanczos (two ortho passes), "
+             "separable chroma upscale",
+        src=(1920, 1080), dst=(2560, 1440), dst_fmt="rgba16hf",
+        src_sys="BT_709", src_csp=csp(PRIM["BT_709"], TRC["BT_1886"]),
+        dst_csp=csp(PRIM["BT_709"], TRC["BT_1886"]), dst_depth=0,
+        upscaler="lanczos", opts=dict()),
     # reduced-size C3 for the CPU-only contract tests of bench.py (not a benchmark configuration)
     "test_c3_480x270": dict(
         desc="config C3 at 480x270 (bench.py contract tests)",

@@ -81,6 +81,28 @@ def test_polar_generic_kernel_matches_literal_oracle(gpu_literal, oracle, case):
     assert ident > 0.999, ident
 
 
+@pytest.mark.parametrize("dw,dh,comps,rect", [(171, 96, 3, (0, 0, 0, 0)), (90, 50, 4, (0, 0, 0, 0)),
+                                              (150, 113, 3, (2.5, 1.25, 120.0, 70.75))])
+def test_polar_generic_rgba16hf_source(gpu, gpu_literal, oracle, dw, dh, comps, rect):
+    """The image-FBO case of the generic kernel (rgba16hf source, clamp addressing, no
+    anti-ringing: format-specialised path) at non-2x ratios, both coordinate modes."""
+    sw, sh = 128, 72
+    src = rand_tex(sh, sw, 4, seed=9)   # float16 texels
+    orect = rect if any(rect) else None
+    rx = dw / ((rect[2] - rect[0]) if any(rect) else sw)
+    ry = dh / ((rect[3] - rect[1]) if any(rect) else sh)
+    blur = max(1.0 / min(rx, ry), 1.0)
+    base = T.t0().filter_generate("ewa_lanczos")
+    f = T.t0().filter_generate("ewa_lanczos", blur=(base["blur"] or 1.0) * blur)
+    for g, mode in ((gpu_literal, T.COORD_LITERAL), (gpu, T.COORD_EXACT)):
+        got = g.polar(src, "rgba16hf", dw, dh, "ewa_lanczos", comps=comps, out_fmt="rgba32f", rect=rect)
+        want = oracle.sample_polar(src.astype(np.float32), dw, dh, f, comp_mask=(1 << comps) - 1,
+                                   rect=orect, coord_mode=mode)
+        assert np.isfinite(got).all()
+        assert max_ulp32(got, want) <= 1
+        assert np.mean(got.view(np.uint32) == want.view(np.uint32)) > 0.999
+
+
 def test_polar_unorm16_source_and_target(gpu_literal, oracle):
     rng = np.random.default_rng(11)
     src = rng.integers(0, 65536, (40, 50, 2), dtype=np.uint16)
