@@ -110,6 +110,14 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
     const float basey = posy - fcoord * pty - pty * off0;
     float ca[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, lo[4] = {1e9f, 1e9f, 1e9f, 1e9f};
     float ws[4] = {0, 0, 0, 0};
+    // aligned pass over an rgba16hf image: the texel index along the unfiltered axis does not
+    // depend on the tap (pt = 0 there, so tu resp. tv is the base coordinate itself)
+    const bool fast = HALF4 && FETCH != 0;
+    const int sw = a.src.w, sh = a.src.h, mode = a.src.addr;
+    int fixed = 0;
+    if (fast)
+        fixed = a.pass == 0 ? plb_wrap_index((int) floorf(basex * (float) sw), sw, mode)
+                            : plb_wrap_index((int) floorf(basey * (float) sh), sh, mode);
     // taps in groups of four (one LUT quad): static indices into ws[] keep it in registers
     for (int n0 = 0; n0 < N; n0 += 4) {
         ortho_weights(a, n0 / 4, fcoord, ws);
@@ -122,7 +130,23 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
             if (a.use_linear)
                 off += ws[(j + 1) & 3];
             const float tu = basex + ptx * off, tv = basey + pty * off;
-            const float4 c4 = ortho_fetch<FETCH, HALF4>(a, tu, tv);
+            float4 c4;
+            if (fast) {
+                const int lim = a.pass == 0 ? sh : sw;
+                const float t = a.pass == 0 ? tv * (float) sh : tu * (float) sw;
+                if (FETCH == 1) {
+                    const int i = plb_wrap_index((int) floorf(t), lim, mode);
+                    c4 = a.pass == 0 ? plb_load_rgba16hf(a.src, fixed, i) : plb_load_rgba16hf(a.src, i, fixed);
+                } else {
+                    const float tt = t - 0.5f, b = floorf(tt), f = tt - b;
+                    const int i0 = plb_wrap_index((int) b, lim, mode), i1 = plb_wrap_index((int) b + 1, lim, mode);
+                    const float4 p = a.pass == 0 ? plb_load_rgba16hf(a.src, fixed, i0) : plb_load_rgba16hf(a.src, i0, fixed);
+                    const float4 q = a.pass == 0 ? plb_load_rgba16hf(a.src, fixed, i1) : plb_load_rgba16hf(a.src, i1, fixed);
+                    c4 = make_float4(plb_mix(p.x, q.x, f), plb_mix(p.y, q.y, f), plb_mix(p.z, q.z, f), plb_mix(p.w, q.w, f));
+                }
+            } else {
+                c4 = ortho_fetch<FETCH, HALF4>(a, tu, tv);
+            }
             const float c[4] = {c4.x, c4.y, c4.z, c4.w};
             if (use_ar && (n == N / 2 - 1 || n == N / 2)) {
                 #pragma unroll
@@ -136,7 +160,7 @@ PLB_DEV void ortho_pixel(const ortho_args &a, int gx, int gy, float out[4])
             const float w = ws[j];
             #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (k < a.src.comps)
+                if (HALF4 || k < a.src.comps)
                     ca[k] = __fmaf_rn(w, c[k], ca[k]);
             }
         }
