@@ -3,25 +3,33 @@
 //
 // Two kernels:
 //
-//  k_polar_generic   any ratio / rect / filter / anti-ringing. One thread per output pixel,
-//                    per-pixel sub-texel fraction and per-tap weight (sqrt + LUT lerp), source
-//                    texels straight from L1/L2. Follows the oracle operation by operation in
-//                    both coordinate modes, so it is bit-exact with it up to store rounding.
+//  k_polar_generic<HALF4>  any ratio / rect / filter / anti-ringing. One thread per output pixel,
+//                    per-pixel sub-texel fraction and per-tap weight (sqrt + division + LUT
+//                    lerp), source texels straight from L1/L2 (HALF4: rgba16hf image without
+//                    anti-ringing, format-specialised fetch). Follows the oracle operation by
+//                    operation in both coordinate modes, so it is bit-exact with it up to store
+//                    rounding.
 //
-//  k_polar_up2<NC,R2> exact 2x upscale of a whole texture (chroma 4:2:0 -> luma size, 1080p ->
-//                    4K): with exact coordinates the sub-texel fraction takes only the values
-//                    {0.75, 0.25} per axis, so the 4 x 64 tap weights are tabulated once on the
-//                    host (same fp32 ops as the per-pixel path -> identical values) and handed
-//                    to the kernel as __grid_constant__ parameters (constant bank operands of
-//                    the FFMAs). Each thread produces a 4x2 output block from a 10x9 source
-//                    window held in registers, read as float2 from a planar fp32 tile staged in
-//                    shared memory; taps are visited in the reference's (y, x) order and
-//                    accumulated with FFMA, so results equal the exact-coordinate oracle bit
-//                    for bit. Taps that can never contribute for radius^2 < R2/16 are removed
-//                    at compile time (30 of 64 for EWA-Lanczos).
+//  k_polar_up2<NC,XM,YM,MODE> (k_up2.cuh, instantiated in k_up2_{a,b,c}.cu)
+//                    exact 2x upscale of a whole texture (chroma 4:2:0 -> luma size, 1080p ->
+//                    4K): with exact coordinates the sub-texel fraction takes only two values
+//                    per axis ({0.75, 0.25} centred, {0, 0.5} for left / top sited chroma), so
+//                    the 4 x 64 tap weights are tabulated once on the host (same fp32 ops as the
+//                    per-pixel path -> identical values) and handed to the kernel as
+//                    __grid_constant__ parameters. CTA = 16x16 threads, each producing an 8x2
+//                    output block of a 128x32 tile; the 72x24 source tile is fetched by TMA
+//                    (cp.async.bulk.tensor.2d + mbarrier; border tiles by clamped loads) and
+//                    repacked into float2 pair-planes whose even / odd 16-byte chunks are split
+//                    for conflict-free LDS.128; taps are visited in the reference's (y, x)
+//                    order and accumulated with packed FFMA2, so results equal the
+//                    exact-coordinate oracle bit for bit. Taps that can never contribute for
+//                    the filter's radius are removed at compile time (30 of 64 for EWA-Lanczos).
+//                    MODE 0: general tail (interpreter); 1: folded "scale + identity swizzle"
+//                    epilogue; 2: the merged HDR plane pass (deband / grain / decode / PQ peak
+//                    tap inlined, run x-fastest from a shared-memory staging of the results).
 //
-// Roofline notes: 2x EWA-Lanczos needs 30 taps x NC FFMA per output
-// pixel; at 128 FFMA/clk/SM that is the binding limit (not HBM): 0.70 clk/px/SM for NC=3.
+// Roofline notes: 2x EWA-Lanczos needs 30 taps x NC FMA per output pixel; at
+// 128 FMA/clk/SM that is the binding limit (not HBM): 0.70 clk/px/SM for NC = 3.
 #include "k_up2_args.cuh"
 
 void plb_fill_tail(plb_tail_args *t, const struct plb_pixel_launch *p);
