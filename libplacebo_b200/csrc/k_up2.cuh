@@ -518,11 +518,13 @@ static void launch_up2_m(pl_gpu gpu, dim3 grid, dim3 block, polar_up2_args &args
     args.use_tma = (args.src_kind == UP2_SRC_HALF4 || args.src_kind == UP2_SRC_HALF2) && tma_on &&
                    make_tile_map(&map, s, args.src_kind == UP2_SRC_HALF4 ? 8 : 4);
     constexpr int smem = up2_smem_bytes<NC, MODE>();
-    static bool attr_set; // per instantiation; the attribute is per function and device-wide
-    if (!attr_set) {
+    // per instantiation and per device (the attribute belongs to the function in one context)
+    static unsigned long long attr_devs;
+    const int dev = plb_gpu_priv(gpu)->device & 63;
+    if (!((attr_devs >> dev) & 1)) {
         cudaFuncSetAttribute(k_polar_up2<NC, XM, YM, MODE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
+        attr_devs |= 1ull << dev;
     }
     k_polar_up2<NC, XM, YM, MODE><<<grid, block, smem, STREAM(gpu)>>>(args, map);
 }

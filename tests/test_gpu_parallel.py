@@ -104,3 +104,36 @@ def test_two_rank_stream_equals_sequential_stream():
     st.close()
     # after the last step every rank holds the state after ALL frames
     assert got[FRAMES - 1][1] == pytest.approx(seq_state, abs=0) or got[FRAMES - 1][1] == seq_state
+
+
+def test_two_gpus_in_one_process_interleaved():
+    """Two pl_gpu objects on two devices driven from ONE process, calls interleaved, while torch
+    keeps a third notion of the current device: every entry point selects its own device
+    (allocations, uploads, launches, TMA descriptors, per-device constants and curve tables).
+    Both must produce the sequential single-GPU result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    sys.path.insert(0, ROOT)
+    from libplacebo_b200 import stream as S
+    sts = [S.Stream(device=d).configure(_workload(), ring=2) for d in (0, 1)]
+    outs = [[], []]
+    try:
+        for f in range(3):
+            for d, st in enumerate(sts):
+                torch.cuda.set_device(1 - d)          # the "wrong" device is current on purpose
+                st.upload(f % 2, *_frame(f))
+            for d, st in enumerate(sts):
+                torch.cuda.set_device(d if f % 2 else 1 - d)
+                st.render(f % 2, f % 2, frame_index=f)
+                o = st.out_array()
+                st.download(f % 2, o)
+                st.join()
+                st.finish()
+                outs[d].append(o.copy())
+    finally:
+        for st in sts:
+            st.close()
+    for f in range(3):
+        assert np.array_equal(outs[0][f], outs[1][f]), f"frame {f}: device 0 and device 1 differ"
+    assert outs[0][0].any()
