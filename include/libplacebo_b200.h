@@ -1256,6 +1256,26 @@ static inline void pl_frame_clear(pl_gpu gpu, const struct pl_frame *frame, cons
 PL_API void pl_frames_infer(pl_renderer rr, struct pl_frame *image, struct pl_frame *target);
 PL_API bool pl_render_image(pl_renderer rr, const struct pl_frame *image,
                             const struct pl_frame *target, const struct pl_render_params *params);
+
+/* renderer.h:754-847 — frame mixing: several source frames around one output vsync. `timestamps`
+ * are relative to the target vsync, in units of source frames; `signatures` identify frames
+ * across calls (their rendered versions are cached). pl_render_image_mix renders every frame
+ * that contributes (weight from `pl_render_params.frame_mixer`: NULL = only the nearest frame,
+ * pl_filter_function_oversample kernel = visible fraction of the vsync interval, any other filter
+ * = pl_filter_sample at the timestamp) through the whole path into a cached rgba16hf image,
+ * mixes them in linear light and sends the result through the output stage.
+ * Differences on this backend: `preserve_mixing_cache` is treated as false. */
+struct pl_frame_mix {
+    int num_frames;
+    const struct pl_frame **frames;
+    const uint64_t *signatures;
+    const float *timestamps;
+    float vsync_duration;
+};
+PL_API const struct pl_frame *pl_frame_mix_current(const struct pl_frame_mix *mix);
+PL_API const struct pl_frame *pl_frame_mix_nearest(const struct pl_frame_mix *mix);
+PL_API bool pl_render_image_mix(pl_renderer rr, const struct pl_frame_mix *images,
+                                const struct pl_frame *target, const struct pl_render_params *params);
 PL_API void pl_renderer_flush_cache(pl_renderer rr);
 
 /* ---- utils/upload.h: frame ingest (src/utils/upload.c) ------------------------------------ */

@@ -264,6 +264,10 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
     case PLB_SRC_ERRDIFF:
         ok = plb_launch_errdiff(gpu, &sh->errdiff);
         break;
+    case PLB_SRC_MIX:
+        sh->mix.tail = *px;
+        ok = plb_launch_mix(gpu, &sh->mix);
+        break;
     default:
         break;
     }

@@ -399,6 +399,20 @@ struct plb_ortho_launch {
 };
 bool plb_launch_ortho(pl_gpu gpu, const struct plb_ortho_launch *p);
 
+// frame mixing (pl_render_image_mix, renderer.c:3906-3966): weighted sum of up to 8 same-sized
+// frames, each linearised first when more than one takes part
+#define PLB_MAX_MIX 8
+struct plb_mix_launch {
+    int n;
+    struct plb_tex_desc tex[PLB_MAX_MIX];
+    float weight[PLB_MAX_MIX];     // already divided by the weight sum
+    int linearize;                 // frames are taken to linear light before mixing
+    struct plb_trc_consts lin;
+    int8_t src_map[4];
+    struct plb_pixel_launch tail;
+};
+bool plb_launch_mix(pl_gpu gpu, const struct plb_mix_launch *p);
+
 struct plb_errdiff_launch {
     struct plb_tex_desc src, dst;
     int w, h;

@@ -687,3 +687,76 @@ extern "C" PL_API bool pl_cuda_math_eval(pl_gpu gpu, int fn, const float *a, con
     cudaFree(d);
     return ok;
 }
+
+// Frame mixing (pl_render_image_mix, renderer.c:3906-3966): texel (x, y) of every cached frame,
+// linearised when several frames take part, accumulated as `mix += w * color` (fma), then the
+// common tail (delinearisation and the output stage recorded behind it).
+struct plb_mix_args {
+    int n, linearize;
+    plb_tex_desc tex[PLB_MAX_MIX];
+    float weight[PLB_MAX_MIX];
+    plb_trc_consts lin;
+    plb_tail_args tail;
+};
+
+__global__ void __launch_bounds__(256)
+k_pixel_mix(const __grid_constant__ plb_mix_args a)
+{
+    plm_tables_init();
+    plb_tail_stage(a.tail);
+    __syncthreads();
+    const plb_tail_args &t = plb_s_tail;
+    const int gx = blockIdx.x * PIX_TILE + threadIdx.x;
+    if (gx >= t.out_w)
+        return;
+    #pragma unroll 1
+    for (int r = 0; r < PIX_TILE / 8; r++) {
+        const int gy = blockIdx.y * PIX_TILE + threadIdx.y + 8 * r;
+        if (gy >= t.out_h)
+            break;
+        float prim[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int i = 0; i < a.n; i++) {
+            const float4 c4 = plb_load(a.tex[i], gx, gy);
+            float c[4] = { c4.x, c4.y, c4.z, c4.w };
+            if (!a.linearize) { // a single frame: nothing to mix
+                prim[0] = c[0]; prim[1] = c[1]; prim[2] = c[2]; prim[3] = c[3];
+                break;
+            }
+            plb_linearize(a.lin.trc, a.lin, c);
+            #pragma unroll
+            for (int k = 0; k < 4; k++)
+                prim[k] = __fmaf_rn(a.weight[i], c[k], prim[k]);
+        }
+        float color[4];
+        uint32_t ypq = 0;
+        const plb_op_peak *pk = nullptr;
+        plb_tail_color(gx, gy, prim, color, &ypq, &pk);
+        if (t.dst.ptr)
+            plb_store(t.dst, t.dst_x0 + gx, t.dst_y0 + gy, make_float4(color[0], color[1], color[2], color[3]));
+    }
+}
+
+extern "C" bool plb_launch_mix(pl_gpu gpu, const struct plb_mix_launch *p)
+{
+    const struct plb_pixel_launch *tl = &p->tail;
+    for (int i = 0; i < tl->prog.n; i++) {
+        if (tl->prog.ops[i].kind == PLB_OP_PEAK) {
+            PLB_ERR(gpu->log, "frame mixing: peak detection cannot follow the mixing stage");
+            return false;
+        }
+    }
+    plb_mix_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = p->n;
+    a.linearize = p->linearize;
+    memcpy(a.tex, p->tex, sizeof(a.tex));
+    memcpy(a.weight, p->weight, sizeof(a.weight));
+    a.lin = p->lin;
+    plb_fill_tail(&a.tail, tl);
+    memcpy(a.tail.src_map, p->src_map, sizeof(p->src_map));
+    dim3 block(32, 8);
+    dim3 grid((tl->out_w + PIX_TILE - 1) / PIX_TILE, (tl->out_h + PIX_TILE - 1) / PIX_TILE);
+    k_pixel_mix<<<grid, block, 0, STREAM(gpu)>>>(a);
+    plb_gpu_priv(gpu)->launches++;
+    return plb_cuda_check(gpu, cudaGetLastError(), "k_pixel_mix");
+}

@@ -40,6 +40,18 @@ struct pl_renderer_t {
     struct sampler_state sampler_main, sampler_contrast, samplers_src[4], samplers_dst[4];
     pl_shader_obj tone_map_state, dither_state, grain_state[4];
     pl_shader_obj lut_state[3];     // LUT_IMAGE, LUT_TARGET, LUT_PARAMS (renderer.c:96-100)
+    // frame mixing cache (renderer.c:73-95 `struct cached_frame`): frames rendered up to the
+    // target colour space, keyed by the caller's signature
+    struct cached_frame {
+        uint64_t signature;
+        uint64_t params_hash;
+        struct pl_color_space color;
+        pl_rect2df crop;
+        int comps;
+        pl_tex tex;
+        bool evict;
+    } frames[16];
+    int num_frames;
     int prev_dither;
     bool have_frame_index;
     uint8_t frame_index;
@@ -143,6 +155,8 @@ void pl_renderer_destroy(pl_renderer *prr)
     pl_shader_obj_destroy(&rr->sampler_contrast.down);
     for (int i = 0; i < 3; i++)
         pl_shader_obj_destroy(&rr->lut_state[i]);
+    for (int i = 0; i < rr->num_frames; i++)
+        pl_tex_destroy(rr->gpu, &rr->frames[i].tex);
     for (int i = 0; i < 4; i++) {
         pl_shader_obj_destroy(&rr->samplers_dst[i].up);
         pl_shader_obj_destroy(&rr->samplers_dst[i].down);
@@ -1763,6 +1777,262 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
         pl_dispatch_abort(rr->dp, &pass.sh);
     }
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------
+// pl_render_image_mix (renderer.c:3477-3508, :3612-4025)
+// ---------------------------------------------------------------------------------------
+
+const struct pl_frame *pl_frame_mix_current(const struct pl_frame_mix *mix)
+{
+    const struct pl_frame *cur = NULL;
+    for (int i = 0; i < mix->num_frames; i++) {
+        if (mix->timestamps[i] > 0.0f)
+            break;
+        cur = mix->frames[i];
+    }
+    return cur;
+}
+
+const struct pl_frame *pl_frame_mix_nearest(const struct pl_frame_mix *mix)
+{
+    if (!mix->num_frames)
+        return NULL;
+    const struct pl_frame *best = mix->frames[0];
+    float best_dist = fabsf(mix->timestamps[0]);
+    for (int i = 1; i < mix->num_frames; i++) {
+        const float dist = fabsf(mix->timestamps[i]);
+        if (dist >= best_dist)
+            break;
+        best = mix->frames[i];
+        best_dist = dist;
+    }
+    return best;
+}
+
+// identity of everything in the parameters that shapes a cached frame (the reference hashes the
+// pointed-to structures, :3510-3560; here: the struct itself plus the structures it points to)
+static uint64_t params_hash(const struct pl_render_params *p)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+#define MIX(ptr, n) do { const uint8_t *b_ = (const uint8_t *) (ptr); \
+        for (size_t i_ = 0; i_ < (n); i_++) h = (h ^ b_[i_]) * 0x100000001b3ull; } while (0)
+    MIX(p, sizeof(*p));
+    if (p->upscaler) MIX(p->upscaler, sizeof(*p->upscaler));
+    if (p->downscaler) MIX(p->downscaler, sizeof(*p->downscaler));
+    if (p->plane_upscaler) MIX(p->plane_upscaler, sizeof(*p->plane_upscaler));
+    if (p->deband_params) MIX(p->deband_params, sizeof(*p->deband_params));
+    if (p->sigmoid_params) MIX(p->sigmoid_params, sizeof(*p->sigmoid_params));
+    if (p->color_map_params) MIX(p->color_map_params, sizeof(*p->color_map_params));
+    if (p->peak_detect_params) MIX(p->peak_detect_params, sizeof(*p->peak_detect_params));
+#undef MIX
+    return h;
+}
+
+extern float plb_filter_radius_bound(const struct pl_filter_config *c);
+extern bool plb_shader_mix(pl_shader sh, int n, const pl_tex *texs, const float *weights, int w, int h,
+                           const struct pl_color_space *lin_csp);
+
+bool pl_render_image_mix(pl_renderer rr, const struct pl_frame_mix *images,
+                         const struct pl_frame *ptarget, const struct pl_render_params *params)
+{
+    params = params ? params : &pl_render_default_params;
+    if (!images || !ptarget) {
+        PLB_ERR(rr->log, "pl_render_image_mix: frame mix and target are required");
+        return false;
+    }
+    if (!images->num_frames) {
+        PLB_ERR(rr->log, "pl_render_image_mix: rendering without a source image (target clearing "
+                "only) is outside the CUDA hot path");
+        return false;
+    }
+    if (!(images->vsync_duration > 0.0)) {
+        PLB_ERR(rr->log, "pl_render_image_mix: vsync_duration must be positive");
+        return false;
+    }
+    for (int i = 0; i < images->num_frames - 1; i++) {
+        if (!(images->timestamps[i] <= images->timestamps[i + 1])) {
+            PLB_ERR(rr->log, "pl_render_image_mix: timestamps must be sorted");
+            return false;
+        }
+    }
+    const struct pl_frame *refimg = pl_frame_mix_nearest(images);
+    if (rr->errors & PL_RENDER_ERR_FRAME_MIXING)
+        return pl_render_image(rr, refimg, ptarget, params);
+
+    struct pass_state pass = { .rr = rr, .params = params, .image = *refimg, .target = *ptarget };
+    if (!pass_begin(&pass))
+        return false;
+    const struct pl_frame *target = &pass.target;
+    const int out_w = abs(pl_rect_w(pass.dst_rect)), out_h = abs(pl_rect_h(pass.dst_rect));
+    if (!out_w || !out_h)
+        return true;
+    const uint64_t phash = params_hash(params);
+
+    for (int i = 0; i < rr->num_frames; i++)
+        rr->frames[i].evict = true;
+
+    // blur the frame mixer according to the vsync ratio (source / display), :3661-3674
+    struct pl_filter_config mixer = {0};
+    if (params->frame_mixer) {
+        mixer = *params->frame_mixer;
+        mixer.blur = PLB_DEF(mixer.blur, 1.0);
+        for (int i = 1; i < images->num_frames; i++) {
+            if (images->timestamps[i] >= 0.0 && images->timestamps[i - 1] < 0) {
+                const float frame_dur = images->timestamps[i] - images->timestamps[i - 1];
+                const float sample_dur = PLB_MAX(frame_dur, images->vsync_duration);
+                if (sample_dur > 1.0f && !params->skip_anti_aliasing)
+                    mixer.blur *= sample_dur;
+                break;
+            }
+        }
+    }
+
+    pl_tex texs[PLB_MAX_MIX];
+    float weights[PLB_MAX_MIX];
+    int fidx = 0;
+    float wsum = 0.0;
+    bool single_frame = !params->frame_mixer || images->num_frames == 1;
+retry:
+    for (int i = 0; i < images->num_frames; i++) {
+        const uint64_t sig = images->signatures[i];
+        float rts = images->timestamps[i];
+        const struct pl_frame *img = images->frames[i];
+        float weight;
+        if (single_frame) {
+            if (img != refimg)
+                continue; // only the reference image
+            weight = 1.0;
+        } else if (!mixer.kernel || mixer.kernel == &pl_filter_function_oversample) {
+            // visible interval [rts, end] of this frame against the vsync interval
+            float end = i + 1 < images->num_frames ? images->timestamps[i + 1] : INFINITY;
+            if (rts > images->vsync_duration || end < 0.0)
+                continue;
+            rts = PLB_MAX(rts, 0.0);
+            end = PLB_MIN(end, images->vsync_duration);
+            weight = (end - rts) / images->vsync_duration;
+            if (mixer.kernel && weight < mixer.kernel->params[0])
+                weight = 0.0; // culled by the threshold
+        } else {
+            const float radius = plb_filter_radius_bound(&mixer);
+            if (fabsf(rts) >= radius)
+                continue;
+            weight = pl_filter_sample(&mixer, rts);
+        }
+
+        struct cached_frame *f = NULL;
+        for (int j = 0; j < rr->num_frames; j++) {
+            if (rr->frames[j].signature == sig) {
+                f = &rr->frames[j];
+                f->evict = false;
+                break;
+            }
+        }
+        // frames with negligible contributions are skipped (never the reference image)
+        if (fabsf(weight) <= 1e-3 && img != refimg)
+            continue;
+        if (fidx == PLB_MAX_MIX) {
+            PLB_ERR(rr->log, "pl_render_image_mix: more than %d contributing frames", PLB_MAX_MIX);
+            goto fail;
+        }
+        if (!f) {
+            if (rr->num_frames == (int) PLB_ARRAY_SIZE(rr->frames)) {
+                PLB_ERR(rr->log, "pl_render_image_mix: frame cache full");
+                goto fail;
+            }
+            f = &rr->frames[rr->num_frames++];
+            memset(f, 0, sizeof(*f));
+            f->signature = sig;
+        }
+        const bool can_reuse = f->tex && f->tex->params.w == out_w && f->tex->params.h == out_h &&
+                               pl_rect2d_eq(f->crop, img->crop) && f->params_hash == phash &&
+                               pl_color_space_equal(&f->color, &target->color);
+        if (!can_reuse) {
+            if (!pl_tex_recreate(rr->gpu, &f->tex, pl_tex_params(
+                    .w = out_w, .h = out_h, .format = rr->fbofmt[4],
+                    .sampleable = true, .renderable = true, .storable = true))) {
+                PLB_ERR(rr->log, "Could not create intermediate texture for frame mixing.. disabling!");
+                goto fail;
+            }
+            // render this frame up to (not including) the output stage, :3822-3853
+            struct pass_state ip = { .rr = rr, .params = params, .image = *img, .target = *ptarget };
+            bool ok = pass_begin(&ip) && pass_read_image(&ip) && pass_scale_main(&ip) &&
+                      pass_convert_colors(&ip);
+            if (ok) {
+                pl_shader ish = img_sh(&ip);
+                ip.sh = NULL;
+                pl_shader_set_alpha(ish, &ip.repr, PL_ALPHA_PREMULTIPLIED); // for frame mixing
+                ok = ip.w == out_w && ip.h == out_h &&
+                     pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = &ish, .target = f->tex ));
+                if (ish)
+                    pl_dispatch_abort(rr->dp, &ish);
+            } else {
+                pl_dispatch_abort(rr->dp, &ip.sh);
+            }
+            free_views(rr);
+            if (!ok)
+                goto fail;
+            f->params_hash = phash;
+            f->crop = img->crop;
+            f->color = ip.color;
+            f->comps = ip.comps;
+        }
+        texs[fidx] = f->tex;
+        weights[fidx] = weight;
+        wsum += weight;
+        fidx++;
+    }
+
+    // evict the frames we do not need any more
+    for (int i = 0; i < rr->num_frames;) {
+        if (rr->frames[i].evict) {
+            pl_tex_destroy(rr->gpu, &rr->frames[i].tex);
+            rr->frames[i] = rr->frames[--rr->num_frames];
+        } else {
+            i++;
+        }
+    }
+
+    if (!fidx) { // no frame intersects the vsync: zero-order hold
+        single_frame = true;
+        goto retry;
+    }
+
+    // sample and mix the output colour, :3906-3990
+    memset(rr->fbo_used, 0, sizeof(rr->fbo_used));
+    const bool mixing = fidx > 1;
+    struct pl_color_space mix_csp = target->color;
+    if (mixing)
+        mix_csp.transfer = PL_COLOR_TRC_LINEAR;
+    for (int i = 0; i < fidx; i++)
+        weights[i] = mixing ? weights[i] / wsum : 1.0f;
+    pl_shader sh = begin(&pass);
+    if (!plb_shader_mix(sh, fidx, texs, weights, out_w, out_h, mixing ? &target->color : NULL)) {
+        pl_dispatch_abort(rr->dp, &sh);
+        goto fail;
+    }
+    pass.sh = sh;
+    pass.tex = NULL;
+    pass.w = out_w;
+    pass.h = out_h;
+    pass.comps = 3;
+    pass.color = target->color;
+    pass.rect = (pl_rect2df) { 0, 0, out_w, out_h };
+    pass.repr = (struct pl_color_repr) { .sys = PL_COLOR_SYSTEM_RGB, .levels = PL_COLOR_LEVELS_FULL,
+                                         .alpha = PL_ALPHA_NONE };
+    // re-encode to the target transfer (in practice: delinearise)
+    if (!pl_color_space_equal(&mix_csp, &pass.color))
+        pl_shader_color_map_ex(sh, NULL, pl_color_map_args( .src = mix_csp, .dst = pass.color ));
+    if (!pass_output_target(&pass)) {
+        pl_dispatch_abort(rr->dp, &pass.sh);
+        return false;
+    }
+    return true;
+
+fail:
+    PLB_ERR(rr->log, "Could not render image for frame mixing.. disabling!");
+    rr->errors |= PL_RENDER_ERR_FRAME_MIXING;
+    return pl_render_image(rr, refimg, ptarget, params);
 }
 
 // Phase 1 of the frame-parallel scheme: run the path up to (and including) the peak detection

@@ -86,6 +86,7 @@ enum plb_src_kind {
     PLB_SRC_POLAR,
     PLB_SRC_ORTHO,
     PLB_SRC_ERRDIFF,    // pl_shader_error_diffusion (compute-only shader)
+    PLB_SRC_MIX,        // frame mixing (pl_render_image_mix)
 };
 
 struct pl_shader_t {
@@ -100,6 +101,7 @@ struct pl_shader_t {
     struct plb_polar_launch polar;
     struct plb_ortho_launch ortho;
     struct plb_errdiff_launch errdiff;
+    struct plb_mix_launch mix;
     struct plb_pixel_launch px;    // planes + program + (later) target
     // shader objects referenced by this shader (kept alive until dispatch)
     pl_shader_obj objs[16];

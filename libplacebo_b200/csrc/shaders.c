@@ -59,6 +59,7 @@ void pl_shader_reset(pl_shader sh, const struct pl_shader_params *params)
     for (int k = 0; k < 4; k++) {
         sh->polar.src_map[k] = k;
         sh->ortho.src_map[k] = k;
+        sh->mix.src_map[k] = k;
     }
 }
 
@@ -909,7 +910,7 @@ void pl_shader_encode_color(pl_shader sh, const struct pl_color_repr *repr)
     }
 }
 
-static void fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp, bool delin)
+void plb_fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp, bool delin)
 {
     memset(t, 0, sizeof(*t));
     t->trc = csp->transfer;
@@ -969,7 +970,7 @@ void plb_record_linearize(pl_shader sh, const struct pl_color_space *csp)
         return;
     struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_LINEARIZE);
     if (op)
-        fill_trc(&op->u.trc, csp, false);
+        plb_fill_trc(&op->u.trc, csp, false);
 }
 
 void plb_record_delinearize(pl_shader sh, const struct pl_color_space *csp)
@@ -978,12 +979,7 @@ void plb_record_delinearize(pl_shader sh, const struct pl_color_space *csp)
         return;
     struct plb_color_op *op = plb_shader_push_op(sh, PLB_OP_DELINEARIZE);
     if (op)
-        fill_trc(&op->u.trc, csp, true);
-}
-
-void plb_fill_trc(struct plb_trc_consts *t, const struct pl_color_space *csp, bool delin)
-{
-    fill_trc(t, csp, delin);
+        plb_fill_trc(&op->u.trc, csp, true);
 }
 
 void pl_shader_linearize(pl_shader sh, const struct pl_color_space *csp)
@@ -996,6 +992,41 @@ void pl_shader_delinearize(pl_shader sh, const struct pl_color_space *csp)
 {
     if (plb_shader_require_color(sh, "pl_shader_delinearize"))
         plb_record_delinearize(sh, csp);
+}
+
+// Source stage of pl_render_image_mix (renderer.c:3906-3966): `n` cached frames of the output
+// size, sampled 1:1, taken to linear light (`lin_csp` != NULL: more than one frame) and summed
+// with the normalised weights.
+bool plb_shader_mix(pl_shader sh, int n, const pl_tex *texs, const float *weights, int w, int h,
+                    const struct pl_color_space *lin_csp)
+{
+    if (sh->src != PLB_SRC_NONE || sh->px.prog.n) {
+        plb_shader_fail(sh, "frame mixing needs an empty shader");
+        return false;
+    }
+    if (n < 1 || n > PLB_MAX_MIX) {
+        plb_shader_fail(sh, "frame mixing: %d frames (max %d)", n, PLB_MAX_MIX);
+        return false;
+    }
+    struct plb_mix_launch *m = &sh->mix;
+    m->n = n;
+    for (int i = 0; i < n; i++) {
+        if (texs[i]->params.w != w || texs[i]->params.h != h) {
+            plb_shader_fail(sh, "frame mixing: cached frame %d has the wrong size", i);
+            return false;
+        }
+        m->tex[i] = plb_tex_priv(texs[i])->d;
+        m->weight[i] = weights[i];
+        plb_shader_use_tex(sh, texs[i]);
+    }
+    m->linearize = lin_csp != NULL;
+    if (lin_csp)
+        plb_fill_trc(&m->lin, lin_csp, false);
+    sh->src = PLB_SRC_MIX;
+    sh->out_w = w;
+    sh->out_h = h;
+    plb_shader_describe(sh, n > 1 ? "frame mixing" : "frame mixing (1 frame)");
+    return true;
 }
 
 const struct pl_sigmoid_params pl_sigmoid_default_params = { PL_SIGMOID_DEFAULTS };

@@ -283,6 +283,12 @@ static float radius_bound(const struct pl_filter_config *c)
     return c->blur > 0.0 ? r * c->blur : r;
 }
 
+// src/filters.h pl_filter_radius_bound (library-internal in the reference; the frame mixer uses it)
+float plb_filter_radius_bound(const struct pl_filter_config *c)
+{
+    return radius_bound(c);
+}
+
 static bool same_function(const struct pl_filter_function *a, const struct pl_filter_function *b)
 {
     return (a ? a->weight : NULL) == (b ? b->weight : NULL);

@@ -273,6 +273,8 @@ ORC_API void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *lu
 
 // pl_shader_extract_features (colorspace.c:1383-1404) on linear RGB; m = rgb2lms (float)
 ORC_API void orc_extract_features(float *rgba, size_t npix, const float m[9]);
+// pl_render_image_mix accumulation (renderer.c:3955): acc = fma(w, rgba, acc), all four components
+ORC_API void orc_mix_accumulate(float *acc, const float *rgba, size_t npix, float w);
 // pl_shader_custom_lut (shaders/lut.c:212-280); data = RGB triples (red fastest), size[1] == 0: 1-D
 ORC_API void orc_custom_lut(float *rgba, size_t npix, const float *data, const int size[3],
                             const float *shaper_in, const float *shaper_out);

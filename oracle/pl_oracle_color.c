@@ -209,6 +209,14 @@ void orc_custom_lut(float *rgba, size_t npix, const float *data, const int size[
         orc_apply_matrix(rgba, npix, shaper_out, NULL);
 }
 
+// frame mixing accumulation of pl_render_image_mix (renderer.c:3955): mix_color += w * color
+void orc_mix_accumulate(float *acc, const float *rgba, size_t npix, float w)
+{
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < 4 * npix; i++)
+        acc[i] = fmaf(w, rgba[i], acc[i]);
+}
+
 void orc_scale(float *rgba, size_t npix, float scale, int with_alpha)
 {
     #pragma omp parallel for schedule(static)

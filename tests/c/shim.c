@@ -59,6 +59,12 @@ struct shim_ctx {
     /* planar target of the next shim_render call (shim_set_target_planes) */
     int tgt_nplanes, tgt_chroma_loc;
     pl_tex tgt_planes[3];
+    /* frame mix of the next shim_render call (shim_set_mix): further frames around the vsync */
+    int mix_n;
+    pl_tex mix_planes[8][3];
+    float mix_ts[8], mix_vsync;
+    uint64_t mix_sig[8];
+    char mix_filter[48];
     /* custom LUTs of the next shim_render call (shim_set_lut): 0 params, 1 image, 2 target */
     struct pl_custom_lut lut[3];
     int lut_type[3];
@@ -495,6 +501,24 @@ API void shim_set_lut(struct shim_ctx *c, int which, int type, const float *data
     }
 }
 
+/* The next shim_render call becomes pl_render_image_mix: n frames of three planes each (planes =
+ * n * 3 textures; the `planes` argument of shim_render is ignored), their timestamps relative to
+ * the vsync, signatures, the vsync duration and the frame mixer ("" = none, i.e. nearest frame;
+ * a filter preset name such as "oversample", "linear", "mitchell_clamp"). */
+API void shim_set_mix(struct shim_ctx *c, int n, void **planes, const float *timestamps,
+                      const unsigned long long *signatures, float vsync, const char *mixer)
+{
+    c->mix_n = n;
+    for (int i = 0; i < n && i < 8; i++) {
+        for (int k = 0; k < 3; k++)
+            c->mix_planes[i][k] = planes[3 * i + k];
+        c->mix_ts[i] = timestamps[i];
+        c->mix_sig[i] = signatures[i];
+    }
+    c->mix_vsync = vsync;
+    snprintf(c->mix_filter, sizeof(c->mix_filter), "%s", mixer ? mixer : "");
+}
+
 /* ---- pl_render_image driver ------------------------------------------------------------------
  * planes: up to 3 source textures (Y, U, V) or a single packed one (nplanes = 1, RGB)
  * img / tgt: repr (sys, levels, sample_depth, color_depth, bit_shift) followed by csp[20]
@@ -648,7 +672,29 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
     }
     if (opts[7] >= 0)
         pl_renderer_set_frame_index(c->rr, (uint8_t) opts[7]);
-    const bool rendered = pl_render_image(c->rr, &image, &target, &par);
+    bool rendered;
+    if (c->mix_n) {
+        struct pl_frame frames[8];
+        const struct pl_frame *fptr[8];
+        for (int i = 0; i < c->mix_n; i++) {
+            frames[i] = image;
+            for (int k = 0; k < 3; k++)
+                frames[i].planes[k].texture = c->mix_planes[i][k];
+            fptr[i] = &frames[i];
+        }
+        const struct pl_frame_mix mix = {
+            .num_frames = c->mix_n,
+            .frames = fptr,
+            .signatures = c->mix_sig,
+            .timestamps = c->mix_ts,
+            .vsync_duration = c->mix_vsync,
+        };
+        par.frame_mixer = c->mix_filter[0] ? pl_find_filter_config(c->mix_filter, 0) : NULL;
+        rendered = pl_render_image_mix(c->rr, &mix, &target, &par);
+        c->mix_n = 0;
+    } else {
+        rendered = pl_render_image(c->rr, &image, &target, &par);
+    }
     memset(c->lut, 0, sizeof(c->lut));
     if (!rendered)
         return -1;

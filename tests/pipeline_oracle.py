@@ -144,7 +144,7 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
            coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
            error_diffusion=None, film_grain=None, contrast_recovery=0.0, contrast_smoothness=3.5,
-           luts=None):
+           luts=None, _return_color=False, _start_color=None):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
     smoothed (avg, max) between frames like sh_color_map_obj.peak does.
     luts: {"params": (type, data, size), "image": (...), "target": (...)} with type in
@@ -410,6 +410,10 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
             p.width, p.height = out_w, out_h
         color = orc.color_map(color, p)
 
+    if _return_color:      # the image in the target colour space, before the output stage
+        return color, new_state
+    if _start_color is not None:
+        color = _start_color
     # ---- output: encode, dither, scale, store
     enc_skip = (tgt.sys in (T.SYS["UNKNOWN"], T.SYS["RGB"]) and tgt.levels in (0, T.LEVELS["FULL"])
                 and (not tbits[0] or not tbits[1] or tbits[0] == tbits[1]) and not tbits[2])
@@ -438,6 +442,78 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
     color = orc.scale(color, float(f32(1.0 / tnorm)), True)
     color[..., 3] = 1.0  # swizzle_color leaves alpha = 1 for opaque images
     return store(orc, color, tgt.fmt), new_state
+
+
+def mix_weights(timestamps, vsync, mixer, t0):
+    """Weights of pl_render_image_mix (renderer.c:3661-3757). Returns [(frame index, weight)]."""
+    n = len(timestamps)
+    ref = 0
+    for i in range(1, n):  # pl_frame_mix_nearest
+        if abs(timestamps[i]) < abs(timestamps[ref]):
+            ref = i
+        else:
+            break
+    if not mixer or n == 1:
+        return [(ref, 1.0)]
+    blur = 1.0
+    for i in range(1, n):
+        if timestamps[i] >= 0.0 and timestamps[i - 1] < 0:
+            sample_dur = max(f32(timestamps[i]) - f32(timestamps[i - 1]), f32(vsync))
+            if sample_dur > 1.0:
+                blur *= float(sample_dur)
+            break
+    out = []
+    for i in range(n):
+        rts = f32(timestamps[i])
+        if mixer == "oversample":
+            end = f32(timestamps[i + 1]) if i + 1 < n else f32(np.inf)
+            if rts > vsync or end < 0.0:
+                continue
+            rts, end = max(rts, f32(0.0)), min(end, f32(vsync))
+            w = f32(f32(end - rts) / f32(vsync))
+        else:
+            # pl_filter_radius_bound: kernel radius * blur (the presets used here are not resizable)
+            radius = f32({"mitchell_clamp": 2.0, "linear": 1.0, "hermite": 1.0, "catmull_rom": 2.0}[mixer] * blur)
+            if abs(rts) >= radius:
+                continue
+            w = f32(t0.filter_sample(mixer, float(rts), blur=blur))
+        if abs(w) <= 1e-3 and i != ref:
+            continue
+        out.append((i, float(w)))
+    return out or [(ref, 1.0)]
+
+
+def render_mix(imgs, timestamps, vsync, tgt, mixer="", **kw):
+    """pl_render_image_mix (renderer.c:3612-4025): every contributing frame is rendered up to the
+    target colour space into an rgba16hf image, the images are linearised, summed with the
+    normalised weights, delinearised and sent through the output stage."""
+    t0, orc = T.t0(), T.oracle()
+    ws = mix_weights(timestamps, vsync, mixer, t0)
+    fbos = []
+    for i, _ in ws:
+        c, _ = render(imgs[i], tgt, _return_color=True, **kw)
+        fbos.append(orc.store_round(c, 0))  # cached frame: rgba16hf at the output size
+    if len(ws) == 1:
+        color = fbos[0]
+    else:
+        _, dst_csp = t0.csp_infer_map(imgs[0].csp.copy(), tgt.csp)
+        dst_trc = int(dst_csp[1])
+        dmin, dmax, _ = t0.nominal_luma(dst_csp, T.META["HDR10"], T.HDR["NORM"])
+        dluma = luma_coeffs(t0, int(dst_csp[0]))
+        wsum = f32(0.0)
+        for _, w in ws:
+            wsum = f32(wsum + f32(w))
+        acc = np.zeros_like(fbos[0])
+        for (_, w), fb in zip(ws, fbos):
+            lin = orc.linearize(fb, dst_trc, dmin, dmax, dluma)
+            acc = orc.mix_accumulate(acc, lin, float(f32(w) / wsum))
+        # re-encode to the target transfer: pl_shader_color_map_ex(NULL, linear -> target)
+        lin_csp = dst_csp.copy()
+        lin_csp[1] = T.TRC["LINEAR"]
+        cm = color_map_params(t0, lin_csp, dst_csp, state=False)
+        color = orc.color_map(acc, cm["params"]) if cm is not None else acc
+    out, _ = render(imgs[0], tgt, _start_color=color, **kw)
+    return out
 
 
 def planar_output(orc, t0, color, tgt, tnorm, depth, dither, dst_trc, frame_index, coord_mode):

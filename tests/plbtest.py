@@ -549,6 +549,12 @@ class Oracle:
         self.lib.orc_extract_features(fp(rgba), C.c_size_t(rgba.size // 4), fp(m))
         return rgba
 
+    def mix_accumulate(self, acc, rgba, w):
+        acc = np.ascontiguousarray(acc, f32).copy()
+        rgba = np.ascontiguousarray(rgba, f32)
+        self.lib.orc_mix_accumulate(fp(acc), fp(rgba), C.c_size_t(rgba.size // 4), C.c_float(w))
+        return acc
+
     def custom_lut(self, rgba, data, size, shaper_in=None, shaper_out=None):
         """pl_shader_custom_lut: data = RGB triples (red fastest); size = (n, 0, 0) or (r, g, b)."""
         rgba = np.ascontiguousarray(rgba, f32).copy()
