@@ -1167,7 +1167,7 @@ struct pl_render_params { /* renderer.h:130-368; members outside the hot path ar
     const struct pl_error_diffusion_kernel *error_diffusion;
     const void *cone_params;
     const struct pl_blend_params *blend_params;
-    const void *deinterlace_params;
+    const struct pl_deinterlace_params *deinterlace_params;   /* renderer.h:305-310 */
     const void *distort_params;
     const void * const *hooks;
     int num_hooks;
@@ -1220,7 +1220,35 @@ struct pl_plane { /* renderer.h:404-472 */
     int component_mapping[4];
     float shift_x, shift_y;
 };
-enum pl_field { PL_FIELD_NONE = 0, PL_FIELD_EVEN, PL_FIELD_ODD };
+enum pl_field { PL_FIELD_NONE = 0, PL_FIELD_EVEN, PL_FIELD_ODD,
+                PL_FIELD_TOP = PL_FIELD_EVEN, PL_FIELD_BOTTOM = PL_FIELD_ODD };
+/* shaders/deinterlacing.h:30-137 — deinterlacing of interleaved (MBAFF) frames */
+struct pl_field_pair { pl_tex top; };
+#define pl_field_pair(...) ((struct pl_field_pair) { __VA_ARGS__ })
+struct pl_deinterlace_source {
+    struct pl_field_pair prev, cur, next;   /* prev / next: optional neighbouring frames */
+    enum pl_field field;                    /* the field being shown (its lines are kept) */
+    enum pl_field first_field;              /* temporal order of the fields; NONE = top first */
+    uint8_t component_mask;                 /* 0 = all components of the texture */
+};
+#define pl_deinterlace_source(...) (&(struct pl_deinterlace_source) { __VA_ARGS__ })
+enum pl_deinterlace_algorithm {
+    PL_DEINTERLACE_WEAVE = 0, PL_DEINTERLACE_BOB, PL_DEINTERLACE_YADIF, PL_DEINTERLACE_BWDIF,
+    PL_DEINTERLACE_ALGORITHM_COUNT,
+};
+static inline bool pl_deinterlace_needs_refs(enum pl_deinterlace_algorithm algo)
+{
+    return algo >= PL_DEINTERLACE_YADIF;
+}
+struct pl_deinterlace_params {
+    enum pl_deinterlace_algorithm algo;
+    bool skip_spatial_check;
+};
+#define PL_DEINTERLACE_DEFAULTS .algo = PL_DEINTERLACE_BWDIF,
+#define pl_deinterlace_params(...) (&(struct pl_deinterlace_params) { PL_DEINTERLACE_DEFAULTS __VA_ARGS__ })
+PL_API extern const struct pl_deinterlace_params pl_deinterlace_default_params;
+PL_API void pl_shader_deinterlace(pl_shader sh, const struct pl_deinterlace_source *src,
+                                  const struct pl_deinterlace_params *params);
 struct pl_frame { /* renderer.h:528-655 */
     int num_planes;
     struct pl_plane planes[PL_MAX_PLANES];

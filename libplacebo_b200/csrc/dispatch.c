@@ -268,6 +268,10 @@ bool plb_dispatch_run(pl_dispatch dp, pl_shader sh, pl_tex target, pl_rect2d rc,
         sh->mix.tail = *px;
         ok = plb_launch_mix(gpu, &sh->mix);
         break;
+    case PLB_SRC_DEINT:
+        sh->deint.tail = *px;
+        ok = plb_launch_deint(gpu, &sh->deint);
+        break;
     default:
         break;
     }

@@ -546,6 +546,7 @@ bool plb_pq_upload_polar(const plb_pq_consts *q);
 bool plb_pq_upload_pixel(const plb_pq_consts *q);
 bool plb_pq_upload_ortho(const plb_pq_consts *q);
 bool plb_pq_upload_up2a(const plb_pq_consts *q);
+bool plb_pq_upload_deint(const plb_pq_consts *q);
 bool plb_pq_upload_up2b(const plb_pq_consts *q);
 bool plb_pq_upload_up2c(const plb_pq_consts *q);
 
@@ -600,7 +601,8 @@ bool plb_upload_pq_consts(pl_gpu gpu)
         q.cv_bank = d;
         ok = ok && cudaMemcpy(d, host, total, cudaMemcpyHostToDevice) == cudaSuccess &&
              plb_pq_upload_polar(&q) && plb_pq_upload_pixel(&q) && plb_pq_upload_ortho(&q) &&
-             plb_pq_upload_up2a(&q) && plb_pq_upload_up2b(&q) && plb_pq_upload_up2c(&q);
+             plb_pq_upload_up2a(&q) && plb_pq_upload_up2b(&q) && plb_pq_upload_up2c(&q) &&
+             plb_pq_upload_deint(&q);
         free(host);
         if (ok) {
             g_bank[p->device].tables = d;

@@ -413,6 +413,18 @@ struct plb_mix_launch {
 };
 bool plb_launch_mix(pl_gpu gpu, const struct plb_mix_launch *p);
 
+// pl_shader_deinterlace (shaders/deinterlacing.c)
+struct plb_deint_launch {
+    struct plb_tex_desc cur, prev, next;   // prev / next = cur when absent
+    int field;                             // enum pl_field
+    int prev2_is_prev, next2_is_cur;
+    int algo, skip_spatial_check, intra_only;
+    uint8_t comp_mask;
+    int8_t src_map[4];
+    struct plb_pixel_launch tail;
+};
+bool plb_launch_deint(pl_gpu gpu, const struct plb_deint_launch *p);
+
 struct plb_errdiff_launch {
     struct plb_tex_desc src, dst;
     int w, h;

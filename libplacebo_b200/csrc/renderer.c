@@ -785,6 +785,54 @@ static bool pass_read_image(struct pass_state *pass)
             }
         }
     }
+    // Deinterlace the planes first (renderer.c:1591-1612). On this backend every deinterlaced
+    // plane goes through a texture of the plane's own format (the reference keeps it as a pending
+    // shader and materialises it the same way as soon as debanding, scaling or grain needs a
+    // texture; a plane merged directly would skip that rounding step).
+    if (image->field != PL_FIELD_NONE && params->deinterlace_params &&
+        !(rr->errors & PL_RENDER_ERR_DEINTERLACING)) {
+        const struct pl_frame *refs[2] = { image->prev, image->next };
+        for (int r = 0; r < 2; r++) {
+            if (!refs[r])
+                continue;
+            bool ok = refs[r]->num_planes == image->num_planes;
+            for (int i = 0; ok && i < image->num_planes; i++) {
+                pl_tex a = refs[r]->planes[i].texture, b = image->planes[i].texture;
+                ok = a && a->params.w == b->params.w && a->params.h == b->params.h &&
+                     a->params.format == b->params.format;
+            }
+            if (!ok) {
+                PLB_ERR(rr->log, "pl_render_image: deinterlacing reference frames must match the "
+                        "image's planes (count, size, format)");
+                return false;
+            }
+        }
+        for (int i = 0; i < image->num_planes; i++) {
+            struct plane_state *st = &planes[i];
+            if (!st->type)
+                continue;
+            const struct pl_deinterlace_source src = {
+                .cur.top = st->tex,
+                .prev.top = image->prev ? image->prev->planes[i].texture : NULL,
+                .next.top = image->next ? image->next->planes[i].texture : NULL,
+                .field = image->field,
+                .first_field = image->first_field,
+                .component_mask = (1 << st->comps) - 1,
+            };
+            pl_tex out = get_fbo(pass, st->w, st->h, st->fmt, 0);
+            pl_shader dsh = out ? begin(pass) : NULL;
+            if (dsh)
+                pl_shader_deinterlace(dsh, &src, params->deinterlace_params);
+            if (!dsh || !pl_dispatch_finish(rr->dp, pl_dispatch_params( .shader = &dsh, .target = out ))) {
+                PLB_ERR(rr->log, "Failed deinterlacing plane.. disabling!");
+                rr->errors |= PL_RENDER_ERR_DEINTERLACING;
+                if (dsh)
+                    pl_dispatch_abort(rr->dp, &dsh);
+                break;
+            }
+            st->tex = out;
+        }
+    }
     pl_tex ref_tex = ref->plane.texture;
 
     // --- A. merge compatible planes (chroma pairs) ---
@@ -1630,7 +1678,6 @@ static bool check_params(pl_renderer rr, const struct pl_render_params *p,
     REJECT(image->num_overlays || target->num_overlays, "overlays");
     REJECT(p->cone_params, "cone distortion");
     REJECT(p->blend_params, "blending");
-    REJECT(p->deinterlace_params && image->field != PL_FIELD_NONE, "deinterlacing");
     REJECT(p->distort_params, "distortion");
     REJECT(p->corner_rounding > 0, "corner rounding");
     REJECT(p->border == PL_CLEAR_BLUR, "blurred borders");

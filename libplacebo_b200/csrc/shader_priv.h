@@ -87,6 +87,7 @@ enum plb_src_kind {
     PLB_SRC_ORTHO,
     PLB_SRC_ERRDIFF,    // pl_shader_error_diffusion (compute-only shader)
     PLB_SRC_MIX,        // frame mixing (pl_render_image_mix)
+    PLB_SRC_DEINT,      // pl_shader_deinterlace
 };
 
 struct pl_shader_t {
@@ -102,6 +103,7 @@ struct pl_shader_t {
     struct plb_ortho_launch ortho;
     struct plb_errdiff_launch errdiff;
     struct plb_mix_launch mix;
+    struct plb_deint_launch deint;
     struct plb_pixel_launch px;    // planes + program + (later) target
     // shader objects referenced by this shader (kept alive until dispatch)
     pl_shader_obj objs[16];

@@ -60,6 +60,7 @@ void pl_shader_reset(pl_shader sh, const struct pl_shader_params *params)
         sh->polar.src_map[k] = k;
         sh->ortho.src_map[k] = k;
         sh->mix.src_map[k] = k;
+        sh->deint.src_map[k] = k;
     }
 }
 
@@ -1027,6 +1028,69 @@ bool plb_shader_mix(pl_shader sh, int n, const pl_tex *texs, const float *weight
     sh->out_h = h;
     plb_shader_describe(sh, n > 1 ? "frame mixing" : "frame mixing (1 frame)");
     return true;
+}
+
+// pl_shader_deinterlace (shaders/deinterlacing.c:32-370): source stage over the interleaved
+// frame `src->cur.top` and, for the temporal algorithms, its neighbours.
+const struct pl_deinterlace_params pl_deinterlace_default_params = { PL_DEINTERLACE_DEFAULTS };
+
+void pl_shader_deinterlace(pl_shader sh, const struct pl_deinterlace_source *src,
+                           const struct pl_deinterlace_params *params)
+{
+    params = params ? params : &pl_deinterlace_default_params;
+    if (!src || !src->cur.top) {
+        plb_shader_fail(sh, "pl_shader_deinterlace: no source texture");
+        return;
+    }
+    if (sh->src != PLB_SRC_NONE || sh->px.prog.n) {
+        plb_shader_fail(sh, "pl_shader_deinterlace: the shader already has a source");
+        return;
+    }
+    const struct pl_tex_params *tp = &src->cur.top->params;
+    if ((sh->out_w && sh->out_w != tp->w) || (sh->out_h && sh->out_h != tp->h)) {
+        plb_shader_fail(sh, "pl_shader_deinterlace: incompatible output size");
+        return;
+    }
+    uint8_t mask = src->component_mask ? src->component_mask : 0xFu;
+    mask &= (1u << tp->format->num_components) - 1u;
+    if (!mask) {
+        plb_shader_fail(sh, "pl_shader_deinterlace: empty component mask?");
+        return;
+    }
+    const enum pl_field first_field = src->first_field ? src->first_field : PL_FIELD_TOP;
+    bool intra_only = params->algo != PL_DEINTERLACE_YADIF;
+    if (params->algo == PL_DEINTERLACE_BWDIF) {
+        intra_only = (!src->prev.top && src->field == first_field) ||
+                     (!src->next.top && src->field != first_field);
+    }
+    pl_tex prev = src->cur.top, next = src->cur.top;
+    if (!intra_only && src->prev.top)
+        prev = src->prev.top;
+    if (!intra_only && src->next.top)
+        next = src->next.top;
+    if (prev->params.w != tp->w || prev->params.h != tp->h || next->params.w != tp->w ||
+        next->params.h != tp->h) {
+        plb_shader_fail(sh, "pl_shader_deinterlace: reference fields differ in size");
+        return;
+    }
+    struct plb_deint_launch *d = &sh->deint;
+    d->cur = plb_tex_priv(src->cur.top)->d;
+    d->prev = plb_tex_priv(prev)->d;
+    d->next = plb_tex_priv(next)->d;
+    d->field = src->field;
+    d->prev2_is_prev = src->field == first_field;   // prev2 = field == first ? prev : cur
+    d->next2_is_cur = src->field == first_field;    // next2 = field == first ? cur : next
+    d->algo = params->algo;
+    d->skip_spatial_check = params->skip_spatial_check;
+    d->intra_only = intra_only;
+    d->comp_mask = mask;
+    plb_shader_use_tex(sh, src->cur.top);
+    plb_shader_use_tex(sh, prev);
+    plb_shader_use_tex(sh, next);
+    sh->src = PLB_SRC_DEINT;
+    sh->out_w = tp->w;
+    sh->out_h = tp->h;
+    plb_shader_describe(sh, "deinterlacing");
 }
 
 const struct pl_sigmoid_params pl_sigmoid_default_params = { PL_SIGMOID_DEFAULTS };

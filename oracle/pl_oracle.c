@@ -191,6 +191,152 @@ float orc_tex_linear_r(const struct orc_tex *t, float u, float v)
 }
 
 // ------------------------------------------------------------------------------------------
+// pl_shader_deinterlace — src/shaders/deinterlacing.c:32-370 (weave / bob / yadif / bwdif on
+// interleaved frames). GET(TEX, X, Y) = NEAREST fetch with MIRROR addressing at pos + pt*(X, Y),
+// i.e. texel (x + X, y + Y) reflected at the borders. out: vec4(0,0,0,1) with the masked
+// components replaced. GLSL statement by statement, fp32, no contraction.
+// ------------------------------------------------------------------------------------------
+
+static inline float dget(const struct orc_tex *t, int x, int y, int k)
+{
+    x = wrap_index(x, t->w, 2);
+    y = wrap_index(y, t->h, 2);
+    return k < t->comps ? t->data[((size_t) y * t->w + x) * t->comps + k] : (k == 3 ? 1.0f : 0.0f);
+}
+
+static float yadif_spatial(const float up[7], const float dn[7])
+{
+    const float a = up[0], b = up[1], c = up[2], d = up[3], e = up[4], f = up[5], g = up[6];
+    const float h = dn[0], i = dn[1], j = dn[2], k = dn[3], l = dn[4], m = dn[5], n = dn[6];
+    float spatial_pred = (d + k) / 2.0f;
+    float spatial_score = fabsf(c - j) + fabsf(d - k) + fabsf(e - l) - 0.003922f; // "%f" of 1/255
+    float score = fabsf(b - k) + fabsf(c - l) + fabsf(d - m);
+    if (score < spatial_score) {
+        spatial_pred = (c + l) / 2.0f;
+        spatial_score = score;
+        score = fabsf(a - l) + fabsf(b - m) + fabsf(c - n);
+        if (score < spatial_score) {
+            spatial_pred = (b + m) / 2.0f;
+            spatial_score = score;
+        }
+    }
+    score = fabsf(d - i) + fabsf(e - j) + fabsf(f - k);
+    if (score < spatial_score) {
+        spatial_pred = (e + j) / 2.0f;
+        spatial_score = score;
+        score = fabsf(e - h) + fabsf(f - i) + fabsf(g - j);
+        if (score < spatial_score) {
+            spatial_pred = (f + i) / 2.0f;
+            spatial_score = score;
+        }
+    }
+    return spatial_pred;
+}
+
+void orc_deinterlace(const struct orc_tex *cur, const struct orc_tex *prev_in,
+                     const struct orc_tex *next_in, int field, int first_field, int algo,
+                     int skip_spatial_check, unsigned comp_mask, float *dst)
+{
+    const int w = cur->w, h = cur->h;
+    if (!first_field)
+        first_field = 1;
+    int intra_only = algo != 2;
+    if (algo == 3)
+        intra_only = (!prev_in && field == first_field) || (!next_in && field != first_field);
+    const struct orc_tex *prev = (!intra_only && prev_in) ? prev_in : cur;
+    const struct orc_tex *next = (!intra_only && next_in) ? next_in : cur;
+    const struct orc_tex *prev2 = field == first_field ? prev : cur;
+    const struct orc_tex *next2 = field == first_field ? cur : next;
+    comp_mask = (comp_mask ? comp_mask : 0xFu) & ((1u << cur->comps) - 1u);
+
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            float res[4];
+            const bool keep = field == 0 || (y % 2) == (field == 1 ? 0 : 1) || algo == 0;
+            for (int k = 0; k < 4; k++) {
+                if (keep) {
+                    res[k] = dget(cur, x, y, k);
+                } else if (algo == 1) {
+                    res[k] = dget(cur, x, y + (field == 1 ? -1 : 1), k);
+                } else if (algo == 2) {
+                    float up[7], dn[7];
+                    for (int i = 0; i < 7; i++) {
+                        up[i] = dget(cur, x + i - 3, y - 1, k);
+                        dn[i] = dget(cur, x + i - 3, y + 1, k);
+                    }
+                    float sp = yadif_spatial(up, dn);
+                    const float A = dget(prev, x, y - 1, k), B = dget(prev, x, y + 1, k);
+                    const float C = dget(prev2, x, y - 2, k), D = dget(prev2, x, y, k), E = dget(prev2, x, y + 2, k);
+                    const float F = up[3], G = dn[3];
+                    const float H = dget(next2, x, y - 2, k), I = dget(next2, x, y, k), J = dget(next2, x, y + 2, k);
+                    const float K = dget(next, x, y - 1, k), L = dget(next, x, y + 1, k);
+                    const float p0 = (C + H) / 2.0f, p1 = F, p2 = (D + I) / 2.0f, p3 = G, p4 = (E + J) / 2.0f;
+                    const float tdiff0 = fabsf(D - I) / 2.0f;
+                    const float tdiff1 = (fabsf(A - F) + fabsf(B - G)) / 2.0f;
+                    const float tdiff2 = (fabsf(K - F) + fabsf(G - L)) / 2.0f;
+                    float diff = fmaxf(tdiff0, fmaxf(tdiff1, tdiff2));
+                    if (!skip_spatial_check) {
+                        const float maxi = fmaxf(p2 - fminf(p3, p1), fminf(p0 - p1, p4 - p3));
+                        const float mini = fminf(p2 - fmaxf(p3, p1), fmaxf(p0 - p1, p4 - p3));
+                        diff = fmaxf(diff, fmaxf(mini, -maxi));
+                    }
+                    if (sp > p2 + diff)
+                        sp = p2 + diff;
+                    if (sp < p2 - diff)
+                        sp = p2 - diff;
+                    res[k] = sp;
+                } else {
+                    const float sp0 = 5077.0f / 8192.0f, sp1 = 981.0f / 8192.0f;
+                    const float cu[4] = { dget(cur, x, y - 3, k), dget(cur, x, y - 1, k),
+                                          dget(cur, x, y + 1, k), dget(cur, x, y + 3, k) };
+                    if (intra_only) {
+                        res[k] = sp0 * (cu[1] + cu[2]) - sp1 * (cu[0] + cu[3]);
+                        continue;
+                    }
+                    const float lf0 = 4309.0f / 8192.0f, lf1 = 213.0f / 8192.0f;
+                    const float hf0 = 5570.0f / 8192.0f, hf1 = 3801.0f / 8192.0f, hf2 = 1016.0f / 8192.0f;
+                    const float pv[2] = { dget(prev, x, y - 1, k), dget(prev, x, y + 1, k) };
+                    const float nx[2] = { dget(next, x, y - 1, k), dget(next, x, y + 1, k) };
+                    float p2v[5], n2v[5];
+                    for (int i = 0; i < 5; i++) {
+                        p2v[i] = dget(prev2, x, y + 2 * i - 4, k);
+                        n2v[i] = dget(next2, x, y + 2 * i - 4, k);
+                    }
+                    const float s = p2v[2] + n2v[2];
+                    const float d = s / 2.0f;
+                    const float c = cu[1], e = cu[2];
+                    const float tdiff0 = fabsf(p2v[2] - n2v[2]);
+                    const float tdiff1 = fabsf(pv[0] - c) + fabsf(pv[1] - e);
+                    const float tdiff2 = fabsf(nx[0] - c) + fabsf(nx[1] - e);
+                    float diff = fmaxf(tdiff0, fmaxf(tdiff1, tdiff2)) / 2.0f;
+                    const bool diff_mask = diff == 0.0f;
+                    const float bs = p2v[1] + n2v[1], fs = p2v[3] + n2v[3];
+                    const float b = (bs / 2.0f) - c, f = (fs / 2.0f) - c;
+                    const float dc = d - c, de = d - e;
+                    const float mmax = fmaxf(de, fmaxf(dc, fminf(b, f)));
+                    const float mmin = fminf(de, fminf(dc, fmaxf(b, f)));
+                    diff = fmaxf(diff, fmaxf(mmin, -mmax));
+                    const float single = sp0 * (c + e) - sp1 * (cu[0] + cu[3]);
+                    float all = (hf0 * s - hf1 * (bs + fs) + hf2 * (p2v[0] + n2v[0] + p2v[4] + n2v[4])) / 4.0f;
+                    all += lf0 * (c + e) - lf1 * (cu[0] + cu[3]);
+                    float interpol = fabsf(c - e) > tdiff0 ? all : single;
+                    interpol = fminf(fmaxf(interpol, d - diff), d + diff);
+                    res[k] = diff_mask ? d : interpol;
+                }
+            }
+            float *o = dst + ((size_t) y * w + x) * 4;
+            o[0] = o[1] = o[2] = 0.0f;
+            o[3] = 1.0f;
+            for (int k = 0; k < 4; k++) {
+                if (comp_mask & (1u << k))
+                    o[k] = res[k];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // pl_shader_sample_polar — src/shaders/sampling.c:587-912; per-tap body polar_sample :503-558
 // ------------------------------------------------------------------------------------------
 

@@ -273,6 +273,11 @@ ORC_API void orc_av1_grain(const struct orc_tex *plane, const struct orc_tex *lu
 
 // pl_shader_extract_features (colorspace.c:1383-1404) on linear RGB; m = rgb2lms (float)
 ORC_API void orc_extract_features(float *rgba, size_t npix, const float m[9]);
+// pl_shader_deinterlace (shaders/deinterlacing.c): field 1 top / 2 bottom (0: passthrough), algo
+// 0 weave, 1 bob, 2 yadif, 3 bwdif; prev / next may be NULL; dst: w*h*4 floats
+ORC_API void orc_deinterlace(const struct orc_tex *cur, const struct orc_tex *prev,
+                             const struct orc_tex *next, int field, int first_field, int algo,
+                             int skip_spatial_check, unsigned comp_mask, float *dst);
 // pl_render_image_mix accumulation (renderer.c:3955): acc = fma(w, rgba, acc), all four components
 ORC_API void orc_mix_accumulate(float *acc, const float *rgba, size_t npix, float w);
 // pl_shader_custom_lut (shaders/lut.c:212-280); data = RGB triples (red fastest), size[1] == 0: 1-D

@@ -59,6 +59,9 @@ struct shim_ctx {
     /* planar target of the next shim_render call (shim_set_target_planes) */
     int tgt_nplanes, tgt_chroma_loc;
     pl_tex tgt_planes[3];
+    /* deinterlacing of the next shim_render call (shim_set_deinterlace) */
+    int di_field, di_first, di_algo, di_skip;
+    pl_tex di_prev[3], di_next[3];
     /* frame mix of the next shim_render call (shim_set_mix): further frames around the vsync */
     int mix_n;
     pl_tex mix_planes[8][3];
@@ -501,6 +504,33 @@ API void shim_set_lut(struct shim_ctx *c, int which, int type, const float *data
     }
 }
 
+/* pl_shader_deinterlace as a stand-alone dispatch: prev / next may be NULL */
+API int shim_deinterlace(struct shim_ctx *c, void *cur, void *prev, void *next, void *dst, int field,
+                         int first_field, int algo, int skip_spatial_check, int comp_mask)
+{
+    pl_shader sh = pl_dispatch_begin(c->dp);
+    pl_shader_deinterlace(sh, pl_deinterlace_source(
+        .cur.top = cur, .prev.top = prev, .next.top = next, .field = field,
+        .first_field = first_field, .component_mask = comp_mask,
+    ), pl_deinterlace_params( .algo = algo, .skip_spatial_check = skip_spatial_check ));
+    return pl_dispatch_finish(c->dp, pl_dispatch_params( .shader = &sh, .target = dst )) ? 0 : -1;
+}
+
+/* The next shim_render call treats the image as an interlaced frame showing `field`, with the
+ * given algorithm; prev / next: three plane textures each, or NULL. */
+API void shim_set_deinterlace(struct shim_ctx *c, int field, int first_field, int algo, int skip,
+                              void **prev, void **next)
+{
+    c->di_field = field;
+    c->di_first = first_field;
+    c->di_algo = algo;
+    c->di_skip = skip;
+    for (int k = 0; k < 3; k++) {
+        c->di_prev[k] = prev ? prev[k] : NULL;
+        c->di_next[k] = next ? next[k] : NULL;
+    }
+}
+
 /* The next shim_render call becomes pl_render_image_mix: n frames of three planes each (planes =
  * n * 3 textures; the `planes` argument of shim_render is ignored), their timestamps relative to
  * the vsync, signatures, the vsync duration and the frame mixer ("" = none, i.e. nearest frame;
@@ -672,6 +702,24 @@ API int shim_render(struct shim_ctx *c, int nplanes, void **planes, void *dst, c
     }
     if (opts[7] >= 0)
         pl_renderer_set_frame_index(c->rr, (uint8_t) opts[7]);
+    struct pl_deinterlace_params dipar = { .algo = c->di_algo, .skip_spatial_check = c->di_skip };
+    struct pl_frame di_prev = image, di_next = image;
+    if (c->di_field) {
+        image.field = c->di_field;
+        image.first_field = c->di_first;
+        par.deinterlace_params = &dipar;
+        if (c->di_prev[0]) {
+            for (int k = 0; k < 3; k++)
+                di_prev.planes[k].texture = c->di_prev[k];
+            image.prev = &di_prev;
+        }
+        if (c->di_next[0]) {
+            for (int k = 0; k < 3; k++)
+                di_next.planes[k].texture = c->di_next[k];
+            image.next = &di_next;
+        }
+        c->di_field = 0;
+    }
     bool rendered;
     if (c->mix_n) {
         struct pl_frame frames[8];

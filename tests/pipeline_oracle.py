@@ -144,7 +144,7 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
            allow_delayed=False, dither=0, cmap_hq=False, frame_index=0, peak_state=None,
            coord_mode=T.COORD_EXACT, tone_fn=None, gamut_fn=None, stats=None,
            error_diffusion=None, film_grain=None, contrast_recovery=0.0, contrast_smoothness=3.5,
-           luts=None, _return_color=False, _start_color=None):
+           luts=None, deinterlace=None, _return_color=False, _start_color=None):
     """Returns (output array in target storage type, new peak state). `peak_state` carries the
     smoothed (avg, max) between frames like sh_color_map_obj.peak does.
     luts: {"params": (type, data, size), "image": (...), "target": (...)} with type in
@@ -162,6 +162,18 @@ def render(img, tgt, *, upscaler=None, plane_upscaler=None, deband=False, peak=0
         contrast_recovery = 0.0
     t0, orc = T.t0(), T.oracle()
     Y, U, V = img.planes
+    if deinterlace is not None:
+        # (field, first_field, algo, prev Frame or None, next Frame or None): every plane is
+        # deinterlaced into a texture of its own format (r16) first, renderer.c:1591-1612
+        field, first, algo, pimg, nimg = deinterlace
+        fix = []
+        for i, pl in enumerate((Y, U, V)):
+            f = lambda a: T.unorm16_to_float(a)[:, :, None]
+            o = orc.deinterlace(f(pl), f(pimg.planes[i]) if pimg is not None else None,
+                                f(nimg.planes[i]) if nimg is not None else None,
+                                field=field, first_field=first, algo=algo, comp_mask=1)
+            fix.append(orc.store_unorm(np.ascontiguousarray(o[..., :1]), 16)[..., 0])
+        Y, U, V = fix
     H, W = Y.shape
     ch, cw = U.shape
     plane_up = plane_upscaler or upscaler

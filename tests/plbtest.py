@@ -549,6 +549,18 @@ class Oracle:
         self.lib.orc_extract_features(fp(rgba), C.c_size_t(rgba.size // 4), fp(m))
         return rgba
 
+    def deinterlace(self, cur, prev=None, nxt=None, field=1, first_field=0, algo=3, skip_spatial_check=False,
+                    comp_mask=0):
+        """pl_shader_deinterlace on float textures (h, w, comps); returns (h, w, 4)."""
+        tc, kc = _tex(cur)
+        tp, kp = _tex(prev) if prev is not None else (None, None)
+        tn, kn = _tex(nxt) if nxt is not None else (None, None)
+        out = np.zeros(kc.shape[:2] + (4,), f32)
+        self.lib.orc_deinterlace(C.byref(tc), C.byref(tp) if tp is not None else None,
+                                 C.byref(tn) if tn is not None else None, field, first_field, algo,
+                                 int(skip_spatial_check), comp_mask, fp(out))
+        return out
+
     def mix_accumulate(self, acc, rgba, w):
         acc = np.ascontiguousarray(acc, f32).copy()
         rgba = np.ascontiguousarray(rgba, f32)
