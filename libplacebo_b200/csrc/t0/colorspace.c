@@ -95,30 +95,27 @@ void pl_transform3x3_invert(pl_transform3x3 *t)
 
 // ---- colour systems / representation ----------------------------------------------------------
 
+// Properties of the colour systems as bit sets over enum pl_color_system
+#define SYS_BIT(s) (1u << (s))
+static const unsigned SYS_NOT_YCBCR = SYS_BIT(PL_COLOR_SYSTEM_UNKNOWN) | SYS_BIT(PL_COLOR_SYSTEM_RGB) |
+                                      SYS_BIT(PL_COLOR_SYSTEM_XYZ);
+static const unsigned SYS_NONLINEAR = SYS_BIT(PL_COLOR_SYSTEM_BT_2020_C) | SYS_BIT(PL_COLOR_SYSTEM_BT_2100_PQ) |
+                                      SYS_BIT(PL_COLOR_SYSTEM_BT_2100_HLG) |
+                                      SYS_BIT(PL_COLOR_SYSTEM_DOLBYVISION) | SYS_BIT(PL_COLOR_SYSTEM_XYZ);
+
+static bool sys_in(unsigned set, enum pl_color_system sys)
+{
+    return (unsigned) sys < 32 && (set >> sys & 1u);
+}
+
 bool pl_color_system_is_ycbcr_like(enum pl_color_system sys)
 {
-    switch (sys) {
-    case PL_COLOR_SYSTEM_UNKNOWN:
-    case PL_COLOR_SYSTEM_RGB:
-    case PL_COLOR_SYSTEM_XYZ:
-        return false;
-    default:
-        return true;
-    }
+    return !sys_in(SYS_NOT_YCBCR, sys);
 }
 
 bool pl_color_system_is_linear(enum pl_color_system sys)
 {
-    switch (sys) {
-    case PL_COLOR_SYSTEM_BT_2020_C:
-    case PL_COLOR_SYSTEM_BT_2100_PQ:
-    case PL_COLOR_SYSTEM_BT_2100_HLG:
-    case PL_COLOR_SYSTEM_DOLBYVISION:
-    case PL_COLOR_SYSTEM_XYZ:
-        return false;
-    default:
-        return true;
-    }
+    return !sys_in(SYS_NONLINEAR, sys);
 }
 
 bool pl_color_repr_equal(const struct pl_color_repr *a, const struct pl_color_repr *b)
@@ -130,36 +127,32 @@ bool pl_color_repr_equal(const struct pl_color_repr *a, const struct pl_color_re
 
 enum pl_color_levels pl_color_levels_guess(const struct pl_color_repr *repr)
 {
-    if (repr->sys == PL_COLOR_SYSTEM_DOLBYVISION)
+    const bool full = repr->sys == PL_COLOR_SYSTEM_DOLBYVISION ||
+                      (!repr->levels && !pl_color_system_is_ycbcr_like(repr->sys));
+    if (full)
         return PL_COLOR_LEVELS_FULL;
-    if (repr->levels)
-        return repr->levels;
-    return pl_color_system_is_ycbcr_like(repr->sys) ? PL_COLOR_LEVELS_LIMITED
-                                                    : PL_COLOR_LEVELS_FULL;
+    return repr->levels ? repr->levels : PL_COLOR_LEVELS_LIMITED;
 }
 
-// Factor that brings sampled values to full [0,1] range of the *colour* depth; afterwards the
-// representation is "as if" sampled at full depth with no shift.
+// Factor that brings sampled values to the full [0,1] range of the *colour* depth; afterwards
+// the representation is "as if" sampled at full depth with no shift. Limited range is defined on
+// the bit-shifted integer grid (ratio of powers of two), full range on the code maxima.
 float pl_color_repr_normalize(struct pl_color_repr *repr)
 {
-    struct pl_bit_encoding *bits = &repr->bits;
-    float scale = 1.0;
-    if (bits->bit_shift) {
-        scale /= (1LL << bits->bit_shift);
-        bits->bit_shift = 0;
-    }
-    int tex_bits = PLB_DEF(bits->sample_depth, bits->color_depth);
-    int col_bits = PLB_DEF(bits->color_depth, bits->sample_depth);
-    if (!tex_bits)
-        tex_bits = col_bits = 8;
-    if (pl_color_levels_guess(repr) == PL_COLOR_LEVELS_LIMITED) {
-        // limited range is defined on the bit-shifted integer grid
-        scale *= (float) (1LL << tex_bits) / (1LL << col_bits);
-    } else {
-        scale *= ((1LL << tex_bits) - 1.) / ((1LL << col_bits) - 1.);
-    }
-    bits->color_depth = bits->sample_depth;
-    return scale;
+    struct pl_bit_encoding *const be = &repr->bits;
+    int sample = be->sample_depth ? be->sample_depth : be->color_depth;
+    int color = be->color_depth ? be->color_depth : be->sample_depth;
+    if (!sample)
+        sample = color = 8;
+    const long long smax = 1LL << sample, cmax = 1LL << color;
+    float factor = 1.0;
+    if (be->bit_shift)
+        factor /= (1LL << be->bit_shift);
+    const bool limited = pl_color_levels_guess(repr) == PL_COLOR_LEVELS_LIMITED;
+    factor *= limited ? (float) smax / cmax : (smax - 1.) / (cmax - 1.);
+    be->bit_shift = 0;
+    be->color_depth = be->sample_depth;
+    return factor;
 }
 
 // ---- transfer characteristics ------------------------------------------------------------------
@@ -167,17 +160,22 @@ float pl_color_repr_normalize(struct pl_color_repr *repr)
 static const float PQ_M1 = 2610./4096 * 1./4, PQ_M2 = 2523./4096 * 128, PQ_C1 = 3424./4096,
                    PQ_C2 = 2413./4096 * 32, PQ_C3 = 2392./4096 * 32;
 
+// peak of the transfer function's signal range relative to SDR white
 float pl_color_transfer_nominal_peak(enum pl_color_transfer trc)
 {
-    switch (trc) {
-    case PL_COLOR_TRC_SCRGB:
-    case PL_COLOR_TRC_PQ:     return 10000.0 / PL_COLOR_SDR_WHITE;
-    case PL_COLOR_TRC_HLG:    return 12.0 / 3.17955;
-    case PL_COLOR_TRC_V_LOG:  return 46.0855;
-    case PL_COLOR_TRC_S_LOG1: return 6.52;
-    case PL_COLOR_TRC_S_LOG2: return 9.212;
-    default:                  return 1.0;
+    static const struct { enum pl_color_transfer trc; float peak; } peaks[] = {
+        { PL_COLOR_TRC_PQ,     10000.0 / PL_COLOR_SDR_WHITE },
+        { PL_COLOR_TRC_SCRGB,  10000.0 / PL_COLOR_SDR_WHITE },
+        { PL_COLOR_TRC_HLG,    12.0 / 3.17955 },
+        { PL_COLOR_TRC_V_LOG,  46.0855 },
+        { PL_COLOR_TRC_S_LOG1, 6.52 },
+        { PL_COLOR_TRC_S_LOG2, 9.212 },
+    };
+    for (size_t i = 0; i < PLB_ARRAY_SIZE(peaks); i++) {
+        if (peaks[i].trc == trc)
+            return peaks[i].peak;
     }
+    return 1.0;
 }
 
 float pl_hdr_rescale(enum pl_hdr_scaling from, enum pl_hdr_scaling to, float x)
@@ -307,19 +305,19 @@ bool pl_color_space_is_hdr(const struct pl_color_space *csp)
     return csp->hdr.max_luma > PL_COLOR_SDR_WHITE || pl_color_transfer_is_hdr(csp->transfer);
 }
 
+// Transfer functions whose black point is part of the curve itself (absolute or display-referred
+// definitions); all others are scaled to the display's black level.
 bool pl_color_space_is_black_scaled(const struct pl_color_space *csp)
 {
-    switch (csp->transfer) {
-    case PL_COLOR_TRC_BT_1886:
-    case PL_COLOR_TRC_PQ:
-    case PL_COLOR_TRC_SCRGB:
-    case PL_COLOR_TRC_V_LOG:
-    case PL_COLOR_TRC_S_LOG1:
-    case PL_COLOR_TRC_S_LOG2:
-        return false;
-    default:
-        return true;
+    static const enum pl_color_transfer absolute_black[] = {
+        PL_COLOR_TRC_BT_1886, PL_COLOR_TRC_PQ, PL_COLOR_TRC_SCRGB,
+        PL_COLOR_TRC_V_LOG, PL_COLOR_TRC_S_LOG1, PL_COLOR_TRC_S_LOG2,
+    };
+    for (size_t i = 0; i < PLB_ARRAY_SIZE(absolute_black); i++) {
+        if (absolute_black[i] == csp->transfer)
+            return false;
     }
+    return true;
 }
 
 void pl_color_space_merge(struct pl_color_space *orig, const struct pl_color_space *update)
@@ -335,19 +333,18 @@ bool pl_color_space_equal(const struct pl_color_space *a, const struct pl_color_
            pl_hdr_metadata_equal(&a->hdr, &b->hdr);
 }
 
-static bool wide_gamut(enum pl_color_primaries prim)
+// the narrow (BT.709-class) gamuts; everything else counts as wide when a default is inferred
+static bool narrow_gamut(enum pl_color_primaries prim)
 {
-    switch (prim) {
-    case PL_COLOR_PRIM_UNKNOWN:
-    case PL_COLOR_PRIM_BT_601_525:
-    case PL_COLOR_PRIM_BT_601_625:
-    case PL_COLOR_PRIM_BT_709:
-    case PL_COLOR_PRIM_BT_470M:
-    case PL_COLOR_PRIM_EBU_3213:
-        return false;
-    default:
-        return true;
+    static const enum pl_color_primaries narrow[] = {
+        PL_COLOR_PRIM_UNKNOWN, PL_COLOR_PRIM_BT_601_525, PL_COLOR_PRIM_BT_601_625,
+        PL_COLOR_PRIM_BT_709, PL_COLOR_PRIM_BT_470M, PL_COLOR_PRIM_EBU_3213,
+    };
+    for (size_t i = 0; i < PLB_ARRAY_SIZE(narrow); i++) {
+        if (narrow[i] == prim)
+            return true;
     }
+    return false;
 }
 
 static float clampf(float x, float lo, float hi) { return x < lo ? lo : x > hi ? hi : x; }
@@ -425,48 +422,54 @@ void pl_color_space_nominal_luma_ex(const struct pl_nominal_luma_params *params)
     if (params->out_avg) *params->out_avg = avg;
 }
 
+// Defaults for an under-specified colour space: BT.709 / BT.1886, luminance range from the
+// HDR10 metadata or the transfer function, mastering primaries from the nominal ones.
 void pl_color_space_infer(struct pl_color_space *space)
 {
-    if (!space->primaries) space->primaries = PL_COLOR_PRIM_BT_709;
-    if (!space->transfer)  space->transfer = PL_COLOR_TRC_BT_1886;
-    pl_color_space_nominal_luma_ex(pl_nominal_luma_params(
+    space->primaries = space->primaries ? space->primaries : PL_COLOR_PRIM_BT_709;
+    space->transfer = space->transfer ? space->transfer : PL_COLOR_TRC_BT_1886;
+    struct pl_nominal_luma_params lp = {
         .color = space,
         .metadata = PL_HDR_METADATA_HDR10,
         .scaling = PL_HDR_NITS,
         .out_max = &space->hdr.max_luma,
-        .out_min = space->hdr.min_luma ? NULL : &space->hdr.min_luma,
-    ));
+    };
+    if (!space->hdr.min_luma)
+        lp.out_min = &space->hdr.min_luma;
+    pl_color_space_nominal_luma_ex(&lp);
     if (!pl_primaries_valid(&space->hdr.prim))
         space->hdr.prim = *pl_raw_primaries_get(space->primaries);
+}
+
+// The transfer function an unspecified space takes next to a reference: SDR curves carry
+// over, HDR / camera-log references pair with BT.1886, ProPhoto with sRGB, the rest gamma 2.2
+static enum pl_color_transfer companion_transfer(enum pl_color_transfer ref)
+{
+    static const struct { enum pl_color_transfer ref, companion; } map[] = {
+        { PL_COLOR_TRC_BT_1886,   PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_SRGB,      PL_COLOR_TRC_SRGB },
+        { PL_COLOR_TRC_GAMMA22,   PL_COLOR_TRC_GAMMA22 },
+        { PL_COLOR_TRC_PQ,        PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_HLG,       PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_V_LOG,     PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_S_LOG1,    PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_S_LOG2,    PL_COLOR_TRC_BT_1886 },
+        { PL_COLOR_TRC_PRO_PHOTO, PL_COLOR_TRC_SRGB },
+    };
+    for (size_t i = 0; i < PLB_ARRAY_SIZE(map); i++) {
+        if (map[i].ref == ref)
+            return map[i].companion;
+    }
+    return PL_COLOR_TRC_GAMMA22;
 }
 
 static void infer_both(struct pl_color_space *space, struct pl_color_space *ref)
 {
     pl_color_space_infer(ref);
     if (!space->primaries)
-        space->primaries = wide_gamut(ref->primaries) ? PL_COLOR_PRIM_BT_709 : ref->primaries;
-    if (!space->transfer) {
-        switch (ref->transfer) {
-        case PL_COLOR_TRC_BT_1886:
-        case PL_COLOR_TRC_SRGB:
-        case PL_COLOR_TRC_GAMMA22:
-            space->transfer = ref->transfer;
-            break;
-        case PL_COLOR_TRC_PQ:
-        case PL_COLOR_TRC_HLG:
-        case PL_COLOR_TRC_V_LOG:
-        case PL_COLOR_TRC_S_LOG1:
-        case PL_COLOR_TRC_S_LOG2:
-            space->transfer = PL_COLOR_TRC_BT_1886;
-            break;
-        case PL_COLOR_TRC_PRO_PHOTO:
-            space->transfer = PL_COLOR_TRC_SRGB;
-            break;
-        default:
-            space->transfer = PL_COLOR_TRC_GAMMA22;
-            break;
-        }
-    }
+        space->primaries = narrow_gamut(ref->primaries) ? ref->primaries : PL_COLOR_PRIM_BT_709;
+    if (!space->transfer)
+        space->transfer = companion_transfer(ref->transfer);
     pl_color_space_infer(space);
 }
 
@@ -629,6 +632,8 @@ pl_matrix3x3 pl_get_color_mapping_matrix(const struct pl_raw_primaries *src,
 }
 
 // IPT (Ebner & Fairchild 1998): Hunt-Pointer-Estevez LMS with 4% crosstalk, D65-adapted
+// RGB -> LMS of IPT-PQ-C2: Hunt-Pointer-Estevez cone fundamentals with 4 % crosstalk between the
+// cone responses, adapted from the primaries' white point to D65.
 pl_matrix3x3 pl_ipt_rgb2lms(const struct pl_raw_primaries *prim)
 {
     static const pl_matrix3x3 hpe = {{
@@ -636,18 +641,18 @@ pl_matrix3x3 pl_ipt_rgb2lms(const struct pl_raw_primaries *prim)
         { -0.22630f, 1.16532f,  0.04570f },
         {  0.00000f, 0.00000f,  0.91822f },
     }};
-    const float c = 0.04;
-    pl_matrix3x3 m = {{
-        { 1 - 2*c, c, c },
-        { c, 1 - 2*c, c },
-        { c, c, 1 - 2*c },
-    }};
-    pl_matrix3x3_mul(&m, &hpe);
-    static const struct pl_cie_xy d65 = D65;
-    chromatic_adaptation(prim->white, d65, &m);
-    const pl_matrix3x3 rgb2xyz = pl_get_rgb2xyz_matrix(prim);
-    pl_matrix3x3_mul(&m, &rgb2xyz);
-    return m;
+    const float crosstalk = 0.04;
+    pl_matrix3x3 lms;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++)
+            lms.m[i][j] = i == j ? 1 - 2*crosstalk : crosstalk;
+    }
+    pl_matrix3x3_mul(&lms, &hpe);
+    const struct pl_cie_xy d65 = D65;
+    chromatic_adaptation(prim->white, d65, &lms);
+    const pl_matrix3x3 to_xyz = pl_get_rgb2xyz_matrix(prim);
+    pl_matrix3x3_mul(&lms, &to_xyz);
+    return lms;
 }
 
 pl_matrix3x3 pl_ipt_lms2rgb(const struct pl_raw_primaries *prim)
