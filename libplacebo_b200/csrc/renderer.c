@@ -237,19 +237,16 @@ static enum plane_type detect_plane_type(const struct pl_plane *plane,
     return repr->sys == PL_COLOR_SYSTEM_XYZ ? PLANE_XYZ : PLANE_RGB;
 }
 
+// index of the plane the frame's geometry refers to: the first one carrying luma / RGB / XYZ
 static int frame_ref(const struct pl_frame *frame)
 {
-    for (int i = 0; i < frame->num_planes; i++) {
-        switch (detect_plane_type(&frame->planes[i], &frame->repr)) {
-        case PLANE_RGB:
-        case PLANE_LUMA:
-        case PLANE_XYZ:
-            return i;
-        default:
-            continue;
-        }
+    int ref = 0;
+    for (int i = frame->num_planes - 1; i >= 0; i--) {
+        const enum plane_type t = detect_plane_type(&frame->planes[i], &frame->repr);
+        if (t == PLANE_RGB || t == PLANE_LUMA || t == PLANE_XYZ)
+            ref = i;
     }
-    return 0;
+    return ref;
 }
 
 static enum pl_color_primaries primaries_guess(int width, int height)
@@ -264,28 +261,37 @@ static enum pl_color_primaries primaries_guess(int width, int height)
     }
 }
 
+// Fill in what a caller may leave open (fix_frame, renderer.c:3122-3160): XYZ implies DCI-P3 /
+// ST 428, unknown primaries are guessed from the resolution, alpha only exists if a plane maps
+// it, and UNORM textures define the sample depth (colour depth at most that, rest = shift).
 static void fix_frame(struct pl_frame *frame)
 {
-    pl_tex tex = frame->planes[frame_ref(frame)].texture;
+    const pl_tex ref = frame->planes[frame_ref(frame)].texture;
+    struct pl_color_space *csp = &frame->color;
     if (frame->repr.sys == PL_COLOR_SYSTEM_XYZ) {
-        frame->color.primaries = PL_COLOR_PRIM_DCI_P3;
-        frame->color.transfer = PL_COLOR_TRC_ST428;
+        csp->primaries = PL_COLOR_PRIM_DCI_P3;
+        csp->transfer = PL_COLOR_TRC_ST428;
+    } else if (ref && !csp->primaries) {
+        csp->primaries = primaries_guess(ref->params.w, ref->params.h);
     }
-    if (tex && !frame->color.primaries)
-        frame->color.primaries = primaries_guess(tex->params.w, tex->params.h);
-    bool has_alpha = false;
-    for (int p = 0; p < frame->num_planes; p++)
-        for (int c = 0; c < frame->planes[p].components; c++)
-            has_alpha |= frame->planes[p].component_mapping[c] == PL_CHANNEL_A;
-    if (!has_alpha)
+
+    int alpha_planes = 0;
+    for (int p = 0; p < frame->num_planes; p++) {
+        const struct pl_plane *pl = &frame->planes[p];
+        for (int c = 0; c < pl->components; c++)
+            alpha_planes += pl->component_mapping[c] == PL_CHANNEL_A;
+    }
+    if (!alpha_planes)
         frame->repr.alpha = PL_ALPHA_NONE;
-    struct pl_bit_encoding *bits = &frame->repr.bits;
-    if (!bits->sample_depth && tex && tex->params.format->type == PL_FMT_UNORM) {
-        bits->sample_depth = tex->params.format->component_depth[0];
-        bits->color_depth = PLB_DEF(bits->color_depth, bits->sample_depth);
-        bits->color_depth = PLB_MIN(bits->color_depth, bits->sample_depth);
-        bits->bit_shift += bits->sample_depth - bits->color_depth;
-    }
+
+    struct pl_bit_encoding *be = &frame->repr.bits;
+    if (be->sample_depth || !ref || ref->params.format->type != PL_FMT_UNORM)
+        return;
+    const int depth = ref->params.format->component_depth[0];
+    const int color = be->color_depth ? PLB_MIN(be->color_depth, depth) : depth;
+    be->sample_depth = depth;
+    be->color_depth = color;
+    be->bit_shift += depth - color;
 }
 
 struct pass_state {
@@ -1830,31 +1836,27 @@ bool pl_render_image(pl_renderer rr, const struct pl_frame *pimage,
 // pl_render_image_mix (renderer.c:3477-3508, :3612-4025)
 // ---------------------------------------------------------------------------------------
 
+// the frame on screen at the vsync: the last one whose timestamp is not in the future
 const struct pl_frame *pl_frame_mix_current(const struct pl_frame_mix *mix)
 {
-    const struct pl_frame *cur = NULL;
-    for (int i = 0; i < mix->num_frames; i++) {
-        if (mix->timestamps[i] > 0.0f)
-            break;
-        cur = mix->frames[i];
-    }
-    return cur;
+    int idx = -1;
+    while (idx + 1 < mix->num_frames && !(mix->timestamps[idx + 1] > 0.0f))
+        idx++;
+    return idx < 0 ? NULL : mix->frames[idx];
 }
 
+// the frame closest to the vsync (timestamps are sorted: stop at the first one farther away)
 const struct pl_frame *pl_frame_mix_nearest(const struct pl_frame_mix *mix)
 {
-    if (!mix->num_frames)
+    if (mix->num_frames <= 0)
         return NULL;
-    const struct pl_frame *best = mix->frames[0];
-    float best_dist = fabsf(mix->timestamps[0]);
+    int best = 0;
     for (int i = 1; i < mix->num_frames; i++) {
-        const float dist = fabsf(mix->timestamps[i]);
-        if (dist >= best_dist)
+        if (!(fabsf(mix->timestamps[i]) < fabsf(mix->timestamps[best])))
             break;
-        best = mix->frames[i];
-        best_dist = dist;
+        best = i;
     }
-    return best;
+    return mix->frames[best];
 }
 
 // identity of everything in the parameters that shapes a cached frame (the reference hashes the
@@ -1879,6 +1881,36 @@ static uint64_t params_hash(const struct pl_render_params *p)
 extern float plb_filter_radius_bound(const struct pl_filter_config *c);
 extern bool plb_shader_mix(pl_shader sh, int n, const pl_tex *texs, const float *weights, int w, int h,
                            const struct pl_color_space *lin_csp);
+
+// Contribution of frame `i` to the vsync (renderer.c:3689-3738). mixer == NULL: only the
+// reference image counts (zero-order hold); oversampling: the visible fraction of the vsync
+// interval; any other filter: its value at the frame's timestamp. Returns false for frames
+// that do not take part at all.
+static bool mix_frame_weight(const struct pl_frame_mix *mix, int i, const struct pl_filter_config *mixer,
+                             bool is_ref, float *out)
+{
+    const float vsync = mix->vsync_duration;
+    const float start = mix->timestamps[i];
+    if (!mixer) {
+        *out = 1.0;
+        return is_ref;
+    }
+    if (!mixer->kernel || mixer->kernel == &pl_filter_function_oversample) {
+        const float stop = i + 1 < mix->num_frames ? mix->timestamps[i + 1] : INFINITY;
+        if (start > vsync || stop < 0.0)
+            return false; // no intersection with the vsync interval
+        const float a = PLB_MAX(start, 0.0), b = PLB_MIN(stop, vsync);
+        float w = (b - a) / vsync;
+        if (mixer->kernel && w < mixer->kernel->params[0])
+            w = 0.0; // below the oversampling threshold
+        *out = w;
+        return true;
+    }
+    if (fabsf(start) >= plb_filter_radius_bound(mixer))
+        return false;
+    *out = pl_filter_sample(mixer, start);
+    return true;
+}
 
 bool pl_render_image_mix(pl_renderer rr, const struct pl_frame_mix *images,
                          const struct pl_frame *ptarget, const struct pl_render_params *params)
@@ -1943,29 +1975,10 @@ bool pl_render_image_mix(pl_renderer rr, const struct pl_frame_mix *images,
 retry:
     for (int i = 0; i < images->num_frames; i++) {
         const uint64_t sig = images->signatures[i];
-        float rts = images->timestamps[i];
         const struct pl_frame *img = images->frames[i];
         float weight;
-        if (single_frame) {
-            if (img != refimg)
-                continue; // only the reference image
-            weight = 1.0;
-        } else if (!mixer.kernel || mixer.kernel == &pl_filter_function_oversample) {
-            // visible interval [rts, end] of this frame against the vsync interval
-            float end = i + 1 < images->num_frames ? images->timestamps[i + 1] : INFINITY;
-            if (rts > images->vsync_duration || end < 0.0)
-                continue;
-            rts = PLB_MAX(rts, 0.0);
-            end = PLB_MIN(end, images->vsync_duration);
-            weight = (end - rts) / images->vsync_duration;
-            if (mixer.kernel && weight < mixer.kernel->params[0])
-                weight = 0.0; // culled by the threshold
-        } else {
-            const float radius = plb_filter_radius_bound(&mixer);
-            if (fabsf(rts) >= radius)
-                continue;
-            weight = pl_filter_sample(&mixer, rts);
-        }
+        if (!mix_frame_weight(images, i, single_frame ? NULL : &mixer, img == refimg, &weight))
+            continue;
 
         struct cached_frame *f = NULL;
         for (int j = 0; j < rr->num_frames; j++) {
