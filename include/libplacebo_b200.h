@@ -1302,6 +1302,8 @@ struct pl_frame_mix {
 };
 PL_API const struct pl_frame *pl_frame_mix_current(const struct pl_frame_mix *mix);
 PL_API const struct pl_frame *pl_frame_mix_nearest(const struct pl_frame_mix *mix);
+PL_API void pl_frames_infer_mix(pl_renderer rr, const struct pl_frame_mix *mix,
+                                struct pl_frame *target, struct pl_frame *out_ref);
 PL_API bool pl_render_image_mix(pl_renderer rr, const struct pl_frame_mix *images,
                                 const struct pl_frame *target, const struct pl_render_params *params);
 PL_API void pl_renderer_flush_cache(pl_renderer rr);

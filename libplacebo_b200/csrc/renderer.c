@@ -404,6 +404,19 @@ void pl_frames_infer(pl_renderer rr, struct pl_frame *image, struct pl_frame *ta
     }
 }
 
+// renderer.h:849-854: the same inference for a frame mix, based on the frame nearest to the vsync
+void pl_frames_infer_mix(pl_renderer rr, const struct pl_frame_mix *mix, struct pl_frame *target,
+                         struct pl_frame *out_ref)
+{
+    const struct pl_frame *nearest = mix ? pl_frame_mix_nearest(mix) : NULL;
+    if (!nearest || !target)
+        return; // nothing to infer from (a mix without frames is outside this backend)
+    struct pl_frame image = *nearest;
+    pl_frames_infer(rr, &image, target);
+    if (out_ref)
+        *out_ref = image;
+}
+
 void pl_frame_set_chroma_location(struct pl_frame *frame, enum pl_chroma_location loc)
 {
     pl_tex ref = frame->planes[frame_ref(frame)].texture;
